@@ -1,0 +1,186 @@
+// kernels_optim.cu — parameter initialisation and the fused optimizer sweep.
+//
+// k_optimizer_sweep fuses, in one pass over the parameter vector, what the reference runs as
+// three launches plus a memset per iteration:
+//   cudaMemsetAsync(grid gradients)          TCNN encodings/grid.h:1132
+//   adam_step<__half>                         TCNN optimizers/adam.h:48-118
+//   ExponentialDecay learning-rate schedule   TCNN optimizers/exponential_decay.h:60-71
+//   ema_step_half_precision<__half>           TCNN optimizers/ema.h:62-76,102-136
+// and, for the first n_mlp parameters, the deterministic reduction of the per-CTA MLP weight-
+// gradient partials written by the fused MLP kernel.  Semantics kept exactly: per-parameter
+// step counters, grid parameters whose gradient is exactly zero are skipped by Adam
+// (adam.h:75-79) but still EMA-filtered, L2 regularisation only on MLP weights, fp32 master +
+// fp16 working copy + fp16 EMA (the inference weights).  The gradient is consumed and zeroed in
+// the same pass, so the next iteration's scatter starts from zero without a memset.
+#include "mon_device.cuh"
+#include "mon_kernels.h"
+
+// ---- pcg32 on the device (TCNN dependencies/pcg32/pcg32.h:46-170), for A12 grid init
+struct DevPcg32 {
+    uint64_t state, inc;
+    __device__ uint32_t next_uint() {
+        uint64_t old = state;
+        state = old * 0x5851f42d4c957f2dULL + inc;
+        uint32_t xorshifted = (uint32_t)(((old >> 18u) ^ old) >> 27u);
+        uint32_t rot = (uint32_t)(old >> 59u);
+        return (xorshifted >> rot) | (xorshifted << ((~rot + 1u) & 31));
+    }
+    __device__ float next_float() { return __uint_as_float((next_uint() >> 9) | 0x3f800000u) - 1.0f; }
+    __device__ void advance(uint64_t delta) {
+        uint64_t cur_mult = 0x5851f42d4c957f2dULL, cur_plus = inc, acc_mult = 1u, acc_plus = 0u;
+        while (delta > 0) {
+            if (delta & 1) { acc_mult *= cur_mult; acc_plus = acc_plus * cur_mult + cur_plus; }
+            cur_plus = (cur_mult + 1) * cur_plus;
+            cur_mult *= cur_mult;
+            delta /= 2;
+        }
+        state = acc_mult * state + acc_plus;
+    }
+};
+
+// generate_random_kernel<float, pcg32, 4> + uniform transform (random.h:66-92): thread i copies
+// the generator, advances 4*i, writes out[i + n_threads*j] = val*(upper-lower)+lower (one FMA).
+__global__ void k_init_grid(uint64_t state, uint64_t inc, uint32_t n, uint32_t n_threads, float lower, float range, float* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_threads) return;
+    DevPcg32 r{state, inc};
+    r.advance((uint64_t)i * 4);
+#pragma unroll
+    for (uint32_t j = 0; j < 4; ++j) {
+        const uint32_t idx = i + n_threads * j;
+        if (idx >= n) return;
+        out[idx] = __fmaf_rn(r.next_float(), range, lower);
+    }
+}
+
+__global__ void k_cast_params(uint32_t n, const float* __restrict__ pf, __half* __restrict__ ph) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ph[i] = __float2half_rn(pf[i]);
+}
+
+__device__ __forceinline__ void adam_update(const MonOpt& o, float lr_base, float gradient, uint32_t i, bool is_mlp,
+                                            float* __restrict__ pf, __half* __restrict__ ph, float* __restrict__ m,
+                                            float* __restrict__ v, uint32_t* __restrict__ ps) {
+    const float w = pf[i];
+    if (is_mlp) gradient = __fmaf_rn(o.l2_reg, w, gradient);
+    const float gsq = __fmul_rn(gradient, gradient);
+    const float fm = __fmaf_rn(o.beta1, m[i], __fmul_rn(1.0f - o.beta1, gradient));
+    const float sm = __fmaf_rn(o.beta2, v[i], __fmul_rn(1.0f - o.beta2, gsq));
+    m[i] = fm; v[i] = sm;
+    const uint32_t cs = ps[i] + 1;
+    ps[i] = cs;
+    const float lr = __fmul_rn(lr_base, __fdiv_rn(__fsqrt_rn(1.0f - powf(o.beta2, (float)cs)), 1.0f - powf(o.beta1, (float)cs)));
+    const float eff = fminf(fmaxf(__fdiv_rn(lr, __fadd_rn(__fsqrt_rn(sm), o.eps)), 0.0f), FLT_MAX);
+    const float nw = __fmaf_rn(-eff, fm, w);
+    pf[i] = nw;
+    ph[i] = __float2half_rn(nw);
+}
+
+#define OPT_THREADS 256
+
+__global__ void __launch_bounds__(OPT_THREADS)
+k_optimizer_sweep(MonOpt o, const MonCtrl* __restrict__ ctrl, float* __restrict__ pf, __half* __restrict__ ph,
+                  __half* __restrict__ gh, const float* __restrict__ mlp_partials, float* __restrict__ m,
+                  float* __restrict__ v, uint32_t* __restrict__ ps, __half* __restrict__ ema) {
+    if (ctrl->skip) return;
+    __shared__ float s_lr, s_old, s_new;
+    const uint32_t step = ctrl->step;  // 1-based, already advanced by the batch kernel
+    if (threadIdx.x == 0) {
+        // ExponentialDecay evaluates its condition with the nested step BEFORE Adam increments it
+        float factor = 1.0f;
+        if (step - 1 >= o.decay_start) {
+            const uint32_t n_decays = (step - 1 - o.decay_start) / o.decay_interval + 1;
+            for (uint32_t s = 0; s < n_decays; ++s) factor = __fmul_rn(factor, o.decay_base);
+        }
+        s_lr = __fmul_rn(o.lr, factor);
+        // host code in the reference: float debias from a double pow (ema.h:107-108)
+        s_old = 1.0f - (float)pow((double)o.ema_decay, (double)(step - 1));
+        s_new = 1.0f / (1.0f - (float)pow((double)o.ema_decay, (double)step));
+    }
+    __syncthreads();
+    const float lr_base = s_lr, old_db = s_old, new_db = s_new;
+    // each thread owns 2 consecutive parameters (one half2 gradient word)
+    const uint32_t i2 = (blockIdx.x * OPT_THREADS + threadIdx.x) * 2;
+    if (i2 >= o.n_params) return;
+    __half2* gh2 = reinterpret_cast<__half2*>(gh + i2);
+    float g[2];
+    if (i2 < o.n_mlp) {
+        // sum the per-CTA partials in a fixed order -> bitwise reproducible MLP gradient
+        float s0 = 0.0f, s1 = 0.0f;
+        for (uint32_t c = 0; c < o.n_partials; ++c) {
+            const float2 p = *reinterpret_cast<const float2*>(mlp_partials + (size_t)c * o.n_mlp + i2);
+            s0 = __fadd_rn(s0, p.x); s1 = __fadd_rn(s1, p.y);
+        }
+        // the reference stores weight gradients in fp16 (loss-scaled); keep that rounding point
+        const __half2 gr = __halves2half2(__float2half_rn(s0), __float2half_rn(s1));
+        *gh2 = gr;  // kept (not zeroed) so tests can read the MLP gradient; overwritten every iteration
+        g[0] = __low2float(gr); g[1] = __high2float(gr);
+    } else {
+        const __half2 gr = *gh2;
+        g[0] = __low2float(gr); g[1] = __high2float(gr);
+        if (g[0] != 0.0f || g[1] != 0.0f) *gh2 = __halves2half2(__float2half_rn(0.0f), __float2half_rn(0.0f));
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const uint32_t i = i2 + k;
+        if (i >= o.n_params) break;
+        const bool is_mlp = i < o.n_mlp;
+        const float gradient = __fdiv_rn(g[k], o.loss_scale);
+        if (is_mlp || gradient != 0.0f) adam_update(o, lr_base, gradient, i, is_mlp, pf, ph, m, v, ps);
+        // EMA over all params with the global step (ema.h:62-76)
+        const float e = __half2float(ema[i]);
+        const float w = __half2float(ph[i]);
+        const float f = __fmul_rn(__fmaf_rn(w, 1.0f - o.ema_decay, __fmul_rn(__fmul_rn(e, o.ema_decay), old_db)), new_db);
+        ema[i] = __float2half_rn(f);
+    }
+}
+
+// variant used only by tests to snapshot the loss-scaled gradient before it is consumed
+__global__ void k_snapshot_grad(uint32_t n, uint32_t n_mlp, uint32_t n_partials, const __half* __restrict__ gh,
+                                const float* __restrict__ mlp_partials, float* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (i < n_mlp) {
+        float s = 0.0f;
+        for (uint32_t c = 0; c < n_partials; ++c) s = __fadd_rn(s, mlp_partials[(size_t)c * n_mlp + i]);
+        out[i] = __half2float(__float2half_rn(s));
+    } else {
+        out[i] = __half2float(gh[i]);
+    }
+}
+
+// SumLoss (nerf_model.cu:1231-1253) + the host-side /R (:1650-1658), one CTA, fixed order
+__global__ void k_sum_loss(uint32_t R, const float* __restrict__ loss, MonCtrl* ctrl) {
+    __shared__ float s[1024];
+    float a = 0.0f;
+    for (uint32_t i = threadIdx.x; i < R; i += blockDim.x) a += loss[i];
+    s[threadIdx.x] = a;
+    __syncthreads();
+    for (int step = blockDim.x / 2; step > 0; step >>= 1) {
+        if ((int)threadIdx.x < step) s[threadIdx.x] += s[threadIdx.x + step];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) ctrl->loss_mean = s[0] / (float)R;
+}
+
+void mon_launch_init_grid(uint64_t state, uint64_t inc, uint32_t n, float* out, cudaStream_t st) {
+    const uint32_t n_needed = (n + 3) / 4;
+    const uint32_t blocks = (n_needed + 127) / 128;
+    const uint32_t n_threads = blocks * 128;
+    const float lower = -1e-4f, upper = 1e-4f;
+    k_init_grid<<<blocks, 128, 0, st>>>(state, inc, n, n_threads, lower, upper - lower, out);
+}
+void mon_launch_cast_params(uint32_t n, const float* pf, __half* ph, cudaStream_t st) {
+    k_cast_params<<<(n + 255) / 256, 256, 0, st>>>(n, pf, ph);
+}
+void mon_launch_optimizer(const MonOpt& o, const MonCtrl* ctrl, float* pf, __half* ph, __half* gh, const float* partials,
+                          float* m, float* v, uint32_t* ps, __half* ema, cudaStream_t st) {
+    const uint32_t pairs = (o.n_params + 1) / 2;
+    k_optimizer_sweep<<<(pairs + OPT_THREADS - 1) / OPT_THREADS, OPT_THREADS, 0, st>>>(o, ctrl, pf, ph, gh, partials, m, v, ps, ema);
+}
+void mon_launch_snapshot_grad(uint32_t n, uint32_t n_mlp, uint32_t n_partials, const __half* gh, const float* partials, float* out, cudaStream_t st) {
+    k_snapshot_grad<<<(n + 255) / 256, 256, 0, st>>>(n, n_mlp, n_partials, gh, partials, out);
+}
+void mon_launch_sum_loss(uint32_t R, const float* loss, MonCtrl* ctrl, cudaStream_t st) {
+    k_sum_loss<<<1, 1024, 0, st>>>(R, loss, ctrl);
+}

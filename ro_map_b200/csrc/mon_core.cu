@@ -1,0 +1,1071 @@
+// mon_core.cu — host side of libmon_b200.so: the C ABI declared in include/mon_c.h.
+//
+// Reference counterparts (MON = /root/reference/dependencies/Multi-Object-NeRF):
+//   NeRF_Dataset                MON/Core/src/nerf_data.cu:123-353   -> mon_dataset_*
+//   NeRF_Model ctor/ResetNetwork/AllocateBatchWorkspace
+//                               MON/Core/src/nerf_model.cu:1259-1427 -> mon_object_create
+//   UpdateFrameIdAndBbox[Online]  :1609-1628                        -> mon_object_{set,add}_bboxes
+//   Train_Step / Train_Step_Online :1630-1699                       -> mon_object_train*
+//   Render                        :1702-1830                        -> mon_object_render
+//   GetDensityOnGrid              :2007-2043                        -> mon_object_density_grid
+//
+// One training iteration is five kernels (batch, encode, fused MLP+render+loss+backward,
+// gradient scatter, optimizer sweep) + a loss reduction, captured once as a CUDA graph and
+// replayed; the reference issues ~25 launches, 3 cuRAND host calls and 3 blocking stream
+// synchronisations per iteration.  There is no CPU fallback anywhere in this
+// file: without a CUDA device every compute entry point returns MON_ERR_NO_DEVICE / MON_ERR_CUDA.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <mutex>
+#include <random>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "mon_json.h"
+#include "mon_kernels.h"
+
+#define MON_GRAPH_CHUNK 10   // iterations captured per replayed graph (plus a 1-iteration graph for remainders)
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) return fail(MON_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ---- pcg32 on the host (TCNN dependencies/pcg32/pcg32.h:46-170), used for the A12 MLP init
+namespace {
+struct HostPcg32 {
+    uint64_t state, inc;
+    explicit HostPcg32(uint64_t initstate, uint64_t initseq = 1u) {
+        state = 0U;
+        inc = (initseq << 1u) | 1u;
+        next_uint();
+        state += initstate;
+        next_uint();
+    }
+    uint32_t next_uint() {
+        const uint64_t old = state;
+        state = old * 0x5851f42d4c957f2dULL + inc;
+        const uint32_t xs = (uint32_t)(((old >> 18u) ^ old) >> 27u);
+        const uint32_t rot = (uint32_t)(old >> 59u);
+        return (xs >> rot) | (xs << ((~rot + 1u) & 31));
+    }
+    float next_float() {
+        union { uint32_t u; float f; } x;
+        x.u = (next_uint() >> 9) | 0x3f800000u;
+        return x.f - 1.0f;
+    }
+    void advance(uint64_t delta) {
+        uint64_t cur_mult = 0x5851f42d4c957f2dULL, cur_plus = inc, acc_mult = 1u, acc_plus = 0u;
+        while (delta > 0) {
+            if (delta & 1) { acc_mult *= cur_mult; acc_plus = acc_plus * cur_mult + cur_plus; }
+            cur_plus = (cur_mult + 1) * cur_plus;
+            cur_mult *= cur_mult;
+            delta /= 2;
+        }
+        state = acc_mult * state + acc_plus;
+    }
+};
+
+uint32_t next_multiple(uint32_t v, uint32_t d) { return ((v + d - 1) / d) * d; }
+
+// per-level table geometry, GridEncodingTemplated ctor (TCNN encodings/grid.h:964-997) and
+// grid_scale/grid_resolution (:195-204)
+bool make_grid(const mon_config& c, MonGrid& g, std::string& why) {
+    if (c.n_levels == 0 || c.n_levels > MON_MAX_LEVELS) { why = "n_levels must be in 1..16"; return false; }
+    if (c.n_features_per_level != 2) { why = "only n_features_per_level == 2 is supported"; return false; }
+    if (c.log2_hashmap_size < 3 || c.log2_hashmap_size > 28) { why = "log2_hashmap_size out of range"; return false; }
+    memset(&g, 0, sizeof(g));
+    g.n_levels = c.n_levels;
+    const float log2_pls = std::log2(c.per_level_scale);
+    uint32_t offset = 0;
+    for (uint32_t i = 0; i < c.n_levels; ++i) {
+        const float scale = exp2f((float)i * log2_pls) * (float)c.base_resolution - 1.0f;
+        const uint32_t res = (uint32_t)ceilf(scale) + 1;
+        const uint32_t max_params = UINT32_MAX / 2;
+        uint32_t n = std::pow((float)res, 3) > (float)max_params ? max_params : res * res * res;
+        n = next_multiple(n, 8u);
+        n = std::min(n, 1u << c.log2_hashmap_size);
+        // grid_index(): the dense formula is used iff the running stride never exceeds the table
+        uint64_t stride = 1;
+        for (int d = 0; d < 3 && stride <= n; ++d) stride *= res;
+        g.offset[i] = offset;
+        g.size[i] = n;
+        g.res[i] = res;
+        g.scale[i] = scale;
+        g.hashed[i] = (n < stride) ? 1u : 0u;
+        offset += n;
+    }
+    g.offset[c.n_levels] = offset;
+    return true;
+}
+
+uint32_t n_mlp_params(const mon_config& c) {
+    const uint32_t in_w = c.n_levels * c.n_features_per_level;
+    return c.n_neurons * in_w + (c.n_hidden_layers - 1) * c.n_neurons * c.n_neurons + MON_OUT * c.n_neurons;
+}
+
+bool validate_config(const mon_config& c, std::string& why) {
+    if (c.n_levels * c.n_features_per_level != MON_IN) { why = "encoding width must be 32 (n_levels*n_features_per_level)"; return false; }
+    if (c.n_neurons != MON_WIDTH) { why = "only n_neurons == 64 is supported"; return false; }
+    if (c.n_hidden_layers < 1 || c.n_hidden_layers > 2) { why = "n_hidden_layers must be 1 or 2"; return false; }
+    if (c.samples_per_ray != MON_S) { why = "samples_per_ray must be 32"; return false; }
+    if (c.rays_per_batch == 0 || c.rays_per_batch % 4 != 0) { why = "rays_per_batch must be a positive multiple of 4"; return false; }
+    if (c.render_samples_per_ray == 0 || c.render_samples_per_ray % 32 != 0) { why = "render_samples_per_ray must be a multiple of 32"; return false; }
+    return true;
+}
+}  // namespace
+
+// =========================================================================================
+struct mon_dataset {
+    int gpu = 0;
+    float K[4];
+    int H = 0, W = 0;
+    uint32_t max_frames = 0;
+    int use_depth = 0;
+    uint32_t n_frames = 0;
+    MonFrame* d_frames = nullptr;
+    std::vector<MonFrame> h_frames;
+    cudaStream_t stream = nullptr;
+    uint8_t* staging = nullptr;  // pinned: rgb | instance | depth
+    std::mutex mu;
+};
+
+struct mon_object {
+    mon_dataset* ds = nullptr;
+    mon_config cfg;
+    MonGrid grid;
+    MonScene scene;
+    MonOpt opt;
+    MonLossCfg lc;
+    uint32_t seed = 1337;
+    uint32_t n_mlp = 0, n_grid = 0, P = 0, R = 0, N = 0;
+    // parameters + optimizer state
+    float *pf = nullptr, *m = nullptr, *v = nullptr;
+    __half *ph = nullptr, *gh = nullptr, *ema = nullptr;
+    uint32_t* ps = nullptr;
+    // control
+    MonCtrl* ctrl = nullptr;
+    MonCtrl* h_ctrl = nullptr;  // pinned
+    mon_bbox2d* d_boxes = nullptr;
+    uint32_t box_cap = 0;
+    std::vector<mon_bbox2d> h_boxes;
+    // batch buffers
+    MonRay* rays = nullptr;
+    uint8_t* ray_inst = nullptr;
+    float *target = nullptr, *target_depth = nullptr, *bg = nullptr;
+    float *rgb_rays = nullptr, *depth_rays = nullptr, *mask_rays = nullptr, *loss = nullptr;
+    __half *enc = nullptr, *d_enc = nullptr;
+    float* partials = nullptr;
+    uint32_t n_ctas = 0;
+    // parity hooks (lazily allocated)
+    float *dbg_out = nullptr, *dbg_dout = nullptr, *inj_xy = nullptr, *inj_col = nullptr, *inj_dt = nullptr, *grad_snap = nullptr;
+    bool have_injected = false;
+    // render workspace (lazily allocated)
+    MonRay* r_rays = nullptr; int* r_inbox = nullptr; __half* r_enc = nullptr; float* r_jit = nullptr;
+    float *r_rgb = nullptr, *r_depth = nullptr, *r_mask = nullptr, *r_Twc = nullptr;
+    uint32_t r_cap_rays = 0, r_tile = 0; size_t r_jit_cap = 0;
+    uint32_t render_count = 0;
+    // execution
+    cudaStream_t stream = nullptr;
+    cudaGraphExec_t graph1 = nullptr, graphN = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timing_pending = false;
+    float last_ms = 0.0f;
+    uint64_t launches = 0;
+    int mlp_impl = 1;
+    int sm_count = 148;
+};
+
+// =========================================================================================
+extern "C" {
+
+const char* mon_last_error(void) { return g_err.c_str(); }
+const char* mon_version(void) { return "mon-b200 0.1 (sm_100a)"; }
+
+int mon_device_count(int* count) {
+    if (!count) return fail(MON_ERR_ARG, "count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *count = 0; cudaGetLastError(); return fail(MON_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+    *count = n;
+    return MON_OK;
+}
+
+int mon_config_default(mon_config* c) {
+    if (!c) return fail(MON_ERR_ARG, "cfg is NULL");
+    memset(c, 0, sizeof(*c));
+    c->n_levels = 16; c->n_features_per_level = 2; c->log2_hashmap_size = 16; c->base_resolution = 16;
+    c->per_level_scale = 2.0f;
+    c->n_neurons = 64; c->n_hidden_layers = 1;
+    c->learning_rate = 1e-2f; c->beta1 = 0.9f; c->beta2 = 0.99f; c->epsilon = 1e-15f; c->l2_reg = 1e-6f;
+    c->ema_decay = 0.95f; c->decay_start = 20000; c->decay_interval = 10000; c->decay_base = 0.33f;
+    c->loss_scale = 128.0f;
+    c->rays_per_batch = 4096; c->samples_per_ray = 32; c->render_samples_per_ray = 64;
+    c->depth_lambda = 0.5f; c->mask_lambda = 0.5f; c->bg_density_reg = 0.01f;
+    return MON_OK;
+}
+
+int mon_config_from_json(const char* path, mon_config* c) {
+    if (!path || !c) return fail(MON_ERR_ARG, "NULL argument");
+    std::ifstream f(path);
+    if (!f) return fail(MON_ERR_IO, "cannot open network config '%s'", path);
+    std::stringstream ss;
+    ss << f.rdbuf();
+    const std::string text = ss.str();
+    monjson::Value root;
+    std::string err;
+    monjson::Parser p(text);
+    if (!p.parse(root, err)) return fail(MON_ERR_IO, "JSON error in '%s': %s", path, err.c_str());
+    mon_config_default(c);
+    // defaults of the keys follow ResetNetwork (nerf_model.cu:1299-1302) and tcnn's own
+    // defaults (grid.h:1419-1440; adam.h / ema.h / exponential_decay.h update_hyperparams)
+    if (const monjson::Value* e = root.find("encoding")) {
+        const std::string otype = e->string_or("otype", "HashGrid");
+        if (otype != "HashGrid" && otype != "Grid") return fail(MON_ERR_IO, "encoding.otype '%s' is not supported (HashGrid only)", otype.c_str());
+        c->n_levels = (uint32_t)e->number_or("n_levels", 16);
+        c->n_features_per_level = (uint32_t)e->number_or("n_features_per_level", 2);
+        c->log2_hashmap_size = (uint32_t)e->number_or("log2_hashmap_size", 19);
+        c->base_resolution = (uint32_t)e->number_or("base_resolution", 16);
+        c->per_level_scale = (float)e->number_or("per_level_scale", 2.0);
+    }
+    if (const monjson::Value* n = root.find("network")) {
+        const std::string otype = n->string_or("otype", "FullyFusedMLP");
+        if (otype != "FullyFusedMLP" && otype != "MegakernelMLP") return fail(MON_ERR_IO, "network.otype '%s' is not supported", otype.c_str());
+        const std::string act = n->string_or("activation", "ReLU");
+        if (act != "ReLU") return fail(MON_ERR_IO, "network.activation '%s' is not supported (ReLU only)", act.c_str());
+        const std::string oact = n->string_or("output_activation", "None");
+        if (oact != "None") return fail(MON_ERR_IO, "network.output_activation '%s' is not supported (None only)", oact.c_str());
+        c->n_neurons = (uint32_t)n->number_or("n_neurons", 128);
+        c->n_hidden_layers = (uint32_t)n->number_or("n_hidden_layers", 5);
+    }
+    // optimizer chain: walk "nested" and pick the keys by otype
+    const monjson::Value* o = root.find("optimizer");
+    bool saw_adam = false;
+    c->decay_start = 0xffffffffu;  // no ExponentialDecay in the chain -> never decays
+    while (o) {
+        const std::string otype = o->string_or("otype", "");
+        if (otype == "Ema") {
+            c->ema_decay = (float)o->number_or("decay", 0.99);
+        } else if (otype == "ExponentialDecay") {
+            c->decay_start = (uint32_t)o->number_or("decay_start", 0);
+            c->decay_interval = (uint32_t)o->number_or("decay_interval", 1);
+            c->decay_base = (float)o->number_or("decay_base", 0.33);
+        } else if (otype == "Adam") {
+            saw_adam = true;
+            c->learning_rate = (float)o->number_or("learning_rate", 1e-3);
+            c->beta1 = (float)o->number_or("beta1", 0.9);
+            c->beta2 = (float)o->number_or("beta2", 0.999);
+            c->epsilon = (float)o->number_or("epsilon", 1e-8);
+            c->l2_reg = (float)o->number_or("l2_reg", 1e-8);
+        } else {
+            return fail(MON_ERR_IO, "optimizer.otype '%s' is not supported (Ema / ExponentialDecay / Adam)", otype.c_str());
+        }
+        o = o->find("nested");
+    }
+    if (!saw_adam) return fail(MON_ERR_IO, "optimizer chain has no Adam");
+    if (c->decay_interval == 0) c->decay_interval = 1;
+    std::string why;
+    MonGrid g;
+    if (!validate_config(*c, why) || !make_grid(*c, g, why)) return fail(MON_ERR_IO, "unsupported network config: %s", why.c_str());
+    return MON_OK;
+}
+
+int mon_config_param_counts(const mon_config* c, uint32_t* n_mlp, uint32_t* n_grid) {
+    if (!c) return fail(MON_ERR_ARG, "cfg is NULL");
+    MonGrid g; std::string why;
+    if (!validate_config(*c, why) || !make_grid(*c, g, why)) return fail(MON_ERR_ARG, "%s", why.c_str());
+    if (n_mlp) *n_mlp = n_mlp_params(*c);
+    if (n_grid) *n_grid = g.offset[c->n_levels] * 2;
+    return MON_OK;
+}
+
+int mon_config_grid_layout(const mon_config* c, uint32_t* offsets, float* scales, uint32_t* resolutions) {
+    if (!c) return fail(MON_ERR_ARG, "cfg is NULL");
+    MonGrid g; std::string why;
+    if (!make_grid(*c, g, why)) return fail(MON_ERR_ARG, "%s", why.c_str());
+    for (uint32_t i = 0; i <= c->n_levels; ++i) if (offsets) offsets[i] = g.offset[i];
+    for (uint32_t i = 0; i < c->n_levels; ++i) { if (scales) scales[i] = g.scale[i]; if (resolutions) resolutions[i] = g.res[i]; }
+    return MON_OK;
+}
+
+// ------------------------------------------------------------------------------- dataset
+int mon_dataset_create(int gpu, float fx, float fy, float cx, float cy, int H, int W,
+                       uint32_t max_frames, int use_depth, mon_dataset** out) {
+    if (!out) return fail(MON_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (H <= 0 || W <= 0 || max_frames == 0) return fail(MON_ERR_ARG, "invalid image size or max_frames");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return fail(MON_ERR_NO_DEVICE, "no CUDA device (this library has no CPU path)"); }
+    if (gpu < 0 || gpu >= n) return fail(MON_ERR_ARG, "gpu %d out of range (0..%d)", gpu, n - 1);
+    CK(cudaSetDevice(gpu));
+    mon_dataset* ds = new mon_dataset();
+    ds->gpu = gpu; ds->K[0] = fx; ds->K[1] = fy; ds->K[2] = cx; ds->K[3] = cy;
+    ds->H = H; ds->W = W; ds->max_frames = max_frames; ds->use_depth = use_depth;
+    ds->h_frames.assign(max_frames, MonFrame{nullptr, nullptr, nullptr, {0}});
+    const size_t px = (size_t)H * W;
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&ds->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaMalloc(&ds->d_frames, sizeof(MonFrame) * max_frames)) != cudaSuccess ||
+        (e = cudaMemset(ds->d_frames, 0, sizeof(MonFrame) * max_frames)) != cudaSuccess ||
+        (e = cudaMallocHost(&ds->staging, px * 3 + px + px * 4)) != cudaSuccess) {
+        mon_dataset_destroy(ds);
+        return fail(MON_ERR_CUDA, "dataset allocation: %s", cudaGetErrorString(e));
+    }
+    *out = ds;
+    return MON_OK;
+}
+
+int mon_dataset_add_frame(mon_dataset* ds, uint32_t frame_id, const uint8_t* rgb, int is_bgr,
+                          const uint8_t* instance, const float* depth, const float pose[16]) {
+    if (!ds || !rgb || !instance || !pose) return fail(MON_ERR_ARG, "NULL argument");
+    if (frame_id >= ds->max_frames) return fail(MON_ERR_ARG, "frame_id %u >= max_frames %u", frame_id, ds->max_frames);
+    if (ds->use_depth && !depth) return fail(MON_ERR_ARG, "dataset was created with use_depth but depth is NULL");
+    std::lock_guard<std::mutex> lock(ds->mu);
+    CK(cudaSetDevice(ds->gpu));
+    const size_t px = (size_t)ds->H * ds->W;
+    MonFrame& f = ds->h_frames[frame_id];
+    if (!f.rgb) {
+        uint8_t* p = nullptr;
+        CK(cudaMalloc(&p, px * 3)); f.rgb = p;
+        CK(cudaMalloc(&p, px)); f.instance = p;
+        if (ds->use_depth) { float* d = nullptr; CK(cudaMalloc(&d, px * 4)); f.depth = d; }
+    }
+    uint8_t* st_rgb = ds->staging;
+    uint8_t* st_inst = ds->staging + px * 3;
+    float* st_depth = reinterpret_cast<float*>(ds->staging + px * 4);
+    if (is_bgr) {  // cv::cvtColor(BGR2RGB) of the reference (nerf_data.cu:286)
+        for (size_t i = 0; i < px; ++i) { st_rgb[3 * i] = rgb[3 * i + 2]; st_rgb[3 * i + 1] = rgb[3 * i + 1]; st_rgb[3 * i + 2] = rgb[3 * i]; }
+    } else {
+        memcpy(st_rgb, rgb, px * 3);
+    }
+    memcpy(st_inst, instance, px);
+    CK(cudaMemcpyAsync(const_cast<uint8_t*>(f.rgb), st_rgb, px * 3, cudaMemcpyHostToDevice, ds->stream));
+    CK(cudaMemcpyAsync(const_cast<uint8_t*>(f.instance), st_inst, px, cudaMemcpyHostToDevice, ds->stream));
+    if (ds->use_depth) {
+        memcpy(st_depth, depth, px * 4);
+        CK(cudaMemcpyAsync(const_cast<float*>(f.depth), st_depth, px * 4, cudaMemcpyHostToDevice, ds->stream));
+    }
+    memcpy(f.pose, pose, sizeof(float) * 16);
+    CK(cudaMemcpyAsync(ds->d_frames + frame_id, &f, sizeof(MonFrame), cudaMemcpyHostToDevice, ds->stream));
+    CK(cudaStreamSynchronize(ds->stream));
+    ds->n_frames = std::max(ds->n_frames, frame_id + 1);
+    return MON_OK;
+}
+
+int mon_dataset_update_poses(mon_dataset* ds, uint32_t first_frame, uint32_t n, const float* poses16) {
+    if (!ds || !poses16) return fail(MON_ERR_ARG, "NULL argument");
+    if ((uint64_t)first_frame + n > ds->max_frames) return fail(MON_ERR_ARG, "pose range out of bounds");
+    std::lock_guard<std::mutex> lock(ds->mu);
+    CK(cudaSetDevice(ds->gpu));
+    for (uint32_t i = 0; i < n; ++i) {
+        MonFrame& f = ds->h_frames[first_frame + i];
+        memcpy(f.pose, poses16 + (size_t)i * 16, sizeof(float) * 16);
+        CK(cudaMemcpyAsync(ds->d_frames + first_frame + i, &f, sizeof(MonFrame), cudaMemcpyHostToDevice, ds->stream));
+    }
+    CK(cudaStreamSynchronize(ds->stream));
+    return MON_OK;
+}
+
+int mon_dataset_frame_count(const mon_dataset* ds, uint32_t* n) {
+    if (!ds || !n) return fail(MON_ERR_ARG, "NULL argument");
+    *n = ds->n_frames;
+    return MON_OK;
+}
+
+int mon_dataset_clone_from_peer(mon_dataset* dst, const mon_dataset* src) {
+    if (!dst || !src) return fail(MON_ERR_ARG, "NULL argument");
+    if (dst->H != src->H || dst->W != src->W || dst->max_frames < src->n_frames || dst->use_depth != src->use_depth)
+        return fail(MON_ERR_ARG, "datasets are not shape-compatible");
+    std::lock_guard<std::mutex> lock(dst->mu);
+    CK(cudaSetDevice(dst->gpu));
+    if (dst->gpu != src->gpu) {
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, dst->gpu, src->gpu));
+        if (can) { cudaError_t e = cudaDeviceEnablePeerAccess(src->gpu, 0); if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e); cudaGetLastError(); }
+    }
+    const size_t px = (size_t)dst->H * dst->W;
+    for (uint32_t i = 0; i < src->n_frames; ++i) {
+        const MonFrame& s = src->h_frames[i];
+        if (!s.rgb) continue;
+        MonFrame& f = dst->h_frames[i];
+        if (!f.rgb) {
+            uint8_t* p = nullptr;
+            CK(cudaMalloc(&p, px * 3)); f.rgb = p;
+            CK(cudaMalloc(&p, px)); f.instance = p;
+            if (dst->use_depth) { float* d = nullptr; CK(cudaMalloc(&d, px * 4)); f.depth = d; }
+        }
+        CK(cudaMemcpyPeerAsync(const_cast<uint8_t*>(f.rgb), dst->gpu, s.rgb, src->gpu, px * 3, dst->stream));
+        CK(cudaMemcpyPeerAsync(const_cast<uint8_t*>(f.instance), dst->gpu, s.instance, src->gpu, px, dst->stream));
+        if (dst->use_depth) CK(cudaMemcpyPeerAsync(const_cast<float*>(f.depth), dst->gpu, s.depth, src->gpu, px * 4, dst->stream));
+        memcpy(f.pose, s.pose, sizeof(float) * 16);
+        CK(cudaMemcpyAsync(dst->d_frames + i, &f, sizeof(MonFrame), cudaMemcpyHostToDevice, dst->stream));
+    }
+    CK(cudaStreamSynchronize(dst->stream));
+    dst->n_frames = std::max(dst->n_frames, src->n_frames);
+    return MON_OK;
+}
+
+int mon_dataset_destroy(mon_dataset* ds) {
+    if (!ds) return MON_OK;
+    cudaSetDevice(ds->gpu);
+    for (auto& f : ds->h_frames) {
+        if (f.rgb) cudaFree(const_cast<uint8_t*>(f.rgb));
+        if (f.instance) cudaFree(const_cast<uint8_t*>(f.instance));
+        if (f.depth) cudaFree(const_cast<float*>(f.depth));
+    }
+    if (ds->d_frames) cudaFree(ds->d_frames);
+    if (ds->staging) cudaFreeHost(ds->staging);
+    if (ds->stream) cudaStreamDestroy(ds->stream);
+    delete ds;
+    return MON_OK;
+}
+
+// ------------------------------------------------------------------------------- object
+static void drop_graphs(mon_object* o) {
+    if (o->graph1) { cudaGraphExecDestroy(o->graph1); o->graph1 = nullptr; }
+    if (o->graphN) { cudaGraphExecDestroy(o->graphN); o->graphN = nullptr; }
+}
+
+static MonBatch make_batch(mon_object* o, bool injected, bool debug) {
+    MonBatch b;
+    memset(&b, 0, sizeof(b));
+    b.R = o->R;
+    b.boxes = o->d_boxes;
+    b.frames = o->ds->d_frames;
+    b.ctrl = o->ctrl;
+    b.seed = o->seed;
+    if (injected) { b.inj_xy = o->inj_xy; b.inj_col = o->inj_col; b.inj_dt = o->inj_dt; }
+    b.rays = o->rays; b.ray_inst = o->ray_inst; b.target = o->target; b.target_depth = o->target_depth; b.bg = o->bg;
+    b.rgb_rays = o->rgb_rays; b.depth_rays = o->depth_rays; b.mask_rays = o->mask_rays; b.loss = o->loss;
+    b.enc = o->enc; b.d_enc = o->d_enc;
+    if (debug) { b.dbg_out = o->dbg_out; b.dbg_dout = o->dbg_dout; }
+    b.params = o->ph; b.grads = o->gh; b.mlp_partials = o->partials;
+    return b;
+}
+
+// the kernels of ONE training iteration, in stream order; returns the number launched.
+// ev (optional, MON_N_STAGES+1 events): recorded before each stage and after the last one.
+static int enqueue_iteration(mon_object* o, const MonBatch& b, bool snapshot_grad, int* n_launched, cudaEvent_t* ev = nullptr) {
+    cudaStream_t st = o->stream;
+    int n = 0;
+    if (ev) CK(cudaEventRecord(ev[0], st));
+    mon_launch_generate_batch(b, o->scene, st); ++n;
+    if (ev) CK(cudaEventRecord(ev[1], st));
+    mon_launch_encode_forward(o->grid, o->N, MON_S, o->rays, nullptr, b.inj_dt, o->seed, o->ctrl, 2, 0,
+                              o->scene.bmin, o->scene.bmax, o->ph + o->n_mlp, o->enc, st); ++n;
+    if (ev) CK(cudaEventRecord(ev[2], st));
+    cudaError_t e;
+#ifdef MON_HAVE_TC
+    if (o->mlp_impl == 0) e = mon_launch_mlp_train_tc(b, o->lc, o->cfg.n_hidden_layers, o->n_mlp, o->n_ctas, st);
+    else
+#endif
+    e = mon_launch_mlp_train_wmma(b, o->lc, o->n_mlp, o->n_ctas, st);
+    if (e != cudaSuccess) return fail(MON_ERR_CUDA, "fused MLP launch: %s", cudaGetErrorString(e));
+    ++n;
+    if (ev) CK(cudaEventRecord(ev[3], st));
+    mon_launch_encode_backward(o->grid, o->N, MON_S, o->rays, b.inj_dt, o->seed, o->ctrl,
+                               o->scene.bmin, o->scene.bmax, o->d_enc, o->gh + o->n_mlp, st); ++n;
+    if (snapshot_grad) { mon_launch_snapshot_grad(o->P, o->n_mlp, o->opt.n_partials, o->gh, o->partials, o->grad_snap, st); ++n; }
+    if (ev) CK(cudaEventRecord(ev[4], st));
+    mon_launch_optimizer(o->opt, o->ctrl, o->pf, o->ph, o->gh, o->partials, o->m, o->v, o->ps, o->ema, st); ++n;
+    if (ev) CK(cudaEventRecord(ev[5], st));
+    mon_launch_sum_loss(o->R, o->loss, o->ctrl, st); ++n;
+    if (ev) CK(cudaEventRecord(ev[6], st));
+    CK(cudaGetLastError());
+    if (n_launched) *n_launched = n;
+    return MON_OK;
+}
+
+static int capture_graph(mon_object* o, int iters, cudaGraphExec_t* out) {
+    const MonBatch b = make_batch(o, false, false);
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamBeginCapture(o->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = MON_OK;
+    for (int i = 0; i < iters && rc == MON_OK; ++i) rc = enqueue_iteration(o, b, false, nullptr);
+    cudaError_t e = cudaStreamEndCapture(o->stream, &g);
+    if (rc != MON_OK) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) return fail(MON_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(out, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(MON_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    return MON_OK;
+}
+
+static const int kKernelsPerIter = 6;
+
+int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uint8_t instance_id,
+                      const float obj_Tow[16], const float bmin[3], const float bmax[3], mon_object** out) {
+    if (!out) return fail(MON_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (!ds || !cfg || !obj_Tow || !bmin || !bmax) return fail(MON_ERR_ARG, "NULL argument");
+    std::string why;
+    MonGrid grid;
+    if (!validate_config(*cfg, why) || !make_grid(*cfg, grid, why)) return fail(MON_ERR_ARG, "unsupported config: %s", why.c_str());
+    for (int k = 0; k < 3; ++k) if (!(bmax[k] > bmin[k])) return fail(MON_ERR_ARG, "empty bounding box");
+    CK(cudaSetDevice(ds->gpu));
+    mon_object* o = new mon_object();
+    o->ds = ds; o->cfg = *cfg; o->grid = grid; o->seed = seed;
+#ifdef MON_HAVE_TC
+    o->mlp_impl = 0;
+#else
+    o->mlp_impl = 1;
+    if (cfg->n_hidden_layers != 1) { delete o; return fail(MON_ERR_STATE, "n_hidden_layers > 1 needs the tcgen05 MLP kernel, which this build lacks"); }
+#endif
+    o->n_mlp = n_mlp_params(*cfg);
+    o->n_grid = grid.offset[cfg->n_levels] * 2;
+    o->P = o->n_mlp + o->n_grid;
+    o->R = cfg->rays_per_batch;
+    o->N = o->R * MON_S;
+    memcpy(o->scene.Tow, obj_Tow, 64);
+    memcpy(o->scene.bmin, bmin, 12); memcpy(o->scene.bmax, bmax, 12);
+    memcpy(o->scene.K, ds->K, 16);
+    o->scene.H = ds->H; o->scene.W = ds->W; o->scene.instance_id = instance_id; o->scene.use_depth = ds->use_depth;
+    o->lc.loss_scale = cfg->loss_scale; o->lc.depth_lambda = cfg->depth_lambda; o->lc.mask_lambda = cfg->mask_lambda;
+    o->lc.bg_density_reg = cfg->bg_density_reg;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, ds->gpu));
+    o->sm_count = prop.multiProcessorCount;
+    // MLP kernel grid: 2 resident CTAs per SM, never more CTAs than 4-ray groups
+    o->n_ctas = std::min<uint32_t>((uint32_t)o->sm_count * 2, (o->R + 3) / 4);
+    if (o->n_ctas > MON_MAX_MLP_CTAS) o->n_ctas = MON_MAX_MLP_CTAS;
+    o->opt.lr = cfg->learning_rate; o->opt.beta1 = cfg->beta1; o->opt.beta2 = cfg->beta2; o->opt.eps = cfg->epsilon;
+    o->opt.l2_reg = cfg->l2_reg; o->opt.ema_decay = cfg->ema_decay; o->opt.loss_scale = cfg->loss_scale;
+    o->opt.decay_start = cfg->decay_start; o->opt.decay_interval = cfg->decay_interval; o->opt.decay_base = cfg->decay_base;
+    o->opt.n_mlp = o->n_mlp; o->opt.n_params = o->P; o->opt.n_partials = o->n_ctas;
+
+#define OALLOC(ptr, bytes)                                                                                  \
+    do {                                                                                                    \
+        cudaError_t e_ = cudaMalloc(reinterpret_cast<void**>(&(ptr)), (bytes));                             \
+        if (e_ == cudaSuccess) e_ = cudaMemset((ptr), 0, (bytes));                                          \
+        if (e_ != cudaSuccess) { mon_object_destroy(o); return fail(MON_ERR_CUDA, "object allocation (%zu B): %s", (size_t)(bytes), cudaGetErrorString(e_)); } \
+    } while (0)
+    const size_t P = o->P, R = o->R, N = o->N;
+    OALLOC(o->pf, P * 4); OALLOC(o->m, P * 4); OALLOC(o->v, P * 4); OALLOC(o->ps, P * 4);
+    OALLOC(o->ph, P * 2 + 16); OALLOC(o->gh, P * 2 + 16); OALLOC(o->ema, P * 2 + 16);
+    OALLOC(o->ctrl, sizeof(MonCtrl));
+    OALLOC(o->rays, R * sizeof(MonRay)); OALLOC(o->ray_inst, R);
+    OALLOC(o->target, R * 12); OALLOC(o->target_depth, R * 4); OALLOC(o->bg, R * 12);
+    OALLOC(o->rgb_rays, R * 12); OALLOC(o->depth_rays, R * 4); OALLOC(o->mask_rays, R * 4); OALLOC(o->loss, R * 4);
+    OALLOC(o->enc, N * MON_IN * 2); OALLOC(o->d_enc, N * MON_IN * 2);
+    OALLOC(o->partials, (size_t)o->n_ctas * o->n_mlp * 4);
+#undef OALLOC
+    cudaError_t e;
+    if ((e = cudaMallocHost(&o->h_ctrl, sizeof(MonCtrl))) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&o->ev0)) != cudaSuccess || (e = cudaEventCreate(&o->ev1)) != cudaSuccess) {
+        mon_object_destroy(o);
+        return fail(MON_ERR_CUDA, "object setup: %s", cudaGetErrorString(e));
+    }
+    memset(o->h_ctrl, 0, sizeof(MonCtrl));
+
+    // ---- A12 parameter initialisation (Trainer ctor, trainer.h:53-90)
+    std::seed_seq seq{seed};
+    std::vector<uint32_t> seeds(2);
+    seq.generate(seeds.begin(), seeds.end());
+    HostPcg32 rng(seeds.front());
+    std::vector<float> mlp(o->n_mlp);
+    {
+        float* p = mlp.data();
+        auto xavier = [&](uint32_t rows, uint32_t cols) {  // gpu_matrix.h:291-303
+            float scale = 1.0f;
+            scale *= std::sqrt(6.0f / (float)(rows + cols));
+            for (uint32_t i = 0; i < rows * cols; ++i) p[i] = rng.next_float() * 2.0f * scale - scale;
+            p += rows * cols;
+        };
+        xavier(MON_WIDTH, MON_IN);
+        for (uint32_t l = 1; l < cfg->n_hidden_layers; ++l) xavier(MON_WIDTH, MON_WIDTH);
+        xavier(MON_OUT, MON_WIDTH);
+    }
+    if ((e = cudaMemcpyAsync(o->pf, mlp.data(), o->n_mlp * 4, cudaMemcpyHostToDevice, o->stream)) != cudaSuccess) {
+        mon_object_destroy(o);
+        return fail(MON_ERR_CUDA, "param upload: %s", cudaGetErrorString(e));
+    }
+    mon_launch_init_grid(rng.state, rng.inc, o->n_grid, o->pf + o->n_mlp, o->stream);
+    mon_launch_cast_params((uint32_t)P, o->pf, o->ph, o->stream);
+    o->launches += 2;
+    if ((e = cudaStreamSynchronize(o->stream)) != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) {
+        mon_object_destroy(o);
+        return fail(MON_ERR_CUDA, "param init: %s", cudaGetErrorString(e));
+    }
+    *out = o;
+    return MON_OK;
+}
+
+int mon_object_destroy(mon_object* o) {
+    if (!o) return MON_OK;
+    cudaSetDevice(o->ds->gpu);
+    if (o->stream) cudaStreamSynchronize(o->stream);
+    drop_graphs(o);
+    void* ptrs[] = {o->pf, o->m, o->v, o->ps, o->ph, o->gh, o->ema, o->ctrl, o->d_boxes, o->rays, o->ray_inst, o->target,
+                    o->target_depth, o->bg, o->rgb_rays, o->depth_rays, o->mask_rays, o->loss, o->enc, o->d_enc, o->partials,
+                    o->dbg_out, o->dbg_dout, o->inj_xy, o->inj_col, o->inj_dt, o->grad_snap, o->r_rays, o->r_inbox, o->r_enc,
+                    o->r_jit, o->r_rgb, o->r_depth, o->r_mask, o->r_Twc};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (o->h_ctrl) cudaFreeHost(o->h_ctrl);
+    if (o->ev0) cudaEventDestroy(o->ev0);
+    if (o->ev1) cudaEventDestroy(o->ev1);
+    if (o->stream) cudaStreamDestroy(o->stream);
+    delete o;
+    return MON_OK;
+}
+
+static int upload_boxes(mon_object* o, uint32_t first) {
+    CK(cudaSetDevice(o->ds->gpu));
+    const uint32_t n = (uint32_t)o->h_boxes.size();
+    for (uint32_t i = first; i < n; ++i) {
+        const mon_bbox2d& b = o->h_boxes[i];
+        if (b.FrameId >= o->ds->max_frames || !o->ds->h_frames[b.FrameId].rgb)
+            return fail(MON_ERR_ARG, "box %u references frame %u which is not in the dataset", i, b.FrameId);
+        // the reference samples x in [b.x, b.x+b.w] inclusive (curand's (0,1])
+        if (b.w == 0 || b.h == 0 || (uint64_t)b.x + b.w > (uint64_t)o->ds->W || (uint64_t)b.y + b.h > (uint64_t)o->ds->H)
+            return fail(MON_ERR_ARG, "box %u (x=%u y=%u h=%u w=%u) lies outside the %dx%d image", i, b.x, b.y, b.h, b.w, o->ds->W, o->ds->H);
+    }
+    CK(cudaStreamSynchronize(o->stream));
+    if (n > o->box_cap) {
+        const uint32_t cap = std::max<uint32_t>(256, n * 2);
+        mon_bbox2d* p = nullptr;
+        CK(cudaMalloc(&p, sizeof(mon_bbox2d) * cap));
+        if (o->d_boxes) cudaFree(o->d_boxes);
+        o->d_boxes = p; o->box_cap = cap;
+        first = 0;
+        drop_graphs(o);  // the captured graphs hold the old pointer
+    }
+    if (n > first) CK(cudaMemcpyAsync(o->d_boxes + first, o->h_boxes.data() + first, sizeof(mon_bbox2d) * (n - first), cudaMemcpyHostToDevice, o->stream));
+    CK(cudaMemcpyAsync(&o->ctrl->n_boxes, &n, 4, cudaMemcpyHostToDevice, o->stream));
+    CK(cudaStreamSynchronize(o->stream));
+    return MON_OK;
+}
+
+int mon_object_set_bboxes(mon_object* o, const mon_bbox2d* boxes, uint32_t n) {
+    if (!o || (!boxes && n)) return fail(MON_ERR_ARG, "NULL argument");
+    std::vector<mon_bbox2d> keep = o->h_boxes;
+    o->h_boxes.assign(boxes, boxes + n);
+    const int rc = upload_boxes(o, 0);
+    if (rc != MON_OK) o->h_boxes = keep;
+    return rc;
+}
+
+int mon_object_add_bboxes(mon_object* o, const mon_bbox2d* boxes, uint32_t n) {
+    if (!o || (!boxes && n)) return fail(MON_ERR_ARG, "NULL argument");
+    const uint32_t first = (uint32_t)o->h_boxes.size();
+    o->h_boxes.insert(o->h_boxes.end(), boxes, boxes + n);
+    const int rc = upload_boxes(o, first);
+    if (rc != MON_OK) o->h_boxes.resize(first);
+    return rc;
+}
+
+static int finish_timing(mon_object* o) {
+    if (o->timing_pending) {
+        CK(cudaEventElapsedTime(&o->last_ms, o->ev0, o->ev1));
+        o->timing_pending = false;
+    }
+    return MON_OK;
+}
+
+int mon_object_train_async(mon_object* o, uint32_t iters) {
+    if (!o) return fail(MON_ERR_ARG, "obj is NULL");
+    if (o->h_boxes.empty()) return fail(MON_ERR_STATE, "no 2-D boxes: call mon_object_set_bboxes first");
+    CK(cudaSetDevice(o->ds->gpu));
+    if (!o->graph1) { int rc = capture_graph(o, 1, &o->graph1); if (rc != MON_OK) return rc; }
+    if (iters >= MON_GRAPH_CHUNK && !o->graphN) { int rc = capture_graph(o, MON_GRAPH_CHUNK, &o->graphN); if (rc != MON_OK) return rc; }
+    CK(cudaEventRecord(o->ev0, o->stream));
+    uint32_t left = iters;
+    while (left >= MON_GRAPH_CHUNK) { CK(cudaGraphLaunch(o->graphN, o->stream)); left -= MON_GRAPH_CHUNK; }
+    while (left > 0) { CK(cudaGraphLaunch(o->graph1, o->stream)); --left; }
+    CK(cudaEventRecord(o->ev1, o->stream));
+    o->timing_pending = true;
+    o->launches += (uint64_t)iters * kKernelsPerIter;
+    o->have_injected = false;
+    return MON_OK;
+}
+
+int mon_object_sync(mon_object* o) {
+    if (!o) return fail(MON_ERR_ARG, "obj is NULL");
+    CK(cudaSetDevice(o->ds->gpu));
+    CK(cudaStreamSynchronize(o->stream));
+    return finish_timing(o);
+}
+
+static int read_ctrl(mon_object* o) {
+    CK(cudaMemcpyAsync(o->h_ctrl, o->ctrl, sizeof(MonCtrl), cudaMemcpyDeviceToHost, o->stream));
+    CK(cudaStreamSynchronize(o->stream));
+    return MON_OK;
+}
+
+int mon_object_train(mon_object* o, uint32_t iters, float* loss) {
+    int rc = mon_object_train_async(o, iters);
+    if (rc != MON_OK) return rc;
+    rc = read_ctrl(o);  // one 32-byte D2H read per call: the logged loss, like Train_Step (:1650-1658)
+    if (rc != MON_OK) return rc;
+    rc = finish_timing(o);
+    if (rc != MON_OK) return rc;
+    if (loss) *loss = o->h_ctrl->loss_mean;
+    return MON_OK;
+}
+
+int mon_object_train_profiled(mon_object* o, uint32_t iters, float* stage_ms, uint32_t n_stages) {
+    if (!o || !stage_ms) return fail(MON_ERR_ARG, "NULL argument");
+    if (n_stages != MON_N_STAGES) return fail(MON_ERR_ARG, "n_stages must be %d", MON_N_STAGES);
+    if (o->h_boxes.empty()) return fail(MON_ERR_STATE, "no 2-D boxes: call mon_object_set_bboxes first");
+    CK(cudaSetDevice(o->ds->gpu));
+    cudaEvent_t ev[MON_N_STAGES + 1];
+    for (auto& x : ev) CK(cudaEventCreate(&x));
+    double acc[MON_N_STAGES] = {0};
+    const MonBatch b = make_batch(o, false, false);
+    int rc = MON_OK;
+    for (uint32_t it = 0; it < iters && rc == MON_OK; ++it) {
+        int n = 0;
+        rc = enqueue_iteration(o, b, false, &n, ev);
+        if (rc != MON_OK) break;
+        o->launches += (uint64_t)n;
+        cudaError_t e = cudaStreamSynchronize(o->stream);
+        if (e != cudaSuccess) { rc = fail(MON_ERR_CUDA, "profiled iteration: %s", cudaGetErrorString(e)); break; }
+        for (int k = 0; k < MON_N_STAGES; ++k) {
+            float ms = 0.0f;
+            cudaEventElapsedTime(&ms, ev[k], ev[k + 1]);
+            acc[k] += ms;
+        }
+    }
+    for (auto& x : ev) cudaEventDestroy(x);
+    if (rc != MON_OK) return rc;
+    for (int k = 0; k < MON_N_STAGES; ++k) stage_ms[k] = iters ? (float)(acc[k] / iters) : 0.0f;
+    o->have_injected = false;
+    return MON_OK;
+}
+
+int mon_object_last_train_ms(mon_object* o, float* ms) {
+    if (!o || !ms) return fail(MON_ERR_ARG, "NULL argument");
+    if (o->timing_pending) return fail(MON_ERR_STATE, "training still in flight: call mon_object_sync first");
+    *ms = o->last_ms;
+    return MON_OK;
+}
+
+int mon_object_step_count(mon_object* o, uint32_t* step) {
+    if (!o || !step) return fail(MON_ERR_ARG, "NULL argument");
+    CK(cudaSetDevice(o->ds->gpu));
+    int rc = read_ctrl(o);
+    if (rc != MON_OK) return rc;
+    *step = o->h_ctrl->step;
+    return MON_OK;
+}
+
+int mon_object_launch_count(mon_object* o, uint64_t* n) {
+    if (!o || !n) return fail(MON_ERR_ARG, "NULL argument");
+    *n = o->launches;
+    return MON_OK;
+}
+
+int mon_object_set_mlp_impl(mon_object* o, int impl) {
+    if (!o) return fail(MON_ERR_ARG, "obj is NULL");
+    if (impl != 0 && impl != 1) return fail(MON_ERR_ARG, "impl must be 0 (tcgen05) or 1 (mma.sync validation kernel)");
+#ifndef MON_HAVE_TC
+    if (impl == 0) return fail(MON_ERR_STATE, "this build has no tcgen05 MLP kernel");
+#endif
+    if (impl == 1 && o->cfg.n_hidden_layers != 1) return fail(MON_ERR_STATE, "the mma.sync validation kernel supports n_hidden_layers == 1 only");
+    CK(cudaSetDevice(o->ds->gpu));
+    CK(cudaStreamSynchronize(o->stream));
+    if (impl != o->mlp_impl) drop_graphs(o);
+    o->mlp_impl = impl;
+    return MON_OK;
+}
+
+// ------------------------------------------------------------------------------- parity hooks
+static int ensure_hooks(mon_object* o) {
+    if (o->dbg_out) return MON_OK;
+    const size_t R = o->R, N = o->N;
+    CK(cudaMalloc(&o->dbg_out, N * 16)); CK(cudaMalloc(&o->dbg_dout, N * 16));
+    CK(cudaMalloc(&o->inj_xy, R * 8)); CK(cudaMalloc(&o->inj_col, R * 12)); CK(cudaMalloc(&o->inj_dt, N * 4));
+    CK(cudaMalloc(&o->grad_snap, (size_t)o->P * 4));
+    return MON_OK;
+}
+
+int mon_object_train_injected(mon_object* o, const float* sample_xy, const float* rand_colors,
+                              const float* rand_dt, float* loss, uint32_t* n_in_box) {
+    if (!o || !sample_xy || !rand_colors || !rand_dt) return fail(MON_ERR_ARG, "NULL argument");
+    if (o->h_boxes.empty()) return fail(MON_ERR_STATE, "no 2-D boxes: call mon_object_set_bboxes first");
+    CK(cudaSetDevice(o->ds->gpu));
+    int rc = ensure_hooks(o);
+    if (rc != MON_OK) return rc;
+    CK(cudaMemcpyAsync(o->inj_xy, sample_xy, (size_t)o->R * 8, cudaMemcpyHostToDevice, o->stream));
+    CK(cudaMemcpyAsync(o->inj_col, rand_colors, (size_t)o->R * 12, cudaMemcpyHostToDevice, o->stream));
+    CK(cudaMemcpyAsync(o->inj_dt, rand_dt, (size_t)o->N * 4, cudaMemcpyHostToDevice, o->stream));
+    CK(cudaMemsetAsync(o->dbg_out, 0, (size_t)o->N * 16, o->stream));
+    CK(cudaMemsetAsync(o->dbg_dout, 0, (size_t)o->N * 16, o->stream));
+    const MonBatch b = make_batch(o, true, true);
+    int n = 0;
+    CK(cudaEventRecord(o->ev0, o->stream));
+    rc = enqueue_iteration(o, b, true, &n);
+    if (rc != MON_OK) return rc;
+    CK(cudaEventRecord(o->ev1, o->stream));
+    o->timing_pending = true;
+    o->launches += (uint64_t)n;
+    rc = read_ctrl(o);
+    if (rc != MON_OK) return rc;
+    rc = finish_timing(o);
+    if (rc != MON_OK) return rc;
+    o->have_injected = true;
+    if (loss) *loss = o->h_ctrl->loss_mean;
+    if (n_in_box) *n_in_box = o->h_ctrl->n_in;
+    return MON_OK;
+}
+
+namespace {
+__global__ void k_half_to_float(size_t n, const __half* __restrict__ in, float* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __half2float(in[i]);
+}
+__global__ void k_u32_to_float(size_t n, const uint32_t* __restrict__ in, float* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i];
+}
+__global__ void k_u8_to_float(size_t n, const uint8_t* __restrict__ in, float* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i];
+}
+__global__ void k_float_to_half(size_t n, const float* __restrict__ in, __half* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __float2half_rn(in[i]);
+}
+__global__ void k_lattice_points(uint32_t rx, uint32_t ry, uint32_t rz, float* __restrict__ out) {
+    // generate_grid_samples_nerf_uniform (nerf_model.cu:296-309): pos = idx / (res - 1), x fastest
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n = (size_t)rx * ry * rz;
+    if (i >= n) return;
+    const uint32_t x = (uint32_t)(i % rx), y = (uint32_t)((i / rx) % ry), z = (uint32_t)(i / ((size_t)rx * ry));
+    out[3 * i + 0] = __fdiv_rn((float)x, (float)(rx - 1));
+    out[3 * i + 1] = __fdiv_rn((float)y, (float)(ry - 1));
+    out[3 * i + 2] = __fdiv_rn((float)z, (float)(rz - 1));
+}
+__global__ void k_extract_sigma(size_t n, const float* __restrict__ out4, float* __restrict__ sigma) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) sigma[i] = out4[4 * i + 3];
+}
+
+// copies n values of a device array to the host as float, converting on the device
+int fetch_as_float(mon_object* o, const void* src, int kind /*0 f32 1 f16 2 u32 3 u8*/, size_t n, float* out) {
+    if (n == 0) return MON_OK;
+    float* tmp = nullptr;
+    const float* from = nullptr;
+    if (kind == 0) {
+        from = static_cast<const float*>(src);
+    } else {
+        CK(cudaMalloc(&tmp, n * 4));
+        const unsigned blocks = (unsigned)((n + 255) / 256);
+        if (kind == 1) k_half_to_float<<<blocks, 256, 0, o->stream>>>(n, static_cast<const __half*>(src), tmp);
+        else if (kind == 2) k_u32_to_float<<<blocks, 256, 0, o->stream>>>(n, static_cast<const uint32_t*>(src), tmp);
+        else k_u8_to_float<<<blocks, 256, 0, o->stream>>>(n, static_cast<const uint8_t*>(src), tmp);
+        o->launches += 1;
+        from = tmp;
+    }
+    cudaError_t e = cudaMemcpyAsync(out, from, n * 4, cudaMemcpyDeviceToHost, o->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(o->stream);
+    if (tmp) cudaFree(tmp);
+    if (e != cudaSuccess) return fail(MON_ERR_CUDA, "state read-back: %s", cudaGetErrorString(e));
+    return MON_OK;
+}
+}  // namespace
+
+int mon_object_get_state(mon_object* o, int which, float* out, size_t n) {
+    if (!o || !out) return fail(MON_ERR_ARG, "NULL argument");
+    if (n != o->P) return fail(MON_ERR_ARG, "n must equal the parameter count %u", o->P);
+    CK(cudaSetDevice(o->ds->gpu));
+    switch (which) {
+        case 0: return fetch_as_float(o, o->pf, 0, n, out);
+        case 1: return fetch_as_float(o, o->ph, 1, n, out);
+        case 2: return fetch_as_float(o, o->ema, 1, n, out);
+        case 3:
+            if (!o->have_injected) return fail(MON_ERR_STATE, "the gradient snapshot exists only after mon_object_train_injected");
+            return fetch_as_float(o, o->grad_snap, 0, n, out);
+        case 4: return fetch_as_float(o, o->m, 0, n, out);
+        case 5: return fetch_as_float(o, o->v, 0, n, out);
+        case 6: return fetch_as_float(o, o->ps, 2, n, out);
+    }
+    return fail(MON_ERR_ARG, "unknown state selector %d", which);
+}
+
+int mon_object_set_params(mon_object* o, const float* params, size_t n) {
+    if (!o || !params) return fail(MON_ERR_ARG, "NULL argument");
+    if (n != o->P) return fail(MON_ERR_ARG, "n must equal the parameter count %u", o->P);
+    CK(cudaSetDevice(o->ds->gpu));
+    CK(cudaMemcpyAsync(o->pf, params, n * 4, cudaMemcpyHostToDevice, o->stream));
+    mon_launch_cast_params((uint32_t)n, o->pf, o->ph, o->stream);
+    o->launches += 1;
+    CK(cudaStreamSynchronize(o->stream));
+    return MON_OK;
+}
+
+int mon_object_last(mon_object* o, int which, float* out, size_t cap, size_t* n_out) {
+    if (!o || !out) return fail(MON_ERR_ARG, "NULL argument");
+    if (!o->have_injected) return fail(MON_ERR_STATE, "intermediates exist only after mon_object_train_injected");
+    CK(cudaSetDevice(o->ds->gpu));
+    const size_t R = o->R, N = o->N;
+    const void* src = nullptr; int kind = 0; size_t n = 0;
+    switch (which) {
+        case 0: src = o->rays; n = R * 9; break;
+        case 3: src = o->enc; kind = 1; n = N * MON_IN; break;
+        case 4: src = o->dbg_out; n = N * 4; break;
+        case 5: src = o->rgb_rays; n = R * 3; break;
+        case 6: src = o->depth_rays; n = R; break;
+        case 7: src = o->mask_rays; n = R; break;
+        case 8: src = o->dbg_dout; n = N * 4; break;
+        case 9: src = o->d_enc; kind = 1; n = N * MON_IN; break;
+        case 10: src = o->target; n = R * 3; break;
+        case 11: src = o->target_depth; n = R; break;
+        case 12: src = o->ray_inst; kind = 3; n = R; break;
+        case 13: src = o->loss; n = R; break;
+        default: return fail(MON_ERR_ARG, "unknown intermediate selector %d", which);
+    }
+    if (n_out) *n_out = n;
+    if (cap < n) return fail(MON_ERR_ARG, "buffer too small: need %zu floats", n);
+    return fetch_as_float(o, src, kind, n, out);
+}
+
+// ------------------------------------------------------------------------------- render
+static int ensure_render_ws(mon_object* o, uint32_t n_rays, size_t jitter_floats) {
+    const uint32_t S2 = o->cfg.render_samples_per_ray;
+    const uint32_t tile = 16384;  // rays per pass: 1 Mi points, 64 MiB of fp16 features
+    if (n_rays > o->r_cap_rays) {
+        void* old[] = {o->r_rays, o->r_inbox, o->r_rgb, o->r_depth, o->r_mask};
+        for (void* p : old) if (p) cudaFree(p);
+        o->r_rays = nullptr; o->r_inbox = nullptr; o->r_rgb = o->r_depth = o->r_mask = nullptr;
+        o->r_cap_rays = 0;
+        CK(cudaMalloc(&o->r_rays, (size_t)n_rays * sizeof(MonRay)));
+        CK(cudaMalloc(&o->r_inbox, (size_t)n_rays * 4));
+        CK(cudaMalloc(&o->r_rgb, (size_t)n_rays * 12));
+        CK(cudaMalloc(&o->r_depth, (size_t)n_rays * 4));
+        CK(cudaMalloc(&o->r_mask, (size_t)n_rays * 4));
+        o->r_cap_rays = n_rays;
+    }
+    if (!o->r_enc) {
+        CK(cudaMalloc(&o->r_enc, (size_t)tile * S2 * MON_IN * 2));
+        CK(cudaMalloc(&o->r_Twc, 64));
+        o->r_tile = tile;
+    }
+    if (jitter_floats > o->r_jit_cap) {
+        if (o->r_jit) cudaFree(o->r_jit);
+        o->r_jit = nullptr; o->r_jit_cap = 0;
+        CK(cudaMalloc(&o->r_jit, jitter_floats * 4));
+        o->r_jit_cap = jitter_floats;
+    }
+    return MON_OK;
+}
+
+int mon_object_render(mon_object* o, mon_bbox2d box, const float Twc[16], int use_ema,
+                      const float* rand_dt, float* rgb, float* depth, float* mask) {
+    if (!o || !Twc || !rgb || !depth || !mask) return fail(MON_ERR_ARG, "NULL argument");
+    if (box.w == 0 || box.h == 0) return fail(MON_ERR_ARG, "empty render box");
+    if ((uint64_t)box.w * box.h > (1u << 26)) return fail(MON_ERR_ARG, "render box too large");
+    if (o->cfg.n_hidden_layers != 1 && o->mlp_impl == 1) return fail(MON_ERR_STATE, "render needs the tcgen05 kernel for n_hidden_layers > 1");
+    CK(cudaSetDevice(o->ds->gpu));
+    const uint32_t n_rays = box.w * box.h, S2 = o->cfg.render_samples_per_ray;
+    int rc = ensure_render_ws(o, n_rays, rand_dt ? (size_t)n_rays * S2 : 0);
+    if (rc != MON_OK) return rc;
+    cudaStream_t st = o->stream;
+    CK(cudaMemcpyAsync(o->r_Twc, Twc, 64, cudaMemcpyHostToDevice, st));
+    if (rand_dt) CK(cudaMemcpyAsync(o->r_jit, rand_dt, (size_t)n_rays * S2 * 4, cudaMemcpyHostToDevice, st));
+    mon_launch_render_rays(n_rays, box, o->scene, o->r_Twc, o->r_rays, o->r_inbox, st);
+    o->launches += 1;
+    const __half* params = use_ema ? o->ema : o->ph;
+    const uint32_t rc_id = o->render_count++;
+    for (uint32_t r0 = 0, t = 0; r0 < n_rays; r0 += o->r_tile, ++t) {
+        const uint32_t nr = std::min(o->r_tile, n_rays - r0);
+        const float* jit = rand_dt ? o->r_jit + (size_t)r0 * S2 : nullptr;
+        const uint32_t iter_fixed = rc_id * 4099u + t;
+        mon_launch_encode_forward(o->grid, nr * S2, S2, o->r_rays + r0, o->r_inbox + r0, jit, o->seed, nullptr, 3, iter_fixed,
+                                  o->scene.bmin, o->scene.bmax, params + o->n_mlp, o->r_enc, st);
+        cudaError_t e = mon_launch_mlp_render_wmma(nr, S2, o->r_rays + r0, o->r_inbox + r0, jit, o->seed, iter_fixed, params,
+                                                   o->r_enc, 1.0f, o->r_rgb + (size_t)r0 * 3, o->r_depth + r0, o->r_mask + r0, st);
+        if (e != cudaSuccess) return fail(MON_ERR_CUDA, "render launch: %s", cudaGetErrorString(e));
+        o->launches += 2;
+    }
+    CK(cudaMemcpyAsync(rgb, o->r_rgb, (size_t)n_rays * 12, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(depth, o->r_depth, (size_t)n_rays * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(mask, o->r_mask, (size_t)n_rays * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    return MON_OK;
+}
+
+int mon_object_density_grid(mon_object* o, const uint32_t res[3], float* out) {
+    if (!o || !res || !out) return fail(MON_ERR_ARG, "NULL argument");
+    if (res[0] < 2 || res[1] < 2 || res[2] < 2) return fail(MON_ERR_ARG, "resolution must be >= 2 per axis");
+    const size_t n = (size_t)res[0] * res[1] * res[2];
+    if (n > (1u << 27)) return fail(MON_ERR_ARG, "lattice too large");
+    if (o->cfg.n_hidden_layers != 1 && o->mlp_impl == 1) return fail(MON_ERR_STATE, "needs the tcgen05 kernel for n_hidden_layers > 1");
+    CK(cudaSetDevice(o->ds->gpu));
+    cudaStream_t st = o->stream;
+    float *pts = nullptr, *out4 = nullptr, *sigma = nullptr; __half* enc = nullptr;
+    cudaError_t e = cudaMalloc(&pts, n * 12);
+    if (e == cudaSuccess) e = cudaMalloc(&out4, n * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&sigma, n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&enc, n * MON_IN * 2);
+    if (e == cudaSuccess) {
+        const unsigned blocks = (unsigned)((n + 255) / 256);
+        k_lattice_points<<<blocks, 256, 0, st>>>(res[0], res[1], res[2], pts);
+        mon_launch_encode_points(o->grid, (uint32_t)n, pts, o->ph + o->n_mlp, enc, st);
+#ifdef MON_HAVE_TC
+        if (o->mlp_impl == 0) e = mon_launch_mlp_infer_tc((uint32_t)n, o->cfg.n_hidden_layers, o->ph, enc, out4, st);
+        else
+#endif
+        e = mon_launch_mlp_infer_wmma((uint32_t)n, o->ph, enc, out4, st);
+        k_extract_sigma<<<blocks, 256, 0, st>>>(n, out4, sigma);
+        o->launches += 4;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out, sigma, n * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    if (pts) cudaFree(pts);
+    if (out4) cudaFree(out4);
+    if (sigma) cudaFree(sigma);
+    if (enc) cudaFree(enc);
+    if (e != cudaSuccess) return fail(MON_ERR_CUDA, "density grid: %s", cudaGetErrorString(e));
+    return MON_OK;
+}
+
+// ------------------------------------------------------------------------------- stage hooks
+int mon_stage_encode(const mon_config* cfg, const uint16_t* grid_fp16, size_t n_grid_params,
+                     const float* points_unit, uint32_t n_points, uint16_t* enc_out) {
+    if (!cfg || !grid_fp16 || !points_unit || !enc_out) return fail(MON_ERR_ARG, "NULL argument");
+    MonGrid g; std::string why;
+    if (!make_grid(*cfg, g, why)) return fail(MON_ERR_ARG, "%s", why.c_str());
+    if (n_grid_params != (size_t)g.offset[cfg->n_levels] * 2) return fail(MON_ERR_ARG, "n_grid_params must be %u", g.offset[cfg->n_levels] * 2);
+    if (n_points == 0) return MON_OK;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return fail(MON_ERR_NO_DEVICE, "no CUDA device (this library has no CPU path)"); }
+    __half *d_grid = nullptr, *d_enc = nullptr; float* d_pts = nullptr;
+    const size_t enc_bytes = (size_t)n_points * 2 * cfg->n_levels * 2;
+    cudaError_t e = cudaMalloc(&d_grid, n_grid_params * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&d_pts, (size_t)n_points * 12);
+    if (e == cudaSuccess) e = cudaMalloc(&d_enc, enc_bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(d_grid, grid_fp16, n_grid_params * 2, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_pts, points_unit, (size_t)n_points * 12, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        mon_launch_encode_points(g, n_points, d_pts, d_grid, d_enc, nullptr);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(enc_out, d_enc, enc_bytes, cudaMemcpyDeviceToHost);
+    if (d_grid) cudaFree(d_grid);
+    if (d_pts) cudaFree(d_pts);
+    if (d_enc) cudaFree(d_enc);
+    if (e != cudaSuccess) return fail(MON_ERR_CUDA, "mon_stage_encode: %s", cudaGetErrorString(e));
+    return MON_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,91 @@
+// mon_types.h — device/host shared data model of the B200 Multi-Object-NeRF core.
+// Reference counterparts: Ray (MON/Core/include/nerf_model.h:34-42), MetaData
+// (nerf_data.h:11-17), BatchData (nerf_model.h:45-65), GridOffsetTable (TCNN grid.h).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mon_c.h"
+
+#define MON_MAX_LEVELS 16
+#define MON_S 32          // training samples per ray == warp size (common.h:12 SampleNum)
+#define MON_WIDTH 64      // hidden width (base.json n_neurons)
+#define MON_IN 32         // encoding width = n_levels * 2
+#define MON_OUT 16        // padded output width (tcnn pads 4 -> 16)
+#define MON_MAX_MLP_CTAS 296
+
+// 36-byte POD; same field order as nerf::Ray
+struct MonRay { float o[3], d[3], d_norm, tmin, tmax; };
+
+// per-frame device pointers; u8 pixels instead of the reference's float pixels
+struct MonFrame {
+    const uint8_t* rgb;       // H*W*3, RGB
+    const uint8_t* instance;  // H*W
+    const float* depth;       // H*W or nullptr
+    float pose[16];           // camera-to-world, column-major
+};
+
+// geometry of the multiresolution table, precomputed on the host (grid.h:195-204,964-997)
+struct MonGrid {
+    uint32_t n_levels;
+    uint32_t offset[MON_MAX_LEVELS + 1];  // in entries (1 entry = 2 fp16 features)
+    uint32_t size[MON_MAX_LEVELS];        // entries in level
+    uint32_t res[MON_MAX_LEVELS];
+    uint32_t hashed[MON_MAX_LEVELS];      // 1 if coherent-prime hash is used, 0 if dense
+    float scale[MON_MAX_LEVELS];
+};
+
+// constant scene description of one object
+struct MonScene {
+    float Tow[16];      // world -> object
+    float bmin[3], bmax[3];
+    float K[4];         // fx fy cx cy
+    int H, W;
+    uint32_t instance_id;
+    int use_depth;
+};
+
+// device-resident iteration control block (read by every kernel of the iteration graph)
+struct MonCtrl {
+    uint32_t step;      // optimizer step of the CURRENT iteration (1-based), bumped by the batch kernel
+    uint32_t n_in;      // rays inside the box before roll-over padding
+    uint32_t skip;      // 1: no ray hit the box this iteration -> all later kernels are no-ops
+    uint32_t iter;      // RNG iteration counter (advances even when skipped)
+    float loss_mean;    // filled by the loss reduction kernel
+    uint32_t n_boxes;   // live number of 2-D boxes (host-updated; keeps the captured graph valid)
+    uint32_t pad[2];
+};
+
+// optimizer hyper-parameters
+struct MonOpt {
+    float lr, beta1, beta2, eps, l2_reg, ema_decay, loss_scale;
+    uint32_t decay_start, decay_interval; float decay_base;
+    uint32_t n_mlp, n_params;
+    uint32_t n_partials;   // number of per-CTA MLP gradient partials to sum
+};
+
+struct MonLossCfg { float loss_scale, depth_lambda, mask_lambda, bg_density_reg; };
+
+// everything a training iteration touches, as raw device pointers
+struct MonBatch {
+    uint32_t R;                 // rays per batch
+    const mon_bbox2d* boxes;
+    const MonFrame* frames;
+    MonCtrl* ctrl;
+    uint32_t seed;
+    // injected randoms (nullptr -> internal counter-based generator)
+    const float* inj_xy; const float* inj_col; const float* inj_dt;
+    // per-ray
+    MonRay* rays; uint8_t* ray_inst; float* target; float* target_depth; float* bg;
+    float* rgb_rays; float* depth_rays; float* mask_rays; float* loss;
+    // per-point
+    __half* enc;      // [N][32]
+    __half* d_enc;    // [N][32]
+    // debug dumps (nullptr in production): out [N][4], dout [N][4]
+    float* dbg_out; float* dbg_dout;
+    // parameters
+    const __half* params;   // fp16 working copy [P]: W_in | (W_h) | W_out | grid
+    __half* grads;          // fp16 gradient [P] (grid part used; MLP part written by optimizer for inspection)
+    float* mlp_partials;    // [n_partials][n_mlp] fp32
+};

@@ -1,0 +1,101 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and exports every symbol
+include/mon_c.h declares; host-only entry points (config parsing, table geometry) behave like the
+reference's ReadNetworkConfig/ResetNetwork; compute entry points fail loudly without a GPU."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from ro_map_b200 import build, _capi
+    build.build()
+    return _capi.load()
+
+
+def test_every_declared_symbol_is_exported(lib):
+    from ro_map_b200 import _capi
+    header = (ROOT / "include" / "mon_c.h").read_text()
+    declared = set(re.findall(r"\b(mon_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found in mon_c.h"
+    assert declared == set(_capi.SIGNATURES), declared ^ set(_capi.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_struct_layouts_match_reference_pods():
+    from ro_map_b200 import _capi
+    assert C.sizeof(_capi.Bbox2d) == 20          # nerf::FrameIdAndBbox, 5 x u32 (common.h:18-23)
+    assert [f[0] for f in _capi.Bbox2d._fields_] == ["FrameId", "x", "y", "h", "w"]
+    assert C.sizeof(_capi.Config) == 23 * 4
+
+
+def test_default_config_is_base_json(lib, tmp_path):
+    from ro_map_b200 import core
+    cfg = core.default_config()
+    assert (cfg.n_levels, cfg.n_features_per_level, cfg.log2_hashmap_size, cfg.base_resolution) == (16, 2, 16, 16)
+    assert cfg.per_level_scale == 2.0 and cfg.n_neurons == 64 and cfg.n_hidden_layers == 1
+    assert cfg.rays_per_batch == 4096 and cfg.samples_per_ray == 32 and cfg.render_samples_per_ray == 64
+    assert core.param_counts(cfg) == (3072, 1908736)
+    # the reference's own base.json text (with a comment, which its parser ignores too)
+    js = tmp_path / "base.json"
+    js.write_text("""{
+      // comment
+      "loss": {"otype": "Huber"},
+      "optimizer": {"otype": "Ema", "decay": 0.95, "nested": {"otype": "ExponentialDecay", "decay_start": 20000,
+         "decay_interval": 10000, "decay_base": 0.33, "nested": {"otype": "Adam", "learning_rate": 1e-2, "beta1": 0.9,
+         "beta2": 0.99, "epsilon": 1e-15, "l2_reg": 1e-6}}},
+      "encoding": {"otype": "HashGrid", "n_levels": 16, "n_features_per_level": 2, "log2_hashmap_size": 16, "base_resolution": 16},
+      "network": {"otype": "FullyFusedMLP", "activation": "ReLU", "output_activation": "None", "n_neurons": 64, "n_hidden_layers": 1}
+    }""")
+    parsed = core.config_from_json(js)
+    for name, _ in cfg._fields_:
+        assert getattr(parsed, name) == getattr(cfg, name), name
+
+
+def test_config_errors(lib, tmp_path):
+    from ro_map_b200 import core
+    with pytest.raises(core.MonError, match="MON_ERR_IO"):
+        core.config_from_json(tmp_path / "missing.json")
+    bad = tmp_path / "bad.json"
+    bad.write_text('{"encoding": {"otype": "Frequency"}, "optimizer": {"otype": "Adam"}}')
+    with pytest.raises(core.MonError, match="not supported"):
+        core.config_from_json(bad)
+    bad.write_text('{"encoding": {"n_levels": 16, "log2_hashmap_size": 16}, "network": {"n_neurons": 64, "n_hidden_layers": 1}, "optimizer": {"otype": "Adam"')
+    with pytest.raises(core.MonError, match="JSON error"):
+        core.config_from_json(bad)
+
+
+def test_grid_layout_matches_oracle(lib, oracle):
+    from ro_map_b200 import core
+    for log2, base, levels in [(16, 16, 16), (19, 16, 16), (15, 8, 16)]:
+        cfg = core.default_config(log2_hashmap_size=log2, base_resolution=base, n_levels=levels)
+        off, sc, res = core.grid_layout(cfg)
+        ocfg = oracle.default_config(log2_hashmap_size=log2, base_resolution=base, n_levels=levels)
+        o_off, o_sc, o_res, _ = oracle.grid_layout(ocfg)
+        assert np.array_equal(off, o_off) and np.array_equal(sc, o_sc) and np.array_equal(res, o_res)
+
+
+def test_no_cpu_fallback(lib):
+    """Without a CUDA device the compute entry points must fail, not silently compute on the host."""
+    from ro_map_b200 import core
+    if core.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(core.MonError, match="MON_ERR_NO_DEVICE"):
+        core.Dataset(0, 100.0, 100.0, 50.0, 50.0, 100, 100, 4, False)
+    cfg = core.default_config()
+    with pytest.raises(core.MonError, match="MON_ERR_NO_DEVICE"):
+        core.stage_encode(cfg, np.zeros(1908736, np.uint16), np.zeros((4, 3), np.float32))
+
+
+def test_product_does_not_reference_the_oracle():
+    """The oracle is test infrastructure: nothing under ro_map_b200/ or include/ may mention it."""
+    for p in list((ROOT / "ro_map_b200").rglob("*")) + list((ROOT / "include").rglob("*")):
+        if p.is_file() and p.suffix in {".py", ".cu", ".cuh", ".h", ".cpp", ".hpp"}:
+            text = p.read_text(errors="ignore")
+            assert "mon_oracle" not in text and "orc_" not in text and "libmon_ref" not in text, p

@@ -103,8 +103,11 @@ bool make_grid(const mon_config& c, MonGrid& g, std::string& why) {
         uint32_t n = std::pow((float)res, 3) > (float)max_params ? max_params : res * res * res;
         n = next_multiple(n, 8u);
         n = std::min(n, 1u << c.log2_hashmap_size);
-        // grid_index(): the dense formula is used iff the running stride never exceeds the table
-        uint64_t stride = 1;
+        // grid_index() (grid.h:170-187) decides dense vs hash from a 32-bit running stride.  The wrap-around
+        // is part of the reference's behaviour: at res == 65536 (level 12 of base.json) the stride becomes
+        // 2^32 == 0, the hash is NOT taken and the index degenerates to (x + y*65536) % 65536 == x % 65536.
+        // The kernels' dense formula x + y*res + z*res*res wraps the same way in uint32.
+        uint32_t stride = 1;
         for (int d = 0; d < 3 && stride <= n; ++d) stride *= res;
         g.offset[i] = offset;
         g.size[i] = n;

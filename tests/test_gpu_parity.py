@@ -121,12 +121,14 @@ def test_one_iteration_stage_by_stage(core, oracle, gpu_dataset, small_seq, R, i
     # A3+A4: sample positions are regenerated in-kernel; the encoding must still be bit-exact
     enc_g, enc_o = g.last("enc"), o2.last("enc")
     assert np.array_equal(enc_g, enc_o)
-    # A5: network output. fp32 accumulation order differs (tensor-core vs sequential): <= 2 fp16 ulp on
-    # >= 99.9% of values, never more than 8 ulp (a hidden unit whose ReLU input rounds across zero)
+    # A5: network output (fp16). fp32 accumulation order differs (tensor core vs sequential) and hidden
+    # activations are re-rounded to fp16: <= 2 fp16 ulp on >= 99.9% of values; everywhere within
+    # 0.2% relative + 2e-4 absolute (outputs that cancel to ~0 have large ulp distances but tiny absolute error)
     out_g = g.last("out").reshape(-1, 4)
     out_o = o2.last("out").reshape(-1, 16)[:, :4]
     d = ulp16_diff(out_g, out_o)
-    assert (d <= 2).mean() >= 0.999 and d.max() <= 8, (d.max(), (d <= 2).mean())
+    assert (d <= 2).mean() >= 0.999, (d <= 2).mean()
+    assert np.all(np.abs(out_g - out_o) <= 2e-3 * np.abs(out_o) + 2e-4), np.abs(out_g - out_o).max()
     # A6: per-ray colour / depth / opacity, fp32, prefix-scan order vs serial order: 2e-4 absolute
     for name in ("rgb_rays", "depth_rays", "mask_rays"):
         assert np.allclose(g.last(name), o2.last(name), atol=2e-4, rtol=1e-3), name
@@ -221,9 +223,12 @@ def test_graph_training_and_render(core, oracle, gpu_dataset, small_seq, n_hidde
     trained weights (same injected jitter): PSNR between the two renders >= 35 dB, identical hit masks."""
     seq, obj = small_seq, small_seq.objects[0]
     R = 1024
-    g, o = make_pair(core, oracle, gpu_dataset, seq, obj, R, n_hidden=n_hidden)
-    if n_hidden == 2:
-        _impl_or_skip(g, 0)
+    try:
+        g, o = make_pair(core, oracle, gpu_dataset, seq, obj, R, n_hidden=n_hidden)
+    except core.MonError as e:
+        if "tcgen05" in str(e):
+            pytest.skip("n_hidden_layers=2 needs the tcgen05 kernel, not in this build")
+        raise
     l0 = g.train(1)
     l1 = g.train(150)
     assert g.step == 151 and np.isfinite(l1) and l1 < 0.7 * l0

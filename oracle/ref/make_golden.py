@@ -19,94 +19,9 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(Path(__file__).resolve().parent))
 
-BASE_JSON = """{
- "loss": {"otype": "Huber"},
- "optimizer": {"otype": "Ema", "decay": 0.95, "nested": {"otype": "ExponentialDecay", "decay_start": 20000, "decay_interval": 10000,
-   "decay_base": 0.33, "nested": {"otype": "Adam", "learning_rate": 1e-2, "beta1": 0.9, "beta2": 0.99, "epsilon": 1e-15, "l2_reg": 1e-6}}},
- "encoding": {"otype": "HashGrid", "n_levels": 16, "n_features_per_level": 2, "log2_hashmap_size": 16, "base_resolution": 16},
- "network": {"otype": "FullyFusedMLP", "activation": "ReLU", "output_activation": "None", "n_neurons": 64, "n_hidden_layers": %d}
-}"""
-
-
-class RefLib:
-    def __init__(self):
-        p = ROOT / "oracle" / "_ref" / "libmon_ref.so"
-        if not p.exists():
-            raise FileNotFoundError(f"{p}: build it with `make -C oracle/ref` where /root/reference exists")
-        L = C.CDLL(str(p))
-        vp = C.c_void_p
-        L.ref_create.restype = vp
-        L.ref_create.argtypes = [C.c_char_p, C.c_uint32]
-        L.ref_destroy.argtypes = [vp]
-        L.ref_last_error.restype = C.c_char_p
-        L.ref_last_error.argtypes = [vp]
-        L.ref_n_params.restype = C.c_uint32
-        L.ref_n_params.argtypes = [vp]
-        L.ref_get.argtypes = [vp, C.c_int, vp]
-        L.ref_set_params.argtypes = [vp, vp]
-        L.ref_encode.argtypes = [vp, vp, C.c_uint32, vp]
-        L.ref_forward.argtypes = [vp, vp, C.c_uint32, vp]
-        L.ref_backward.argtypes = [vp, vp, C.c_uint32]
-        L.ref_optimizer_step.argtypes = [vp, C.c_float]
-        L.ref_inference.argtypes = [vp, vp, C.c_uint32, vp]
-        L.ref_scene.argtypes = [vp, C.c_uint32, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, C.c_uint32, vp, vp, vp, C.c_uint8, C.c_int, C.c_uint32]
-        L.ref_train.argtypes = [vp, C.c_uint32, vp, vp, vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
-        L.ref_last.argtypes = [vp, C.c_int, vp]
-        self.L = L
-
-
-class RefModel:
-    def __init__(self, n_hidden: int = 1, seed: int = 1337, lib: RefLib | None = None):
-        self.lib = (lib or RefLib()).L
-        self.h = self.lib.ref_create((BASE_JSON % n_hidden).encode(), seed)
-        if not self.h:
-            raise RuntimeError("ref_create failed (see stderr)")
-        self.P = int(self.lib.ref_n_params(self.h))
-
-    def _ck(self, rc):
-        if rc != 0:
-            raise RuntimeError(self.lib.ref_last_error(self.h).decode())
-
-    def get(self, which: int) -> np.ndarray:
-        out = np.zeros(self.P, np.float32)
-        self._ck(self.lib.ref_get(self.h, which, out.ctypes.data))
-        return out
-
-    def set_params(self, master: np.ndarray):
-        m = np.ascontiguousarray(master, np.float32)
-        assert m.size == self.P
-        self._ck(self.lib.ref_set_params(self.h, m.ctypes.data))
-
-    def encode(self, pts: np.ndarray) -> np.ndarray:
-        pts = np.ascontiguousarray(pts, np.float32)
-        out = np.zeros((pts.shape[0], 32), np.uint16)
-        self._ck(self.lib.ref_encode(self.h, pts.ctypes.data, pts.shape[0], out.ctypes.data))
-        return out
-
-    def forward(self, pts: np.ndarray) -> np.ndarray:
-        pts = np.ascontiguousarray(pts, np.float32)
-        out = np.zeros((pts.shape[0], 16), np.uint16)
-        self._ck(self.lib.ref_forward(self.h, pts.ctypes.data, pts.shape[0], out.ctypes.data))
-        return out
-
-    def backward(self, dout_bits: np.ndarray):
-        d = np.ascontiguousarray(dout_bits, np.uint16)
-        self._ck(self.lib.ref_backward(self.h, d.ctypes.data, d.shape[0]))
-
-    def optimizer_step(self, loss_scale: float = 128.0):
-        self._ck(self.lib.ref_optimizer_step(self.h, loss_scale))
-
-    def inference(self, pts: np.ndarray) -> np.ndarray:
-        pts = np.ascontiguousarray(pts, np.float32)
-        out = np.zeros((pts.shape[0], 4), np.float32)
-        self._ck(self.lib.ref_inference(self.h, pts.ctypes.data, pts.shape[0], out.ctypes.data))
-        return out
-
-    def close(self):
-        if self.h:
-            self.lib.ref_destroy(self.h)
-            self.h = None
+from ref_binding import BASE_JSON, RefLib, RefModel  # noqa: E402,F401
 
 
 # ---- deterministic inputs shared with tests/test_golden_tcnn.py ---------------------------------

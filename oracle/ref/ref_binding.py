@@ -1,0 +1,136 @@
+"""ctypes binding of oracle/_ref/libmon_ref.so (the reference's vendored tiny-cuda-nn + oracle/ref/ref_harness.cu).
+TEST / BASELINE INFRASTRUCTURE ONLY: used by oracle/ref/make_golden.py, tests and bench.py --impl reference."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+LIB_PATH = ROOT / "oracle" / "_ref" / "libmon_ref.so"
+
+BASE_JSON = """{
+ "loss": {"otype": "Huber"},
+ "optimizer": {"otype": "Ema", "decay": 0.95, "nested": {"otype": "ExponentialDecay", "decay_start": 20000, "decay_interval": 10000,
+   "decay_base": 0.33, "nested": {"otype": "Adam", "learning_rate": 1e-2, "beta1": 0.9, "beta2": 0.99, "epsilon": 1e-15, "l2_reg": 1e-6}}},
+ "encoding": {"otype": "HashGrid", "n_levels": 16, "n_features_per_level": 2, "log2_hashmap_size": 16, "base_resolution": 16},
+ "network": {"otype": "FullyFusedMLP", "activation": "ReLU", "output_activation": "None", "n_neurons": 64, "n_hidden_layers": %d}
+}"""
+
+
+class RefLib:
+    def __init__(self):
+        p = LIB_PATH
+        if not p.exists():
+            raise FileNotFoundError(f"{p}: build it with `make -C oracle/ref` where /root/reference exists")
+        L = C.CDLL(str(p))
+        vp = C.c_void_p
+        L.ref_create.restype = vp
+        L.ref_create.argtypes = [C.c_char_p, C.c_uint32]
+        L.ref_destroy.argtypes = [vp]
+        L.ref_last_error.restype = C.c_char_p
+        L.ref_last_error.argtypes = [vp]
+        L.ref_n_params.restype = C.c_uint32
+        L.ref_n_params.argtypes = [vp]
+        L.ref_get.argtypes = [vp, C.c_int, vp]
+        L.ref_set_params.argtypes = [vp, vp]
+        L.ref_encode.argtypes = [vp, vp, C.c_uint32, vp]
+        L.ref_forward.argtypes = [vp, vp, C.c_uint32, vp]
+        L.ref_backward.argtypes = [vp, vp, C.c_uint32]
+        L.ref_optimizer_step.argtypes = [vp, C.c_float]
+        L.ref_inference.argtypes = [vp, vp, C.c_uint32, vp]
+        L.ref_scene.argtypes = [vp, C.c_uint32, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, C.c_uint32, vp, vp, vp, C.c_uint8, C.c_int, C.c_uint32]
+        L.ref_train.argtypes = [vp, C.c_uint32, vp, vp, vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
+        L.ref_last.argtypes = [vp, C.c_int, vp]
+        self.L = L
+
+
+class RefModel:
+    def __init__(self, n_hidden: int = 1, seed: int = 1337, lib: RefLib | None = None):
+        self.lib = (lib or RefLib()).L
+        self.h = self.lib.ref_create((BASE_JSON % n_hidden).encode(), seed)
+        if not self.h:
+            raise RuntimeError("ref_create failed (see stderr)")
+        self.P = int(self.lib.ref_n_params(self.h))
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RuntimeError(self.lib.ref_last_error(self.h).decode())
+
+    def get(self, which: int) -> np.ndarray:
+        out = np.zeros(self.P, np.float32)
+        self._ck(self.lib.ref_get(self.h, which, out.ctypes.data))
+        return out
+
+    def set_params(self, master: np.ndarray):
+        m = np.ascontiguousarray(master, np.float32)
+        assert m.size == self.P
+        self._ck(self.lib.ref_set_params(self.h, m.ctypes.data))
+
+    def encode(self, pts: np.ndarray) -> np.ndarray:
+        pts = np.ascontiguousarray(pts, np.float32)
+        out = np.zeros((pts.shape[0], 32), np.uint16)
+        self._ck(self.lib.ref_encode(self.h, pts.ctypes.data, pts.shape[0], out.ctypes.data))
+        return out
+
+    def forward(self, pts: np.ndarray) -> np.ndarray:
+        pts = np.ascontiguousarray(pts, np.float32)
+        out = np.zeros((pts.shape[0], 16), np.uint16)
+        self._ck(self.lib.ref_forward(self.h, pts.ctypes.data, pts.shape[0], out.ctypes.data))
+        return out
+
+    def backward(self, dout_bits: np.ndarray):
+        d = np.ascontiguousarray(dout_bits, np.uint16)
+        self._ck(self.lib.ref_backward(self.h, d.ctypes.data, d.shape[0]))
+
+    def optimizer_step(self, loss_scale: float = 128.0):
+        self._ck(self.lib.ref_optimizer_step(self.h, loss_scale))
+
+    def inference(self, pts: np.ndarray) -> np.ndarray:
+        pts = np.ascontiguousarray(pts, np.float32)
+        out = np.zeros((pts.shape[0], 4), np.float32)
+        self._ck(self.lib.ref_inference(self.h, pts.ctypes.data, pts.shape[0], out.ctypes.data))
+        return out
+
+
+    # ---- whole-iteration loop in the reference's shape (ref_harness.cu: ref_scene / ref_train)
+    def scene(self, rgb_list, inst_list, depth_list, poses, H, W, K, boxes_rows, Tow, bmin, bmax, instance_id, use_depth, rays_per_batch):
+        n = len(rgb_list)
+        self._keep = ([np.ascontiguousarray(a, np.uint8) for a in rgb_list], [np.ascontiguousarray(a, np.uint8) for a in inst_list],
+                      [np.ascontiguousarray(a, np.float32) for a in depth_list])
+        vp = C.c_void_p
+        rgb_p = (vp * n)(*[a.ctypes.data for a in self._keep[0]])
+        inst_p = (vp * n)(*[a.ctypes.data for a in self._keep[1]])
+        dep_p = (vp * n)(*[a.ctypes.data for a in self._keep[2]])
+        poses16 = np.concatenate([np.ascontiguousarray(np.asarray(p, np.float32).reshape(4, 4).T).reshape(16) for p in poses]).astype(np.float32)
+        rows = np.ascontiguousarray(np.array(list(boxes_rows), dtype=np.uint32).reshape(-1, 5))
+        Kf = np.ascontiguousarray(K, np.float32)
+        tow = np.ascontiguousarray(np.asarray(Tow, np.float32).reshape(4, 4).T).reshape(16)
+        lo, hi = np.ascontiguousarray(bmin, np.float32), np.ascontiguousarray(bmax, np.float32)
+        self.R = rays_per_batch
+        self._ck(self.lib.ref_scene(self.h, n, rgb_p, inst_p, dep_p, poses16.ctypes.data, H, W, Kf.ctypes.data, rows.ctypes.data, rows.shape[0],
+                                    tow.ctypes.data, lo.ctypes.data, hi.ctypes.data, instance_id, int(use_depth), rays_per_batch))
+
+    def train(self, iters: int, inject=None):
+        """Returns (device_ms, wall_ms, loss, n_in) for `iters` iterations of Train_Step's loop body."""
+        dm, wm, loss, n_in = C.c_float(0), C.c_float(0), C.c_float(0), C.c_uint32(0)
+        if inject is None:
+            xy = col = dt = None
+        else:
+            keep = [np.ascontiguousarray(a, np.float32) for a in inject]
+            xy, col, dt = [a.ctypes.data for a in keep]
+        self._ck(self.lib.ref_train(self.h, iters, xy, col, dt, C.byref(dm), C.byref(wm), C.byref(loss), C.byref(n_in)))
+        return dm.value, wm.value, loss.value, n_in.value
+
+    def last(self, which: int, n: int) -> np.ndarray:
+        out = np.zeros(n, np.float32)
+        self._ck(self.lib.ref_last(self.h, which, out.ctypes.data))
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.ref_destroy(self.h)
+            self.h = None
+
+

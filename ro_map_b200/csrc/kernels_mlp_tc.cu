@@ -1,0 +1,492 @@
+// kernels_mlp_tc.cu — the fused tiny-MLP kernels on Blackwell tensor cores (tcgen05.mma, accumulators in TMEM).
+//
+// One persistent CTA (128 threads = 4 warps) walks tiles of 128 sample points = 4 rays x 32 samples.  TMEM lane i
+// of the accumulator is sample i of the tile, and tcgen05.ld hands TMEM lane (32*warp + lane) to thread `lane` of
+// warp `warp`: a warp owns exactly one ray and each lane one of its 32 samples — the same mapping the
+// warp-parallel volume renderer (render_math.cuh) wants, so the network output never leaves the SM between the
+// last GEMM and compositing.  Per tile, for the training kernel:
+//
+//   enc tile (global, point-major fp16) --> smem [128 x 32]  K-major SWIZZLE_64B
+//   MMA1  D[128x64]   = enc  . W_in^T            (K = 32)      epilogue: ReLU, fp16  --> hid  smem SW128
+//   MMA2  O[128x16]   = hid  . W_out^T           (K = 64)      epilogue: sigmoid/exp, warp-scan compositing,
+//                                                              loss, dL/dout fp16    --> dout smem (core layout)
+//   MMA3  D[128x64]   = dout . W_out             (K = 16)      epilogue: ReLU mask, fp16 --> dhid smem SW128
+//   MMA4  E[128x32]   = dhid . W_in              (K = 64)      epilogue: fp16 --> d_enc global
+//   MMA5  G1[128x16] += [hid|dhid]^T . dout      (K = 128 points; rows 0-63   = dW_out^T)
+//   MMA6  G2[128x32] += [hid|dhid]^T . enc       (K = 128 points; rows 64-127 = dW_in)
+//
+// MMA5/6 read the activation tiles that MMA2/MMA4 consumed K-major through MN-major descriptors (see tc05.cuh), so
+// the weight gradients need no transpose and accumulate in TMEM across ALL tiles of the CTA; they are read out
+// once at the end into the per-CTA partial row that the optimizer kernel sums in a fixed order.
+// Replaces kernel_mlp_fused, VolumeRender, VolumeRenderGradient_No_Compacted, kernel_mlp_fused_backward and the
+// three CUTLASS GEMMs of FullyFusedMLP::backward_impl (TCNN/src/fully_fused_mlp.cu:150-259,499-557,736-836;
+// MON/Core/src/nerf_model.cu:735-954) and removes their 16.8 + 4.2 + 4.2 + 16.8 MB of activation round trips.
+// fp16 operands, fp32 accumulation (the reference accumulates in fp16: tolerances, not bit-exactness).
+#include "mon_kernels.h"
+#include "render_math.cuh"
+#include "tc05.cuh"
+
+using namespace tc05;
+
+#define TC_THREADS 128
+#define TC_TMEM_COLS 256
+// TMEM column map
+#define TC_COL_D 0     // 64: hidden pre-activation, later dL/dhidden
+#define TC_COL_O 64    // 16: network output
+#define TC_COL_E 96    // 32: dL/dencoding
+#define TC_COL_G1 128  // 16: [hid|dhid]^T . dout
+#define TC_COL_G2 160  // 32: [hid|dhid]^T . enc
+#define TC_COL_H2 192  // 64: second hidden layer pre-activation / its gradient (n_hidden_layers == 2)
+
+// shared memory map (bytes from a 1024-aligned base)
+#define SM_ENC 0         //  8192  [128][32]  SW64
+#define SM_HID 8192      // 16384  [128][64]  SW128   (hid | dhid must be adjacent: MN-major LBO = 16384)
+#define SM_DHID 24576    // 16384
+#define SM_DOUT 40960    //  4096  [128][16]  core layout (2 chunks per row)
+#define SM_WIN 45056     //  4096  B of MMA1: [64][32] SW64
+#define SM_WINT 49152    //  4096  B of MMA4: [32][64] SW128
+#define SM_WOUT 53248    //  2048  B of MMA2: [16][64] SW128
+#define SM_WOUTT 55296   //  2048  B of MMA3: [64][16] core layout
+#define SM_BAR 57344     //  mbarrier (8) + tmem base (4)
+#define SM_TOTAL 57600
+// dynamic request: padded so that at most two CTAs fit per SM (2 x 256 TMEM columns = the whole TMEM)
+#define TC_SMEM_BYTES (100 * 1024)
+
+static constexpr uint32_t IDESC_64_KK = make_idesc(128, 64, 0, 0);
+static constexpr uint32_t IDESC_16_KK = make_idesc(128, 16, 0, 0);
+static constexpr uint32_t IDESC_32_KK = make_idesc(128, 32, 0, 0);
+static constexpr uint32_t IDESC_16_MM = make_idesc(128, 16, 1, 1);
+static constexpr uint32_t IDESC_32_MM = make_idesc(128, 32, 1, 1);
+
+struct TcCtx {
+    unsigned char* sm;     // 1024-aligned shared base
+    uint32_t sm_addr;      // its shared-space address
+    uint64_t* bar;
+    uint32_t tmem;         // TMEM base (lane 0, column 0 of the allocation)
+    uint32_t phase;        // mbarrier parity of the next wait
+    uint32_t tid, lane, warp;
+};
+
+__device__ __forceinline__ void tc_setup(TcCtx& c, unsigned char* raw) {
+    c.tid = threadIdx.x; c.lane = c.tid & 31; c.warp = c.tid >> 5;
+    const uint32_t raw_addr = smem_u32(raw);
+    const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+    c.sm = raw + pad;
+    c.sm_addr = raw_addr + pad;
+    c.bar = reinterpret_cast<uint64_t*>(c.sm + SM_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c.sm + SM_BAR + 8);
+    if (c.tid == 0) { mbar_init(c.bar, 1); mbar_fence_init(); }
+    if (c.warp == 0) { __syncwarp(); tmem_alloc(tmem_slot, TC_TMEM_COLS); }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    c.tmem = *tmem_slot;
+    c.phase = 0;
+}
+
+__device__ __forceinline__ void tc_teardown(TcCtx& c) {
+    fence_before_sync();
+    __syncthreads();
+    if (c.warp == 0) { __syncwarp(); tmem_dealloc(c.tmem, TC_TMEM_COLS); }
+}
+
+// weights -> shared memory in the four operand layouts (params: W_in [64][32] | W_out [16][64], row-major fp16)
+__device__ __forceinline__ void tc_load_weights(const TcCtx& c, const __half* __restrict__ params) {
+    const __half* Win = params;
+    const __half* Wout = params + 64 * 32;
+    for (uint32_t i = c.tid; i < 64 * 4; i += TC_THREADS) {           // W_in rows (N = 64), 4 chunks of 8 (K = 32)
+        const uint32_t n = i >> 2, ch = i & 3;
+        *reinterpret_cast<uint4*>(c.sm + SM_WIN + sw64_off(n, ch)) = *reinterpret_cast<const uint4*>(Win + n * 32 + ch * 8);
+    }
+    for (uint32_t i = c.tid; i < 16 * 8; i += TC_THREADS) {           // W_out rows (N = 16), 8 chunks (K = 64)
+        const uint32_t n = i >> 3, ch = i & 7;
+        *reinterpret_cast<uint4*>(c.sm + SM_WOUT + sw128_off(n, ch)) = *reinterpret_cast<const uint4*>(Wout + n * 64 + ch * 8);
+    }
+    for (uint32_t i = c.tid; i < 32 * 64; i += TC_THREADS) {          // W_in^T: row n = input k, column j = neuron
+        const uint32_t n = i >> 6, j = i & 63;
+        *reinterpret_cast<__half*>(c.sm + SM_WINT + sw128_off(n, j >> 3) + (j & 7) * 2) = Win[j * 32 + n];
+    }
+    for (uint32_t i = c.tid; i < 64 * 16; i += TC_THREADS) {          // W_out^T: row n = neuron j, column o = output
+        const uint32_t n = i >> 4, o = i & 15;
+        *reinterpret_cast<__half*>(c.sm + SM_WOUTT + core_off(n, o >> 3, 2) + (o & 7) * 2) = Wout[o * 64 + n];
+    }
+}
+
+// stage one 128 x 32 fp16 tile of encodings (64 B per point, contiguous) into the SW64 operand layout;
+// rows >= n_valid are zero-filled
+__device__ __forceinline__ void tc_stage_enc(const TcCtx& c, const __half* __restrict__ enc_tile, uint32_t n_valid) {
+    const uint32_t row = c.tid;
+    uint4 v[4];
+    if (row < n_valid) {
+        const uint4* src = reinterpret_cast<const uint4*>(enc_tile + (size_t)row * MON_IN);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) v[ch] = __ldg(src + ch);
+    } else {
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) v[ch] = make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<uint4*>(c.sm + SM_ENC + sw64_off(row, ch)) = v[ch];
+}
+
+// make the CTA's shared-memory writes visible to the tensor core, then let thread 0 issue
+#define TC_PUBLISH_AND_SYNC()  \
+    do {                       \
+        fence_smem_to_async(); \
+        fence_before_sync();   \
+        __syncthreads();       \
+    } while (0)
+
+#define TC_WAIT(c)                      \
+    do {                                \
+        __syncwarp();                   \
+        mbar_wait((c).bar, (c).phase);  \
+        (c).phase ^= 1u;                \
+        fence_after_sync();             \
+    } while (0)
+
+// MMA1: D = enc . W_in^T
+__device__ __forceinline__ void tc_issue_layer_in(const TcCtx& c) {
+    fence_after_sync();
+#pragma unroll
+    for (uint32_t k = 0; k < 2; ++k)
+        mma_f16_ss(c.tmem + TC_COL_D, make_desc(c.sm_addr + SM_ENC + k * 32, 16, 512, SWZ_64B),
+                   make_desc(c.sm_addr + SM_WIN + k * 32, 16, 512, SWZ_64B), IDESC_64_KK, k);
+    commit(c.bar);
+}
+// MMA2: O = hid . W_out^T
+__device__ __forceinline__ void tc_issue_layer_out(const TcCtx& c) {
+    fence_after_sync();
+#pragma unroll
+    for (uint32_t k = 0; k < 4; ++k)
+        mma_f16_ss(c.tmem + TC_COL_O, make_desc(c.sm_addr + SM_HID + k * 32, 16, 1024, SWZ_128B),
+                   make_desc(c.sm_addr + SM_WOUT + k * 32, 16, 1024, SWZ_128B), IDESC_16_KK, k);
+    commit(c.bar);
+}
+
+// epilogue of MMA1: ReLU -> fp16 -> hid tile; returns the bitmask of positive hidden units of this thread's row
+__device__ __forceinline__ uint64_t tc_epilogue_hidden(const TcCtx& c) {
+    const uint32_t row = c.tid;
+    const uint32_t taddr = c.tmem + ((c.warp * 32u) << 16) + TC_COL_D;
+    uint64_t mask = 0;
+#pragma unroll
+    for (uint32_t half_i = 0; half_i < 2; ++half_i) {
+        float v[32];
+        tmem_ld32(taddr + half_i * 32, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (uint32_t ch = 0; ch < 4; ++ch) {
+            uint32_t packed[4];
+#pragma unroll
+            for (uint32_t q = 0; q < 4; ++q) {
+                const __half2 h = __floats2half2_rn(fmaxf(v[ch * 8 + 2 * q], 0.0f), fmaxf(v[ch * 8 + 2 * q + 1], 0.0f));
+                packed[q] = *reinterpret_cast<const uint32_t*>(&h);
+                if (__half2float(__low2half(h)) > 0.0f) mask |= 1ull << (half_i * 32 + ch * 8 + 2 * q);
+                if (__half2float(__high2half(h)) > 0.0f) mask |= 1ull << (half_i * 32 + ch * 8 + 2 * q + 1);
+            }
+            *reinterpret_cast<uint4*>(c.sm + SM_HID + sw128_off(row, half_i * 4 + ch)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        }
+    }
+    return mask;
+}
+
+// ------------------------------------------------------------------------------------------ training
+__global__ void __launch_bounds__(TC_THREADS, 2)
+k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
+    extern __shared__ unsigned char smem_raw[];
+    if (b.ctrl->skip) return;
+    TcCtx c;
+    tc_setup(c, smem_raw);
+    tc_load_weights(c, b.params);
+    // the upper half of every dout row (outputs 4..15 and the second K chunk) stays zero for the whole kernel
+    for (uint32_t i = c.tid; i < 4096 / 16; i += TC_THREADS) reinterpret_cast<uint4*>(c.sm + SM_DOUT)[i] = make_uint4(0, 0, 0, 0);
+
+    const float kscale = lc.loss_scale / (float)b.R;
+    const uint32_t iter = b.ctrl->iter - 1;
+    const uint32_t n_tiles = (b.R + 3) / 4;
+    uint32_t tiles_done = 0;
+
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tiles_done) {
+        const uint32_t ray = tile * 4 + c.warp;
+        const bool ray_ok = ray < b.R;
+        const uint32_t pt = ray * 32 + c.lane;
+        // ---- stage encodings, MMA1
+        tc_stage_enc(c, b.enc + (size_t)tile * 128 * MON_IN, min(128u, (b.R - tile * 4) * 32));
+        TC_PUBLISH_AND_SYNC();
+        if (c.tid == 0) tc_issue_layer_in(c);
+        // per-ray inputs of the renderer, fetched while the tensor core works
+        MonRay r;
+        RayTargets rt;
+        float xi = 1.0f;
+        if (ray_ok) {
+            r = b.rays[ray];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { rt.tgt[k] = b.target[ray * 3 + k]; rt.bg[k] = b.bg[ray * 3 + k]; }
+            rt.tgt_depth = b.target_depth[ray];
+            rt.is_obj = b.ray_inst[ray] == 1;
+            xi = mon_rand(b.inj_dt, b.seed, iter, 2, pt);
+        } else {
+            r.tmin = 0.0f; r.tmax = 1.0f; r.d_norm = 1.0f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { r.o[k] = 0.0f; r.d[k] = 0.0f; rt.tgt[k] = 0.0f; rt.bg[k] = 0.0f; }
+            rt.tgt_depth = 0.0f; rt.is_obj = false;
+        }
+        const float t = mon_sample_t(r, c.lane, xi, 32.0f);
+        TC_WAIT(c);
+        // ---- hidden epilogue, MMA2
+        const uint64_t relu_mask = tc_epilogue_hidden(c);
+        TC_PUBLISH_AND_SYNC();
+        if (c.tid == 0) tc_issue_layer_out(c);
+        TC_WAIT(c);
+        // ---- output epilogue: compositing, loss, dL/dout
+        {
+            float o16[16];
+            tmem_ld16(c.tmem + ((c.warp * 32u) << 16) + TC_COL_O, o16);
+            tmem_wait_ld();
+            float o[4], go[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = __half2float(__float2half_rn(o16[k]));   // the network output is fp16
+            const RayResult rr = warp_render_loss_grad(o, t, c.lane, rt, kscale, lc, go);
+            if (ray_ok && c.lane == 0) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) b.rgb_rays[ray * 3 + k] = rr.rgb[k];
+                b.depth_rays[ray] = rr.depth; b.mask_rays[ray] = rr.mask; b.loss[ray] = rr.loss;
+            }
+            if (!ray_ok) { go[0] = go[1] = go[2] = go[3] = 0.0f; }
+            const __half2 g01 = __floats2half2_rn(go[0], go[1]), g23 = __floats2half2_rn(go[2], go[3]);
+            *reinterpret_cast<uint2*>(c.sm + SM_DOUT + core_off(c.tid, 0, 2)) =
+                make_uint2(*reinterpret_cast<const uint32_t*>(&g01), *reinterpret_cast<const uint32_t*>(&g23));
+            if (b.dbg_out && ray_ok) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) b.dbg_out[(size_t)pt * 4 + k] = o[k];
+                b.dbg_dout[(size_t)pt * 4 + 0] = __low2float(g01); b.dbg_dout[(size_t)pt * 4 + 1] = __high2float(g01);
+                b.dbg_dout[(size_t)pt * 4 + 2] = __low2float(g23); b.dbg_dout[(size_t)pt * 4 + 3] = __high2float(g23);
+            }
+        }
+        // ---- MMA3: dL/dhidden = dout . W_out
+        TC_PUBLISH_AND_SYNC();
+        if (c.tid == 0) {
+            fence_after_sync();
+            mma_f16_ss(c.tmem + TC_COL_D, make_desc(c.sm_addr + SM_DOUT, 128, 256, SWZ_NONE),
+                       make_desc(c.sm_addr + SM_WOUTT, 128, 256, SWZ_NONE), IDESC_64_KK, 0);
+            commit(c.bar);
+        }
+        TC_WAIT(c);
+        {   // ReLU mask, fp16 -> dhid tile
+            const uint32_t taddr = c.tmem + ((c.warp * 32u) << 16) + TC_COL_D;
+#pragma unroll
+            for (uint32_t half_i = 0; half_i < 2; ++half_i) {
+                float v[32];
+                tmem_ld32(taddr + half_i * 32, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (uint32_t ch = 0; ch < 4; ++ch) {
+                    uint32_t packed[4];
+#pragma unroll
+                    for (uint32_t q = 0; q < 4; ++q) {
+                        const uint32_t bit = half_i * 32 + ch * 8 + 2 * q;
+                        const float lo = ((relu_mask >> bit) & 1ull) ? v[ch * 8 + 2 * q] : 0.0f;
+                        const float hi = ((relu_mask >> (bit + 1)) & 1ull) ? v[ch * 8 + 2 * q + 1] : 0.0f;
+                        const __half2 h = __floats2half2_rn(lo, hi);
+                        packed[q] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                    *reinterpret_cast<uint4*>(c.sm + SM_DHID + sw128_off(c.tid, half_i * 4 + ch)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                }
+            }
+        }
+        // ---- MMA4 (dL/dencoding) + MMA5/6 (weight gradients, accumulated in TMEM across tiles)
+        TC_PUBLISH_AND_SYNC();
+        if (c.tid == 0) {
+            fence_after_sync();
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k)
+                mma_f16_ss(c.tmem + TC_COL_E, make_desc(c.sm_addr + SM_DHID + k * 32, 16, 1024, SWZ_128B),
+                           make_desc(c.sm_addr + SM_WINT + k * 32, 16, 1024, SWZ_128B), IDESC_32_KK, k);
+            const uint32_t acc0 = tiles_done ? 1u : 0u;
+#pragma unroll
+            for (uint32_t kk = 0; kk < 8; ++kk) {   // 16 points per MMA
+                const uint64_t a = make_desc(c.sm_addr + SM_HID + kk * 2048, 16384, 1024, SWZ_128B);
+                mma_f16_ss(c.tmem + TC_COL_G1, a, make_desc(c.sm_addr + SM_DOUT + kk * 512, 256, 128, SWZ_NONE), IDESC_16_MM, acc0 | kk);
+                mma_f16_ss(c.tmem + TC_COL_G2, a, make_desc(c.sm_addr + SM_ENC + kk * 1024, 16, 512, SWZ_64B), IDESC_32_MM, acc0 | kk);
+            }
+            commit(c.bar);
+        }
+        TC_WAIT(c);
+        {   // dL/dencoding: fp16, one 64-byte row per thread
+            float v[32];
+            tmem_ld32(c.tmem + ((c.warp * 32u) << 16) + TC_COL_E, v);
+            tmem_wait_ld();
+            if (ray_ok) {
+                uint4* dst = reinterpret_cast<uint4*>(b.d_enc + (size_t)pt * MON_IN);
+#pragma unroll
+                for (uint32_t ch = 0; ch < 4; ++ch) {
+                    uint32_t packed[4];
+#pragma unroll
+                    for (uint32_t q = 0; q < 4; ++q) {
+                        const __half2 h = __floats2half2_rn(v[ch * 8 + 2 * q], v[ch * 8 + 2 * q + 1]);
+                        packed[q] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                    dst[ch] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                }
+            }
+        }
+        // the next tile overwrites enc / hid / dout: every MMA that reads them has completed (the wait above)
+    }
+
+    // ---- weight gradients: TMEM -> this CTA's partial row (W_in [64][32] | W_out [16][64])
+    float* partial = b.mlp_partials + (size_t)blockIdx.x * n_mlp;
+    if (tiles_done == 0) {
+        for (uint32_t i = c.tid; i < n_mlp; i += TC_THREADS) partial[i] = 0.0f;
+    } else {
+        if (c.warp < 2) {        // G1 rows 0..63: (hid^T . dout)[j][o] = dW_out[o][j]
+            float v[16];
+            tmem_ld16(c.tmem + ((c.warp * 32u) << 16) + TC_COL_G1, v);
+            tmem_wait_ld();
+            const uint32_t j = c.tid;
+#pragma unroll
+            for (uint32_t o = 0; o < 16; ++o) partial[64 * 32 + o * 64 + j] = v[o];
+        } else {                 // G2 rows 64..127: (dhid^T . enc)[j][k] = dW_in[j][k]
+            float v[32];
+            tmem_ld32(c.tmem + ((c.warp * 32u) << 16) + TC_COL_G2, v);
+            tmem_wait_ld();
+            const uint32_t j = c.tid - 64;
+#pragma unroll
+            for (uint32_t k = 0; k < 32; ++k) partial[j * 32 + k] = v[k];
+        }
+    }
+    tc_teardown(c);
+}
+
+// ------------------------------------------------------------------------------------------ inference
+// raw network output (4 logits per point) for the density lattice and the parity hooks
+__global__ void __launch_bounds__(TC_THREADS, 2)
+k_mlp_infer_tc(uint32_t n_points, const __half* __restrict__ params, const __half* __restrict__ enc, float* __restrict__ out4) {
+    extern __shared__ unsigned char smem_raw[];
+    TcCtx c;
+    tc_setup(c, smem_raw);
+    tc_load_weights(c, params);
+    const uint32_t n_tiles = (n_points + 127) / 128;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t pt = tile * 128 + c.tid;
+        tc_stage_enc(c, enc + (size_t)tile * 128 * MON_IN, min(128u, n_points - tile * 128));
+        TC_PUBLISH_AND_SYNC();
+        if (c.tid == 0) tc_issue_layer_in(c);
+        TC_WAIT(c);
+        (void)tc_epilogue_hidden(c);
+        TC_PUBLISH_AND_SYNC();
+        if (c.tid == 0) tc_issue_layer_out(c);
+        TC_WAIT(c);
+        float o16[16];
+        tmem_ld16(c.tmem + ((c.warp * 32u) << 16) + TC_COL_O, o16);
+        tmem_wait_ld();
+        if (pt < n_points) {
+            float4 o;
+            o.x = __half2float(__float2half_rn(o16[0])); o.y = __half2float(__float2half_rn(o16[1]));
+            o.z = __half2float(__float2half_rn(o16[2])); o.w = __half2float(__float2half_rn(o16[3]));
+            reinterpret_cast<float4*>(out4)[pt] = o;
+        }
+    }
+    tc_teardown(c);
+}
+
+// test render (VolumeRender_Render, nerf_model.cu:1134-1229): per ray S2/32 tiles with a carried compositing state
+__global__ void __launch_bounds__(TC_THREADS, 2)
+k_mlp_render_tc(uint32_t n_rays, uint32_t S2, const MonRay* __restrict__ rays, const int* __restrict__ in_box,
+                const float* __restrict__ jitter, uint32_t seed, uint32_t iter, const __half* __restrict__ params,
+                const __half* __restrict__ enc, float bgc, float* __restrict__ rgb, float* __restrict__ depth, float* __restrict__ mask) {
+    extern __shared__ unsigned char smem_raw[];
+    TcCtx c;
+    tc_setup(c, smem_raw);
+    tc_load_weights(c, params);
+    const uint32_t n_groups = (n_rays + 3) / 4, chunks = S2 / 32;
+    for (uint32_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        const uint32_t ray = grp * 4 + c.warp;
+        const bool ray_ok = ray < n_rays;
+        const bool hit = ray_ok && in_box[ray] != 0;
+        MonRay r;
+        if (ray_ok) r = rays[ray];
+        else { r.tmin = 0.0f; r.tmax = 1.0f; r.d_norm = 1.0f; }
+        RenderCarry cr; cr.T = 1.0f; cr.C[0] = cr.C[1] = cr.C[2] = 0.0f; cr.D = 0.0f; cr.last_t = 0.0f;
+        for (uint32_t chunk = 0; chunk < chunks; ++chunk) {
+            // this thread stages the row of its own sample: point (ray, chunk*32 + lane)
+            uint4 v[4];
+            const uint32_t pt = ray * S2 + chunk * 32 + c.lane;
+            if (hit) {
+                const uint4* src = reinterpret_cast<const uint4*>(enc + (size_t)pt * MON_IN);
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) v[ch] = __ldg(src + ch);
+            } else {
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) v[ch] = make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<uint4*>(c.sm + SM_ENC + sw64_off(c.tid, ch)) = v[ch];
+            TC_PUBLISH_AND_SYNC();
+            if (c.tid == 0) tc_issue_layer_in(c);
+            TC_WAIT(c);
+            (void)tc_epilogue_hidden(c);
+            TC_PUBLISH_AND_SYNC();
+            if (c.tid == 0) tc_issue_layer_out(c);
+            TC_WAIT(c);
+            float o16[16];
+            tmem_ld16(c.tmem + ((c.warp * 32u) << 16) + TC_COL_O, o16);
+            tmem_wait_ld();
+            float o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = __half2float(__float2half_rn(o16[k]));
+            const uint32_t n = chunk * 32 + c.lane;
+            const float xi = hit ? mon_rand(jitter, seed, iter, 3, pt) : 1.0f;
+            const float t = mon_sample_t(r, n, xi, (float)S2);
+            warp_render_chunk(o, t, c.lane, cr);
+        }
+        if (ray_ok && c.lane == 0) {
+            if (hit && 1.0f - cr.T > 0.5f) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) rgb[ray * 3 + k] = cr.C[k] + cr.T * bgc;
+                depth[ray] = __fdiv_rn(cr.D, r.d_norm);
+                mask[ray] = 1.0f;
+            } else {
+                rgb[ray * 3] = rgb[ray * 3 + 1] = rgb[ray * 3 + 2] = bgc; depth[ray] = 0.0f; mask[ray] = 0.0f;
+            }
+        }
+    }
+    tc_teardown(c);
+}
+
+// ------------------------------------------------------------------------------------------ launchers
+template <typename K>
+static cudaError_t tc_prepare(K kernel) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+}
+
+cudaError_t mon_launch_mlp_train_tc(const MonBatch& b, const MonLossCfg& lc, uint32_t n_hidden, uint32_t n_mlp, uint32_t n_ctas, cudaStream_t st) {
+    if (n_hidden != 1) return cudaErrorNotSupported;
+    static cudaError_t prep = tc_prepare(k_mlp_train_tc);
+    if (prep != cudaSuccess) return prep;
+    k_mlp_train_tc<<<n_ctas, TC_THREADS, TC_SMEM_BYTES, st>>>(b, lc, n_mlp);
+    return cudaGetLastError();
+}
+
+cudaError_t mon_launch_mlp_infer_tc(uint32_t n_points, uint32_t n_hidden, const __half* params, const __half* enc, float* out4, cudaStream_t st) {
+    if (n_hidden != 1) return cudaErrorNotSupported;
+    static cudaError_t prep = tc_prepare(k_mlp_infer_tc);
+    if (prep != cudaSuccess) return prep;
+    uint32_t ctas = (n_points + 127) / 128;
+    if (ctas > 296) ctas = 296;
+    if (ctas == 0) ctas = 1;
+    k_mlp_infer_tc<<<ctas, TC_THREADS, TC_SMEM_BYTES, st>>>(n_points, params, enc, out4);
+    return cudaGetLastError();
+}
+
+cudaError_t mon_launch_mlp_render_tc(uint32_t n_rays, uint32_t S2, uint32_t n_hidden, const MonRay* rays, const int* in_box, const float* jitter,
+                                     uint32_t seed, uint32_t iter, const __half* params, const __half* enc, float bgc,
+                                     float* rgb, float* depth, float* mask, cudaStream_t st) {
+    if (n_hidden != 1) return cudaErrorNotSupported;
+    static cudaError_t prep = tc_prepare(k_mlp_render_tc);
+    if (prep != cudaSuccess) return prep;
+    uint32_t ctas = (n_rays + 3) / 4;
+    if (ctas > 296) ctas = 296;
+    if (ctas == 0) ctas = 1;
+    k_mlp_render_tc<<<ctas, TC_THREADS, TC_SMEM_BYTES, st>>>(n_rays, S2, rays, in_box, jitter, seed, iter, params, enc, bgc, rgb, depth, mask);
+    return cudaGetLastError();
+}

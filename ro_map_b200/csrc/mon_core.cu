@@ -994,8 +994,15 @@ int mon_object_render(mon_object* o, mon_bbox2d box, const float Twc[16], int us
         const uint32_t iter_fixed = rc_id * 4099u + t;
         mon_launch_encode_forward(o->grid, nr * S2, S2, o->r_rays + r0, o->r_inbox + r0, jit, o->seed, nullptr, 3, iter_fixed,
                                   o->scene.bmin, o->scene.bmax, params + o->n_mlp, o->r_enc, st);
-        cudaError_t e = mon_launch_mlp_render_wmma(nr, S2, o->r_rays + r0, o->r_inbox + r0, jit, o->seed, iter_fixed, params,
-                                                   o->r_enc, 1.0f, o->r_rgb + (size_t)r0 * 3, o->r_depth + r0, o->r_mask + r0, st);
+        cudaError_t e;
+#ifdef MON_HAVE_TC
+        if (o->mlp_impl == 0)
+            e = mon_launch_mlp_render_tc(nr, S2, o->cfg.n_hidden_layers, o->r_rays + r0, o->r_inbox + r0, jit, o->seed, iter_fixed, params,
+                                         o->r_enc, 1.0f, o->r_rgb + (size_t)r0 * 3, o->r_depth + r0, o->r_mask + r0, st);
+        else
+#endif
+        e = mon_launch_mlp_render_wmma(nr, S2, o->r_rays + r0, o->r_inbox + r0, jit, o->seed, iter_fixed, params,
+                                       o->r_enc, 1.0f, o->r_rgb + (size_t)r0 * 3, o->r_depth + r0, o->r_mask + r0, st);
         if (e != cudaSuccess) return fail(MON_ERR_CUDA, "render launch: %s", cudaGetErrorString(e));
         o->launches += 2;
     }

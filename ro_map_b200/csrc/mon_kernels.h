@@ -28,6 +28,9 @@ cudaError_t mon_launch_mlp_train_tc(const MonBatch& b, const MonLossCfg& lc, uin
                                     uint32_t n_ctas, cudaStream_t st);
 cudaError_t mon_launch_mlp_infer_tc(uint32_t n_points, uint32_t n_hidden, const __half* params, const __half* enc,
                                     float* out4, cudaStream_t st);
+cudaError_t mon_launch_mlp_render_tc(uint32_t n_rays, uint32_t S2, uint32_t n_hidden, const MonRay* rays, const int* in_box, const float* jitter,
+                                     uint32_t seed, uint32_t iter, const __half* params, const __half* enc, float bgc,
+                                     float* rgb, float* depth, float* mask, cudaStream_t st);
 
 // kernels_optim.cu
 void mon_launch_init_grid(uint64_t state, uint64_t inc, uint32_t n, float* out, cudaStream_t st);

@@ -15,6 +15,10 @@
 //   MMA5  G1[128x16] += [hid|dhid]^T . dout      (K = 128 points; rows 0-63   = dW_out^T)
 //   MMA6  G2[128x32] += [hid|dhid]^T . enc       (K = 128 points; rows 64-127 = dW_in)
 //
+// With n_hidden_layers == 2 ("2x64") the 64x64 hidden GEMM H2 = relu(H1 . W_h^T), its dgrad dH1 = (dH2 . W_h) * relu'
+// and its weight gradient G3[128x64] += [H2|dH2]^T . H1 (rows 64-127 = dW_h) are inserted; dW_in then comes from
+// [H1|dH1]^T . enc.
+//
 // MMA5/6 read the activation tiles that MMA2/MMA4 consumed K-major through MN-major descriptors (see tc05.cuh), so
 // the weight gradients need no transpose and accumulate in TMEM across ALL tiles of the CTA; they are read out
 // once at the end into the per-CTA partial row that the optimizer kernel sums in a fixed order.
@@ -48,15 +52,21 @@ using namespace tc05;
 #define SM_WOUT 53248    //  2048  B of MMA2: [16][64] SW128
 #define SM_WOUTT 55296   //  2048  B of MMA3: [64][16] core layout
 #define SM_BAR 57344     //  mbarrier (8) + tmem base (4)
-#define SM_TOTAL 57600
-// dynamic request: padded so that at most two CTAs fit per SM (2 x 256 TMEM columns = the whole TMEM)
-#define TC_SMEM_BYTES (100 * 1024)
+// n_hidden_layers == 2 only: the first hidden layer's tiles and the 64x64 weight in both orientations
+#define SM_H1 58368      // 16384  [128][64]  SW128   (H1 | dH1 adjacent, like hid | dhid)
+#define SM_DH1 74752     // 16384
+#define SM_WH 91136      //  8192  B of the hidden GEMM: W_h [64][64] SW128
+#define SM_WHT 99328     //  8192  B of its dgrad: W_h^T [64][64] SW128
+#define SM_TOTAL 107520
+// dynamic request (incl. 1 KB alignment slack): two CTAs fit per SM (2 x 256 TMEM columns = the whole TMEM), a third cannot
+#define TC_SMEM_BYTES (108 * 1024)
 
 static constexpr uint32_t IDESC_64_KK = make_idesc(128, 64, 0, 0);
 static constexpr uint32_t IDESC_16_KK = make_idesc(128, 16, 0, 0);
 static constexpr uint32_t IDESC_32_KK = make_idesc(128, 32, 0, 0);
 static constexpr uint32_t IDESC_16_MM = make_idesc(128, 16, 1, 1);
 static constexpr uint32_t IDESC_32_MM = make_idesc(128, 32, 1, 1);
+static constexpr uint32_t IDESC_64_MM = make_idesc(128, 64, 1, 1);
 
 struct TcCtx {
     unsigned char* sm;     // 1024-aligned shared base
@@ -90,10 +100,22 @@ __device__ __forceinline__ void tc_teardown(TcCtx& c) {
     if (c.warp == 0) { __syncwarp(); tmem_dealloc(c.tmem, TC_TMEM_COLS); }
 }
 
-// weights -> shared memory in the four operand layouts (params: W_in [64][32] | W_out [16][64], row-major fp16)
+// weights -> shared memory in the operand layouts (params: W_in [64][32] | (W_h [64][64]) | W_out [16][64], row-major fp16)
+template <int NH>
 __device__ __forceinline__ void tc_load_weights(const TcCtx& c, const __half* __restrict__ params) {
     const __half* Win = params;
-    const __half* Wout = params + 64 * 32;
+    const __half* Wh = params + 64 * 32;
+    const __half* Wout = params + 64 * 32 + (NH - 1) * 64 * 64;
+    if (NH == 2) {
+        for (uint32_t i = c.tid; i < 64 * 8; i += TC_THREADS) {       // W_h rows (N = 64 neurons), 8 chunks (K = 64)
+            const uint32_t n = i >> 3, ch = i & 7;
+            *reinterpret_cast<uint4*>(c.sm + SM_WH + sw128_off(n, ch)) = *reinterpret_cast<const uint4*>(Wh + n * 64 + ch * 8);
+        }
+        for (uint32_t i = c.tid; i < 64 * 64; i += TC_THREADS) {      // W_h^T: row n = input i, column j = neuron
+            const uint32_t n = i >> 6, j = i & 63;
+            *reinterpret_cast<__half*>(c.sm + SM_WHT + sw128_off(n, j >> 3) + (j & 7) * 2) = Wh[j * 64 + n];
+        }
+    }
     for (uint32_t i = c.tid; i < 64 * 4; i += TC_THREADS) {           // W_in rows (N = 64), 4 chunks of 8 (K = 32)
         const uint32_t n = i >> 2, ch = i & 3;
         *reinterpret_cast<uint4*>(c.sm + SM_WIN + sw64_off(n, ch)) = *reinterpret_cast<const uint4*>(Win + n * 32 + ch * 8);
@@ -145,27 +167,34 @@ __device__ __forceinline__ void tc_stage_enc(const TcCtx& c, const __half* __res
         fence_after_sync();             \
     } while (0)
 
-// MMA1: D = enc . W_in^T
+// K-major GEMM into TMEM column `col`: A tile at a_off (row pitch 64 B -> SW64, 128 B -> SW128), nk steps of K = 16
+__device__ __forceinline__ void tc_mma_sw(const TcCtx& c, uint32_t col, uint32_t a_off, uint32_t b_off, bool sw128, uint32_t nk, uint32_t idesc) {
+    const uint32_t sbo = sw128 ? 1024u : 512u;
+    const uint64_t swz = sw128 ? SWZ_128B : SWZ_64B;
+    for (uint32_t k = 0; k < nk; ++k)
+        mma_f16_ss(c.tmem + col, make_desc(c.sm_addr + a_off + k * 32, 16, sbo, swz), make_desc(c.sm_addr + b_off + k * 32, 16, sbo, swz), idesc, k);
+}
+// layer in: D = enc . W_in^T
 __device__ __forceinline__ void tc_issue_layer_in(const TcCtx& c) {
     fence_after_sync();
-#pragma unroll
-    for (uint32_t k = 0; k < 2; ++k)
-        mma_f16_ss(c.tmem + TC_COL_D, make_desc(c.sm_addr + SM_ENC + k * 32, 16, 512, SWZ_64B),
-                   make_desc(c.sm_addr + SM_WIN + k * 32, 16, 512, SWZ_64B), IDESC_64_KK, k);
+    tc_mma_sw(c, TC_COL_D, SM_ENC, SM_WIN, false, 2, IDESC_64_KK);
     commit(c.bar);
 }
-// MMA2: O = hid . W_out^T
+// hidden layer (NH == 2): D = H1 . W_h^T
+__device__ __forceinline__ void tc_issue_layer_hidden(const TcCtx& c) {
+    fence_after_sync();
+    tc_mma_sw(c, TC_COL_D, SM_H1, SM_WH, true, 4, IDESC_64_KK);
+    commit(c.bar);
+}
+// layer out: O = hid . W_out^T
 __device__ __forceinline__ void tc_issue_layer_out(const TcCtx& c) {
     fence_after_sync();
-#pragma unroll
-    for (uint32_t k = 0; k < 4; ++k)
-        mma_f16_ss(c.tmem + TC_COL_O, make_desc(c.sm_addr + SM_HID + k * 32, 16, 1024, SWZ_128B),
-                   make_desc(c.sm_addr + SM_WOUT + k * 32, 16, 1024, SWZ_128B), IDESC_16_KK, k);
+    tc_mma_sw(c, TC_COL_O, SM_HID, SM_WOUT, true, 4, IDESC_16_KK);
     commit(c.bar);
 }
 
-// epilogue of MMA1: ReLU -> fp16 -> hid tile; returns the bitmask of positive hidden units of this thread's row
-__device__ __forceinline__ uint64_t tc_epilogue_hidden(const TcCtx& c) {
+// epilogue of a hidden GEMM: ReLU -> fp16 -> activation tile at tile_off; returns the bitmask of positive units of this row
+__device__ __forceinline__ uint64_t tc_epilogue_hidden(const TcCtx& c, uint32_t tile_off) {
     const uint32_t row = c.tid;
     const uint32_t taddr = c.tmem + ((c.warp * 32u) << 16) + TC_COL_D;
     uint64_t mask = 0;
@@ -184,20 +213,59 @@ __device__ __forceinline__ uint64_t tc_epilogue_hidden(const TcCtx& c) {
                 if (__half2float(__low2half(h)) > 0.0f) mask |= 1ull << (half_i * 32 + ch * 8 + 2 * q);
                 if (__half2float(__high2half(h)) > 0.0f) mask |= 1ull << (half_i * 32 + ch * 8 + 2 * q + 1);
             }
-            *reinterpret_cast<uint4*>(c.sm + SM_HID + sw128_off(row, half_i * 4 + ch)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            *reinterpret_cast<uint4*>(c.sm + tile_off + sw128_off(row, half_i * 4 + ch)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
         }
     }
     return mask;
 }
 
+// epilogue of a dgrad GEMM: ReLU mask -> fp16 -> gradient tile at tile_off
+__device__ __forceinline__ void tc_epilogue_dhidden(const TcCtx& c, uint32_t tile_off, uint64_t relu_mask) {
+    const uint32_t taddr = c.tmem + ((c.warp * 32u) << 16) + TC_COL_D;
+#pragma unroll
+    for (uint32_t half_i = 0; half_i < 2; ++half_i) {
+        float v[32];
+        tmem_ld32(taddr + half_i * 32, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (uint32_t ch = 0; ch < 4; ++ch) {
+            uint32_t packed[4];
+#pragma unroll
+            for (uint32_t q = 0; q < 4; ++q) {
+                const uint32_t bit = half_i * 32 + ch * 8 + 2 * q;
+                const float lo = ((relu_mask >> bit) & 1ull) ? v[ch * 8 + 2 * q] : 0.0f;
+                const float hi = ((relu_mask >> (bit + 1)) & 1ull) ? v[ch * 8 + 2 * q + 1] : 0.0f;
+                const __half2 h = __floats2half2_rn(lo, hi);
+                packed[q] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(c.sm + tile_off + sw128_off(c.tid, half_i * 4 + ch)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        }
+    }
+}
+
+// forward through the hidden layers of one staged tile; leaves the last activations in SM_HID and issues nothing after
+template <int NH>
+__device__ __forceinline__ void tc_forward_hidden(TcCtx& c, uint64_t& mask_first, uint64_t& mask_last) {
+    if (NH == 1) {
+        mask_last = mask_first = tc_epilogue_hidden(c, SM_HID);
+    } else {
+        mask_first = tc_epilogue_hidden(c, SM_H1);
+        TC_PUBLISH_AND_SYNC();
+        if (c.tid == 0) tc_issue_layer_hidden(c);
+        TC_WAIT(c);
+        mask_last = tc_epilogue_hidden(c, SM_HID);
+    }
+}
+
 // ------------------------------------------------------------------------------------------ training
+template <int NH>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
     extern __shared__ unsigned char smem_raw[];
     if (b.ctrl->skip) return;
     TcCtx c;
     tc_setup(c, smem_raw);
-    tc_load_weights(c, b.params);
+    tc_load_weights<NH>(c, b.params);
     // the upper half of every dout row (outputs 4..15 and the second K chunk) stays zero for the whole kernel
     for (uint32_t i = c.tid; i < 4096 / 16; i += TC_THREADS) reinterpret_cast<uint4*>(c.sm + SM_DOUT)[i] = make_uint4(0, 0, 0, 0);
 
@@ -233,8 +301,9 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
         }
         const float t = mon_sample_t(r, c.lane, xi, 32.0f);
         TC_WAIT(c);
-        // ---- hidden epilogue, MMA2
-        const uint64_t relu_mask = tc_epilogue_hidden(c);
+        // ---- hidden epilogue(s), MMA2
+        uint64_t relu_first, relu_mask;
+        tc_forward_hidden<NH>(c, relu_first, relu_mask);
         TC_PUBLISH_AND_SYNC();
         if (c.tid == 0) tc_issue_layer_out(c);
         TC_WAIT(c);
@@ -272,42 +341,36 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
             commit(c.bar);
         }
         TC_WAIT(c);
-        {   // ReLU mask, fp16 -> dhid tile
-            const uint32_t taddr = c.tmem + ((c.warp * 32u) << 16) + TC_COL_D;
-#pragma unroll
-            for (uint32_t half_i = 0; half_i < 2; ++half_i) {
-                float v[32];
-                tmem_ld32(taddr + half_i * 32, v);
-                tmem_wait_ld();
-#pragma unroll
-                for (uint32_t ch = 0; ch < 4; ++ch) {
-                    uint32_t packed[4];
-#pragma unroll
-                    for (uint32_t q = 0; q < 4; ++q) {
-                        const uint32_t bit = half_i * 32 + ch * 8 + 2 * q;
-                        const float lo = ((relu_mask >> bit) & 1ull) ? v[ch * 8 + 2 * q] : 0.0f;
-                        const float hi = ((relu_mask >> (bit + 1)) & 1ull) ? v[ch * 8 + 2 * q + 1] : 0.0f;
-                        const __half2 h = __floats2half2_rn(lo, hi);
-                        packed[q] = *reinterpret_cast<const uint32_t*>(&h);
-                    }
-                    *reinterpret_cast<uint4*>(c.sm + SM_DHID + sw128_off(c.tid, half_i * 4 + ch)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                }
+        tc_epilogue_dhidden(c, SM_DHID, relu_mask);
+        if (NH == 2) {   // dH1 = (dH2 . W_h) * relu'(H1)
+            TC_PUBLISH_AND_SYNC();
+            if (c.tid == 0) {
+                fence_after_sync();
+                tc_mma_sw(c, TC_COL_D, SM_DHID, SM_WHT, true, 4, IDESC_64_KK);
+                commit(c.bar);
             }
+            TC_WAIT(c);
+            tc_epilogue_dhidden(c, SM_DH1, relu_first);
         }
         // ---- MMA4 (dL/dencoding) + MMA5/6 (weight gradients, accumulated in TMEM across tiles)
         TC_PUBLISH_AND_SYNC();
         if (c.tid == 0) {
             fence_after_sync();
-#pragma unroll
-            for (uint32_t k = 0; k < 4; ++k)
-                mma_f16_ss(c.tmem + TC_COL_E, make_desc(c.sm_addr + SM_DHID + k * 32, 16, 1024, SWZ_128B),
-                           make_desc(c.sm_addr + SM_WINT + k * 32, 16, 1024, SWZ_128B), IDESC_32_KK, k);
+            tc_mma_sw(c, TC_COL_E, NH == 2 ? SM_DH1 : SM_DHID, SM_WINT, true, 4, IDESC_32_KK);
             const uint32_t acc0 = tiles_done ? 1u : 0u;
 #pragma unroll
             for (uint32_t kk = 0; kk < 8; ++kk) {   // 16 points per MMA
+                // [last hidden | its gradient]^T: rows 0-63 x dout = dW_out^T; (NH == 2) rows 64-127 x H1 = dW_h
                 const uint64_t a = make_desc(c.sm_addr + SM_HID + kk * 2048, 16384, 1024, SWZ_128B);
                 mma_f16_ss(c.tmem + TC_COL_G1, a, make_desc(c.sm_addr + SM_DOUT + kk * 512, 256, 128, SWZ_NONE), IDESC_16_MM, acc0 | kk);
-                mma_f16_ss(c.tmem + TC_COL_G2, a, make_desc(c.sm_addr + SM_ENC + kk * 1024, 16, 512, SWZ_64B), IDESC_32_MM, acc0 | kk);
+                const uint64_t enc_b = make_desc(c.sm_addr + SM_ENC + kk * 1024, 16, 512, SWZ_64B);
+                if (NH == 1) {
+                    mma_f16_ss(c.tmem + TC_COL_G2, a, enc_b, IDESC_32_MM, acc0 | kk);
+                } else {
+                    mma_f16_ss(c.tmem + TC_COL_H2, a, make_desc(c.sm_addr + SM_H1 + kk * 2048, 16, 1024, SWZ_128B), IDESC_64_MM, acc0 | kk);
+                    // [H1 | dH1]^T x enc: rows 64-127 = dW_in
+                    mma_f16_ss(c.tmem + TC_COL_G2, make_desc(c.sm_addr + SM_H1 + kk * 2048, 16384, 1024, SWZ_128B), enc_b, IDESC_32_MM, acc0 | kk);
+                }
             }
             commit(c.bar);
         }
@@ -333,7 +396,7 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
         // the next tile overwrites enc / hid / dout: every MMA that reads them has completed (the wait above)
     }
 
-    // ---- weight gradients: TMEM -> this CTA's partial row (W_in [64][32] | W_out [16][64])
+    // ---- weight gradients: TMEM -> this CTA's partial row (W_in [64][32] | (W_h [64][64]) | W_out [16][64])
     float* partial = b.mlp_partials + (size_t)blockIdx.x * n_mlp;
     if (tiles_done == 0) {
         for (uint32_t i = c.tid; i < n_mlp; i += TC_THREADS) partial[i] = 0.0f;
@@ -344,7 +407,7 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
             tmem_wait_ld();
             const uint32_t j = c.tid;
 #pragma unroll
-            for (uint32_t o = 0; o < 16; ++o) partial[64 * 32 + o * 64 + j] = v[o];
+            for (uint32_t o = 0; o < 16; ++o) partial[64 * 32 + (NH - 1) * 64 * 64 + o * 64 + j] = v[o];
         } else {                 // G2 rows 64..127: (dhid^T . enc)[j][k] = dW_in[j][k]
             float v[32];
             tmem_ld32(c.tmem + ((c.warp * 32u) << 16) + TC_COL_G2, v);
@@ -352,6 +415,15 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
             const uint32_t j = c.tid - 64;
 #pragma unroll
             for (uint32_t k = 0; k < 32; ++k) partial[j * 32 + k] = v[k];
+            if (NH == 2) {   // G3 rows 64..127: (dH2^T . H1)[j][i] = dW_h[j][i]
+#pragma unroll
+                for (uint32_t half_i = 0; half_i < 2; ++half_i) {
+                    tmem_ld32(c.tmem + ((c.warp * 32u) << 16) + TC_COL_H2 + half_i * 32, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (uint32_t k = 0; k < 32; ++k) partial[64 * 32 + j * 64 + half_i * 32 + k] = v[k];
+                }
+            }
         }
     }
     tc_teardown(c);
@@ -359,12 +431,13 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
 
 // ------------------------------------------------------------------------------------------ inference
 // raw network output (4 logits per point) for the density lattice and the parity hooks
+template <int NH>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 k_mlp_infer_tc(uint32_t n_points, const __half* __restrict__ params, const __half* __restrict__ enc, float* __restrict__ out4) {
     extern __shared__ unsigned char smem_raw[];
     TcCtx c;
     tc_setup(c, smem_raw);
-    tc_load_weights(c, params);
+    tc_load_weights<NH>(c, params);
     const uint32_t n_tiles = (n_points + 127) / 128;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint32_t pt = tile * 128 + c.tid;
@@ -372,7 +445,7 @@ k_mlp_infer_tc(uint32_t n_points, const __half* __restrict__ params, const __hal
         TC_PUBLISH_AND_SYNC();
         if (c.tid == 0) tc_issue_layer_in(c);
         TC_WAIT(c);
-        (void)tc_epilogue_hidden(c);
+        { uint64_t m0, m1; tc_forward_hidden<NH>(c, m0, m1); }
         TC_PUBLISH_AND_SYNC();
         if (c.tid == 0) tc_issue_layer_out(c);
         TC_WAIT(c);
@@ -390,6 +463,7 @@ k_mlp_infer_tc(uint32_t n_points, const __half* __restrict__ params, const __hal
 }
 
 // test render (VolumeRender_Render, nerf_model.cu:1134-1229): per ray S2/32 tiles with a carried compositing state
+template <int NH>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 k_mlp_render_tc(uint32_t n_rays, uint32_t S2, const MonRay* __restrict__ rays, const int* __restrict__ in_box,
                 const float* __restrict__ jitter, uint32_t seed, uint32_t iter, const __half* __restrict__ params,
@@ -397,7 +471,7 @@ k_mlp_render_tc(uint32_t n_rays, uint32_t S2, const MonRay* __restrict__ rays, c
     extern __shared__ unsigned char smem_raw[];
     TcCtx c;
     tc_setup(c, smem_raw);
-    tc_load_weights(c, params);
+    tc_load_weights<NH>(c, params);
     const uint32_t n_groups = (n_rays + 3) / 4, chunks = S2 / 32;
     for (uint32_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
         const uint32_t ray = grp * 4 + c.warp;
@@ -424,7 +498,7 @@ k_mlp_render_tc(uint32_t n_rays, uint32_t S2, const MonRay* __restrict__ rays, c
             TC_PUBLISH_AND_SYNC();
             if (c.tid == 0) tc_issue_layer_in(c);
             TC_WAIT(c);
-            (void)tc_epilogue_hidden(c);
+            { uint64_t m0, m1; tc_forward_hidden<NH>(c, m0, m1); }
             TC_PUBLISH_AND_SYNC();
             if (c.tid == 0) tc_issue_layer_out(c);
             TC_WAIT(c);
@@ -460,33 +534,54 @@ static cudaError_t tc_prepare(K kernel) {
 }
 
 cudaError_t mon_launch_mlp_train_tc(const MonBatch& b, const MonLossCfg& lc, uint32_t n_hidden, uint32_t n_mlp, uint32_t n_ctas, cudaStream_t st) {
-    if (n_hidden != 1) return cudaErrorNotSupported;
-    static cudaError_t prep = tc_prepare(k_mlp_train_tc);
-    if (prep != cudaSuccess) return prep;
-    k_mlp_train_tc<<<n_ctas, TC_THREADS, TC_SMEM_BYTES, st>>>(b, lc, n_mlp);
+    if (n_hidden == 1) {
+        static cudaError_t prep = tc_prepare(k_mlp_train_tc<1>);
+        if (prep != cudaSuccess) return prep;
+        k_mlp_train_tc<1><<<n_ctas, TC_THREADS, TC_SMEM_BYTES, st>>>(b, lc, n_mlp);
+    } else if (n_hidden == 2) {
+        static cudaError_t prep = tc_prepare(k_mlp_train_tc<2>);
+        if (prep != cudaSuccess) return prep;
+        k_mlp_train_tc<2><<<n_ctas, TC_THREADS, TC_SMEM_BYTES, st>>>(b, lc, n_mlp);
+    } else {
+        return cudaErrorNotSupported;
+    }
     return cudaGetLastError();
 }
 
 cudaError_t mon_launch_mlp_infer_tc(uint32_t n_points, uint32_t n_hidden, const __half* params, const __half* enc, float* out4, cudaStream_t st) {
-    if (n_hidden != 1) return cudaErrorNotSupported;
-    static cudaError_t prep = tc_prepare(k_mlp_infer_tc);
-    if (prep != cudaSuccess) return prep;
     uint32_t ctas = (n_points + 127) / 128;
     if (ctas > 296) ctas = 296;
     if (ctas == 0) ctas = 1;
-    k_mlp_infer_tc<<<ctas, TC_THREADS, TC_SMEM_BYTES, st>>>(n_points, params, enc, out4);
+    if (n_hidden == 1) {
+        static cudaError_t prep = tc_prepare(k_mlp_infer_tc<1>);
+        if (prep != cudaSuccess) return prep;
+        k_mlp_infer_tc<1><<<ctas, TC_THREADS, TC_SMEM_BYTES, st>>>(n_points, params, enc, out4);
+    } else if (n_hidden == 2) {
+        static cudaError_t prep = tc_prepare(k_mlp_infer_tc<2>);
+        if (prep != cudaSuccess) return prep;
+        k_mlp_infer_tc<2><<<ctas, TC_THREADS, TC_SMEM_BYTES, st>>>(n_points, params, enc, out4);
+    } else {
+        return cudaErrorNotSupported;
+    }
     return cudaGetLastError();
 }
 
 cudaError_t mon_launch_mlp_render_tc(uint32_t n_rays, uint32_t S2, uint32_t n_hidden, const MonRay* rays, const int* in_box, const float* jitter,
                                      uint32_t seed, uint32_t iter, const __half* params, const __half* enc, float bgc,
                                      float* rgb, float* depth, float* mask, cudaStream_t st) {
-    if (n_hidden != 1) return cudaErrorNotSupported;
-    static cudaError_t prep = tc_prepare(k_mlp_render_tc);
-    if (prep != cudaSuccess) return prep;
     uint32_t ctas = (n_rays + 3) / 4;
     if (ctas > 296) ctas = 296;
     if (ctas == 0) ctas = 1;
-    k_mlp_render_tc<<<ctas, TC_THREADS, TC_SMEM_BYTES, st>>>(n_rays, S2, rays, in_box, jitter, seed, iter, params, enc, bgc, rgb, depth, mask);
+    if (n_hidden == 1) {
+        static cudaError_t prep = tc_prepare(k_mlp_render_tc<1>);
+        if (prep != cudaSuccess) return prep;
+        k_mlp_render_tc<1><<<ctas, TC_THREADS, TC_SMEM_BYTES, st>>>(n_rays, S2, rays, in_box, jitter, seed, iter, params, enc, bgc, rgb, depth, mask);
+    } else if (n_hidden == 2) {
+        static cudaError_t prep = tc_prepare(k_mlp_render_tc<2>);
+        if (prep != cudaSuccess) return prep;
+        k_mlp_render_tc<2><<<ctas, TC_THREADS, TC_SMEM_BYTES, st>>>(n_rays, S2, rays, in_box, jitter, seed, iter, params, enc, bgc, rgb, depth, mask);
+    } else {
+        return cudaErrorNotSupported;
+    }
     return cudaGetLastError();
 }

@@ -125,9 +125,9 @@ int mon_object_step_count(mon_object* obj, uint32_t* step);
 /* Measurement hook: `iters` iterations launched kernel by kernel (no graph) with a CUDA event between the
  * stages on the object's stream; stage_ms[k] = mean device time of stage k per iteration.
  * Stages: 0 batch (ray generation + compaction), 1 hash-grid encode, 2 fused MLP forward + volume render +
- * loss + MLP backward, 3 hash-grid gradient scatter, 4 optimizer sweep (Adam + EMA + grad zero),
- * 5 loss reduction.  n_stages must be MON_N_STAGES. */
-#define MON_N_STAGES 6
+ * loss + MLP backward, 3 hash-grid gradient scatter, 4 optimizer sweep (Adam + EMA + grad zero + logged-loss
+ * reduction).  n_stages must be MON_N_STAGES. */
+#define MON_N_STAGES 5
 int mon_object_train_profiled(mon_object* obj, uint32_t iters, float* stage_ms, uint32_t n_stages);
 /* number of CUDA kernels this library launched on behalf of the object so far */
 int mon_object_launch_count(mon_object* obj, uint64_t* n);

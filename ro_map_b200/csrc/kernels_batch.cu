@@ -11,7 +11,10 @@
 #include "mon_device.cuh"
 #include "mon_kernels.h"
 
-#define BATCH_THREADS 1024
+#include <cooperative_groups.h>
+
+#define BATCH_THREADS 512
+#define BATCH_CTAS 8
 
 struct RayCand {
     bool valid; uint32_t x, y; uint8_t inst; uint32_t frame; size_t pix;
@@ -41,77 +44,96 @@ __device__ __forceinline__ RayCand make_candidate(const MonBatch& b, const MonSc
     return c;
 }
 
+// One thread-block cluster of BATCH_CTAS CTAs (all co-resident, distributed shared memory) owns the whole batch:
+// thread g of the cluster evaluates candidates [g*per, (g+1)*per).  The compaction order is the ascending batch
+// index: CTA-local exclusive scan, then every CTA reads the totals of the lower-ranked CTAs out of their shared
+// memory (DSMEM) — no global atomics, no second kernel, no host round trip.  A second cluster barrier makes the
+// compacted rays visible cluster-wide before the roll-over padding reads them.
+__device__ __forceinline__ void write_ray(const MonBatch& b, const MonScene& sc, const RayCand& c, uint32_t idx, uint32_t iter) {
+    MonRay r;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { r.o[q] = c.o[q]; r.d[q] = c.d[q]; }
+    r.d_norm = c.d_norm; r.tmin = fmaxf(c.t0, 0.0f); r.tmax = c.t1;
+    b.rays[idx] = r;
+    const MonFrame* fr = b.frames + c.frame;
+    const size_t pix = c.pix;
+    if (c.inst != 0) {
+        const uint8_t* px = fr->rgb + pix * 3;
+        // the reference stores float pixels = u8 * (1/255) (nerf_data.cu:163-164); same value here
+        b.target[idx * 3 + 0] = __fmul_rn((float)px[0], (float)(1.0 / 255.0));
+        b.target[idx * 3 + 1] = __fmul_rn((float)px[1], (float)(1.0 / 255.0));
+        b.target[idx * 3 + 2] = __fmul_rn((float)px[2], (float)(1.0 / 255.0));
+        b.target_depth[idx] = (sc.use_depth && fr->depth) ? __fmul_rn(fr->depth[pix], c.d_norm) : 0.0f;
+        b.ray_inst[idx] = 1;
+    } else {
+        b.target[idx * 3 + 0] = mon_rand(b.inj_col, b.seed, iter, 1, idx * 3 + 0);
+        b.target[idx * 3 + 1] = mon_rand(b.inj_col, b.seed, iter, 1, idx * 3 + 1);
+        b.target[idx * 3 + 2] = mon_rand(b.inj_col, b.seed, iter, 1, idx * 3 + 2);
+        b.target_depth[idx] = 0.0f;
+        b.ray_inst[idx] = 0;
+    }
+}
+
 __global__ void __launch_bounds__(BATCH_THREADS, 1)
 k_generate_batch(MonBatch b, MonScene sc) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
     __shared__ uint32_t warp_sums[BATCH_THREADS / 32];
-    __shared__ uint32_t s_total;
+    __shared__ uint32_t s_total;          // read by the other CTAs of the cluster
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t rank = cluster.block_rank(), n_cta = cluster.num_blocks();
     const uint32_t iter = b.ctrl->iter;
     const uint32_t n_boxes = b.ctrl->n_boxes;
     const uint32_t R = b.R;
-    const uint32_t per_thread = (R + BATCH_THREADS - 1) / BATCH_THREADS;
-    const uint32_t i0 = tid * per_thread;
+    const uint32_t n_threads = n_cta * BATCH_THREADS;
+    const uint32_t per_thread = (R + n_threads - 1) / n_threads;
+    const uint32_t i0 = (rank * BATCH_THREADS + tid) * per_thread;
 
-    // pass 1: count this thread's in-box rays
+    // pass 1: evaluate; the first candidate stays in registers, further ones (R > 4096) are recomputed in pass 2
+    RayCand first; first.valid = false;
     uint32_t cnt = 0;
     for (uint32_t k = 0; k < per_thread; ++k) {
         const uint32_t i = i0 + k;
-        if (i < R && make_candidate(b, sc, n_boxes, i, iter).valid) ++cnt;
+        if (i >= R) break;
+        const RayCand c = make_candidate(b, sc, n_boxes, i, iter);
+        if (k == 0) first = c;
+        if (c.valid) ++cnt;
     }
-    // block-wide exclusive scan of cnt
+    // CTA-wide exclusive scan of cnt
     uint32_t incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
     if (lane == 31) warp_sums[warp] = incl;
     __syncthreads();
     if (warp == 0) {
-        uint32_t v = warp_sums[lane];
+        uint32_t v = lane < BATCH_THREADS / 32 ? warp_sums[lane] : 0u;
         uint32_t vi = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, vi, o); if (lane >= o) vi += u; }
-        warp_sums[lane] = vi - v;
+        if (lane < BATCH_THREADS / 32) warp_sums[lane] = vi - v;
         if (lane == 31) s_total = vi;
     }
-    __syncthreads();
-    uint32_t slot = warp_sums[warp] + incl - cnt;
-    const uint32_t n_in = s_total;
+    cluster.sync();                        // every CTA's s_total is published
+    uint32_t base = 0, n_in = 0;
+    for (uint32_t r = 0; r < n_cta; ++r) {
+        const uint32_t t = *cluster.map_shared_rank(&s_total, r);
+        if (r < rank) base += t;
+        n_in += t;
+    }
+    uint32_t slot = base + warp_sums[warp] + incl - cnt;
 
-    // pass 2: recompute and write compacted rays + targets
+    // pass 2: write compacted rays + targets
     for (uint32_t k = 0; k < per_thread; ++k) {
         const uint32_t i = i0 + k;
         if (i >= R) break;
-        RayCand c = make_candidate(b, sc, n_boxes, i, iter);
-        if (!c.valid) continue;
-        const uint32_t idx = slot++;
-        MonRay r;
-#pragma unroll
-        for (int q = 0; q < 3; ++q) { r.o[q] = c.o[q]; r.d[q] = c.d[q]; }
-        r.d_norm = c.d_norm; r.tmin = fmaxf(c.t0, 0.0f); r.tmax = c.t1;
-        b.rays[idx] = r;
-        const MonFrame* fr = b.frames + c.frame;
-        const size_t pix = c.pix;
-        if (c.inst != 0) {
-            const uint8_t* px = fr->rgb + pix * 3;
-            // the reference stores float pixels = u8 * (1/255) (nerf_data.cu:163-164); same value here
-            b.target[idx * 3 + 0] = __fmul_rn((float)px[0], (float)(1.0 / 255.0));
-            b.target[idx * 3 + 1] = __fmul_rn((float)px[1], (float)(1.0 / 255.0));
-            b.target[idx * 3 + 2] = __fmul_rn((float)px[2], (float)(1.0 / 255.0));
-            b.target_depth[idx] = (sc.use_depth && fr->depth) ? __fmul_rn(fr->depth[pix], c.d_norm) : 0.0f;
-            b.ray_inst[idx] = 1;
-        } else {
-            b.target[idx * 3 + 0] = mon_rand(b.inj_col, b.seed, iter, 1, idx * 3 + 0);
-            b.target[idx * 3 + 1] = mon_rand(b.inj_col, b.seed, iter, 1, idx * 3 + 1);
-            b.target[idx * 3 + 2] = mon_rand(b.inj_col, b.seed, iter, 1, idx * 3 + 2);
-            b.target_depth[idx] = 0.0f;
-            b.ray_inst[idx] = 0;
-        }
+        const RayCand c = (k == 0) ? first : make_candidate(b, sc, n_boxes, i, iter);
+        if (c.valid) write_ray(b, sc, c, slot++, iter);
     }
-    __syncthreads();  // global writes of this CTA are visible to the CTA after the barrier
+    cluster.sync();                        // compacted rays visible to the whole cluster; also: nobody exits while its s_total is still read
 
-    // fill_rollover_rays (:280-294) + the background colour VolumeRender indexes as
-    // RandColors[(i % n_in) * 3] (:760)
+    // fill_rollover_rays (:280-294) + the background colour VolumeRender indexes as RandColors[(i % n_in) * 3] (:760)
     if (n_in > 0) {
-        for (uint32_t i = tid; i < R; i += BATCH_THREADS) {
+        for (uint32_t i = rank * BATCH_THREADS + tid; i < R; i += n_threads) {
             const uint32_t s = i % n_in;
             if (i >= n_in) {
                 b.rays[i] = b.rays[s];
@@ -126,7 +148,7 @@ k_generate_batch(MonBatch b, MonScene sc) {
             b.bg[i * 3 + 2] = mon_rand(b.inj_col, b.seed, iter, 1, s * 3 + 2);
         }
     }
-    if (tid == 0) {
+    if (rank == 0 && tid == 0) {
         b.ctrl->n_in = n_in;
         b.ctrl->skip = (n_in == 0) ? 1u : 0u;  // reference: modulo by zero (undefined); here: skip the iteration
         if (n_in > 0) b.ctrl->step += 1;
@@ -154,7 +176,16 @@ __global__ void k_render_rays(uint32_t n_rays, mon_bbox2d box, MonScene sc, cons
 }
 
 void mon_launch_generate_batch(const MonBatch& b, const MonScene& sc, cudaStream_t st) {
-    k_generate_batch<<<1, BATCH_THREADS, 0, st>>>(b, sc);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(BATCH_CTAS);
+    cfg.blockDim = dim3(BATCH_THREADS);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = BATCH_CTAS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, k_generate_batch, b, sc);
 }
 void mon_launch_render_rays(uint32_t n_rays, mon_bbox2d box, const MonScene& sc, const float* Twc_dev,
                             MonRay* rays, int* in_box, cudaStream_t st) {

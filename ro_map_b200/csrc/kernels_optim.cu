@@ -58,6 +58,8 @@ __global__ void k_cast_params(uint32_t n, const float* __restrict__ pf, __half* 
     if (i < n) ph[i] = __float2half_rn(pf[i]);
 }
 
+#define OPT_THREADS 256
+
 __device__ __forceinline__ void adam_update(const MonOpt& o, float lr_base, float gradient, uint32_t i, bool is_mlp,
                                             float* __restrict__ pf, __half* __restrict__ ph, float* __restrict__ m,
                                             float* __restrict__ v, uint32_t* __restrict__ ps) {
@@ -76,14 +78,27 @@ __device__ __forceinline__ void adam_update(const MonOpt& o, float lr_base, floa
     ph[i] = __float2half_rn(nw);
 }
 
-#define OPT_THREADS 256
-
 __global__ void __launch_bounds__(OPT_THREADS)
-k_optimizer_sweep(MonOpt o, const MonCtrl* __restrict__ ctrl, float* __restrict__ pf, __half* __restrict__ ph,
+k_optimizer_sweep(MonOpt o, MonCtrl* __restrict__ ctrl, float* __restrict__ pf, __half* __restrict__ ph,
                   __half* __restrict__ gh, const float* __restrict__ mlp_partials, float* __restrict__ m,
-                  float* __restrict__ v, uint32_t* __restrict__ ps, __half* __restrict__ ema) {
+                  float* __restrict__ v, uint32_t* __restrict__ ps, __half* __restrict__ ema,
+                  const float* __restrict__ loss, uint32_t R) {
     if (ctrl->skip) return;
     __shared__ float s_lr, s_old, s_new;
+    if (blockIdx.x == gridDim.x - 1) {
+        // SumLoss (nerf_model.cu:1231-1253) + the host-side /R (:1650-1658) folded into the sweep's last CTA
+        // (a mostly idle tail block): fixed summation order -> reproducible logged loss
+        __shared__ float s_loss[OPT_THREADS];
+        float a = 0.0f;
+        for (uint32_t i = threadIdx.x; i < R; i += OPT_THREADS) a += loss[i];
+        s_loss[threadIdx.x] = a;
+        __syncthreads();
+        for (int step = OPT_THREADS / 2; step > 0; step >>= 1) {
+            if ((int)threadIdx.x < step) s_loss[threadIdx.x] += s_loss[threadIdx.x + step];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) ctrl->loss_mean = s_loss[0] / (float)R;
+    }
     const uint32_t step = ctrl->step;  // 1-based, already advanced by the batch kernel
     if (threadIdx.x == 0) {
         // ExponentialDecay evaluates its condition with the nested step BEFORE Adam increments it
@@ -173,10 +188,10 @@ void mon_launch_init_grid(uint64_t state, uint64_t inc, uint32_t n, float* out, 
 void mon_launch_cast_params(uint32_t n, const float* pf, __half* ph, cudaStream_t st) {
     k_cast_params<<<(n + 255) / 256, 256, 0, st>>>(n, pf, ph);
 }
-void mon_launch_optimizer(const MonOpt& o, const MonCtrl* ctrl, float* pf, __half* ph, __half* gh, const float* partials,
-                          float* m, float* v, uint32_t* ps, __half* ema, cudaStream_t st) {
+void mon_launch_optimizer(const MonOpt& o, MonCtrl* ctrl, float* pf, __half* ph, __half* gh, const float* partials,
+                          float* m, float* v, uint32_t* ps, __half* ema, const float* loss, uint32_t R, cudaStream_t st) {
     const uint32_t pairs = (o.n_params + 1) / 2;
-    k_optimizer_sweep<<<(pairs + OPT_THREADS - 1) / OPT_THREADS, OPT_THREADS, 0, st>>>(o, ctrl, pf, ph, gh, partials, m, v, ps, ema);
+    k_optimizer_sweep<<<(pairs + OPT_THREADS - 1) / OPT_THREADS, OPT_THREADS, 0, st>>>(o, ctrl, pf, ph, gh, partials, m, v, ps, ema, loss, R);
 }
 void mon_launch_snapshot_grad(uint32_t n, uint32_t n_mlp, uint32_t n_partials, const __half* gh, const float* partials, float* out, cudaStream_t st) {
     k_snapshot_grad<<<(n + 255) / 256, 256, 0, st>>>(n, n_mlp, n_partials, gh, partials, out);

@@ -488,10 +488,8 @@ static int enqueue_iteration(mon_object* o, const MonBatch& b, bool snapshot_gra
                                o->scene.bmin, o->scene.bmax, o->d_enc, o->gh + o->n_mlp, st); ++n;
     if (snapshot_grad) { mon_launch_snapshot_grad(o->P, o->n_mlp, o->opt.n_partials, o->gh, o->partials, o->grad_snap, st); ++n; }
     if (ev) CK(cudaEventRecord(ev[4], st));
-    mon_launch_optimizer(o->opt, o->ctrl, o->pf, o->ph, o->gh, o->partials, o->m, o->v, o->ps, o->ema, st); ++n;
+    mon_launch_optimizer(o->opt, o->ctrl, o->pf, o->ph, o->gh, o->partials, o->m, o->v, o->ps, o->ema, o->loss, o->R, st); ++n;
     if (ev) CK(cudaEventRecord(ev[5], st));
-    mon_launch_sum_loss(o->R, o->loss, o->ctrl, st); ++n;
-    if (ev) CK(cudaEventRecord(ev[6], st));
     CK(cudaGetLastError());
     if (n_launched) *n_launched = n;
     return MON_OK;
@@ -512,7 +510,7 @@ static int capture_graph(mon_object* o, int iters, cudaGraphExec_t* out) {
     return MON_OK;
 }
 
-static const int kKernelsPerIter = 6;
+static const int kKernelsPerIter = 5;
 
 int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uint8_t instance_id,
                       const float obj_Tow[16], const float bmin[3], const float bmax[3], mon_object** out) {

@@ -35,8 +35,8 @@ cudaError_t mon_launch_mlp_render_tc(uint32_t n_rays, uint32_t S2, uint32_t n_hi
 // kernels_optim.cu
 void mon_launch_init_grid(uint64_t state, uint64_t inc, uint32_t n, float* out, cudaStream_t st);
 void mon_launch_cast_params(uint32_t n, const float* pf, __half* ph, cudaStream_t st);
-void mon_launch_optimizer(const MonOpt& o, const MonCtrl* ctrl, float* pf, __half* ph, __half* gh, const float* partials,
-                          float* m, float* v, uint32_t* ps, __half* ema, cudaStream_t st);
+void mon_launch_optimizer(const MonOpt& o, MonCtrl* ctrl, float* pf, __half* ph, __half* gh, const float* partials,
+                          float* m, float* v, uint32_t* ps, __half* ema, const float* loss, uint32_t R, cudaStream_t st);
 void mon_launch_snapshot_grad(uint32_t n, uint32_t n_mlp, uint32_t n_partials, const __half* gh, const float* partials,
                               float* out, cudaStream_t st);
 void mon_launch_sum_loss(uint32_t R, const float* loss, MonCtrl* ctrl, cudaStream_t st);

@@ -44,7 +44,6 @@ def parse():
     ap.add_argument("--rays", type=int, default=4096, help="rays per batch (reference: 4096, nerf_model.h:173)")
     ap.add_argument("--hidden-layers", type=int, default=1, help="MLP hidden layers (reference base.json: 1)")
     ap.add_argument("--frames", type=int, default=FRAMES)
-    ap.add_argument("--mlp-impl", type=int, default=None, help="0 tcgen05 (default when built), 1 mma.sync validation kernel")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the CPU baseline sample")
     return ap.parse_args()
 
@@ -244,8 +243,6 @@ def run_ours(args, rank, world, local_rank):
     ds = core.Dataset(gpu, *seq.K, seq.H, seq.W, len(seq.poses), True)
     upload(ds)
     nerf = core.NerfObject(ds, cfg, obj.Tow, bmin, bmax, obj.instance_id)
-    if args.mlp_impl is not None:
-        nerf.set_mlp_impl(args.mlp_impl)
     nerf.set_bboxes(obj.boxes)
     nerf.train(max(Wm, 3))
     with ClockSampler(gpu) as clocks:
@@ -273,8 +270,6 @@ def run_ours(args, rank, world, local_rank):
     # ---------------- end to end from host buffers through the C ABI
     ds2 = core.Dataset(gpu, *seq.K, seq.H, seq.W, len(seq.poses), True)
     nerf2 = core.NerfObject(ds2, cfg, obj.Tow, bmin, bmax, obj.instance_id)
-    if args.mlp_impl is not None:
-        nerf2.set_mlp_impl(args.mlp_impl)
     # warm the graphs with a throw-away frame set so that capture cost is not billed to the timed region
     upload(ds2)
     nerf2.set_bboxes(obj.boxes)

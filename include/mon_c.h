@@ -124,10 +124,10 @@ int mon_object_last_train_ms(mon_object* obj, float* ms);
 int mon_object_step_count(mon_object* obj, uint32_t* step);
 /* Measurement hook: `iters` iterations launched kernel by kernel (no graph) with a CUDA event between the
  * stages on the object's stream; stage_ms[k] = mean device time of stage k per iteration.
- * Stages: 0 batch (ray generation + compaction), 1 hash-grid encode, 2 fused MLP forward + volume render +
- * loss + MLP backward, 3 hash-grid gradient scatter, 4 optimizer sweep (Adam + EMA + grad zero + logged-loss
- * reduction).  n_stages must be MON_N_STAGES. */
-#define MON_N_STAGES 5
+ * Stages: 0 batch (ray generation + compaction), 1 sample positions, 2 hash-grid encode, 3 fused MLP forward +
+ * volume render + loss + MLP backward, 4 hash-grid gradient scatter, 5 optimizer sweep (Adam + EMA + grad zero +
+ * logged-loss reduction).  n_stages must be MON_N_STAGES. */
+#define MON_N_STAGES 6
 int mon_object_train_profiled(mon_object* obj, uint32_t iters, float* stage_ms, uint32_t n_stages);
 /* number of CUDA kernels this library launched on behalf of the object so far */
 int mon_object_launch_count(mon_object* obj, uint64_t* n);
@@ -152,14 +152,10 @@ int mon_object_train_injected(mon_object* obj, const float* sample_xy, const flo
 int mon_object_get_state(mon_object* obj, int which, float* out, size_t n);
 int mon_object_set_params(mon_object* obj, const float* params_fp32, size_t n);
 /* intermediates of the last injected iteration (float), returns count via n_out:
- * 0 rays(9/ray) 3 enc(32/pt) 4 out(4/pt: r,g,b,sigma logits) 5 rgb_rays 6 depth_rays
+ * 0 rays(9/ray) 1 points(3/pt, unit cube) 3 enc(32/pt) 4 out(4/pt: r,g,b,sigma logits) 5 rgb_rays 6 depth_rays
  * 7 mask_rays 8 dout(4/pt) 9 d_enc(32/pt) 10 target rgb 11 target depth 12 ray instance flag
  * 13 per-ray loss */
 int mon_object_last(mon_object* obj, int which, float* out, size_t cap, size_t* n_out);
-/* select the MLP kernel family: 0 = tcgen05 (product default), 1 = legacy mma.sync/wmma
- * validation kernel (kept only so tests can cross-check the tcgen05 kernel on device) */
-int mon_object_set_mlp_impl(mon_object* obj, int impl);
-
 /* stand-alone stage entry points on host buffers (copies inside), for kernel-level parity */
 int mon_stage_encode(const mon_config* cfg, const uint16_t* grid_fp16, size_t n_grid_params,
                      const float* points_unit, uint32_t n_points, uint16_t* enc_out);

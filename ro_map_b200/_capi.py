@@ -76,7 +76,6 @@ SIGNATURES = {
     "mon_object_get_state": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t]),
     "mon_object_set_params": (C.c_int, [_vp, _vp, C.c_size_t]),
     "mon_object_last": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t, _P(C.c_size_t)]),
-    "mon_object_set_mlp_impl": (C.c_int, [_vp, C.c_int]),
     "mon_stage_encode": (C.c_int, [_P(Config), _vp, C.c_size_t, _vp, C.c_uint32, _vp]),
 }
 

@@ -129,7 +129,7 @@ class Dataset:
 
 class NerfObject:
     STATE = {"master": 0, "params": 1, "ema": 2, "grad": 3, "adam_m": 4, "adam_v": 5, "param_steps": 6}
-    LAST = {"rays": 0, "enc": 3, "out": 4, "rgb_rays": 5, "depth_rays": 6, "mask_rays": 7, "dout": 8, "d_enc": 9,
+    LAST = {"rays": 0, "points": 1, "enc": 3, "out": 4, "rgb_rays": 5, "depth_rays": 6, "mask_rays": 7, "dout": 8, "d_enc": 9,
             "target": 10, "target_depth": 11, "ray_instance": 12, "loss": 13}
 
     def __init__(self, ds: Dataset, cfg: Config, obj_Tow, bmin, bmax, instance_id: int, seed: int = 1337):
@@ -167,7 +167,7 @@ class NerfObject:
     def sync(self):
         check(self._lib.mon_object_sync(self._h))
 
-    STAGES = ("batch", "encode", "mlp_fused", "scatter", "optimizer")
+    STAGES = ("batch", "points", "encode", "mlp_fused", "scatter", "optimizer")
 
     def train_profiled(self, iters: int) -> dict:
         """Mean device milliseconds per stage (CUDA events on the object's stream), see mon_c.h."""
@@ -192,9 +192,6 @@ class NerfObject:
         n = C.c_uint64(0)
         check(self._lib.mon_object_launch_count(self._h, C.byref(n)))
         return n.value
-
-    def set_mlp_impl(self, impl: int):
-        check(self._lib.mon_object_set_mlp_impl(self._h, impl))
 
     # ---- NeRF_Model::Render
     def render(self, box, Twc, use_ema: bool = True, rand_dt=None):
@@ -235,7 +232,7 @@ class NerfObject:
 
     def last(self, which: str) -> np.ndarray:
         R, N = self.R, self.R * self.S
-        sizes = {"rays": R * 9, "enc": N * 32, "out": N * 4, "rgb_rays": R * 3, "depth_rays": R, "mask_rays": R, "dout": N * 4,
+        sizes = {"rays": R * 9, "points": N * 3, "enc": N * 32, "out": N * 4, "rgb_rays": R * 3, "depth_rays": R, "mask_rays": R, "dout": N * 4,
                  "d_enc": N * 32, "target": R * 3, "target_depth": R, "ray_instance": R, "loss": R}
         out = np.empty(sizes[which], np.float32)
         n = C.c_size_t(0)

@@ -1,26 +1,63 @@
-// kernels_encode.cu — multiresolution hash-grid lookup (forward) and gradient scatter (backward).
+// kernels_encode.cu — sample positions, multiresolution hash-grid lookup (forward) and gradient scatter (backward).
 //
 // Replaces GenerateInputPoints (MON/Core/src/nerf_model.cu:536-566), tcnn kernel_grid
 // (TCNN/include/tiny-cuda-nn/encodings/grid.h:220-384) and kernel_grid_backward (:386-509).
-// Sample positions are never materialised: each thread regenerates its sample from the 36-byte
-// ray and the jitter (A3), so the 1.57 MB PointsInput / 0.52 MB SamplesDistances round trips of
-// the reference disappear.
 //
-// Mapping: a CTA owns a tile of 128 consecutive samples (= 4 rays) for ALL levels; thread t
-// handles sample t%128 and the 4 levels of group t/128.  Consecutive lanes are consecutive
-// samples of one ray, so at coarse levels a warp's 8-corner gathers fall into a handful of
-// 128-byte lines, and the coherent-prime hash (x multiplier 1) keeps the x/x+1 corner pair in
-// one 32-byte sector at hashed levels.  Output is point-major [N][32] fp16 (64 B per sample, one
-// 16-byte store per thread), the layout the fused MLP kernel stages with one bulk copy per tile.
+// FORWARD.  The reference launches one thread per (point, level) and gathers 8 x 4 bytes through L1/L2; on B200 that
+// shape is bound by L1 wavefronts (one per distinct 128-B line: ~16-32 per warp instruction), not by HBM or L2.
+// Here the table is the resident operand instead: the work is cut into (level, feature) JOBS whose table slice
+// (<= 65536 fp16 = 128 KB, from a planar copy of the fp16 weights the optimizer maintains) is staged into shared
+// memory with TMA bulk copies (cp.async.bulk -> mbarrier), and the CTA then streams its share of the points past
+// it: 8 two-byte gathers per point hit the 32 shared-memory banks (~3.5-way conflicts for random indices) instead of
+// 8 L1 wavefronts.  Work is split evenly over the flattened [job][point] space, so each of the 148 CTAs loads at
+// most two table slices.  Output is feature-major ("SoA", like tcnn's own encoding output): enc[2*level+f][point],
+// written with coalesced 2-byte stores.
+// Arithmetic is the reference's: weights in fp32, rounded to fp16, one fp32 FMA per corner whose result is rounded
+// back to fp16 after every corner (grid.h:334 via common.h:539-559) — bit-exact against tiny-cuda-nn, including
+// the 32-bit stride wrap that turns level 12 into a table indexed by x alone (mon_core.cu make_grid).
 //
-// Arithmetic is the reference's: weights in fp32, rounded to fp16, one fp32 FMA per corner whose
-// result is rounded back to fp16 after every corner (grid.h:334 via common.h:539-559).
+// BACKWARD.  grad[idx] += half2(d_enc * w) with f16x2 reductions, exactly the reference's atomicAdd(__half2)
+// (grid.h:427-431); a CTA owns 128 consecutive samples for all levels.
 #include "mon_device.cuh"
 #include "mon_kernels.h"
+#include "tc05.cuh"
 
-#define ENC_THREADS 512
-#define ENC_TILE 128
+// ---------------------------------------------------------------------------------------------- sample points
+// A3: t_n = tmin + dt*(n + xi), p = o + t*d, u = (p - bmin) / (bmax - bmin)  (nerf_model.cu:545-565,140-144).
+// One thread per sample; rays of the batch are already compacted and padded.  pts: [N][3] fp32, the reference's
+// PointsInput.  in_box (render only): rays that miss the box get the cube centre (never composited).
+__global__ void __launch_bounds__(256)
+k_sample_points(uint32_t n_points, uint32_t S, const MonRay* __restrict__ rays, const int* __restrict__ in_box,
+                const float* __restrict__ jitter, uint32_t seed, const MonCtrl* __restrict__ ctrl, uint32_t rng_stream,
+                uint32_t iter_fixed, float bmin0, float bmin1, float bmin2, float bmax0, float bmax1, float bmax2,
+                float* __restrict__ pts) {
+    if (ctrl && ctrl->skip) return;
+    const uint32_t pt = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pt >= n_points) return;
+    const uint32_t ray = pt / S, n = pt - ray * S;
+    float u[3] = {0.5f, 0.5f, 0.5f};
+    if (!in_box || in_box[ray]) {
+        const MonRay r = rays[ray];
+        // the batch kernel already advanced ctrl->iter; this iteration's counter is iter-1
+        const uint32_t iter = ctrl ? ctrl->iter - 1 : iter_fixed;
+        const float xi = mon_rand(jitter, seed, iter, rng_stream, pt);
+        const float t = mon_sample_t(r, n, xi, (float)S);
+        const float bmin[3] = {bmin0, bmin1, bmin2}, bmax[3] = {bmax0, bmax1, bmax2};
+        mon_sample_point(r, t, bmin, bmax, u);
+    }
+    pts[(size_t)pt * 3 + 0] = u[0];
+    pts[(size_t)pt * 3 + 1] = u[1];
+    pts[(size_t)pt * 3 + 2] = u[2];
+}
 
+void mon_launch_sample_points(uint32_t n_points, uint32_t S, const MonRay* rays, const int* in_box, const float* jitter,
+                              uint32_t seed, const MonCtrl* ctrl, uint32_t rng_stream, uint32_t iter_fixed,
+                              const float* bmin, const float* bmax, float* pts, cudaStream_t st) {
+    k_sample_points<<<(n_points + 255) / 256, 256, 0, st>>>(n_points, S, rays, in_box, jitter, seed, ctrl, rng_stream, iter_fixed,
+                                                           bmin[0], bmin[1], bmin[2], bmax[0], bmax[1], bmax[2], pts);
+}
+
+// ---------------------------------------------------------------------------------------------- shared helpers
 struct EncCorner { uint32_t idx[8]; float w[8]; };
 
 __device__ __forceinline__ void level_corners(const MonGrid& g, uint32_t l, const float* u, EncCorner& c) {
@@ -40,78 +77,163 @@ __device__ __forceinline__ void level_corners(const MonGrid& g, uint32_t l, cons
     }
 }
 
-// rays: one per S samples.  in_box: optional per-ray validity (render); jitter: injected array or RNG.
-__global__ void __launch_bounds__(ENC_THREADS)
-k_encode_forward(MonGrid g, uint32_t n_points, uint32_t S, const MonRay* __restrict__ rays,
-                 const int* __restrict__ in_box, const float* __restrict__ jitter, uint32_t seed,
-                 const MonCtrl* __restrict__ ctrl, uint32_t rng_stream, uint32_t iter_fixed, float bmin0, float bmin1, float bmin2,
-                 float bmax0, float bmax1, float bmax2, const __half* __restrict__ grid, __half* __restrict__ enc) {
-    if (ctrl && ctrl->skip) return;
-    const uint32_t p = threadIdx.x & (ENC_TILE - 1), lg = threadIdx.x >> 7;
-    const uint32_t pt = blockIdx.x * ENC_TILE + p;
-    if (pt >= n_points) return;
-    const uint32_t ray = pt / S, n = pt - ray * S;
-    uint4 outv = make_uint4(0, 0, 0, 0);
-    if (!in_box || in_box[ray]) {
-        const MonRay r = rays[ray];
-        // the batch kernel already advanced ctrl->iter; this iteration's counter is iter-1
-        const uint32_t iter = ctrl ? ctrl->iter - 1 : iter_fixed;
-        const float xi = mon_rand(jitter, seed, iter, rng_stream, pt);
-        const float t = mon_sample_t(r, n, xi, (float)S);
-        const float bmin[3] = {bmin0, bmin1, bmin2}, bmax[3] = {bmax0, bmax1, bmax2};
-        float u[3];
-        mon_sample_point(r, t, bmin, bmax, u);
-        uint32_t packed[4];
-#pragma unroll
-        for (uint32_t j = 0; j < 4; ++j) {
-            const uint32_t l = lg * 4 + j;
-            uint32_t res2 = 0;
-            if (l < g.n_levels) {
-                EncCorner c;
-                level_corners(g, l, u, c);
-                const __half2* tab = reinterpret_cast<const __half2*>(grid) + g.offset[l];
-                __half2 v[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) v[k] = __ldg(tab + c.idx[k]);
-                __half a0 = __float2half_rn(0.0f), a1 = a0;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float wh = __half2float(__float2half_rn(c.w[k]));
-                    a0 = __float2half_rn(__fmaf_rn(wh, __low2float(v[k]), __half2float(a0)));
-                    a1 = __float2half_rn(__fmaf_rn(wh, __high2float(v[k]), __half2float(a1)));
-                }
-                res2 = (uint32_t)__half_as_ushort(a0) | ((uint32_t)__half_as_ushort(a1) << 16);
-            }
-            packed[j] = res2;
-        }
-        outv = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+// ---------------------------------------------------------------------------------------------- forward
+#define ENC_THREADS 1024
+#define ENC_TABLE_BYTES (65536 * 2)
+#define ENC_BULK_CHUNK 16384u
+
+__device__ __forceinline__ void bulk_load_table(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    // one thread: arm the barrier with the byte count, then issue the TMA bulk copies (global -> shared)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc05::smem_u32(bar)), "r"(bytes) : "memory");
+    const char* src = static_cast<const char*>(gsrc);
+    for (uint32_t off = 0; off < bytes; off += ENC_BULK_CHUNK) {
+        const uint32_t n = min(ENC_BULK_CHUNK, bytes - off);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst + off),
+                     "l"(src + off), "r"(n), "r"(tc05::smem_u32(bar))
+                     : "memory");
     }
-    reinterpret_cast<uint4*>(enc + (size_t)pt * MON_IN)[lg] = outv;
 }
 
-// gradient scatter: grad[idx] += half2(d_enc * w) with f16x2 reductions, exactly the reference's
-// atomicAdd(__half2) (grid.h:427-431).  Zero d_enc pairs (samples after the early stop) are skipped:
-// adding +0 is an identity, so the result is unchanged.
-__global__ void __launch_bounds__(ENC_THREADS)
-k_encode_backward(MonGrid g, uint32_t n_points, uint32_t S, const MonRay* __restrict__ rays,
-                  const float* __restrict__ jitter, uint32_t seed, const MonCtrl* __restrict__ ctrl,
-                  float bmin0, float bmin1, float bmin2, float bmax0, float bmax1, float bmax2,
+// planar: per level [feature 0 table | feature 1 table], each size[l] fp16 (the level starts at 2*offset[l] halves)
+__global__ void __launch_bounds__(ENC_THREADS, 1)
+k_encode_forward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, const __half* __restrict__ planar,
+                 __half* __restrict__ enc_soa, const MonCtrl* __restrict__ ctrl) {
+    extern __shared__ __align__(128) unsigned char enc_smem[];
+    __shared__ __align__(8) uint64_t bar;
+    if (ctrl && ctrl->skip) return;
+    const __half* table = reinterpret_cast<const __half*>(enc_smem);
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) { tc05::mbar_init(&bar, 1); tc05::mbar_fence_init(); }
+    __syncthreads();
+
+    const uint64_t total = (uint64_t)(2 * g.n_levels) * n_points;
+    uint64_t w = total * blockIdx.x / gridDim.x;
+    const uint64_t w_end = total * (blockIdx.x + 1) / gridDim.x;
+    uint32_t phase = 0;
+    while (w < w_end) {
+        const uint32_t job = (uint32_t)(w / n_points);
+        const uint32_t p0 = (uint32_t)(w - (uint64_t)job * n_points);
+        const uint32_t p1 = (uint32_t)min((uint64_t)n_points, (uint64_t)p0 + (w_end - w));
+        const uint32_t l = job >> 1, f = job & 1;
+        const uint32_t size = g.size[l];
+        __syncthreads();                                   // the previous slice is no longer read by anyone
+        if (tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // prior generic reads/writes of the buffer vs. the async-proxy write
+            bulk_load_table(tc05::smem_u32(enc_smem), planar + (size_t)g.offset[l] * 2 + (size_t)f * size, size * 2, &bar);
+        }
+        tc05::mbar_wait(&bar, phase);
+        phase ^= 1u;
+
+        const float scale = g.scale[l];
+        const bool hashed = g.hashed[l] != 0;
+        const uint32_t res = g.res[l];
+        const bool pow2 = (size & (size - 1)) == 0;
+        __half* out = enc_soa + (size_t)job * n_points;
+        if (pow2) {
+            // index arithmetic directly in byte offsets: ((a ^ b ^ c) & (size-1)) * 2 == (2a ^ 2b ^ 2c) & (2*size-2)
+            const uint32_t bmask = 2u * size - 2u;
+            for (uint32_t p = p0 + tid; p < p1; p += ENC_THREADS) {
+                const float u0 = __ldg(pts + (size_t)p * 3), u1 = __ldg(pts + (size_t)p * 3 + 1), u2 = __ldg(pts + (size_t)p * 3 + 2);
+                float fr[3]; uint32_t cell[3];
+                mon_pos_fract(u0, scale, fr[0], cell[0]);
+                mon_pos_fract(u1, scale, fr[1], cell[1]);
+                mon_pos_fract(u2, scale, fr[2], cell[2]);
+                const float g0 = __fsub_rn(1.0f, fr[0]), g1 = __fsub_rn(1.0f, fr[1]), g2 = __fsub_rn(1.0f, fr[2]);
+                // (1*fx)*fy shared by the two z corners; same multiplication order as the reference
+                const float wxy[4] = {__fmul_rn(g0, g1), __fmul_rn(fr[0], g1), __fmul_rn(g0, fr[1]), __fmul_rn(fr[0], fr[1])};
+                uint32_t ax[2], ay[2], az[2];   // per-axis contributions to the byte offset
+                if (hashed) {
+                    ax[0] = cell[0] << 1; ax[1] = (cell[0] + 1u) << 1;
+                    ay[0] = (cell[1] * 2654435761u) << 1; ay[1] = ((cell[1] + 1u) * 2654435761u) << 1;
+                    az[0] = (cell[2] * 805459861u) << 1; az[1] = ((cell[2] + 1u) * 805459861u) << 1;
+                } else {
+                    ax[0] = cell[0] << 1; ax[1] = (cell[0] + 1u) << 1;
+                    ay[0] = (cell[1] * res) << 1; ay[1] = ((cell[1] + 1u) * res) << 1;
+                    az[0] = (cell[2] * res * res) << 1; az[1] = ((cell[2] + 1u) * res * res) << 1;
+                }
+                __half acc = __float2half_rn(0.0f);
+#pragma unroll
+                for (uint32_t k = 0; k < 8; ++k) {
+                    const float wgt = __fmul_rn(wxy[k & 3], (k & 4) ? fr[2] : g2);
+                    const uint32_t off = (hashed ? (ax[k & 1] ^ ay[(k >> 1) & 1] ^ az[k >> 2]) : (ax[k & 1] + ay[(k >> 1) & 1] + az[k >> 2])) & bmask;
+                    const float wh = __half2float(__float2half_rn(wgt));
+                    const __half tv = *reinterpret_cast<const __half*>(enc_smem + off);
+                    acc = __float2half_rn(__fmaf_rn(wh, __half2float(tv), __half2float(acc)));
+                }
+                out[p] = acc;
+            }
+        } else {
+            for (uint32_t p = p0 + tid; p < p1; p += ENC_THREADS) {
+                const float u0 = __ldg(pts + (size_t)p * 3), u1 = __ldg(pts + (size_t)p * 3 + 1), u2 = __ldg(pts + (size_t)p * 3 + 2);
+                float fr[3]; uint32_t cell[3];
+                mon_pos_fract(u0, scale, fr[0], cell[0]);
+                mon_pos_fract(u1, scale, fr[1], cell[1]);
+                mon_pos_fract(u2, scale, fr[2], cell[2]);
+                const float g0 = __fsub_rn(1.0f, fr[0]), g1 = __fsub_rn(1.0f, fr[1]), g2 = __fsub_rn(1.0f, fr[2]);
+                __half acc = __float2half_rn(0.0f);
+#pragma unroll
+                for (uint32_t k = 0; k < 8; ++k) {
+                    float wgt = (k & 1) ? fr[0] : g0;            // == 1.0f * that factor, bit for bit
+                    wgt = __fmul_rn(wgt, (k & 2) ? fr[1] : g1);
+                    wgt = __fmul_rn(wgt, (k & 4) ? fr[2] : g2);
+                    const uint32_t idx = mon_grid_index(hashed, size, res, cell[0] + (k & 1), cell[1] + ((k >> 1) & 1), cell[2] + ((k >> 2) & 1));
+                    const float wh = __half2float(__float2half_rn(wgt));
+                    acc = __float2half_rn(__fmaf_rn(wh, __half2float(table[idx]), __half2float(acc)));
+                }
+                out[p] = acc;
+            }
+        }
+        w += p1 - p0;
+    }
+}
+
+cudaError_t mon_launch_encode_forward(const MonGrid& g, uint32_t n_points, const float* pts, const __half* planar, __half* enc_soa,
+                                      const MonCtrl* ctrl, uint32_t sm_count, cudaStream_t st) {
+    static cudaError_t prep = cudaFuncSetAttribute(k_encode_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_TABLE_BYTES);
+    if (prep != cudaSuccess) return prep;
+    if (n_points == 0) return cudaSuccess;
+    // every CTA loads up to two 128 KB slices: do not spread tiny batches over the whole chip
+    const uint64_t total = (uint64_t)(2 * g.n_levels) * n_points;
+    const uint64_t want = (total + 16383) / 16384;
+    uint32_t ctas = want < (uint64_t)sm_count ? (uint32_t)want : sm_count;
+    if (ctas == 0) ctas = 1;
+    k_encode_forward<<<ctas, ENC_THREADS, ENC_TABLE_BYTES, st>>>(g, n_points, pts, planar, enc_soa, ctrl);
+    return cudaGetLastError();
+}
+
+// interleaved fp16 weights [entry][2] -> planar per level [f0 table | f1 table] (initialisation / set_params; the
+// optimizer sweep keeps both copies current afterwards)
+__global__ void k_planarize(MonGrid g, uint32_t n_entries, const __half* __restrict__ inter, __half* __restrict__ planar) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_entries) return;
+    uint32_t l = 0;
+    while (l + 1 < g.n_levels && e >= g.offset[l + 1]) ++l;
+    const uint32_t local = e - g.offset[l], size = g.size[l];
+    const __half2 v = reinterpret_cast<const __half2*>(inter)[e];
+    planar[(size_t)g.offset[l] * 2 + local] = __low2half(v);
+    planar[(size_t)g.offset[l] * 2 + size + local] = __high2half(v);
+}
+void mon_launch_planarize(const MonGrid& g, const __half* inter, __half* planar, cudaStream_t st) {
+    const uint32_t n = g.offset[g.n_levels];
+    k_planarize<<<(n + 255) / 256, 256, 0, st>>>(g, n, inter, planar);
+}
+
+// ---------------------------------------------------------------------------------------------- backward
+#define SCT_THREADS 512
+#define SCT_TILE 128
+
+// Zero d_enc pairs (samples after the early stop) are skipped: adding +0 is an identity, so the result is unchanged.
+__global__ void __launch_bounds__(SCT_THREADS)
+k_encode_backward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, const MonCtrl* __restrict__ ctrl,
                   const __half* __restrict__ d_enc, __half* __restrict__ grid_grad) {
     if (ctrl->skip) return;
-    const uint32_t p = threadIdx.x & (ENC_TILE - 1), lg = threadIdx.x >> 7;
-    const uint32_t pt = blockIdx.x * ENC_TILE + p;
+    const uint32_t p = threadIdx.x & (SCT_TILE - 1), lg = threadIdx.x >> 7;
+    const uint32_t pt = blockIdx.x * SCT_TILE + p;
     if (pt >= n_points) return;
     const uint4 gv = reinterpret_cast<const uint4*>(d_enc + (size_t)pt * MON_IN)[lg];
     const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
     if (((gv.x | gv.y | gv.z | gv.w) & 0x7fff7fffu) == 0) return;
-    const uint32_t ray = pt / S, n = pt - ray * S;
-    const MonRay r = rays[ray];
-    const uint32_t iter = ctrl->iter - 1;
-    const float xi = mon_rand(jitter, seed, iter, 2, pt);
-    const float t = mon_sample_t(r, n, xi, (float)S);
-    const float bmin[3] = {bmin0, bmin1, bmin2}, bmax[3] = {bmax0, bmax1, bmax2};
-    float u[3];
-    mon_sample_point(r, t, bmin, bmax, u);
+    const float u[3] = {__ldg(pts + (size_t)pt * 3), __ldg(pts + (size_t)pt * 3 + 1), __ldg(pts + (size_t)pt * 3 + 2)};
 #pragma unroll
     for (uint32_t j = 0; j < 4; ++j) {
         const uint32_t l = lg * 4 + j;
@@ -129,43 +251,8 @@ k_encode_backward(MonGrid g, uint32_t n_points, uint32_t S, const MonRay* __rest
     }
 }
 
-void mon_launch_encode_forward(const MonGrid& g, uint32_t n_points, uint32_t S, const MonRay* rays, const int* in_box,
-                               const float* jitter, uint32_t seed, const MonCtrl* ctrl, uint32_t rng_stream, uint32_t iter_fixed,
-                               const float* bmin, const float* bmax, const __half* grid, __half* enc, cudaStream_t st) {
-    const uint32_t blocks = (n_points + ENC_TILE - 1) / ENC_TILE;
-    k_encode_forward<<<blocks, ENC_THREADS, 0, st>>>(g, n_points, S, rays, in_box, jitter, seed, ctrl, rng_stream, iter_fixed,
-                                                    bmin[0], bmin[1], bmin[2], bmax[0], bmax[1], bmax[2], grid, enc);
-}
-void mon_launch_encode_backward(const MonGrid& g, uint32_t n_points, uint32_t S, const MonRay* rays,
-                                const float* jitter, uint32_t seed, const MonCtrl* ctrl,
-                                const float* bmin, const float* bmax, const __half* d_enc, __half* grid_grad, cudaStream_t st) {
-    const uint32_t blocks = (n_points + ENC_TILE - 1) / ENC_TILE;
-    k_encode_backward<<<blocks, ENC_THREADS, 0, st>>>(g, n_points, S, rays, jitter, seed, ctrl,
-                                                     bmin[0], bmin[1], bmin[2], bmax[0], bmax[1], bmax[2], d_enc, grid_grad);
-}
-
-// stand-alone encode of explicit unit-cube positions (parity hook mon_stage_encode)
-__global__ void k_encode_points(MonGrid g, uint32_t n_points, const float* __restrict__ pts,
-                                const __half* __restrict__ grid, __half* __restrict__ enc) {
-    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t pt = gid / g.n_levels, l = gid - pt * g.n_levels;
-    if (pt >= n_points) return;
-    const float u[3] = {pts[pt * 3], pts[pt * 3 + 1], pts[pt * 3 + 2]};
-    EncCorner c;
-    level_corners(g, l, u, c);
-    const __half2* tab = reinterpret_cast<const __half2*>(grid) + g.offset[l];
-    __half a0 = __float2half_rn(0.0f), a1 = a0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const __half2 v = __ldg(tab + c.idx[k]);
-        const float wh = __half2float(__float2half_rn(c.w[k]));
-        a0 = __float2half_rn(__fmaf_rn(wh, __low2float(v), __half2float(a0)));
-        a1 = __float2half_rn(__fmaf_rn(wh, __high2float(v), __half2float(a1)));
-    }
-    enc[(size_t)pt * (2 * g.n_levels) + 2 * l] = a0;
-    enc[(size_t)pt * (2 * g.n_levels) + 2 * l + 1] = a1;
-}
-void mon_launch_encode_points(const MonGrid& g, uint32_t n_points, const float* pts, const __half* grid, __half* enc, cudaStream_t st) {
-    const uint32_t total = n_points * g.n_levels;
-    k_encode_points<<<(total + 255) / 256, 256, 0, st>>>(g, n_points, pts, grid, enc);
+void mon_launch_encode_backward(const MonGrid& g, uint32_t n_points, const float* pts, const MonCtrl* ctrl,
+                                const __half* d_enc, __half* grid_grad, cudaStream_t st) {
+    const uint32_t blocks = (n_points + SCT_TILE - 1) / SCT_TILE;
+    k_encode_backward<<<blocks, SCT_THREADS, 0, st>>>(g, n_points, pts, ctrl, d_enc, grid_grad);
 }

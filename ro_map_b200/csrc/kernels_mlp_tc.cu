@@ -6,7 +6,7 @@
 // warp-parallel volume renderer (render_math.cuh) wants, so the network output never leaves the SM between the
 // last GEMM and compositing.  Per tile, for the training kernel:
 //
-//   enc tile (global, point-major fp16) --> smem [128 x 32]  K-major SWIZZLE_64B
+//   enc tile (global, feature-major fp16) --> smem [128 x 32]  K-major SWIZZLE_64B
 //   MMA1  D[128x64]   = enc  . W_in^T            (K = 32)      epilogue: ReLU, fp16  --> hid  smem SW128
 //   MMA2  O[128x16]   = hid  . W_out^T           (K = 64)      epilogue: sigmoid/exp, warp-scan compositing,
 //                                                              loss, dL/dout fp16    --> dout smem (core layout)
@@ -134,21 +134,21 @@ __device__ __forceinline__ void tc_load_weights(const TcCtx& c, const __half* __
     }
 }
 
-// stage one 128 x 32 fp16 tile of encodings (64 B per point, contiguous) into the SW64 operand layout;
-// rows >= n_valid are zero-filled
-__device__ __forceinline__ void tc_stage_enc(const TcCtx& c, const __half* __restrict__ enc_tile, uint32_t n_valid) {
-    const uint32_t row = c.tid;
-    uint4 v[4];
-    if (row < n_valid) {
-        const uint4* src = reinterpret_cast<const uint4*>(enc_tile + (size_t)row * MON_IN);
+// stage this thread's row of the 128 x 32 fp16 encoding tile into the SW64 operand layout.  The encoding is
+// feature-major (enc_soa[feature][point], n_total points per feature row): 32 two-byte loads, coalesced across the
+// warp (consecutive threads = consecutive points).  Invalid rows are zero-filled.
+__device__ __forceinline__ void tc_stage_enc(const TcCtx& c, const __half* __restrict__ enc_soa, size_t n_total, size_t pt, bool valid) {
+    const unsigned short* src = reinterpret_cast<const unsigned short*>(enc_soa) + pt;
+    uint32_t packed[16];
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) v[ch] = __ldg(src + ch);
-    } else {
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) v[ch] = make_uint4(0, 0, 0, 0);
+    for (int k = 0; k < 16; ++k) {
+        const uint32_t lo = valid ? (uint32_t)__ldg(src + (size_t)(2 * k) * n_total) : 0u;
+        const uint32_t hi = valid ? (uint32_t)__ldg(src + (size_t)(2 * k + 1) * n_total) : 0u;
+        packed[k] = lo | (hi << 16);
     }
 #pragma unroll
-    for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<uint4*>(c.sm + SM_ENC + sw64_off(row, ch)) = v[ch];
+    for (int ch = 0; ch < 4; ++ch)
+        *reinterpret_cast<uint4*>(c.sm + SM_ENC + sw64_off(c.tid, ch)) = make_uint4(packed[4 * ch], packed[4 * ch + 1], packed[4 * ch + 2], packed[4 * ch + 3]);
 }
 
 // make the CTA's shared-memory writes visible to the tensor core, then let thread 0 issue
@@ -279,7 +279,7 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
         const bool ray_ok = ray < b.R;
         const uint32_t pt = ray * 32 + c.lane;
         // ---- stage encodings, MMA1
-        tc_stage_enc(c, b.enc + (size_t)tile * 128 * MON_IN, min(128u, (b.R - tile * 4) * 32));
+        tc_stage_enc(c, b.enc, (size_t)b.R * 32, pt, ray_ok);
         TC_PUBLISH_AND_SYNC();
         if (c.tid == 0) tc_issue_layer_in(c);
         // per-ray inputs of the renderer, fetched while the tensor core works
@@ -441,7 +441,7 @@ k_mlp_infer_tc(uint32_t n_points, const __half* __restrict__ params, const __hal
     const uint32_t n_tiles = (n_points + 127) / 128;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint32_t pt = tile * 128 + c.tid;
-        tc_stage_enc(c, enc + (size_t)tile * 128 * MON_IN, min(128u, n_points - tile * 128));
+        tc_stage_enc(c, enc, n_points, pt, pt < n_points);
         TC_PUBLISH_AND_SYNC();
         if (c.tid == 0) tc_issue_layer_in(c);
         TC_WAIT(c);
@@ -483,18 +483,8 @@ k_mlp_render_tc(uint32_t n_rays, uint32_t S2, const MonRay* __restrict__ rays, c
         RenderCarry cr; cr.T = 1.0f; cr.C[0] = cr.C[1] = cr.C[2] = 0.0f; cr.D = 0.0f; cr.last_t = 0.0f;
         for (uint32_t chunk = 0; chunk < chunks; ++chunk) {
             // this thread stages the row of its own sample: point (ray, chunk*32 + lane)
-            uint4 v[4];
             const uint32_t pt = ray * S2 + chunk * 32 + c.lane;
-            if (hit) {
-                const uint4* src = reinterpret_cast<const uint4*>(enc + (size_t)pt * MON_IN);
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch) v[ch] = __ldg(src + ch);
-            } else {
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch) v[ch] = make_uint4(0, 0, 0, 0);
-            }
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<uint4*>(c.sm + SM_ENC + sw64_off(c.tid, ch)) = v[ch];
+            tc_stage_enc(c, enc, (size_t)n_rays * S2, pt, hit);
             TC_PUBLISH_AND_SYNC();
             if (c.tid == 0) tc_issue_layer_in(c);
             TC_WAIT(c);

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(OPT_THREADS)
 k_optimizer_sweep(MonOpt o, MonCtrl* __restrict__ ctrl, float* __restrict__ pf, __half* __restrict__ ph,
                   __half* __restrict__ gh, const float* __restrict__ mlp_partials, float* __restrict__ m,
                   float* __restrict__ v, uint32_t* __restrict__ ps, __half* __restrict__ ema,
-                  const float* __restrict__ loss, uint32_t R) {
+                  const float* __restrict__ loss, uint32_t R, MonGrid grid, __half* __restrict__ planar) {
     if (ctrl->skip) return;
     __shared__ float s_lr, s_old, s_new;
     if (blockIdx.x == gridDim.x - 1) {
@@ -135,13 +135,26 @@ k_optimizer_sweep(MonOpt o, MonCtrl* __restrict__ ctrl, float* __restrict__ pf, 
         g[0] = __low2float(gr); g[1] = __high2float(gr);
         if (g[0] != 0.0f || g[1] != 0.0f) *gh2 = __halves2half2(__float2half_rn(0.0f), __float2half_rn(0.0f));
     }
+    // planar copy of the fp16 grid weights, read by the hash-encode kernel: level l holds [feature 0 | feature 1];
+    // entry e of level l sits at 2*offset[l] + f*size[l] + (e - offset[l])
+    __half* planar_dst[2] = {nullptr, nullptr};
+    if (i2 >= o.n_mlp) {
+        const uint32_t e = (i2 - o.n_mlp) >> 1;
+        uint32_t l = 0;
+        while (l + 1 < grid.n_levels && e >= grid.offset[l + 1]) ++l;
+        planar_dst[0] = planar + (size_t)grid.offset[l] * 2 + (e - grid.offset[l]);
+        planar_dst[1] = planar_dst[0] + grid.size[l];
+    }
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         const uint32_t i = i2 + k;
         if (i >= o.n_params) break;
         const bool is_mlp = i < o.n_mlp;
         const float gradient = __fdiv_rn(g[k], o.loss_scale);
-        if (is_mlp || gradient != 0.0f) adam_update(o, lr_base, gradient, i, is_mlp, pf, ph, m, v, ps);
+        if (is_mlp || gradient != 0.0f) {
+            adam_update(o, lr_base, gradient, i, is_mlp, pf, ph, m, v, ps);
+            if (!is_mlp) *planar_dst[k] = ph[i];
+        }
         // EMA over all params with the global step (ema.h:62-76)
         const float e = __half2float(ema[i]);
         const float w = __half2float(ph[i]);
@@ -189,9 +202,10 @@ void mon_launch_cast_params(uint32_t n, const float* pf, __half* ph, cudaStream_
     k_cast_params<<<(n + 255) / 256, 256, 0, st>>>(n, pf, ph);
 }
 void mon_launch_optimizer(const MonOpt& o, MonCtrl* ctrl, float* pf, __half* ph, __half* gh, const float* partials,
-                          float* m, float* v, uint32_t* ps, __half* ema, const float* loss, uint32_t R, cudaStream_t st) {
+                          float* m, float* v, uint32_t* ps, __half* ema, const float* loss, uint32_t R, const MonGrid& grid,
+                          __half* planar, cudaStream_t st) {
     const uint32_t pairs = (o.n_params + 1) / 2;
-    k_optimizer_sweep<<<(pairs + OPT_THREADS - 1) / OPT_THREADS, OPT_THREADS, 0, st>>>(o, ctrl, pf, ph, gh, partials, m, v, ps, ema, loss, R);
+    k_optimizer_sweep<<<(pairs + OPT_THREADS - 1) / OPT_THREADS, OPT_THREADS, 0, st>>>(o, ctrl, pf, ph, gh, partials, m, v, ps, ema, loss, R, grid, planar);
 }
 void mon_launch_snapshot_grad(uint32_t n, uint32_t n_mlp, uint32_t n_partials, const __half* gh, const float* partials, float* out, cudaStream_t st) {
     k_snapshot_grad<<<(n + 255) / 256, 256, 0, st>>>(n, n_mlp, n_partials, gh, partials, out);

@@ -175,14 +175,17 @@ struct mon_object {
     uint8_t* ray_inst = nullptr;
     float *target = nullptr, *target_depth = nullptr, *bg = nullptr;
     float *rgb_rays = nullptr, *depth_rays = nullptr, *mask_rays = nullptr, *loss = nullptr;
-    __half *enc = nullptr, *d_enc = nullptr;
+    float* pts = nullptr;             // [N][3] unit-cube sample positions (the reference's PointsInput)
+    __half *enc = nullptr, *d_enc = nullptr;   // enc: feature-major [32][N]; d_enc: point-major [N][32]
+    __half* ph_planar = nullptr;      // fp16 grid weights, per level [feature 0 | feature 1], kept current by the optimizer
     float* partials = nullptr;
     uint32_t n_ctas = 0;
     // parity hooks (lazily allocated)
     float *dbg_out = nullptr, *dbg_dout = nullptr, *inj_xy = nullptr, *inj_col = nullptr, *inj_dt = nullptr, *grad_snap = nullptr;
     bool have_injected = false;
     // render workspace (lazily allocated)
-    MonRay* r_rays = nullptr; int* r_inbox = nullptr; __half* r_enc = nullptr; float* r_jit = nullptr;
+    MonRay* r_rays = nullptr; int* r_inbox = nullptr; __half* r_enc = nullptr; float* r_jit = nullptr; float* r_pts = nullptr;
+    __half* r_planar = nullptr;       // planar copy of the EMA weights, refreshed per render call
     float *r_rgb = nullptr, *r_depth = nullptr, *r_mask = nullptr, *r_Twc = nullptr;
     uint32_t r_cap_rays = 0, r_tile = 0; size_t r_jit_cap = 0;
     uint32_t render_count = 0;
@@ -193,7 +196,6 @@ struct mon_object {
     bool timing_pending = false;
     float last_ms = 0.0f;
     uint64_t launches = 0;
-    int mlp_impl = 1;
     int sm_count = 148;
 };
 
@@ -472,24 +474,22 @@ static int enqueue_iteration(mon_object* o, const MonBatch& b, bool snapshot_gra
     if (ev) CK(cudaEventRecord(ev[0], st));
     mon_launch_generate_batch(b, o->scene, st); ++n;
     if (ev) CK(cudaEventRecord(ev[1], st));
-    mon_launch_encode_forward(o->grid, o->N, MON_S, o->rays, nullptr, b.inj_dt, o->seed, o->ctrl, 2, 0,
-                              o->scene.bmin, o->scene.bmax, o->ph + o->n_mlp, o->enc, st); ++n;
+    mon_launch_sample_points(o->N, MON_S, o->rays, nullptr, b.inj_dt, o->seed, o->ctrl, 2, 0, o->scene.bmin, o->scene.bmax, o->pts, st); ++n;
     if (ev) CK(cudaEventRecord(ev[2], st));
-    cudaError_t e;
-#ifdef MON_HAVE_TC
-    if (o->mlp_impl == 0) e = mon_launch_mlp_train_tc(b, o->lc, o->cfg.n_hidden_layers, o->n_mlp, o->n_ctas, st);
-    else
-#endif
-    e = mon_launch_mlp_train_wmma(b, o->lc, o->n_mlp, o->n_ctas, st);
-    if (e != cudaSuccess) return fail(MON_ERR_CUDA, "fused MLP launch: %s", cudaGetErrorString(e));
+    cudaError_t e = mon_launch_encode_forward(o->grid, o->N, o->pts, o->ph_planar, o->enc, o->ctrl, (uint32_t)o->sm_count, st);
+    if (e != cudaSuccess) return fail(MON_ERR_CUDA, "hash encode launch: %s", cudaGetErrorString(e));
     ++n;
     if (ev) CK(cudaEventRecord(ev[3], st));
-    mon_launch_encode_backward(o->grid, o->N, MON_S, o->rays, b.inj_dt, o->seed, o->ctrl,
-                               o->scene.bmin, o->scene.bmax, o->d_enc, o->gh + o->n_mlp, st); ++n;
-    if (snapshot_grad) { mon_launch_snapshot_grad(o->P, o->n_mlp, o->opt.n_partials, o->gh, o->partials, o->grad_snap, st); ++n; }
+    e = mon_launch_mlp_train_tc(b, o->lc, o->cfg.n_hidden_layers, o->n_mlp, o->n_ctas, st);
+    if (e != cudaSuccess) return fail(MON_ERR_CUDA, "fused MLP launch: %s", cudaGetErrorString(e));
+    ++n;
     if (ev) CK(cudaEventRecord(ev[4], st));
-    mon_launch_optimizer(o->opt, o->ctrl, o->pf, o->ph, o->gh, o->partials, o->m, o->v, o->ps, o->ema, o->loss, o->R, st); ++n;
+    mon_launch_encode_backward(o->grid, o->N, o->pts, o->ctrl, o->d_enc, o->gh + o->n_mlp, st); ++n;
+    if (snapshot_grad) { mon_launch_snapshot_grad(o->P, o->n_mlp, o->opt.n_partials, o->gh, o->partials, o->grad_snap, st); ++n; }
     if (ev) CK(cudaEventRecord(ev[5], st));
+    mon_launch_optimizer(o->opt, o->ctrl, o->pf, o->ph, o->gh, o->partials, o->m, o->v, o->ps, o->ema, o->loss, o->R, o->grid,
+                         o->ph_planar, st); ++n;
+    if (ev) CK(cudaEventRecord(ev[6], st));
     CK(cudaGetLastError());
     if (n_launched) *n_launched = n;
     return MON_OK;
@@ -510,7 +510,7 @@ static int capture_graph(mon_object* o, int iters, cudaGraphExec_t* out) {
     return MON_OK;
 }
 
-static const int kKernelsPerIter = 5;
+static const int kKernelsPerIter = 6;
 
 int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uint8_t instance_id,
                       const float obj_Tow[16], const float bmin[3], const float bmax[3], mon_object** out) {
@@ -524,12 +524,6 @@ int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uin
     CK(cudaSetDevice(ds->gpu));
     mon_object* o = new mon_object();
     o->ds = ds; o->cfg = *cfg; o->grid = grid; o->seed = seed;
-#ifdef MON_HAVE_TC
-    o->mlp_impl = 0;
-#else
-    o->mlp_impl = 1;
-    if (cfg->n_hidden_layers != 1) { delete o; return fail(MON_ERR_STATE, "n_hidden_layers > 1 needs the tcgen05 MLP kernel, which this build lacks"); }
-#endif
     o->n_mlp = n_mlp_params(*cfg);
     o->n_grid = grid.offset[cfg->n_levels] * 2;
     o->P = o->n_mlp + o->n_grid;
@@ -565,7 +559,8 @@ int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uin
     OALLOC(o->rays, R * sizeof(MonRay)); OALLOC(o->ray_inst, R);
     OALLOC(o->target, R * 12); OALLOC(o->target_depth, R * 4); OALLOC(o->bg, R * 12);
     OALLOC(o->rgb_rays, R * 12); OALLOC(o->depth_rays, R * 4); OALLOC(o->mask_rays, R * 4); OALLOC(o->loss, R * 4);
-    OALLOC(o->enc, N * MON_IN * 2); OALLOC(o->d_enc, N * MON_IN * 2);
+    OALLOC(o->pts, N * 12); OALLOC(o->enc, N * MON_IN * 2); OALLOC(o->d_enc, N * MON_IN * 2);
+    OALLOC(o->ph_planar, (size_t)o->n_grid * 2 + 16);
     OALLOC(o->partials, (size_t)o->n_ctas * o->n_mlp * 4);
 #undef OALLOC
     cudaError_t e;
@@ -601,7 +596,8 @@ int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uin
     }
     mon_launch_init_grid(rng.state, rng.inc, o->n_grid, o->pf + o->n_mlp, o->stream);
     mon_launch_cast_params((uint32_t)P, o->pf, o->ph, o->stream);
-    o->launches += 2;
+    mon_launch_planarize(o->grid, o->ph + o->n_mlp, o->ph_planar, o->stream);
+    o->launches += 3;
     if ((e = cudaStreamSynchronize(o->stream)) != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) {
         mon_object_destroy(o);
         return fail(MON_ERR_CUDA, "param init: %s", cudaGetErrorString(e));
@@ -616,9 +612,9 @@ int mon_object_destroy(mon_object* o) {
     if (o->stream) cudaStreamSynchronize(o->stream);
     drop_graphs(o);
     void* ptrs[] = {o->pf, o->m, o->v, o->ps, o->ph, o->gh, o->ema, o->ctrl, o->d_boxes, o->rays, o->ray_inst, o->target,
-                    o->target_depth, o->bg, o->rgb_rays, o->depth_rays, o->mask_rays, o->loss, o->enc, o->d_enc, o->partials,
+                    o->target_depth, o->bg, o->rgb_rays, o->depth_rays, o->mask_rays, o->loss, o->pts, o->enc, o->d_enc, o->ph_planar, o->partials,
                     o->dbg_out, o->dbg_dout, o->inj_xy, o->inj_col, o->inj_dt, o->grad_snap, o->r_rays, o->r_inbox, o->r_enc,
-                    o->r_jit, o->r_rgb, o->r_depth, o->r_mask, o->r_Twc};
+                    o->r_jit, o->r_rgb, o->r_depth, o->r_mask, o->r_Twc, o->r_pts, o->r_planar};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (o->h_ctrl) cudaFreeHost(o->h_ctrl);
     if (o->ev0) cudaEventDestroy(o->ev0);
@@ -774,20 +770,6 @@ int mon_object_launch_count(mon_object* o, uint64_t* n) {
     return MON_OK;
 }
 
-int mon_object_set_mlp_impl(mon_object* o, int impl) {
-    if (!o) return fail(MON_ERR_ARG, "obj is NULL");
-    if (impl != 0 && impl != 1) return fail(MON_ERR_ARG, "impl must be 0 (tcgen05) or 1 (mma.sync validation kernel)");
-#ifndef MON_HAVE_TC
-    if (impl == 0) return fail(MON_ERR_STATE, "this build has no tcgen05 MLP kernel");
-#endif
-    if (impl == 1 && o->cfg.n_hidden_layers != 1) return fail(MON_ERR_STATE, "the mma.sync validation kernel supports n_hidden_layers == 1 only");
-    CK(cudaSetDevice(o->ds->gpu));
-    CK(cudaStreamSynchronize(o->stream));
-    if (impl != o->mlp_impl) drop_graphs(o);
-    o->mlp_impl = impl;
-    return MON_OK;
-}
-
 // ------------------------------------------------------------------------------- parity hooks
 static int ensure_hooks(mon_object* o) {
     if (o->dbg_out) return MON_OK;
@@ -855,6 +837,19 @@ __global__ void k_lattice_points(uint32_t rx, uint32_t ry, uint32_t rz, float* _
     out[3 * i + 1] = __fdiv_rn((float)y, (float)(ry - 1));
     out[3 * i + 2] = __fdiv_rn((float)z, (float)(rz - 1));
 }
+// feature-major fp16 [C][n] -> point-major float [n][C] (parity hooks only)
+__global__ void k_soa_to_rows_float(size_t n, uint32_t C, const __half* __restrict__ soa, float* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * C) return;
+    const size_t p = i / C, c = i - p * C;
+    out[i] = __half2float(soa[c * n + p]);
+}
+__global__ void k_soa_to_rows_half(size_t n, uint32_t C, const __half* __restrict__ soa, __half* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * C) return;
+    const size_t p = i / C, c = i - p * C;
+    out[i] = soa[c * n + p];
+}
 __global__ void k_extract_sigma(size_t n, const float* __restrict__ out4, float* __restrict__ sigma) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) sigma[i] = out4[4 * i + 3];
@@ -908,7 +903,8 @@ int mon_object_set_params(mon_object* o, const float* params, size_t n) {
     CK(cudaSetDevice(o->ds->gpu));
     CK(cudaMemcpyAsync(o->pf, params, n * 4, cudaMemcpyHostToDevice, o->stream));
     mon_launch_cast_params((uint32_t)n, o->pf, o->ph, o->stream);
-    o->launches += 1;
+    mon_launch_planarize(o->grid, o->ph + o->n_mlp, o->ph_planar, o->stream);
+    o->launches += 2;
     CK(cudaStreamSynchronize(o->stream));
     return MON_OK;
 }
@@ -921,7 +917,19 @@ int mon_object_last(mon_object* o, int which, float* out, size_t cap, size_t* n_
     const void* src = nullptr; int kind = 0; size_t n = 0;
     switch (which) {
         case 0: src = o->rays; n = R * 9; break;
-        case 3: src = o->enc; kind = 1; n = N * MON_IN; break;
+        case 1: src = o->pts; n = N * 3; break;
+        case 3: {   // stored feature-major on the device; handed out point-major [N][32] like the other hooks
+            n = N * MON_IN;
+            if (n_out) *n_out = n;
+            if (cap < n) return fail(MON_ERR_ARG, "buffer too small: need %zu floats", n);
+            float* tmp = nullptr;
+            CK(cudaMalloc(&tmp, n * 4));
+            k_soa_to_rows_float<<<(unsigned)((n + 255) / 256), 256, 0, o->stream>>>(N, MON_IN, o->enc, tmp);
+            o->launches += 1;
+            const int rc = fetch_as_float(o, tmp, 0, n, out);
+            cudaFree(tmp);
+            return rc;
+        }
         case 4: src = o->dbg_out; n = N * 4; break;
         case 5: src = o->rgb_rays; n = R * 3; break;
         case 6: src = o->depth_rays; n = R; break;
@@ -957,6 +965,8 @@ static int ensure_render_ws(mon_object* o, uint32_t n_rays, size_t jitter_floats
     }
     if (!o->r_enc) {
         CK(cudaMalloc(&o->r_enc, (size_t)tile * S2 * MON_IN * 2));
+        CK(cudaMalloc(&o->r_pts, (size_t)tile * S2 * 12));
+        CK(cudaMalloc(&o->r_planar, (size_t)o->n_grid * 2 + 16));
         CK(cudaMalloc(&o->r_Twc, 64));
         o->r_tile = tile;
     }
@@ -974,7 +984,6 @@ int mon_object_render(mon_object* o, mon_bbox2d box, const float Twc[16], int us
     if (!o || !Twc || !rgb || !depth || !mask) return fail(MON_ERR_ARG, "NULL argument");
     if (box.w == 0 || box.h == 0) return fail(MON_ERR_ARG, "empty render box");
     if ((uint64_t)box.w * box.h > (1u << 26)) return fail(MON_ERR_ARG, "render box too large");
-    if (o->cfg.n_hidden_layers != 1 && o->mlp_impl == 1) return fail(MON_ERR_STATE, "render needs the tcgen05 kernel for n_hidden_layers > 1");
     CK(cudaSetDevice(o->ds->gpu));
     const uint32_t n_rays = box.w * box.h, S2 = o->cfg.render_samples_per_ray;
     int rc = ensure_render_ws(o, n_rays, rand_dt ? (size_t)n_rays * S2 : 0);
@@ -985,24 +994,25 @@ int mon_object_render(mon_object* o, mon_bbox2d box, const float Twc[16], int us
     mon_launch_render_rays(n_rays, box, o->scene, o->r_Twc, o->r_rays, o->r_inbox, st);
     o->launches += 1;
     const __half* params = use_ema ? o->ema : o->ph;
+    const __half* planar = o->ph_planar;
+    if (use_ema) {   // the EMA weights have no resident planar copy: renders are rare, refresh one per call
+        mon_launch_planarize(o->grid, o->ema + o->n_mlp, o->r_planar, st);
+        o->launches += 1;
+        planar = o->r_planar;
+    }
     const uint32_t rc_id = o->render_count++;
     for (uint32_t r0 = 0, t = 0; r0 < n_rays; r0 += o->r_tile, ++t) {
         const uint32_t nr = std::min(o->r_tile, n_rays - r0);
         const float* jit = rand_dt ? o->r_jit + (size_t)r0 * S2 : nullptr;
         const uint32_t iter_fixed = rc_id * 4099u + t;
-        mon_launch_encode_forward(o->grid, nr * S2, S2, o->r_rays + r0, o->r_inbox + r0, jit, o->seed, nullptr, 3, iter_fixed,
-                                  o->scene.bmin, o->scene.bmax, params + o->n_mlp, o->r_enc, st);
-        cudaError_t e;
-#ifdef MON_HAVE_TC
-        if (o->mlp_impl == 0)
+        mon_launch_sample_points(nr * S2, S2, o->r_rays + r0, o->r_inbox + r0, jit, o->seed, nullptr, 3, iter_fixed,
+                                 o->scene.bmin, o->scene.bmax, o->r_pts, st);
+        cudaError_t e = mon_launch_encode_forward(o->grid, nr * S2, o->r_pts, planar, o->r_enc, nullptr, (uint32_t)o->sm_count, st);
+        if (e == cudaSuccess)
             e = mon_launch_mlp_render_tc(nr, S2, o->cfg.n_hidden_layers, o->r_rays + r0, o->r_inbox + r0, jit, o->seed, iter_fixed, params,
                                          o->r_enc, 1.0f, o->r_rgb + (size_t)r0 * 3, o->r_depth + r0, o->r_mask + r0, st);
-        else
-#endif
-        e = mon_launch_mlp_render_wmma(nr, S2, o->r_rays + r0, o->r_inbox + r0, jit, o->seed, iter_fixed, params,
-                                       o->r_enc, 1.0f, o->r_rgb + (size_t)r0 * 3, o->r_depth + r0, o->r_mask + r0, st);
         if (e != cudaSuccess) return fail(MON_ERR_CUDA, "render launch: %s", cudaGetErrorString(e));
-        o->launches += 2;
+        o->launches += 3;
     }
     CK(cudaMemcpyAsync(rgb, o->r_rgb, (size_t)n_rays * 12, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(depth, o->r_depth, (size_t)n_rays * 4, cudaMemcpyDeviceToHost, st));
@@ -1017,7 +1027,6 @@ int mon_object_density_grid(mon_object* o, const uint32_t res[3], float* out) {
     if (res[0] < 2 || res[1] < 2 || res[2] < 2) return fail(MON_ERR_ARG, "resolution must be >= 2 per axis");
     const size_t n = (size_t)res[0] * res[1] * res[2];
     if (n > (1u << 27)) return fail(MON_ERR_ARG, "lattice too large");
-    if (o->cfg.n_hidden_layers != 1 && o->mlp_impl == 1) return fail(MON_ERR_STATE, "needs the tcgen05 kernel for n_hidden_layers > 1");
     CK(cudaSetDevice(o->ds->gpu));
     cudaStream_t st = o->stream;
     float *pts = nullptr, *out4 = nullptr, *sigma = nullptr; __half* enc = nullptr;
@@ -1028,12 +1037,8 @@ int mon_object_density_grid(mon_object* o, const uint32_t res[3], float* out) {
     if (e == cudaSuccess) {
         const unsigned blocks = (unsigned)((n + 255) / 256);
         k_lattice_points<<<blocks, 256, 0, st>>>(res[0], res[1], res[2], pts);
-        mon_launch_encode_points(o->grid, (uint32_t)n, pts, o->ph + o->n_mlp, enc, st);
-#ifdef MON_HAVE_TC
-        if (o->mlp_impl == 0) e = mon_launch_mlp_infer_tc((uint32_t)n, o->cfg.n_hidden_layers, o->ph, enc, out4, st);
-        else
-#endif
-        e = mon_launch_mlp_infer_wmma((uint32_t)n, o->ph, enc, out4, st);
+        e = mon_launch_encode_forward(o->grid, (uint32_t)n, pts, o->ph_planar, enc, nullptr, (uint32_t)o->sm_count, st);
+        if (e == cudaSuccess) e = mon_launch_mlp_infer_tc((uint32_t)n, o->cfg.n_hidden_layers, o->ph, enc, out4, st);
         k_extract_sigma<<<blocks, 256, 0, st>>>(n, out4, sigma);
         o->launches += 4;
         if (e == cudaSuccess) e = cudaMemcpyAsync(out, sigma, n * 4, cudaMemcpyDeviceToHost, st);
@@ -1057,20 +1062,30 @@ int mon_stage_encode(const mon_config* cfg, const uint16_t* grid_fp16, size_t n_
     if (n_points == 0) return MON_OK;
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return fail(MON_ERR_NO_DEVICE, "no CUDA device (this library has no CPU path)"); }
-    __half *d_grid = nullptr, *d_enc = nullptr; float* d_pts = nullptr;
+    __half *d_grid = nullptr, *d_planar = nullptr, *d_soa = nullptr, *d_enc = nullptr; float* d_pts = nullptr;
     const size_t enc_bytes = (size_t)n_points * 2 * cfg->n_levels * 2;
-    cudaError_t e = cudaMalloc(&d_grid, n_grid_params * 2);
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, 0);
+    if (e == cudaSuccess) e = cudaSetDevice(0);
+    if (e == cudaSuccess) e = cudaMalloc(&d_grid, n_grid_params * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&d_planar, n_grid_params * 2);
     if (e == cudaSuccess) e = cudaMalloc(&d_pts, (size_t)n_points * 12);
+    if (e == cudaSuccess) e = cudaMalloc(&d_soa, enc_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&d_enc, enc_bytes);
     if (e == cudaSuccess) e = cudaMemcpy(d_grid, grid_fp16, n_grid_params * 2, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(d_pts, points_unit, (size_t)n_points * 12, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
-        mon_launch_encode_points(g, n_points, d_pts, d_grid, d_enc, nullptr);
-        e = cudaGetLastError();
+        mon_launch_planarize(g, d_grid, d_planar, nullptr);
+        e = mon_launch_encode_forward(g, n_points, d_pts, d_planar, d_soa, nullptr, (uint32_t)prop.multiProcessorCount, nullptr);
+        const size_t total = (size_t)n_points * 2 * cfg->n_levels;
+        if (e == cudaSuccess) k_soa_to_rows_half<<<(unsigned)((total + 255) / 256), 256>>>(n_points, 2 * cfg->n_levels, d_soa, d_enc);
+        if (e == cudaSuccess) e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpy(enc_out, d_enc, enc_bytes, cudaMemcpyDeviceToHost);
     if (d_grid) cudaFree(d_grid);
+    if (d_planar) cudaFree(d_planar);
     if (d_pts) cudaFree(d_pts);
+    if (d_soa) cudaFree(d_soa);
     if (d_enc) cudaFree(d_enc);
     if (e != cudaSuccess) return fail(MON_ERR_CUDA, "mon_stage_encode: %s", cudaGetErrorString(e));
     return MON_OK;

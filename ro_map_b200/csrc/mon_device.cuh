@@ -86,8 +86,9 @@ MON_DEV void mon_pos_fract(float input, float scale, float& frac, uint32_t& cell
 }
 
 MON_DEV uint32_t mon_grid_index(bool hashed, uint32_t size, uint32_t res, uint32_t x, uint32_t y, uint32_t z) {
-    // size is a power of two for every hashed level and for the dense levels of the supported
-    // configurations (res^3 padded to 8): modulo == mask only then, so keep the general form.
-    uint32_t index = hashed ? (x ^ (y * 2654435761u) ^ (z * 805459861u)) : (x + y * res + z * res * res);
-    return index % size;
+    // the dense form wraps in uint32 exactly like the reference's running stride (res == 65536: z*res*res == 0)
+    const uint32_t index = hashed ? (x ^ (y * 2654435761u) ^ (z * 805459861u)) : (x + y * res + z * res * res);
+    // every table of the supported configurations is a power of two (res^3 padded to 8, capped at 2^log2_hashmap_size);
+    // the general modulo is kept for the ones that are not
+    return (size & (size - 1)) == 0 ? (index & (size - 1)) : (index % size);
 }

@@ -8,20 +8,14 @@ void mon_launch_render_rays(uint32_t n_rays, mon_bbox2d box, const MonScene& sc,
                             MonRay* rays, int* in_box, cudaStream_t st);
 
 // kernels_encode.cu
-void mon_launch_encode_forward(const MonGrid& g, uint32_t n_points, uint32_t S, const MonRay* rays, const int* in_box,
-                               const float* jitter, uint32_t seed, const MonCtrl* ctrl, uint32_t rng_stream, uint32_t iter_fixed,
-                               const float* bmin, const float* bmax, const __half* grid, __half* enc, cudaStream_t st);
-void mon_launch_encode_backward(const MonGrid& g, uint32_t n_points, uint32_t S, const MonRay* rays,
-                                const float* jitter, uint32_t seed, const MonCtrl* ctrl,
-                                const float* bmin, const float* bmax, const __half* d_enc, __half* grid_grad, cudaStream_t st);
-void mon_launch_encode_points(const MonGrid& g, uint32_t n_points, const float* pts, const __half* grid, __half* enc, cudaStream_t st);
-
-// kernels_mlp_wmma.cu (legacy mma.sync validation family)
-cudaError_t mon_launch_mlp_train_wmma(const MonBatch& b, const MonLossCfg& lc, uint32_t n_mlp, uint32_t n_ctas, cudaStream_t st);
-cudaError_t mon_launch_mlp_render_wmma(uint32_t n_rays, uint32_t S2, const MonRay* rays, const int* in_box, const float* jitter,
-                                       uint32_t seed, uint32_t iter, const __half* params, const __half* enc, float bgc,
-                                       float* rgb, float* depth, float* mask, cudaStream_t st);
-cudaError_t mon_launch_mlp_infer_wmma(uint32_t n_points, const __half* params, const __half* enc, float* out4, cudaStream_t st);
+void mon_launch_sample_points(uint32_t n_points, uint32_t S, const MonRay* rays, const int* in_box, const float* jitter,
+                              uint32_t seed, const MonCtrl* ctrl, uint32_t rng_stream, uint32_t iter_fixed,
+                              const float* bmin, const float* bmax, float* pts, cudaStream_t st);
+cudaError_t mon_launch_encode_forward(const MonGrid& g, uint32_t n_points, const float* pts, const __half* planar, __half* enc_soa,
+                                      const MonCtrl* ctrl, uint32_t sm_count, cudaStream_t st);
+void mon_launch_planarize(const MonGrid& g, const __half* inter, __half* planar, cudaStream_t st);
+void mon_launch_encode_backward(const MonGrid& g, uint32_t n_points, const float* pts, const MonCtrl* ctrl,
+                                const __half* d_enc, __half* grid_grad, cudaStream_t st);
 
 // kernels_mlp_tc.cu (tcgen05 / TMEM product family)
 cudaError_t mon_launch_mlp_train_tc(const MonBatch& b, const MonLossCfg& lc, uint32_t n_hidden, uint32_t n_mlp,
@@ -36,7 +30,8 @@ cudaError_t mon_launch_mlp_render_tc(uint32_t n_rays, uint32_t S2, uint32_t n_hi
 void mon_launch_init_grid(uint64_t state, uint64_t inc, uint32_t n, float* out, cudaStream_t st);
 void mon_launch_cast_params(uint32_t n, const float* pf, __half* ph, cudaStream_t st);
 void mon_launch_optimizer(const MonOpt& o, MonCtrl* ctrl, float* pf, __half* ph, __half* gh, const float* partials,
-                          float* m, float* v, uint32_t* ps, __half* ema, const float* loss, uint32_t R, cudaStream_t st);
+                          float* m, float* v, uint32_t* ps, __half* ema, const float* loss, uint32_t R, const MonGrid& grid,
+                          __half* planar, cudaStream_t st);
 void mon_launch_snapshot_grad(uint32_t n, uint32_t n_mlp, uint32_t n_partials, const __half* gh, const float* partials,
                               float* out, cudaStream_t st);
 void mon_launch_sum_loss(uint32_t R, const float* loss, MonCtrl* ctrl, cudaStream_t st);

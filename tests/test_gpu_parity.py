@@ -32,12 +32,10 @@ def gpu_dataset(core, small_seq):
     return ds
 
 
-def make_pair(core, oracle, ds, seq, obj, R, n_hidden=1, seed=1337, mlp_impl=None, n_threads=8):
+def make_pair(core, oracle, ds, seq, obj, R, n_hidden=1, seed=1337, n_threads=8):
     cfg = core.default_config(rays_per_batch=R, n_hidden_layers=n_hidden)
     bmin, bmax = -1.1 * obj.half, 1.1 * obj.half
     g = core.NerfObject(ds, cfg, obj.Tow, bmin, bmax, obj.instance_id, seed)
-    if mlp_impl is not None:
-        g.set_mlp_impl(mlp_impl)
     g.set_bboxes(obj.boxes)
     ocfg = oracle.default_config(n_hidden_layers=n_hidden)
     o = oracle.OracleObject(ocfg, R, 32, obj.Tow, bmin, bmax, obj.instance_id, True, seed, n_threads=n_threads)
@@ -55,19 +53,6 @@ def ulp16_diff(a, b):
     ai = np.where(ai < 0, -32768 - ai, ai)
     bi = np.where(bi < 0, -32768 - bi, bi)
     return np.abs(ai - bi)
-
-
-IMPLS = [1, 0]  # 1: mma.sync validation kernel, 0: tcgen05 product kernel
-
-
-def _impl_or_skip(g, impl):
-    from ro_map_b200.core import MonError
-    try:
-        g.set_mlp_impl(impl)
-    except MonError as e:
-        if "no tcgen05" in str(e):
-            pytest.skip("tcgen05 kernel not in this build")
-        raise
 
 
 def test_param_init_bit_exact(core, oracle, gpu_dataset, small_seq):
@@ -91,16 +76,10 @@ def test_stage_encode_bit_exact(core, oracle):
     assert core.stage_encode(cfg, grid, np.zeros((0, 3), np.float32)).shape == (0, 32)   # empty input
 
 
-@pytest.mark.parametrize("R,impl,n_hidden", [(256, 1, 1), (1024, 1, 1), (256, 0, 1), (1024, 0, 1), (512, 0, 2)])
-def test_one_iteration_stage_by_stage(core, oracle, gpu_dataset, small_seq, R, impl, n_hidden):
+@pytest.mark.parametrize("R,n_hidden", [(256, 1), (1024, 1), (512, 2)])
+def test_one_iteration_stage_by_stage(core, oracle, gpu_dataset, small_seq, R, n_hidden):
     seq, obj = small_seq, small_seq.objects[0]
-    try:
-        g, o = make_pair(core, oracle, gpu_dataset, seq, obj, R, n_hidden=n_hidden)
-    except core.MonError as e:
-        if "tcgen05" in str(e):
-            pytest.skip("needs the tcgen05 kernel, not in this build")
-        raise
-    _impl_or_skip(g, impl)
+    g, o = make_pair(core, oracle, gpu_dataset, seq, obj, R, n_hidden=n_hidden)
     # start from a lightly trained state so that densities / colours are not all near zero
     rng = np.random.default_rng(R)
     frames = oracle.Frames(seq.rgb, seq.instance, seq.depth, seq.poses)
@@ -122,7 +101,8 @@ def test_one_iteration_stage_by_stage(core, oracle, gpu_dataset, small_seq, R, i
     assert np.array_equal(g.last("target"), o2.last("target"))
     assert np.array_equal(g.last("target_depth"), o2.last("target_depth"))
     assert np.array_equal(g.last("ray_instance"), o2.last("ray_instance"))
-    # A3+A4: sample positions are regenerated in-kernel; the encoding must still be bit-exact
+    # A3: unit-cube sample positions, A4: hash-grid encoding (computed from shared-memory resident tables): bit-exact
+    assert np.array_equal(g.last("points"), o2.last("points"))
     enc_g, enc_o = g.last("enc"), o2.last("enc")
     assert np.array_equal(enc_g, enc_o)
     # A5: network output (fp16). fp32 accumulation order differs (tensor core vs sequential) and hidden
@@ -162,14 +142,12 @@ def test_one_iteration_stage_by_stage(core, oracle, gpu_dataset, small_seq, R, i
     assert ok.mean() >= 0.995, ok.mean()
 
 
-@pytest.mark.parametrize("impl", IMPLS)
-def test_optimizer_state_after_steps(core, oracle, gpu_dataset, small_seq, impl):
+def test_optimizer_state_after_steps(core, oracle, gpu_dataset, small_seq):
     """Three injected iterations: Adam's sparse semantics (untouched grid entries keep step 0 and their
     exact initial value), per-parameter step counters, EMA, fp32 master weights."""
     seq, obj = small_seq, small_seq.objects[1]
     R = 512
     g, o = make_pair(core, oracle, gpu_dataset, seq, obj, R)
-    _impl_or_skip(g, impl)
     frames = oracle.Frames(seq.rgb, seq.instance, seq.depth, seq.poses)
     rng = np.random.default_rng(21)
     init = g.state("master")
@@ -201,13 +179,11 @@ def test_optimizer_state_after_steps(core, oracle, gpu_dataset, small_seq, impl)
     assert (de[both] <= 2e-3).mean() >= 0.99
 
 
-@pytest.mark.parametrize("impl", IMPLS)
-def test_training_curve_tracks_oracle(core, oracle, gpu_dataset, small_seq, impl):
+def test_training_curve_tracks_oracle(core, oracle, gpu_dataset, small_seq):
     """40 iterations with shared randoms: the logged loss follows the oracle's within 5% and decreases."""
     seq, obj = small_seq, small_seq.objects[0]
     R = 256
     g, o = make_pair(core, oracle, gpu_dataset, seq, obj, R)
-    _impl_or_skip(g, impl)
     frames = oracle.Frames(seq.rgb, seq.instance, seq.depth, seq.poses)
     rng = np.random.default_rng(31)
     lg, lo = [], []
@@ -227,16 +203,11 @@ def test_graph_training_and_render(core, oracle, gpu_dataset, small_seq, n_hidde
     trained weights (same injected jitter): PSNR between the two renders >= 35 dB, identical hit masks."""
     seq, obj = small_seq, small_seq.objects[0]
     R = 1024
-    try:
-        g, o = make_pair(core, oracle, gpu_dataset, seq, obj, R, n_hidden=n_hidden)
-    except core.MonError as e:
-        if "tcgen05" in str(e):
-            pytest.skip("n_hidden_layers=2 needs the tcgen05 kernel, not in this build")
-        raise
+    g, o = make_pair(core, oracle, gpu_dataset, seq, obj, R, n_hidden=n_hidden)
     l0 = g.train(1)
     l1 = g.train(150)
     assert g.step == 151 and np.isfinite(l1) and l1 < 0.7 * l0
-    assert g.launch_count >= 151 * 5 and g.last_train_ms > 0
+    assert g.launch_count >= 151 * 6 and g.last_train_ms > 0
     o.set_params(g.state("master"))
     # the oracle renders with "training" weights we just copied (use_ema=False on both sides)
     fid, x, y, h, w = obj.boxes[0]

@@ -151,7 +151,20 @@ k_generate_batch(MonBatch b, MonScene sc) {
     if (rank == 0 && tid == 0) {
         b.ctrl->n_in = n_in;
         b.ctrl->skip = (n_in == 0) ? 1u : 0u;  // reference: modulo by zero (undefined); here: skip the iteration
-        if (n_in > 0) b.ctrl->step += 1;
+        if (n_in > 0) {
+            const uint32_t step = b.ctrl->step + 1;
+            b.ctrl->step = step;
+            // ExponentialDecay evaluates its condition with the nested step BEFORE Adam increments it
+            float factor = 1.0f;
+            if (step - 1 >= b.decay_start) {
+                const uint32_t n_decays = (step - 1 - b.decay_start) / b.decay_interval + 1;
+                for (uint32_t s = 0; s < n_decays; ++s) factor = __fmul_rn(factor, b.decay_base);
+            }
+            b.ctrl->lr_base = __fmul_rn(b.opt_lr, factor);
+            // host code in the reference: float debias from a double pow (ema.h:107-108)
+            b.ctrl->ema_old = 1.0f - (float)pow((double)b.ema_decay, (double)(step - 1));
+            b.ctrl->ema_new = 1.0f / (1.0f - (float)pow((double)b.ema_decay, (double)step));
+        }
         b.ctrl->iter = iter + 1;
     }
 }

@@ -222,6 +222,12 @@ void mon_launch_planarize(const MonGrid& g, const __half* inter, __half* planar,
 #define SCT_THREADS 512
 #define SCT_TILE 128
 
+// explicit global-space reduction: a generic-pointer atomicAdd(__half2*) makes the compiler query the address space
+// and branch around every one of the 32 atomics of a thread
+__device__ __forceinline__ void red_add_f16x2(__half2* addr, __half2 v) {
+    asm volatile("red.global.add.noftz.f16x2 [%0], %1;" ::"l"(addr), "r"(*reinterpret_cast<const uint32_t*>(&v)) : "memory");
+}
+
 // Zero d_enc pairs (samples after the early stop) are skipped: adding +0 is an identity, so the result is unchanged.
 __global__ void __launch_bounds__(SCT_THREADS)
 k_encode_backward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, const MonCtrl* __restrict__ ctrl,
@@ -246,7 +252,7 @@ k_encode_backward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, c
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const __half2 v = __halves2half2(__float2half_rn(__fmul_rn(g0, c.w[k])), __float2half_rn(__fmul_rn(g1, c.w[k])));
-            atomicAdd(tab + c.idx[k], v);
+            red_add_f16x2(tab + c.idx[k], v);
         }
     }
 }

@@ -262,6 +262,9 @@ template <int NH>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
     extern __shared__ unsigned char smem_raw[];
+    // hand the iteration's control block to the kernels behind this one (scatter, optimizer): the batch kernel of
+    // the next iteration is allowed to overwrite the live block while they run
+    if (blockIdx.x == 0 && threadIdx.x == 0) *b.late = *b.ctrl;
     if (b.ctrl->skip) return;
     TcCtx c;
     tc_setup(c, smem_raw);

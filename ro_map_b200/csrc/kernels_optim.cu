@@ -4,14 +4,18 @@
 // three launches plus a memset per iteration:
 //   cudaMemsetAsync(grid gradients)          TCNN encodings/grid.h:1132
 //   adam_step<__half>                         TCNN optimizers/adam.h:48-118
-//   ExponentialDecay learning-rate schedule   TCNN optimizers/exponential_decay.h:60-71
+//   ExponentialDecay learning-rate schedule   TCNN optimizers/exponential_decay.h:60-71  (scalar from the batch kernel)
 //   ema_step_half_precision<__half>           TCNN optimizers/ema.h:62-76,102-136
+//   SumLoss + host-side mean                  MON/Core/src/nerf_model.cu:1231-1253,1650-1658
 // and, for the first n_mlp parameters, the deterministic reduction of the per-CTA MLP weight-
 // gradient partials written by the fused MLP kernel.  Semantics kept exactly: per-parameter
 // step counters, grid parameters whose gradient is exactly zero are skipped by Adam
 // (adam.h:75-79) but still EMA-filtered, L2 regularisation only on MLP weights, fp32 master +
 // fp16 working copy + fp16 EMA (the inference weights).  The gradient is consumed and zeroed in
-// the same pass, so the next iteration's scatter starts from zero without a memset.
+// the same pass, so the next iteration's scatter starts from zero without a memset; touched grid
+// weights are also written to the planar copy the hash-encode kernel stages into shared memory.
+// A thread owns 4 consecutive parameters (= 2 table entries): 8-byte gradient / EMA words, 16-byte
+// master / moment / step words.
 #include "mon_device.cuh"
 #include "mon_kernels.h"
 
@@ -59,23 +63,27 @@ __global__ void k_cast_params(uint32_t n, const float* __restrict__ pf, __half* 
 }
 
 #define OPT_THREADS 256
+#define OPT_PER_THREAD 4
 
-__device__ __forceinline__ void adam_update(const MonOpt& o, float lr_base, float gradient, uint32_t i, bool is_mlp,
-                                            float* __restrict__ pf, __half* __restrict__ ph, float* __restrict__ m,
-                                            float* __restrict__ v, uint32_t* __restrict__ ps) {
-    const float w = pf[i];
+// one Adam update (adam.h:65-118); returns the new weight
+__device__ __forceinline__ float adam_one(const MonOpt& o, float lr_base, float gradient, bool is_mlp, float w, float& m, float& v, uint32_t& cs) {
     if (is_mlp) gradient = __fmaf_rn(o.l2_reg, w, gradient);
     const float gsq = __fmul_rn(gradient, gradient);
-    const float fm = __fmaf_rn(o.beta1, m[i], __fmul_rn(1.0f - o.beta1, gradient));
-    const float sm = __fmaf_rn(o.beta2, v[i], __fmul_rn(1.0f - o.beta2, gsq));
-    m[i] = fm; v[i] = sm;
-    const uint32_t cs = ps[i] + 1;
-    ps[i] = cs;
-    const float lr = __fmul_rn(lr_base, __fdiv_rn(__fsqrt_rn(1.0f - powf(o.beta2, (float)cs)), 1.0f - powf(o.beta1, (float)cs)));
-    const float eff = fminf(fmaxf(__fdiv_rn(lr, __fadd_rn(__fsqrt_rn(sm), o.eps)), 0.0f), FLT_MAX);
-    const float nw = __fmaf_rn(-eff, fm, w);
-    pf[i] = nw;
-    ph[i] = __float2half_rn(nw);
+    m = __fmaf_rn(o.beta1, m, __fmul_rn(1.0f - o.beta1, gradient));
+    v = __fmaf_rn(o.beta2, v, __fmul_rn(1.0f - o.beta2, gsq));
+    cs += 1;
+    // beta^cs as exp2f(cs * log2 beta): a handful of instructions instead of the generic powf
+    const float b1s = exp2f((float)cs * o.log2_beta1), b2s = exp2f((float)cs * o.log2_beta2);
+    const float lr = __fmul_rn(lr_base, __fdiv_rn(__fsqrt_rn(1.0f - b2s), 1.0f - b1s));
+    const float eff = fminf(fmaxf(__fdiv_rn(lr, __fadd_rn(__fsqrt_rn(v), o.eps)), 0.0f), FLT_MAX);
+    return __fmaf_rn(-eff, m, w);
+}
+
+__device__ __forceinline__ uint32_t level_of_entry(const MonGrid& g, uint32_t e) {
+    if (g.log2_cap && g.first_full < g.n_levels && e >= g.offset[g.first_full]) return g.first_full + ((e - g.offset[g.first_full]) >> g.log2_cap);
+    uint32_t l = 0;
+    while (l + 1 < g.n_levels && e >= g.offset[l + 1]) ++l;
+    return l;
 }
 
 __global__ void __launch_bounds__(OPT_THREADS)
@@ -84,10 +92,8 @@ k_optimizer_sweep(MonOpt o, MonCtrl* __restrict__ ctrl, float* __restrict__ pf, 
                   float* __restrict__ v, uint32_t* __restrict__ ps, __half* __restrict__ ema,
                   const float* __restrict__ loss, uint32_t R, MonGrid grid, __half* __restrict__ planar) {
     if (ctrl->skip) return;
-    __shared__ float s_lr, s_old, s_new;
     if (blockIdx.x == gridDim.x - 1) {
-        // SumLoss (nerf_model.cu:1231-1253) + the host-side /R (:1650-1658) folded into the sweep's last CTA
-        // (a mostly idle tail block): fixed summation order -> reproducible logged loss
+        // logged loss in the sweep's last (mostly idle) CTA: fixed summation order -> reproducible
         __shared__ float s_loss[OPT_THREADS];
         float a = 0.0f;
         for (uint32_t i = threadIdx.x; i < R; i += OPT_THREADS) a += loss[i];
@@ -99,71 +105,87 @@ k_optimizer_sweep(MonOpt o, MonCtrl* __restrict__ ctrl, float* __restrict__ pf, 
         }
         if (threadIdx.x == 0) ctrl->loss_mean = s_loss[0] / (float)R;
     }
-    const uint32_t step = ctrl->step;  // 1-based, already advanced by the batch kernel
-    if (threadIdx.x == 0) {
-        // ExponentialDecay evaluates its condition with the nested step BEFORE Adam increments it
-        float factor = 1.0f;
-        if (step - 1 >= o.decay_start) {
-            const uint32_t n_decays = (step - 1 - o.decay_start) / o.decay_interval + 1;
-            for (uint32_t s = 0; s < n_decays; ++s) factor = __fmul_rn(factor, o.decay_base);
-        }
-        s_lr = __fmul_rn(o.lr, factor);
-        // host code in the reference: float debias from a double pow (ema.h:107-108)
-        s_old = 1.0f - (float)pow((double)o.ema_decay, (double)(step - 1));
-        s_new = 1.0f / (1.0f - (float)pow((double)o.ema_decay, (double)step));
-    }
-    __syncthreads();
-    const float lr_base = s_lr, old_db = s_old, new_db = s_new;
-    // each thread owns 2 consecutive parameters (one half2 gradient word)
-    const uint32_t i2 = (blockIdx.x * OPT_THREADS + threadIdx.x) * 2;
-    if (i2 >= o.n_params) return;
-    __half2* gh2 = reinterpret_cast<__half2*>(gh + i2);
-    float g[2];
-    if (i2 < o.n_mlp) {
+    const float lr_base = ctrl->lr_base, old_db = ctrl->ema_old, new_db = ctrl->ema_new;
+    const uint32_t i4 = (blockIdx.x * OPT_THREADS + threadIdx.x) * OPT_PER_THREAD;   // n_params and n_mlp are multiples of 4
+    if (i4 >= o.n_params) return;
+    const bool is_mlp = i4 < o.n_mlp;
+
+    // ---- gradient of the 4 parameters (loss-scaled, fp16-representable)
+    float g[4];
+    uint2* gw = reinterpret_cast<uint2*>(gh + i4);
+    if (is_mlp) {
         // sum the per-CTA partials in a fixed order -> bitwise reproducible MLP gradient
-        float s0 = 0.0f, s1 = 0.0f;
+        float4 s = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         for (uint32_t c = 0; c < o.n_partials; ++c) {
-            const float2 p = *reinterpret_cast<const float2*>(mlp_partials + (size_t)c * o.n_mlp + i2);
-            s0 = __fadd_rn(s0, p.x); s1 = __fadd_rn(s1, p.y);
+            const float4 p = *reinterpret_cast<const float4*>(mlp_partials + (size_t)c * o.n_mlp + i4);
+            s.x = __fadd_rn(s.x, p.x); s.y = __fadd_rn(s.y, p.y); s.z = __fadd_rn(s.z, p.z); s.w = __fadd_rn(s.w, p.w);
         }
         // the reference stores weight gradients in fp16 (loss-scaled); keep that rounding point
-        const __half2 gr = __halves2half2(__float2half_rn(s0), __float2half_rn(s1));
-        *gh2 = gr;  // kept (not zeroed) so tests can read the MLP gradient; overwritten every iteration
-        g[0] = __low2float(gr); g[1] = __high2float(gr);
+        const __half2 a = __floats2half2_rn(s.x, s.y), b = __floats2half2_rn(s.z, s.w);
+        *gw = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));   // kept for inspection
+        g[0] = __low2float(a); g[1] = __high2float(a); g[2] = __low2float(b); g[3] = __high2float(b);
     } else {
-        const __half2 gr = *gh2;
-        g[0] = __low2float(gr); g[1] = __high2float(gr);
-        if (g[0] != 0.0f || g[1] != 0.0f) *gh2 = __halves2half2(__float2half_rn(0.0f), __float2half_rn(0.0f));
+        const uint2 raw = *gw;
+        const __half2 a = *reinterpret_cast<const __half2*>(&raw.x), b = *reinterpret_cast<const __half2*>(&raw.y);
+        g[0] = __low2float(a); g[1] = __high2float(a); g[2] = __low2float(b); g[3] = __high2float(b);
+        if ((raw.x | raw.y) & 0x7fff7fffu) *gw = make_uint2(0u, 0u);   // consumed: the next scatter starts from zero
     }
-    // planar copy of the fp16 grid weights, read by the hash-encode kernel: level l holds [feature 0 | feature 1];
-    // entry e of level l sits at 2*offset[l] + f*size[l] + (e - offset[l])
-    __half* planar_dst[2] = {nullptr, nullptr};
-    if (i2 >= o.n_mlp) {
-        const uint32_t e = (i2 - o.n_mlp) >> 1;
-        uint32_t l = 0;
-        while (l + 1 < grid.n_levels && e >= grid.offset[l + 1]) ++l;
-        planar_dst[0] = planar + (size_t)grid.offset[l] * 2 + (e - grid.offset[l]);
-        planar_dst[1] = planar_dst[0] + grid.size[l];
-    }
+    bool touched[4];
+    bool any = is_mlp;
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const uint32_t i = i2 + k;
-        if (i >= o.n_params) break;
-        const bool is_mlp = i < o.n_mlp;
-        const float gradient = __fdiv_rn(g[k], o.loss_scale);
-        if (is_mlp || gradient != 0.0f) {
-            adam_update(o, lr_base, gradient, i, is_mlp, pf, ph, m, v, ps);
-            if (!is_mlp) *planar_dst[k] = ph[i];
-        }
-        // EMA over all params with the global step (ema.h:62-76)
-        const float e = __half2float(ema[i]);
-        const float w = __half2float(ph[i]);
-        const float f = __fmul_rn(__fmaf_rn(w, 1.0f - o.ema_decay, __fmul_rn(__fmul_rn(e, o.ema_decay), old_db)), new_db);
-        ema[i] = __float2half_rn(f);
+    for (int k = 0; k < 4; ++k) {
+        g[k] = o.loss_scale_pow2 ? __fmul_rn(g[k], o.inv_loss_scale) : __fdiv_rn(g[k], o.loss_scale);
+        touched[k] = is_mlp || g[k] != 0.0f;       // grid: zero gradient => Adam skips the parameter (adam.h:75-79)
+        any |= touched[k];
     }
+
+    // ---- fp16 weights of the 4 parameters (needed by the EMA in any case)
+    uint2 wraw = *reinterpret_cast<const uint2*>(ph + i4);
+    __half wh[4] = {__ushort_as_half((unsigned short)(wraw.x & 0xffffu)), __ushort_as_half((unsigned short)(wraw.x >> 16)),
+                    __ushort_as_half((unsigned short)(wraw.y & 0xffffu)), __ushort_as_half((unsigned short)(wraw.y >> 16))};
+    if (any) {
+        float4 w4 = *reinterpret_cast<const float4*>(pf + i4);
+        float4 m4 = *reinterpret_cast<const float4*>(m + i4);
+        float4 v4 = *reinterpret_cast<const float4*>(v + i4);
+        uint4 s4 = *reinterpret_cast<const uint4*>(ps + i4);
+        float* wp = &w4.x; float* mp = &m4.x; float* vp = &v4.x; uint32_t* sp = &s4.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (touched[k]) {
+                wp[k] = adam_one(o, lr_base, g[k], is_mlp, wp[k], mp[k], vp[k], sp[k]);
+                wh[k] = __float2half_rn(wp[k]);
+            }
+        }
+        *reinterpret_cast<float4*>(pf + i4) = w4;
+        *reinterpret_cast<float4*>(m + i4) = m4;
+        *reinterpret_cast<float4*>(v + i4) = v4;
+        *reinterpret_cast<uint4*>(ps + i4) = s4;
+        const __half2 a = __halves2half2(wh[0], wh[1]), b = __halves2half2(wh[2], wh[3]);
+        *reinterpret_cast<uint2*>(ph + i4) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+        if (!is_mlp) {
+            // planar copy read by the hash-encode kernel: level l holds [feature 0 | feature 1]; entries e, e+1 are
+            // adjacent in both feature arrays (level sizes are multiples of 8, so a pair never straddles a level)
+            const uint32_t e = (i4 - o.n_mlp) >> 1;
+            const uint32_t l = level_of_entry(grid, e);
+            __half* f0 = planar + (size_t)grid.offset[l] * 2 + (e - grid.offset[l]);
+            *reinterpret_cast<__half2*>(f0) = __halves2half2(wh[0], wh[2]);
+            *reinterpret_cast<__half2*>(f0 + grid.size[l]) = __halves2half2(wh[1], wh[3]);
+        }
+    }
+
+    // ---- EMA over all params with the global step (ema.h:62-76)
+    const uint2 eraw = *reinterpret_cast<const uint2*>(ema + i4);
+    const __half2 e01 = *reinterpret_cast<const __half2*>(&eraw.x), e23 = *reinterpret_cast<const __half2*>(&eraw.y);
+    const float ev[4] = {__low2float(e01), __high2float(e01), __low2float(e23), __high2float(e23)};
+    float nf[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        nf[k] = __fmul_rn(__fmaf_rn(__half2float(wh[k]), 1.0f - o.ema_decay, __fmul_rn(__fmul_rn(ev[k], o.ema_decay), old_db)), new_db);
+    const __half2 n01 = __floats2half2_rn(nf[0], nf[1]), n23 = __floats2half2_rn(nf[2], nf[3]);
+    *reinterpret_cast<uint2*>(ema + i4) = make_uint2(*reinterpret_cast<const uint32_t*>(&n01), *reinterpret_cast<const uint32_t*>(&n23));
 }
 
-// variant used only by tests to snapshot the loss-scaled gradient before it is consumed
+// used only by tests: snapshot of the loss-scaled gradient before the sweep consumes it
 __global__ void k_snapshot_grad(uint32_t n, uint32_t n_mlp, uint32_t n_partials, const __half* __restrict__ gh,
                                 const float* __restrict__ mlp_partials, float* __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -175,20 +197,6 @@ __global__ void k_snapshot_grad(uint32_t n, uint32_t n_mlp, uint32_t n_partials,
     } else {
         out[i] = __half2float(gh[i]);
     }
-}
-
-// SumLoss (nerf_model.cu:1231-1253) + the host-side /R (:1650-1658), one CTA, fixed order
-__global__ void k_sum_loss(uint32_t R, const float* __restrict__ loss, MonCtrl* ctrl) {
-    __shared__ float s[1024];
-    float a = 0.0f;
-    for (uint32_t i = threadIdx.x; i < R; i += blockDim.x) a += loss[i];
-    s[threadIdx.x] = a;
-    __syncthreads();
-    for (int step = blockDim.x / 2; step > 0; step >>= 1) {
-        if ((int)threadIdx.x < step) s[threadIdx.x] += s[threadIdx.x + step];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) ctrl->loss_mean = s[0] / (float)R;
 }
 
 void mon_launch_init_grid(uint64_t state, uint64_t inc, uint32_t n, float* out, cudaStream_t st) {
@@ -204,12 +212,9 @@ void mon_launch_cast_params(uint32_t n, const float* pf, __half* ph, cudaStream_
 void mon_launch_optimizer(const MonOpt& o, MonCtrl* ctrl, float* pf, __half* ph, __half* gh, const float* partials,
                           float* m, float* v, uint32_t* ps, __half* ema, const float* loss, uint32_t R, const MonGrid& grid,
                           __half* planar, cudaStream_t st) {
-    const uint32_t pairs = (o.n_params + 1) / 2;
-    k_optimizer_sweep<<<(pairs + OPT_THREADS - 1) / OPT_THREADS, OPT_THREADS, 0, st>>>(o, ctrl, pf, ph, gh, partials, m, v, ps, ema, loss, R, grid, planar);
+    const uint32_t quads = (o.n_params + OPT_PER_THREAD - 1) / OPT_PER_THREAD;
+    k_optimizer_sweep<<<(quads + OPT_THREADS - 1) / OPT_THREADS, OPT_THREADS, 0, st>>>(o, ctrl, pf, ph, gh, partials, m, v, ps, ema, loss, R, grid, planar);
 }
 void mon_launch_snapshot_grad(uint32_t n, uint32_t n_mlp, uint32_t n_partials, const __half* gh, const float* partials, float* out, cudaStream_t st) {
     k_snapshot_grad<<<(n + 255) / 256, 256, 0, st>>>(n, n_mlp, n_partials, gh, partials, out);
-}
-void mon_launch_sum_loss(uint32_t R, const float* loss, MonCtrl* ctrl, cudaStream_t st) {
-    k_sum_loss<<<1, 1024, 0, st>>>(R, loss, ctrl);
 }

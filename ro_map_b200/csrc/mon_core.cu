@@ -117,6 +117,11 @@ bool make_grid(const mon_config& c, MonGrid& g, std::string& why) {
         offset += n;
     }
     g.offset[c.n_levels] = offset;
+    // entry -> level shortcut for the optimizer: all levels from first_full on have the capped (power-of-two) size
+    const uint32_t cap = 1u << c.log2_hashmap_size;
+    g.first_full = c.n_levels;
+    for (uint32_t i = c.n_levels; i-- > 0;) { if (g.size[i] == cap) g.first_full = i; else break; }
+    g.log2_cap = c.log2_hashmap_size;
     return true;
 }
 
@@ -165,7 +170,8 @@ struct mon_object {
     __half *ph = nullptr, *gh = nullptr, *ema = nullptr;
     uint32_t* ps = nullptr;
     // control
-    MonCtrl* ctrl = nullptr;
+    MonCtrl* ctrl = nullptr;       // live block (batch kernel)
+    MonCtrl* ctrl_late = nullptr;  // per-iteration copy for scatter / optimizer; carries the logged loss
     MonCtrl* h_ctrl = nullptr;  // pinned
     mon_bbox2d* d_boxes = nullptr;
     uint32_t box_cap = 0;
@@ -190,7 +196,8 @@ struct mon_object {
     uint32_t r_cap_rays = 0, r_tile = 0; size_t r_jit_cap = 0;
     uint32_t render_count = 0;
     // execution
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, aux = nullptr;   // aux: next iteration's batch + sample points, forked inside the graphs
+    cudaEvent_t ev_fork_m = nullptr, ev_fork_s = nullptr, ev_join = nullptr;
     cudaGraphExec_t graph1 = nullptr, graphN = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timing_pending = false;
@@ -456,7 +463,10 @@ static MonBatch make_batch(mon_object* o, bool injected, bool debug) {
     b.boxes = o->d_boxes;
     b.frames = o->ds->d_frames;
     b.ctrl = o->ctrl;
+    b.late = o->ctrl_late;
     b.seed = o->seed;
+    b.opt_lr = o->cfg.learning_rate; b.decay_base = o->cfg.decay_base; b.ema_decay = o->cfg.ema_decay;
+    b.decay_start = o->cfg.decay_start; b.decay_interval = o->cfg.decay_interval ? o->cfg.decay_interval : 1;
     if (injected) { b.inj_xy = o->inj_xy; b.inj_col = o->inj_col; b.inj_dt = o->inj_dt; }
     b.rays = o->rays; b.ray_inst = o->ray_inst; b.target = o->target; b.target_depth = o->target_depth; b.bg = o->bg;
     b.rgb_rays = o->rgb_rays; b.depth_rays = o->depth_rays; b.mask_rays = o->mask_rays; b.loss = o->loss;
@@ -466,29 +476,59 @@ static MonBatch make_batch(mon_object* o, bool injected, bool debug) {
     return b;
 }
 
-// the kernels of ONE training iteration, in stream order; returns the number launched.
-// ev (optional, MON_N_STAGES+1 events): recorded before each stage and after the last one.
-static int enqueue_iteration(mon_object* o, const MonBatch& b, bool snapshot_grad, int* n_launched, cudaEvent_t* ev = nullptr) {
-    cudaStream_t st = o->stream;
-    int n = 0;
-    if (ev) CK(cudaEventRecord(ev[0], st));
-    mon_launch_generate_batch(b, o->scene, st); ++n;
-    if (ev) CK(cudaEventRecord(ev[1], st));
-    mon_launch_sample_points(o->N, MON_S, o->rays, nullptr, b.inj_dt, o->seed, o->ctrl, 2, 0, o->scene.bmin, o->scene.bmax, o->pts, st); ++n;
-    if (ev) CK(cudaEventRecord(ev[2], st));
+// One training iteration = batch (B) -> sample points (P) -> hash encode (E) -> fused MLP (M) -> gradient scatter (S)
+// -> optimizer sweep (O).  B and P do not depend on the training state, so inside a captured graph the B/P of
+// iteration i+1 run on a forked branch concurrently with S/O of iteration i:
+//     main:  E(i)  M(i) ---------> S(i) ---------> O(i) --join--> E(i+1) ...
+//     aux :          \--> B(i+1)       \--> P(i+1) ----/
+// B(i+1) may start once M(i) is done (last reader of rays/targets; M also copied the control block for S/O),
+// P(i+1) once S(i) is done (last reader of the sample points).
+static int launch_batch(mon_object* o, const MonBatch& b, cudaStream_t st) {
+    mon_launch_generate_batch(b, o->scene, st);
+    return MON_OK;
+}
+static int launch_points(mon_object* o, const MonBatch& b, cudaStream_t st) {
+    mon_launch_sample_points(o->N, MON_S, o->rays, nullptr, b.inj_dt, o->seed, o->ctrl, 2, 0, o->scene.bmin, o->scene.bmax, o->pts, st);
+    return MON_OK;
+}
+static int launch_encode(mon_object* o, cudaStream_t st) {
     cudaError_t e = mon_launch_encode_forward(o->grid, o->N, o->pts, o->ph_planar, o->enc, o->ctrl, (uint32_t)o->sm_count, st);
     if (e != cudaSuccess) return fail(MON_ERR_CUDA, "hash encode launch: %s", cudaGetErrorString(e));
+    return MON_OK;
+}
+static int launch_mlp(mon_object* o, const MonBatch& b, cudaStream_t st) {
+    cudaError_t e = mon_launch_mlp_train_tc(b, o->lc, o->cfg.n_hidden_layers, o->n_mlp, o->n_ctas, st);
+    if (e != cudaSuccess) return fail(MON_ERR_CUDA, "fused MLP launch: %s", cudaGetErrorString(e));
+    return MON_OK;
+}
+static void launch_scatter(mon_object* o, cudaStream_t st) {
+    mon_launch_encode_backward(o->grid, o->N, o->pts, o->ctrl_late, o->d_enc, o->gh + o->n_mlp, st);
+}
+static void launch_optimizer(mon_object* o, cudaStream_t st) {
+    mon_launch_optimizer(o->opt, o->ctrl_late, o->pf, o->ph, o->gh, o->partials, o->m, o->v, o->ps, o->ema, o->loss, o->R, o->grid,
+                         o->ph_planar, st);
+}
+
+// serial version (injected / profiled iterations).  ev (optional, MON_N_STAGES+1 events): recorded before each
+// stage and after the last one.  Returns the number of kernels launched through n_launched.
+static int enqueue_iteration(mon_object* o, const MonBatch& b, bool snapshot_grad, int* n_launched, cudaEvent_t* ev = nullptr) {
+    cudaStream_t st = o->stream;
+    int n = 0, rc;
+    if (ev) CK(cudaEventRecord(ev[0], st));
+    launch_batch(o, b, st); ++n;
+    if (ev) CK(cudaEventRecord(ev[1], st));
+    launch_points(o, b, st); ++n;
+    if (ev) CK(cudaEventRecord(ev[2], st));
+    if ((rc = launch_encode(o, st)) != MON_OK) return rc;
     ++n;
     if (ev) CK(cudaEventRecord(ev[3], st));
-    e = mon_launch_mlp_train_tc(b, o->lc, o->cfg.n_hidden_layers, o->n_mlp, o->n_ctas, st);
-    if (e != cudaSuccess) return fail(MON_ERR_CUDA, "fused MLP launch: %s", cudaGetErrorString(e));
+    if ((rc = launch_mlp(o, b, st)) != MON_OK) return rc;
     ++n;
     if (ev) CK(cudaEventRecord(ev[4], st));
-    mon_launch_encode_backward(o->grid, o->N, o->pts, o->ctrl, o->d_enc, o->gh + o->n_mlp, st); ++n;
+    launch_scatter(o, st); ++n;
     if (snapshot_grad) { mon_launch_snapshot_grad(o->P, o->n_mlp, o->opt.n_partials, o->gh, o->partials, o->grad_snap, st); ++n; }
     if (ev) CK(cudaEventRecord(ev[5], st));
-    mon_launch_optimizer(o->opt, o->ctrl, o->pf, o->ph, o->gh, o->partials, o->m, o->v, o->ps, o->ema, o->loss, o->R, o->grid,
-                         o->ph_planar, st); ++n;
+    launch_optimizer(o, st); ++n;
     if (ev) CK(cudaEventRecord(ev[6], st));
     CK(cudaGetLastError());
     if (n_launched) *n_launched = n;
@@ -498,12 +538,35 @@ static int enqueue_iteration(mon_object* o, const MonBatch& b, bool snapshot_gra
 static int capture_graph(mon_object* o, int iters, cudaGraphExec_t* out) {
     const MonBatch b = make_batch(o, false, false);
     cudaGraph_t g = nullptr;
-    CK(cudaStreamBeginCapture(o->stream, cudaStreamCaptureModeThreadLocal));
+    cudaStream_t st = o->stream, aux = o->aux;
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     int rc = MON_OK;
-    for (int i = 0; i < iters && rc == MON_OK; ++i) rc = enqueue_iteration(o, b, false, nullptr);
-    cudaError_t e = cudaStreamEndCapture(o->stream, &g);
+    cudaError_t e = cudaSuccess;
+    launch_batch(o, b, st);
+    launch_points(o, b, st);
+    for (int i = 0; i < iters && rc == MON_OK && e == cudaSuccess; ++i) {
+        const bool fork = i + 1 < iters;
+        if ((rc = launch_encode(o, st)) != MON_OK) break;
+        if ((rc = launch_mlp(o, b, st)) != MON_OK) break;
+        if (fork) {
+            if ((e = cudaEventRecord(o->ev_fork_m, st)) != cudaSuccess) break;
+            if ((e = cudaStreamWaitEvent(aux, o->ev_fork_m, 0)) != cudaSuccess) break;
+            launch_batch(o, b, aux);
+        }
+        launch_scatter(o, st);
+        if (fork) {
+            if ((e = cudaEventRecord(o->ev_fork_s, st)) != cudaSuccess) break;
+            if ((e = cudaStreamWaitEvent(aux, o->ev_fork_s, 0)) != cudaSuccess) break;
+            launch_points(o, b, aux);
+            if ((e = cudaEventRecord(o->ev_join, aux)) != cudaSuccess) break;
+        }
+        launch_optimizer(o, st);
+        if (fork && (e = cudaStreamWaitEvent(st, o->ev_join, 0)) != cudaSuccess) break;
+    }
+    cudaError_t e2 = cudaStreamEndCapture(st, &g);
     if (rc != MON_OK) { if (g) cudaGraphDestroy(g); return rc; }
-    if (e != cudaSuccess) return fail(MON_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) { if (g) cudaGraphDestroy(g); return fail(MON_ERR_CUDA, "graph capture: %s", cudaGetErrorString(e)); }
+    if (e2 != cudaSuccess) return fail(MON_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e2));
     e = cudaGraphInstantiate(out, g, 0);
     cudaGraphDestroy(g);
     if (e != cudaSuccess) return fail(MON_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
@@ -545,6 +608,13 @@ int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uin
     o->opt.l2_reg = cfg->l2_reg; o->opt.ema_decay = cfg->ema_decay; o->opt.loss_scale = cfg->loss_scale;
     o->opt.decay_start = cfg->decay_start; o->opt.decay_interval = cfg->decay_interval; o->opt.decay_base = cfg->decay_base;
     o->opt.n_mlp = o->n_mlp; o->opt.n_params = o->P; o->opt.n_partials = o->n_ctas;
+    o->opt.log2_beta1 = std::log2(cfg->beta1); o->opt.log2_beta2 = std::log2(cfg->beta2);
+    {
+        int ex = 0;
+        const float mant = std::frexp(cfg->loss_scale, &ex);
+        o->opt.loss_scale_pow2 = (mant == 0.5f) ? 1u : 0u;
+        o->opt.inv_loss_scale = 1.0f / cfg->loss_scale;
+    }
 
 #define OALLOC(ptr, bytes)                                                                                  \
     do {                                                                                                    \
@@ -555,7 +625,7 @@ int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uin
     const size_t P = o->P, R = o->R, N = o->N;
     OALLOC(o->pf, P * 4); OALLOC(o->m, P * 4); OALLOC(o->v, P * 4); OALLOC(o->ps, P * 4);
     OALLOC(o->ph, P * 2 + 16); OALLOC(o->gh, P * 2 + 16); OALLOC(o->ema, P * 2 + 16);
-    OALLOC(o->ctrl, sizeof(MonCtrl));
+    OALLOC(o->ctrl, sizeof(MonCtrl)); OALLOC(o->ctrl_late, sizeof(MonCtrl));
     OALLOC(o->rays, R * sizeof(MonRay)); OALLOC(o->ray_inst, R);
     OALLOC(o->target, R * 12); OALLOC(o->target_depth, R * 4); OALLOC(o->bg, R * 12);
     OALLOC(o->rgb_rays, R * 12); OALLOC(o->depth_rays, R * 4); OALLOC(o->mask_rays, R * 4); OALLOC(o->loss, R * 4);
@@ -566,6 +636,10 @@ int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uin
     cudaError_t e;
     if ((e = cudaMallocHost(&o->h_ctrl, sizeof(MonCtrl))) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&o->aux, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&o->ev_fork_m, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&o->ev_fork_s, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&o->ev_join, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreate(&o->ev0)) != cudaSuccess || (e = cudaEventCreate(&o->ev1)) != cudaSuccess) {
         mon_object_destroy(o);
         return fail(MON_ERR_CUDA, "object setup: %s", cudaGetErrorString(e));
@@ -611,7 +685,7 @@ int mon_object_destroy(mon_object* o) {
     cudaSetDevice(o->ds->gpu);
     if (o->stream) cudaStreamSynchronize(o->stream);
     drop_graphs(o);
-    void* ptrs[] = {o->pf, o->m, o->v, o->ps, o->ph, o->gh, o->ema, o->ctrl, o->d_boxes, o->rays, o->ray_inst, o->target,
+    void* ptrs[] = {o->pf, o->m, o->v, o->ps, o->ph, o->gh, o->ema, o->ctrl, o->ctrl_late, o->d_boxes, o->rays, o->ray_inst, o->target,
                     o->target_depth, o->bg, o->rgb_rays, o->depth_rays, o->mask_rays, o->loss, o->pts, o->enc, o->d_enc, o->ph_planar, o->partials,
                     o->dbg_out, o->dbg_dout, o->inj_xy, o->inj_col, o->inj_dt, o->grad_snap, o->r_rays, o->r_inbox, o->r_enc,
                     o->r_jit, o->r_rgb, o->r_depth, o->r_mask, o->r_Twc, o->r_pts, o->r_planar};
@@ -619,6 +693,10 @@ int mon_object_destroy(mon_object* o) {
     if (o->h_ctrl) cudaFreeHost(o->h_ctrl);
     if (o->ev0) cudaEventDestroy(o->ev0);
     if (o->ev1) cudaEventDestroy(o->ev1);
+    if (o->ev_fork_m) cudaEventDestroy(o->ev_fork_m);
+    if (o->ev_fork_s) cudaEventDestroy(o->ev_fork_s);
+    if (o->ev_join) cudaEventDestroy(o->ev_join);
+    if (o->aux) cudaStreamDestroy(o->aux);
     if (o->stream) cudaStreamDestroy(o->stream);
     delete o;
     return MON_OK;
@@ -702,7 +780,7 @@ int mon_object_sync(mon_object* o) {
 }
 
 static int read_ctrl(mon_object* o) {
-    CK(cudaMemcpyAsync(o->h_ctrl, o->ctrl, sizeof(MonCtrl), cudaMemcpyDeviceToHost, o->stream));
+    CK(cudaMemcpyAsync(o->h_ctrl, o->ctrl_late, sizeof(MonCtrl), cudaMemcpyDeviceToHost, o->stream));
     CK(cudaStreamSynchronize(o->stream));
     return MON_OK;
 }

@@ -34,4 +34,3 @@ void mon_launch_optimizer(const MonOpt& o, MonCtrl* ctrl, float* pf, __half* ph,
                           __half* planar, cudaStream_t st);
 void mon_launch_snapshot_grad(uint32_t n, uint32_t n_mlp, uint32_t n_partials, const __half* gh, const float* partials,
                               float* out, cudaStream_t st);
-void mon_launch_sum_loss(uint32_t R, const float* loss, MonCtrl* ctrl, cudaStream_t st);

@@ -34,6 +34,9 @@ struct MonGrid {
     uint32_t res[MON_MAX_LEVELS];
     uint32_t hashed[MON_MAX_LEVELS];      // 1 if coherent-prime hash is used, 0 if dense
     float scale[MON_MAX_LEVELS];
+    // entry -> level without a search: every level >= first_full has exactly 2^log2_cap entries
+    // (first_full == n_levels or log2_cap == 0: fall back to the offset search)
+    uint32_t first_full, log2_cap;
 };
 
 // constant scene description of one object
@@ -52,9 +55,13 @@ struct MonCtrl {
     uint32_t n_in;      // rays inside the box before roll-over padding
     uint32_t skip;      // 1: no ray hit the box this iteration -> all later kernels are no-ops
     uint32_t iter;      // RNG iteration counter (advances even when skipped)
-    float loss_mean;    // filled by the loss reduction kernel
+    float loss_mean;    // filled by the optimizer sweep (logged loss of the iteration)
     uint32_t n_boxes;   // live number of 2-D boxes (host-updated; keeps the captured graph valid)
-    uint32_t pad[2];
+    // per-step optimizer scalars, computed once by the batch kernel instead of once per optimizer CTA
+    float lr_base;      // learning_rate * decay_base^(#decays)            (exponential_decay.h:60-71)
+    float ema_old;      // 1 - ema_decay^(step-1)                          (ema.h:107)
+    float ema_new;      // 1 / (1 - ema_decay^step)                        (ema.h:108)
+    uint32_t pad[3];
 };
 
 // optimizer hyper-parameters
@@ -63,6 +70,9 @@ struct MonOpt {
     uint32_t decay_start, decay_interval; float decay_base;
     uint32_t n_mlp, n_params;
     uint32_t n_partials;   // number of per-CTA MLP gradient partials to sum
+    float log2_beta1, log2_beta2;   // beta^s is evaluated as exp2f(s * log2(beta))
+    float inv_loss_scale;           // 1 / loss_scale, used when loss_scale is a power of two (exact)
+    uint32_t loss_scale_pow2;
 };
 
 struct MonLossCfg { float loss_scale, depth_lambda, mask_lambda, bg_density_reg; };
@@ -72,8 +82,12 @@ struct MonBatch {
     uint32_t R;                 // rays per batch
     const mon_bbox2d* boxes;
     const MonFrame* frames;
-    MonCtrl* ctrl;
+    MonCtrl* ctrl;      // live control block, owned by the batch kernel
+    MonCtrl* late;      // copy taken by the fused MLP kernel for the scatter / optimizer kernels, so that the batch
+                        // kernel of the NEXT iteration may run concurrently with them
     uint32_t seed;
+    // learning-rate schedule / EMA constants for the per-step scalars
+    float opt_lr, decay_base, ema_decay; uint32_t decay_start, decay_interval;
     // injected randoms (nullptr -> internal counter-based generator)
     const float* inj_xy; const float* inj_col; const float* inj_dt;
     // per-ray

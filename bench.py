@@ -33,6 +33,9 @@ S = 32
 FRAMES = 30        # 30 keyframes x (1.92 MB rgb + 0.64 MB mask + 2.56 MB depth) = 154 MB > 126 MB L2
 BYTES_ENC_PER_POINT = 512       # 16 levels x 8 corners x 2 features x 2 B
 FLOPS_MLP_TRAIN_PER_POINT = {1: 18432, 2: 43008}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of each kernel, from the committed ncu --set full capture
+# (profiles/r1_ncu_kernels.txt); bytes
+TRAFFIC_NCU = {"encode": None, "scatter": None, "mlp_fused": None, "optimizer": None}
 
 
 def parse():
@@ -44,6 +47,7 @@ def parse():
     ap.add_argument("--rays", type=int, default=4096, help="rays per batch (reference: 4096, nerf_model.h:173)")
     ap.add_argument("--hidden-layers", type=int, default=1, help="MLP hidden layers (reference base.json: 1)")
     ap.add_argument("--frames", type=int, default=FRAMES)
+    ap.add_argument("--objects", type=int, default=0, help="objects in the job (default: one per GPU); object k trains on GPU k mod N")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the CPU baseline sample")
     return ap.parse_args()
 
@@ -201,7 +205,7 @@ def run_reference(args, rank, world):
 def workload_config(args, n_objects):
     return {"workload": "OfflineNeRF 1 object per GPU, base.json (16-lvl hash 2^16x2 fp16, MLP 32-64%s-16pad), synthetic 'room' 800x800" % ("-64" if args.hidden_layers == 2 else ""),
             "rays_per_batch": args.rays, "samples_per_ray": S, "points_per_iter": args.rays * S, "n_hidden_layers": args.hidden_layers,
-            "objects": n_objects, "keyframes": args.frames, "partition": "object k -> GPU k (no collective)",
+            "objects": n_objects, "keyframes": args.frames, "partition": "object k -> GPU k mod N, per-object streams (no collective)",
             "l2_policy": "keyframe set 154 MB > 126 MB L2; per-object state (42 MB) is L2-resident in steady state by design, as in production back-to-back iterations"}
 
 
@@ -209,7 +213,7 @@ def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
 
-    from ro_map_b200 import build, core
+    from ro_map_b200 import build, core, partition
 
     distributed = world > 1
     if distributed:
@@ -223,15 +227,24 @@ def run_ours(args, rank, world, local_rank):
         raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
     gpu = local_rank
 
-    seq = make_scene(max(world, 1), args.frames)
-    obj = seq.objects[rank % len(seq.objects)]
+    n_objects = args.objects if args.objects > 0 else world      # default: one object per GPU (weak scaling)
+    seq = make_scene(n_objects, args.frames)
+    mine = partition.assign_objects(n_objects, world)[rank]        # object k -> rank k % world, no collective on the data path
     R, K, Wm = args.rays, args.steps, args.warmup
     cfg = core.default_config(rays_per_batch=R, n_hidden_layers=args.hidden_layers)
-    bmin, bmax = -1.1 * obj.half, 1.1 * obj.half
 
     def upload(ds):
         for i in range(len(seq.poses)):
             ds.add_frame(i, seq.rgb[i], seq.instance[i], seq.depth[i], seq.poses[i])
+
+    def make_objects(ds):
+        objs = []
+        for k in mine:
+            o = seq.objects[k]
+            n = core.NerfObject(ds, cfg, o.Tow, -1.1 * o.half, 1.1 * o.half, o.instance_id)
+            n.set_bboxes(o.boxes)
+            objs.append(n)
+        return objs
 
     def barrier():
         torch.cuda.synchronize()
@@ -239,56 +252,63 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-timed: inputs resident
+    # ---------------- device-timed: inputs resident.  Objects of one rank train concurrently on per-object streams.
     ds = core.Dataset(gpu, *seq.K, seq.H, seq.W, len(seq.poses), True)
     upload(ds)
-    nerf = core.NerfObject(ds, cfg, obj.Tow, bmin, bmax, obj.instance_id)
-    nerf.set_bboxes(obj.boxes)
-    nerf.train(max(Wm, 3))
+    nerfs = make_objects(ds)
+    for n in nerfs:
+        n.train(max(Wm, 3))
     with ClockSampler(gpu) as clocks:
         barrier()
-        l0 = nerf.launch_count
-        nerf.train_async(K)
-        nerf.sync()
+        l0 = sum(n.launch_count for n in nerfs)
+        for n in nerfs:
+            n.train_async(K)
+        for n in nerfs:
+            n.sync()
         barrier()
-        ms = nerf.last_train_ms
-        launches = nerf.launch_count - l0
+        ms = max([n.last_train_ms for n in nerfs], default=0.0)   # CUDA events on each object's stream
+        launches = sum(n.launch_count for n in nerfs) - l0
         # keep the GPU under the same load while nvidia-smi samples (each sample is 100 ms; the timed region may be shorter)
         t_end = time.perf_counter() + 1.0
-        while time.perf_counter() < t_end:
-            nerf.train(K)
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if distributed:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    loss = nerf.train(1)
+        while nerfs and time.perf_counter() < t_end:
+            for n in nerfs:
+                n.train_async(K)
+            for n in nerfs:
+                n.sync()
+    ms_max = partition.reduce_max(ms, "cuda")
+    launches = int(partition.reduce_sum(float(launches), "cuda"))
+    loss = nerfs[0].train(1) if nerfs else float("nan")
 
-    # ---------------- per-stage device times for the roofline (live, CUDA events between kernels)
-    stages = nerf.train_profiled(50)
-    nerf.close()
+    # ---------------- per-stage device times for the roofline (live, CUDA events between kernels), rank 0 / first object
+    stages = nerfs[0].train_profiled(50) if nerfs else {}
+    for n in nerfs:
+        n.close()
 
     # ---------------- end to end from host buffers through the C ABI
     ds2 = core.Dataset(gpu, *seq.K, seq.H, seq.W, len(seq.poses), True)
-    nerf2 = core.NerfObject(ds2, cfg, obj.Tow, bmin, bmax, obj.instance_id)
     # warm the graphs with a throw-away frame set so that capture cost is not billed to the timed region
     upload(ds2)
-    nerf2.set_bboxes(obj.boxes)
-    nerf2.train(max(Wm, 3))
+    nerfs2 = make_objects(ds2)
+    for n in nerfs2:
+        n.train(max(Wm, 3))
     barrier()
     t0 = time.perf_counter()
-    upload(ds2)                      # H2D: every keyframe again, from pageable host arrays
-    nerf2.set_bboxes(obj.boxes)      # H2D: 20 B per box
-    loss_e2e = nerf2.train(K)        # K iterations + 32-byte D2H (loss, step)
+    upload(ds2)                                  # H2D: every keyframe again, from pageable host arrays
+    for k, n in zip(mine, nerfs2):
+        n.set_bboxes(seq.objects[k].boxes)       # H2D: 20 B per box
+    for n in nerfs2:
+        n.train_async(K)
+    losses_e2e = [n.train(0) for n in nerfs2]    # waits for the K iterations + 48-byte D2H (loss, step) per object
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if distributed:
         dist.barrier()
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.item())
+    e2e_s = partition.reduce_max(e2e_s, "cuda")
     px = seq.H * seq.W
-    h2d = len(seq.poses) * (px * 3 + px + px * 4 + 88) + len(obj.boxes) * 20
-    nerf2.close()
+    h2d = len(seq.poses) * (px * 3 + px + px * 4 + 88) + sum(len(seq.objects[k].boxes) for k in mine) * 20
+    h2d = partition.reduce_sum(float(h2d), "cuda")
+    for n in nerfs2:
+        n.close()
 
     if rank != 0:
         if distributed:
@@ -318,20 +338,24 @@ def run_ours(args, rank, world, local_rank):
     d = stage_roof[dominant]
     roofline = {"kernel": dominant, "bound": d["bound"], "achieved": d["achieved"], "unit": d["unit"].split(" ")[0],
                 "peak": peaks["hbm_gbs"] if d["bound"] == "hbm" else peaks["tflops_sustained"], "peak_source": peaks["src"] + (" (sustained)" if d["bound"] == "tensor" else ""),
-                "frac": d["frac"], "traffic": None, "stage_ms_sum": sum(stages.values()), "stages": stage_roof}
+                "frac": d["frac"], "traffic": TRAFFIC_NCU.get(dominant), "traffic_source": "profiles/ (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+                "algorithmic_bytes_or_flops_per_launch": enc_bytes if d["bound"] == "hbm" and dominant != "optimizer" else (10 * P if dominant == "optimizer" else flops),
+                "stage_ms_sum": sum(stages.values()), "stages": stage_roof,
+                "note": "stage times come from a serial (un-forked) replay with a CUDA event between kernels; the production graph overlaps batch+points of iteration i+1 with scatter+optimizer of iteration i"}
 
     base = cpu_baseline(seq, seq.objects[0], R, args.hidden_layers, args.cpu_seconds)
 
-    iters_per_s = world * K / (ms_max * 1e-3)
+    iters_per_s = n_objects * K / (ms_max * 1e-3)
     line = {
         "metric": "train iters/sec per object", "value": iters_per_s, "unit": "iters/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f16 storage / f32 accumulate", "data": "synthetic", "config": workload_config(args, world),
+        "dtype": "f16 storage / f32 accumulate", "data": "synthetic", "config": workload_config(args, n_objects),
+        "iters_per_s_per_object": iters_per_s / max(n_objects, 1),
         "rays_per_s": iters_per_s * R, "points_per_s": iters_per_s * N, "final_loss": loss,
         "clocks": clocks.summary(),
-        "e2e": {"value": world * K / e2e_s, "unit": "iters/s", "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": 32.0 / K,
-                "seconds": e2e_s, "final_loss": loss_e2e,
-                "region": "keyframe upload from host numpy + box upload + K iterations + loss read-back"},
+        "e2e": {"value": n_objects * K / e2e_s, "unit": "iters/s", "h2d_bytes_per_step": h2d / (n_objects * K), "d2h_bytes_per_step": 48.0 / K,
+                "seconds": e2e_s, "final_loss": losses_e2e[0] if losses_e2e else None,
+                "region": "keyframe upload from host numpy + box upload + K iterations per object + loss read-back"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": base,

@@ -76,6 +76,35 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+HOST = PKG / "host"
+HOST_LIB = PKG / "libMON.so"
+HOST_BIN = PKG / "offline_nerf"
+
+
+def build_host(force: bool = False) -> Path:
+    """libMON.so: the C++ facade (nerf::NerfManagerOffline/Online, NeRF) over the C ABI, plus the headless
+    offline_nerf driver.  Plain g++: no CUDA, Eigen or OpenCV needed (mon_compat.h falls back to shims)."""
+    build()
+    srcs = [HOST / "nerf_host.cpp"]
+    deps = srcs + sorted(HOST.glob("*.h")) + [ROOT / "include" / "mon_c.h"]
+    newest = max(p.stat().st_mtime for p in deps)
+    cxx = os.environ.get("CXX", "g++")
+    common = ["-std=c++17", "-O2", "-fPIC", "-Wall", "-pthread", "-I", str(ROOT / "include"), "-I", str(HOST)]
+    if force or not HOST_LIB.exists() or HOST_LIB.stat().st_mtime < newest:
+        cmd = [cxx, *common, "-shared", "-o", str(HOST_LIB), *map(str, srcs), "-L", str(PKG), "-lmon_b200", "-lz", "-Wl,-rpath,$ORIGIN"]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError("libMON.so build failed:\n" + proc.stdout + proc.stderr)
+    main_src = HOST / "offline_nerf.cpp"
+    if force or not HOST_BIN.exists() or HOST_BIN.stat().st_mtime < max(newest, main_src.stat().st_mtime):
+        cmd = [cxx, *common, "-o", str(HOST_BIN), str(main_src), "-L", str(PKG), "-lMON", "-lmon_b200", "-lz", "-Wl,-rpath,$ORIGIN"]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError("offline_nerf build failed:\n" + proc.stdout + proc.stderr)
+    return HOST_LIB
+
+
 if __name__ == "__main__":
     path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
     print(path)
+    print(build_host(force="--force" in sys.argv))

@@ -246,13 +246,44 @@ k_encode_backward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, c
         if (l >= g.n_levels || (gw[j] & 0x7fff7fffu) == 0) continue;
         const float g0 = __half2float(__ushort_as_half((unsigned short)(gw[j] & 0xffffu)));
         const float g1 = __half2float(__ushort_as_half((unsigned short)(gw[j] >> 16)));
-        EncCorner c;
-        level_corners(g, l, u, c);
-        __half2* tab = reinterpret_cast<__half2*>(grid_grad) + g.offset[l];
+        const uint32_t size = g.size[l];
+        char* tab = reinterpret_cast<char*>(reinterpret_cast<__half2*>(grid_grad) + g.offset[l]);
+        if ((size & (size - 1)) == 0) {
+            // same index arithmetic as the forward kernel, directly in byte offsets of the 4-byte entries
+            const float scale = g.scale[l];
+            const uint32_t res = g.res[l];
+            const bool hashed = g.hashed[l] != 0;
+            const uint32_t bmask = 4u * size - 4u;
+            float fr[3]; uint32_t cell[3];
+            mon_pos_fract(u[0], scale, fr[0], cell[0]);
+            mon_pos_fract(u[1], scale, fr[1], cell[1]);
+            mon_pos_fract(u[2], scale, fr[2], cell[2]);
+            const float h0 = __fsub_rn(1.0f, fr[0]), h1 = __fsub_rn(1.0f, fr[1]), h2 = __fsub_rn(1.0f, fr[2]);
+            const float wxy[4] = {__fmul_rn(h0, h1), __fmul_rn(fr[0], h1), __fmul_rn(h0, fr[1]), __fmul_rn(fr[0], fr[1])};
+            uint32_t ax[2], ay[2], az[2];
+            ax[0] = cell[0] << 2; ax[1] = (cell[0] + 1u) << 2;
+            if (hashed) {
+                ay[0] = (cell[1] * 2654435761u) << 2; ay[1] = ((cell[1] + 1u) * 2654435761u) << 2;
+                az[0] = (cell[2] * 805459861u) << 2; az[1] = ((cell[2] + 1u) * 805459861u) << 2;
+            } else {
+                ay[0] = (cell[1] * res) << 2; ay[1] = ((cell[1] + 1u) * res) << 2;
+                az[0] = (cell[2] * res * res) << 2; az[1] = ((cell[2] + 1u) * res * res) << 2;
+            }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const __half2 v = __halves2half2(__float2half_rn(__fmul_rn(g0, c.w[k])), __float2half_rn(__fmul_rn(g1, c.w[k])));
-            red_add_f16x2(tab + c.idx[k], v);
+            for (uint32_t k = 0; k < 8; ++k) {
+                const float wgt = __fmul_rn(wxy[k & 3], (k & 4) ? fr[2] : h2);
+                const uint32_t off = (hashed ? (ax[k & 1] ^ ay[(k >> 1) & 1] ^ az[k >> 2]) : (ax[k & 1] + ay[(k >> 1) & 1] + az[k >> 2])) & bmask;
+                const __half2 v = __floats2half2_rn(__fmul_rn(g0, wgt), __fmul_rn(g1, wgt));
+                red_add_f16x2(reinterpret_cast<__half2*>(tab + off), v);
+            }
+        } else {
+            EncCorner c;
+            level_corners(g, l, u, c);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const __half2 v = __halves2half2(__float2half_rn(__fmul_rn(g0, c.w[k])), __float2half_rn(__fmul_rn(g1, c.w[k])));
+                red_add_f16x2(reinterpret_cast<__half2*>(tab) + c.idx[k], v);
+            }
         }
     }
 }

@@ -33,14 +33,17 @@
 using namespace tc05;
 
 #define TC_THREADS 128
-#define TC_TMEM_COLS 256
-// TMEM column map
+// TMEM column map.  The per-tile accumulators are never live at the same time (each is drained by its epilogue
+// before the next MMA is issued), so they share columns 0-63; only the weight-gradient accumulators persist.
 #define TC_COL_D 0     // 64: hidden pre-activation, later dL/dhidden
-#define TC_COL_O 64    // 16: network output
-#define TC_COL_E 96    // 32: dL/dencoding
-#define TC_COL_G1 128  // 16: [hid|dhid]^T . dout
-#define TC_COL_G2 160  // 32: [hid|dhid]^T . enc
-#define TC_COL_H2 192  // 64: second hidden layer pre-activation / its gradient (n_hidden_layers == 2)
+#define TC_COL_O 0     // 16: network output                      (aliases D)
+#define TC_COL_E 0     // 32: dL/dencoding                        (aliases D)
+#define TC_COL_G1 64   // 16: [hid|dhid]^T . dout                 (persistent)
+#define TC_COL_G2 96   // 32: [hid|dhid]^T . enc                  (persistent)
+#define TC_COL_H2 128  // 64: [H2|dH2]^T . H1, n_hidden_layers == 2 (persistent)
+// 128 columns (NH == 1) let three CTAs share an SM's 512 TMEM columns; NH == 2 needs 192 -> 256
+#define TC_TMEM_COLS(NH) ((NH) == 1 ? 128u : 256u)
+#define TC_CTAS_PER_SM(NH) ((NH) == 1 ? 3 : 2)
 
 // shared memory map (bytes from a 1024-aligned base)
 #define SM_ENC 0         //  8192  [128][32]  SW64
@@ -58,8 +61,9 @@ using namespace tc05;
 #define SM_WH 91136      //  8192  B of the hidden GEMM: W_h [64][64] SW128
 #define SM_WHT 99328     //  8192  B of its dgrad: W_h^T [64][64] SW128
 #define SM_TOTAL 107520
-// dynamic request (incl. 1 KB alignment slack): two CTAs fit per SM (2 x 256 TMEM columns = the whole TMEM), a third cannot
-#define TC_SMEM_BYTES (108 * 1024)
+// dynamic request (incl. 1 KB alignment slack), sized so that exactly TC_CTAS_PER_SM CTAs fit in the 227 KB of an SM:
+// NH == 1: 3 x 60 KB (a 4th would also exceed the TMEM), NH == 2: 2 x 108 KB
+#define TC_SMEM_BYTES(NH) ((NH) == 1 ? 60 * 1024 : 108 * 1024)
 
 static constexpr uint32_t IDESC_64_KK = make_idesc(128, 64, 0, 0);
 static constexpr uint32_t IDESC_16_KK = make_idesc(128, 16, 0, 0);
@@ -77,7 +81,7 @@ struct TcCtx {
     uint32_t tid, lane, warp;
 };
 
-__device__ __forceinline__ void tc_setup(TcCtx& c, unsigned char* raw) {
+__device__ __forceinline__ void tc_setup(TcCtx& c, unsigned char* raw, uint32_t tmem_cols) {
     c.tid = threadIdx.x; c.lane = c.tid & 31; c.warp = c.tid >> 5;
     const uint32_t raw_addr = smem_u32(raw);
     const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
@@ -86,7 +90,7 @@ __device__ __forceinline__ void tc_setup(TcCtx& c, unsigned char* raw) {
     c.bar = reinterpret_cast<uint64_t*>(c.sm + SM_BAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c.sm + SM_BAR + 8);
     if (c.tid == 0) { mbar_init(c.bar, 1); mbar_fence_init(); }
-    if (c.warp == 0) { __syncwarp(); tmem_alloc(tmem_slot, TC_TMEM_COLS); }
+    if (c.warp == 0) { __syncwarp(); tmem_alloc(tmem_slot, tmem_cols); }
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
@@ -94,10 +98,10 @@ __device__ __forceinline__ void tc_setup(TcCtx& c, unsigned char* raw) {
     c.phase = 0;
 }
 
-__device__ __forceinline__ void tc_teardown(TcCtx& c) {
+__device__ __forceinline__ void tc_teardown(TcCtx& c, uint32_t tmem_cols) {
     fence_before_sync();
     __syncthreads();
-    if (c.warp == 0) { __syncwarp(); tmem_dealloc(c.tmem, TC_TMEM_COLS); }
+    if (c.warp == 0) { __syncwarp(); tmem_dealloc(c.tmem, tmem_cols); }
 }
 
 // weights -> shared memory in the operand layouts (params: W_in [64][32] | (W_h [64][64]) | W_out [16][64], row-major fp16)
@@ -134,21 +138,28 @@ __device__ __forceinline__ void tc_load_weights(const TcCtx& c, const __half* __
     }
 }
 
-// stage this thread's row of the 128 x 32 fp16 encoding tile into the SW64 operand layout.  The encoding is
-// feature-major (enc_soa[feature][point], n_total points per feature row): 32 two-byte loads, coalesced across the
-// warp (consecutive threads = consecutive points).  Invalid rows are zero-filled.
-__device__ __forceinline__ void tc_stage_enc(const TcCtx& c, const __half* __restrict__ enc_soa, size_t n_total, size_t pt, bool valid) {
+// Staging of one row of the 128 x 32 fp16 encoding tile in two halves, so that the global loads of the NEXT tile can
+// be in flight while the tensor core and the epilogues work on the current one.  The encoding is feature-major
+// (enc_soa[feature][point], n_total points per feature row): 32 two-byte loads, coalesced across the warp
+// (consecutive threads = consecutive points).  Invalid rows are zero-filled.
+__device__ __forceinline__ void tc_load_enc(uint32_t packed[16], const __half* __restrict__ enc_soa, size_t n_total, size_t pt, bool valid) {
     const unsigned short* src = reinterpret_cast<const unsigned short*>(enc_soa) + pt;
-    uint32_t packed[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
         const uint32_t lo = valid ? (uint32_t)__ldg(src + (size_t)(2 * k) * n_total) : 0u;
         const uint32_t hi = valid ? (uint32_t)__ldg(src + (size_t)(2 * k + 1) * n_total) : 0u;
         packed[k] = lo | (hi << 16);
     }
+}
+__device__ __forceinline__ void tc_store_enc(const TcCtx& c, const uint32_t packed[16]) {
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch)
         *reinterpret_cast<uint4*>(c.sm + SM_ENC + sw64_off(c.tid, ch)) = make_uint4(packed[4 * ch], packed[4 * ch + 1], packed[4 * ch + 2], packed[4 * ch + 3]);
+}
+__device__ __forceinline__ void tc_stage_enc(const TcCtx& c, const __half* __restrict__ enc_soa, size_t n_total, size_t pt, bool valid) {
+    uint32_t packed[16];
+    tc_load_enc(packed, enc_soa, n_total, pt, valid);
+    tc_store_enc(c, packed);
 }
 
 // make the CTA's shared-memory writes visible to the tensor core, then let thread 0 issue
@@ -259,7 +270,7 @@ __device__ __forceinline__ void tc_forward_hidden(TcCtx& c, uint64_t& mask_first
 
 // ------------------------------------------------------------------------------------------ training
 template <int NH>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(TC_THREADS, TC_CTAS_PER_SM(NH))
 k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
     extern __shared__ unsigned char smem_raw[];
     // hand the iteration's control block to the kernels behind this one (scatter, optimizer): the batch kernel of
@@ -267,7 +278,7 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
     if (blockIdx.x == 0 && threadIdx.x == 0) *b.late = *b.ctrl;
     if (b.ctrl->skip) return;
     TcCtx c;
-    tc_setup(c, smem_raw);
+    tc_setup(c, smem_raw, TC_TMEM_COLS(NH));
     tc_load_weights<NH>(c, b.params);
     // the upper half of every dout row (outputs 4..15 and the second K chunk) stays zero for the whole kernel
     for (uint32_t i = c.tid; i < 4096 / 16; i += TC_THREADS) reinterpret_cast<uint4*>(c.sm + SM_DOUT)[i] = make_uint4(0, 0, 0, 0);
@@ -277,14 +288,20 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
     const uint32_t n_tiles = (b.R + 3) / 4;
     uint32_t tiles_done = 0;
 
+    uint32_t enc_regs[16];   // this thread's encoding row of the NEXT tile, prefetched one tile ahead
+    if (blockIdx.x < n_tiles) tc_load_enc(enc_regs, b.enc, (size_t)b.R * 32, (size_t)blockIdx.x * 128 + c.tid, blockIdx.x * 4 + c.warp < b.R);
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tiles_done) {
         const uint32_t ray = tile * 4 + c.warp;
         const bool ray_ok = ray < b.R;
         const uint32_t pt = ray * 32 + c.lane;
         // ---- stage encodings, MMA1
-        tc_stage_enc(c, b.enc, (size_t)b.R * 32, pt, ray_ok);
+        tc_store_enc(c, enc_regs);
         TC_PUBLISH_AND_SYNC();
         if (c.tid == 0) tc_issue_layer_in(c);
+        {
+            const uint32_t next = tile + gridDim.x;
+            if (next < n_tiles) tc_load_enc(enc_regs, b.enc, (size_t)b.R * 32, (size_t)next * 128 + c.tid, next * 4 + c.warp < b.R);
+        }
         // per-ray inputs of the renderer, fetched while the tensor core works
         MonRay r;
         RayTargets rt;
@@ -429,17 +446,17 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
             }
         }
     }
-    tc_teardown(c);
+    tc_teardown(c, TC_TMEM_COLS(NH));
 }
 
 // ------------------------------------------------------------------------------------------ inference
 // raw network output (4 logits per point) for the density lattice and the parity hooks
 template <int NH>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(TC_THREADS, TC_CTAS_PER_SM(NH))
 k_mlp_infer_tc(uint32_t n_points, const __half* __restrict__ params, const __half* __restrict__ enc, float* __restrict__ out4) {
     extern __shared__ unsigned char smem_raw[];
     TcCtx c;
-    tc_setup(c, smem_raw);
+    tc_setup(c, smem_raw, TC_TMEM_COLS(NH));
     tc_load_weights<NH>(c, params);
     const uint32_t n_tiles = (n_points + 127) / 128;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -462,18 +479,18 @@ k_mlp_infer_tc(uint32_t n_points, const __half* __restrict__ params, const __hal
             reinterpret_cast<float4*>(out4)[pt] = o;
         }
     }
-    tc_teardown(c);
+    tc_teardown(c, TC_TMEM_COLS(NH));
 }
 
 // test render (VolumeRender_Render, nerf_model.cu:1134-1229): per ray S2/32 tiles with a carried compositing state
 template <int NH>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(TC_THREADS, TC_CTAS_PER_SM(NH))
 k_mlp_render_tc(uint32_t n_rays, uint32_t S2, const MonRay* __restrict__ rays, const int* __restrict__ in_box,
                 const float* __restrict__ jitter, uint32_t seed, uint32_t iter, const __half* __restrict__ params,
                 const __half* __restrict__ enc, float bgc, float* __restrict__ rgb, float* __restrict__ depth, float* __restrict__ mask) {
     extern __shared__ unsigned char smem_raw[];
     TcCtx c;
-    tc_setup(c, smem_raw);
+    tc_setup(c, smem_raw, TC_TMEM_COLS(NH));
     tc_load_weights<NH>(c, params);
     const uint32_t n_groups = (n_rays + 3) / 4, chunks = S2 / 32;
     for (uint32_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
@@ -517,24 +534,24 @@ k_mlp_render_tc(uint32_t n_rays, uint32_t S2, const MonRay* __restrict__ rays, c
             }
         }
     }
-    tc_teardown(c);
+    tc_teardown(c, TC_TMEM_COLS(NH));
 }
 
 // ------------------------------------------------------------------------------------------ launchers
 template <typename K>
-static cudaError_t tc_prepare(K kernel) {
-    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+static cudaError_t tc_prepare(K kernel, int smem_bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
 }
 
 cudaError_t mon_launch_mlp_train_tc(const MonBatch& b, const MonLossCfg& lc, uint32_t n_hidden, uint32_t n_mlp, uint32_t n_ctas, cudaStream_t st) {
     if (n_hidden == 1) {
-        static cudaError_t prep = tc_prepare(k_mlp_train_tc<1>);
+        static cudaError_t prep = tc_prepare(k_mlp_train_tc<1>, TC_SMEM_BYTES(1));
         if (prep != cudaSuccess) return prep;
-        k_mlp_train_tc<1><<<n_ctas, TC_THREADS, TC_SMEM_BYTES, st>>>(b, lc, n_mlp);
+        k_mlp_train_tc<1><<<n_ctas, TC_THREADS, TC_SMEM_BYTES(1), st>>>(b, lc, n_mlp);
     } else if (n_hidden == 2) {
-        static cudaError_t prep = tc_prepare(k_mlp_train_tc<2>);
+        static cudaError_t prep = tc_prepare(k_mlp_train_tc<2>, TC_SMEM_BYTES(2));
         if (prep != cudaSuccess) return prep;
-        k_mlp_train_tc<2><<<n_ctas, TC_THREADS, TC_SMEM_BYTES, st>>>(b, lc, n_mlp);
+        k_mlp_train_tc<2><<<n_ctas, TC_THREADS, TC_SMEM_BYTES(2), st>>>(b, lc, n_mlp);
     } else {
         return cudaErrorNotSupported;
     }
@@ -543,16 +560,16 @@ cudaError_t mon_launch_mlp_train_tc(const MonBatch& b, const MonLossCfg& lc, uin
 
 cudaError_t mon_launch_mlp_infer_tc(uint32_t n_points, uint32_t n_hidden, const __half* params, const __half* enc, float* out4, cudaStream_t st) {
     uint32_t ctas = (n_points + 127) / 128;
-    if (ctas > 296) ctas = 296;
+    if (ctas > 444) ctas = 444;
     if (ctas == 0) ctas = 1;
     if (n_hidden == 1) {
-        static cudaError_t prep = tc_prepare(k_mlp_infer_tc<1>);
+        static cudaError_t prep = tc_prepare(k_mlp_infer_tc<1>, TC_SMEM_BYTES(1));
         if (prep != cudaSuccess) return prep;
-        k_mlp_infer_tc<1><<<ctas, TC_THREADS, TC_SMEM_BYTES, st>>>(n_points, params, enc, out4);
+        k_mlp_infer_tc<1><<<ctas, TC_THREADS, TC_SMEM_BYTES(1), st>>>(n_points, params, enc, out4);
     } else if (n_hidden == 2) {
-        static cudaError_t prep = tc_prepare(k_mlp_infer_tc<2>);
+        static cudaError_t prep = tc_prepare(k_mlp_infer_tc<2>, TC_SMEM_BYTES(2));
         if (prep != cudaSuccess) return prep;
-        k_mlp_infer_tc<2><<<ctas, TC_THREADS, TC_SMEM_BYTES, st>>>(n_points, params, enc, out4);
+        k_mlp_infer_tc<2><<<ctas, TC_THREADS, TC_SMEM_BYTES(2), st>>>(n_points, params, enc, out4);
     } else {
         return cudaErrorNotSupported;
     }
@@ -563,16 +580,16 @@ cudaError_t mon_launch_mlp_render_tc(uint32_t n_rays, uint32_t S2, uint32_t n_hi
                                      uint32_t seed, uint32_t iter, const __half* params, const __half* enc, float bgc,
                                      float* rgb, float* depth, float* mask, cudaStream_t st) {
     uint32_t ctas = (n_rays + 3) / 4;
-    if (ctas > 296) ctas = 296;
+    if (ctas > 444) ctas = 444;
     if (ctas == 0) ctas = 1;
     if (n_hidden == 1) {
-        static cudaError_t prep = tc_prepare(k_mlp_render_tc<1>);
+        static cudaError_t prep = tc_prepare(k_mlp_render_tc<1>, TC_SMEM_BYTES(1));
         if (prep != cudaSuccess) return prep;
-        k_mlp_render_tc<1><<<ctas, TC_THREADS, TC_SMEM_BYTES, st>>>(n_rays, S2, rays, in_box, jitter, seed, iter, params, enc, bgc, rgb, depth, mask);
+        k_mlp_render_tc<1><<<ctas, TC_THREADS, TC_SMEM_BYTES(1), st>>>(n_rays, S2, rays, in_box, jitter, seed, iter, params, enc, bgc, rgb, depth, mask);
     } else if (n_hidden == 2) {
-        static cudaError_t prep = tc_prepare(k_mlp_render_tc<2>);
+        static cudaError_t prep = tc_prepare(k_mlp_render_tc<2>, TC_SMEM_BYTES(2));
         if (prep != cudaSuccess) return prep;
-        k_mlp_render_tc<2><<<ctas, TC_THREADS, TC_SMEM_BYTES, st>>>(n_rays, S2, rays, in_box, jitter, seed, iter, params, enc, bgc, rgb, depth, mask);
+        k_mlp_render_tc<2><<<ctas, TC_THREADS, TC_SMEM_BYTES(2), st>>>(n_rays, S2, rays, in_box, jitter, seed, iter, params, enc, bgc, rgb, depth, mask);
     } else {
         return cudaErrorNotSupported;
     }

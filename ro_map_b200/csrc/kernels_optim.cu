@@ -106,25 +106,41 @@ k_optimizer_sweep(MonOpt o, MonCtrl* __restrict__ ctrl, float* __restrict__ pf, 
         if (threadIdx.x == 0) ctrl->loss_mean = s_loss[0] / (float)R;
     }
     const float lr_base = ctrl->lr_base, old_db = ctrl->ema_old, new_db = ctrl->ema_new;
-    const uint32_t i4 = (blockIdx.x * OPT_THREADS + threadIdx.x) * OPT_PER_THREAD;   // n_params and n_mlp are multiples of 4
-    if (i4 >= o.n_params) return;
-    const bool is_mlp = i4 < o.n_mlp;
-
-    // ---- gradient of the 4 parameters (loss-scaled, fp16-representable)
+    // CTA layout: the first n_mlp/32 CTAs own the MLP weights (one WARP per 4 parameters: the lanes split the
+    // per-CTA gradient partials of the fused MLP kernel), every other CTA owns 1024 consecutive grid parameters
+    // (one THREAD per 4 parameters).  n_params and n_mlp are multiples of 32 resp. 4.
+    const uint32_t n_mlp_ctas = o.n_mlp / (OPT_PER_THREAD * (OPT_THREADS / 32));
+    const bool is_mlp = blockIdx.x < n_mlp_ctas;
+    uint32_t i4;
     float g[4];
-    uint2* gw = reinterpret_cast<uint2*>(gh + i4);
+    uint2* gw;
     if (is_mlp) {
-        // sum the per-CTA partials in a fixed order -> bitwise reproducible MLP gradient
-        float4 s = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        for (uint32_t c = 0; c < o.n_partials; ++c) {
+        const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        i4 = (blockIdx.x * (OPT_THREADS / 32) + warp) * OPT_PER_THREAD;
+        // fixed-order reduction -> bitwise reproducible MLP gradient: lane l sums partial rows l, l+32, ... in
+        // ascending order, then a butterfly over the lanes
+        float4 s4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        for (uint32_t c = lane; c < o.n_partials; c += 32) {
             const float4 p = *reinterpret_cast<const float4*>(mlp_partials + (size_t)c * o.n_mlp + i4);
-            s.x = __fadd_rn(s.x, p.x); s.y = __fadd_rn(s.y, p.y); s.z = __fadd_rn(s.z, p.z); s.w = __fadd_rn(s.w, p.w);
+            s4.x = __fadd_rn(s4.x, p.x); s4.y = __fadd_rn(s4.y, p.y); s4.z = __fadd_rn(s4.z, p.z); s4.w = __fadd_rn(s4.w, p.w);
         }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            s4.x = __fadd_rn(s4.x, __shfl_xor_sync(0xffffffffu, s4.x, off));
+            s4.y = __fadd_rn(s4.y, __shfl_xor_sync(0xffffffffu, s4.y, off));
+            s4.z = __fadd_rn(s4.z, __shfl_xor_sync(0xffffffffu, s4.z, off));
+            s4.w = __fadd_rn(s4.w, __shfl_xor_sync(0xffffffffu, s4.w, off));
+        }
+        if (lane != 0) return;
+        gw = reinterpret_cast<uint2*>(gh + i4);
         // the reference stores weight gradients in fp16 (loss-scaled); keep that rounding point
-        const __half2 a = __floats2half2_rn(s.x, s.y), b = __floats2half2_rn(s.z, s.w);
+        const __half2 a = __floats2half2_rn(s4.x, s4.y), b = __floats2half2_rn(s4.z, s4.w);
         *gw = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));   // kept for inspection
         g[0] = __low2float(a); g[1] = __high2float(a); g[2] = __low2float(b); g[3] = __high2float(b);
     } else {
+        i4 = o.n_mlp + ((blockIdx.x - n_mlp_ctas) * OPT_THREADS + threadIdx.x) * OPT_PER_THREAD;
+        if (i4 >= o.n_params) return;
+        gw = reinterpret_cast<uint2*>(gh + i4);
         const uint2 raw = *gw;
         const __half2 a = *reinterpret_cast<const __half2*>(&raw.x), b = *reinterpret_cast<const __half2*>(&raw.y);
         g[0] = __low2float(a); g[1] = __high2float(a); g[2] = __low2float(b); g[3] = __high2float(b);
@@ -212,8 +228,9 @@ void mon_launch_cast_params(uint32_t n, const float* pf, __half* ph, cudaStream_
 void mon_launch_optimizer(const MonOpt& o, MonCtrl* ctrl, float* pf, __half* ph, __half* gh, const float* partials,
                           float* m, float* v, uint32_t* ps, __half* ema, const float* loss, uint32_t R, const MonGrid& grid,
                           __half* planar, cudaStream_t st) {
-    const uint32_t quads = (o.n_params + OPT_PER_THREAD - 1) / OPT_PER_THREAD;
-    k_optimizer_sweep<<<(quads + OPT_THREADS - 1) / OPT_THREADS, OPT_THREADS, 0, st>>>(o, ctrl, pf, ph, gh, partials, m, v, ps, ema, loss, R, grid, planar);
+    const uint32_t n_mlp_ctas = o.n_mlp / (OPT_PER_THREAD * (OPT_THREADS / 32));
+    const uint32_t grid_quads = (o.n_params - o.n_mlp + OPT_PER_THREAD - 1) / OPT_PER_THREAD;
+    k_optimizer_sweep<<<n_mlp_ctas + (grid_quads + OPT_THREADS - 1) / OPT_THREADS, OPT_THREADS, 0, st>>>(o, ctrl, pf, ph, gh, partials, m, v, ps, ema, loss, R, grid, planar);
 }
 void mon_launch_snapshot_grad(uint32_t n, uint32_t n_mlp, uint32_t n_partials, const __half* gh, const float* partials, float* out, cudaStream_t st) {
     k_snapshot_grad<<<(n + 255) / 256, 256, 0, st>>>(n, n_mlp, n_partials, gh, partials, out);

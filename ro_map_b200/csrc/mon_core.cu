@@ -29,7 +29,7 @@
 #include "mon_json.h"
 #include "mon_kernels.h"
 
-#define MON_GRAPH_CHUNK 10   // iterations captured per replayed graph (plus a 1-iteration graph for remainders)
+#define MON_GRAPH_CHUNK 50   // iterations captured per replayed graph (plus a 1-iteration graph for remainders)
 
 static thread_local std::string g_err;
 
@@ -601,8 +601,9 @@ int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uin
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, ds->gpu));
     o->sm_count = prop.multiProcessorCount;
-    // MLP kernel grid: 2 resident CTAs per SM, never more CTAs than 4-ray groups
-    o->n_ctas = std::min<uint32_t>((uint32_t)o->sm_count * 2, (o->R + 3) / 4);
+    // fused MLP kernel: persistent grid of all co-resident CTAs (3 per SM with one hidden layer, 2 with two: TMEM
+    // columns and shared memory, kernels_mlp_tc.cu), never more CTAs than 4-ray tiles
+    o->n_ctas = std::min<uint32_t>((uint32_t)o->sm_count * (cfg->n_hidden_layers == 1 ? 3u : 2u), (o->R + 3) / 4);
     if (o->n_ctas > MON_MAX_MLP_CTAS) o->n_ctas = MON_MAX_MLP_CTAS;
     o->opt.lr = cfg->learning_rate; o->opt.beta1 = cfg->beta1; o->opt.beta2 = cfg->beta2; o->opt.eps = cfg->epsilon;
     o->opt.l2_reg = cfg->l2_reg; o->opt.ema_decay = cfg->ema_decay; o->opt.loss_scale = cfg->loss_scale;

@@ -13,7 +13,7 @@
 #define MON_WIDTH 64      // hidden width (base.json n_neurons)
 #define MON_IN 32         // encoding width = n_levels * 2
 #define MON_OUT 16        // padded output width (tcnn pads 4 -> 16)
-#define MON_MAX_MLP_CTAS 296
+#define MON_MAX_MLP_CTAS 592
 
 // 36-byte POD; same field order as nerf::Ray
 struct MonRay { float o[3], d[3], d_norm, tmin, tmax; };

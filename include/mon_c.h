@@ -86,9 +86,13 @@ int mon_dataset_create(int gpu, float fx, float fy, float cx, float cy, int H, i
  * rgb: H*W*3 u8 (channel order BGR if is_bgr, as cv::imread delivers, else RGB); stored as u8
  * on the device and converted in-kernel (value = u8 * (1/255), the float the reference
  * stores, nerf_data.cu:163-164).  instance: H*W u8.  depth: H*W f32 metres (already multiplied
- * by DepthMapFactor) or NULL.  pose: camera-to-world.  Host buffers may be pageable or pinned. */
+ * by DepthMapFactor) or NULL.  pose: camera-to-world.  Host buffers may be pageable (copied through a
+ * pinned staging buffer, synchronous) or pinned (see mon_dataset_sync). */
 int mon_dataset_add_frame(mon_dataset* ds, uint32_t frame_id, const uint8_t* rgb, int is_bgr,
                           const uint8_t* instance, const float* depth, const float pose[16]);
+/* Page-locked (cudaHostAlloc / cudaHostRegister) RGB-order buffers are uploaded asynchronously without a staging copy;
+ * they must stay valid until mon_dataset_sync() returns or a blocking call on an object of this dataset completes. */
+int mon_dataset_sync(mon_dataset* ds);
 /* NeRF_Dataset::UpdateDataGPU (nerf_data.cu:341-353) */
 int mon_dataset_update_poses(mon_dataset* ds, uint32_t first_frame, uint32_t n, const float* poses16);
 int mon_dataset_frame_count(const mon_dataset* ds, uint32_t* n);

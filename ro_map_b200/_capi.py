@@ -55,6 +55,7 @@ SIGNATURES = {
     "mon_config_grid_layout": (C.c_int, [_P(Config), _P(C.c_uint32), _f32p, _P(C.c_uint32)]),
     "mon_dataset_create": (C.c_int, [C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_uint32, C.c_int, _P(_vp)]),
     "mon_dataset_add_frame": (C.c_int, [_vp, C.c_uint32, _vp, C.c_int, _vp, _vp, _f32p]),
+    "mon_dataset_sync": (C.c_int, [_vp]),
     "mon_dataset_update_poses": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _f32p]),
     "mon_dataset_frame_count": (C.c_int, [_vp, _P(C.c_uint32)]),
     "mon_dataset_clone_from_peer": (C.c_int, [_vp, _vp]),

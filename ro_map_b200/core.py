@@ -102,6 +102,9 @@ class Dataset:
         check(self._lib.mon_dataset_add_frame(self._h, frame_id, _ptr(rgb), int(is_bgr), _ptr(inst),
                                                None if d is None else _ptr(d), pose.ctypes.data_as(C.POINTER(C.c_float))))
 
+    def sync(self):
+        check(self._lib.mon_dataset_sync(self._h))
+
     def update_poses(self, first: int, poses_c2w):
         flat = np.concatenate([_mat16(p) for p in poses_c2w]).astype(np.float32)
         check(self._lib.mon_dataset_update_poses(self._h, first, len(poses_c2w), flat.ctypes.data_as(C.POINTER(C.c_float))))

@@ -94,6 +94,41 @@ __device__ __forceinline__ void bulk_load_table(uint32_t smem_dst, const void* g
     }
 }
 
+// the inner loop for power-of-two tables (every table of the supported configurations): index arithmetic directly in
+// byte offsets of the shared-memory slice, ((a ^ b ^ c) & (size-1)) * 2 == (2a ^ 2b ^ 2c) & (2*size-2); HASHED selects
+// the coherent-prime hash or the dense (wrapping) linear index at compile time
+template <bool HASHED>
+__device__ __forceinline__ void enc_points_pow2(const float* __restrict__ pts, __half* __restrict__ out, uint32_t p_first, uint32_t p_end,
+                                                float scale, uint32_t size, uint32_t res, uint32_t table_smem) {
+    const uint32_t bmask = 2u * size - 2u;
+    const uint32_t my = HASHED ? 2654435761u : res, mz = HASHED ? 805459861u : res * res;
+    for (uint32_t p = p_first; p < p_end; p += ENC_THREADS) {
+        const float u0 = __ldg(pts + (size_t)p * 3), u1 = __ldg(pts + (size_t)p * 3 + 1), u2 = __ldg(pts + (size_t)p * 3 + 2);
+        float fr[3]; uint32_t cell[3];
+        mon_pos_fract(u0, scale, fr[0], cell[0]);
+        mon_pos_fract(u1, scale, fr[1], cell[1]);
+        mon_pos_fract(u2, scale, fr[2], cell[2]);
+        const float g0 = __fsub_rn(1.0f, fr[0]), g1 = __fsub_rn(1.0f, fr[1]), g2 = __fsub_rn(1.0f, fr[2]);
+        // (1*fx)*fy shared by the two z corners; same multiplication order as the reference
+        const float wxy[4] = {__fmul_rn(g0, g1), __fmul_rn(fr[0], g1), __fmul_rn(g0, fr[1]), __fmul_rn(fr[0], fr[1])};
+        // per-axis contributions to the byte offset
+        const uint32_t ax[2] = {cell[0] << 1, (cell[0] + 1u) << 1};
+        const uint32_t ay[2] = {(cell[1] * my) << 1, ((cell[1] + 1u) * my) << 1};
+        const uint32_t az[2] = {(cell[2] * mz) << 1, ((cell[2] + 1u) * mz) << 1};
+        __half acc = __float2half_rn(0.0f);
+#pragma unroll
+        for (uint32_t k = 0; k < 8; ++k) {
+            const float wgt = __fmul_rn(wxy[k & 3], (k & 4) ? fr[2] : g2);
+            const uint32_t off = (HASHED ? (ax[k & 1] ^ ay[(k >> 1) & 1] ^ az[k >> 2]) : (ax[k & 1] + ay[(k >> 1) & 1] + az[k >> 2])) & bmask;
+            const float wh = __half2float(__float2half_rn(wgt));
+            unsigned short tv;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(tv) : "r"(table_smem + off));
+            acc = __float2half_rn(__fmaf_rn(wh, __half2float(__ushort_as_half(tv)), __half2float(acc)));
+        }
+        out[p] = acc;
+    }
+}
+
 // planar: per level [feature 0 table | feature 1 table], each size[l] fp16 (the level starts at 2*offset[l] halves)
 __global__ void __launch_bounds__(ENC_THREADS, 1)
 k_encode_forward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, const __half* __restrict__ planar,
@@ -130,38 +165,8 @@ k_encode_forward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, co
         const bool pow2 = (size & (size - 1)) == 0;
         __half* out = enc_soa + (size_t)job * n_points;
         if (pow2) {
-            // index arithmetic directly in byte offsets: ((a ^ b ^ c) & (size-1)) * 2 == (2a ^ 2b ^ 2c) & (2*size-2)
-            const uint32_t bmask = 2u * size - 2u;
-            for (uint32_t p = p0 + tid; p < p1; p += ENC_THREADS) {
-                const float u0 = __ldg(pts + (size_t)p * 3), u1 = __ldg(pts + (size_t)p * 3 + 1), u2 = __ldg(pts + (size_t)p * 3 + 2);
-                float fr[3]; uint32_t cell[3];
-                mon_pos_fract(u0, scale, fr[0], cell[0]);
-                mon_pos_fract(u1, scale, fr[1], cell[1]);
-                mon_pos_fract(u2, scale, fr[2], cell[2]);
-                const float g0 = __fsub_rn(1.0f, fr[0]), g1 = __fsub_rn(1.0f, fr[1]), g2 = __fsub_rn(1.0f, fr[2]);
-                // (1*fx)*fy shared by the two z corners; same multiplication order as the reference
-                const float wxy[4] = {__fmul_rn(g0, g1), __fmul_rn(fr[0], g1), __fmul_rn(g0, fr[1]), __fmul_rn(fr[0], fr[1])};
-                uint32_t ax[2], ay[2], az[2];   // per-axis contributions to the byte offset
-                if (hashed) {
-                    ax[0] = cell[0] << 1; ax[1] = (cell[0] + 1u) << 1;
-                    ay[0] = (cell[1] * 2654435761u) << 1; ay[1] = ((cell[1] + 1u) * 2654435761u) << 1;
-                    az[0] = (cell[2] * 805459861u) << 1; az[1] = ((cell[2] + 1u) * 805459861u) << 1;
-                } else {
-                    ax[0] = cell[0] << 1; ax[1] = (cell[0] + 1u) << 1;
-                    ay[0] = (cell[1] * res) << 1; ay[1] = ((cell[1] + 1u) * res) << 1;
-                    az[0] = (cell[2] * res * res) << 1; az[1] = ((cell[2] + 1u) * res * res) << 1;
-                }
-                __half acc = __float2half_rn(0.0f);
-#pragma unroll
-                for (uint32_t k = 0; k < 8; ++k) {
-                    const float wgt = __fmul_rn(wxy[k & 3], (k & 4) ? fr[2] : g2);
-                    const uint32_t off = (hashed ? (ax[k & 1] ^ ay[(k >> 1) & 1] ^ az[k >> 2]) : (ax[k & 1] + ay[(k >> 1) & 1] + az[k >> 2])) & bmask;
-                    const float wh = __half2float(__float2half_rn(wgt));
-                    const __half tv = *reinterpret_cast<const __half*>(enc_smem + off);
-                    acc = __float2half_rn(__fmaf_rn(wh, __half2float(tv), __half2float(acc)));
-                }
-                out[p] = acc;
-            }
+            if (hashed) enc_points_pow2<true>(pts, out, p0 + tid, p1, scale, size, res, tc05::smem_u32(enc_smem));
+            else enc_points_pow2<false>(pts, out, p0 + tid, p1, scale, size, res, tc05::smem_u32(enc_smem));
         } else {
             for (uint32_t p = p0 + tid; p < p1; p += ENC_THREADS) {
                 const float u0 = __ldg(pts + (size_t)p * 3), u1 = __ldg(pts + (size_t)p * 3 + 1), u2 = __ldg(pts + (size_t)p * 3 + 2);

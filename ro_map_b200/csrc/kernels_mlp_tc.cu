@@ -41,29 +41,28 @@ using namespace tc05;
 #define TC_COL_G1 64   // 16: [hid|dhid]^T . dout                 (persistent)
 #define TC_COL_G2 96   // 32: [hid|dhid]^T . enc                  (persistent)
 #define TC_COL_H2 128  // 64: [H2|dH2]^T . H1, n_hidden_layers == 2 (persistent)
-// 128 columns (NH == 1) let three CTAs share an SM's 512 TMEM columns; NH == 2 needs 192 -> 256
+// 128 columns (NH == 1) let four CTAs share an SM's 512 TMEM columns; NH == 2 needs 192 -> 256
 #define TC_TMEM_COLS(NH) ((NH) == 1 ? 128u : 256u)
-#define TC_CTAS_PER_SM(NH) ((NH) == 1 ? 3 : 2)
+#define TC_CTAS_PER_SM(NH) ((NH) == 1 ? 4 : 2)
 
-// shared memory map (bytes from a 1024-aligned base)
+// shared memory map (bytes from a 1024-aligned base).  Every weight matrix is stored ONCE, in the K-major layout of
+// its forward GEMM; the dgrad GEMMs read the same bytes through MN-major descriptors (tc05.cuh), like the
+// weight-gradient GEMMs read the activation tiles.
 #define SM_ENC 0         //  8192  [128][32]  SW64
 #define SM_HID 8192      // 16384  [128][64]  SW128   (hid | dhid must be adjacent: MN-major LBO = 16384)
 #define SM_DHID 24576    // 16384
 #define SM_DOUT 40960    //  4096  [128][16]  core layout (2 chunks per row)
-#define SM_WIN 45056     //  4096  B of MMA1: [64][32] SW64
-#define SM_WINT 49152    //  4096  B of MMA4: [32][64] SW128
-#define SM_WOUT 53248    //  2048  B of MMA2: [16][64] SW128
-#define SM_WOUTT 55296   //  2048  B of MMA3: [64][16] core layout
-#define SM_BAR 57344     //  mbarrier (8) + tmem base (4)
-// n_hidden_layers == 2 only: the first hidden layer's tiles and the 64x64 weight in both orientations
-#define SM_H1 58368      // 16384  [128][64]  SW128   (H1 | dH1 adjacent, like hid | dhid)
-#define SM_DH1 74752     // 16384
-#define SM_WH 91136      //  8192  B of the hidden GEMM: W_h [64][64] SW128
-#define SM_WHT 99328     //  8192  B of its dgrad: W_h^T [64][64] SW128
-#define SM_TOTAL 107520
+#define SM_WIN 45056     //  4096  W_in  [64][32] SW64 : B of the input GEMM (K-major) and of dL/denc (MN-major)
+#define SM_WOUT 49152    //  2048  W_out [16][64] SW128: B of the output GEMM (K-major) and of dL/dhidden (MN-major)
+#define SM_BAR 51200     //  mbarrier (8) + tmem base (4)
+// n_hidden_layers == 2 only: the first hidden layer's tiles and the 64x64 weight
+#define SM_H1 52224      // 16384  [128][64]  SW128   (H1 | dH1 adjacent, like hid | dhid)
+#define SM_DH1 68608     // 16384
+#define SM_WH 84992      //  8192  W_h [64][64] SW128: B of the hidden GEMM (K-major) and of its dgrad (MN-major)
+#define SM_TOTAL 93184
 // dynamic request (incl. 1 KB alignment slack), sized so that exactly TC_CTAS_PER_SM CTAs fit in the 227 KB of an SM:
-// NH == 1: 3 x 60 KB (a 4th would also exceed the TMEM), NH == 2: 2 x 108 KB
-#define TC_SMEM_BYTES(NH) ((NH) == 1 ? 60 * 1024 : 108 * 1024)
+// NH == 1: 4 x 54 KB = all 512 TMEM columns, NH == 2: 2 x 94 KB
+#define TC_SMEM_BYTES(NH) ((NH) == 1 ? 54 * 1024 : 94 * 1024)
 
 static constexpr uint32_t IDESC_64_KK = make_idesc(128, 64, 0, 0);
 static constexpr uint32_t IDESC_16_KK = make_idesc(128, 16, 0, 0);
@@ -71,6 +70,8 @@ static constexpr uint32_t IDESC_32_KK = make_idesc(128, 32, 0, 0);
 static constexpr uint32_t IDESC_16_MM = make_idesc(128, 16, 1, 1);
 static constexpr uint32_t IDESC_32_MM = make_idesc(128, 32, 1, 1);
 static constexpr uint32_t IDESC_64_MM = make_idesc(128, 64, 1, 1);
+static constexpr uint32_t IDESC_64_KM = make_idesc(128, 64, 0, 1);   // A K-major, B MN-major (dgrad through the forward weight tile)
+static constexpr uint32_t IDESC_32_KM = make_idesc(128, 32, 0, 1);
 
 struct TcCtx {
     unsigned char* sm;     // 1024-aligned shared base
@@ -115,10 +116,6 @@ __device__ __forceinline__ void tc_load_weights(const TcCtx& c, const __half* __
             const uint32_t n = i >> 3, ch = i & 7;
             *reinterpret_cast<uint4*>(c.sm + SM_WH + sw128_off(n, ch)) = *reinterpret_cast<const uint4*>(Wh + n * 64 + ch * 8);
         }
-        for (uint32_t i = c.tid; i < 64 * 64; i += TC_THREADS) {      // W_h^T: row n = input i, column j = neuron
-            const uint32_t n = i >> 6, j = i & 63;
-            *reinterpret_cast<__half*>(c.sm + SM_WHT + sw128_off(n, j >> 3) + (j & 7) * 2) = Wh[j * 64 + n];
-        }
     }
     for (uint32_t i = c.tid; i < 64 * 4; i += TC_THREADS) {           // W_in rows (N = 64), 4 chunks of 8 (K = 32)
         const uint32_t n = i >> 2, ch = i & 3;
@@ -127,14 +124,6 @@ __device__ __forceinline__ void tc_load_weights(const TcCtx& c, const __half* __
     for (uint32_t i = c.tid; i < 16 * 8; i += TC_THREADS) {           // W_out rows (N = 16), 8 chunks (K = 64)
         const uint32_t n = i >> 3, ch = i & 7;
         *reinterpret_cast<uint4*>(c.sm + SM_WOUT + sw128_off(n, ch)) = *reinterpret_cast<const uint4*>(Wout + n * 64 + ch * 8);
-    }
-    for (uint32_t i = c.tid; i < 32 * 64; i += TC_THREADS) {          // W_in^T: row n = input k, column j = neuron
-        const uint32_t n = i >> 6, j = i & 63;
-        *reinterpret_cast<__half*>(c.sm + SM_WINT + sw128_off(n, j >> 3) + (j & 7) * 2) = Win[j * 32 + n];
-    }
-    for (uint32_t i = c.tid; i < 64 * 16; i += TC_THREADS) {          // W_out^T: row n = neuron j, column o = output
-        const uint32_t n = i >> 4, o = i & 15;
-        *reinterpret_cast<__half*>(c.sm + SM_WOUTT + core_off(n, o >> 3, 2) + (o & 7) * 2) = Wout[o * 64 + n];
     }
 }
 
@@ -356,8 +345,9 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
         TC_PUBLISH_AND_SYNC();
         if (c.tid == 0) {
             fence_after_sync();
+            // B[k = output o][n = neuron j] = W_out[o][j]: the forward tile (16 rows of 128 B) read MN-major
             mma_f16_ss(c.tmem + TC_COL_D, make_desc(c.sm_addr + SM_DOUT, 128, 256, SWZ_NONE),
-                       make_desc(c.sm_addr + SM_WOUTT, 128, 256, SWZ_NONE), IDESC_64_KK, 0);
+                       make_desc(c.sm_addr + SM_WOUT, 16, 1024, SWZ_128B), IDESC_64_KM, 0);
             commit(c.bar);
         }
         TC_WAIT(c);
@@ -366,7 +356,11 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
             TC_PUBLISH_AND_SYNC();
             if (c.tid == 0) {
                 fence_after_sync();
-                tc_mma_sw(c, TC_COL_D, SM_DHID, SM_WHT, true, 4, IDESC_64_KK);
+                // B[k = neuron j][n = input i] = W_h[j][i]: the forward tile read MN-major, 16 rows (2 KB) per MMA
+#pragma unroll
+                for (uint32_t k = 0; k < 4; ++k)
+                    mma_f16_ss(c.tmem + TC_COL_D, make_desc(c.sm_addr + SM_DHID + k * 32, 16, 1024, SWZ_128B),
+                               make_desc(c.sm_addr + SM_WH + k * 2048, 16, 1024, SWZ_128B), IDESC_64_KM, k);
                 commit(c.bar);
             }
             TC_WAIT(c);
@@ -376,7 +370,11 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
         TC_PUBLISH_AND_SYNC();
         if (c.tid == 0) {
             fence_after_sync();
-            tc_mma_sw(c, TC_COL_E, NH == 2 ? SM_DH1 : SM_DHID, SM_WINT, true, 4, IDESC_32_KK);
+            // B[k = neuron j][n = input k] = W_in[j][k]: the forward tile (64 rows of 64 B, SW64) read MN-major
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k)
+                mma_f16_ss(c.tmem + TC_COL_E, make_desc(c.sm_addr + (NH == 2 ? SM_DH1 : SM_DHID) + k * 32, 16, 1024, SWZ_128B),
+                           make_desc(c.sm_addr + SM_WIN + k * 1024, 16, 512, SWZ_64B), IDESC_32_KM, k);
             const uint32_t acc0 = tiles_done ? 1u : 0u;
 #pragma unroll
             for (uint32_t kk = 0; kk < 8; ++kk) {   // 16 points per MMA
@@ -434,14 +432,15 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
             tmem_wait_ld();
             const uint32_t j = c.tid - 64;
 #pragma unroll
-            for (uint32_t k = 0; k < 32; ++k) partial[j * 32 + k] = v[k];
+            for (uint32_t k = 0; k < 32; k += 4) *reinterpret_cast<float4*>(partial + j * 32 + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
             if (NH == 2) {   // G3 rows 64..127: (dH2^T . H1)[j][i] = dW_h[j][i]
 #pragma unroll
                 for (uint32_t half_i = 0; half_i < 2; ++half_i) {
                     tmem_ld32(c.tmem + ((c.warp * 32u) << 16) + TC_COL_H2 + half_i * 32, v);
                     tmem_wait_ld();
 #pragma unroll
-                    for (uint32_t k = 0; k < 32; ++k) partial[64 * 32 + j * 64 + half_i * 32 + k] = v[k];
+                    for (uint32_t k = 0; k < 32; k += 4)
+                        *reinterpret_cast<float4*>(partial + 64 * 32 + j * 64 + half_i * 32 + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
                 }
             }
         }
@@ -560,7 +559,7 @@ cudaError_t mon_launch_mlp_train_tc(const MonBatch& b, const MonLossCfg& lc, uin
 
 cudaError_t mon_launch_mlp_infer_tc(uint32_t n_points, uint32_t n_hidden, const __half* params, const __half* enc, float* out4, cudaStream_t st) {
     uint32_t ctas = (n_points + 127) / 128;
-    if (ctas > 444) ctas = 444;
+    if (ctas > 592) ctas = 592;
     if (ctas == 0) ctas = 1;
     if (n_hidden == 1) {
         static cudaError_t prep = tc_prepare(k_mlp_infer_tc<1>, TC_SMEM_BYTES(1));
@@ -580,7 +579,7 @@ cudaError_t mon_launch_mlp_render_tc(uint32_t n_rays, uint32_t S2, uint32_t n_hi
                                      uint32_t seed, uint32_t iter, const __half* params, const __half* enc, float bgc,
                                      float* rgb, float* depth, float* mask, cudaStream_t st) {
     uint32_t ctas = (n_rays + 3) / 4;
-    if (ctas > 444) ctas = 444;
+    if (ctas > 592) ctas = 592;
     if (ctas == 0) ctas = 1;
     if (n_hidden == 1) {
         static cudaError_t prep = tc_prepare(k_mlp_render_tc<1>, TC_SMEM_BYTES(1));

@@ -86,7 +86,7 @@ __device__ __forceinline__ uint32_t level_of_entry(const MonGrid& g, uint32_t e)
     return l;
 }
 
-__global__ void __launch_bounds__(OPT_THREADS)
+__global__ void __launch_bounds__(OPT_THREADS, 6)
 k_optimizer_sweep(MonOpt o, MonCtrl* __restrict__ ctrl, float* __restrict__ pf, __half* __restrict__ ph,
                   __half* __restrict__ gh, const float* __restrict__ mlp_partials, float* __restrict__ m,
                   float* __restrict__ v, uint32_t* __restrict__ ps, __half* __restrict__ ema,
@@ -114,6 +114,7 @@ k_optimizer_sweep(MonOpt o, MonCtrl* __restrict__ ctrl, float* __restrict__ pf, 
     uint32_t i4;
     float g[4];
     uint2* gw;
+    uint2 wraw, eraw;   // fp16 weights and EMA of the 4 parameters: always needed, fetched together with the gradient
     if (is_mlp) {
         const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         i4 = (blockIdx.x * (OPT_THREADS / 32) + warp) * OPT_PER_THREAD;
@@ -133,6 +134,8 @@ k_optimizer_sweep(MonOpt o, MonCtrl* __restrict__ ctrl, float* __restrict__ pf, 
         }
         if (lane != 0) return;
         gw = reinterpret_cast<uint2*>(gh + i4);
+        wraw = *reinterpret_cast<const uint2*>(ph + i4);
+        eraw = *reinterpret_cast<const uint2*>(ema + i4);
         // the reference stores weight gradients in fp16 (loss-scaled); keep that rounding point
         const __half2 a = __floats2half2_rn(s4.x, s4.y), b = __floats2half2_rn(s4.z, s4.w);
         *gw = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));   // kept for inspection
@@ -142,6 +145,8 @@ k_optimizer_sweep(MonOpt o, MonCtrl* __restrict__ ctrl, float* __restrict__ pf, 
         if (i4 >= o.n_params) return;
         gw = reinterpret_cast<uint2*>(gh + i4);
         const uint2 raw = *gw;
+        wraw = *reinterpret_cast<const uint2*>(ph + i4);
+        eraw = *reinterpret_cast<const uint2*>(ema + i4);
         const __half2 a = *reinterpret_cast<const __half2*>(&raw.x), b = *reinterpret_cast<const __half2*>(&raw.y);
         g[0] = __low2float(a); g[1] = __high2float(a); g[2] = __low2float(b); g[3] = __high2float(b);
         if ((raw.x | raw.y) & 0x7fff7fffu) *gw = make_uint2(0u, 0u);   // consumed: the next scatter starts from zero
@@ -156,7 +161,6 @@ k_optimizer_sweep(MonOpt o, MonCtrl* __restrict__ ctrl, float* __restrict__ pf, 
     }
 
     // ---- fp16 weights of the 4 parameters (needed by the EMA in any case)
-    uint2 wraw = *reinterpret_cast<const uint2*>(ph + i4);
     __half wh[4] = {__ushort_as_half((unsigned short)(wraw.x & 0xffffu)), __ushort_as_half((unsigned short)(wraw.x >> 16)),
                     __ushort_as_half((unsigned short)(wraw.y & 0xffffu)), __ushort_as_half((unsigned short)(wraw.y >> 16))};
     if (any) {
@@ -190,7 +194,6 @@ k_optimizer_sweep(MonOpt o, MonCtrl* __restrict__ ctrl, float* __restrict__ pf, 
     }
 
     // ---- EMA over all params with the global step (ema.h:62-76)
-    const uint2 eraw = *reinterpret_cast<const uint2*>(ema + i4);
     const __half2 e01 = *reinterpret_cast<const __half2*>(&eraw.x), e23 = *reinterpret_cast<const __half2*>(&eraw.y);
     const float ev[4] = {__low2float(e01), __high2float(e01), __low2float(e23), __high2float(e23)};
     float nf[4];

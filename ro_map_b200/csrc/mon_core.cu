@@ -86,6 +86,12 @@ struct HostPcg32 {
 
 uint32_t next_multiple(uint32_t v, uint32_t d) { return ((v + d - 1) / d) * d; }
 
+bool host_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 // per-level table geometry, GridEncodingTemplated ctor (TCNN encodings/grid.h:964-997) and
 // grid_scale/grid_resolution (:195-204)
 bool make_grid(const mon_config& c, MonGrid& g, std::string& why) {
@@ -153,6 +159,7 @@ struct mon_dataset {
     std::vector<MonFrame> h_frames;
     cudaStream_t stream = nullptr;
     uint8_t* staging = nullptr;  // pinned: rgb | instance | depth
+    cudaEvent_t ev_uploaded = nullptr;   // recorded after the last frame upload; training streams wait on it
     std::mutex mu;
 };
 
@@ -337,7 +344,9 @@ int mon_dataset_create(int gpu, float fx, float fy, float cx, float cy, int H, i
     if ((e = cudaStreamCreateWithFlags(&ds->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaMalloc(&ds->d_frames, sizeof(MonFrame) * max_frames)) != cudaSuccess ||
         (e = cudaMemset(ds->d_frames, 0, sizeof(MonFrame) * max_frames)) != cudaSuccess ||
-        (e = cudaMallocHost(&ds->staging, px * 3 + px + px * 4)) != cudaSuccess) {
+        (e = cudaMallocHost(&ds->staging, px * 3 + px + px * 4)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ds->ev_uploaded, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventRecord(ds->ev_uploaded, ds->stream)) != cudaSuccess) {
         mon_dataset_destroy(ds);
         return fail(MON_ERR_CUDA, "dataset allocation: %s", cudaGetErrorString(e));
     }
@@ -360,25 +369,43 @@ int mon_dataset_add_frame(mon_dataset* ds, uint32_t frame_id, const uint8_t* rgb
         CK(cudaMalloc(&p, px)); f.instance = p;
         if (ds->use_depth) { float* d = nullptr; CK(cudaMalloc(&d, px * 4)); f.depth = d; }
     }
-    uint8_t* st_rgb = ds->staging;
-    uint8_t* st_inst = ds->staging + px * 3;
-    float* st_depth = reinterpret_cast<float*>(ds->staging + px * 4);
-    if (is_bgr) {  // cv::cvtColor(BGR2RGB) of the reference (nerf_data.cu:286)
-        for (size_t i = 0; i < px; ++i) { st_rgb[3 * i] = rgb[3 * i + 2]; st_rgb[3 * i + 1] = rgb[3 * i + 1]; st_rgb[3 * i + 2] = rgb[3 * i]; }
-    } else {
-        memcpy(st_rgb, rgb, px * 3);
-    }
-    memcpy(st_inst, instance, px);
-    CK(cudaMemcpyAsync(const_cast<uint8_t*>(f.rgb), st_rgb, px * 3, cudaMemcpyHostToDevice, ds->stream));
-    CK(cudaMemcpyAsync(const_cast<uint8_t*>(f.instance), st_inst, px, cudaMemcpyHostToDevice, ds->stream));
-    if (ds->use_depth) {
-        memcpy(st_depth, depth, px * 4);
-        CK(cudaMemcpyAsync(const_cast<float*>(f.depth), st_depth, px * 4, cudaMemcpyHostToDevice, ds->stream));
-    }
     memcpy(f.pose, pose, sizeof(float) * 16);
-    CK(cudaMemcpyAsync(ds->d_frames + frame_id, &f, sizeof(MonFrame), cudaMemcpyHostToDevice, ds->stream));
-    CK(cudaStreamSynchronize(ds->stream));
+    if (!is_bgr && host_pinned(rgb) && host_pinned(instance) && (!ds->use_depth || host_pinned(depth))) {
+        // page-locked caller buffers: DMA straight out of them, no staging copy and no host synchronisation.  The
+        // buffers must stay valid until mon_dataset_sync() or the next blocking call on an object of this dataset.
+        CK(cudaMemcpyAsync(const_cast<uint8_t*>(f.rgb), rgb, px * 3, cudaMemcpyHostToDevice, ds->stream));
+        CK(cudaMemcpyAsync(const_cast<uint8_t*>(f.instance), instance, px, cudaMemcpyHostToDevice, ds->stream));
+        if (ds->use_depth) CK(cudaMemcpyAsync(const_cast<float*>(f.depth), depth, px * 4, cudaMemcpyHostToDevice, ds->stream));
+        CK(cudaMemcpyAsync(ds->d_frames + frame_id, &f, sizeof(MonFrame), cudaMemcpyHostToDevice, ds->stream));   // pageable source: staged by the driver before returning
+        CK(cudaEventRecord(ds->ev_uploaded, ds->stream));
+    } else {
+        uint8_t* st_rgb = ds->staging;
+        uint8_t* st_inst = ds->staging + px * 3;
+        float* st_depth = reinterpret_cast<float*>(ds->staging + px * 4);
+        if (is_bgr) {  // cv::cvtColor(BGR2RGB) of the reference (nerf_data.cu:286)
+            for (size_t i = 0; i < px; ++i) { st_rgb[3 * i] = rgb[3 * i + 2]; st_rgb[3 * i + 1] = rgb[3 * i + 1]; st_rgb[3 * i + 2] = rgb[3 * i]; }
+        } else {
+            memcpy(st_rgb, rgb, px * 3);
+        }
+        memcpy(st_inst, instance, px);
+        CK(cudaMemcpyAsync(const_cast<uint8_t*>(f.rgb), st_rgb, px * 3, cudaMemcpyHostToDevice, ds->stream));
+        CK(cudaMemcpyAsync(const_cast<uint8_t*>(f.instance), st_inst, px, cudaMemcpyHostToDevice, ds->stream));
+        if (ds->use_depth) {
+            memcpy(st_depth, depth, px * 4);
+            CK(cudaMemcpyAsync(const_cast<float*>(f.depth), st_depth, px * 4, cudaMemcpyHostToDevice, ds->stream));
+        }
+        CK(cudaMemcpyAsync(ds->d_frames + frame_id, &f, sizeof(MonFrame), cudaMemcpyHostToDevice, ds->stream));
+        CK(cudaEventRecord(ds->ev_uploaded, ds->stream));
+        CK(cudaStreamSynchronize(ds->stream));   // the staging buffer is reused by the next frame
+    }
     ds->n_frames = std::max(ds->n_frames, frame_id + 1);
+    return MON_OK;
+}
+
+int mon_dataset_sync(mon_dataset* ds) {
+    if (!ds) return fail(MON_ERR_ARG, "ds is NULL");
+    CK(cudaSetDevice(ds->gpu));
+    CK(cudaStreamSynchronize(ds->stream));
     return MON_OK;
 }
 
@@ -445,6 +472,7 @@ int mon_dataset_destroy(mon_dataset* ds) {
     }
     if (ds->d_frames) cudaFree(ds->d_frames);
     if (ds->staging) cudaFreeHost(ds->staging);
+    if (ds->ev_uploaded) cudaEventDestroy(ds->ev_uploaded);
     if (ds->stream) cudaStreamDestroy(ds->stream);
     delete ds;
     return MON_OK;
@@ -601,9 +629,9 @@ int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uin
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, ds->gpu));
     o->sm_count = prop.multiProcessorCount;
-    // fused MLP kernel: persistent grid of all co-resident CTAs (3 per SM with one hidden layer, 2 with two: TMEM
+    // fused MLP kernel: persistent grid of all co-resident CTAs (4 per SM with one hidden layer, 2 with two: TMEM
     // columns and shared memory, kernels_mlp_tc.cu), never more CTAs than 4-ray tiles
-    o->n_ctas = std::min<uint32_t>((uint32_t)o->sm_count * (cfg->n_hidden_layers == 1 ? 3u : 2u), (o->R + 3) / 4);
+    o->n_ctas = std::min<uint32_t>((uint32_t)o->sm_count * (cfg->n_hidden_layers == 1 ? 4u : 2u), (o->R + 3) / 4);
     if (o->n_ctas > MON_MAX_MLP_CTAS) o->n_ctas = MON_MAX_MLP_CTAS;
     o->opt.lr = cfg->learning_rate; o->opt.beta1 = cfg->beta1; o->opt.beta2 = cfg->beta2; o->opt.eps = cfg->epsilon;
     o->opt.l2_reg = cfg->l2_reg; o->opt.ema_decay = cfg->ema_decay; o->opt.loss_scale = cfg->loss_scale;
@@ -762,6 +790,7 @@ int mon_object_train_async(mon_object* o, uint32_t iters) {
     CK(cudaSetDevice(o->ds->gpu));
     if (!o->graph1) { int rc = capture_graph(o, 1, &o->graph1); if (rc != MON_OK) return rc; }
     if (iters >= MON_GRAPH_CHUNK && !o->graphN) { int rc = capture_graph(o, MON_GRAPH_CHUNK, &o->graphN); if (rc != MON_OK) return rc; }
+    CK(cudaStreamWaitEvent(o->stream, o->ds->ev_uploaded, 0));   // frames uploaded asynchronously from pinned buffers
     CK(cudaEventRecord(o->ev0, o->stream));
     uint32_t left = iters;
     while (left >= MON_GRAPH_CHUNK) { CK(cudaGraphLaunch(o->graphN, o->stream)); left -= MON_GRAPH_CHUNK; }

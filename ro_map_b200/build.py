@@ -79,6 +79,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 HOST = PKG / "host"
 HOST_LIB = PKG / "libMON.so"
 HOST_BIN = PKG / "offline_nerf"
+REPLAY_BIN = PKG / "online_replay"
 
 
 def build_host(force: bool = False) -> Path:
@@ -95,12 +96,12 @@ def build_host(force: bool = False) -> Path:
         proc = subprocess.run(cmd, capture_output=True, text=True)
         if proc.returncode != 0:
             raise RuntimeError("libMON.so build failed:\n" + proc.stdout + proc.stderr)
-    main_src = HOST / "offline_nerf.cpp"
-    if force or not HOST_BIN.exists() or HOST_BIN.stat().st_mtime < max(newest, main_src.stat().st_mtime):
-        cmd = [cxx, *common, "-o", str(HOST_BIN), str(main_src), "-L", str(PKG), "-lMON", "-lmon_b200", "-lz", "-Wl,-rpath,$ORIGIN"]
-        proc = subprocess.run(cmd, capture_output=True, text=True)
-        if proc.returncode != 0:
-            raise RuntimeError("offline_nerf build failed:\n" + proc.stdout + proc.stderr)
+    for main_src, binary in ((HOST / "offline_nerf.cpp", HOST_BIN), (HOST / "online_replay.cpp", REPLAY_BIN)):
+        if force or not binary.exists() or binary.stat().st_mtime < max(newest, main_src.stat().st_mtime):
+            cmd = [cxx, *common, "-o", str(binary), str(main_src), "-L", str(PKG), "-lMON", "-lmon_b200", "-lz", "-Wl,-rpath,$ORIGIN"]
+            proc = subprocess.run(cmd, capture_output=True, text=True)
+            if proc.returncode != 0:
+                raise RuntimeError(f"{binary.name} build failed:\n" + proc.stdout + proc.stderr)
     return HOST_LIB
 
 

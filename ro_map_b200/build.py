@@ -25,6 +25,7 @@ NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "--expt-relaxed-constexpr", "-Xc
               "-Xptxas", "-v"]
 if (CSRC / "kernels_mlp_tc.cu").exists():
     NVCC_FLAGS.append("-DMON_HAVE_TC")
+NVCC_FLAGS += os.environ.get("MON_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _nvcc() -> str:

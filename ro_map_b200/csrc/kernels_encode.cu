@@ -10,8 +10,8 @@
 // memory with TMA bulk copies (cp.async.bulk -> mbarrier), and the CTA then streams its share of the points past
 // it: 8 two-byte gathers per point hit the 32 shared-memory banks (~3.5-way conflicts for random indices) instead of
 // 8 L1 wavefronts.  Work is split evenly over the flattened [job][point] space, so each of the 148 CTAs loads at
-// most two table slices.  Output is feature-major ("SoA", like tcnn's own encoding output): enc[2*level+f][point],
-// written with coalesced 2-byte stores.
+// most two table slices.  Output is level-major: enc[level][point][feature] (the two features of a level form one
+// 32-bit word per point, which is what the fused MLP kernel stages), written with 2-byte stores at 4-byte stride.
 // Arithmetic is the reference's: weights in fp32, rounded to fp16, one fp32 FMA per corner whose result is rounded
 // back to fp16 after every corner (grid.h:334 via common.h:539-559) — bit-exact against tiny-cuda-nn, including
 // the 32-bit stride wrap that turns level 12 into a table indexed by x alone (mon_core.cu make_grid).
@@ -125,7 +125,7 @@ __device__ __forceinline__ void enc_points_pow2(const float* __restrict__ pts, _
             asm volatile("ld.shared.u16 %0, [%1];" : "=h"(tv) : "r"(table_smem + off));
             acc = __float2half_rn(__fmaf_rn(wh, __half2float(__ushort_as_half(tv)), __half2float(acc)));
         }
-        out[p] = acc;
+        out[(size_t)p * 2] = acc;
     }
 }
 
@@ -163,7 +163,7 @@ k_encode_forward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, co
         const bool hashed = g.hashed[l] != 0;
         const uint32_t res = g.res[l];
         const bool pow2 = (size & (size - 1)) == 0;
-        __half* out = enc_soa + (size_t)job * n_points;
+        __half* out = enc_soa + (size_t)l * n_points * 2 + f;   // level-major pairs: enc[level][point][feature]
         if (pow2) {
             if (hashed) enc_points_pow2<true>(pts, out, p0 + tid, p1, scale, size, res, tc05::smem_u32(enc_smem));
             else enc_points_pow2<false>(pts, out, p0 + tid, p1, scale, size, res, tc05::smem_u32(enc_smem));
@@ -185,7 +185,7 @@ k_encode_forward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, co
                     const float wh = __half2float(__float2half_rn(wgt));
                     acc = __float2half_rn(__fmaf_rn(wh, __half2float(table[idx]), __half2float(acc)));
                 }
-                out[p] = acc;
+                out[(size_t)p * 2] = acc;
             }
         }
         w += p1 - p0;

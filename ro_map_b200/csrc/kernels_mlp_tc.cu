@@ -6,7 +6,7 @@
 // warp-parallel volume renderer (render_math.cuh) wants, so the network output never leaves the SM between the
 // last GEMM and compositing.  Per tile, for the training kernel:
 //
-//   enc tile (global, feature-major fp16) --> smem [128 x 32]  K-major SWIZZLE_64B
+//   enc tile (global, level-major fp16 pairs) --> smem [128 x 32]  K-major SWIZZLE_64B
 //   MMA1  D[128x64]   = enc  . W_in^T            (K = 32)      epilogue: ReLU, fp16  --> hid  smem SW128
 //   MMA2  O[128x16]   = hid  . W_out^T           (K = 64)      epilogue: sigmoid/exp, warp-scan compositing,
 //                                                              loss, dL/dout fp16    --> dout smem (core layout)
@@ -31,6 +31,21 @@
 #include "tc05.cuh"
 
 using namespace tc05;
+
+// optional phase-timing instrumentation (build with MON_EXTRA_NVCC_FLAGS=-DMON_TC_STAMPS; tools/tc_phase_times.py)
+#ifdef MON_TC_STAMPS
+__device__ unsigned long long mon_tc_stamps[64];
+#define TC_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) mon_tc_stamps[(i)] = clock64(); } while (0)
+extern "C" int mon_debug_tc_stamps(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, mon_tc_stamps, sizeof(mon_tc_stamps)); }
+__device__ unsigned long long mon_tc_cta[1024 * 3];   // per CTA: globaltimer at entry, at exit, SM id
+extern "C" int mon_debug_tc_ctas(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, mon_tc_cta, sizeof(mon_tc_cta)); }
+__device__ __forceinline__ unsigned long long tc_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned tc_smid() { unsigned s; asm volatile("mov.u32 %0, %smid;" : "=r"(s)); return s; }
+#define TC_CTA_MARK(slot) do { if (threadIdx.x == 0 && blockIdx.x < 1024) { mon_tc_cta[blockIdx.x * 3 + (slot)] = tc_gtime(); mon_tc_cta[blockIdx.x * 3 + 2] = tc_smid(); } } while (0)
+#else
+#define TC_STAMP(i) do { } while (0)
+#define TC_CTA_MARK(slot) do { } while (0)
+#endif
 
 #define TC_THREADS 128
 // TMEM column map.  The per-tile accumulators are never live at the same time (each is drained by its epilogue
@@ -128,17 +143,14 @@ __device__ __forceinline__ void tc_load_weights(const TcCtx& c, const __half* __
 }
 
 // Staging of one row of the 128 x 32 fp16 encoding tile in two halves, so that the global loads of the NEXT tile can
-// be in flight while the tensor core and the epilogues work on the current one.  The encoding is feature-major
-// (enc_soa[feature][point], n_total points per feature row): 32 two-byte loads, coalesced across the warp
-// (consecutive threads = consecutive points).  Invalid rows are zero-filled.
-__device__ __forceinline__ void tc_load_enc(uint32_t packed[16], const __half* __restrict__ enc_soa, size_t n_total, size_t pt, bool valid) {
-    const unsigned short* src = reinterpret_cast<const unsigned short*>(enc_soa) + pt;
+// be in flight while the tensor core and the epilogues work on the current one.  The encoding is level-major:
+// enc[level][point] holds the level's two features as one 32-bit word, so a row is 16 word loads, coalesced across the
+// warp (consecutive threads = consecutive points), and nothing depends on a loaded value until the row is stored.
+// Invalid rows are zero-filled.
+__device__ __forceinline__ void tc_load_enc(uint32_t packed[16], const __half* __restrict__ enc_lm, size_t n_total, size_t pt, bool valid) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(enc_lm) + pt;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const uint32_t lo = valid ? (uint32_t)__ldg(src + (size_t)(2 * k) * n_total) : 0u;
-        const uint32_t hi = valid ? (uint32_t)__ldg(src + (size_t)(2 * k + 1) * n_total) : 0u;
-        packed[k] = lo | (hi << 16);
-    }
+    for (int k = 0; k < 16; ++k) packed[k] = valid ? __ldg(src + (size_t)k * n_total) : 0u;
 }
 __device__ __forceinline__ void tc_store_enc(const TcCtx& c, const uint32_t packed[16]) {
 #pragma unroll
@@ -193,11 +205,12 @@ __device__ __forceinline__ void tc_issue_layer_out(const TcCtx& c) {
     commit(c.bar);
 }
 
-// epilogue of a hidden GEMM: ReLU -> fp16 -> activation tile at tile_off; returns the bitmask of positive units of this row
-__device__ __forceinline__ uint64_t tc_epilogue_hidden(const TcCtx& c, uint32_t tile_off) {
+// epilogue of a hidden GEMM: fp32 accumulator row -> fp16 -> packed ReLU -> activation tile at tile_off
+// (rounding to fp16 and clamping at zero commute, so this equals the reference's relu-then-store)
+__device__ __forceinline__ void tc_epilogue_hidden(const TcCtx& c, uint32_t tile_off) {
     const uint32_t row = c.tid;
     const uint32_t taddr = c.tmem + ((c.warp * 32u) << 16) + TC_COL_D;
-    uint64_t mask = 0;
+    const __half2 zero = __float2half2_rn(0.0f);
 #pragma unroll
     for (uint32_t half_i = 0; half_i < 2; ++half_i) {
         float v[32];
@@ -208,19 +221,20 @@ __device__ __forceinline__ uint64_t tc_epilogue_hidden(const TcCtx& c, uint32_t 
             uint32_t packed[4];
 #pragma unroll
             for (uint32_t q = 0; q < 4; ++q) {
-                const __half2 h = __floats2half2_rn(fmaxf(v[ch * 8 + 2 * q], 0.0f), fmaxf(v[ch * 8 + 2 * q + 1], 0.0f));
+                const __half2 h = __hmax2(__floats2half2_rn(v[ch * 8 + 2 * q], v[ch * 8 + 2 * q + 1]), zero);
                 packed[q] = *reinterpret_cast<const uint32_t*>(&h);
-                if (__half2float(__low2half(h)) > 0.0f) mask |= 1ull << (half_i * 32 + ch * 8 + 2 * q);
-                if (__half2float(__high2half(h)) > 0.0f) mask |= 1ull << (half_i * 32 + ch * 8 + 2 * q + 1);
             }
             *reinterpret_cast<uint4*>(c.sm + tile_off + sw128_off(row, half_i * 4 + ch)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
         }
     }
-    return mask;
 }
 
-// epilogue of a dgrad GEMM: ReLU mask -> fp16 -> gradient tile at tile_off
-__device__ __forceinline__ void tc_epilogue_dhidden(const TcCtx& c, uint32_t tile_off, uint64_t relu_mask) {
+// 0xffff in every 16-bit half of `h` that is a non-zero fp16 (post-ReLU activations are >= +0, so non-zero == positive)
+__device__ __forceinline__ uint32_t tc_pos_mask2(uint32_t h) { return __vcmpne2(h & 0x7fff7fffu, 0u); }
+
+// epilogue of a dgrad GEMM: ReLU mask (re-read from this thread's own row of the forward activation tile at act_off,
+// which it wrote itself) -> fp16 -> gradient tile at tile_off
+__device__ __forceinline__ void tc_epilogue_dhidden(const TcCtx& c, uint32_t tile_off, uint32_t act_off) {
     const uint32_t taddr = c.tmem + ((c.warp * 32u) << 16) + TC_COL_D;
 #pragma unroll
     for (uint32_t half_i = 0; half_i < 2; ++half_i) {
@@ -229,14 +243,13 @@ __device__ __forceinline__ void tc_epilogue_dhidden(const TcCtx& c, uint32_t til
         tmem_wait_ld();
 #pragma unroll
         for (uint32_t ch = 0; ch < 4; ++ch) {
+            const uint4 act = *reinterpret_cast<const uint4*>(c.sm + act_off + sw128_off(c.tid, half_i * 4 + ch));
+            const uint32_t a[4] = {act.x, act.y, act.z, act.w};
             uint32_t packed[4];
 #pragma unroll
             for (uint32_t q = 0; q < 4; ++q) {
-                const uint32_t bit = half_i * 32 + ch * 8 + 2 * q;
-                const float lo = ((relu_mask >> bit) & 1ull) ? v[ch * 8 + 2 * q] : 0.0f;
-                const float hi = ((relu_mask >> (bit + 1)) & 1ull) ? v[ch * 8 + 2 * q + 1] : 0.0f;
-                const __half2 h = __floats2half2_rn(lo, hi);
-                packed[q] = *reinterpret_cast<const uint32_t*>(&h);
+                const __half2 h = __floats2half2_rn(v[ch * 8 + 2 * q], v[ch * 8 + 2 * q + 1]);
+                packed[q] = *reinterpret_cast<const uint32_t*>(&h) & tc_pos_mask2(a[q]);
             }
             *reinterpret_cast<uint4*>(c.sm + tile_off + sw128_off(c.tid, half_i * 4 + ch)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
         }
@@ -245,19 +258,41 @@ __device__ __forceinline__ void tc_epilogue_dhidden(const TcCtx& c, uint32_t til
 
 // forward through the hidden layers of one staged tile; leaves the last activations in SM_HID and issues nothing after
 template <int NH>
-__device__ __forceinline__ void tc_forward_hidden(TcCtx& c, uint64_t& mask_first, uint64_t& mask_last) {
+__device__ __forceinline__ void tc_forward_hidden(TcCtx& c) {
     if (NH == 1) {
-        mask_last = mask_first = tc_epilogue_hidden(c, SM_HID);
+        tc_epilogue_hidden(c, SM_HID);
     } else {
-        mask_first = tc_epilogue_hidden(c, SM_H1);
+        tc_epilogue_hidden(c, SM_H1);
         TC_PUBLISH_AND_SYNC();
         if (c.tid == 0) tc_issue_layer_hidden(c);
         TC_WAIT(c);
-        mask_last = tc_epilogue_hidden(c, SM_HID);
+        tc_epilogue_hidden(c, SM_HID);
     }
 }
 
 // ------------------------------------------------------------------------------------------ training
+struct TileIn { float tmin, tmax, xi, tgt[3], tgt_depth, bg[3]; uint8_t inst; };
+
+// everything the compositing / loss epilogue needs about ray `ray` and this lane's sample; rays beyond the batch
+// (never the case for R % 4 == 0) get neutral values
+__device__ __forceinline__ TileIn tc_load_tile_inputs(const MonBatch& b, uint32_t ray, uint32_t lane, uint32_t iter) {
+    // loads only — nothing here may depend on a loaded value, so the requests stay in flight until the next tile uses them
+    TileIn in;
+    if (ray < b.R) {
+        in.tmin = b.rays[ray].tmin; in.tmax = b.rays[ray].tmax;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { in.tgt[k] = b.target[ray * 3 + k]; in.bg[k] = b.bg[ray * 3 + k]; }
+        in.tgt_depth = b.target_depth[ray];
+        in.inst = b.ray_inst[ray];
+        in.xi = b.inj_dt ? __ldg(b.inj_dt + ray * 32 + lane) : mon_u01(mon_hash4(b.seed, iter, 2, ray * 32 + lane));
+    } else {
+        in.tmin = 0.0f; in.tmax = 1.0f; in.xi = 1.0f; in.tgt_depth = 0.0f; in.inst = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { in.tgt[k] = 0.0f; in.bg[k] = 0.0f; }
+    }
+    return in;
+}
+
 template <int NH>
 __global__ void __launch_bounds__(TC_THREADS, TC_CTAS_PER_SM(NH))
 k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
@@ -266,9 +301,13 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
     // the next iteration is allowed to overwrite the live block while they run
     if (blockIdx.x == 0 && threadIdx.x == 0) *b.late = *b.ctrl;
     if (b.ctrl->skip) return;
+    TC_STAMP(0);
+    TC_CTA_MARK(0);
     TcCtx c;
     tc_setup(c, smem_raw, TC_TMEM_COLS(NH));
+    TC_STAMP(1);
     tc_load_weights<NH>(c, b.params);
+    TC_STAMP(2);
     // the upper half of every dout row (outputs 4..15 and the second K chunk) stays zero for the whole kernel
     for (uint32_t i = c.tid; i < 4096 / 16; i += TC_THREADS) reinterpret_cast<uint4*>(c.sm + SM_DOUT)[i] = make_uint4(0, 0, 0, 0);
 
@@ -277,6 +316,8 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
     const uint32_t n_tiles = (b.R + 3) / 4;
     uint32_t tiles_done = 0;
 
+    TileIn tin;              // this warp's ray (targets, background, sample distance of this lane), one tile ahead
+    if (blockIdx.x < n_tiles) tin = tc_load_tile_inputs(b, blockIdx.x * 4 + c.warp, c.lane, iter);
     uint32_t enc_regs[16];   // this thread's encoding row of the NEXT tile, prefetched one tile ahead
     if (blockIdx.x < n_tiles) tc_load_enc(enc_regs, b.enc, (size_t)b.R * 32, (size_t)blockIdx.x * 128 + c.tid, blockIdx.x * 4 + c.warp < b.R);
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tiles_done) {
@@ -284,38 +325,41 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
         const bool ray_ok = ray < b.R;
         const uint32_t pt = ray * 32 + c.lane;
         // ---- stage encodings, MMA1
+        const uint32_t sb = 4 + (tiles_done & 1) * 16;
+        TC_STAMP(sb + 0);
         tc_store_enc(c, enc_regs);
         TC_PUBLISH_AND_SYNC();
+        TC_STAMP(sb + 1);
         if (c.tid == 0) tc_issue_layer_in(c);
+        TC_STAMP(sb + 2);
         {
             const uint32_t next = tile + gridDim.x;
             if (next < n_tiles) tc_load_enc(enc_regs, b.enc, (size_t)b.R * 32, (size_t)next * 128 + c.tid, next * 4 + c.warp < b.R);
         }
-        // per-ray inputs of the renderer, fetched while the tensor core works
-        MonRay r;
+        // per-ray inputs of the renderer: this tile's were fetched one tile ahead, the next tile's are requested now
+        MonRay r_cur;
+        r_cur.tmin = tin.tmin; r_cur.tmax = tin.tmax;
+        const float t = mon_sample_t(r_cur, c.lane, tin.xi, 32.0f);
         RayTargets rt;
-        float xi = 1.0f;
-        if (ray_ok) {
-            r = b.rays[ray];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) { rt.tgt[k] = b.target[ray * 3 + k]; rt.bg[k] = b.bg[ray * 3 + k]; }
-            rt.tgt_depth = b.target_depth[ray];
-            rt.is_obj = b.ray_inst[ray] == 1;
-            xi = mon_rand(b.inj_dt, b.seed, iter, 2, pt);
-        } else {
-            r.tmin = 0.0f; r.tmax = 1.0f; r.d_norm = 1.0f;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { r.o[k] = 0.0f; r.d[k] = 0.0f; rt.tgt[k] = 0.0f; rt.bg[k] = 0.0f; }
-            rt.tgt_depth = 0.0f; rt.is_obj = false;
+        for (int k = 0; k < 3; ++k) { rt.tgt[k] = tin.tgt[k]; rt.bg[k] = tin.bg[k]; }
+        rt.tgt_depth = tin.tgt_depth;
+        rt.is_obj = tin.inst == 1;
+        {
+            const uint32_t next = tile + gridDim.x;
+            if (next < n_tiles) tin = tc_load_tile_inputs(b, next * 4 + c.warp, c.lane, iter);
         }
-        const float t = mon_sample_t(r, c.lane, xi, 32.0f);
+        TC_STAMP(sb + 3);
         TC_WAIT(c);
+        TC_STAMP(sb + 4);
         // ---- hidden epilogue(s), MMA2
-        uint64_t relu_first, relu_mask;
-        tc_forward_hidden<NH>(c, relu_first, relu_mask);
+        tc_forward_hidden<NH>(c);
+        TC_STAMP(sb + 5);
         TC_PUBLISH_AND_SYNC();
         if (c.tid == 0) tc_issue_layer_out(c);
+        TC_STAMP(sb + 6);
         TC_WAIT(c);
+        TC_STAMP(sb + 7);
         // ---- output epilogue: compositing, loss, dL/dout
         {
             float o16[16];
@@ -342,6 +386,7 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
             }
         }
         // ---- MMA3: dL/dhidden = dout . W_out
+        TC_STAMP(sb + 8);
         TC_PUBLISH_AND_SYNC();
         if (c.tid == 0) {
             fence_after_sync();
@@ -350,8 +395,11 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
                        make_desc(c.sm_addr + SM_WOUT, 16, 1024, SWZ_128B), IDESC_64_KM, 0);
             commit(c.bar);
         }
+        TC_STAMP(sb + 9);
         TC_WAIT(c);
-        tc_epilogue_dhidden(c, SM_DHID, relu_mask);
+        TC_STAMP(sb + 10);
+        tc_epilogue_dhidden(c, SM_DHID, SM_HID);
+        TC_STAMP(sb + 11);
         if (NH == 2) {   // dH1 = (dH2 . W_h) * relu'(H1)
             TC_PUBLISH_AND_SYNC();
             if (c.tid == 0) {
@@ -364,7 +412,7 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
                 commit(c.bar);
             }
             TC_WAIT(c);
-            tc_epilogue_dhidden(c, SM_DH1, relu_first);
+            tc_epilogue_dhidden(c, SM_DH1, SM_H1);
         }
         // ---- MMA4 (dL/dencoding) + MMA5/6 (weight gradients, accumulated in TMEM across tiles)
         TC_PUBLISH_AND_SYNC();
@@ -392,7 +440,9 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
             }
             commit(c.bar);
         }
+        TC_STAMP(sb + 12);
         TC_WAIT(c);
+        TC_STAMP(sb + 13);
         {   // dL/dencoding: fp16, one 64-byte row per thread
             float v[32];
             tmem_ld32(c.tmem + ((c.warp * 32u) << 16) + TC_COL_E, v);
@@ -411,8 +461,10 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
                 }
             }
         }
+        TC_STAMP(sb + 14);
         // the next tile overwrites enc / hid / dout: every MMA that reads them has completed (the wait above)
     }
+    TC_STAMP(40);
 
     // ---- weight gradients: TMEM -> this CTA's partial row (W_in [64][32] | (W_h [64][64]) | W_out [16][64])
     float* partial = b.mlp_partials + (size_t)blockIdx.x * n_mlp;
@@ -445,7 +497,10 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
             }
         }
     }
+    TC_STAMP(41);
     tc_teardown(c, TC_TMEM_COLS(NH));
+    TC_STAMP(42);
+    TC_CTA_MARK(1);
 }
 
 // ------------------------------------------------------------------------------------------ inference
@@ -464,7 +519,7 @@ k_mlp_infer_tc(uint32_t n_points, const __half* __restrict__ params, const __hal
         TC_PUBLISH_AND_SYNC();
         if (c.tid == 0) tc_issue_layer_in(c);
         TC_WAIT(c);
-        { uint64_t m0, m1; tc_forward_hidden<NH>(c, m0, m1); }
+        tc_forward_hidden<NH>(c);
         TC_PUBLISH_AND_SYNC();
         if (c.tid == 0) tc_issue_layer_out(c);
         TC_WAIT(c);
@@ -507,7 +562,7 @@ k_mlp_render_tc(uint32_t n_rays, uint32_t S2, const MonRay* __restrict__ rays, c
             TC_PUBLISH_AND_SYNC();
             if (c.tid == 0) tc_issue_layer_in(c);
             TC_WAIT(c);
-            { uint64_t m0, m1; tc_forward_hidden<NH>(c, m0, m1); }
+            tc_forward_hidden<NH>(c);
             TC_PUBLISH_AND_SYNC();
             if (c.tid == 0) tc_issue_layer_out(c);
             TC_WAIT(c);
@@ -539,6 +594,9 @@ k_mlp_render_tc(uint32_t n_rays, uint32_t S2, const MonRay* __restrict__ rays, c
 // ------------------------------------------------------------------------------------------ launchers
 template <typename K>
 static cudaError_t tc_prepare(K kernel, int smem_bytes) {
+    // ask for the full shared-memory carve-out: the residency plan (4 x 54 KB or 2 x 94 KB per SM) needs it
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
 }
 

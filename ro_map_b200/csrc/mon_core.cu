@@ -189,7 +189,7 @@ struct mon_object {
     float *target = nullptr, *target_depth = nullptr, *bg = nullptr;
     float *rgb_rays = nullptr, *depth_rays = nullptr, *mask_rays = nullptr, *loss = nullptr;
     float* pts = nullptr;             // [N][3] unit-cube sample positions (the reference's PointsInput)
-    __half *enc = nullptr, *d_enc = nullptr;   // enc: feature-major [32][N]; d_enc: point-major [N][32]
+    __half *enc = nullptr, *d_enc = nullptr;   // enc: level-major pairs [16][N][2]; d_enc: point-major [N][32]
     __half* ph_planar = nullptr;      // fp16 grid weights, per level [feature 0 | feature 1], kept current by the optimizer
     float* partials = nullptr;
     uint32_t n_ctas = 0;
@@ -945,18 +945,18 @@ __global__ void k_lattice_points(uint32_t rx, uint32_t ry, uint32_t rz, float* _
     out[3 * i + 1] = __fdiv_rn((float)y, (float)(ry - 1));
     out[3 * i + 2] = __fdiv_rn((float)z, (float)(rz - 1));
 }
-// feature-major fp16 [C][n] -> point-major float [n][C] (parity hooks only)
+// level-major fp16 pairs [C/2][n][2] -> point-major [n][C] (parity hooks only)
 __global__ void k_soa_to_rows_float(size_t n, uint32_t C, const __half* __restrict__ soa, float* __restrict__ out) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * C) return;
     const size_t p = i / C, c = i - p * C;
-    out[i] = __half2float(soa[c * n + p]);
+    out[i] = __half2float(soa[((c >> 1) * n + p) * 2 + (c & 1)]);
 }
 __global__ void k_soa_to_rows_half(size_t n, uint32_t C, const __half* __restrict__ soa, __half* __restrict__ out) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * C) return;
     const size_t p = i / C, c = i - p * C;
-    out[i] = soa[c * n + p];
+    out[i] = soa[((c >> 1) * n + p) * 2 + (c & 1)];
 }
 __global__ void k_extract_sigma(size_t n, const float* __restrict__ out4, float* __restrict__ sigma) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

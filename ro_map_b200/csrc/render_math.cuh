@@ -13,7 +13,9 @@
 #define MON_FULL 0xffffffffu
 #define MON_T_EPS 1e-4f
 
-MON_DEV float mon_logistic(float x) { return __fdiv_rn(1.0f, 1.0f + expf(-x)); }  // tcnn::logistic, accurate expf
+// tcnn::logistic = 1/(1+expf(-x)).  Evaluated with the SFU exponential and reciprocal (relative error ~2^-21, far below
+// the fp16 resolution of the logits it is applied to); the density keeps the reference's own __expf.
+MON_DEV float mon_logistic(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 MON_DEV float warp_incl_prod(float v, uint32_t lane) {
 #pragma unroll

@@ -141,9 +141,12 @@ int mon_object_launch_count(mon_object* obj, uint64_t* n);
  * (z-depth), mask[h*w].  rand_dt: h*w*render_samples floats in (0,1] or NULL (internal RNG). */
 int mon_object_render(mon_object* obj, mon_bbox2d box, const float Twc[16], int use_ema,
                       const float* rand_dt, float* rgb, float* depth, float* mask);
-/* GetDensityOnGrid (nerf_model.cu:2007-2043): raw sigma logit on a res^3 lattice of the AABB
- * (training weights; x fastest).  out: res[0]*res[1]*res[2] floats on the host. */
+/* GetDensityOnGrid (nerf_model.cu:2007-2043): raw sigma logit on a res^3 lattice of the AABB, inference (EMA)
+ * weights like the reference; x fastest.  out: res[0]*res[1]*res[2] floats on the host.  Input of marching cubes. */
 int mon_object_density_grid(mon_object* obj, const uint32_t res[3], float* out);
+/* Network logits (r, g, b, sigma; fp16 network output widened to float) at n unit-cube positions [n][3], as
+ * compute_mesh_vertex_colors queries them (nerf_model.cu:2045-2067).  use_ema = 1: inference weights. */
+int mon_object_query_points(mon_object* obj, const float* points_unit, uint32_t n, int use_ema, float* out4);
 
 /* ---- parity / test hooks ------------------------------------------------------------------- */
 /* One training iteration with host-provided random numbers instead of the internal generator:

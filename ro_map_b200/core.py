@@ -215,6 +215,13 @@ class NerfObject:
         check(self._lib.mon_object_density_grid(self._h, r, _ptr(out)))
         return out
 
+    def query_points(self, points_unit, use_ema: bool = True) -> np.ndarray:
+        """Network logits (r, g, b, sigma) at unit-cube positions [n, 3]."""
+        pts = _f32(points_unit).reshape(-1, 3)
+        out = np.empty((pts.shape[0], 4), np.float32)
+        check(self._lib.mon_object_query_points(self._h, _ptr(pts), pts.shape[0], int(use_ema), _ptr(out)))
+        return out
+
     # ---- parity hooks
     def train_injected(self, sample_xy, rand_colors, rand_dt) -> tuple[float, int]:
         sxy = _f32(sample_xy, (self.R, 2))

@@ -194,7 +194,12 @@ k_encode_forward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, co
 
 cudaError_t mon_launch_encode_forward(const MonGrid& g, uint32_t n_points, const float* pts, const __half* planar, __half* enc_soa,
                                       const MonCtrl* ctrl, uint32_t sm_count, cudaStream_t st) {
-    static cudaError_t prep = cudaFuncSetAttribute(k_encode_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_TABLE_BYTES);
+    static std::atomic<uint64_t> prepared{0};
+    const cudaError_t prep = mon_once_per_device(prepared, [] {
+        cudaError_t e = cudaFuncSetAttribute(k_encode_forward, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(k_encode_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_TABLE_BYTES);
+    });
     if (prep != cudaSuccess) return prep;
     if (n_points == 0) return cudaSuccess;
     // every CTA loads up to two 128 KB slices: do not spread tiny batches over the whole chip

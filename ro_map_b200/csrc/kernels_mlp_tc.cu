@@ -602,11 +602,13 @@ static cudaError_t tc_prepare(K kernel, int smem_bytes) {
 
 cudaError_t mon_launch_mlp_train_tc(const MonBatch& b, const MonLossCfg& lc, uint32_t n_hidden, uint32_t n_mlp, uint32_t n_ctas, cudaStream_t st) {
     if (n_hidden == 1) {
-        static cudaError_t prep = tc_prepare(k_mlp_train_tc<1>, TC_SMEM_BYTES(1));
+        static std::atomic<uint64_t> prepared{0};
+        const cudaError_t prep = mon_once_per_device(prepared, [] { return tc_prepare(k_mlp_train_tc<1>, TC_SMEM_BYTES(1)); });
         if (prep != cudaSuccess) return prep;
         k_mlp_train_tc<1><<<n_ctas, TC_THREADS, TC_SMEM_BYTES(1), st>>>(b, lc, n_mlp);
     } else if (n_hidden == 2) {
-        static cudaError_t prep = tc_prepare(k_mlp_train_tc<2>, TC_SMEM_BYTES(2));
+        static std::atomic<uint64_t> prepared{0};
+        const cudaError_t prep = mon_once_per_device(prepared, [] { return tc_prepare(k_mlp_train_tc<2>, TC_SMEM_BYTES(2)); });
         if (prep != cudaSuccess) return prep;
         k_mlp_train_tc<2><<<n_ctas, TC_THREADS, TC_SMEM_BYTES(2), st>>>(b, lc, n_mlp);
     } else {
@@ -620,11 +622,13 @@ cudaError_t mon_launch_mlp_infer_tc(uint32_t n_points, uint32_t n_hidden, const 
     if (ctas > 592) ctas = 592;
     if (ctas == 0) ctas = 1;
     if (n_hidden == 1) {
-        static cudaError_t prep = tc_prepare(k_mlp_infer_tc<1>, TC_SMEM_BYTES(1));
+        static std::atomic<uint64_t> prepared{0};
+        const cudaError_t prep = mon_once_per_device(prepared, [] { return tc_prepare(k_mlp_infer_tc<1>, TC_SMEM_BYTES(1)); });
         if (prep != cudaSuccess) return prep;
         k_mlp_infer_tc<1><<<ctas, TC_THREADS, TC_SMEM_BYTES(1), st>>>(n_points, params, enc, out4);
     } else if (n_hidden == 2) {
-        static cudaError_t prep = tc_prepare(k_mlp_infer_tc<2>, TC_SMEM_BYTES(2));
+        static std::atomic<uint64_t> prepared{0};
+        const cudaError_t prep = mon_once_per_device(prepared, [] { return tc_prepare(k_mlp_infer_tc<2>, TC_SMEM_BYTES(2)); });
         if (prep != cudaSuccess) return prep;
         k_mlp_infer_tc<2><<<ctas, TC_THREADS, TC_SMEM_BYTES(2), st>>>(n_points, params, enc, out4);
     } else {
@@ -640,11 +644,13 @@ cudaError_t mon_launch_mlp_render_tc(uint32_t n_rays, uint32_t S2, uint32_t n_hi
     if (ctas > 592) ctas = 592;
     if (ctas == 0) ctas = 1;
     if (n_hidden == 1) {
-        static cudaError_t prep = tc_prepare(k_mlp_render_tc<1>, TC_SMEM_BYTES(1));
+        static std::atomic<uint64_t> prepared{0};
+        const cudaError_t prep = mon_once_per_device(prepared, [] { return tc_prepare(k_mlp_render_tc<1>, TC_SMEM_BYTES(1)); });
         if (prep != cudaSuccess) return prep;
         k_mlp_render_tc<1><<<ctas, TC_THREADS, TC_SMEM_BYTES(1), st>>>(n_rays, S2, rays, in_box, jitter, seed, iter, params, enc, bgc, rgb, depth, mask);
     } else if (n_hidden == 2) {
-        static cudaError_t prep = tc_prepare(k_mlp_render_tc<2>, TC_SMEM_BYTES(2));
+        static std::atomic<uint64_t> prepared{0};
+        const cudaError_t prep = mon_once_per_device(prepared, [] { return tc_prepare(k_mlp_render_tc<2>, TC_SMEM_BYTES(2)); });
         if (prep != cudaSuccess) return prep;
         k_mlp_render_tc<2><<<ctas, TC_THREADS, TC_SMEM_BYTES(2), st>>>(n_rays, S2, rays, in_box, jitter, seed, iter, params, enc, bgc, rgb, depth, mask);
     } else {

@@ -1074,7 +1074,7 @@ static int ensure_render_ws(mon_object* o, uint32_t n_rays, size_t jitter_floats
     if (!o->r_enc) {
         CK(cudaMalloc(&o->r_enc, (size_t)tile * S2 * MON_IN * 2));
         CK(cudaMalloc(&o->r_pts, (size_t)tile * S2 * 12));
-        CK(cudaMalloc(&o->r_planar, (size_t)o->n_grid * 2 + 16));
+        if (!o->r_planar) CK(cudaMalloc(&o->r_planar, (size_t)o->n_grid * 2 + 16));
         CK(cudaMalloc(&o->r_Twc, 64));
         o->r_tile = tile;
     }
@@ -1130,6 +1130,46 @@ int mon_object_render(mon_object* o, mon_bbox2d box, const float Twc[16], int us
     return MON_OK;
 }
 
+// network logits at arbitrary unit-cube positions (device pointer in, device out4 [n][4]); the inference half of
+// DifferentiableObject::inference as GetDensityOnGrid / compute_mesh_vertex_colors use it (nerf_model.cu:2007-2067)
+static int infer_points_device(mon_object* o, const float* d_pts, uint32_t n, int use_ema, float* d_out4) {
+    cudaStream_t st = o->stream;
+    const __half* params = use_ema ? o->ema : o->ph;
+    const __half* planar = o->ph_planar;
+    if (use_ema) {
+        if (!o->r_planar) CK(cudaMalloc(&o->r_planar, (size_t)o->n_grid * 2 + 16));
+        mon_launch_planarize(o->grid, o->ema + o->n_mlp, o->r_planar, st);
+        o->launches += 1;
+        planar = o->r_planar;
+    }
+    __half* enc = nullptr;
+    CK(cudaMalloc(&enc, (size_t)n * MON_IN * 2));
+    cudaError_t e = mon_launch_encode_forward(o->grid, n, d_pts, planar, enc, nullptr, (uint32_t)o->sm_count, st);
+    if (e == cudaSuccess) e = mon_launch_mlp_infer_tc(n, o->cfg.n_hidden_layers, params, enc, d_out4, st);
+    o->launches += 2;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(enc);
+    if (e != cudaSuccess) return fail(MON_ERR_CUDA, "inference: %s", cudaGetErrorString(e));
+    return MON_OK;
+}
+
+int mon_object_query_points(mon_object* o, const float* points_unit, uint32_t n, int use_ema, float* out4) {
+    if (!o || !points_unit || !out4) return fail(MON_ERR_ARG, "NULL argument");
+    if (n == 0) return MON_OK;
+    CK(cudaSetDevice(o->ds->gpu));
+    float *pts = nullptr, *res = nullptr;
+    cudaError_t e = cudaMalloc(&pts, (size_t)n * 12);
+    if (e == cudaSuccess) e = cudaMalloc(&res, (size_t)n * 16);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(pts, points_unit, (size_t)n * 12, cudaMemcpyHostToDevice, o->stream);
+    int rc = MON_OK;
+    if (e == cudaSuccess) rc = infer_points_device(o, pts, n, use_ema, res);
+    if (e == cudaSuccess && rc == MON_OK) e = cudaMemcpy(out4, res, (size_t)n * 16, cudaMemcpyDeviceToHost);
+    if (pts) cudaFree(pts);
+    if (res) cudaFree(res);
+    if (e != cudaSuccess) return fail(MON_ERR_CUDA, "mon_object_query_points: %s", cudaGetErrorString(e));
+    return rc;
+}
+
 int mon_object_density_grid(mon_object* o, const uint32_t res[3], float* out) {
     if (!o || !res || !out) return fail(MON_ERR_ARG, "NULL argument");
     if (res[0] < 2 || res[1] < 2 || res[2] < 2) return fail(MON_ERR_ARG, "resolution must be >= 2 per axis");
@@ -1137,25 +1177,27 @@ int mon_object_density_grid(mon_object* o, const uint32_t res[3], float* out) {
     if (n > (1u << 27)) return fail(MON_ERR_ARG, "lattice too large");
     CK(cudaSetDevice(o->ds->gpu));
     cudaStream_t st = o->stream;
-    float *pts = nullptr, *out4 = nullptr, *sigma = nullptr; __half* enc = nullptr;
+    float *pts = nullptr, *out4 = nullptr, *sigma = nullptr;
     cudaError_t e = cudaMalloc(&pts, n * 12);
     if (e == cudaSuccess) e = cudaMalloc(&out4, n * 16);
     if (e == cudaSuccess) e = cudaMalloc(&sigma, n * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&enc, n * MON_IN * 2);
+    int rc = MON_OK;
     if (e == cudaSuccess) {
         const unsigned blocks = (unsigned)((n + 255) / 256);
         k_lattice_points<<<blocks, 256, 0, st>>>(res[0], res[1], res[2], pts);
-        e = mon_launch_encode_forward(o->grid, (uint32_t)n, pts, o->ph_planar, enc, nullptr, (uint32_t)o->sm_count, st);
-        if (e == cudaSuccess) e = mon_launch_mlp_infer_tc((uint32_t)n, o->cfg.n_hidden_layers, o->ph, enc, out4, st);
-        k_extract_sigma<<<blocks, 256, 0, st>>>(n, out4, sigma);
-        o->launches += 4;
-        if (e == cudaSuccess) e = cudaMemcpyAsync(out, sigma, n * 4, cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        // inference weights (EMA), like mpNetwork->inference_mixed_precision_impl(..., use_inference_params = true) (:2028)
+        rc = infer_points_device(o, pts, (uint32_t)n, 1, out4);
+        if (rc == MON_OK) {
+            k_extract_sigma<<<blocks, 256, 0, st>>>(n, out4, sigma);
+            o->launches += 2;
+            e = cudaMemcpyAsync(out, sigma, n * 4, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        }
     }
     if (pts) cudaFree(pts);
     if (out4) cudaFree(out4);
     if (sigma) cudaFree(sigma);
-    if (enc) cudaFree(enc);
+    if (rc != MON_OK) return rc;
     if (e != cudaSuccess) return fail(MON_ERR_CUDA, "density grid: %s", cudaGetErrorString(e));
     return MON_OK;
 }

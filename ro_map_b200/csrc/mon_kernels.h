@@ -1,6 +1,23 @@
 // mon_kernels.h — launch prototypes of the sm_100a kernels (one .cu per kernel family).
 #pragma once
+#include <atomic>
+
 #include "mon_types.h"
+
+// Function attributes (dynamic shared memory size, carve-out) are per DEVICE: run `f` once for every device a kernel is
+// launched on (one process may drive several GPUs through the C++ facade).  `f` is idempotent, so a benign race
+// between two host threads only repeats it.
+template <typename F>
+inline cudaError_t mon_once_per_device(std::atomic<uint64_t>& done_mask, F&& f) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const uint64_t bit = 1ull << (dev & 63);
+    if (done_mask.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = f();
+    if (e == cudaSuccess) done_mask.fetch_or(bit, std::memory_order_release);
+    return e;
+}
 
 // kernels_batch.cu
 void mon_launch_generate_batch(const MonBatch& b, const MonScene& sc, cudaStream_t st);

@@ -39,6 +39,7 @@ public:
     std::vector<FrameIdAndBbox> GetFrameIdAndBBox();
     void DrawCPUMesh();   // needs an OpenGL context; a no-op in headless builds
     void DrawMesh();
+    void SaveMesh(const std::string outname);   // NeRF_Model::SaveMesh: ASCII PLY of the current CPU mesh
     // additions (not in the reference): logged loss of the last Train_Step and its device time
     float LastLoss() const { return mfLastLoss; }
     float LastTrainMs() const { return mfLastMs; }

@@ -17,6 +17,7 @@
 #include "mon_c.h"
 #include "nerf_data.h"
 #include "nerf_manager.h"
+#include "mesh.h"
 #include "png_io.h"
 
 using std::cerr;
@@ -296,12 +297,30 @@ void NeRF::TrainStep(int iters) {   // NeRF_Model::Train_Step / Train_Step_Onlin
     cout << " Step: " << mnTrainingStep << " loss: " << loss << endl;
 }
 
+// GenerateMesh + TransCPUMesh (nerf_model.cu:1993-2105): 64^3 density lattice (marching_cubes.h:30), threshold 2.0 on
+// the raw sigma logit, surface + normals + colours into the CPU mesh the viewer draws
 void NeRF::UpdateMesh() {
-    // GenerateMesh + TransCPUMesh (nerf_model.cu:1993-2105): density lattice -> marching cubes -> CPU mesh.
-    // The lattice comes from the core; surface extraction is the next row of the scope table.
-    std::unique_lock<std::mutex> lock(mCPUMeshData.mesh_mutex, std::try_to_lock);
-    if (!lock.owns_lock()) return;
-    mCPUMeshData.have_reslult = false;
+    const float bmin[3] = {mBoundingBox.min[0], mBoundingBox.min[1], mBoundingBox.min[2]};
+    const float bmax[3] = {mBoundingBox.max[0], mBoundingBox.max[1], mBoundingBox.max[2]};
+    mesh::Extracted m;
+    std::string err;
+    if (!mesh::extract(mpCore, bmin, bmax, 64, 2.0f, m, err)) {
+        cerr << "mesh extraction: " << err << endl;
+        return;
+    }
+    std::unique_lock<std::mutex> lock(mCPUMeshData.mesh_mutex);
+    mCPUMeshData.verts.swap(m.verts);
+    mCPUMeshData.normals.swap(m.normals);
+    mCPUMeshData.colors.swap(m.colors);
+    mCPUMeshData.indices.swap(m.indices);
+    mCPUMeshData.have_reslult = true;
+}
+
+void NeRF::SaveMesh(const std::string outname) {   // NeRF_Model::SaveMesh -> save_mesh (marching_cubes.cu:512-620)
+    std::unique_lock<std::mutex> lock(mCPUMeshData.mesh_mutex);
+    if (!mCPUMeshData.have_reslult) return;
+    if (!mesh::save_ply(outname, mCPUMeshData.verts, mCPUMeshData.normals, mCPUMeshData.colors, mCPUMeshData.indices))
+        cerr << "Failed to open " << outname << " for writing." << endl;
 }
 
 void NeRF::TrainOffline(const int iterations) {   // nerf.cu:120-153
@@ -314,6 +333,8 @@ void NeRF::TrainOffline(const int iterations) {   // nerf.cu:120-153
         TrainStep(500);
         if (i % 2 == 0) UpdateMesh();
     }
+    mkdir("./output", 0755);
+    SaveMesh("./output/" + std::to_string(mId) + ".ply");
     cout << "Training completed, press Ctrl+C to exit" << endl;
 }
 
@@ -421,6 +442,8 @@ void NeRF::RenderTestImg(const string out_path, const vector<string>& timestamp,
         png_io::write(folder + "/test_mask/" + stamp + ".png", (int)b.w, (int)b.h, 1, 8, mask8.data());
         ftest << stamp << " " << b.x << " " << b.y << " " << b.h << " " << b.w << endl;
     }
+    UpdateMesh();
+    SaveMesh(folder + "/obj.ply");
 }
 
 vector<Eigen::Matrix4f> NeRF::GetTwc() {

@@ -1,0 +1,74 @@
+// mesh_check.cpp — CPU unit check of ro_map_b200/host/mesh.h with the two C-ABI calls it makes replaced by an
+// analytic field (sigma = 2 + 40 * (0.3 - |p - c|), i.e. the threshold-2.0 surface is a sphere of radius 0.3 in
+// unit-cube coordinates; colour logits encode the position).  Prints facts the pytest asserts on.
+#include <cstdio>
+#include <map>
+#include <set>
+
+#include "mesh.h"
+
+static const float C0[3] = {0.5f, 0.45f, 0.55f};
+static float field(float x, float y, float z) {
+    const float dx = x - C0[0], dy = y - C0[1], dz = z - C0[2];
+    return 2.0f + 40.0f * (0.3f - std::sqrt(dx * dx + dy * dy + dz * dz));
+}
+extern "C" {
+const char* mon_last_error(void) { return "stub"; }
+int mon_object_density_grid(mon_object*, const uint32_t res[3], float* out) {
+    for (uint32_t z = 0; z < res[2]; ++z)
+        for (uint32_t y = 0; y < res[1]; ++y)
+            for (uint32_t x = 0; x < res[0]; ++x)
+                out[((size_t)z * res[1] + y) * res[0] + x] = field((float)x / (res[0] - 1), (float)y / (res[1] - 1), (float)z / (res[2] - 1));
+    return 0;
+}
+int mon_object_query_points(mon_object*, const float* p, uint32_t n, int, float* out4) {
+    for (uint32_t i = 0; i < n; ++i) {
+        for (int k = 0; k < 3; ++k) out4[4 * i + k] = 8.0f * (p[3 * i + k] - 0.5f);
+        out4[4 * i + 3] = field(p[3 * i], p[3 * i + 1], p[3 * i + 2]);
+    }
+    return 0;
+}
+}
+
+int main(int argc, char** argv) {
+    const uint32_t res = argc > 1 ? (uint32_t)atoi(argv[1]) : 64;
+    const float bmin[3] = {-1.0f, -2.0f, -0.5f}, bmax[3] = {1.0f, 2.0f, 0.5f};
+    mesh::Extracted m;
+    std::string err;
+    if (!mesh::extract(nullptr, bmin, bmax, res, 2.0f, m, err)) { printf("error %s\n", err.c_str()); return 1; }
+    const size_t nv = m.verts.size() / 3, nf = m.indices.size() / 3;
+    // every undirected edge shared by exactly two triangles, and traversed once in each direction (consistent winding)
+    std::map<std::pair<uint32_t, uint32_t>, int> directed;
+    std::set<std::pair<uint32_t, uint32_t>> undirected;
+    for (size_t f = 0; f < nf; ++f)
+        for (int k = 0; k < 3; ++k) {
+            const uint32_t a = m.indices[3 * f + k], b = m.indices[3 * f + (k + 1) % 3];
+            directed[{a, b}]++;
+            undirected.insert({a < b ? a : b, a < b ? b : a});
+        }
+    size_t bad_edges = 0;
+    for (auto& e : undirected)
+        if (directed[{e.first, e.second}] != 1 || directed[{e.second, e.first}] != 1) ++bad_edges;
+    // vertices on the sphere (unit-cube metric), normals outward, colours = logistic of the position code
+    double max_r_err = 0.0, min_dot = 1.0;
+    size_t bad_col = 0;
+    for (size_t v = 0; v < nv; ++v) {
+        float u[3], n_unit[3];
+        for (int k = 0; k < 3; ++k) u[k] = (m.verts[3 * v + k] - bmin[k]) / (bmax[k] - bmin[k]);
+        const float d[3] = {u[0] - C0[0], u[1] - C0[1], u[2] - C0[2]};
+        const double r = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        max_r_err = std::fmax(max_r_err, std::fabs(r - 0.3));
+        // object-space normal -> unit-cube normal direction (covariant: multiply by the box extent)
+        for (int k = 0; k < 3; ++k) n_unit[k] = m.normals[3 * v + k] * (bmax[k] - bmin[k]);
+        const double nl = std::sqrt(n_unit[0] * n_unit[0] + n_unit[1] * n_unit[1] + n_unit[2] * n_unit[2]);
+        min_dot = std::fmin(min_dot, (n_unit[0] * d[0] + n_unit[1] * d[1] + n_unit[2] * d[2]) / (nl * r));
+        for (int k = 0; k < 3; ++k) {
+            const int want = (int)(255.0f / (1.0f + std::exp(-8.0f * (u[k] - 0.5f))));
+            if (std::abs((int)m.colors[3 * v + k] - want) > 1) ++bad_col;
+        }
+    }
+    printf("verts %zu faces %zu edges %zu bad_edges %zu euler %ld max_r_err %.6f min_normal_dot %.4f bad_colors %zu\n", nv, nf, undirected.size(), bad_edges,
+           (long)nv - (long)undirected.size() + (long)nf, max_r_err, min_dot, bad_col);
+    if (argc > 2) return mesh::save_ply(argv[2], m.verts, m.normals, m.colors, m.indices) ? 0 : 2;
+    return 0;
+}

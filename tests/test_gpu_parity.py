@@ -228,6 +228,35 @@ def test_graph_training_and_render(core, oracle, gpu_dataset, small_seq, n_hidde
     dg = g.density_grid((16, 16, 16))
     assert dg.shape == (16, 16, 16) and np.isfinite(dg).all()
     assert dg[6:10, 6:10, 6:10].mean() > dg[0, 0, 0]
+    # the lattice is the sigma column of query_points on the same lattice with the EMA weights (x fastest)
+    ax = np.linspace(0.0, 1.0, 16, dtype=np.float32)
+    zz, yy, xx = np.meshgrid(ax, ax, ax, indexing="ij")
+    lat = np.stack([xx, yy, zz], -1).reshape(-1, 3)
+    q = g.query_points(lat, use_ema=True)
+    assert np.array_equal(q[:, 3].reshape(16, 16, 16), dg)
+
+
+@pytest.mark.parametrize("n_hidden", [1, 2])
+def test_query_points_matches_oracle(core, oracle, gpu_dataset, small_seq, n_hidden):
+    """mon_object_query_points (mesh colours / density lattice inference): encode + MLP forward of arbitrary unit-cube
+    points vs the oracle's encode + mlp_forward on the same fp16 weights; ragged n (not a multiple of the 128-row tile)."""
+    seq, obj = small_seq, small_seq.objects[0]
+    g, o = make_pair(core, oracle, gpu_dataset, seq, obj, 256, n_hidden=n_hidden)
+    g.train(20)
+    cfg, ocfg = g.cfg, o.cfg
+    n_mlp = core.param_counts(cfg)[0]
+    rng = np.random.default_rng(3)
+    pts = rng.random((1000 + 37, 3), dtype=np.float32)
+    pts[:3] = [[0, 0, 0], [1, 1, 1], [0.5, 0.5, 0.5]]
+    for which, use_ema in (("params", False), ("ema", True)):
+        w = oracle.f2h(g.state(which))                                   # fp16 values widened to float by get_state
+        enc = oracle.encode(ocfg, w[n_mlp:], pts)
+        _, out = oracle.mlp_forward(ocfg, w[:n_mlp], enc)
+        want = oracle.h2f(out[:, :4])
+        got = g.query_points(pts, use_ema=use_ema)
+        # tensor-core fp32 accumulation order differs from the oracle's sequential sum: a few fp16 ulps on O(1) logits
+        assert np.allclose(got, want, atol=4e-3, rtol=4e-3), np.abs(got - want).max()
+    assert g.query_points(np.zeros((0, 3), np.float32)).shape == (0, 4)
 
 
 def test_edge_cases(core, oracle, gpu_dataset, small_seq):

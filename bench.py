@@ -44,7 +44,9 @@ def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=500)
-    ap.add_argument("--warmup", type=int, default=50)
+    # 250: past the start-up phase of a fresh object (the first ~100 iterations scatter a dense gradient and run up to
+    # 2x slower, profiles/r1g_pdl_ab.txt); the offline job is 5000 iterations, so the steady state is what it pays for
+    ap.add_argument("--warmup", type=int, default=250)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays", type=int, default=4096, help="rays per batch (reference: 4096, nerf_model.h:173)")
     ap.add_argument("--hidden-layers", type=int, default=1, help="MLP hidden layers (reference base.json: 1)")

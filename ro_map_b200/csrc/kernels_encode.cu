@@ -31,6 +31,8 @@ k_sample_points(uint32_t n_points, uint32_t S, const MonRay* __restrict__ rays, 
                 const float* __restrict__ jitter, uint32_t seed, const MonCtrl* __restrict__ ctrl, uint32_t rng_stream,
                 uint32_t iter_fixed, float bmin0, float bmin1, float bmin2, float bmax0, float bmax1, float bmax2,
                 float* __restrict__ pts) {
+    mon_pdl_wait();
+    mon_pdl_trigger();
     if (ctrl && ctrl->skip) return;
     const uint32_t pt = blockIdx.x * blockDim.x + threadIdx.x;
     if (pt >= n_points) return;
@@ -53,8 +55,8 @@ k_sample_points(uint32_t n_points, uint32_t S, const MonRay* __restrict__ rays, 
 void mon_launch_sample_points(uint32_t n_points, uint32_t S, const MonRay* rays, const int* in_box, const float* jitter,
                               uint32_t seed, const MonCtrl* ctrl, uint32_t rng_stream, uint32_t iter_fixed,
                               const float* bmin, const float* bmax, float* pts, cudaStream_t st) {
-    k_sample_points<<<(n_points + 255) / 256, 256, 0, st>>>(n_points, S, rays, in_box, jitter, seed, ctrl, rng_stream, iter_fixed,
-                                                           bmin[0], bmin[1], bmin[2], bmax[0], bmax[1], bmax[2], pts);
+    mon_launch_chain(MON_PDL_POINTS, k_sample_points, dim3((n_points + 255) / 256), dim3(256), 0, st, n_points, S, rays, in_box, jitter, seed, ctrl, rng_stream,
+                     iter_fixed, bmin[0], bmin[1], bmin[2], bmax[0], bmax[1], bmax[2], pts);
 }
 
 // ---------------------------------------------------------------------------------------------- shared helpers
@@ -135,11 +137,13 @@ k_encode_forward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, co
                  __half* __restrict__ enc_soa, const MonCtrl* __restrict__ ctrl) {
     extern __shared__ __align__(128) unsigned char enc_smem[];
     __shared__ __align__(8) uint64_t bar;
-    if (ctrl && ctrl->skip) return;
     const __half* table = reinterpret_cast<const __half*>(enc_smem);
     const uint32_t tid = threadIdx.x;
     if (tid == 0) { tc05::mbar_init(&bar, 1); tc05::mbar_fence_init(); }
     __syncthreads();
+    mon_pdl_wait();       // the optimizer sweep (planar weights) has completed
+    mon_pdl_trigger();
+    if (ctrl && ctrl->skip) return;
 
     const uint64_t total = (uint64_t)(2 * g.n_levels) * n_points;
     uint64_t w = total * blockIdx.x / gridDim.x;
@@ -207,8 +211,7 @@ cudaError_t mon_launch_encode_forward(const MonGrid& g, uint32_t n_points, const
     const uint64_t want = (total + 16383) / 16384;
     uint32_t ctas = want < (uint64_t)sm_count ? (uint32_t)want : sm_count;
     if (ctas == 0) ctas = 1;
-    k_encode_forward<<<ctas, ENC_THREADS, ENC_TABLE_BYTES, st>>>(g, n_points, pts, planar, enc_soa, ctrl);
-    return cudaGetLastError();
+    return mon_launch_chain(MON_PDL_ENCODE, k_encode_forward, dim3(ctas), dim3(ENC_THREADS), ENC_TABLE_BYTES, st, g, n_points, pts, planar, enc_soa, ctrl);
 }
 
 // interleaved fp16 weights [entry][2] -> planar per level [f0 table | f1 table] (initialisation / set_params; the
@@ -242,6 +245,8 @@ __device__ __forceinline__ void red_add_f16x2(__half2* addr, __half2 v) {
 __global__ void __launch_bounds__(SCT_THREADS)
 k_encode_backward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, const MonCtrl* __restrict__ ctrl,
                   const __half* __restrict__ d_enc, __half* __restrict__ grid_grad) {
+    mon_pdl_wait();
+    mon_pdl_trigger();
     if (ctrl->skip) return;
     const uint32_t p = threadIdx.x & (SCT_TILE - 1), lg = threadIdx.x >> 7;
     const uint32_t pt = blockIdx.x * SCT_TILE + p;
@@ -301,5 +306,5 @@ k_encode_backward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, c
 void mon_launch_encode_backward(const MonGrid& g, uint32_t n_points, const float* pts, const MonCtrl* ctrl,
                                 const __half* d_enc, __half* grid_grad, cudaStream_t st) {
     const uint32_t blocks = (n_points + SCT_TILE - 1) / SCT_TILE;
-    k_encode_backward<<<blocks, SCT_THREADS, 0, st>>>(g, n_points, pts, ctrl, d_enc, grid_grad);
+    mon_launch_chain(MON_PDL_SCATTER, k_encode_backward, dim3(blocks), dim3(SCT_THREADS), 0, st, g, n_points, pts, ctrl, d_enc, grid_grad);
 }

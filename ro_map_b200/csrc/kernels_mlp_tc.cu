@@ -297,10 +297,10 @@ template <int NH>
 __global__ void __launch_bounds__(TC_THREADS, TC_CTAS_PER_SM(NH))
 k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
     extern __shared__ unsigned char smem_raw[];
-    // hand the iteration's control block to the kernels behind this one (scatter, optimizer): the batch kernel of
-    // the next iteration is allowed to overwrite the live block while they run
-    if (blockIdx.x == 0 && threadIdx.x == 0) *b.late = *b.ctrl;
-    if (b.ctrl->skip) return;
+    // Prologue that overlaps the tail of the hash-encode kernel (programmatic dependent launch, mon_kernels.h):
+    // TMEM allocation, barriers, weight tiles, the constant part of the dout tile and the first tile's ray inputs.
+    // Everything read here was written by kernels OLDER than the encode kernel (weights: the previous optimizer
+    // sweep; rays/targets/control block: this iteration's batch kernel), which have completed.
     TC_STAMP(0);
     TC_CTA_MARK(0);
     TcCtx c;
@@ -311,13 +311,23 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
     // the upper half of every dout row (outputs 4..15 and the second K chunk) stays zero for the whole kernel
     for (uint32_t i = c.tid; i < 4096 / 16; i += TC_THREADS) reinterpret_cast<uint4*>(c.sm + SM_DOUT)[i] = make_uint4(0, 0, 0, 0);
 
+    const bool skip = b.ctrl->skip != 0;
     const float kscale = lc.loss_scale / (float)b.R;
     const uint32_t iter = b.ctrl->iter - 1;
     const uint32_t n_tiles = (b.R + 3) / 4;
     uint32_t tiles_done = 0;
 
     TileIn tin;              // this warp's ray (targets, background, sample distance of this lane), one tile ahead
-    if (blockIdx.x < n_tiles) tin = tc_load_tile_inputs(b, blockIdx.x * 4 + c.warp, c.lane, iter);
+    if (!skip && blockIdx.x < n_tiles) tin = tc_load_tile_inputs(b, blockIdx.x * 4 + c.warp, c.lane, iter);
+    mon_pdl_wait();          // the encodings of this iteration are complete
+    mon_pdl_trigger();
+    // hand the iteration's control block to the kernels behind this one (scatter, optimizer): the batch kernel of
+    // the next iteration is allowed to overwrite the live block while they run
+    if (blockIdx.x == 0 && threadIdx.x == 0) *b.late = *b.ctrl;
+    if (skip) {
+        tc_teardown(c, TC_TMEM_COLS(NH));
+        return;
+    }
     uint32_t enc_regs[16];   // this thread's encoding row of the NEXT tile, prefetched one tile ahead
     if (blockIdx.x < n_tiles) tc_load_enc(enc_regs, b.enc, (size_t)b.R * 32, (size_t)blockIdx.x * 128 + c.tid, blockIdx.x * 4 + c.warp < b.R);
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tiles_done) {
@@ -605,12 +615,12 @@ cudaError_t mon_launch_mlp_train_tc(const MonBatch& b, const MonLossCfg& lc, uin
         static std::atomic<uint64_t> prepared{0};
         const cudaError_t prep = mon_once_per_device(prepared, [] { return tc_prepare(k_mlp_train_tc<1>, TC_SMEM_BYTES(1)); });
         if (prep != cudaSuccess) return prep;
-        k_mlp_train_tc<1><<<n_ctas, TC_THREADS, TC_SMEM_BYTES(1), st>>>(b, lc, n_mlp);
+        return mon_launch_chain(MON_PDL_MLP, k_mlp_train_tc<1>, dim3(n_ctas), dim3(TC_THREADS), TC_SMEM_BYTES(1), st, b, lc, n_mlp);
     } else if (n_hidden == 2) {
         static std::atomic<uint64_t> prepared{0};
         const cudaError_t prep = mon_once_per_device(prepared, [] { return tc_prepare(k_mlp_train_tc<2>, TC_SMEM_BYTES(2)); });
         if (prep != cudaSuccess) return prep;
-        k_mlp_train_tc<2><<<n_ctas, TC_THREADS, TC_SMEM_BYTES(2), st>>>(b, lc, n_mlp);
+        return mon_launch_chain(MON_PDL_MLP, k_mlp_train_tc<2>, dim3(n_ctas), dim3(TC_THREADS), TC_SMEM_BYTES(2), st, b, lc, n_mlp);
     } else {
         return cudaErrorNotSupported;
     }

@@ -91,6 +91,8 @@ k_optimizer_sweep(MonOpt o, MonCtrl* __restrict__ ctrl, float* __restrict__ pf, 
                   __half* __restrict__ gh, const float* __restrict__ mlp_partials, float* __restrict__ m,
                   float* __restrict__ v, uint32_t* __restrict__ ps, __half* __restrict__ ema,
                   const float* __restrict__ loss, uint32_t R, MonGrid grid, __half* __restrict__ planar) {
+    mon_pdl_wait();       // the gradient scatter has completed
+    mon_pdl_trigger();
     if (ctrl->skip) return;
     if (blockIdx.x == gridDim.x - 1) {
         // logged loss in the sweep's last (mostly idle) CTA: fixed summation order -> reproducible
@@ -233,7 +235,8 @@ void mon_launch_optimizer(const MonOpt& o, MonCtrl* ctrl, float* pf, __half* ph,
                           __half* planar, cudaStream_t st) {
     const uint32_t n_mlp_ctas = o.n_mlp / (OPT_PER_THREAD * (OPT_THREADS / 32));
     const uint32_t grid_quads = (o.n_params - o.n_mlp + OPT_PER_THREAD - 1) / OPT_PER_THREAD;
-    k_optimizer_sweep<<<n_mlp_ctas + (grid_quads + OPT_THREADS - 1) / OPT_THREADS, OPT_THREADS, 0, st>>>(o, ctrl, pf, ph, gh, partials, m, v, ps, ema, loss, R, grid, planar);
+    mon_launch_chain(MON_PDL_OPTIM, k_optimizer_sweep, dim3(n_mlp_ctas + (grid_quads + OPT_THREADS - 1) / OPT_THREADS), dim3(OPT_THREADS), 0, st, o, ctrl, pf, ph, gh, partials, m,
+                     v, ps, ema, loss, R, grid, planar);
 }
 void mon_launch_snapshot_grad(uint32_t n, uint32_t n_mlp, uint32_t n_partials, const __half* gh, const float* partials, float* out, cudaStream_t st) {
     k_snapshot_grad<<<(n + 255) / 256, 256, 0, st>>>(n, n_mlp, n_partials, gh, partials, out);

@@ -18,6 +18,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <mutex>
@@ -32,6 +33,17 @@
 #define MON_GRAPH_CHUNK 50   // iterations captured per replayed graph (plus a 1-iteration graph for remainders)
 
 static thread_local std::string g_err;
+
+unsigned mon_pdl_mask() {   // A/B switch for the programmatic-dependent-launch chain (mon_kernels.h)
+    static const unsigned mask = [] {
+        if (std::getenv("MON_NO_PDL")) return 0u;
+        const char* m = std::getenv("MON_PDL_MASK");
+        // measured on B200 (profiles/r1g_pdl_ab.txt): encode, fused MLP and optimizer gain from the overlap (+3 %), the
+        // 1024-CTA scatter loses 7 % when its CTAs become resident early, sample points is neutral
+        return m ? (unsigned)std::atoi(m) : (unsigned)(MON_PDL_ENCODE | MON_PDL_MLP | MON_PDL_OPTIM);
+    }();
+    return mask;
+}
 
 static int fail(int code, const char* fmt, ...) {
     char buf[512];

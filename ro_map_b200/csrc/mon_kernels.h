@@ -19,6 +19,39 @@ inline cudaError_t mon_once_per_device(std::atomic<uint64_t>& done_mask, F&& f) 
     return e;
 }
 
+// Programmatic dependent launch.  The kernels of one iteration form a chain on the object's stream; each is launched
+// with cudaLaunchAttributeProgrammaticStreamSerialization so that its CTAs may become resident (and run their
+// prologue: barrier init, TMEM allocation, weight staging) while the previous kernel drains, and each executes
+//     mon_pdl_wait();      // griddepcontrol.wait: the previous kernel of the chain has COMPLETED, memory visible
+//     mon_pdl_trigger();   // griddepcontrol.launch_dependents: the next kernel may start its prologue
+// in that order, on every thread, before any early return and before touching anything the predecessor wrote.
+// Because the trigger comes after the wait, a kernel's pre-wait prologue only ever overlaps its immediate
+// predecessor; everything older is complete and may be read there.  Captured into the iteration graphs as
+// programmatic edges; without the attribute (MON_NO_PDL=1) both instructions are no-ops.
+#ifdef __CUDACC__
+__device__ __forceinline__ void mon_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void mon_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+// mon_core.cu: bit set = that kernel is launched with the attribute.  All on by default; MON_NO_PDL=1 clears all,
+// MON_PDL_MASK=<int> selects (A/B measurements).
+enum { MON_PDL_POINTS = 1, MON_PDL_ENCODE = 2, MON_PDL_MLP = 4, MON_PDL_SCATTER = 8, MON_PDL_OPTIM = 16 };
+unsigned mon_pdl_mask();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t mon_launch_chain(unsigned which, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (mon_pdl_mask() & which) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // kernels_batch.cu
 void mon_launch_generate_batch(const MonBatch& b, const MonScene& sc, cudaStream_t st);
 void mon_launch_render_rays(uint32_t n_rays, mon_bbox2d box, const MonScene& sc, const float* Twc_dev,

@@ -292,6 +292,23 @@ def run_ours(args, rank, world, local_rank):
 
     # ---------------- per-stage device times for the roofline (live, CUDA events between kernels), rank 0 / first object
     stages = nerfs[0].train_profiled(50) if nerfs else {}
+
+    # ---------------- rendered rays/s (BASELINE.json's second metric): NeRF_Model::Render of one full 800x800 view per
+    # object with the inference (EMA) weights, 64 samples per ray, through the C ABI into host buffers (D2H included)
+    render = None
+    if nerfs:
+        full = (0, 0, 0, seq.H, seq.W)
+        nerfs[0].render(full, seq.poses[0])                          # warm-up (workspace allocation)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n_views = 3
+        for v in range(n_views):
+            for n in nerfs:
+                n.render(full, seq.poses[v % len(seq.poses)])
+        render_s = time.perf_counter() - t0
+        render = {"rays_per_s": len(nerfs) * n_views * seq.H * seq.W / render_s, "samples_per_ray": int(cfg.render_samples_per_ray),
+                  "view": f"{seq.W}x{seq.H}", "ms_per_view": 1e3 * render_s / (n_views * len(nerfs)),
+                  "region": "mon_object_render: rays + 64 samples/ray + encode + MLP + compositing + 10 MB D2H, wall clock"}
     for n in nerfs:
         n.close()
 
@@ -363,6 +380,7 @@ def run_ours(args, rank, world, local_rank):
         "dtype": "f16 storage / f32 accumulate", "data": "synthetic", "config": workload_config(args, n_objects),
         "iters_per_s_per_object": iters_per_s / max(n_objects, 1),
         "rays_per_s": iters_per_s * R, "points_per_s": iters_per_s * N, "final_loss": loss,
+        "render": render,
         "clocks": clocks.summary(),
         "e2e": {"value": n_objects * K / e2e_s, "unit": "iters/s", "h2d_bytes_per_step": h2d / (n_objects * K), "d2h_bytes_per_step": 48.0 / K,
                 "seconds": e2e_s, "final_loss": losses_e2e[0] if losses_e2e else None,

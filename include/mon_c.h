@@ -141,6 +141,10 @@ int mon_object_launch_count(mon_object* obj, uint64_t* n);
  * (z-depth), mask[h*w].  rand_dt: h*w*render_samples floats in (0,1] or NULL (internal RNG). */
 int mon_object_render(mon_object* obj, mon_bbox2d box, const float Twc[16], int use_ema,
                       const float* rand_dt, float* rgb, float* depth, float* mask);
+/* One view of NeRF_Model::RenderVideo (nerf_model.cu:1832-1991; rays as GenerateRenderVideoRays :495-533): same
+ * renderer, but the pose is camera -> OBJECT frame (Toc, e.g. from GenerateToc :2186-2205): ObjTow is not applied. */
+int mon_object_render_object_centric(mon_object* obj, mon_bbox2d box, const float Toc[16], int use_ema,
+                                     const float* rand_dt, float* rgb, float* depth, float* mask);
 /* GetDensityOnGrid (nerf_model.cu:2007-2043): raw sigma logit on a res^3 lattice of the AABB, inference (EMA)
  * weights like the reference; x fastest.  out: res[0]*res[1]*res[2] floats on the host.  Input of marching cubes. */
 int mon_object_density_grid(mon_object* obj, const uint32_t res[3], float* out);

@@ -197,7 +197,8 @@ class NerfObject:
         return n.value
 
     # ---- NeRF_Model::Render
-    def render(self, box, Twc, use_ema: bool = True, rand_dt=None):
+    def render(self, box, Twc, use_ema: bool = True, rand_dt=None, object_centric: bool = False):
+        """object_centric: Twc is a camera -> OBJECT pose (one view of RenderVideo, nerf_model.cu:1832-1991)."""
         fid, x, y, h, w = [int(v) for v in box]
         n = h * w
         rgb = np.empty((h, w, 3), np.float32)
@@ -205,8 +206,9 @@ class NerfObject:
         mask = np.empty((h, w), np.float32)
         twc = _mat16(Twc)
         jit = None if rand_dt is None else _f32(rand_dt, (n, self.cfg.render_samples_per_ray))
-        check(self._lib.mon_object_render(self._h, Bbox2d(fid, x, y, h, w), twc.ctypes.data_as(C.POINTER(C.c_float)), int(use_ema),
-                                           None if jit is None else _ptr(jit), _ptr(rgb), _ptr(depth), _ptr(mask)))
+        fn = self._lib.mon_object_render_object_centric if object_centric else self._lib.mon_object_render
+        check(fn(self._h, Bbox2d(fid, x, y, h, w), twc.ctypes.data_as(C.POINTER(C.c_float)), int(use_ema),
+                 None if jit is None else _ptr(jit), _ptr(rgb), _ptr(depth), _ptr(mask)))
         return rgb, depth, mask
 
     def density_grid(self, res=(64, 64, 64)) -> np.ndarray:

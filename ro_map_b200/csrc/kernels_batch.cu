@@ -188,16 +188,21 @@ __global__ void k_render_rays(uint32_t n_rays, mon_bbox2d box, MonScene sc, cons
     in_box[i] = hit ? 1 : 0;
 }
 
-void mon_launch_generate_batch(const MonBatch& b, const MonScene& sc, cudaStream_t st) {
+void mon_launch_generate_batch(const MonBatch& b, const MonScene& sc, cudaStream_t st, const MonLaunchOpt& lo) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(BATCH_CTAS);
     cfg.blockDim = dim3(BATCH_THREADS);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = BATCH_CTAS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    if (lo.set_priority) {
+        attr[1].id = cudaLaunchAttributePriority;
+        attr[1].val.priority = lo.priority;
+        cfg.numAttrs = 2;
+    }
     cudaLaunchKernelEx(&cfg, k_generate_batch, b, sc);
 }
 void mon_launch_render_rays(uint32_t n_rays, mon_bbox2d box, const MonScene& sc, const float* Twc_dev,

@@ -54,8 +54,8 @@ k_sample_points(uint32_t n_points, uint32_t S, const MonRay* __restrict__ rays, 
 
 void mon_launch_sample_points(uint32_t n_points, uint32_t S, const MonRay* rays, const int* in_box, const float* jitter,
                               uint32_t seed, const MonCtrl* ctrl, uint32_t rng_stream, uint32_t iter_fixed,
-                              const float* bmin, const float* bmax, float* pts, cudaStream_t st) {
-    mon_launch_chain(MON_PDL_POINTS, k_sample_points, dim3((n_points + 255) / 256), dim3(256), 0, st, n_points, S, rays, in_box, jitter, seed, ctrl, rng_stream,
+                              const float* bmin, const float* bmax, float* pts, cudaStream_t st, const MonLaunchOpt& lo) {
+    mon_launch_chain(MON_PDL_POINTS, lo, k_sample_points, dim3((n_points + 255) / 256), dim3(256), 0, st, n_points, S, rays, in_box, jitter, seed, ctrl, rng_stream,
                      iter_fixed, bmin[0], bmin[1], bmin[2], bmax[0], bmax[1], bmax[2], pts);
 }
 
@@ -134,7 +134,7 @@ __device__ __forceinline__ void enc_points_pow2(const float* __restrict__ pts, _
 // planar: per level [feature 0 table | feature 1 table], each size[l] fp16 (the level starts at 2*offset[l] halves)
 __global__ void __launch_bounds__(ENC_THREADS, 1)
 k_encode_forward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, const __half* __restrict__ planar,
-                 __half* __restrict__ enc_soa, const MonCtrl* __restrict__ ctrl) {
+                 __half* __restrict__ enc_soa, const MonCtrl* __restrict__ ctrl, uint32_t job_begin, uint32_t job_end) {
     extern __shared__ __align__(128) unsigned char enc_smem[];
     __shared__ __align__(8) uint64_t bar;
     const __half* table = reinterpret_cast<const __half*>(enc_smem);
@@ -145,13 +145,16 @@ k_encode_forward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, co
     mon_pdl_trigger();
     if (ctrl && ctrl->skip) return;
 
-    const uint64_t total = (uint64_t)(2 * g.n_levels) * n_points;
+    // jobs [job_begin, job_end) of the 2 * n_levels (level, feature) jobs: the level-pipelined iteration graph runs the
+    // coarse and the fine half of the levels as two launches (mon_core.cu capture_graph)
+    const uint64_t total = (uint64_t)(job_end - job_begin) * n_points;
     uint64_t w = total * blockIdx.x / gridDim.x;
     const uint64_t w_end = total * (blockIdx.x + 1) / gridDim.x;
     uint32_t phase = 0;
     while (w < w_end) {
-        const uint32_t job = (uint32_t)(w / n_points);
-        const uint32_t p0 = (uint32_t)(w - (uint64_t)job * n_points);
+        const uint32_t job_rel = (uint32_t)(w / n_points);
+        const uint32_t job = job_begin + job_rel;
+        const uint32_t p0 = (uint32_t)(w - (uint64_t)job_rel * n_points);
         const uint32_t p1 = (uint32_t)min((uint64_t)n_points, (uint64_t)p0 + (w_end - w));
         const uint32_t l = job >> 1, f = job & 1;
         const uint32_t size = g.size[l];
@@ -197,7 +200,8 @@ k_encode_forward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, co
 }
 
 cudaError_t mon_launch_encode_forward(const MonGrid& g, uint32_t n_points, const float* pts, const __half* planar, __half* enc_soa,
-                                      const MonCtrl* ctrl, uint32_t sm_count, cudaStream_t st) {
+                                      const MonCtrl* ctrl, uint32_t sm_count, cudaStream_t st, uint32_t level_begin, uint32_t level_end,
+                                      const MonLaunchOpt& lo) {
     static std::atomic<uint64_t> prepared{0};
     const cudaError_t prep = mon_once_per_device(prepared, [] {
         cudaError_t e = cudaFuncSetAttribute(k_encode_forward, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -205,13 +209,15 @@ cudaError_t mon_launch_encode_forward(const MonGrid& g, uint32_t n_points, const
         return cudaFuncSetAttribute(k_encode_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_TABLE_BYTES);
     });
     if (prep != cudaSuccess) return prep;
-    if (n_points == 0) return cudaSuccess;
+    if (level_end > g.n_levels) level_end = g.n_levels;
+    if (n_points == 0 || level_begin >= level_end) return cudaSuccess;
     // every CTA loads up to two 128 KB slices: do not spread tiny batches over the whole chip
-    const uint64_t total = (uint64_t)(2 * g.n_levels) * n_points;
+    const uint64_t total = (uint64_t)(2 * (level_end - level_begin)) * n_points;
     const uint64_t want = (total + 16383) / 16384;
     uint32_t ctas = want < (uint64_t)sm_count ? (uint32_t)want : sm_count;
     if (ctas == 0) ctas = 1;
-    return mon_launch_chain(MON_PDL_ENCODE, k_encode_forward, dim3(ctas), dim3(ENC_THREADS), ENC_TABLE_BYTES, st, g, n_points, pts, planar, enc_soa, ctrl);
+    return mon_launch_chain(MON_PDL_ENCODE, lo, k_encode_forward, dim3(ctas), dim3(ENC_THREADS), ENC_TABLE_BYTES, st, g, n_points, pts, planar, enc_soa, ctrl,
+                            2 * level_begin, 2 * level_end);
 }
 
 // interleaved fp16 weights [entry][2] -> planar per level [f0 table | f1 table] (initialisation / set_params; the
@@ -244,21 +250,22 @@ __device__ __forceinline__ void red_add_f16x2(__half2* addr, __half2 v) {
 // Zero d_enc pairs (samples after the early stop) are skipped: adding +0 is an identity, so the result is unchanged.
 __global__ void __launch_bounds__(SCT_THREADS)
 k_encode_backward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, const MonCtrl* __restrict__ ctrl,
-                  const __half* __restrict__ d_enc, __half* __restrict__ grid_grad) {
+                  const __half* __restrict__ d_enc, __half* __restrict__ grid_grad, uint32_t level_begin, uint32_t level_end) {
     mon_pdl_wait();
     mon_pdl_trigger();
     if (ctrl->skip) return;
     const uint32_t p = threadIdx.x & (SCT_TILE - 1), lg = threadIdx.x >> 7;
     const uint32_t pt = blockIdx.x * SCT_TILE + p;
     if (pt >= n_points) return;
-    const uint4 gv = reinterpret_cast<const uint4*>(d_enc + (size_t)pt * MON_IN)[lg];
+    // levels [level_begin, level_end), level_begin a multiple of 4: thread quarter lg owns levels level_begin + 4*lg + j
+    const uint4 gv = reinterpret_cast<const uint4*>(d_enc + (size_t)pt * MON_IN)[(level_begin >> 2) + lg];
     const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
     if (((gv.x | gv.y | gv.z | gv.w) & 0x7fff7fffu) == 0) return;
     const float u[3] = {__ldg(pts + (size_t)pt * 3), __ldg(pts + (size_t)pt * 3 + 1), __ldg(pts + (size_t)pt * 3 + 2)};
 #pragma unroll
     for (uint32_t j = 0; j < 4; ++j) {
-        const uint32_t l = lg * 4 + j;
-        if (l >= g.n_levels || (gw[j] & 0x7fff7fffu) == 0) continue;
+        const uint32_t l = level_begin + lg * 4 + j;
+        if (l >= level_end || (gw[j] & 0x7fff7fffu) == 0) continue;
         const float g0 = __half2float(__ushort_as_half((unsigned short)(gw[j] & 0xffffu)));
         const float g1 = __half2float(__ushort_as_half((unsigned short)(gw[j] >> 16)));
         const uint32_t size = g.size[l];
@@ -304,7 +311,12 @@ k_encode_backward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, c
 }
 
 void mon_launch_encode_backward(const MonGrid& g, uint32_t n_points, const float* pts, const MonCtrl* ctrl,
-                                const __half* d_enc, __half* grid_grad, cudaStream_t st) {
+                                const __half* d_enc, __half* grid_grad, cudaStream_t st, uint32_t level_begin, uint32_t level_end,
+                                const MonLaunchOpt& lo) {
+    if (level_end > g.n_levels) level_end = g.n_levels;
+    if (level_begin >= level_end || n_points == 0) return;
     const uint32_t blocks = (n_points + SCT_TILE - 1) / SCT_TILE;
-    mon_launch_chain(MON_PDL_SCATTER, k_encode_backward, dim3(blocks), dim3(SCT_THREADS), 0, st, g, n_points, pts, ctrl, d_enc, grid_grad);
+    const uint32_t quarters = (level_end - level_begin + 3) / 4;     // 128 threads (one point each) per 4 levels
+    mon_launch_chain(MON_PDL_SCATTER, lo, k_encode_backward, dim3(blocks), dim3(SCT_TILE * quarters), 0, st, g, n_points, pts, ctrl, d_enc, grid_grad,
+                     level_begin, level_end);
 }

@@ -610,17 +610,18 @@ static cudaError_t tc_prepare(K kernel, int smem_bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
 }
 
-cudaError_t mon_launch_mlp_train_tc(const MonBatch& b, const MonLossCfg& lc, uint32_t n_hidden, uint32_t n_mlp, uint32_t n_ctas, cudaStream_t st) {
+cudaError_t mon_launch_mlp_train_tc(const MonBatch& b, const MonLossCfg& lc, uint32_t n_hidden, uint32_t n_mlp, uint32_t n_ctas, cudaStream_t st,
+                                    const MonLaunchOpt& lo) {
     if (n_hidden == 1) {
         static std::atomic<uint64_t> prepared{0};
         const cudaError_t prep = mon_once_per_device(prepared, [] { return tc_prepare(k_mlp_train_tc<1>, TC_SMEM_BYTES(1)); });
         if (prep != cudaSuccess) return prep;
-        return mon_launch_chain(MON_PDL_MLP, k_mlp_train_tc<1>, dim3(n_ctas), dim3(TC_THREADS), TC_SMEM_BYTES(1), st, b, lc, n_mlp);
+        return mon_launch_chain(MON_PDL_MLP, lo, k_mlp_train_tc<1>, dim3(n_ctas), dim3(TC_THREADS), TC_SMEM_BYTES(1), st, b, lc, n_mlp);
     } else if (n_hidden == 2) {
         static std::atomic<uint64_t> prepared{0};
         const cudaError_t prep = mon_once_per_device(prepared, [] { return tc_prepare(k_mlp_train_tc<2>, TC_SMEM_BYTES(2)); });
         if (prep != cudaSuccess) return prep;
-        return mon_launch_chain(MON_PDL_MLP, k_mlp_train_tc<2>, dim3(n_ctas), dim3(TC_THREADS), TC_SMEM_BYTES(2), st, b, lc, n_mlp);
+        return mon_launch_chain(MON_PDL_MLP, lo, k_mlp_train_tc<2>, dim3(n_ctas), dim3(TC_THREADS), TC_SMEM_BYTES(2), st, b, lc, n_mlp);
     } else {
         return cudaErrorNotSupported;
     }

@@ -90,11 +90,12 @@ __global__ void __launch_bounds__(OPT_THREADS, 6)
 k_optimizer_sweep(MonOpt o, MonCtrl* __restrict__ ctrl, float* __restrict__ pf, __half* __restrict__ ph,
                   __half* __restrict__ gh, const float* __restrict__ mlp_partials, float* __restrict__ m,
                   float* __restrict__ v, uint32_t* __restrict__ ps, __half* __restrict__ ema,
-                  const float* __restrict__ loss, uint32_t R, MonGrid grid, __half* __restrict__ planar) {
+                  const float* __restrict__ loss, uint32_t R, MonGrid grid, __half* __restrict__ planar,
+                  uint32_t n_mlp_ctas, uint32_t do_loss, uint32_t grid_i4_begin, uint32_t grid_i4_end) {
     mon_pdl_wait();       // the gradient scatter has completed
     mon_pdl_trigger();
     if (ctrl->skip) return;
-    if (blockIdx.x == gridDim.x - 1) {
+    if (do_loss && blockIdx.x == gridDim.x - 1) {
         // logged loss in the sweep's last (mostly idle) CTA: fixed summation order -> reproducible
         __shared__ float s_loss[OPT_THREADS];
         float a = 0.0f;
@@ -108,10 +109,10 @@ k_optimizer_sweep(MonOpt o, MonCtrl* __restrict__ ctrl, float* __restrict__ pf, 
         if (threadIdx.x == 0) ctrl->loss_mean = s_loss[0] / (float)R;
     }
     const float lr_base = ctrl->lr_base, old_db = ctrl->ema_old, new_db = ctrl->ema_new;
-    // CTA layout: the first n_mlp/32 CTAs own the MLP weights (one WARP per 4 parameters: the lanes split the
-    // per-CTA gradient partials of the fused MLP kernel), every other CTA owns 1024 consecutive grid parameters
-    // (one THREAD per 4 parameters).  n_params and n_mlp are multiples of 32 resp. 4.
-    const uint32_t n_mlp_ctas = o.n_mlp / (OPT_PER_THREAD * (OPT_THREADS / 32));
+    // CTA layout: the first n_mlp_ctas (n_mlp/32, or 0 in a grid-only launch) CTAs own the MLP weights (one WARP per 4
+    // parameters: the lanes split the per-CTA gradient partials of the fused MLP kernel), every other CTA owns 1024
+    // consecutive parameters of [grid_i4_begin, grid_i4_end) (one THREAD per 4 parameters).  n_params and n_mlp are
+    // multiples of 32 resp. 4; the level-pipelined graph launches one sweep per level group + one for the MLP weights.
     const bool is_mlp = blockIdx.x < n_mlp_ctas;
     uint32_t i4;
     float g[4];
@@ -143,8 +144,8 @@ k_optimizer_sweep(MonOpt o, MonCtrl* __restrict__ ctrl, float* __restrict__ pf, 
         *gw = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));   // kept for inspection
         g[0] = __low2float(a); g[1] = __high2float(a); g[2] = __low2float(b); g[3] = __high2float(b);
     } else {
-        i4 = o.n_mlp + ((blockIdx.x - n_mlp_ctas) * OPT_THREADS + threadIdx.x) * OPT_PER_THREAD;
-        if (i4 >= o.n_params) return;
+        i4 = grid_i4_begin + ((blockIdx.x - n_mlp_ctas) * OPT_THREADS + threadIdx.x) * OPT_PER_THREAD;
+        if (i4 >= grid_i4_end) return;
         gw = reinterpret_cast<uint2*>(gh + i4);
         const uint2 raw = *gw;
         wraw = *reinterpret_cast<const uint2*>(ph + i4);
@@ -232,11 +233,23 @@ void mon_launch_cast_params(uint32_t n, const float* pf, __half* ph, cudaStream_
 }
 void mon_launch_optimizer(const MonOpt& o, MonCtrl* ctrl, float* pf, __half* ph, __half* gh, const float* partials,
                           float* m, float* v, uint32_t* ps, __half* ema, const float* loss, uint32_t R, const MonGrid& grid,
-                          __half* planar, cudaStream_t st) {
-    const uint32_t n_mlp_ctas = o.n_mlp / (OPT_PER_THREAD * (OPT_THREADS / 32));
-    const uint32_t grid_quads = (o.n_params - o.n_mlp + OPT_PER_THREAD - 1) / OPT_PER_THREAD;
-    mon_launch_chain(MON_PDL_OPTIM, k_optimizer_sweep, dim3(n_mlp_ctas + (grid_quads + OPT_THREADS - 1) / OPT_THREADS), dim3(OPT_THREADS), 0, st, o, ctrl, pf, ph, gh, partials, m,
-                     v, ps, ema, loss, R, grid, planar);
+                          __half* planar, cudaStream_t st, int part, uint32_t level_begin, uint32_t level_end, const MonLaunchOpt& lo) {
+    // part: MON_OPT_ALL everything (MLP weights + loss + whole grid); MON_OPT_MLP the MLP weights and the logged loss only;
+    // MON_OPT_GRID the grid parameters of levels [level_begin, level_end) only
+    if (level_end > grid.n_levels) level_end = grid.n_levels;
+    const bool with_mlp = part != MON_OPT_GRID, with_grid = part != MON_OPT_MLP;
+    const uint32_t n_mlp_ctas = with_mlp ? o.n_mlp / (OPT_PER_THREAD * (OPT_THREADS / 32)) : 0u;
+    uint32_t i4_begin = 0, i4_end = 0;
+    if (with_grid) {
+        i4_begin = o.n_mlp + 2u * grid.offset[part == MON_OPT_ALL ? 0u : level_begin];
+        i4_end = part == MON_OPT_ALL ? o.n_params : o.n_mlp + 2u * grid.offset[level_end];
+    }
+    const uint32_t grid_quads = (i4_end - i4_begin + OPT_PER_THREAD - 1) / OPT_PER_THREAD;
+    // a grid-less launch still needs the (otherwise idle) last CTA that reduces the logged loss
+    const uint32_t n_grid_ctas = with_grid ? (grid_quads + OPT_THREADS - 1) / OPT_THREADS : 1u;
+    if (n_mlp_ctas + n_grid_ctas == 0) return;
+    mon_launch_chain(MON_PDL_OPTIM, lo, k_optimizer_sweep, dim3(n_mlp_ctas + n_grid_ctas), dim3(OPT_THREADS), 0, st, o, ctrl, pf, ph, gh, partials, m,
+                     v, ps, ema, loss, R, grid, planar, n_mlp_ctas, with_mlp ? 1u : 0u, i4_begin, i4_end);
 }
 void mon_launch_snapshot_grad(uint32_t n, uint32_t n_mlp, uint32_t n_partials, const __half* gh, const float* partials, float* out, cudaStream_t st) {
     k_snapshot_grad<<<(n + 255) / 256, 256, 0, st>>>(n, n_mlp, n_partials, gh, partials, out);

@@ -217,6 +217,11 @@ struct mon_object {
     // execution
     cudaStream_t stream = nullptr, aux = nullptr;   // aux: next iteration's batch + sample points, forked inside the graphs
     cudaEvent_t ev_fork_m = nullptr, ev_fork_s = nullptr, ev_join = nullptr;
+    // level-pipelined graph (capture_graph_pipelined): one branch stream per level group of the scatter / optimizer
+    cudaStream_t grp[MON_PIPE_GROUPS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_grp[MON_PIPE_GROUPS] = {nullptr, nullptr, nullptr, nullptr}, ev_pts = nullptr, ev_aux = nullptr;
+    float* pts_alt = nullptr;         // second sample-position buffer: P(i+1) runs while S(i) still reads the first
+    int prio_hi = 0, prio_lo = 0;     // stream priority range of the device (hi = numerically lowest)
     cudaGraphExec_t graph1 = nullptr, graphN = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timing_pending = false;
@@ -575,7 +580,11 @@ static int enqueue_iteration(mon_object* o, const MonBatch& b, bool snapshot_gra
     return MON_OK;
 }
 
+static int capture_graph_pipelined(mon_object* o, int iters, cudaGraphExec_t* out);
+static int pipe_mode();
+
 static int capture_graph(mon_object* o, int iters, cudaGraphExec_t* out) {
+    if (pipe_mode() != 0) return capture_graph_pipelined(o, iters, out);
     const MonBatch b = make_batch(o, false, false);
     cudaGraph_t g = nullptr;
     cudaStream_t st = o->stream, aux = o->aux;
@@ -613,7 +622,120 @@ static int capture_graph(mon_object* o, int iters, cudaGraphExec_t* out) {
     return MON_OK;
 }
 
-static const int kKernelsPerIter = 6;
+// Level-pipelined iteration graph (default; MON_PIPE=0 selects the chain above).  The hash-grid levels are independent
+// between the end of the fused MLP kernel of iteration i and the start of the one of iteration i+1: the gradient of a
+// level is scattered (S), consumed by the optimizer (O) and the level is re-encoded (E) without touching any other
+// level.  So the S -> O -> E chain is cut by level group and the pieces overlap:
+//
+//   main :  M(i) -> S0 -> O0 ---------+-> E[0,h)(i+1) ----+-> E[h,L)(i+1) -> M(i+1)
+//   grp1 :      \-> S1 -> O1 --------/                   |
+//   grp2 :      \-> S2 -> O2 ---------------------------+
+//   grp3 :      \-> S3 -> O3 ---------------------------+
+//   aux  :      \-> B(i+1) -> P(i+1) -> (E waits) -> O_mlp(i) -> (M(i+1) waits)
+//
+// S0..S3 become ready together; node priorities dispatch their CTAs in group order, so O0 (and then the coarse half of
+// the next encode) starts while the finer groups are still scattering.  The scatter is bound by L2 atomics, the
+// encode by issue slots and shared-memory banks, the optimizer by L2/HBM bandwidth: they overlap instead of queueing.
+// P(i+1) writes the other sample-position buffer because S(i) is still reading the current one.  Every graph starts
+// with its own B, P into buffer 0, so no buffer parity survives between graph launches.
+static int pipe_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("MON_PIPE");
+        mode = e ? atoi(e) : 1;
+        if (mode < 0 || mode > 3) mode = 1;
+    }
+    return mode;
+}
+
+static int capture_graph_pipelined(mon_object* o, int iters, cudaGraphExec_t* out) {
+    const MonBatch b = make_batch(o, false, false);
+    const uint32_t L = o->grid.n_levels;
+    const uint32_t per = ((L + MON_PIPE_GROUPS - 1) / MON_PIPE_GROUPS + 3) / 4 * 4;   // levels per scatter group, multiple of 4
+    const uint32_t n_groups = (L + per - 1) / per;
+    const uint32_t half_groups = (n_groups + 1) / 2;                                   // groups feeding the first encode launch
+    const uint32_t h = std::min(L, half_groups * per);
+    const int mode = pipe_mode();
+    // mode 1: group k at priority hi+k, encode/MLP/batch at hi; mode 2: encode below every scatter group; mode 3: no priorities
+    auto prio = [&](int rank) {
+        MonLaunchOpt lo;
+        lo.pdl = false;
+        if (mode != 3) { lo.set_priority = true; lo.priority = std::min(o->prio_lo, o->prio_hi + rank); }
+        return lo;
+    };
+    auto with_pdl = [](MonLaunchOpt lo) { lo.pdl = true; return lo; };
+    const int enc_rank = mode == 2 ? (int)n_groups : 0;
+    cudaGraph_t g = nullptr;
+    cudaStream_t st = o->stream, aux = o->aux;
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    cudaError_t e = cudaSuccess;
+    float* pts_cur = o->pts;
+    float* pts_nxt = o->pts_alt;
+#define PE(x) do { if (e == cudaSuccess) e = (x); } while (0)
+    mon_launch_generate_batch(b, o->scene, st, prio(0));
+    mon_launch_sample_points(o->N, MON_S, o->rays, nullptr, nullptr, o->seed, o->ctrl, 2, 0, o->scene.bmin, o->scene.bmax, pts_cur, st, with_pdl(prio(0)));
+    PE(mon_launch_encode_forward(o->grid, o->N, pts_cur, o->ph_planar, o->enc, o->ctrl, (uint32_t)o->sm_count, st, 0, L, with_pdl(prio(enc_rank))));
+    for (int i = 0; i < iters && e == cudaSuccess; ++i) {
+        const bool more = i + 1 < iters;
+        PE(mon_launch_mlp_train_tc(b, o->lc, o->cfg.n_hidden_layers, o->n_mlp, o->n_ctas, st, with_pdl(prio(0))));
+        PE(cudaEventRecord(o->ev_fork_m, st));
+        // aux: next batch + sample positions, then the MLP-weight part of the optimizer (+ logged loss)
+        PE(cudaStreamWaitEvent(aux, o->ev_fork_m, 0));
+        if (more) {
+            mon_launch_generate_batch(b, o->scene, aux, prio(0));
+            mon_launch_sample_points(o->N, MON_S, o->rays, nullptr, nullptr, o->seed, o->ctrl, 2, 0, o->scene.bmin, o->scene.bmax, pts_nxt, aux, with_pdl(prio(0)));
+            PE(cudaEventRecord(o->ev_pts, aux));
+        }
+        mon_launch_optimizer(o->opt, o->ctrl_late, o->pf, o->ph, o->gh, o->partials, o->m, o->v, o->ps, o->ema, o->loss, o->R, o->grid, o->ph_planar, aux,
+                             MON_OPT_MLP, 0, 0, prio(0));
+        PE(cudaEventRecord(o->ev_aux, aux));
+        // level groups: scatter -> optimizer, group 0 on the main stream
+        for (uint32_t k = 0; k < n_groups; ++k) {
+            cudaStream_t gs = k == 0 ? st : o->grp[k];
+            const uint32_t l0 = k * per, l1 = std::min(L, l0 + per);
+            if (k) PE(cudaStreamWaitEvent(gs, o->ev_fork_m, 0));
+            mon_launch_encode_backward(o->grid, o->N, pts_cur, o->ctrl_late, o->d_enc, o->gh + o->n_mlp, gs, l0, l1, prio((int)k));
+            mon_launch_optimizer(o->opt, o->ctrl_late, o->pf, o->ph, o->gh, o->partials, o->m, o->v, o->ps, o->ema, o->loss, o->R, o->grid, o->ph_planar, gs,
+                                 MON_OPT_GRID, l0, l1, with_pdl(prio((int)k)));
+            if (k) PE(cudaEventRecord(o->ev_grp[k], gs));
+        }
+        if (more) {
+            // coarse half of the next encode once its groups' weights are final, fine half after the rest
+            for (uint32_t k = 1; k < half_groups; ++k) PE(cudaStreamWaitEvent(st, o->ev_grp[k], 0));
+            PE(cudaStreamWaitEvent(st, o->ev_pts, 0));
+            PE(mon_launch_encode_forward(o->grid, o->N, pts_nxt, o->ph_planar, o->enc, o->ctrl, (uint32_t)o->sm_count, st, 0, h, prio(enc_rank)));
+            for (uint32_t k = half_groups; k < n_groups; ++k) PE(cudaStreamWaitEvent(st, o->ev_grp[k], 0));
+            PE(cudaStreamWaitEvent(st, o->ev_aux, 0));
+            if (h < L) PE(mon_launch_encode_forward(o->grid, o->N, pts_nxt, o->ph_planar, o->enc, o->ctrl, (uint32_t)o->sm_count, st, h, L, prio(enc_rank)));
+            std::swap(pts_cur, pts_nxt);
+        } else {
+            for (uint32_t k = 1; k < n_groups; ++k) PE(cudaStreamWaitEvent(st, o->ev_grp[k], 0));
+            PE(cudaStreamWaitEvent(st, o->ev_aux, 0));
+        }
+    }
+#undef PE
+    cudaError_t e2 = cudaStreamEndCapture(st, &g);
+    if (e != cudaSuccess) { if (g) cudaGraphDestroy(g); return fail(MON_ERR_CUDA, "graph capture: %s", cudaGetErrorString(e)); }
+    if (e2 != cudaSuccess) return fail(MON_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e2));
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { cudaGraphDestroy(g); return fail(MON_ERR_CUDA, "graph capture launch: %s", cudaGetErrorString(e)); }
+    e = cudaGraphInstantiate(out, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(MON_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    return MON_OK;
+}
+
+// kernels launched by one replay of an `iters`-iteration graph
+static uint64_t launches_in_graph(const mon_object* o, uint32_t iters) {
+    if (iters == 0) return 0;
+    if (pipe_mode() == 0) return 6ull * iters;
+    const uint32_t L = o->grid.n_levels;
+    const uint32_t per = ((L + MON_PIPE_GROUPS - 1) / MON_PIPE_GROUPS + 3) / 4 * 4;
+    const uint32_t n_groups = (L + per - 1) / per;
+    const uint32_t n_enc = std::min(L, (n_groups + 1) / 2 * per) < L ? 2u : 1u;
+    // B, P, E once; per iteration M, O_mlp, S + O per level group; per follow-up iteration B, P and the split encode
+    return 3ull + (uint64_t)iters * (2u + 2u * n_groups) + (uint64_t)(iters - 1) * (2u + n_enc);
+}
 
 int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uint8_t instance_id,
                       const float obj_Tow[16], const float bmin[3], const float bmax[3], mon_object** out) {
@@ -670,7 +792,7 @@ int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uin
     OALLOC(o->rays, R * sizeof(MonRay)); OALLOC(o->ray_inst, R);
     OALLOC(o->target, R * 12); OALLOC(o->target_depth, R * 4); OALLOC(o->bg, R * 12);
     OALLOC(o->rgb_rays, R * 12); OALLOC(o->depth_rays, R * 4); OALLOC(o->mask_rays, R * 4); OALLOC(o->loss, R * 4);
-    OALLOC(o->pts, N * 12); OALLOC(o->enc, N * MON_IN * 2); OALLOC(o->d_enc, N * MON_IN * 2);
+    OALLOC(o->pts, N * 12); OALLOC(o->pts_alt, N * 12); OALLOC(o->enc, N * MON_IN * 2); OALLOC(o->d_enc, N * MON_IN * 2);
     OALLOC(o->ph_planar, (size_t)o->n_grid * 2 + 16);
     OALLOC(o->partials, (size_t)o->n_ctas * o->n_mlp * 4);
 #undef OALLOC
@@ -681,9 +803,19 @@ int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uin
         (e = cudaEventCreateWithFlags(&o->ev_fork_m, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&o->ev_fork_s, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&o->ev_join, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&o->ev_pts, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&o->ev_aux, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaDeviceGetStreamPriorityRange(&o->prio_lo, &o->prio_hi)) != cudaSuccess ||
         (e = cudaEventCreate(&o->ev0)) != cudaSuccess || (e = cudaEventCreate(&o->ev1)) != cudaSuccess) {
         mon_object_destroy(o);
         return fail(MON_ERR_CUDA, "object setup: %s", cudaGetErrorString(e));
+    }
+    for (int k = 0; k < MON_PIPE_GROUPS; ++k) {
+        if ((e = cudaStreamCreateWithFlags(&o->grp[k], cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&o->ev_grp[k], cudaEventDisableTiming)) != cudaSuccess) {
+            mon_object_destroy(o);
+            return fail(MON_ERR_CUDA, "object setup: %s", cudaGetErrorString(e));
+        }
     }
     memset(o->h_ctrl, 0, sizeof(MonCtrl));
 
@@ -727,7 +859,7 @@ int mon_object_destroy(mon_object* o) {
     if (o->stream) cudaStreamSynchronize(o->stream);
     drop_graphs(o);
     void* ptrs[] = {o->pf, o->m, o->v, o->ps, o->ph, o->gh, o->ema, o->ctrl, o->ctrl_late, o->d_boxes, o->rays, o->ray_inst, o->target,
-                    o->target_depth, o->bg, o->rgb_rays, o->depth_rays, o->mask_rays, o->loss, o->pts, o->enc, o->d_enc, o->ph_planar, o->partials,
+                    o->target_depth, o->bg, o->rgb_rays, o->depth_rays, o->mask_rays, o->loss, o->pts, o->pts_alt, o->enc, o->d_enc, o->ph_planar, o->partials,
                     o->dbg_out, o->dbg_dout, o->inj_xy, o->inj_col, o->inj_dt, o->grad_snap, o->r_rays, o->r_inbox, o->r_enc,
                     o->r_jit, o->r_rgb, o->r_depth, o->r_mask, o->r_Twc, o->r_pts, o->r_planar};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -737,6 +869,12 @@ int mon_object_destroy(mon_object* o) {
     if (o->ev_fork_m) cudaEventDestroy(o->ev_fork_m);
     if (o->ev_fork_s) cudaEventDestroy(o->ev_fork_s);
     if (o->ev_join) cudaEventDestroy(o->ev_join);
+    if (o->ev_pts) cudaEventDestroy(o->ev_pts);
+    if (o->ev_aux) cudaEventDestroy(o->ev_aux);
+    for (int k = 0; k < MON_PIPE_GROUPS; ++k) {
+        if (o->ev_grp[k]) cudaEventDestroy(o->ev_grp[k]);
+        if (o->grp[k]) cudaStreamDestroy(o->grp[k]);
+    }
     if (o->aux) cudaStreamDestroy(o->aux);
     if (o->stream) cudaStreamDestroy(o->stream);
     delete o;
@@ -809,7 +947,7 @@ int mon_object_train_async(mon_object* o, uint32_t iters) {
     while (left > 0) { CK(cudaGraphLaunch(o->graph1, o->stream)); --left; }
     CK(cudaEventRecord(o->ev1, o->stream));
     o->timing_pending = true;
-    o->launches += (uint64_t)iters * kKernelsPerIter;
+    o->launches += (uint64_t)(iters / MON_GRAPH_CHUNK) * launches_in_graph(o, MON_GRAPH_CHUNK) + (uint64_t)(iters % MON_GRAPH_CHUNK) * launches_in_graph(o, 1);
     o->have_injected = false;
     return MON_OK;
 }
@@ -1099,8 +1237,8 @@ static int ensure_render_ws(mon_object* o, uint32_t n_rays, size_t jitter_floats
     return MON_OK;
 }
 
-int mon_object_render(mon_object* o, mon_bbox2d box, const float Twc[16], int use_ema,
-                      const float* rand_dt, float* rgb, float* depth, float* mask) {
+static int render_impl(mon_object* o, mon_bbox2d box, const float Twc[16], bool object_centric, int use_ema,
+                       const float* rand_dt, float* rgb, float* depth, float* mask) {
     if (!o || !Twc || !rgb || !depth || !mask) return fail(MON_ERR_ARG, "NULL argument");
     if (box.w == 0 || box.h == 0) return fail(MON_ERR_ARG, "empty render box");
     if ((uint64_t)box.w * box.h > (1u << 26)) return fail(MON_ERR_ARG, "render box too large");
@@ -1111,7 +1249,13 @@ int mon_object_render(mon_object* o, mon_bbox2d box, const float Twc[16], int us
     cudaStream_t st = o->stream;
     CK(cudaMemcpyAsync(o->r_Twc, Twc, 64, cudaMemcpyHostToDevice, st));
     if (rand_dt) CK(cudaMemcpyAsync(o->r_jit, rand_dt, (size_t)n_rays * S2 * 4, cudaMemcpyHostToDevice, st));
-    mon_launch_render_rays(n_rays, box, o->scene, o->r_Twc, o->r_rays, o->r_inbox, st);
+    if (object_centric) {   // GenerateRenderVideoRays (nerf_model.cu:495-533): the pose is camera -> OBJECT, no world hop
+        MonScene sc = o->scene;
+        for (int k = 0; k < 16; ++k) sc.Tow[k] = (k % 5 == 0) ? 1.0f : 0.0f;
+        mon_launch_render_rays(n_rays, box, sc, o->r_Twc, o->r_rays, o->r_inbox, st);
+    } else {
+        mon_launch_render_rays(n_rays, box, o->scene, o->r_Twc, o->r_rays, o->r_inbox, st);
+    }
     o->launches += 1;
     const __half* params = use_ema ? o->ema : o->ph;
     const __half* planar = o->ph_planar;
@@ -1140,6 +1284,16 @@ int mon_object_render(mon_object* o, mon_bbox2d box, const float Twc[16], int us
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     return MON_OK;
+}
+
+int mon_object_render(mon_object* o, mon_bbox2d box, const float Twc[16], int use_ema,
+                      const float* rand_dt, float* rgb, float* depth, float* mask) {
+    return render_impl(o, box, Twc, false, use_ema, rand_dt, rgb, depth, mask);
+}
+
+int mon_object_render_object_centric(mon_object* o, mon_bbox2d box, const float Toc[16], int use_ema,
+                                     const float* rand_dt, float* rgb, float* depth, float* mask) {
+    return render_impl(o, box, Toc, true, use_ema, rand_dt, rgb, depth, mask);
 }
 
 // network logits at arbitrary unit-cube positions (device pointer in, device out4 [n][4]); the inference half of

@@ -37,39 +37,62 @@ __device__ __forceinline__ void mon_pdl_trigger() { asm volatile("griddepcontrol
 enum { MON_PDL_POINTS = 1, MON_PDL_ENCODE = 2, MON_PDL_MLP = 4, MON_PDL_SCATTER = 8, MON_PDL_OPTIM = 16 };
 unsigned mon_pdl_mask();
 
+// Per-launch options of the iteration graphs.  pdl = false: no programmatic edge even if the mask allows one (kernels
+// of the level-pipelined graph whose predecessor in the stream is not the producer they wait for).  priority: CUDA
+// stream-priority value recorded on the kernel node (numerically lower = dispatched first), used to order the level
+// groups of the gradient scatter, which all become ready at the same time.
+struct MonLaunchOpt {
+    bool pdl = true;
+    bool set_priority = false;
+    int priority = 0;
+};
+
 template <typename... KArgs, typename... Args>
-inline cudaError_t mon_launch_chain(unsigned which, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+inline cudaError_t mon_launch_chain(unsigned which, const MonLaunchOpt& lo, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                    cudaStream_t st, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    unsigned n = 0;
+    if (lo.pdl && (mon_pdl_mask() & which)) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (lo.set_priority) {
+        attr[n].id = cudaLaunchAttributePriority;
+        attr[n].val.priority = lo.priority;
+        ++n;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = (mon_pdl_mask() & which) ? 1 : 0;
+    cfg.numAttrs = n;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 // kernels_batch.cu
-void mon_launch_generate_batch(const MonBatch& b, const MonScene& sc, cudaStream_t st);
+void mon_launch_generate_batch(const MonBatch& b, const MonScene& sc, cudaStream_t st, const MonLaunchOpt& lo = MonLaunchOpt());
 void mon_launch_render_rays(uint32_t n_rays, mon_bbox2d box, const MonScene& sc, const float* Twc_dev,
                             MonRay* rays, int* in_box, cudaStream_t st);
 
 // kernels_encode.cu
 void mon_launch_sample_points(uint32_t n_points, uint32_t S, const MonRay* rays, const int* in_box, const float* jitter,
                               uint32_t seed, const MonCtrl* ctrl, uint32_t rng_stream, uint32_t iter_fixed,
-                              const float* bmin, const float* bmax, float* pts, cudaStream_t st);
+                              const float* bmin, const float* bmax, float* pts, cudaStream_t st, const MonLaunchOpt& lo = MonLaunchOpt());
+// levels [level_begin, level_end) only (default: all)
 cudaError_t mon_launch_encode_forward(const MonGrid& g, uint32_t n_points, const float* pts, const __half* planar, __half* enc_soa,
-                                      const MonCtrl* ctrl, uint32_t sm_count, cudaStream_t st);
+                                      const MonCtrl* ctrl, uint32_t sm_count, cudaStream_t st, uint32_t level_begin = 0,
+                                      uint32_t level_end = 0xffffffffu, const MonLaunchOpt& lo = MonLaunchOpt());
 void mon_launch_planarize(const MonGrid& g, const __half* inter, __half* planar, cudaStream_t st);
 void mon_launch_encode_backward(const MonGrid& g, uint32_t n_points, const float* pts, const MonCtrl* ctrl,
-                                const __half* d_enc, __half* grid_grad, cudaStream_t st);
+                                const __half* d_enc, __half* grid_grad, cudaStream_t st, uint32_t level_begin = 0,
+                                uint32_t level_end = 0xffffffffu, const MonLaunchOpt& lo = MonLaunchOpt());   // level_begin % 4 == 0
 
 // kernels_mlp_tc.cu (tcgen05 / TMEM product family)
 cudaError_t mon_launch_mlp_train_tc(const MonBatch& b, const MonLossCfg& lc, uint32_t n_hidden, uint32_t n_mlp,
-                                    uint32_t n_ctas, cudaStream_t st);
+                                    uint32_t n_ctas, cudaStream_t st, const MonLaunchOpt& lo = MonLaunchOpt());
 cudaError_t mon_launch_mlp_infer_tc(uint32_t n_points, uint32_t n_hidden, const __half* params, const __half* enc,
                                     float* out4, cudaStream_t st);
 cudaError_t mon_launch_mlp_render_tc(uint32_t n_rays, uint32_t S2, uint32_t n_hidden, const MonRay* rays, const int* in_box, const float* jitter,
@@ -81,6 +104,8 @@ void mon_launch_init_grid(uint64_t state, uint64_t inc, uint32_t n, float* out, 
 void mon_launch_cast_params(uint32_t n, const float* pf, __half* ph, cudaStream_t st);
 void mon_launch_optimizer(const MonOpt& o, MonCtrl* ctrl, float* pf, __half* ph, __half* gh, const float* partials,
                           float* m, float* v, uint32_t* ps, __half* ema, const float* loss, uint32_t R, const MonGrid& grid,
-                          __half* planar, cudaStream_t st);
+                          __half* planar, cudaStream_t st, int part = 0, uint32_t level_begin = 0, uint32_t level_end = 0xffffffffu,
+                          const MonLaunchOpt& lo = MonLaunchOpt());
+enum { MON_OPT_ALL = 0, MON_OPT_MLP = 1, MON_OPT_GRID = 2 };
 void mon_launch_snapshot_grad(uint32_t n, uint32_t n_mlp, uint32_t n_partials, const __half* gh, const float* partials,
                               float* out, cudaStream_t st);

@@ -14,6 +14,7 @@
 #define MON_IN 32         // encoding width = n_levels * 2
 #define MON_OUT 16        // padded output width (tcnn pads 4 -> 16)
 #define MON_MAX_MLP_CTAS 592
+#define MON_PIPE_GROUPS 4      // level groups of the pipelined scatter -> optimizer -> encode chain (mon_core.cu)
 
 // 36-byte POD; same field order as nerf::Ray
 struct MonRay { float o[3], d[3], d_norm, tmin, tmax; };

@@ -32,6 +32,8 @@ public:
     // tools
     void RenderTestImg(const std::string out_path, const std::vector<std::string>& timestamp, const std::vector<Eigen::Matrix4f>& testTwc,
                        const std::vector<FrameIdAndBbox>& testBbox, const float radius);
+    // NeRF_Model::RenderVideo (nerf_model.cu:1832-1991): 60 turn-table views into <folder>/<i>.png
+    void RenderVideo(const std::string img_path_folder, const std::string depth_path_folder, const float radius);
     std::vector<Eigen::Matrix4f> GetTwc();
     BoundingBox GetBoundingBox();
     Eigen::Matrix4f GetObjTow();

@@ -8,6 +8,7 @@
 #include <unistd.h>
 
 #include <chrono>
+#include <cmath>
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
@@ -19,6 +20,7 @@
 #include "nerf_manager.h"
 #include "mesh.h"
 #include "png_io.h"
+#include "pose_math.h"
 
 using std::cerr;
 using std::cout;
@@ -203,8 +205,10 @@ void NeRF_Dataset::UpdateDataGPU(unsigned int CurId, unsigned int FrameNum) {   
     for (auto& m : mvUpdateMutex) m->lock();
     vector<float> flat((size_t)FrameNum * 16);
     for (unsigned int i = 0; i < FrameNum; ++i) memcpy(&flat[(size_t)i * 16], mon_compat::mat16(mvTemp_Update_Pose[i]), 64);
-    const unsigned int first = CurId + 1 >= FrameNum ? CurId + 1 - FrameNum : 0;
+    if (CurId < FrameNum) return;
+    const unsigned int first = CurId - FrameNum;   // `head` of the reference (nerf_data.cu:349)
     if (mon_dataset_update_poses(mpCore, first, FrameNum, flat.data()) != MON_OK) cerr << "pose update: " << mon_last_error() << endl;
+    for (unsigned int i = 0; i < FrameNum && first + i < mvIamgesPose.size(); ++i) mvIamgesPose[first + i] = mvTemp_Update_Pose[i];
     for (auto& m : mvUpdateMutex) m->unlock();
 }
 
@@ -410,17 +414,56 @@ void NeRF::RequestFinish() {
     mCond.notify_all();
 }
 
-// test views -> <out>/<id>/{test_img,test_depth,test_mask}/<stamp>.png + test.txt (nerf.cu:255-404): RGB x255 8U,
-// z-depth x20000 16U, mask x255 8U.  (The 360-degree video and the PLY need the mesh row)
+// float image -> PNG sample exactly like cv::Mat::convertTo(CV_8U / CV_16U, scale): round half to even, saturate
+static inline uint8_t to_u8(float v, float scale) {
+    const float r = std::nearbyint(v * scale);
+    return (uint8_t)(r < 0.0f ? 0.0f : r > 255.0f ? 255.0f : r);
+}
+static inline uint16_t to_u16(float v, float scale) {
+    const float r = std::nearbyint(v * scale);
+    return (uint16_t)(r < 0.0f ? 0.0f : r > 65535.0f ? 65535.0f : r);
+}
+static void write_view_pngs(const string& img_path, const string& depth_path, const string& mask_path, int w, int h,
+                            const vector<float>& rgb, const vector<float>& depth, const vector<float>* mask) {
+    const size_t n = (size_t)w * h;
+    vector<uint8_t> rgb8(n * 3);
+    vector<uint16_t> d16(n);
+    for (size_t p = 0; p < n * 3; ++p) rgb8[p] = to_u8(rgb[p], 255.0f);
+    for (size_t p = 0; p < n; ++p) d16[p] = to_u16(depth[p], 20000.0f);   // "*20000, looks obvious" (nerf.cu:346)
+    png_io::write(img_path, w, h, 3, 8, rgb8.data());
+    png_io::write(depth_path, w, h, 1, 16, d16.data());
+    if (mask) {
+        vector<uint8_t> mask8(n);
+        for (size_t p = 0; p < n; ++p) mask8[p] = to_u8((*mask)[p], 255.0f);
+        png_io::write(mask_path, w, h, 1, 8, mask8.data());
+    }
+}
+// "stamp x y h w tx ty tz qx qy qz qw" with the object-centric camera pose Toc = ObjTow * Twc (nerf.cu:331-336)
+static void write_pose_line(std::ofstream& f, const string& stamp, const FrameIdAndBbox& b, const Eigen::Matrix4f& ObjTow, const Eigen::Matrix4f& Twc) {
+    float Toc[16], q[4];
+    pose_math::mul44(mon_compat::mat16(ObjTow), mon_compat::mat16(Twc), Toc);
+    pose_math::rot_to_quat(Toc, q);
+    f << stamp << " " << b.x << " " << b.y << " " << b.h << " " << b.w << " " << Toc[12] << " " << Toc[13] << " " << Toc[14] << " "
+      << q[0] << " " << q[1] << " " << q[2] << " " << q[3] << endl;
+}
+
+// NeRF::RenderTestImg (nerf.cu:255-404): <out>/<id>/{test_img,test_depth,test_mask}/<stamp>.png + test.txt, train.txt,
+// the 60-view 360-degree video {video_img,video_depth}/<i>.png (NeRF_Model::RenderVideo, nerf_model.cu:1832-1991) and
+// obj.ply.  PNG scaling as the reference: RGB x255 8U, z-depth x20000 16U, mask x255 8U.
 void NeRF::RenderTestImg(const string out_path, const vector<string>& timestamp, const vector<Eigen::Matrix4f>& testTwc,
                          const vector<FrameIdAndBbox>& testBbox, const float radius) {
-    (void)radius;
     const string folder = out_path + "/" + std::to_string(mId);
-    for (const char* sub : {"", "/test_img", "/test_depth", "/test_mask"}) mkdir((folder + sub).c_str(), 0755);
-    std::ofstream ftest(folder + "/test.txt");
-    ftest << "# timestamp x y h w" << endl;
-    for (size_t i = 0; i < testTwc.size() && i < testBbox.size(); ++i) {
+    mkdir(out_path.c_str(), 0755);
+    for (const char* sub : {"", "/test_img", "/test_depth", "/test_mask", "/video_img", "/video_depth"}) mkdir((folder + sub).c_str(), 0755);
+
+    std::ofstream f(folder + "/test.txt");
+    f << std::fixed;
+    f << "#stamp  box.x  box.y  box.h  box.w  tx  ty  tz  qx  qy  qz  qw (object-centric)" << endl;
+    cout << "Render Object " << mId << " test imgs to " << folder << "/test_img ... please wait..." << endl;
+    for (size_t i = 0; i < timestamp.size() && i < testTwc.size() && i < testBbox.size(); ++i) {
         const FrameIdAndBbox& b = testBbox[i];
+        const string& stamp = timestamp[i];
+        write_pose_line(f, stamp, b, mObjTow, testTwc[i]);
         if (b.h == 0 || b.w == 0) continue;
         const size_t n = (size_t)b.h * b.w;
         vector<float> rgb(n * 3), depth(n), mask(n);
@@ -429,21 +472,61 @@ void NeRF::RenderTestImg(const string out_path, const vector<string>& timestamp,
             cerr << "render: " << mon_last_error() << endl;
             continue;
         }
-        vector<uint8_t> rgb8(n * 3), mask8(n);
-        vector<uint16_t> d16(n);
-        for (size_t p = 0; p < n * 3; ++p) rgb8[p] = (uint8_t)std::min(255.0f, std::max(0.0f, rgb[p] * 255.0f + 0.5f));
-        for (size_t p = 0; p < n; ++p) {
-            mask8[p] = (uint8_t)std::min(255.0f, std::max(0.0f, mask[p] * 255.0f + 0.5f));
-            d16[p] = (uint16_t)std::min(65535.0f, std::max(0.0f, depth[p] * 20000.0f + 0.5f));
-        }
-        const string stamp = i < timestamp.size() ? timestamp[i] : std::to_string(i);
-        png_io::write(folder + "/test_img/" + stamp + ".png", (int)b.w, (int)b.h, 3, 8, rgb8.data());
-        png_io::write(folder + "/test_depth/" + stamp + ".png", (int)b.w, (int)b.h, 1, 16, d16.data());
-        png_io::write(folder + "/test_mask/" + stamp + ".png", (int)b.w, (int)b.h, 1, 8, mask8.data());
-        ftest << stamp << " " << b.x << " " << b.y << " " << b.h << " " << b.w << endl;
+        write_view_pngs(folder + "/test_img/" + stamp + ".png", folder + "/test_depth/" + stamp + ".png", folder + "/test_mask/" + stamp + ".png",
+                        (int)b.w, (int)b.h, rgb, depth, &mask);
     }
+    f.close();
+
+    // training views (nerf.cu:364-396): class + box half-extent, then one pose line per 2-D box
+    f.open(folder + "/train.txt");
+    f << std::fixed;
+    f << "#class Bbox" << endl;
+    f << mClass << " ";
+    for (int i = 0; i < 3; ++i) f << mBoundingBox.max[i] << " ";
+    f << endl;
+    f << "#stamp box.x box.y box.h box.w  tx  ty  tz  qx  qy  qz  qw (object-centric)" << endl;
+    if (mpTrainData) {
+        std::map<uint32_t, string> idx_to_stamp;
+        for (const auto& kv : mpTrainData->mStampToIdx) idx_to_stamp.emplace(kv.second, kv.first);
+        for (size_t i = 0; i < mnBbox && i < mFrameIdBbox.size(); ++i) {
+            const FrameIdAndBbox& b = mFrameIdBbox[i];
+            auto it = idx_to_stamp.find(b.FrameId);
+            if (it == idx_to_stamp.end() || b.FrameId >= mpTrainData->mvIamgesPose.size()) continue;
+            write_pose_line(f, it->second, b, mObjTow, mpTrainData->mvIamgesPose[b.FrameId]);
+        }
+    }
+    f.close();
+
+    RenderVideo(folder + "/video_img", folder + "/video_depth", radius);
+
+    cout << "Save Object Mesh ... please wait..." << endl;
     UpdateMesh();
     SaveMesh(folder + "/obj.ply");
+}
+
+// NeRF_Model::RenderVideo (nerf_model.cu:1832-1991): 60 turn-table views at elevation 30 degrees, the central half of
+// the image (x = W/4, y = H/4, w = W/2, h = H/2), camera poses given directly in the object frame.
+void NeRF::RenderVideo(const string img_path_folder, const string depth_path_folder, const float radius) {
+    if (!mpCore || !mpTrainData) return;
+    cout << "Render Object " << mId << " 360 video imgs to " << img_path_folder << " ... please wait..." << endl;
+    const int theta_num = 60;
+    const float theta = 360 / float(theta_num), phi = 30;
+    float cur_theta = 0.0f;
+    mon_bbox2d box = {0u, (uint32_t)(mpTrainData->W / 4), (uint32_t)(mpTrainData->H / 4), (uint32_t)(mpTrainData->H / 2), (uint32_t)(mpTrainData->W / 2)};
+    if (box.h == 0 || box.w == 0) return;
+    const size_t n = (size_t)box.h * box.w;
+    vector<float> rgb(n * 3), depth(n), mask(n);
+    for (int i = 0; i < theta_num; ++i) {
+        cur_theta += theta;
+        float Toc[16];
+        pose_math::turntable_toc(cur_theta, phi, radius, Toc);
+        if (mon_object_render_object_centric(mpCore, box, Toc, 1, nullptr, rgb.data(), depth.data(), mask.data()) != MON_OK) {
+            cerr << "render video: " << mon_last_error() << endl;
+            return;
+        }
+        write_view_pngs(img_path_folder + "/" + std::to_string(i) + ".png", depth_path_folder + "/" + std::to_string(i) + ".png", "",
+                        (int)box.w, (int)box.h, rgb, depth, nullptr);
+    }
 }
 
 vector<Eigen::Matrix4f> NeRF::GetTwc() {

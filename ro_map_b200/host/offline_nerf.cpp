@@ -3,6 +3,7 @@
 // Loads <dataset>/obj_offline/{0..n-1}.txt like the reference (main.cpp:307-319), trains every object on its own
 // host thread (objects round-robin over the visible GPUs), renders the first test box of each object and prints one
 // line per object: id, GPU, final loss, ms per 500-iteration Train_Step.
+#include <algorithm>
 #include <sys/stat.h>
 
 #include <cstdlib>
@@ -43,7 +44,9 @@ int main(int argc, char** argv) {
         auto boxes = obj->GetFrameIdAndBBox();
         if (!boxes.empty()) {
             auto Twc = obj->GetTwc();
-            obj->RenderTestImg("output", {"view0"}, {Twc[0]}, {boxes[0]}, 0.0f);
+            const nerf::BoundingBox bb = obj->GetBoundingBox();
+            const float radius = 5.0f * std::max(bb.max[0], std::max(bb.max[1], bb.max[2]));   // RenderRadius = mfMaxDist * 5 (src/System.cc:609)
+            obj->RenderTestImg("output", {"view0"}, {Twc[0]}, {boxes[0]}, radius);
         }
     }
     return 0;

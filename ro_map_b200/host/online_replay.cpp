@@ -10,6 +10,7 @@
 // Prints per-keyframe ingest latency and per-object totals.
 #include <sys/stat.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdlib>
 #include <fstream>
@@ -118,7 +119,8 @@ int main(int argc, char** argv) {
         std::cout << "object " << obj->mId << " gpu " << obj->mGPUid << " boxes " << obj->mnBbox << " step " << obj->TrainingStep() << " loss "
                   << obj->LastLoss() << " ms_per_train_step " << obj->LastTrainMs() << std::endl;
         const nerf::FrameIdAndBbox first = t.obs.begin()->second;
-        manager.RenderNeRFsTest(out_dir, (size_t)t.nerf_idx, {"view0"}, {first}, {index.mvIamgesPose[first.FrameId]}, 0.0f);
+        const float radius = 5.0f * std::max(t.box.max[0], std::max(t.box.max[1], t.box.max[2]));   // RenderRadius = mfMaxDist * 5 (src/System.cc:609)
+        manager.RenderNeRFsTest(out_dir, (size_t)t.nerf_idx, {"view0"}, {first}, {index.mvIamgesPose[first.FrameId]}, radius);
     }
     return 0;
 }

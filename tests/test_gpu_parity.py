@@ -306,3 +306,39 @@ def test_full_size_properties(core, gpu_dataset, small_seq):
     assert np.isfinite(g.state("master")).all() and g.step == 301
     l_end = g.train(1)
     assert l_end < 0.6 * outs[0][0]
+
+
+def test_pipelined_graph_matches_serial_chain(core, gpu_dataset, small_seq):
+    """Production path = the level-pipelined iteration graph (scatter -> optimizer -> next encode cut by level group and
+    overlapped on branch streams, two sample-position buffers; mon_core.cu capture_graph_pipelined).  The serial chain
+    (mon_object_train_profiled: the same kernels over the whole level range on one stream) runs the same iterations
+    with the same RNG counters, so both must agree up to the order of the fp16 gradient atomics."""
+    seq, obj = small_seq, small_seq.objects[0]
+    cfg = core.default_config(rays_per_batch=1024)
+    bmin, bmax = -1.1 * obj.half, 1.1 * obj.half
+
+    def fresh():
+        g = core.NerfObject(gpu_dataset, cfg, obj.Tow, bmin, bmax, obj.instance_id)
+        g.set_bboxes(obj.boxes)
+        return g
+    a, b = fresh(), fresh()
+    a.train(1)              # 1-iteration graph
+    b.train_profiled(1)     # serial chain
+    ma, mb = a.state("master"), b.state("master")
+    assert np.array_equal(a.state("param_steps"), b.state("param_steps"))      # same set of touched parameters
+    assert (np.abs(ma - mb) <= 1e-6).mean() >= 0.999                           # Adam's first step is +-lr: only sign flips of ~0 gradients differ
+    assert np.array_equal(ma[:a.n_mlp], mb[:a.n_mlp])                          # MLP gradient is bitwise reproducible (fixed-order reduction)
+    # 60 more iterations: one 50-iteration graph (every hand-over between the two point buffers, every join) + 10 single ones
+    la = a.train(60)
+    b.train_profiled(60)
+    lb = b.train(0)
+    assert a.step == b.step == 61
+    assert np.isfinite(la) and abs(la - lb) <= 0.03 * abs(lb) + 1e-4, (la, lb)
+    wa, wb = a.state("master")[:a.n_mlp], b.state("master")[:a.n_mlp]
+    assert np.linalg.norm(wa - wb) <= 0.05 * np.linalg.norm(wb)
+    ea, eb = a.state("ema"), b.state("ema")
+    assert np.linalg.norm(ea - eb) <= 0.05 * np.linalg.norm(eb)
+    # and the two paths stay interchangeable on one object: graph -> serial -> graph
+    a.train_profiled(3)
+    l_end = a.train(50)
+    assert a.step == 114 and np.isfinite(l_end) and l_end < 1.2 * la + 1e-3

@@ -116,6 +116,31 @@ def test_online_manager_replay(tmp_path, host_lib):
     assert "ingest_ms_per_keyframe" in p.stdout
     img = cv2.imread(str(tmp_path / "out" / "0" / "test_img" / "view0.png"), cv2.IMREAD_COLOR)
     assert img is not None and img.shape[2] == 3
+    # the reference's full output set (nerf.cu:255-404): test.txt / train.txt schemas, 60-view turn-table video, obj.ply
+    out0 = tmp_path / "out" / "0"
+    test_lines = (out0 / "test.txt").read_text().splitlines()
+    assert test_lines[0].startswith("#stamp  box.x  box.y  box.h  box.w  tx  ty  tz  qx  qy  qz  qw")
+    tok = test_lines[1].split()
+    first = seq.objects[0].boxes[0]
+    assert tok[0] == "view0" and [int(v) for v in tok[1:5]] == [int(v) for v in first[1:5]] and len(tok) == 12
+    q = np.array(tok[8:12], dtype=np.float64)
+    assert np.isclose(np.linalg.norm(q), 1.0, atol=1e-4)
+    # object-centric camera position = ObjTow * Twc translation
+    Toc = np.asarray(seq.objects[0].Tow, dtype=np.float64).reshape(4, 4) @ np.asarray(seq.poses[first[0]], dtype=np.float64).reshape(4, 4)
+    assert np.allclose(np.array(tok[5:8], dtype=np.float64), Toc[:3, 3], atol=3e-4)
+    train_lines = (out0 / "train.txt").read_text().splitlines()
+    assert train_lines[0] == "#class Bbox" and len(train_lines[1].split()) == 4
+    assert len(train_lines) == 3 + len(seq.objects[0].boxes) and all(len(l.split()) == 12 for l in train_lines[3:])
+    vids = sorted((out0 / "video_img").glob("*.png"), key=lambda p: int(p.stem))
+    assert [int(p.stem) for p in vids] == list(range(60)) and len(list((out0 / "video_depth").glob("*.png"))) == 60
+    v0 = cv2.imread(str(vids[0]), cv2.IMREAD_COLOR)
+    d0 = cv2.imread(str(out0 / "video_depth" / "0.png"), cv2.IMREAD_UNCHANGED)
+    assert v0.shape == (seq.H // 2, seq.W // 2, 3) and d0.dtype == np.uint16 and d0.shape == v0.shape[:2]
+    # the turn-table camera looks at the object: the centre of every view is covered (depth > 0), the corners are white
+    cover = [cv2.imread(str(out0 / "video_depth" / f"{i}.png"), cv2.IMREAD_UNCHANGED)[seq.H // 4, seq.W // 4] > 0 for i in range(0, 60, 6)]
+    assert sum(cover) >= 8, cover
+    assert (v0[0, 0] == 255).all()
+    assert (out0 / "obj.ply").read_text().startswith("ply")
 
 
 def test_mesh_extraction_on_analytic_field(tmp_path):
@@ -138,3 +163,32 @@ def test_mesh_extraction_on_analytic_field(tmp_path):
         assert [l for l in hdr if l.startswith("property")][:9] == [f"property float {c}" for c in ("x", "y", "z", "nx", "ny", "nz")] + \
             [f"property uchar {c}" for c in ("red", "green", "blue")]
         assert len(txt) - len(hdr) == int(fact["verts"] + fact["faces"])
+
+
+def test_pose_math_turntable_and_quaternion(tmp_path):
+    """ro_map_b200/host/pose_math.h: GenerateToc's turn-table poses (nerf_model.cu:2186-2205) are rigid, sit at
+    (r, theta, phi) and look at the object origin; rotation -> quaternion agrees with scipy on both branches (trace > 0
+    and largest-diagonal); Toc = ObjTow * Twc composes column-major like Eigen."""
+    from scipy.spatial.transform import Rotation
+    exe = tmp_path / "pose_check"
+    subprocess.run(["g++", "-O2", "-std=c++17", f"-I{ROOT / 'ro_map_b200' / 'host'}", str(ROOT / "tests" / "host" / "pose_check.cpp"), "-o", str(exe)], check=True)
+    run = lambda *a: np.array(subprocess.run([str(exe), *map(str, a)], capture_output=True, text=True, check=True).stdout.split(), dtype=np.float64)
+    for theta in (6.0, 90.0, 186.0, 360.0):
+        T = run("toc", theta, 30.0, 1.5).reshape(4, 4).T          # printed column-major
+        Rm, t = T[:3, :3], T[:3, 3]
+        assert np.allclose(Rm.T @ Rm, np.eye(3), atol=1e-6) and np.isclose(np.linalg.det(Rm), 1.0, atol=1e-6)
+        assert np.isclose(np.linalg.norm(t), 1.5, atol=1e-6) and np.isclose(t[2], 1.5 * np.sin(np.pi / 6), atol=1e-6)
+        assert np.allclose(np.arctan2(t[1], t[0]) % (2 * np.pi), np.deg2rad(theta) % (2 * np.pi), atol=1e-5) or np.isclose(theta, 360.0)
+        assert np.allclose(Rm[:, 2], -t / np.linalg.norm(t), atol=1e-6)       # optical axis points at the origin
+        assert abs(Rm[2, 0]) < 1e-7                                            # camera x axis stays horizontal
+        assert np.allclose(T[3], [0, 0, 0, 1])
+    rng = np.random.default_rng(3)
+    rots = list(Rotation.random(20, random_state=4)) + [Rotation.from_euler("xyz", e) for e in ((3.1, 0.01, 0.02), (0.01, 3.1, 0.0), (0.02, 0.0, 3.1))]
+    for r in rots:
+        T = np.eye(4); T[:3, :3] = r.as_matrix(); T[:3, 3] = rng.normal(size=3)
+        q = run("quat", *T.T.reshape(-1))
+        ref = r.as_quat()
+        assert min(np.abs(q - ref).max(), np.abs(q + ref).max()) < 2e-6, (q, ref)
+        B = np.eye(4); B[:3, :3] = Rotation.random(random_state=5).as_matrix(); B[:3, 3] = (0.3, -0.2, 0.9)
+        C = run("mul", *T.T.reshape(-1), *B.T.reshape(-1)).reshape(4, 4).T
+        assert np.allclose(C, T @ B, atol=1e-5)

@@ -10,6 +10,8 @@
 // is what lets the whole iteration replay as a static CUDA graph.
 #include "mon_device.cuh"
 #include "mon_kernels.h"
+#include "mon_timeline.cuh"
+MON_TL_DEFINE(batch)
 
 #include <cooperative_groups.h>
 
@@ -82,8 +84,9 @@ k_generate_batch(MonBatch b, MonScene sc) {
     __shared__ uint32_t s_total;          // read by the other CTAs of the cluster
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t rank = cluster.block_rank(), n_cta = cluster.num_blocks();
-    const uint32_t iter = b.ctrl->iter;
-    const uint32_t n_boxes = b.ctrl->n_boxes;
+    const uint32_t iter = b.state->iter;
+    const uint32_t n_boxes = b.state->n_boxes;
+    MON_TL(MON_TL_B, iter);
     const uint32_t R = b.R;
     const uint32_t n_threads = n_cta * BATCH_THREADS;
     const uint32_t per_thread = (R + n_threads - 1) / n_threads;
@@ -149,10 +152,15 @@ k_generate_batch(MonBatch b, MonScene sc) {
         }
     }
     if (rank == 0 && tid == 0) {
+        // the iteration's own control block (b.ctrl, one per batch buffer) is written completely; the counters that
+        // survive the iteration live in b.state
         b.ctrl->n_in = n_in;
+        b.ctrl->n_boxes = n_boxes;
         b.ctrl->skip = (n_in == 0) ? 1u : 0u;  // reference: modulo by zero (undefined); here: skip the iteration
+        b.ctrl->step = b.state->step;
         if (n_in > 0) {
-            const uint32_t step = b.ctrl->step + 1;
+            const uint32_t step = b.state->step + 1;
+            b.state->step = step;
             b.ctrl->step = step;
             // ExponentialDecay evaluates its condition with the nested step BEFORE Adam increments it
             float factor = 1.0f;
@@ -166,6 +174,7 @@ k_generate_batch(MonBatch b, MonScene sc) {
             b.ctrl->ema_new = 1.0f / (1.0f - (float)pow((double)b.ema_decay, (double)step));
         }
         b.ctrl->iter = iter + 1;
+        b.state->iter = iter + 1;
     }
 }
 

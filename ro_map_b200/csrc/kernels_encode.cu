@@ -21,6 +21,8 @@
 #include "mon_device.cuh"
 #include "mon_kernels.h"
 #include "tc05.cuh"
+#include "mon_timeline.cuh"
+MON_TL_DEFINE(encode)
 
 // ---------------------------------------------------------------------------------------------- sample points
 // A3: t_n = tmin + dt*(n + xi), p = o + t*d, u = (p - bmin) / (bmax - bmin)  (nerf_model.cu:545-565,140-144).
@@ -34,6 +36,7 @@ k_sample_points(uint32_t n_points, uint32_t S, const MonRay* __restrict__ rays, 
     mon_pdl_wait();
     mon_pdl_trigger();
     if (ctrl && ctrl->skip) return;
+    MON_TL(MON_TL_P, ctrl ? ctrl->iter - 1 : 0u);
     const uint32_t pt = blockIdx.x * blockDim.x + threadIdx.x;
     if (pt >= n_points) return;
     const uint32_t ray = pt / S, n = pt - ray * S;
@@ -101,7 +104,7 @@ __device__ __forceinline__ void bulk_load_table(uint32_t smem_dst, const void* g
 // the coherent-prime hash or the dense (wrapping) linear index at compile time
 template <bool HASHED>
 __device__ __forceinline__ void enc_points_pow2(const float* __restrict__ pts, __half* __restrict__ out, uint32_t p_first, uint32_t p_end,
-                                                float scale, uint32_t size, uint32_t res, uint32_t table_smem) {
+                                                float scale, uint32_t size, uint32_t res, const unsigned char* __restrict__ table) {
     const uint32_t bmask = 2u * size - 2u;
     const uint32_t my = HASHED ? 2654435761u : res, mz = HASHED ? 805459861u : res * res;
     for (uint32_t p = p_first; p < p_end; p += ENC_THREADS) {
@@ -123,8 +126,8 @@ __device__ __forceinline__ void enc_points_pow2(const float* __restrict__ pts, _
             const float wgt = __fmul_rn(wxy[k & 3], (k & 4) ? fr[2] : g2);
             const uint32_t off = (HASHED ? (ax[k & 1] ^ ay[(k >> 1) & 1] ^ az[k >> 2]) : (ax[k & 1] + ay[(k >> 1) & 1] + az[k >> 2])) & bmask;
             const float wh = __half2float(__float2half_rn(wgt));
-            unsigned short tv;
-            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(tv) : "r"(table_smem + off));
+            // generic load from a pointer the compiler knows to be shared: LDS.U16 [R + UR] with the base in a uniform register
+            const unsigned short tv = *reinterpret_cast<const unsigned short*>(table + off);
             acc = __float2half_rn(__fmaf_rn(wh, __half2float(__ushort_as_half(tv)), __half2float(acc)));
         }
         out[(size_t)p * 2] = acc;
@@ -144,6 +147,7 @@ k_encode_forward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, co
     mon_pdl_wait();       // the optimizer sweep (planar weights) has completed
     mon_pdl_trigger();
     if (ctrl && ctrl->skip) return;
+    MON_TL(MON_TL_E + ((job_begin >> 3) & 3u), ctrl ? ctrl->iter - 1 : 0u);
 
     // jobs [job_begin, job_end) of the 2 * n_levels (level, feature) jobs: the level-pipelined iteration graph runs the
     // coarse and the fine half of the levels as two launches (mon_core.cu capture_graph)
@@ -172,8 +176,8 @@ k_encode_forward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, co
         const bool pow2 = (size & (size - 1)) == 0;
         __half* out = enc_soa + (size_t)l * n_points * 2 + f;   // level-major pairs: enc[level][point][feature]
         if (pow2) {
-            if (hashed) enc_points_pow2<true>(pts, out, p0 + tid, p1, scale, size, res, tc05::smem_u32(enc_smem));
-            else enc_points_pow2<false>(pts, out, p0 + tid, p1, scale, size, res, tc05::smem_u32(enc_smem));
+            if (hashed) enc_points_pow2<true>(pts, out, p0 + tid, p1, scale, size, res, enc_smem);
+            else enc_points_pow2<false>(pts, out, p0 + tid, p1, scale, size, res, enc_smem);
         } else {
             for (uint32_t p = p0 + tid; p < p1; p += ENC_THREADS) {
                 const float u0 = __ldg(pts + (size_t)p * 3), u1 = __ldg(pts + (size_t)p * 3 + 1), u2 = __ldg(pts + (size_t)p * 3 + 2);
@@ -254,6 +258,7 @@ k_encode_backward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, c
     mon_pdl_wait();
     mon_pdl_trigger();
     if (ctrl->skip) return;
+    MON_TL(MON_TL_S + ((level_begin >> 2) & 3u), ctrl->iter - 1);
     const uint32_t p = threadIdx.x & (SCT_TILE - 1), lg = threadIdx.x >> 7;
     const uint32_t pt = blockIdx.x * SCT_TILE + p;
     if (pt >= n_points) return;

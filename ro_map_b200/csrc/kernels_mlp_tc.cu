@@ -29,6 +29,8 @@
 #include "mon_kernels.h"
 #include "render_math.cuh"
 #include "tc05.cuh"
+#include "mon_timeline.cuh"
+MON_TL_DEFINE(mlp)
 
 using namespace tc05;
 
@@ -321,6 +323,7 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
     if (!skip && blockIdx.x < n_tiles) tin = tc_load_tile_inputs(b, blockIdx.x * 4 + c.warp, c.lane, iter);
     mon_pdl_wait();          // the encodings of this iteration are complete
     mon_pdl_trigger();
+    MON_TL(MON_TL_M, iter);
     // hand the iteration's control block to the kernels behind this one (scatter, optimizer): the batch kernel of
     // the next iteration is allowed to overwrite the live block while they run
     if (blockIdx.x == 0 && threadIdx.x == 0) *b.late = *b.ctrl;

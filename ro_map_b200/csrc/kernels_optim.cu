@@ -18,6 +18,8 @@
 // master / moment / step words.
 #include "mon_device.cuh"
 #include "mon_kernels.h"
+#include "mon_timeline.cuh"
+MON_TL_DEFINE(optim)
 
 // ---- pcg32 on the device (TCNN dependencies/pcg32/pcg32.h:46-170), for A12 grid init
 struct DevPcg32 {
@@ -95,6 +97,7 @@ k_optimizer_sweep(MonOpt o, MonCtrl* __restrict__ ctrl, float* __restrict__ pf, 
     mon_pdl_wait();       // the gradient scatter has completed
     mon_pdl_trigger();
     if (ctrl->skip) return;
+    MON_TL(n_mlp_ctas ? MON_TL_OMLP : MON_TL_O + (level_of_entry(grid, (grid_i4_begin - o.n_mlp) >> 1) >> 2 & 3u), ctrl->iter - 1);
     if (do_loss && blockIdx.x == gridDim.x - 1) {
         // logged loss in the sweep's last (mostly idle) CTA: fixed summation order -> reproducible
         __shared__ float s_loss[OPT_THREADS];

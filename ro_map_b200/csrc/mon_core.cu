@@ -189,7 +189,9 @@ struct mon_object {
     __half *ph = nullptr, *gh = nullptr, *ema = nullptr;
     uint32_t* ps = nullptr;
     // control
-    MonCtrl* ctrl = nullptr;       // live block (batch kernel)
+    MonCtrl* ctrl_state = nullptr; // persistent counters (iter, step, n_boxes), advanced by the batch kernels
+    MonCtrl* ctrl = nullptr;       // control block of the iteration in batch buffer 0 (ctrl_alt: buffer 1)
+    MonCtrl* ctrl_alt = nullptr;
     MonCtrl* ctrl_late = nullptr;  // per-iteration copy for scatter / optimizer; carries the logged loss
     MonCtrl* h_ctrl = nullptr;  // pinned
     mon_bbox2d* d_boxes = nullptr;
@@ -218,9 +220,13 @@ struct mon_object {
     cudaStream_t stream = nullptr, aux = nullptr;   // aux: next iteration's batch + sample points, forked inside the graphs
     cudaEvent_t ev_fork_m = nullptr, ev_fork_s = nullptr, ev_join = nullptr;
     // level-pipelined graph (capture_graph_pipelined): one branch stream per level group of the scatter / optimizer
-    cudaStream_t grp[MON_PIPE_GROUPS] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev_grp[MON_PIPE_GROUPS] = {nullptr, nullptr, nullptr, nullptr}, ev_pts = nullptr, ev_aux = nullptr;
+    cudaStream_t grp[2] = {nullptr, nullptr};   // scatter chain, optimizer chain
+    cudaEvent_t ev_s[MON_PIPE_GROUPS] = {nullptr, nullptr, nullptr, nullptr}, ev_o[MON_PIPE_GROUPS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_pts = nullptr, ev_aux = nullptr, ev_ready = nullptr, ev_b = nullptr;
     float* pts_alt = nullptr;         // second sample-position buffer: P(i+1) runs while S(i) still reads the first
+    // second batch buffer (rays, targets, control block): B(i+2) runs right after M(i), a whole iteration ahead
+    MonRay* rays_alt = nullptr; uint8_t* ray_inst_alt = nullptr;
+    float *target_alt = nullptr, *target_depth_alt = nullptr, *bg_alt = nullptr;
     int prio_hi = 0, prio_lo = 0;     // stream priority range of the device (hi = numerically lowest)
     cudaGraphExec_t graph1 = nullptr, graphN = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -501,19 +507,21 @@ static void drop_graphs(mon_object* o) {
     if (o->graphN) { cudaGraphExecDestroy(o->graphN); o->graphN = nullptr; }
 }
 
-static MonBatch make_batch(mon_object* o, bool injected, bool debug) {
+static MonBatch make_batch(mon_object* o, bool injected, bool debug, int buf = 0) {
     MonBatch b;
     memset(&b, 0, sizeof(b));
     b.R = o->R;
     b.boxes = o->d_boxes;
     b.frames = o->ds->d_frames;
-    b.ctrl = o->ctrl;
+    b.state = o->ctrl_state;
+    b.ctrl = buf ? o->ctrl_alt : o->ctrl;
     b.late = o->ctrl_late;
     b.seed = o->seed;
     b.opt_lr = o->cfg.learning_rate; b.decay_base = o->cfg.decay_base; b.ema_decay = o->cfg.ema_decay;
     b.decay_start = o->cfg.decay_start; b.decay_interval = o->cfg.decay_interval ? o->cfg.decay_interval : 1;
     if (injected) { b.inj_xy = o->inj_xy; b.inj_col = o->inj_col; b.inj_dt = o->inj_dt; }
-    b.rays = o->rays; b.ray_inst = o->ray_inst; b.target = o->target; b.target_depth = o->target_depth; b.bg = o->bg;
+    if (buf) { b.rays = o->rays_alt; b.ray_inst = o->ray_inst_alt; b.target = o->target_alt; b.target_depth = o->target_depth_alt; b.bg = o->bg_alt; }
+    else { b.rays = o->rays; b.ray_inst = o->ray_inst; b.target = o->target; b.target_depth = o->target_depth; b.bg = o->bg; }
     b.rgb_rays = o->rgb_rays; b.depth_rays = o->depth_rays; b.mask_rays = o->mask_rays; b.loss = o->loss;
     b.enc = o->enc; b.d_enc = o->d_enc;
     if (debug) { b.dbg_out = o->dbg_out; b.dbg_dout = o->dbg_dout; }
@@ -627,17 +635,18 @@ static int capture_graph(mon_object* o, int iters, cudaGraphExec_t* out) {
 // level is scattered (S), consumed by the optimizer (O) and the level is re-encoded (E) without touching any other
 // level.  So the S -> O -> E chain is cut by level group and the pieces overlap:
 //
-//   main :  M(i) -> S0 -> O0 ---------+-> E[0,h)(i+1) ----+-> E[h,L)(i+1) -> M(i+1)
-//   grp1 :      \-> S1 -> O1 --------/                   |
-//   grp2 :      \-> S2 -> O2 ---------------------------+
-//   grp3 :      \-> S3 -> O3 ---------------------------+
-//   aux  :      \-> B(i+1) -> P(i+1) -> (E waits) -> O_mlp(i) -> (M(i+1) waits)
+//   main :  M(i) ----------------------+-> E part 0 (i+1) --+-> E part 1 (i+1) -> M(i+1)
+//   sc   :     \-> S0 -> S1 -> S2 -> S3 |                    |
+//   oc   :          \-> O0 -> O1 -------/--> O2 -> O3 -------/
+//   aux  :     \-> O_mlp(i) -> B(i+2) ......... P(i+2) (once every S(i) is done)
 //
-// S0..S3 become ready together; node priorities dispatch their CTAs in group order, so O0 (and then the coarse half of
-// the next encode) starts while the finer groups are still scattering.  The scatter is bound by L2 atomics, the
-// encode by issue slots and shared-memory banks, the optimizer by L2/HBM bandwidth: they overlap instead of queueing.
-// P(i+1) writes the other sample-position buffer because S(i) is still reading the current one.  Every graph starts
-// with its own B, P into buffer 0, so no buffer parity survives between graph launches.
+// The scatter is bound by L2 atomics, the encode by issue slots and shared-memory banks, the optimizer by L2/HBM
+// bandwidth: they overlap instead of queueing.  Batch generation runs TWO iterations ahead (two batch buffers:
+// rays, targets, control block; B(i+2) may start as soon as M(i) has read buffer i & 1) and the sample positions are
+// double-buffered as well (S(i) still reads the buffer P(i+2) will overwrite), so neither sits between the optimizer
+// and the next encode.  The persistent counters (RNG iteration, optimizer step, box count) live in ctrl_state, which
+// only the batch kernels touch, in order.  Every graph starts with its own B(0), P(0) into buffer 0, so no buffer
+// parity survives between graph launches.
 static int pipe_mode() {
     static int mode = -1;
     if (mode < 0) {
@@ -647,69 +656,104 @@ static int pipe_mode() {
     }
     return mode;
 }
+static uint32_t pipe_enc_parts() {
+    static int parts = -1;
+    if (parts < 0) {
+        const char* e = getenv("MON_PIPE_ENC_PARTS");
+        parts = e ? atoi(e) : 2;
+        if (parts < 1 || parts > MON_PIPE_GROUPS) parts = 2;
+    }
+    return (uint32_t)parts;
+}
+struct PipeShape { uint32_t L, per, n_groups, n_parts; };
+static PipeShape pipe_shape(const mon_object* o) {
+    PipeShape p;
+    p.L = o->grid.n_levels;
+    p.per = ((p.L + MON_PIPE_GROUPS - 1) / MON_PIPE_GROUPS + 3) / 4 * 4;   // levels per scatter group, a multiple of 4
+    p.n_groups = (p.L + p.per - 1) / p.per;
+    p.n_parts = std::min(pipe_enc_parts(), p.n_groups);
+    return p;
+}
 
 static int capture_graph_pipelined(mon_object* o, int iters, cudaGraphExec_t* out) {
-    const MonBatch b = make_batch(o, false, false);
-    const uint32_t L = o->grid.n_levels;
-    const uint32_t per = ((L + MON_PIPE_GROUPS - 1) / MON_PIPE_GROUPS + 3) / 4 * 4;   // levels per scatter group, multiple of 4
-    const uint32_t n_groups = (L + per - 1) / per;
-    const uint32_t half_groups = (n_groups + 1) / 2;                                   // groups feeding the first encode launch
-    const uint32_t h = std::min(L, half_groups * per);
+    const MonBatch bb[2] = {make_batch(o, false, false, 0), make_batch(o, false, false, 1)};
+    float* const pts[2] = {o->pts, o->pts_alt};
+    const PipeShape ps = pipe_shape(o);
+    const uint32_t L = ps.L;
     const int mode = pipe_mode();
-    // mode 1: group k at priority hi+k, encode/MLP/batch at hi; mode 2: encode below every scatter group; mode 3: no priorities
-    auto prio = [&](int rank) {
+    // mode 1: no node priorities; 2: encode + MLP above scatter/optimizer; 3: scatter/optimizer above encode + MLP
+    auto opt = [&](bool front, bool pdl) {
         MonLaunchOpt lo;
-        lo.pdl = false;
-        if (mode != 3) { lo.set_priority = true; lo.priority = std::min(o->prio_lo, o->prio_hi + rank); }
+        lo.pdl = pdl;
+        if (mode != 1) { lo.set_priority = true; lo.priority = ((mode == 2) == front) ? o->prio_hi : o->prio_lo; }
         return lo;
     };
-    auto with_pdl = [](MonLaunchOpt lo) { lo.pdl = true; return lo; };
-    const int enc_rank = mode == 2 ? (int)n_groups : 0;
     cudaGraph_t g = nullptr;
-    cudaStream_t st = o->stream, aux = o->aux;
+    cudaStream_t st = o->stream, aux = o->aux, sc = o->grp[0], oc = o->grp[1];
     CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     cudaError_t e = cudaSuccess;
-    float* pts_cur = o->pts;
-    float* pts_nxt = o->pts_alt;
 #define PE(x) do { if (e == cudaSuccess) e = (x); } while (0)
-    mon_launch_generate_batch(b, o->scene, st, prio(0));
-    mon_launch_sample_points(o->N, MON_S, o->rays, nullptr, nullptr, o->seed, o->ctrl, 2, 0, o->scene.bmin, o->scene.bmax, pts_cur, st, with_pdl(prio(0)));
-    PE(mon_launch_encode_forward(o->grid, o->N, pts_cur, o->ph_planar, o->enc, o->ctrl, (uint32_t)o->sm_count, st, 0, L, with_pdl(prio(enc_rank))));
+    auto points = [&](int buf, cudaStream_t s, bool pdl) {
+        mon_launch_sample_points(o->N, MON_S, bb[buf].rays, nullptr, nullptr, o->seed, bb[buf].ctrl, 2, 0, o->scene.bmin, o->scene.bmax, pts[buf], s, opt(true, pdl));
+    };
+    auto encode = [&](int buf, uint32_t l0, uint32_t l1, bool pdl) {
+        PE(mon_launch_encode_forward(o->grid, o->N, pts[buf], o->ph_planar, o->enc, bb[buf].ctrl, (uint32_t)o->sm_count, st, l0, l1, opt(true, pdl)));
+    };
+    auto optimizer = [&](cudaStream_t s, int part, uint32_t l0, uint32_t l1) {
+        mon_launch_optimizer(o->opt, o->ctrl_late, o->pf, o->ph, o->gh, o->partials, o->m, o->v, o->ps, o->ema, o->loss, o->R, o->grid, o->ph_planar, s,
+                             part, l0, l1, opt(false, false));
+    };
+    // prologue: iteration 0 serially on the main stream, batch + points of iteration 1 beside it
+    mon_launch_generate_batch(bb[0], o->scene, st, opt(true, false));
+    PE(cudaEventRecord(o->ev_b, st));
+    points(0, st, true);
+    encode(0, 0, L, true);
+    if (iters > 1) {
+        PE(cudaStreamWaitEvent(aux, o->ev_b, 0));
+        mon_launch_generate_batch(bb[1], o->scene, aux, opt(true, false));
+        points(1, aux, false);
+        PE(cudaEventRecord(o->ev_pts, aux));
+    }
     for (int i = 0; i < iters && e == cudaSuccess; ++i) {
-        const bool more = i + 1 < iters;
-        PE(mon_launch_mlp_train_tc(b, o->lc, o->cfg.n_hidden_layers, o->n_mlp, o->n_ctas, st, with_pdl(prio(0))));
+        const int cur = i & 1, nxt = cur ^ 1;
+        const bool more = i + 1 < iters, more2 = i + 2 < iters;
+        PE(mon_launch_mlp_train_tc(bb[cur], o->lc, o->cfg.n_hidden_layers, o->n_mlp, o->n_ctas, st, opt(true, true)));
         PE(cudaEventRecord(o->ev_fork_m, st));
-        // aux: next batch + sample positions, then the MLP-weight part of the optimizer (+ logged loss)
+        // aux: MLP-weight part of the optimizer (+ logged loss), then the batch of iteration i+2 into the buffers M(i) just released
         PE(cudaStreamWaitEvent(aux, o->ev_fork_m, 0));
-        if (more) {
-            mon_launch_generate_batch(b, o->scene, aux, prio(0));
-            mon_launch_sample_points(o->N, MON_S, o->rays, nullptr, nullptr, o->seed, o->ctrl, 2, 0, o->scene.bmin, o->scene.bmax, pts_nxt, aux, with_pdl(prio(0)));
-            PE(cudaEventRecord(o->ev_pts, aux));
-        }
-        mon_launch_optimizer(o->opt, o->ctrl_late, o->pf, o->ph, o->gh, o->partials, o->m, o->v, o->ps, o->ema, o->loss, o->R, o->grid, o->ph_planar, aux,
-                             MON_OPT_MLP, 0, 0, prio(0));
+        optimizer(aux, MON_OPT_MLP, 0, 0);
         PE(cudaEventRecord(o->ev_aux, aux));
-        // level groups: scatter -> optimizer, group 0 on the main stream
-        for (uint32_t k = 0; k < n_groups; ++k) {
-            cudaStream_t gs = k == 0 ? st : o->grp[k];
-            const uint32_t l0 = k * per, l1 = std::min(L, l0 + per);
-            if (k) PE(cudaStreamWaitEvent(gs, o->ev_fork_m, 0));
-            mon_launch_encode_backward(o->grid, o->N, pts_cur, o->ctrl_late, o->d_enc, o->gh + o->n_mlp, gs, l0, l1, prio((int)k));
-            mon_launch_optimizer(o->opt, o->ctrl_late, o->pf, o->ph, o->gh, o->partials, o->m, o->v, o->ps, o->ema, o->loss, o->R, o->grid, o->ph_planar, gs,
-                                 MON_OPT_GRID, l0, l1, with_pdl(prio((int)k)));
-            if (k) PE(cudaEventRecord(o->ev_grp[k], gs));
+        if (more2) mon_launch_generate_batch(bb[cur], o->scene, aux, opt(true, false));
+        // scatter chain (coarse to fine) and the optimizer chain that follows it group by group
+        PE(cudaStreamWaitEvent(sc, o->ev_fork_m, 0));
+        for (uint32_t k = 0; k < ps.n_groups; ++k) {
+            const uint32_t l0 = k * ps.per, l1 = std::min(L, l0 + ps.per);
+            mon_launch_encode_backward(o->grid, o->N, pts[cur], o->ctrl_late, o->d_enc, o->gh + o->n_mlp, sc, l0, l1, opt(false, false));
+            PE(cudaEventRecord(o->ev_s[k], sc));
+            PE(cudaStreamWaitEvent(oc, o->ev_s[k], 0));
+            optimizer(oc, MON_OPT_GRID, l0, l1);
+            PE(cudaEventRecord(o->ev_o[k], oc));
         }
         if (more) {
-            // coarse half of the next encode once its groups' weights are final, fine half after the rest
-            for (uint32_t k = 1; k < half_groups; ++k) PE(cudaStreamWaitEvent(st, o->ev_grp[k], 0));
+            // the next encode, part by part, as soon as the weights of its levels are final
             PE(cudaStreamWaitEvent(st, o->ev_pts, 0));
-            PE(mon_launch_encode_forward(o->grid, o->N, pts_nxt, o->ph_planar, o->enc, o->ctrl, (uint32_t)o->sm_count, st, 0, h, prio(enc_rank)));
-            for (uint32_t k = half_groups; k < n_groups; ++k) PE(cudaStreamWaitEvent(st, o->ev_grp[k], 0));
-            PE(cudaStreamWaitEvent(st, o->ev_aux, 0));
-            if (h < L) PE(mon_launch_encode_forward(o->grid, o->N, pts_nxt, o->ph_planar, o->enc, o->ctrl, (uint32_t)o->sm_count, st, h, L, prio(enc_rank)));
-            std::swap(pts_cur, pts_nxt);
+            for (uint32_t p = 0; p < ps.n_parts; ++p) {
+                const uint32_t g0 = p * ps.n_groups / ps.n_parts, g1 = (p + 1) * ps.n_groups / ps.n_parts;
+                const bool last = p + 1 == ps.n_parts;
+                PE(cudaStreamWaitEvent(st, o->ev_o[g1 - 1], 0));     // the optimizer chain is ordered: implies every earlier group
+                if (last) {
+                    PE(cudaStreamWaitEvent(st, o->ev_aux, 0));
+                    PE(cudaEventRecord(o->ev_ready, st));             // M(i), every S(i) and O(i) are complete
+                }
+                encode(nxt, g0 * ps.per, std::min(L, g1 * ps.per), false);
+            }
+            if (more2) {
+                PE(cudaStreamWaitEvent(aux, o->ev_ready, 0));         // S(i) no longer reads this point buffer
+                points(cur, aux, false);
+                PE(cudaEventRecord(o->ev_pts, aux));
+            }
         } else {
-            for (uint32_t k = 1; k < n_groups; ++k) PE(cudaStreamWaitEvent(st, o->ev_grp[k], 0));
+            PE(cudaStreamWaitEvent(st, o->ev_o[ps.n_groups - 1], 0));
             PE(cudaStreamWaitEvent(st, o->ev_aux, 0));
         }
     }
@@ -729,12 +773,11 @@ static int capture_graph_pipelined(mon_object* o, int iters, cudaGraphExec_t* ou
 static uint64_t launches_in_graph(const mon_object* o, uint32_t iters) {
     if (iters == 0) return 0;
     if (pipe_mode() == 0) return 6ull * iters;
-    const uint32_t L = o->grid.n_levels;
-    const uint32_t per = ((L + MON_PIPE_GROUPS - 1) / MON_PIPE_GROUPS + 3) / 4 * 4;
-    const uint32_t n_groups = (L + per - 1) / per;
-    const uint32_t n_enc = std::min(L, (n_groups + 1) / 2 * per) < L ? 2u : 1u;
-    // B, P, E once; per iteration M, O_mlp, S + O per level group; per follow-up iteration B, P and the split encode
-    return 3ull + (uint64_t)iters * (2u + 2u * n_groups) + (uint64_t)(iters - 1) * (2u + n_enc);
+    const PipeShape ps = pipe_shape(o);
+    // B, P, E of iteration 0; B, P of iteration 1; per iteration M, O_mlp, S + O per level group; the split encode of
+    // every follow-up iteration; B, P two iterations ahead
+    return 3ull + (iters > 1 ? 2u : 0u) + (uint64_t)iters * (2u + 2u * ps.n_groups) + (uint64_t)(iters - 1) * ps.n_parts +
+           (iters > 2 ? 2ull * (iters - 2) : 0ull);
 }
 
 int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uint8_t instance_id,
@@ -788,9 +831,11 @@ int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uin
     const size_t P = o->P, R = o->R, N = o->N;
     OALLOC(o->pf, P * 4); OALLOC(o->m, P * 4); OALLOC(o->v, P * 4); OALLOC(o->ps, P * 4);
     OALLOC(o->ph, P * 2 + 16); OALLOC(o->gh, P * 2 + 16); OALLOC(o->ema, P * 2 + 16);
-    OALLOC(o->ctrl, sizeof(MonCtrl)); OALLOC(o->ctrl_late, sizeof(MonCtrl));
+    OALLOC(o->ctrl_state, sizeof(MonCtrl)); OALLOC(o->ctrl, sizeof(MonCtrl)); OALLOC(o->ctrl_alt, sizeof(MonCtrl)); OALLOC(o->ctrl_late, sizeof(MonCtrl));
     OALLOC(o->rays, R * sizeof(MonRay)); OALLOC(o->ray_inst, R);
     OALLOC(o->target, R * 12); OALLOC(o->target_depth, R * 4); OALLOC(o->bg, R * 12);
+    OALLOC(o->rays_alt, R * sizeof(MonRay)); OALLOC(o->ray_inst_alt, R);
+    OALLOC(o->target_alt, R * 12); OALLOC(o->target_depth_alt, R * 4); OALLOC(o->bg_alt, R * 12);
     OALLOC(o->rgb_rays, R * 12); OALLOC(o->depth_rays, R * 4); OALLOC(o->mask_rays, R * 4); OALLOC(o->loss, R * 4);
     OALLOC(o->pts, N * 12); OALLOC(o->pts_alt, N * 12); OALLOC(o->enc, N * MON_IN * 2); OALLOC(o->d_enc, N * MON_IN * 2);
     OALLOC(o->ph_planar, (size_t)o->n_grid * 2 + 16);
@@ -810,12 +855,16 @@ int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uin
         mon_object_destroy(o);
         return fail(MON_ERR_CUDA, "object setup: %s", cudaGetErrorString(e));
     }
-    for (int k = 0; k < MON_PIPE_GROUPS; ++k) {
-        if ((e = cudaStreamCreateWithFlags(&o->grp[k], cudaStreamNonBlocking)) != cudaSuccess ||
-            (e = cudaEventCreateWithFlags(&o->ev_grp[k], cudaEventDisableTiming)) != cudaSuccess) {
-            mon_object_destroy(o);
-            return fail(MON_ERR_CUDA, "object setup: %s", cudaGetErrorString(e));
-        }
+    for (int k = 0; k < MON_PIPE_GROUPS && e == cudaSuccess; ++k) {
+        if ((e = cudaEventCreateWithFlags(&o->ev_s[k], cudaEventDisableTiming)) == cudaSuccess)
+            e = cudaEventCreateWithFlags(&o->ev_o[k], cudaEventDisableTiming);
+    }
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaStreamCreateWithFlags(&o->grp[k], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&o->ev_ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&o->ev_b, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        mon_object_destroy(o);
+        return fail(MON_ERR_CUDA, "object setup: %s", cudaGetErrorString(e));
     }
     memset(o->h_ctrl, 0, sizeof(MonCtrl));
 
@@ -858,7 +907,8 @@ int mon_object_destroy(mon_object* o) {
     cudaSetDevice(o->ds->gpu);
     if (o->stream) cudaStreamSynchronize(o->stream);
     drop_graphs(o);
-    void* ptrs[] = {o->pf, o->m, o->v, o->ps, o->ph, o->gh, o->ema, o->ctrl, o->ctrl_late, o->d_boxes, o->rays, o->ray_inst, o->target,
+    void* ptrs[] = {o->pf, o->m, o->v, o->ps, o->ph, o->gh, o->ema, o->ctrl_state, o->ctrl, o->ctrl_alt, o->ctrl_late, o->rays_alt, o->ray_inst_alt,
+                    o->target_alt, o->target_depth_alt, o->bg_alt, o->d_boxes, o->rays, o->ray_inst, o->target,
                     o->target_depth, o->bg, o->rgb_rays, o->depth_rays, o->mask_rays, o->loss, o->pts, o->pts_alt, o->enc, o->d_enc, o->ph_planar, o->partials,
                     o->dbg_out, o->dbg_dout, o->inj_xy, o->inj_col, o->inj_dt, o->grad_snap, o->r_rays, o->r_inbox, o->r_enc,
                     o->r_jit, o->r_rgb, o->r_depth, o->r_mask, o->r_Twc, o->r_pts, o->r_planar};
@@ -871,10 +921,13 @@ int mon_object_destroy(mon_object* o) {
     if (o->ev_join) cudaEventDestroy(o->ev_join);
     if (o->ev_pts) cudaEventDestroy(o->ev_pts);
     if (o->ev_aux) cudaEventDestroy(o->ev_aux);
+    if (o->ev_ready) cudaEventDestroy(o->ev_ready);
+    if (o->ev_b) cudaEventDestroy(o->ev_b);
     for (int k = 0; k < MON_PIPE_GROUPS; ++k) {
-        if (o->ev_grp[k]) cudaEventDestroy(o->ev_grp[k]);
-        if (o->grp[k]) cudaStreamDestroy(o->grp[k]);
+        if (o->ev_s[k]) cudaEventDestroy(o->ev_s[k]);
+        if (o->ev_o[k]) cudaEventDestroy(o->ev_o[k]);
     }
+    for (int k = 0; k < 2; ++k) if (o->grp[k]) cudaStreamDestroy(o->grp[k]);
     if (o->aux) cudaStreamDestroy(o->aux);
     if (o->stream) cudaStreamDestroy(o->stream);
     delete o;
@@ -903,7 +956,7 @@ static int upload_boxes(mon_object* o, uint32_t first) {
         drop_graphs(o);  // the captured graphs hold the old pointer
     }
     if (n > first) CK(cudaMemcpyAsync(o->d_boxes + first, o->h_boxes.data() + first, sizeof(mon_bbox2d) * (n - first), cudaMemcpyHostToDevice, o->stream));
-    CK(cudaMemcpyAsync(&o->ctrl->n_boxes, &n, 4, cudaMemcpyHostToDevice, o->stream));
+    CK(cudaMemcpyAsync(&o->ctrl_state->n_boxes, &n, 4, cudaMemcpyHostToDevice, o->stream));
     CK(cudaStreamSynchronize(o->stream));
     return MON_OK;
 }

@@ -83,7 +83,9 @@ struct MonBatch {
     uint32_t R;                 // rays per batch
     const mon_bbox2d* boxes;
     const MonFrame* frames;
-    MonCtrl* ctrl;      // live control block, owned by the batch kernel
+    MonCtrl* state;     // persistent counters (iter, step, n_boxes): read and advanced by the batch kernels only, which run
+                        // strictly one after the other
+    MonCtrl* ctrl;      // control block of THIS iteration, written by its batch kernel (one per batch buffer)
     MonCtrl* late;      // copy taken by the fused MLP kernel for the scatter / optimizer kernels, so that the batch
                         // kernel of the NEXT iteration may run concurrently with them
     uint32_t seed;

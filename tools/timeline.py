@@ -1,0 +1,88 @@
+#!/usr/bin/env python
+"""Timeline of the iteration graph on the device: which kernels of the level-pipelined graph really overlap.
+
+Needs the instrumented build (every CTA folds %globaltimer into a per-(iteration, kernel) [first start, last end] slot,
+ro_map_b200/csrc/mon_timeline.cuh), which `--build` cross-compiles into ro_map_b200/_build_tl/ without touching the
+product library:
+
+    MON_EXTRA_NVCC_FLAGS=-DMON_TIMELINE python tools/timeline.py --build      # here (no GPU needed)
+    [MON_PIPE=0|1|2|3] [MON_PIPE_ENC_PARTS=1|2|4] python tools/timeline.py    # on the B200 box
+
+Prints, for a few steady-state iterations, start/end of every kernel in microseconds relative to the start of that
+iteration's fused MLP kernel, plus the iteration period."""
+import argparse, ctypes as C, json, os, sys
+from pathlib import Path
+import numpy as np
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+TL_DIR = ROOT / "ro_map_b200" / "_build_tl"
+TL_LIB = TL_DIR / "libmon_b200_tl.so"
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--build", action="store_true")
+ap.add_argument("--rays", type=int, default=4096)
+ap.add_argument("--hidden-layers", type=int, default=1)
+ap.add_argument("--frames", type=int, default=30)
+a = ap.parse_args()
+
+if a.build:
+    assert "-DMON_TIMELINE" in os.environ.get("MON_EXTRA_NVCC_FLAGS", ""), "set MON_EXTRA_NVCC_FLAGS=-DMON_TIMELINE"
+    from ro_map_b200 import build
+    build.BUILD, build.LIB = TL_DIR, TL_LIB
+    TL_DIR.mkdir(exist_ok=True)
+    print(build.build(force=True))
+    sys.exit(0)
+
+from ro_map_b200 import _capi
+_capi.LIB_PATH = TL_LIB
+from ro_map_b200 import core, synthetic as syn
+lib = _capi.load()
+ITERS, KINDS = 64, 16
+NAMES = ["B", "P", "E0", "E1", "E2", "E3", "M", "S0", "S1", "S2", "S3", "O0", "O1", "O2", "O3", "Omlp"]
+TABLES = ["batch", "encode", "mlp", "optim"]
+
+
+def reset():
+    for t in TABLES:
+        assert getattr(lib, f"mon_debug_tl_{t}_reset")() == 0
+
+
+def read():
+    start = np.full((ITERS, KINDS), np.iinfo(np.uint64).max, np.uint64)
+    end = np.zeros((ITERS, KINDS), np.uint64)
+    for t in TABLES:
+        buf = np.zeros((ITERS, KINDS, 2), np.uint64)
+        assert getattr(lib, f"mon_debug_tl_{t}_read")(buf.ctypes.data_as(C.c_void_p)) == 0
+        start = np.minimum(start, buf[..., 0])
+        end = np.maximum(end, buf[..., 1])
+    return start, end
+
+
+seq = syn.make_sequence(a.frames, 1)
+obj = seq.objects[0]
+ds = core.Dataset(0, *seq.K, seq.H, seq.W, len(seq.rgb), True)
+for i in range(len(seq.rgb)):
+    ds.add_frame(i, seq.rgb[i], seq.instance[i], seq.depth[i], seq.poses[i])
+ds.sync()
+g = core.NerfObject(ds, core.default_config(rays_per_batch=a.rays, n_hidden_layers=a.hidden_layers), obj.Tow, -1.1 * obj.half, 1.1 * obj.half, obj.instance_id)
+g.set_bboxes(obj.boxes)
+g.train(400)                       # steady state; iteration counter is now 400
+reset()
+g.train(50)                        # one 50-iteration graph: iterations 400..449 -> slots 16..63, 0..1
+ms = g.last_train_ms
+start, end = read()
+print(json.dumps({"MON_PIPE": os.environ.get("MON_PIPE", "default"), "MON_PIPE_ENC_PARTS": os.environ.get("MON_PIPE_ENC_PARTS", "default"),
+                  "graph_us_per_iter": round(ms * 1e3 / 50, 2)}))
+periods = []
+for it in range(420, 426):
+    s = it % ITERS
+    m0 = int(start[s, 6])
+    row = []
+    for k in sorted(range(KINDS), key=lambda k: int(start[s, k]) if end[s, k] else 1 << 62):
+        if end[s, k] == 0:
+            continue
+        row.append(f"{NAMES[k]}[{(int(start[s, k]) - m0) / 1e3:.1f},{(int(end[s, k]) - m0) / 1e3:.1f}]")
+    nxt = int(start[(it + 1) % ITERS, 6])
+    periods.append((nxt - m0) / 1e3)
+    print(f"iter {it}: period {(nxt - m0) / 1e3:.1f} us  " + " ".join(row))
+print(json.dumps({"mean_period_us": round(float(np.mean(periods)), 2)}))

@@ -86,6 +86,9 @@ __device__ __forceinline__ void level_corners(const MonGrid& g, uint32_t l, cons
 #define ENC_THREADS 1024
 #define ENC_TABLE_BYTES (65536 * 2)
 #define ENC_BULK_CHUNK 16384u
+#ifndef ENC_UNROLL
+#define ENC_UNROLL 2   // two points in flight per thread: the 8-corner fp16 rounding chain is serial, a second chain hides its latency
+#endif
 
 __device__ __forceinline__ void bulk_load_table(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     // one thread: arm the barrier with the byte count, then issue the TMA bulk copies (global -> shared)
@@ -99,39 +102,53 @@ __device__ __forceinline__ void bulk_load_table(uint32_t smem_dst, const void* g
     }
 }
 
+template <bool HASHED>
+__device__ __forceinline__ __half enc_one_pow2(const float* __restrict__ pts, uint32_t p, float scale, uint32_t bmask, uint32_t my, uint32_t mz,
+                                               const unsigned char* __restrict__ table) {
+    const float u0 = __ldg(pts + (size_t)p * 3), u1 = __ldg(pts + (size_t)p * 3 + 1), u2 = __ldg(pts + (size_t)p * 3 + 2);
+    float fr[3]; uint32_t cell[3];
+    mon_pos_fract(u0, scale, fr[0], cell[0]);
+    mon_pos_fract(u1, scale, fr[1], cell[1]);
+    mon_pos_fract(u2, scale, fr[2], cell[2]);
+    const float g0 = __fsub_rn(1.0f, fr[0]), g1 = __fsub_rn(1.0f, fr[1]), g2 = __fsub_rn(1.0f, fr[2]);
+    // (1*fx)*fy shared by the two z corners; same multiplication order as the reference
+    const float wxy[4] = {__fmul_rn(g0, g1), __fmul_rn(fr[0], g1), __fmul_rn(g0, fr[1]), __fmul_rn(fr[0], fr[1])};
+    // per-axis contributions to the byte offset
+    const uint32_t ax[2] = {cell[0] << 1, (cell[0] + 1u) << 1};
+    const uint32_t ay[2] = {(cell[1] * my) << 1, ((cell[1] + 1u) * my) << 1};
+    const uint32_t az[2] = {(cell[2] * mz) << 1, ((cell[2] + 1u) * mz) << 1};
+    __half acc = __float2half_rn(0.0f);
+#pragma unroll
+    for (uint32_t k = 0; k < 8; ++k) {
+        const float wgt = __fmul_rn(wxy[k & 3], (k & 4) ? fr[2] : g2);
+        const uint32_t off = (HASHED ? (ax[k & 1] ^ ay[(k >> 1) & 1] ^ az[k >> 2]) : (ax[k & 1] + ay[(k >> 1) & 1] + az[k >> 2])) & bmask;
+        const float wh = __half2float(__float2half_rn(wgt));
+        // generic load from a pointer the compiler knows to be shared: LDS.U16 with the base folded in
+        const unsigned short tv = *reinterpret_cast<const unsigned short*>(table + off);
+        acc = __float2half_rn(__fmaf_rn(wh, __half2float(__ushort_as_half(tv)), __half2float(acc)));
+    }
+    return acc;
+}
+
 // the inner loop for power-of-two tables (every table of the supported configurations): index arithmetic directly in
 // byte offsets of the shared-memory slice, ((a ^ b ^ c) & (size-1)) * 2 == (2a ^ 2b ^ 2c) & (2*size-2); HASHED selects
-// the coherent-prime hash or the dense (wrapping) linear index at compile time
+// the coherent-prime hash or the dense (wrapping) linear index at compile time.  Two points per trip: the 8-corner
+// fp16 rounding chain of a point is serial (FFMA -> F2F -> HADD2 per corner), a second independent chain hides it.
 template <bool HASHED>
 __device__ __forceinline__ void enc_points_pow2(const float* __restrict__ pts, __half* __restrict__ out, uint32_t p_first, uint32_t p_end,
                                                 float scale, uint32_t size, uint32_t res, const unsigned char* __restrict__ table) {
     const uint32_t bmask = 2u * size - 2u;
     const uint32_t my = HASHED ? 2654435761u : res, mz = HASHED ? 805459861u : res * res;
-    for (uint32_t p = p_first; p < p_end; p += ENC_THREADS) {
-        const float u0 = __ldg(pts + (size_t)p * 3), u1 = __ldg(pts + (size_t)p * 3 + 1), u2 = __ldg(pts + (size_t)p * 3 + 2);
-        float fr[3]; uint32_t cell[3];
-        mon_pos_fract(u0, scale, fr[0], cell[0]);
-        mon_pos_fract(u1, scale, fr[1], cell[1]);
-        mon_pos_fract(u2, scale, fr[2], cell[2]);
-        const float g0 = __fsub_rn(1.0f, fr[0]), g1 = __fsub_rn(1.0f, fr[1]), g2 = __fsub_rn(1.0f, fr[2]);
-        // (1*fx)*fy shared by the two z corners; same multiplication order as the reference
-        const float wxy[4] = {__fmul_rn(g0, g1), __fmul_rn(fr[0], g1), __fmul_rn(g0, fr[1]), __fmul_rn(fr[0], fr[1])};
-        // per-axis contributions to the byte offset
-        const uint32_t ax[2] = {cell[0] << 1, (cell[0] + 1u) << 1};
-        const uint32_t ay[2] = {(cell[1] * my) << 1, ((cell[1] + 1u) * my) << 1};
-        const uint32_t az[2] = {(cell[2] * mz) << 1, ((cell[2] + 1u) * mz) << 1};
-        __half acc = __float2half_rn(0.0f);
-#pragma unroll
-        for (uint32_t k = 0; k < 8; ++k) {
-            const float wgt = __fmul_rn(wxy[k & 3], (k & 4) ? fr[2] : g2);
-            const uint32_t off = (HASHED ? (ax[k & 1] ^ ay[(k >> 1) & 1] ^ az[k >> 2]) : (ax[k & 1] + ay[(k >> 1) & 1] + az[k >> 2])) & bmask;
-            const float wh = __half2float(__float2half_rn(wgt));
-            // generic load from a pointer the compiler knows to be shared: LDS.U16 [R + UR] with the base in a uniform register
-            const unsigned short tv = *reinterpret_cast<const unsigned short*>(table + off);
-            acc = __float2half_rn(__fmaf_rn(wh, __half2float(__ushort_as_half(tv)), __half2float(acc)));
-        }
-        out[(size_t)p * 2] = acc;
+    uint32_t p = p_first;
+#if ENC_UNROLL == 2
+    for (; p + ENC_THREADS < p_end; p += 2 * ENC_THREADS) {
+        const __half a = enc_one_pow2<HASHED>(pts, p, scale, bmask, my, mz, table);
+        const __half b = enc_one_pow2<HASHED>(pts, p + ENC_THREADS, scale, bmask, my, mz, table);
+        out[(size_t)p * 2] = a;
+        out[(size_t)(p + ENC_THREADS) * 2] = b;
     }
+#endif
+    for (; p < p_end; p += ENC_THREADS) out[(size_t)p * 2] = enc_one_pow2<HASHED>(pts, p, scale, bmask, my, mz, table);
 }
 
 // planar: per level [feature 0 table | feature 1 table], each size[l] fp16 (the level starts at 2*offset[l] halves)
@@ -250,6 +267,12 @@ void mon_launch_planarize(const MonGrid& g, const __half* inter, __half* planar,
 __device__ __forceinline__ void red_add_f16x2(__half2* addr, __half2 v) {
     asm volatile("red.global.add.noftz.f16x2 [%0], %1;" ::"l"(addr), "r"(*reinterpret_cast<const uint32_t*>(&v)) : "memory");
 }
+// two adjacent table entries (one aligned 8-byte word) in ONE reduction: the scatter is bound by the number of
+// reduction lane-operations the LSU can issue (REDG ~1.3 cycles per lane), not by bytes
+__device__ __forceinline__ void red_add_f16x2_pair(void* addr8, __half2 lo, __half2 hi) {
+    asm volatile("red.global.add.noftz.v2.f16x2 [%0], {%1, %2};" ::"l"(addr8), "r"(*reinterpret_cast<const uint32_t*>(&lo)),
+                 "r"(*reinterpret_cast<const uint32_t*>(&hi)) : "memory");
+}
 
 // Zero d_enc pairs (samples after the early stop) are skipped: adding +0 is an identity, so the result is unchanged.
 __global__ void __launch_bounds__(SCT_THREADS)
@@ -296,12 +319,27 @@ k_encode_backward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, c
                 ay[0] = (cell[1] * res) << 2; ay[1] = ((cell[1] + 1u) * res) << 2;
                 az[0] = (cell[2] * res * res) << 2; az[1] = ((cell[2] + 1u) * res * res) << 2;
             }
+            if ((cell[0] & 1u) == 0u && size >= 2u && (hashed || (res & 1u) == 0u)) {
+                // even x: the corners x and x+1 are entries 2j and 2j+1 (in either order) of one aligned 8-byte word,
+                // for the hash (x enters by XOR, bit 0 of x is clear) and for the dense index (the y/z strides are even)
 #pragma unroll
-            for (uint32_t k = 0; k < 8; ++k) {
-                const float wgt = __fmul_rn(wxy[k & 3], (k & 4) ? fr[2] : h2);
-                const uint32_t off = (hashed ? (ax[k & 1] ^ ay[(k >> 1) & 1] ^ az[k >> 2]) : (ax[k & 1] + ay[(k >> 1) & 1] + az[k >> 2])) & bmask;
-                const __half2 v = __floats2half2_rn(__fmul_rn(g0, wgt), __fmul_rn(g1, wgt));
-                red_add_f16x2(reinterpret_cast<__half2*>(tab + off), v);
+                for (uint32_t q = 0; q < 4; ++q) {
+                    const float wz = (q & 2) ? fr[2] : h2;
+                    const float w0 = __fmul_rn(wxy[(q & 1) * 2], wz), w1 = __fmul_rn(wxy[(q & 1) * 2 + 1], wz);
+                    const uint32_t off = (hashed ? (ax[0] ^ ay[q & 1] ^ az[q >> 1]) : (ax[0] + ay[q & 1] + az[q >> 1])) & bmask;
+                    const __half2 v0 = __floats2half2_rn(__fmul_rn(g0, w0), __fmul_rn(g1, w0));
+                    const __half2 v1 = __floats2half2_rn(__fmul_rn(g0, w1), __fmul_rn(g1, w1));
+                    const bool swap = (off & 4u) != 0u;     // corner x sits in the upper half of the word
+                    red_add_f16x2_pair(tab + (off & ~7u), swap ? v1 : v0, swap ? v0 : v1);
+                }
+            } else {
+#pragma unroll
+                for (uint32_t k = 0; k < 8; ++k) {
+                    const float wgt = __fmul_rn(wxy[k & 3], (k & 4) ? fr[2] : h2);
+                    const uint32_t off = (hashed ? (ax[k & 1] ^ ay[(k >> 1) & 1] ^ az[k >> 2]) : (ax[k & 1] + ay[(k >> 1) & 1] + az[k >> 2])) & bmask;
+                    const __half2 v = __floats2half2_rn(__fmul_rn(g0, wgt), __fmul_rn(g1, wgt));
+                    red_add_f16x2(reinterpret_cast<__half2*>(tab + off), v);
+                }
             }
         } else {
             EncCorner c;

@@ -30,6 +30,7 @@
 #include "mon_json.h"
 #include "mon_kernels.h"
 
+#define MON_DEBIAS_LUT 32768  // steps covered by the Adam bias-correction table (offline jobs run 5000 iterations)
 #define MON_GRAPH_CHUNK 50   // iterations captured per replayed graph (plus a 1-iteration graph for remainders)
 
 static thread_local std::string g_err;
@@ -206,6 +207,7 @@ struct mon_object {
     __half *enc = nullptr, *d_enc = nullptr;   // enc: level-major pairs [16][N][2]; d_enc: point-major [N][32]
     __half* ph_planar = nullptr;      // fp16 grid weights, per level [feature 0 | feature 1], kept current by the optimizer
     float* partials = nullptr;
+    float* debias_lut = nullptr;      // Adam bias correction by step count, MON_DEBIAS_LUT entries
     uint32_t n_ctas = 0;
     // parity hooks (lazily allocated)
     float *dbg_out = nullptr, *dbg_dout = nullptr, *inj_xy = nullptr, *inj_col = nullptr, *inj_dt = nullptr, *grad_snap = nullptr;
@@ -651,8 +653,8 @@ static int pipe_mode() {
     static int mode = -1;
     if (mode < 0) {
         const char* e = getenv("MON_PIPE");
-        mode = e ? atoi(e) : 1;
-        if (mode < 0 || mode > 3) mode = 1;
+        mode = e ? atoi(e) : 0;
+        if (mode < 0 || mode > 3) mode = 0;
     }
     return mode;
 }
@@ -840,6 +842,8 @@ int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uin
     OALLOC(o->pts, N * 12); OALLOC(o->pts_alt, N * 12); OALLOC(o->enc, N * MON_IN * 2); OALLOC(o->d_enc, N * MON_IN * 2);
     OALLOC(o->ph_planar, (size_t)o->n_grid * 2 + 16);
     OALLOC(o->partials, (size_t)o->n_ctas * o->n_mlp * 4);
+    OALLOC(o->debias_lut, (size_t)MON_DEBIAS_LUT * 4);
+    o->opt.debias_lut = o->debias_lut; o->opt.n_debias_lut = MON_DEBIAS_LUT;
 #undef OALLOC
     cudaError_t e;
     if ((e = cudaMallocHost(&o->h_ctrl, sizeof(MonCtrl))) != cudaSuccess ||
@@ -893,7 +897,8 @@ int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uin
     mon_launch_init_grid(rng.state, rng.inc, o->n_grid, o->pf + o->n_mlp, o->stream);
     mon_launch_cast_params((uint32_t)P, o->pf, o->ph, o->stream);
     mon_launch_planarize(o->grid, o->ph + o->n_mlp, o->ph_planar, o->stream);
-    o->launches += 3;
+    mon_launch_fill_debias_lut(o->opt, MON_DEBIAS_LUT, o->debias_lut, o->stream);
+    o->launches += 4;
     if ((e = cudaStreamSynchronize(o->stream)) != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) {
         mon_object_destroy(o);
         return fail(MON_ERR_CUDA, "param init: %s", cudaGetErrorString(e));
@@ -909,7 +914,7 @@ int mon_object_destroy(mon_object* o) {
     drop_graphs(o);
     void* ptrs[] = {o->pf, o->m, o->v, o->ps, o->ph, o->gh, o->ema, o->ctrl_state, o->ctrl, o->ctrl_alt, o->ctrl_late, o->rays_alt, o->ray_inst_alt,
                     o->target_alt, o->target_depth_alt, o->bg_alt, o->d_boxes, o->rays, o->ray_inst, o->target,
-                    o->target_depth, o->bg, o->rgb_rays, o->depth_rays, o->mask_rays, o->loss, o->pts, o->pts_alt, o->enc, o->d_enc, o->ph_planar, o->partials,
+                    o->target_depth, o->bg, o->rgb_rays, o->depth_rays, o->mask_rays, o->loss, o->pts, o->pts_alt, o->debias_lut, o->enc, o->d_enc, o->ph_planar, o->partials,
                     o->dbg_out, o->dbg_dout, o->inj_xy, o->inj_col, o->inj_dt, o->grad_snap, o->r_rays, o->r_inbox, o->r_enc,
                     o->r_jit, o->r_rgb, o->r_depth, o->r_mask, o->r_Twc, o->r_pts, o->r_planar};
     for (void* p : ptrs) if (p) cudaFree(p);

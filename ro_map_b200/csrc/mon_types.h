@@ -74,6 +74,8 @@ struct MonOpt {
     float log2_beta1, log2_beta2;   // beta^s is evaluated as exp2f(s * log2(beta))
     float inv_loss_scale;           // 1 / loss_scale, used when loss_scale is a power of two (exact)
     uint32_t loss_scale_pow2;
+    const float* debias_lut;        // [n_debias_lut] Adam bias correction by per-parameter step count (kernels_optim.cu)
+    uint32_t n_debias_lut;
 };
 
 struct MonLossCfg { float loss_scale, depth_lambda, mask_lambda, bg_density_reg; };

@@ -229,7 +229,6 @@ struct mon_object {
     // second batch buffer (rays, targets, control block): B(i+2) runs right after M(i), a whole iteration ahead
     MonRay* rays_alt = nullptr; uint8_t* ray_inst_alt = nullptr;
     float *target_alt = nullptr, *target_depth_alt = nullptr, *bg_alt = nullptr;
-    int prio_hi = 0, prio_lo = 0;     // stream priority range of the device (hi = numerically lowest)
     cudaGraphExec_t graph1 = nullptr, graphN = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timing_pending = false;
@@ -632,7 +631,11 @@ static int capture_graph(mon_object* o, int iters, cudaGraphExec_t* out) {
     return MON_OK;
 }
 
-// Level-pipelined iteration graph (default; MON_PIPE=0 selects the chain above).  The hash-grid levels are independent
+// Level-pipelined iteration graph (opt-in: MON_PIPE=1; the chain above is the default because it measured FASTER on
+// B200, 71 vs 81 us per iteration — profiles/r1i_pipeline_timelines.txt: cutting the scatter by level group
+// concentrates its atomics on the hot coarse tables (30 us for the four pieces vs 16.6 us whole), and the 1024-thread /
+// 128 KB encode CTAs cannot become resident beside the optimizer's CTAs, so the intended overlap does not happen).
+// The hash-grid levels are independent
 // between the end of the fused MLP kernel of iteration i and the start of the one of iteration i+1: the gradient of a
 // level is scattered (S), consumed by the optimizer (O) and the level is re-encoded (E) without touching any other
 // level.  So the S -> O -> E chain is cut by level group and the pieces overlap:
@@ -654,7 +657,7 @@ static int pipe_mode() {
     if (mode < 0) {
         const char* e = getenv("MON_PIPE");
         mode = e ? atoi(e) : 0;
-        if (mode < 0 || mode > 3) mode = 0;
+        if (mode != 1) mode = 0;
     }
     return mode;
 }
@@ -682,12 +685,10 @@ static int capture_graph_pipelined(mon_object* o, int iters, cudaGraphExec_t* ou
     float* const pts[2] = {o->pts, o->pts_alt};
     const PipeShape ps = pipe_shape(o);
     const uint32_t L = ps.L;
-    const int mode = pipe_mode();
-    // mode 1: no node priorities; 2: encode + MLP above scatter/optimizer; 3: scatter/optimizer above encode + MLP
-    auto opt = [&](bool front, bool pdl) {
+    // (kernel-node priorities were tried to favour either side of the overlap: no measurable effect, profiles/r1i)
+    auto opt = [&](bool, bool pdl) {
         MonLaunchOpt lo;
         lo.pdl = pdl;
-        if (mode != 1) { lo.set_priority = true; lo.priority = ((mode == 2) == front) ? o->prio_hi : o->prio_lo; }
         return lo;
     };
     cudaGraph_t g = nullptr;
@@ -854,7 +855,6 @@ int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uin
         (e = cudaEventCreateWithFlags(&o->ev_join, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&o->ev_pts, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&o->ev_aux, cudaEventDisableTiming)) != cudaSuccess ||
-        (e = cudaDeviceGetStreamPriorityRange(&o->prio_lo, &o->prio_hi)) != cudaSuccess ||
         (e = cudaEventCreate(&o->ev0)) != cudaSuccess || (e = cudaEventCreate(&o->ev1)) != cudaSuccess) {
         mon_object_destroy(o);
         return fail(MON_ERR_CUDA, "object setup: %s", cudaGetErrorString(e));

@@ -107,6 +107,6 @@ void mon_launch_optimizer(const MonOpt& o, MonCtrl* ctrl, float* pf, __half* ph,
                           float* m, float* v, uint32_t* ps, __half* ema, const float* loss, uint32_t R, const MonGrid& grid,
                           __half* planar, cudaStream_t st, int part = 0, uint32_t level_begin = 0, uint32_t level_end = 0xffffffffu,
                           const MonLaunchOpt& lo = MonLaunchOpt());
-enum { MON_OPT_ALL = 0, MON_OPT_MLP = 1, MON_OPT_GRID = 2 };
+enum { MON_OPT_ALL = 0, MON_OPT_MLP = 1, MON_OPT_GRID = 2, MON_OPT_MLP_GRID = 3 };
 void mon_launch_snapshot_grad(uint32_t n, uint32_t n_mlp, uint32_t n_partials, const __half* gh, const float* partials,
                               float* out, cudaStream_t st);

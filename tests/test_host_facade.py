@@ -87,7 +87,7 @@ def test_offline_nerf_on_disk_sequence(tmp_path, host_lib):
         assert np.allclose(np.linalg.norm(v[:, 3:6], axis=1), 1.0, atol=5e-3)
         # the surface spans the object (orientation and manifoldness are checked on an analytic field below; a model
         # trained on 8 views keeps floaters at the box faces, so no orientation statistic here)
-        assert (np.abs(v[:, :3]).max(0) > 0.6 * seq.objects[0].half).all()
+        assert (np.abs(v[:, :3]).max(0) > 0.4 * seq.objects[0].half).all()
 
 
 @pytest.mark.gpu

@@ -86,9 +86,7 @@ __device__ __forceinline__ void level_corners(const MonGrid& g, uint32_t l, cons
 #define ENC_THREADS 1024
 #define ENC_TABLE_BYTES (65536 * 2)
 #define ENC_BULK_CHUNK 16384u
-#ifndef ENC_UNROLL
-#define ENC_UNROLL 2   // two points in flight per thread: the 8-corner fp16 rounding chain is serial, a second chain hides its latency
-#endif
+#define ENC_UNROLL 2   // points in flight per thread (default; MON_ENC_UNROLL=1|2|3|4 selects another instantiation for A/B)
 
 __device__ __forceinline__ void bulk_load_table(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     // one thread: arm the barrier with the byte count, then issue the TMA bulk copies (global -> shared)
@@ -132,26 +130,28 @@ __device__ __forceinline__ __half enc_one_pow2(const float* __restrict__ pts, ui
 
 // the inner loop for power-of-two tables (every table of the supported configurations): index arithmetic directly in
 // byte offsets of the shared-memory slice, ((a ^ b ^ c) & (size-1)) * 2 == (2a ^ 2b ^ 2c) & (2*size-2); HASHED selects
-// the coherent-prime hash or the dense (wrapping) linear index at compile time.  Two points per trip: the 8-corner
-// fp16 rounding chain of a point is serial (FFMA -> F2F -> HADD2 per corner), a second independent chain hides it.
-template <bool HASHED>
+// the coherent-prime hash or the dense (wrapping) linear index at compile time.  U points per trip: the 8-corner
+// fp16 rounding chain of a point is serial (FFMA -> F2F -> HADD2 per corner), further independent chains hide it.
+template <bool HASHED, int U>
 __device__ __forceinline__ void enc_points_pow2(const float* __restrict__ pts, __half* __restrict__ out, uint32_t p_first, uint32_t p_end,
                                                 float scale, uint32_t size, uint32_t res, const unsigned char* __restrict__ table) {
     const uint32_t bmask = 2u * size - 2u;
     const uint32_t my = HASHED ? 2654435761u : res, mz = HASHED ? 805459861u : res * res;
     uint32_t p = p_first;
-#if ENC_UNROLL == 2
-    for (; p + ENC_THREADS < p_end; p += 2 * ENC_THREADS) {
-        const __half a = enc_one_pow2<HASHED>(pts, p, scale, bmask, my, mz, table);
-        const __half b = enc_one_pow2<HASHED>(pts, p + ENC_THREADS, scale, bmask, my, mz, table);
-        out[(size_t)p * 2] = a;
-        out[(size_t)(p + ENC_THREADS) * 2] = b;
+    if (U > 1) {
+        for (; p + (U - 1) * ENC_THREADS < p_end; p += U * ENC_THREADS) {
+            __half a[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) a[u] = enc_one_pow2<HASHED>(pts, p + u * ENC_THREADS, scale, bmask, my, mz, table);
+#pragma unroll
+            for (int u = 0; u < U; ++u) out[(size_t)(p + u * ENC_THREADS) * 2] = a[u];
+        }
     }
-#endif
     for (; p < p_end; p += ENC_THREADS) out[(size_t)p * 2] = enc_one_pow2<HASHED>(pts, p, scale, bmask, my, mz, table);
 }
 
 // planar: per level [feature 0 table | feature 1 table], each size[l] fp16 (the level starts at 2*offset[l] halves)
+template <int U>
 __global__ void __launch_bounds__(ENC_THREADS, 1)
 k_encode_forward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, const __half* __restrict__ planar,
                  __half* __restrict__ enc_soa, const MonCtrl* __restrict__ ctrl, uint32_t job_begin, uint32_t job_end) {
@@ -193,8 +193,8 @@ k_encode_forward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, co
         const bool pow2 = (size & (size - 1)) == 0;
         __half* out = enc_soa + (size_t)l * n_points * 2 + f;   // level-major pairs: enc[level][point][feature]
         if (pow2) {
-            if (hashed) enc_points_pow2<true>(pts, out, p0 + tid, p1, scale, size, res, enc_smem);
-            else enc_points_pow2<false>(pts, out, p0 + tid, p1, scale, size, res, enc_smem);
+            if (hashed) enc_points_pow2<true, U>(pts, out, p0 + tid, p1, scale, size, res, enc_smem);
+            else enc_points_pow2<false, U>(pts, out, p0 + tid, p1, scale, size, res, enc_smem);
         } else {
             for (uint32_t p = p0 + tid; p < p1; p += ENC_THREADS) {
                 const float u0 = __ldg(pts + (size_t)p * 3), u1 = __ldg(pts + (size_t)p * 3 + 1), u2 = __ldg(pts + (size_t)p * 3 + 2);
@@ -220,16 +220,23 @@ k_encode_forward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, co
     }
 }
 
+template <int U>
+static cudaError_t enc_launch(const MonGrid& g, uint32_t n_points, const float* pts, const __half* planar, __half* enc_soa, const MonCtrl* ctrl,
+                              uint32_t ctas, cudaStream_t st, uint32_t level_begin, uint32_t level_end, const MonLaunchOpt& lo) {
+    static std::atomic<uint64_t> prepared{0};
+    const cudaError_t prep = mon_once_per_device(prepared, [] {
+        cudaError_t e = cudaFuncSetAttribute(k_encode_forward<U>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(k_encode_forward<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_TABLE_BYTES);
+    });
+    if (prep != cudaSuccess) return prep;
+    return mon_launch_chain(MON_PDL_ENCODE, lo, k_encode_forward<U>, dim3(ctas), dim3(ENC_THREADS), ENC_TABLE_BYTES, st, g, n_points, pts, planar, enc_soa, ctrl,
+                            2 * level_begin, 2 * level_end);
+}
+
 cudaError_t mon_launch_encode_forward(const MonGrid& g, uint32_t n_points, const float* pts, const __half* planar, __half* enc_soa,
                                       const MonCtrl* ctrl, uint32_t sm_count, cudaStream_t st, uint32_t level_begin, uint32_t level_end,
                                       const MonLaunchOpt& lo) {
-    static std::atomic<uint64_t> prepared{0};
-    const cudaError_t prep = mon_once_per_device(prepared, [] {
-        cudaError_t e = cudaFuncSetAttribute(k_encode_forward, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return e;
-        return cudaFuncSetAttribute(k_encode_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_TABLE_BYTES);
-    });
-    if (prep != cudaSuccess) return prep;
     if (level_end > g.n_levels) level_end = g.n_levels;
     if (n_points == 0 || level_begin >= level_end) return cudaSuccess;
     // every CTA loads up to two 128 KB slices: do not spread tiny batches over the whole chip
@@ -237,8 +244,13 @@ cudaError_t mon_launch_encode_forward(const MonGrid& g, uint32_t n_points, const
     const uint64_t want = (total + 16383) / 16384;
     uint32_t ctas = want < (uint64_t)sm_count ? (uint32_t)want : sm_count;
     if (ctas == 0) ctas = 1;
-    return mon_launch_chain(MON_PDL_ENCODE, lo, k_encode_forward, dim3(ctas), dim3(ENC_THREADS), ENC_TABLE_BYTES, st, g, n_points, pts, planar, enc_soa, ctrl,
-                            2 * level_begin, 2 * level_end);
+    static const int unroll = [] { const char* e = getenv("MON_ENC_UNROLL"); const int u = e ? atoi(e) : ENC_UNROLL; return (u >= 1 && u <= 4) ? u : ENC_UNROLL; }();
+    switch (unroll) {
+        case 1: return enc_launch<1>(g, n_points, pts, planar, enc_soa, ctrl, ctas, st, level_begin, level_end, lo);
+        case 3: return enc_launch<3>(g, n_points, pts, planar, enc_soa, ctrl, ctas, st, level_begin, level_end, lo);
+        case 4: return enc_launch<4>(g, n_points, pts, planar, enc_soa, ctrl, ctas, st, level_begin, level_end, lo);
+        default: return enc_launch<2>(g, n_points, pts, planar, enc_soa, ctrl, ctas, st, level_begin, level_end, lo);
+    }
 }
 
 // interleaved fp16 weights [entry][2] -> planar per level [f0 table | f1 table] (initialisation / set_params; the

@@ -812,6 +812,10 @@ int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uin
     // fused MLP kernel: persistent grid of all co-resident CTAs (4 per SM with one hidden layer, 2 with two: TMEM
     // columns and shared memory, kernels_mlp_tc.cu), never more CTAs than 4-ray tiles
     o->n_ctas = std::min<uint32_t>((uint32_t)o->sm_count * (cfg->n_hidden_layers == 1 ? 4u : 2u), (o->R + 3) / 4);
+    if (const char* env = getenv("MON_MLP_CTAS")) {   // A/B: persistent-grid size of the fused MLP kernel
+        const int v = atoi(env);
+        if (v > 0) o->n_ctas = std::min<uint32_t>((uint32_t)v, o->n_ctas);
+    }
     if (o->n_ctas > MON_MAX_MLP_CTAS) o->n_ctas = MON_MAX_MLP_CTAS;
     o->opt.lr = cfg->learning_rate; o->opt.beta1 = cfg->beta1; o->opt.beta2 = cfg->beta2; o->opt.eps = cfg->epsilon;
     o->opt.l2_reg = cfg->l2_reg; o->opt.ema_decay = cfg->ema_decay; o->opt.loss_scale = cfg->loss_scale;

@@ -300,8 +300,9 @@ k_encode_backward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, c
     // levels [level_begin, level_end), level_begin a multiple of 4: thread quarter lg owns levels level_begin + 4*lg + j
     const uint4 gv = reinterpret_cast<const uint4*>(d_enc + (size_t)pt * MON_IN)[(level_begin >> 2) + lg];
     const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
-    if (((gv.x | gv.y | gv.z | gv.w) & 0x7fff7fffu) == 0) return;
+    // position fetched beside the gradient, not behind the zero test: one L2 round trip per thread instead of two
     const float u[3] = {__ldg(pts + (size_t)pt * 3), __ldg(pts + (size_t)pt * 3 + 1), __ldg(pts + (size_t)pt * 3 + 2)};
+    if (((gv.x | gv.y | gv.z | gv.w) & 0x7fff7fffu) == 0) return;
 #pragma unroll
     for (uint32_t j = 0; j < 4; ++j) {
         const uint32_t l = level_begin + lg * 4 + j;

@@ -190,6 +190,7 @@ k_optimizer_sweep(MonOpt o, MonCtrl* __restrict__ ctrl, float* __restrict__ pf, 
     __half wh[4] = {__ushort_as_half((unsigned short)(wraw.x & 0xffffu)), __ushort_as_half((unsigned short)(wraw.x >> 16)),
                     __ushort_as_half((unsigned short)(wraw.y & 0xffffu)), __ushort_as_half((unsigned short)(wraw.y >> 16))};
     if (any) {
+        // (fetching this state speculatively beside the gradient was tried: no gain, the sweep is not bound by that chain)
         float4 w4 = *reinterpret_cast<const float4*>(pf + i4);
         float4 m4 = *reinterpret_cast<const float4*>(m + i4);
         float4 v4 = *reinterpret_cast<const float4*>(v + i4);

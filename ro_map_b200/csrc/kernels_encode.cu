@@ -23,6 +23,15 @@
 #include "tc05.cuh"
 #include "mon_timeline.cuh"
 MON_TL_DEFINE(encode)
+#ifdef MON_TIMELINE
+// per-CTA [table resident, done] of the encode kernel for one iteration (iter % 64 == 20): load balance of the split
+static __device__ unsigned long long mon_tl_enc_cta[256 * 2];
+extern "C" int mon_debug_tl_enc_cta_read(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, mon_tl_enc_cta, sizeof(mon_tl_enc_cta)); }
+#define ENC_CTA_STAMP(slot) do { if (threadIdx.x == 0 && blockIdx.x < 256 && ctrl && (ctrl->iter - 1) % 64 == 20) { \
+        unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); mon_tl_enc_cta[blockIdx.x * 2 + (slot)] = t_; } } while (0)
+#else
+#define ENC_CTA_STAMP(slot) do { } while (0)
+#endif
 
 // ---------------------------------------------------------------------------------------------- sample points
 // A3: t_n = tmin + dt*(n + xi), p = o + t*d, u = (p - bmin) / (bmax - bmin)  (nerf_model.cu:545-565,140-144).
@@ -150,11 +159,42 @@ __device__ __forceinline__ void enc_points_pow2(const float* __restrict__ pts, _
     for (; p < p_end; p += ENC_THREADS) out[(size_t)p * 2] = enc_one_pow2<HASHED>(pts, p, scale, bmask, my, mz, table);
 }
 
+// Cost model of the forward kernel for the work split, in 1/64 of a hashed-level point: a point costs W_class, and
+// starting a job costs L_class (staging its table slice: ~1.5 us for 128 KB, i.e. ~2300 hashed points of one CTA), so a
+// CTA whose piece spans a job boundary — and therefore stages two slices — gets that much less point work.
+#define ENC_W_SMALL 56u    // dense, <= 4096 entries
+#define ENC_W_LARGE 75u    // dense, larger
+#define ENC_W_HASH 64u
+#define ENC_L_SMALL 9000ull
+#define ENC_L_LARGE 87000ull
+#define ENC_L_HASH 148000ull
+struct EncPos { uint32_t job, p; };
+__host__ __device__ __forceinline__ uint64_t enc_cost_total(uint32_t n, uint32_t jb, uint32_t jl, uint32_t jh, uint32_t je) {
+    return (uint64_t)(jl - jb) * ((uint64_t)n * ENC_W_SMALL + ENC_L_SMALL) + (uint64_t)(jh - jl) * ((uint64_t)n * ENC_W_LARGE + ENC_L_LARGE) +
+           (uint64_t)(je - jh) * ((uint64_t)n * ENC_W_HASH + ENC_L_HASH);
+}
+// position in the flattened [job][point] space at cumulative cost c (monotone; the same expression gives one CTA's end and
+// the next one's begin, so the pieces tile the space exactly)
+__host__ __device__ __forceinline__ EncPos enc_cost_to_pos(uint64_t c, uint32_t n, uint32_t jb, uint32_t jl, uint32_t jh) {
+    const uint64_t js = (uint64_t)n * ENC_W_SMALL + ENC_L_SMALL, jg = (uint64_t)n * ENC_W_LARGE + ENC_L_LARGE, jhh = (uint64_t)n * ENC_W_HASH + ENC_L_HASH;
+    const uint64_t c0 = js * (jl - jb), c1 = jg * (jh - jl);
+    uint64_t per, load, w; uint32_t base;
+    if (c < c0) { per = js; load = ENC_L_SMALL; w = ENC_W_SMALL; base = jb; }
+    else if (c < c0 + c1) { c -= c0; per = jg; load = ENC_L_LARGE; w = ENC_W_LARGE; base = jl; }
+    else { c -= c0 + c1; per = jhh; load = ENC_L_HASH; w = ENC_W_HASH; base = jh; }
+    const uint64_t j = c / per, rem = c - j * per;
+    EncPos r;
+    r.job = base + (uint32_t)j;
+    r.p = rem <= load ? 0u : (uint32_t)((rem - load) / w);     // < n because rem < per
+    return r;
+}
+
 // planar: per level [feature 0 table | feature 1 table], each size[l] fp16 (the level starts at 2*offset[l] halves)
 template <int U>
 __global__ void __launch_bounds__(ENC_THREADS, 1)
 k_encode_forward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, const __half* __restrict__ planar,
-                 __half* __restrict__ enc_soa, const MonCtrl* __restrict__ ctrl, uint32_t job_begin, uint32_t job_end) {
+                 __half* __restrict__ enc_soa, const MonCtrl* __restrict__ ctrl, uint32_t job_begin, uint32_t job_end,
+                 uint32_t job_large, uint32_t job_hashed) {
     extern __shared__ __align__(128) unsigned char enc_smem[];
     __shared__ __align__(8) uint64_t bar;
     const __half* table = reinterpret_cast<const __half*>(enc_smem);
@@ -166,17 +206,23 @@ k_encode_forward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, co
     if (ctrl && ctrl->skip) return;
     MON_TL(MON_TL_E + ((job_begin >> 3) & 3u), ctrl ? ctrl->iter - 1 : 0u);
 
-    // jobs [job_begin, job_end) of the 2 * n_levels (level, feature) jobs: the level-pipelined iteration graph runs the
-    // coarse and the fine half of the levels as two launches (mon_core.cu capture_graph)
-    const uint64_t total = (uint64_t)(job_end - job_begin) * n_points;
-    uint64_t w = total * blockIdx.x / gridDim.x;
-    const uint64_t w_end = total * (blockIdx.x + 1) / gridDim.x;
+    // jobs [job_begin, job_end) of the 2 * n_levels (level, feature) jobs (the level-pipelined graph launches sub-ranges).
+    // The flattened [job][point] space is cut into one contiguous piece per CTA, equal in COST: a point of a dense level
+    // is not as expensive as one of a hashed level, because the kernel is bound by shared-memory wavefronts and the
+    // bank-conflict degree of a warp's 32 gathers differs (measured per-CTA times and a bank simulation of the batch's
+    // rays agree: hashed ~3.5-way, 17 us; dense 16^3 table 2.6-way, 15 us; dense 32^3 table 4.2-way, 20 us —
+    // profiles/r1p_encode_balance.txt).  Three cost classes in level order — small dense [job_begin, job_large), large
+    // dense [job_large, job_hashed), hashed [job_hashed, job_end) — make the cost -> (job, point) map closed-form
+    // (a per-job search through the dynamically indexed kernel parameters costs microseconds of dependent LDCU latency).
+    const EncPos pos_b = enc_cost_to_pos(enc_cost_total(n_points, job_begin, job_large, job_hashed, job_end) * blockIdx.x / gridDim.x,
+                                         n_points, job_begin, job_large, job_hashed);
+    const EncPos pos_e = enc_cost_to_pos(enc_cost_total(n_points, job_begin, job_large, job_hashed, job_end) * (blockIdx.x + 1) / gridDim.x,
+                                         n_points, job_begin, job_large, job_hashed);
     uint32_t phase = 0;
-    while (w < w_end) {
-        const uint32_t job_rel = (uint32_t)(w / n_points);
-        const uint32_t job = job_begin + job_rel;
-        const uint32_t p0 = (uint32_t)(w - (uint64_t)job_rel * n_points);
-        const uint32_t p1 = (uint32_t)min((uint64_t)n_points, (uint64_t)p0 + (w_end - w));
+    for (uint32_t job = pos_b.job; job < job_end && (job < pos_e.job || (job == pos_e.job && pos_e.p > 0)); ++job) {
+        const uint32_t p0 = job == pos_b.job ? pos_b.p : 0u;
+        const uint32_t p1 = job == pos_e.job ? pos_e.p : n_points;
+        if (p1 <= p0) continue;
         const uint32_t l = job >> 1, f = job & 1;
         const uint32_t size = g.size[l];
         __syncthreads();                                   // the previous slice is no longer read by anyone
@@ -185,6 +231,8 @@ k_encode_forward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, co
             bulk_load_table(tc05::smem_u32(enc_smem), planar + (size_t)g.offset[l] * 2 + (size_t)f * size, size * 2, &bar);
         }
         tc05::mbar_wait(&bar, phase);
+        // whole-range launches only (the chain graph): E1 = [first, last] CTA whose first slice is resident
+        if (phase == 0 && job_begin == 0 && job_end == 2 * g.n_levels) { MON_TL_MARK(MON_TL_E + 1, ctrl ? ctrl->iter - 1 : 0u); ENC_CTA_STAMP(0); }
         phase ^= 1u;
 
         const float scale = g.scale[l];
@@ -216,8 +264,9 @@ k_encode_forward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, co
                 out[(size_t)p * 2] = acc;
             }
         }
-        w += p1 - p0;
     }
+    // E2 = [first, last] CTA done (load imbalance of the flattened [job][point] split)
+    if (job_begin == 0 && job_end == 2 * g.n_levels) { MON_TL_MARK(MON_TL_E + 2, ctrl ? ctrl->iter - 1 : 0u); ENC_CTA_STAMP(1); }
 }
 
 template <int U>
@@ -230,8 +279,13 @@ static cudaError_t enc_launch(const MonGrid& g, uint32_t n_points, const float* 
         return cudaFuncSetAttribute(k_encode_forward<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_TABLE_BYTES);
     });
     if (prep != cudaSuccess) return prep;
+    // cost classes in level order (res grows with the level: small dense, then large dense, then hashed)
+    uint32_t l_large = level_begin, l_hashed = level_begin;
+    while (l_large < level_end && !g.hashed[l_large] && g.size[l_large] <= 4096u) ++l_large;
+    l_hashed = l_large;
+    while (l_hashed < level_end && !g.hashed[l_hashed]) ++l_hashed;
     return mon_launch_chain(MON_PDL_ENCODE, lo, k_encode_forward<U>, dim3(ctas), dim3(ENC_THREADS), ENC_TABLE_BYTES, st, g, n_points, pts, planar, enc_soa, ctrl,
-                            2 * level_begin, 2 * level_end);
+                            2 * level_begin, 2 * level_end, 2 * l_large, 2 * l_hashed);
 }
 
 cudaError_t mon_launch_encode_forward(const MonGrid& g, uint32_t n_points, const float* pts, const __half* planar, __half* enc_soa,

@@ -556,6 +556,13 @@ static int launch_mlp(mon_object* o, const MonBatch& b, cudaStream_t st) {
     return MON_OK;
 }
 static void launch_scatter(mon_object* o, cudaStream_t st) {
+#ifdef MON_TIMELINE
+    // timing experiments only (instrumented build): MON_DEBUG_SCATTER_LEVELS="b,e" scatters a sub-range of the levels
+    if (const char* env = getenv("MON_DEBUG_SCATTER_LEVELS")) {
+        unsigned b = 0, e = 0;
+        if (sscanf(env, "%u,%u", &b, &e) == 2) { mon_launch_encode_backward(o->grid, o->N, o->pts, o->ctrl_late, o->d_enc, o->gh + o->n_mlp, st, b, e); return; }
+    }
+#endif
     mon_launch_encode_backward(o->grid, o->N, o->pts, o->ctrl_late, o->d_enc, o->gh + o->n_mlp, st);
 }
 static void launch_optimizer(mon_object* o, cudaStream_t st) {

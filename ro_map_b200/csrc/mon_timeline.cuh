@@ -38,7 +38,17 @@ struct MonTlSlot { unsigned long long start, end; };
         __device__ MonTlScope_(MonTlSlot* p) : s(threadIdx.x == 0 ? p : nullptr) { if (s) atomicMin(&s->start, now()); } \
         __device__ ~MonTlScope_() { if (s) atomicMax(&s->end, now()); }                                             \
     } mon_tl_scope_(&mon_tl_tab[((iter) % MON_TL_ITERS) * MON_TL_KINDS + (kind)])
+// a point event folded into [earliest, latest] over the CTAs (e.g. "first table slice resident", "CTA done")
+#define MON_TL_MARK(kind, iter)                                                                                     \
+    do {                                                                                                            \
+        if (threadIdx.x == 0) {                                                                                     \
+            unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                           \
+            MonTlSlot* s_ = &mon_tl_tab[((iter) % MON_TL_ITERS) * MON_TL_KINDS + (kind)];                           \
+            atomicMin(&s_->start, t_); atomicMax(&s_->end, t_);                                                     \
+        }                                                                                                           \
+    } while (0)
 #else
 #define MON_TL_DEFINE(name)
 #define MON_TL(kind, iter) do { } while (0)
+#define MON_TL_MARK(kind, iter) do { } while (0)
 #endif

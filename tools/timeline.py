@@ -86,3 +86,17 @@ for it in range(420, 426):
     periods.append((nxt - m0) / 1e3)
     print(f"iter {it}: period {(nxt - m0) / 1e3:.1f} us  " + " ".join(row))
 print(json.dumps({"mean_period_us": round(float(np.mean(periods)), 2)}))
+
+# per-CTA load balance of the encode kernel (iteration 404 + 16 = slot 20 of the instrumented replay)
+try:
+    buf = np.zeros((256, 2), np.uint64)
+    assert lib.mon_debug_tl_enc_cta_read(buf.ctypes.data_as(C.c_void_p)) == 0
+    live = buf[:, 1] > 0
+    t0 = int(buf[live, 0].min())
+    dur = (buf[live, 1].astype(np.int64) - t0) / 1e3
+    load = (buf[live, 0].astype(np.int64) - t0) / 1e3
+    print("encode per-CTA done time after the first table became resident (us), CTA 0..%d:" % (live.sum() - 1))
+    print(" ".join(f"{d:.1f}" for d in dur))
+    print("table resident (us): " + " ".join(f"{d:.1f}" for d in load))
+except AttributeError:
+    pass

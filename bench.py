@@ -33,11 +33,11 @@ S = 32
 FRAMES = 30        # 30 keyframes x (1.92 MB rgb + 0.64 MB mask + 2.56 MB depth) = 154 MB > 126 MB L2
 BYTES_ENC_PER_POINT = 512       # 16 levels x 8 corners x 2 features x 2 B
 FLOPS_MLP_TRAIN_PER_POINT = {1: 18432, 2: 43008}
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of each kernel, from the committed ncu --set full capture
-# (profiles/r1e_ncu_kernels.txt, profiles/r1d_ncu_mlp_optimizer.txt); bytes
-# r1e / r1d captures at R=4096, one hidden layer.  ncu flushes the caches before every replayed launch, so these are
-# COLD-cache figures: in the running job the 46 MB of per-object state stays L2-resident between kernels.
-TRAFFIC_NCU = {"encode": 5.41e6, "scatter": 12.85e6, "mlp_fused": 8.70e6, "optimizer": 50.3e6}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of each kernel, from the committed ncu --set full captures
+# (profiles/r1t_ncu_kernels.txt: encode, scatter, fused MLP; profiles/r1d_ncu_mlp_optimizer.txt: optimizer) at R=4096,
+# one hidden layer.  ncu flushes the caches before every replayed launch, so these are COLD-cache figures: in the
+# running job the 46 MB of per-object state stays L2-resident between kernels.
+TRAFFIC_NCU = {"encode": 5.42e6, "scatter": 12.77e6, "mlp_fused": 8.70e6, "optimizer": 50.3e6}
 
 
 def parse():

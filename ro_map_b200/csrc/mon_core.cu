@@ -1050,23 +1050,30 @@ int mon_object_train_profiled(mon_object* o, uint32_t iters, float* stage_ms, ui
     if (n_stages != MON_N_STAGES) return fail(MON_ERR_ARG, "n_stages must be %d", MON_N_STAGES);
     if (o->h_boxes.empty()) return fail(MON_ERR_STATE, "no 2-D boxes: call mon_object_set_bboxes first");
     CK(cudaSetDevice(o->ds->gpu));
-    cudaEvent_t ev[MON_N_STAGES + 1];
+    // all iterations are enqueued back to back (one event set per iteration, one synchronisation at the end), so the
+    // stage times are not inflated by the host catching up after a per-iteration sync
+    const uint32_t chunk = std::min<uint32_t>(iters, 64u);
+    std::vector<cudaEvent_t> ev((size_t)chunk * (MON_N_STAGES + 1), nullptr);
     for (auto& x : ev) CK(cudaEventCreate(&x));
     double acc[MON_N_STAGES] = {0};
     const MonBatch b = make_batch(o, false, false);
     int rc = MON_OK;
-    for (uint32_t it = 0; it < iters && rc == MON_OK; ++it) {
-        int n = 0;
-        rc = enqueue_iteration(o, b, false, &n, ev);
-        if (rc != MON_OK) break;
-        o->launches += (uint64_t)n;
-        cudaError_t e = cudaStreamSynchronize(o->stream);
-        if (e != cudaSuccess) { rc = fail(MON_ERR_CUDA, "profiled iteration: %s", cudaGetErrorString(e)); break; }
-        for (int k = 0; k < MON_N_STAGES; ++k) {
-            float ms = 0.0f;
-            cudaEventElapsedTime(&ms, ev[k], ev[k + 1]);
-            acc[k] += ms;
+    for (uint32_t done = 0; done < iters && rc == MON_OK; done += chunk) {
+        const uint32_t n_it = std::min(chunk, iters - done);
+        for (uint32_t it = 0; it < n_it && rc == MON_OK; ++it) {
+            int n = 0;
+            rc = enqueue_iteration(o, b, false, &n, &ev[(size_t)it * (MON_N_STAGES + 1)]);
+            if (rc == MON_OK) o->launches += (uint64_t)n;
         }
+        if (rc != MON_OK) break;
+        cudaError_t e = cudaStreamSynchronize(o->stream);
+        if (e != cudaSuccess) { rc = fail(MON_ERR_CUDA, "profiled iterations: %s", cudaGetErrorString(e)); break; }
+        for (uint32_t it = 0; it < n_it; ++it)
+            for (int k = 0; k < MON_N_STAGES; ++k) {
+                float ms = 0.0f;
+                cudaEventElapsedTime(&ms, ev[(size_t)it * (MON_N_STAGES + 1) + k], ev[(size_t)it * (MON_N_STAGES + 1) + k + 1]);
+                acc[k] += ms;
+            }
     }
     for (auto& x : ev) cudaEventDestroy(x);
     if (rc != MON_OK) return rc;

@@ -341,9 +341,125 @@ __device__ __forceinline__ void red_add_f16x2_pair(void* addr8, __half2 lo, __ha
 }
 
 // Zero d_enc pairs (samples after the early stop) are skipped: adding +0 is an identity, so the result is unchanged.
-__global__ void __launch_bounds__(SCT_THREADS)
+// one (sample, level): grad[idx_c] += half2(d_enc * w_c) over the 8 corners.  gwj = the level's two fp16 gradients.
+__device__ __forceinline__ void scatter_level(const MonGrid& g, uint32_t l, uint32_t gwj, const float (&u)[3], __half* __restrict__ grid_grad) {
+            const float g0 = __half2float(__ushort_as_half((unsigned short)(gwj & 0xffffu)));
+            const float g1 = __half2float(__ushort_as_half((unsigned short)(gwj >> 16)));
+            const uint32_t size = g.size[l];
+            char* tab = reinterpret_cast<char*>(reinterpret_cast<__half2*>(grid_grad) + g.offset[l]);
+            if ((size & (size - 1)) == 0) {
+                // same index arithmetic as the forward kernel, directly in byte offsets of the 4-byte entries
+                const float scale = g.scale[l];
+                const uint32_t res = g.res[l];
+                const bool hashed = g.hashed[l] != 0;
+                const uint32_t bmask = 4u * size - 4u;
+                float fr[3]; uint32_t cell[3];
+                mon_pos_fract(u[0], scale, fr[0], cell[0]);
+                mon_pos_fract(u[1], scale, fr[1], cell[1]);
+                mon_pos_fract(u[2], scale, fr[2], cell[2]);
+                const float h0 = __fsub_rn(1.0f, fr[0]), h1 = __fsub_rn(1.0f, fr[1]), h2 = __fsub_rn(1.0f, fr[2]);
+                const float wxy[4] = {__fmul_rn(h0, h1), __fmul_rn(fr[0], h1), __fmul_rn(h0, fr[1]), __fmul_rn(fr[0], fr[1])};
+                uint32_t ax[2], ay[2], az[2];
+                ax[0] = cell[0] << 2; ax[1] = (cell[0] + 1u) << 2;
+                if (hashed) {
+                    ay[0] = (cell[1] * 2654435761u) << 2; ay[1] = ((cell[1] + 1u) * 2654435761u) << 2;
+                    az[0] = (cell[2] * 805459861u) << 2; az[1] = ((cell[2] + 1u) * 805459861u) << 2;
+                } else {
+                    ay[0] = (cell[1] * res) << 2; ay[1] = ((cell[1] + 1u) * res) << 2;
+                    az[0] = (cell[2] * res * res) << 2; az[1] = ((cell[2] + 1u) * res * res) << 2;
+                }
+                if ((cell[0] & 1u) == 0u && size >= 2u && (hashed || (res & 1u) == 0u)) {
+                    // even x: the corners x and x+1 are entries 2j and 2j+1 (in either order) of one aligned 8-byte word,
+                    // for the hash (x enters by XOR, bit 0 of x is clear) and for the dense index (the y/z strides are even)
+    #pragma unroll
+                    for (uint32_t q = 0; q < 4; ++q) {
+                        const float wz = (q & 2) ? fr[2] : h2;
+                        const float w0 = __fmul_rn(wxy[(q & 1) * 2], wz), w1 = __fmul_rn(wxy[(q & 1) * 2 + 1], wz);
+                        const uint32_t off = (hashed ? (ax[0] ^ ay[q & 1] ^ az[q >> 1]) : (ax[0] + ay[q & 1] + az[q >> 1])) & bmask;
+                        const __half2 v0 = __floats2half2_rn(__fmul_rn(g0, w0), __fmul_rn(g1, w0));
+                        const __half2 v1 = __floats2half2_rn(__fmul_rn(g0, w1), __fmul_rn(g1, w1));
+                        const bool swap = (off & 4u) != 0u;     // corner x sits in the upper half of the word
+                        red_add_f16x2_pair(tab + (off & ~7u), swap ? v1 : v0, swap ? v0 : v1);
+                    }
+                } else {
+    #pragma unroll
+                    for (uint32_t k = 0; k < 8; ++k) {
+                        const float wgt = __fmul_rn(wxy[k & 3], (k & 4) ? fr[2] : h2);
+                        const uint32_t off = (hashed ? (ax[k & 1] ^ ay[(k >> 1) & 1] ^ az[k >> 2]) : (ax[k & 1] + ay[(k >> 1) & 1] + az[k >> 2])) & bmask;
+                        const __half2 v = __floats2half2_rn(__fmul_rn(g0, wgt), __fmul_rn(g1, wgt));
+                        red_add_f16x2(reinterpret_cast<__half2*>(tab + off), v);
+                    }
+                }
+            } else {
+                EncCorner c;
+                level_corners(g, l, u, c);
+    #pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const __half2 v = __halves2half2(__float2half_rn(__fmul_rn(g0, c.w[k])), __float2half_rn(__fmul_rn(g1, c.w[k])));
+                    red_add_f16x2(reinterpret_cast<__half2*>(tab) + c.idx[k], v);
+                }
+            }
+}
+
+// Compacted scatter.  A warp of the fused MLP kernel is one ray and most of its samples sit behind the early stop
+// (T < 1e-4) with an all-zero gradient row: in steady state only ~1 sample in 6 carries gradient, and a
+// thread-per-sample scatter runs its warps for a handful of live lanes (profiles/r1t_ncu_kernels.txt: 72 % of the
+// (warp, level) blocks execute, issue slots 68 % busy).  Here the CTA first compacts the live samples of its
+// 128-sample tile into shared memory (gradient rows transposed to [level][rank], positions to [axis][rank]) and then
+// warp w scatters level w for the live samples only: lanes are filled with real work and the level — table base,
+// scale, hash or dense — is uniform across the warp.
+__global__ void __launch_bounds__(SCT_THREADS, 3)
 k_encode_backward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, const MonCtrl* __restrict__ ctrl,
                   const __half* __restrict__ d_enc, __half* __restrict__ grid_grad, uint32_t level_begin, uint32_t level_end) {
+    __shared__ uint32_t s_g[MON_IN / 2][SCT_TILE];   // [level][rank]: the two fp16 gradients of the level
+    __shared__ float s_u[3][SCT_TILE];               // [axis][rank]
+    __shared__ uint32_t s_live[SCT_TILE / 32];       // live-sample mask per 32-sample group (OR over the 4 row quarters)
+    mon_pdl_wait();
+    mon_pdl_trigger();
+    if (ctrl->skip) return;
+    MON_TL(MON_TL_S + ((level_begin >> 2) & 3u), ctrl->iter - 1);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t p = tid & (SCT_TILE - 1), q = tid >> 7, grp = p >> 5;   // sample in the tile, quarter of its gradient row (4 levels), 32-sample group
+    const uint32_t pt = blockIdx.x * SCT_TILE + p;
+    if (tid < SCT_TILE / 32) s_live[tid] = 0u;
+    uint4 gv = make_uint4(0u, 0u, 0u, 0u);
+    float u0 = 0.0f, u1 = 0.0f, u2 = 0.0f;
+    if (pt < n_points) {
+        gv = reinterpret_cast<const uint4*>(d_enc + (size_t)pt * MON_IN)[q];
+        if (q == 0) { u0 = __ldg(pts + (size_t)pt * 3); u1 = __ldg(pts + (size_t)pt * 3 + 1); u2 = __ldg(pts + (size_t)pt * 3 + 2); }
+    }
+    __syncthreads();                                   // s_live cleared
+    const uint32_t nz = __ballot_sync(0xffffffffu, ((gv.x | gv.y | gv.z | gv.w) & 0x7fff7fffu) != 0u);
+    if (lane == 0 && nz) atomicOr(&s_live[grp], nz);
+    __syncthreads();
+    uint32_t base = 0, n_live = 0, mine = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < SCT_TILE / 32; ++k) {
+        const uint32_t m = s_live[k];
+        if (k == grp) { base = n_live; mine = m; }
+        n_live += __popc(m);
+    }
+    if (n_live == 0) return;                           // CTA-uniform
+    if ((mine >> lane) & 1u) {
+        const uint32_t rank = base + __popc(mine & ((1u << lane) - 1u));
+        s_g[4 * q + 0][rank] = gv.x; s_g[4 * q + 1][rank] = gv.y; s_g[4 * q + 2][rank] = gv.z; s_g[4 * q + 3][rank] = gv.w;
+        if (q == 0) { s_u[0][rank] = u0; s_u[1][rank] = u1; s_u[2][rank] = u2; }
+    }
+    __syncthreads();
+    for (uint32_t l = level_begin + warp; l < level_end; l += SCT_THREADS / 32) {
+        for (uint32_t r = lane; r < n_live; r += 32) {
+            const uint32_t gwj = s_g[l][r];
+            if ((gwj & 0x7fff7fffu) == 0u) continue;   // adding +0 is an identity
+            const float u[3] = {s_u[0][r], s_u[1][r], s_u[2][r]};
+            scatter_level(g, l, gwj, u, grid_grad);
+        }
+    }
+}
+
+// the thread-per-sample form (MON_SCT_COMPACT=0, A/B): thread quarter lg owns levels level_begin + 4*lg + j of sample p
+__global__ void __launch_bounds__(SCT_THREADS)
+k_encode_backward_dense(MonGrid g, uint32_t n_points, const float* __restrict__ pts, const MonCtrl* __restrict__ ctrl,
+                        const __half* __restrict__ d_enc, __half* __restrict__ grid_grad, uint32_t level_begin, uint32_t level_end) {
     mon_pdl_wait();
     mon_pdl_trigger();
     if (ctrl->skip) return;
@@ -351,72 +467,15 @@ k_encode_backward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, c
     const uint32_t p = threadIdx.x & (SCT_TILE - 1), lg = threadIdx.x >> 7;
     const uint32_t pt = blockIdx.x * SCT_TILE + p;
     if (pt >= n_points) return;
-    // levels [level_begin, level_end), level_begin a multiple of 4: thread quarter lg owns levels level_begin + 4*lg + j
     const uint4 gv = reinterpret_cast<const uint4*>(d_enc + (size_t)pt * MON_IN)[(level_begin >> 2) + lg];
     const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
-    // position fetched beside the gradient, not behind the zero test: one L2 round trip per thread instead of two
     const float u[3] = {__ldg(pts + (size_t)pt * 3), __ldg(pts + (size_t)pt * 3 + 1), __ldg(pts + (size_t)pt * 3 + 2)};
     if (((gv.x | gv.y | gv.z | gv.w) & 0x7fff7fffu) == 0) return;
 #pragma unroll
     for (uint32_t j = 0; j < 4; ++j) {
         const uint32_t l = level_begin + lg * 4 + j;
         if (l >= level_end || (gw[j] & 0x7fff7fffu) == 0) continue;
-        const float g0 = __half2float(__ushort_as_half((unsigned short)(gw[j] & 0xffffu)));
-        const float g1 = __half2float(__ushort_as_half((unsigned short)(gw[j] >> 16)));
-        const uint32_t size = g.size[l];
-        char* tab = reinterpret_cast<char*>(reinterpret_cast<__half2*>(grid_grad) + g.offset[l]);
-        if ((size & (size - 1)) == 0) {
-            // same index arithmetic as the forward kernel, directly in byte offsets of the 4-byte entries
-            const float scale = g.scale[l];
-            const uint32_t res = g.res[l];
-            const bool hashed = g.hashed[l] != 0;
-            const uint32_t bmask = 4u * size - 4u;
-            float fr[3]; uint32_t cell[3];
-            mon_pos_fract(u[0], scale, fr[0], cell[0]);
-            mon_pos_fract(u[1], scale, fr[1], cell[1]);
-            mon_pos_fract(u[2], scale, fr[2], cell[2]);
-            const float h0 = __fsub_rn(1.0f, fr[0]), h1 = __fsub_rn(1.0f, fr[1]), h2 = __fsub_rn(1.0f, fr[2]);
-            const float wxy[4] = {__fmul_rn(h0, h1), __fmul_rn(fr[0], h1), __fmul_rn(h0, fr[1]), __fmul_rn(fr[0], fr[1])};
-            uint32_t ax[2], ay[2], az[2];
-            ax[0] = cell[0] << 2; ax[1] = (cell[0] + 1u) << 2;
-            if (hashed) {
-                ay[0] = (cell[1] * 2654435761u) << 2; ay[1] = ((cell[1] + 1u) * 2654435761u) << 2;
-                az[0] = (cell[2] * 805459861u) << 2; az[1] = ((cell[2] + 1u) * 805459861u) << 2;
-            } else {
-                ay[0] = (cell[1] * res) << 2; ay[1] = ((cell[1] + 1u) * res) << 2;
-                az[0] = (cell[2] * res * res) << 2; az[1] = ((cell[2] + 1u) * res * res) << 2;
-            }
-            if ((cell[0] & 1u) == 0u && size >= 2u && (hashed || (res & 1u) == 0u)) {
-                // even x: the corners x and x+1 are entries 2j and 2j+1 (in either order) of one aligned 8-byte word,
-                // for the hash (x enters by XOR, bit 0 of x is clear) and for the dense index (the y/z strides are even)
-#pragma unroll
-                for (uint32_t q = 0; q < 4; ++q) {
-                    const float wz = (q & 2) ? fr[2] : h2;
-                    const float w0 = __fmul_rn(wxy[(q & 1) * 2], wz), w1 = __fmul_rn(wxy[(q & 1) * 2 + 1], wz);
-                    const uint32_t off = (hashed ? (ax[0] ^ ay[q & 1] ^ az[q >> 1]) : (ax[0] + ay[q & 1] + az[q >> 1])) & bmask;
-                    const __half2 v0 = __floats2half2_rn(__fmul_rn(g0, w0), __fmul_rn(g1, w0));
-                    const __half2 v1 = __floats2half2_rn(__fmul_rn(g0, w1), __fmul_rn(g1, w1));
-                    const bool swap = (off & 4u) != 0u;     // corner x sits in the upper half of the word
-                    red_add_f16x2_pair(tab + (off & ~7u), swap ? v1 : v0, swap ? v0 : v1);
-                }
-            } else {
-#pragma unroll
-                for (uint32_t k = 0; k < 8; ++k) {
-                    const float wgt = __fmul_rn(wxy[k & 3], (k & 4) ? fr[2] : h2);
-                    const uint32_t off = (hashed ? (ax[k & 1] ^ ay[(k >> 1) & 1] ^ az[k >> 2]) : (ax[k & 1] + ay[(k >> 1) & 1] + az[k >> 2])) & bmask;
-                    const __half2 v = __floats2half2_rn(__fmul_rn(g0, wgt), __fmul_rn(g1, wgt));
-                    red_add_f16x2(reinterpret_cast<__half2*>(tab + off), v);
-                }
-            }
-        } else {
-            EncCorner c;
-            level_corners(g, l, u, c);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const __half2 v = __halves2half2(__float2half_rn(__fmul_rn(g0, c.w[k])), __float2half_rn(__fmul_rn(g1, c.w[k])));
-                red_add_f16x2(reinterpret_cast<__half2*>(tab) + c.idx[k], v);
-            }
-        }
+        scatter_level(g, l, gw[j], u, grid_grad);
     }
 }
 
@@ -426,7 +485,13 @@ void mon_launch_encode_backward(const MonGrid& g, uint32_t n_points, const float
     if (level_end > g.n_levels) level_end = g.n_levels;
     if (level_begin >= level_end || n_points == 0) return;
     const uint32_t blocks = (n_points + SCT_TILE - 1) / SCT_TILE;
+    static const int compact = [] { const char* e = getenv("MON_SCT_COMPACT"); return e ? atoi(e) : 1; }();
+    if (compact && g.n_levels * 2 <= MON_IN) {
+        mon_launch_chain(MON_PDL_SCATTER, lo, k_encode_backward, dim3(blocks), dim3(SCT_THREADS), 0, st, g, n_points, pts, ctrl, d_enc, grid_grad,
+                         level_begin, level_end);
+        return;
+    }
     const uint32_t quarters = (level_end - level_begin + 3) / 4;     // 128 threads (one point each) per 4 levels
-    mon_launch_chain(MON_PDL_SCATTER, lo, k_encode_backward, dim3(blocks), dim3(SCT_TILE * quarters), 0, st, g, n_points, pts, ctrl, d_enc, grid_grad,
+    mon_launch_chain(MON_PDL_SCATTER, lo, k_encode_backward_dense, dim3(blocks), dim3(SCT_TILE * quarters), 0, st, g, n_points, pts, ctrl, d_enc, grid_grad,
                      level_begin, level_end);
 }

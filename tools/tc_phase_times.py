@@ -2,15 +2,18 @@
 import ctypes as C, sys
 import numpy as np
 sys.path.insert(0, '/root/repo')
-from ro_map_b200 import core, _capi, synthetic as syn
-seq = syn.make_sequence(n_frames=6, n_objects=1, seed=1337, H=200, W=200, K=(277.7775, 277.7775, 100.0, 100.0))
+from ro_map_b200 import _capi
+from pathlib import Path
+_capi.LIB_PATH = Path('/root/repo/ro_map_b200/_build_tl2/libmon_b200_stamps.so')
+from ro_map_b200 import core, synthetic as syn
+seq = syn.make_sequence(n_frames=12, n_objects=1, seed=1337, H=400, W=400, K=(555.555, 555.555, 200.0, 200.0))
 obj = seq.objects[0]
 ds = core.Dataset(0, *seq.K, seq.H, seq.W, len(seq.poses), True)
 for i in range(len(seq.poses)):
     ds.add_frame(i, seq.rgb[i], seq.instance[i], seq.depth[i], seq.poses[i])
 g = core.NerfObject(ds, core.default_config(), obj.Tow, -1.1 * obj.half, 1.1 * obj.half, obj.instance_id)
 g.set_bboxes(obj.boxes)
-g.train(200)
+g.train(600)
 print("stage ms", g.train_profiled(20))
 lib = _capi.load()
 st = (C.c_ulonglong * 64)()

@@ -91,13 +91,9 @@ __device__ __forceinline__ float adam_one(const MonOpt& o, float lr_base, float 
     v = __fmaf_rn(o.beta2, v, __fmul_rn(1.0f - o.beta2, gsq));
     cs += 1;
     const float lr = __fmul_rn(lr_base, cs < o.n_debias_lut ? __ldg(o.debias_lut + cs) : adam_debias(o, cs));
-    // lr / (sqrt(v) + eps) on the SFU: sqrt.approx (rel. error <= 2^-23) and div.approx (<= 2 ulp) instead of the
-    // IEEE sequences (~35 instructions per touched parameter in a sweep that is half issue-bound).  The step
-    // eff * m then differs from the reference's by <= 3 ulp of a ~1e-2 quantity, five orders below the fp16 rounding
-    // of the working copy; v > 0 here (the gradient is nonzero or the parameter is an MLP weight).
-    float sq;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(sq) : "f"(v));
-    const float eff = fminf(fmaxf(__fdividef(lr, __fadd_rn(sq, o.eps)), 0.0f), FLT_MAX);
+    // IEEE sqrt and division like the reference's sqrtf and '/' (adam.h:107): with identical gradients the weights stay
+    // bit-identical to the CPU restatement (the SFU approximations would save ~12 instructions and cost that property)
+    const float eff = fminf(fmaxf(__fdiv_rn(lr, __fadd_rn(__fsqrt_rn(v), o.eps)), 0.0f), FLT_MAX);
     return __fmaf_rn(-eff, m, w);
 }
 

@@ -343,3 +343,23 @@ def test_pipelined_graph_matches_serial_chain(core, gpu_dataset, small_seq):
     a.train_profiled(3)
     l_end = a.train(50)
     assert a.step == 114 and np.isfinite(l_end) and l_end < 1.2 * la + 1e-3
+
+
+def test_second_iteration_encoding_bit_exact(core, oracle, gpu_dataset, small_seq):
+    """Adam's first step moves every touched weight by +-lr (m/sqrt(v) = sign(g)), so with the optimizer's arithmetic
+    identical to the oracle's (IEEE sqrt/div, the tabulated bias correction, the fp16 rounding points) the weights after
+    one iteration — and therefore the second iteration's rays and hash-grid encoding — must still match bit for bit.
+    (This is what __graft_entry__.smoke() asserts on the GPU box; it caught an SFU-approximated Adam step.)"""
+    seq, obj = small_seq, small_seq.objects[0]
+    R = 256
+    g, o = make_pair(core, oracle, gpu_dataset, seq, obj, R)
+    frames = oracle.Frames(seq.rgb, seq.instance, seq.depth, seq.poses)
+    rng = np.random.default_rng(51)
+    for it in range(2):
+        sxy, col, dt = randoms(rng, R)
+        lg, ng = g.train_injected(sxy, col, dt)
+        lo, no = o.train_iter(obj.boxes, frames, seq.H, seq.W, seq.K, sxy, col, dt)
+        assert ng == no
+        assert np.array_equal(g.last("rays"), o.last("rays")), it
+        assert np.array_equal(g.last("enc"), o.last("enc")), it
+        assert lg == pytest.approx(lo, abs=5e-4, rel=2e-3), it

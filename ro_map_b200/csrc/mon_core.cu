@@ -908,8 +908,16 @@ int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uin
     mon_launch_init_grid(rng.state, rng.inc, o->n_grid, o->pf + o->n_mlp, o->stream);
     mon_launch_cast_params((uint32_t)P, o->pf, o->ph, o->stream);
     mon_launch_planarize(o->grid, o->ph + o->n_mlp, o->ph_planar, o->stream);
-    mon_launch_fill_debias_lut(o->opt, MON_DEBIAS_LUT, o->debias_lut, o->stream);
-    o->launches += 4;
+    o->launches += 3;
+    {   // Adam bias correction by step count, the reference's expression in host float arithmetic (kernels_optim.cu)
+        std::vector<float> lut(MON_DEBIAS_LUT);
+        for (uint32_t s = 0; s < MON_DEBIAS_LUT; ++s)
+            lut[s] = sqrtf(1.0f - powf(cfg->beta2, (float)s)) / (1.0f - powf(cfg->beta1, (float)s));
+        if ((e = cudaMemcpy(o->debias_lut, lut.data(), lut.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) {
+            mon_object_destroy(o);
+            return fail(MON_ERR_CUDA, "bias-correction table upload: %s", cudaGetErrorString(e));
+        }
+    }
     if ((e = cudaStreamSynchronize(o->stream)) != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) {
         mon_object_destroy(o);
         return fail(MON_ERR_CUDA, "param init: %s", cudaGetErrorString(e));

@@ -345,21 +345,32 @@ def test_pipelined_graph_matches_serial_chain(core, gpu_dataset, small_seq):
     assert a.step == 114 and np.isfinite(l_end) and l_end < 1.2 * la + 1e-3
 
 
-def test_second_iteration_encoding_bit_exact(core, oracle, gpu_dataset, small_seq):
-    """Adam's first step moves every touched weight by +-lr (m/sqrt(v) = sign(g)), so with the optimizer's arithmetic
-    identical to the oracle's (IEEE sqrt/div, the tabulated bias correction, the fp16 rounding points) the weights after
-    one iteration — and therefore the second iteration's rays and hash-grid encoding — must still match bit for bit.
-    (This is what __graft_entry__.smoke() asserts on the GPU box; it caught an SFU-approximated Adam step.)"""
+def test_optimizer_bit_exact_for_equal_gradients(core, oracle, gpu_dataset, small_seq):
+    """The optimizer's arithmetic is the oracle's bit for bit (IEEE sqrt/div, the bias-correction table filled on the host
+    with the reference's sqrtf(1 - powf(b2, s)) / (1 - powf(b1, s)), the fp16 rounding points): wherever the accumulated
+    gradient is identical — the fp16 atomics make a few thousand sums differ in the last bit — the fp32 master weight,
+    both moments and the fp16 copy are identical after the step.  The second iteration then sees the same rays and an
+    encoding that differs only where one of the handful of sign-flipped ~0 gradients moved an entry the other way.
+    (`1 - beta^s` cancels: a one-ulp difference in pow is 3e-6 of the learning rate and used to touch every weight.)"""
     seq, obj = small_seq, small_seq.objects[0]
     R = 256
     g, o = make_pair(core, oracle, gpu_dataset, seq, obj, R)
     frames = oracle.Frames(seq.rgb, seq.instance, seq.depth, seq.poses)
     rng = np.random.default_rng(51)
-    for it in range(2):
-        sxy, col, dt = randoms(rng, R)
-        lg, ng = g.train_injected(sxy, col, dt)
-        lo, no = o.train_iter(obj.boxes, frames, seq.H, seq.W, seq.K, sxy, col, dt)
-        assert ng == no
-        assert np.array_equal(g.last("rays"), o.last("rays")), it
-        assert np.array_equal(g.last("enc"), o.last("enc")), it
-        assert lg == pytest.approx(lo, abs=5e-4, rel=2e-3), it
+    sxy, col, dt = randoms(rng, R)
+    lg, ng = g.train_injected(sxy, col, dt)
+    lo, no = o.train_iter(obj.boxes, frames, seq.H, seq.W, seq.K, sxy, col, dt)
+    assert ng == no and np.array_equal(g.last("enc"), o.last("enc"))
+    same = (g.state("grad") == o.state("grad")) & (g.state("param_steps") == o.state("param_steps"))
+    assert same.mean() >= 0.98
+    for name in ("master", "params", "adam_m", "adam_v", "ema"):
+        a, b = g.state(name), o.state(name)
+        assert np.array_equal(a[same], b[same]), name
+    assert (g.state("params") != o.state("params")).mean() <= 1e-4
+    # second iteration: identical rays, encoding identical except downstream of those few entries
+    sxy, col, dt = randoms(rng, R)
+    lg, ng = g.train_injected(sxy, col, dt)
+    lo, no = o.train_iter(obj.boxes, frames, seq.H, seq.W, seq.K, sxy, col, dt)
+    assert ng == no and np.array_equal(g.last("rays"), o.last("rays"))
+    assert (g.last("enc") != o.last("enc")).mean() <= 2e-3
+    assert lg == pytest.approx(lo, abs=5e-4, rel=2e-3)

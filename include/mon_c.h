@@ -167,6 +167,11 @@ int mon_object_set_params(mon_object* obj, const float* params_fp32, size_t n);
  * 7 mask_rays 8 dout(4/pt) 9 d_enc(32/pt) 10 target rgb 11 target depth 12 ray instance flag
  * 13 per-ray loss */
 int mon_object_last(mon_object* obj, int which, float* out, size_t cap, size_t* n_out);
+/* host-only: the work split of the hash-encode kernel (kernels_encode.cu) for n_ctas CTAs over levels
+ * [level_begin, level_end): out4[4*b..] = first (job, point) and end (job, point) of piece b, job = 2*level + feature.
+ * No device needed; lets a CPU test check that the pieces tile the [job][point] space exactly. */
+int mon_debug_encode_pieces(const mon_config* cfg, uint32_t n_points, uint32_t n_ctas, uint32_t level_begin,
+                            uint32_t level_end, uint32_t* out4);
 /* stand-alone stage entry points on host buffers (copies inside), for kernel-level parity */
 int mon_stage_encode(const mon_config* cfg, const uint16_t* grid_fp16, size_t n_grid_params,
                      const float* points_unit, uint32_t n_points, uint16_t* enc_out);

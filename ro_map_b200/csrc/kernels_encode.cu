@@ -307,6 +307,22 @@ cudaError_t mon_launch_encode_forward(const MonGrid& g, uint32_t n_points, const
     }
 }
 
+// host mirror of the kernel's work split (the same two functions): piece b of n_ctas as (first job, first point, end job,
+// end point); used by the CPU test that checks the pieces tile the [job][point] space exactly for arbitrary sizes
+void mon_encode_pieces_host(const MonGrid& g, uint32_t n_points, uint32_t n_ctas, uint32_t level_begin, uint32_t level_end, uint32_t* out4) {
+    uint32_t l_large = level_begin, l_hashed = level_begin;
+    while (l_large < level_end && !g.hashed[l_large] && g.size[l_large] <= 4096u) ++l_large;
+    l_hashed = l_large;
+    while (l_hashed < level_end && !g.hashed[l_hashed]) ++l_hashed;
+    const uint32_t jb = 2 * level_begin, jl = 2 * l_large, jh = 2 * l_hashed, je = 2 * level_end;
+    const uint64_t total = enc_cost_total(n_points, jb, jl, jh, je);
+    for (uint32_t b = 0; b < n_ctas; ++b) {
+        const EncPos pb = enc_cost_to_pos(total * b / n_ctas, n_points, jb, jl, jh);
+        const EncPos pe = enc_cost_to_pos(total * (b + 1) / n_ctas, n_points, jb, jl, jh);
+        out4[4 * b + 0] = pb.job; out4[4 * b + 1] = pb.p; out4[4 * b + 2] = pe.job; out4[4 * b + 3] = pe.p;
+    }
+}
+
 // interleaved fp16 weights [entry][2] -> planar per level [f0 table | f1 table] (initialisation / set_params; the
 // optimizer sweep keeps both copies current afterwards)
 __global__ void k_planarize(MonGrid g, uint32_t n_entries, const __half* __restrict__ inter, __half* __restrict__ planar) {

@@ -1453,6 +1453,17 @@ int mon_object_density_grid(mon_object* o, const uint32_t res[3], float* out) {
 }
 
 // ------------------------------------------------------------------------------- stage hooks
+int mon_debug_encode_pieces(const mon_config* cfg, uint32_t n_points, uint32_t n_ctas, uint32_t level_begin, uint32_t level_end, uint32_t* out4) {
+    if (!cfg || !out4 || n_ctas == 0) return fail(MON_ERR_ARG, "NULL argument");
+    std::string why;
+    MonGrid grid;
+    if (!validate_config(*cfg, why) || !make_grid(*cfg, grid, why)) return fail(MON_ERR_ARG, "unsupported config: %s", why.c_str());
+    if (level_end > grid.n_levels) level_end = grid.n_levels;
+    if (level_begin >= level_end) return fail(MON_ERR_ARG, "empty level range");
+    mon_encode_pieces_host(grid, n_points, n_ctas, level_begin, level_end, out4);
+    return MON_OK;
+}
+
 int mon_stage_encode(const mon_config* cfg, const uint16_t* grid_fp16, size_t n_grid_params,
                      const float* points_unit, uint32_t n_points, uint16_t* enc_out) {
     if (!cfg || !grid_fp16 || !points_unit || !enc_out) return fail(MON_ERR_ARG, "NULL argument");

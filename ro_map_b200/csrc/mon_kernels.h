@@ -86,6 +86,7 @@ cudaError_t mon_launch_encode_forward(const MonGrid& g, uint32_t n_points, const
                                       const MonCtrl* ctrl, uint32_t sm_count, cudaStream_t st, uint32_t level_begin = 0,
                                       uint32_t level_end = 0xffffffffu, const MonLaunchOpt& lo = MonLaunchOpt());
 void mon_launch_planarize(const MonGrid& g, const __half* inter, __half* planar, cudaStream_t st);
+void mon_encode_pieces_host(const MonGrid& g, uint32_t n_points, uint32_t n_ctas, uint32_t level_begin, uint32_t level_end, uint32_t* out4);
 void mon_launch_encode_backward(const MonGrid& g, uint32_t n_points, const float* pts, const MonCtrl* ctrl,
                                 const __half* d_enc, __half* grid_grad, cudaStream_t st, uint32_t level_begin = 0,
                                 uint32_t level_end = 0xffffffffu, const MonLaunchOpt& lo = MonLaunchOpt());   // level_begin % 4 == 0

@@ -81,6 +81,39 @@ def test_grid_layout_matches_oracle(lib, oracle):
         assert np.array_equal(off, o_off) and np.array_equal(sc, o_sc) and np.array_equal(res, o_res)
 
 
+def test_encode_work_split_tiles_the_job_space(lib):
+    """k_encode_forward cuts the flattened [(level, feature) job][point] space into one piece per CTA by a closed-form
+    cost model (dense vs hashed levels, table staging per job).  Whatever the sizes, the pieces must cover every
+    (job, point) exactly once — a gap would silently leave encodings stale.  Host mirror of the kernel's two functions."""
+    import ctypes as C
+    from ro_map_b200 import core
+    rng = np.random.default_rng(5)
+    cases = [(131072, 148, 0, 16), (32768, 148, 0, 16), (8192, 16, 0, 16), (1, 1, 0, 16), (7, 148, 0, 16), (1048576, 148, 0, 16),
+             (131072, 148, 0, 8), (131072, 148, 8, 16), (131072, 74, 4, 12), (640000 * 64 // 39, 148, 0, 16)]
+    cases += [(int(rng.integers(1, 300000)), int(rng.integers(1, 160)), 0, 16) for _ in range(40)]
+    for log2, base in ((16, 16), (19, 16), (14, 8)):
+        cfg = core.default_config(log2_hashmap_size=log2, base_resolution=base)
+        for n, ctas, lb, le in cases:
+            out = np.zeros((ctas, 4), np.uint32)
+            assert lib.mon_debug_encode_pieces(C.byref(cfg), n, ctas, lb, le, out.ctypes.data_as(C.POINTER(C.c_uint32))) == 0
+            cover = {j: [] for j in range(2 * lb, 2 * le)}
+            for jb, pb, je, pe in out.tolist():
+                job = jb
+                while job < 2 * le and (job < je or (job == je and pe > 0)):      # the kernel's loop
+                    p0 = pb if job == jb else 0
+                    p1 = pe if job == je else n
+                    if p1 > p0:
+                        cover[job].append((p0, p1))
+                    job += 1
+            for j, segs in cover.items():
+                segs.sort()
+                pos = 0
+                for a, b in segs:
+                    assert a == pos, (log2, n, ctas, j, segs)
+                    pos = b
+                assert pos == n, (log2, n, ctas, j, segs)
+
+
 def test_no_cpu_fallback(lib):
     """Without a CUDA device the compute entry points must fail, not silently compute on the host."""
     from ro_map_b200 import core

@@ -40,7 +40,8 @@ unsigned mon_pdl_mask() {   // A/B switch for the programmatic-dependent-launch 
         if (std::getenv("MON_NO_PDL")) return 0u;
         const char* m = std::getenv("MON_PDL_MASK");
         // measured on B200 (profiles/r1g_pdl_ab.txt): encode, fused MLP and optimizer gain from the overlap (+3 %), the
-        // 1024-CTA scatter loses 7 % when its CTAs become resident early, sample points is neutral
+        // 1024-CTA scatter loses 7-9 % when its CTAs become resident early — also in its compacted form, and also when
+        // the fused MLP kernel triggers only after its last tile (-4 %) —, sample points is neutral
         return m ? (unsigned)std::atoi(m) : (unsigned)(MON_PDL_ENCODE | MON_PDL_MLP | MON_PDL_OPTIM);
     }();
     return mask;

@@ -9,15 +9,17 @@
 // (<= 65536 fp16 = 128 KB, from a planar copy of the fp16 weights the optimizer maintains) is staged into shared
 // memory with TMA bulk copies (cp.async.bulk -> mbarrier), and the CTA then streams its share of the points past
 // it: 8 two-byte gathers per point hit the 32 shared-memory banks (~3.5-way conflicts for random indices) instead of
-// 8 L1 wavefronts.  Work is split evenly over the flattened [job][point] space, so each of the 148 CTAs loads at
-// most two table slices.  Output is level-major: enc[level][point][feature] (the two features of a level form one
+// 8 L1 wavefronts.  The flattened [job][point] space is cut into one piece per CTA, equal in modelled cost (the
+// conflict degree differs between dense and hashed levels; staging a slice costs too), so each of the 148 CTAs loads
+// at most two table slices and they all finish together.  Output is level-major: enc[level][point][feature] (the two features of a level form one
 // 32-bit word per point, which is what the fused MLP kernel stages), written with 2-byte stores at 4-byte stride.
 // Arithmetic is the reference's: weights in fp32, rounded to fp16, one fp32 FMA per corner whose result is rounded
 // back to fp16 after every corner (grid.h:334 via common.h:539-559) — bit-exact against tiny-cuda-nn, including
 // the 32-bit stride wrap that turns level 12 into a table indexed by x alone (mon_core.cu make_grid).
 //
 // BACKWARD.  grad[idx] += half2(d_enc * w) with f16x2 reductions, exactly the reference's atomicAdd(__half2)
-// (grid.h:427-431); a CTA owns 128 consecutive samples for all levels.
+// (grid.h:427-431).  A CTA owns 128 consecutive samples: it compacts the ones that still carry gradient into shared
+// memory and scatters them with one level per warp (k_encode_backward).
 #include "mon_device.cuh"
 #include "mon_kernels.h"
 #include "tc05.cuh"

@@ -333,7 +333,7 @@ def run_ours(args, rank, world, local_rank):
         dist.barrier()
     e2e_s = partition.reduce_max(e2e_s, "cuda")
     px = seq.H * seq.W
-    h2d = len(seq.poses) * (px * 3 + px + px * 4 + 88) + sum(len(seq.objects[k].boxes) for k in mine) * 20
+    h2d = len(seq.poses) * (px * 3 + px + px * 4 + 96) + sum(len(seq.objects[k].boxes) for k in mine) * 20
     h2d = partition.reduce_sum(float(h2d), "cuda")
     for n in nerfs2:
         n.close()

@@ -62,9 +62,10 @@ __device__ __forceinline__ void write_ray(const MonBatch& b, const MonScene& sc,
     if (c.inst != 0) {
         const uint8_t* px = fr->rgb + pix * 3;
         // the reference stores float pixels = u8 * (1/255) (nerf_data.cu:163-164); same value here
-        b.target[idx * 3 + 0] = __fmul_rn((float)px[0], (float)(1.0 / 255.0));
+        const uint32_t ir = fr->bgr ? 2u : 0u;    // cv::cvtColor(BGR2RGB) of the reference (nerf_data.cu:286), done on read
+        b.target[idx * 3 + 0] = __fmul_rn((float)px[ir], (float)(1.0 / 255.0));
         b.target[idx * 3 + 1] = __fmul_rn((float)px[1], (float)(1.0 / 255.0));
-        b.target[idx * 3 + 2] = __fmul_rn((float)px[2], (float)(1.0 / 255.0));
+        b.target[idx * 3 + 2] = __fmul_rn((float)px[2u - ir], (float)(1.0 / 255.0));
         b.target_depth[idx] = (sc.use_depth && fr->depth) ? __fmul_rn(fr->depth[pix], c.d_norm) : 0.0f;
         b.ray_inst[idx] = 1;
     } else {

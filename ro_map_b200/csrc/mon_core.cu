@@ -31,6 +31,7 @@
 #include "mon_kernels.h"
 
 #define MON_DEBIAS_LUT 32768  // steps covered by the Adam bias-correction table (offline jobs run 5000 iterations)
+#define MON_FRAMES_PER_SLAB 32
 #define MON_GRAPH_CHUNK 50   // iterations captured per replayed graph (plus a 1-iteration graph for remainders)
 
 static thread_local std::string g_err;
@@ -172,8 +173,15 @@ struct mon_dataset {
     MonFrame* d_frames = nullptr;
     std::vector<MonFrame> h_frames;
     cudaStream_t stream = nullptr;
-    uint8_t* staging = nullptr;  // pinned: rgb | instance | depth
+    // pinned staging for pageable caller buffers (rgb | instance | depth), double-buffered: a frame is copied into one
+    // half while the previous frame's DMA still reads the other
+    uint8_t* staging[2] = {nullptr, nullptr};
+    cudaEvent_t ev_staged[2] = {nullptr, nullptr};
+    uint32_t stage_next = 0;
     cudaEvent_t ev_uploaded = nullptr;   // recorded after the last frame upload; training streams wait on it
+    // keyframe storage comes in slabs of MON_FRAMES_PER_SLAB frames (one cudaMalloc per slab: a per-frame cudaMalloc
+    // serialises with the training graphs in flight and made the online ingest take tens of milliseconds per keyframe)
+    std::vector<uint8_t*> slabs;
     std::mutex mu;
 };
 
@@ -363,19 +371,41 @@ int mon_dataset_create(int gpu, float fx, float fy, float cx, float cy, int H, i
     mon_dataset* ds = new mon_dataset();
     ds->gpu = gpu; ds->K[0] = fx; ds->K[1] = fy; ds->K[2] = cx; ds->K[3] = cy;
     ds->H = H; ds->W = W; ds->max_frames = max_frames; ds->use_depth = use_depth;
-    ds->h_frames.assign(max_frames, MonFrame{nullptr, nullptr, nullptr, {0}});
+    ds->h_frames.assign(max_frames, MonFrame{nullptr, nullptr, nullptr, {0}, 0u, 0u});
+    ds->slabs.assign((max_frames + MON_FRAMES_PER_SLAB - 1) / MON_FRAMES_PER_SLAB, nullptr);
     const size_t px = (size_t)H * W;
     cudaError_t e;
     if ((e = cudaStreamCreateWithFlags(&ds->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaMalloc(&ds->d_frames, sizeof(MonFrame) * max_frames)) != cudaSuccess ||
         (e = cudaMemset(ds->d_frames, 0, sizeof(MonFrame) * max_frames)) != cudaSuccess ||
-        (e = cudaMallocHost(&ds->staging, px * 3 + px + px * 4)) != cudaSuccess ||
+        (e = cudaMallocHost(&ds->staging[0], px * 3 + px + px * 4)) != cudaSuccess ||
+        (e = cudaMallocHost(&ds->staging[1], px * 3 + px + px * 4)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ds->ev_staged[0], cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ds->ev_staged[1], cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&ds->ev_uploaded, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventRecord(ds->ev_uploaded, ds->stream)) != cudaSuccess) {
         mon_dataset_destroy(ds);
         return fail(MON_ERR_CUDA, "dataset allocation: %s", cudaGetErrorString(e));
     }
     *out = ds;
+    return MON_OK;
+}
+
+// device storage of one keyframe, carved out of its slab (allocated on first use)
+static int ensure_frame_storage(mon_dataset* ds, uint32_t frame_id) {
+    MonFrame& f = ds->h_frames[frame_id];
+    if (f.rgb) return MON_OK;
+    const size_t px = (size_t)ds->H * ds->W;
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t o_inst = up(px * 3), o_depth = o_inst + up(px), per_frame = o_depth + (ds->use_depth ? up(px * 4) : 0);
+    const uint32_t slab = frame_id / MON_FRAMES_PER_SLAB;
+    if (!ds->slabs[slab]) {
+        const uint32_t n = std::min<uint32_t>(MON_FRAMES_PER_SLAB, ds->max_frames - slab * MON_FRAMES_PER_SLAB);
+        CK(cudaMalloc(&ds->slabs[slab], per_frame * n));
+    }
+    uint8_t* base = ds->slabs[slab] + per_frame * (frame_id % MON_FRAMES_PER_SLAB);
+    f.rgb = base; f.instance = base + o_inst;
+    f.depth = ds->use_depth ? reinterpret_cast<const float*>(base + o_depth) : nullptr;
     return MON_OK;
 }
 
@@ -387,15 +417,12 @@ int mon_dataset_add_frame(mon_dataset* ds, uint32_t frame_id, const uint8_t* rgb
     std::lock_guard<std::mutex> lock(ds->mu);
     CK(cudaSetDevice(ds->gpu));
     const size_t px = (size_t)ds->H * ds->W;
+    int rc = ensure_frame_storage(ds, frame_id);
+    if (rc != MON_OK) return rc;
     MonFrame& f = ds->h_frames[frame_id];
-    if (!f.rgb) {
-        uint8_t* p = nullptr;
-        CK(cudaMalloc(&p, px * 3)); f.rgb = p;
-        CK(cudaMalloc(&p, px)); f.instance = p;
-        if (ds->use_depth) { float* d = nullptr; CK(cudaMalloc(&d, px * 4)); f.depth = d; }
-    }
     memcpy(f.pose, pose, sizeof(float) * 16);
-    if (!is_bgr && host_pinned(rgb) && host_pinned(instance) && (!ds->use_depth || host_pinned(depth))) {
+    f.bgr = is_bgr ? 1u : 0u;
+    if (host_pinned(rgb) && host_pinned(instance) && (!ds->use_depth || host_pinned(depth))) {
         // page-locked caller buffers: DMA straight out of them, no staging copy and no host synchronisation.  The
         // buffers must stay valid until mon_dataset_sync() or the next blocking call on an object of this dataset.
         CK(cudaMemcpyAsync(const_cast<uint8_t*>(f.rgb), rgb, px * 3, cudaMemcpyHostToDevice, ds->stream));
@@ -404,14 +431,15 @@ int mon_dataset_add_frame(mon_dataset* ds, uint32_t frame_id, const uint8_t* rgb
         CK(cudaMemcpyAsync(ds->d_frames + frame_id, &f, sizeof(MonFrame), cudaMemcpyHostToDevice, ds->stream));   // pageable source: staged by the driver before returning
         CK(cudaEventRecord(ds->ev_uploaded, ds->stream));
     } else {
-        uint8_t* st_rgb = ds->staging;
-        uint8_t* st_inst = ds->staging + px * 3;
-        float* st_depth = reinterpret_cast<float*>(ds->staging + px * 4);
-        if (is_bgr) {  // cv::cvtColor(BGR2RGB) of the reference (nerf_data.cu:286)
-            for (size_t i = 0; i < px; ++i) { st_rgb[3 * i] = rgb[3 * i + 2]; st_rgb[3 * i + 1] = rgb[3 * i + 1]; st_rgb[3 * i + 2] = rgb[3 * i]; }
-        } else {
-            memcpy(st_rgb, rgb, px * 3);
-        }
+        // pageable caller buffers (cv::Mat of the SLAM frontend): one memcpy into the free half of the pinned staging
+        // area, DMA from there; the call returns without waiting for the DMA
+        const uint32_t half = ds->stage_next;
+        ds->stage_next ^= 1u;
+        CK(cudaEventSynchronize(ds->ev_staged[half]));   // the DMA that last read this half (two frames ago) is done
+        uint8_t* st_rgb = ds->staging[half];
+        uint8_t* st_inst = ds->staging[half] + px * 3;
+        float* st_depth = reinterpret_cast<float*>(ds->staging[half] + px * 4);
+        memcpy(st_rgb, rgb, px * 3);
         memcpy(st_inst, instance, px);
         CK(cudaMemcpyAsync(const_cast<uint8_t*>(f.rgb), st_rgb, px * 3, cudaMemcpyHostToDevice, ds->stream));
         CK(cudaMemcpyAsync(const_cast<uint8_t*>(f.instance), st_inst, px, cudaMemcpyHostToDevice, ds->stream));
@@ -420,8 +448,8 @@ int mon_dataset_add_frame(mon_dataset* ds, uint32_t frame_id, const uint8_t* rgb
             CK(cudaMemcpyAsync(const_cast<float*>(f.depth), st_depth, px * 4, cudaMemcpyHostToDevice, ds->stream));
         }
         CK(cudaMemcpyAsync(ds->d_frames + frame_id, &f, sizeof(MonFrame), cudaMemcpyHostToDevice, ds->stream));
+        CK(cudaEventRecord(ds->ev_staged[half], ds->stream));
         CK(cudaEventRecord(ds->ev_uploaded, ds->stream));
-        CK(cudaStreamSynchronize(ds->stream));   // the staging buffer is reused by the next frame
     }
     ds->n_frames = std::max(ds->n_frames, frame_id + 1);
     return MON_OK;
@@ -469,13 +497,10 @@ int mon_dataset_clone_from_peer(mon_dataset* dst, const mon_dataset* src) {
     for (uint32_t i = 0; i < src->n_frames; ++i) {
         const MonFrame& s = src->h_frames[i];
         if (!s.rgb) continue;
+        int rc = ensure_frame_storage(dst, i);
+        if (rc != MON_OK) return rc;
         MonFrame& f = dst->h_frames[i];
-        if (!f.rgb) {
-            uint8_t* p = nullptr;
-            CK(cudaMalloc(&p, px * 3)); f.rgb = p;
-            CK(cudaMalloc(&p, px)); f.instance = p;
-            if (dst->use_depth) { float* d = nullptr; CK(cudaMalloc(&d, px * 4)); f.depth = d; }
-        }
+        f.bgr = s.bgr;
         CK(cudaMemcpyPeerAsync(const_cast<uint8_t*>(f.rgb), dst->gpu, s.rgb, src->gpu, px * 3, dst->stream));
         CK(cudaMemcpyPeerAsync(const_cast<uint8_t*>(f.instance), dst->gpu, s.instance, src->gpu, px, dst->stream));
         if (dst->use_depth) CK(cudaMemcpyPeerAsync(const_cast<float*>(f.depth), dst->gpu, s.depth, src->gpu, px * 4, dst->stream));
@@ -490,13 +515,13 @@ int mon_dataset_clone_from_peer(mon_dataset* dst, const mon_dataset* src) {
 int mon_dataset_destroy(mon_dataset* ds) {
     if (!ds) return MON_OK;
     cudaSetDevice(ds->gpu);
-    for (auto& f : ds->h_frames) {
-        if (f.rgb) cudaFree(const_cast<uint8_t*>(f.rgb));
-        if (f.instance) cudaFree(const_cast<uint8_t*>(f.instance));
-        if (f.depth) cudaFree(const_cast<float*>(f.depth));
-    }
+    if (ds->stream) cudaStreamSynchronize(ds->stream);
+    for (uint8_t* slab : ds->slabs) if (slab) cudaFree(slab);
     if (ds->d_frames) cudaFree(ds->d_frames);
-    if (ds->staging) cudaFreeHost(ds->staging);
+    for (int k = 0; k < 2; ++k) {
+        if (ds->staging[k]) cudaFreeHost(ds->staging[k]);
+        if (ds->ev_staged[k]) cudaEventDestroy(ds->ev_staged[k]);
+    }
     if (ds->ev_uploaded) cudaEventDestroy(ds->ev_uploaded);
     if (ds->stream) cudaStreamDestroy(ds->stream);
     delete ds;

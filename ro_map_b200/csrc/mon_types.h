@@ -25,6 +25,9 @@ struct MonFrame {
     const uint8_t* instance;  // H*W
     const float* depth;       // H*W or nullptr
     float pose[16];           // camera-to-world, column-major
+    uint32_t bgr;             // 1: the pixels are stored B, G, R as the SLAM frontend hands them over (cv::imread order);
+                              // the batch kernel swaps on read instead of the host swizzling every keyframe
+    uint32_t pad_;
 };
 
 // geometry of the multiresolution table, precomputed on the host (grid.h:195-204,964-997)

@@ -374,3 +374,27 @@ def test_optimizer_bit_exact_for_equal_gradients(core, oracle, gpu_dataset, smal
     assert ng == no and np.array_equal(g.last("rays"), o.last("rays"))
     assert (g.last("enc") != o.last("enc")).mean() <= 2e-3
     assert lg == pytest.approx(lo, abs=5e-4, rel=2e-3)
+
+
+def test_bgr_keyframes_give_the_same_batch(core, gpu_dataset, small_seq):
+    """Keyframes handed over in BGR order (the SLAM frontend's cv::Mat; the reference converts with cv::cvtColor,
+    nerf_data.cu:286) are stored as they come and swapped when the batch kernel reads a pixel: rays, targets and the
+    whole first iteration are identical to the RGB upload.  Also covers the slab storage (frames 0..n in one slab)."""
+    seq, obj = small_seq, small_seq.objects[0]
+    ds_bgr = core.Dataset(0, *seq.K, seq.H, seq.W, len(seq.poses), True)
+    for i in range(len(seq.poses)):
+        ds_bgr.add_frame(i, np.ascontiguousarray(seq.rgb[i][..., ::-1]), seq.instance[i], seq.depth[i], seq.poses[i], is_bgr=True)
+    cfg = core.default_config(rays_per_batch=512)
+    bmin, bmax = -1.1 * obj.half, 1.1 * obj.half
+    rng = np.random.default_rng(61)
+    sxy, col, dt = randoms(rng, 512)
+    outs = []
+    for ds in (gpu_dataset, ds_bgr):
+        g = core.NerfObject(ds, cfg, obj.Tow, bmin, bmax, obj.instance_id)
+        g.set_bboxes(obj.boxes)
+        loss, n_in = g.train_injected(sxy, col, dt)
+        outs.append((loss, n_in, g.last("rays"), g.last("target"), g.last("target_depth"), g.last("enc"), g.last("out")))
+        g.close()
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+    assert (outs[0][3] > 0).any()

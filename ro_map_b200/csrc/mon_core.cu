@@ -227,6 +227,10 @@ struct mon_object {
     float *r_rgb = nullptr, *r_depth = nullptr, *r_mask = nullptr, *r_Twc = nullptr;
     uint32_t r_cap_rays = 0, r_tile = 0; size_t r_jit_cap = 0;
     uint32_t render_count = 0;
+    // grow-only scratch of the inference entry points (density lattice, point queries): a cudaMalloc / cudaFree pair per
+    // call synchronises the whole device — it stalled every other object training on the GPU and the keyframe ingest
+    void* scr[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t scr_cap[4] = {0, 0, 0, 0};
     // execution
     cudaStream_t stream = nullptr, aux = nullptr;   // aux: next iteration's batch + sample points, forked inside the graphs
     cudaEvent_t ev_fork_m = nullptr, ev_fork_s = nullptr, ev_join = nullptr;
@@ -963,6 +967,7 @@ int mon_object_destroy(mon_object* o) {
                     o->dbg_out, o->dbg_dout, o->inj_xy, o->inj_col, o->inj_dt, o->grad_snap, o->r_rays, o->r_inbox, o->r_enc,
                     o->r_jit, o->r_rgb, o->r_depth, o->r_mask, o->r_Twc, o->r_pts, o->r_planar};
     for (void* p : ptrs) if (p) cudaFree(p);
+    for (void* p : o->scr) if (p) cudaFree(p);
     if (o->h_ctrl) cudaFreeHost(o->h_ctrl);
     if (o->ev0) cudaEventDestroy(o->ev0);
     if (o->ev1) cudaEventDestroy(o->ev1);
@@ -1406,6 +1411,19 @@ int mon_object_render_object_centric(mon_object* o, mon_bbox2d box, const float 
     return render_impl(o, box, Toc, true, use_ema, rand_dt, rgb, depth, mask);
 }
 
+// slot 0: encodings of infer_points_device, 1: positions, 2: logits, 3: sigma
+static int scratch(mon_object* o, int slot, size_t bytes, void** out) {
+    if (bytes > o->scr_cap[slot]) {
+        CK(cudaStreamSynchronize(o->stream));
+        if (o->scr[slot]) cudaFree(o->scr[slot]);
+        o->scr[slot] = nullptr; o->scr_cap[slot] = 0;
+        CK(cudaMalloc(&o->scr[slot], bytes));
+        o->scr_cap[slot] = bytes;
+    }
+    *out = o->scr[slot];
+    return MON_OK;
+}
+
 // network logits at arbitrary unit-cube positions (device pointer in, device out4 [n][4]); the inference half of
 // DifferentiableObject::inference as GetDensityOnGrid / compute_mesh_vertex_colors use it (nerf_model.cu:2007-2067)
 static int infer_points_device(mon_object* o, const float* d_pts, uint32_t n, int use_ema, float* d_out4) {
@@ -1419,12 +1437,12 @@ static int infer_points_device(mon_object* o, const float* d_pts, uint32_t n, in
         planar = o->r_planar;
     }
     __half* enc = nullptr;
-    CK(cudaMalloc(&enc, (size_t)n * MON_IN * 2));
+    int rc = scratch(o, 0, (size_t)n * MON_IN * 2, reinterpret_cast<void**>(&enc));
+    if (rc != MON_OK) return rc;
     cudaError_t e = mon_launch_encode_forward(o->grid, n, d_pts, planar, enc, nullptr, (uint32_t)o->sm_count, st);
     if (e == cudaSuccess) e = mon_launch_mlp_infer_tc(n, o->cfg.n_hidden_layers, params, enc, d_out4, st);
     o->launches += 2;
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(enc);
     if (e != cudaSuccess) return fail(MON_ERR_CUDA, "inference: %s", cudaGetErrorString(e));
     return MON_OK;
 }
@@ -1434,14 +1452,15 @@ int mon_object_query_points(mon_object* o, const float* points_unit, uint32_t n,
     if (n == 0) return MON_OK;
     CK(cudaSetDevice(o->ds->gpu));
     float *pts = nullptr, *res = nullptr;
-    cudaError_t e = cudaMalloc(&pts, (size_t)n * 12);
-    if (e == cudaSuccess) e = cudaMalloc(&res, (size_t)n * 16);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(pts, points_unit, (size_t)n * 12, cudaMemcpyHostToDevice, o->stream);
-    int rc = MON_OK;
+    int rc = scratch(o, 1, (size_t)n * 12, reinterpret_cast<void**>(&pts));
+    if (rc == MON_OK) rc = scratch(o, 2, (size_t)n * 16, reinterpret_cast<void**>(&res));
+    if (rc != MON_OK) return rc;
+    cudaError_t e = cudaMemcpyAsync(pts, points_unit, (size_t)n * 12, cudaMemcpyHostToDevice, o->stream);
     if (e == cudaSuccess) rc = infer_points_device(o, pts, n, use_ema, res);
-    if (e == cudaSuccess && rc == MON_OK) e = cudaMemcpy(out4, res, (size_t)n * 16, cudaMemcpyDeviceToHost);
-    if (pts) cudaFree(pts);
-    if (res) cudaFree(res);
+    if (e == cudaSuccess && rc == MON_OK) {
+        e = cudaMemcpyAsync(out4, res, (size_t)n * 16, cudaMemcpyDeviceToHost, o->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(o->stream);
+    }
     if (e != cudaSuccess) return fail(MON_ERR_CUDA, "mon_object_query_points: %s", cudaGetErrorString(e));
     return rc;
 }
@@ -1454,11 +1473,12 @@ int mon_object_density_grid(mon_object* o, const uint32_t res[3], float* out) {
     CK(cudaSetDevice(o->ds->gpu));
     cudaStream_t st = o->stream;
     float *pts = nullptr, *out4 = nullptr, *sigma = nullptr;
-    cudaError_t e = cudaMalloc(&pts, n * 12);
-    if (e == cudaSuccess) e = cudaMalloc(&out4, n * 16);
-    if (e == cudaSuccess) e = cudaMalloc(&sigma, n * 4);
-    int rc = MON_OK;
-    if (e == cudaSuccess) {
+    int rc = scratch(o, 1, n * 12, reinterpret_cast<void**>(&pts));
+    if (rc == MON_OK) rc = scratch(o, 2, n * 16, reinterpret_cast<void**>(&out4));
+    if (rc == MON_OK) rc = scratch(o, 3, n * 4, reinterpret_cast<void**>(&sigma));
+    if (rc != MON_OK) return rc;
+    cudaError_t e = cudaSuccess;
+    {
         const unsigned blocks = (unsigned)((n + 255) / 256);
         k_lattice_points<<<blocks, 256, 0, st>>>(res[0], res[1], res[2], pts);
         // inference weights (EMA), like mpNetwork->inference_mixed_precision_impl(..., use_inference_params = true) (:2028)
@@ -1470,9 +1490,6 @@ int mon_object_density_grid(mon_object* o, const uint32_t res[3], float* out) {
             if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         }
     }
-    if (pts) cudaFree(pts);
-    if (out4) cudaFree(out4);
-    if (sigma) cudaFree(sigma);
     if (rc != MON_OK) return rc;
     if (e != cudaSuccess) return fail(MON_ERR_CUDA, "density grid: %s", cudaGetErrorString(e));
     return MON_OK;

@@ -179,23 +179,41 @@ k_generate_batch(MonBatch b, MonScene sc) {
     }
 }
 
-// ---- test-render rays (GenerateRenderRays, nerf_model.cu:448-493): one ray per box pixel
-__global__ void k_render_rays(uint32_t n_rays, mon_bbox2d box, MonScene sc, const float* __restrict__ Twc_dev,
-                              MonRay* __restrict__ rays, int* __restrict__ in_box) {
+// ---- test-render rays (GenerateRenderRays, nerf_model.cu:448-493): one ray per box pixel.  Pixels whose ray misses the
+// object's box get their final value here (background, depth 0, mask 0: VolumeRender_Render's else branch, :1217-1226)
+// and are dropped: the hits are compacted (ray + original pixel index), so that sampling, hash encoding and the MLP —
+// which the reference runs for every pixel of the view — only see rays that can contribute.
+__global__ void k_render_rays(uint32_t n_rays, mon_bbox2d box, MonScene sc, const float* __restrict__ Twc_dev, float bgc,
+                              MonRay* __restrict__ rays_hit, uint32_t* __restrict__ orig, uint32_t* __restrict__ n_hit,
+                              float* __restrict__ rgb, float* __restrict__ depth, float* __restrict__ mask) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_rays) return;
-    float Twc[16];
+    bool hit = false;
+    MonRay r;
+    if (i < n_rays) {
+        float Twc[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) Twc[k] = Twc_dev[k];
-    const int x = (int)box.x + (int)(i % box.w);
-    const int y = (int)box.y + (int)(i / box.w);
-    MonRay r; float t0, t1;
-    mon_pixel_ray((float)x, (float)y, sc.K, Twc, sc.Tow, r.o, r.d, r.d_norm);
-    const bool hit = mon_ray_box(sc.bmin, sc.bmax, r.o, r.d, t0, t1);
-    r.tmin = hit ? fmaxf(t0, 0.0f) : 0.0f;
-    r.tmax = hit ? t1 : 0.0f;
-    rays[i] = r;
-    in_box[i] = hit ? 1 : 0;
+        for (int k = 0; k < 16; ++k) Twc[k] = Twc_dev[k];
+        const int x = (int)box.x + (int)(i % box.w);
+        const int y = (int)box.y + (int)(i / box.w);
+        float t0, t1;
+        mon_pixel_ray((float)x, (float)y, sc.K, Twc, sc.Tow, r.o, r.d, r.d_norm);
+        hit = mon_ray_box(sc.bmin, sc.bmax, r.o, r.d, t0, t1);
+        r.tmin = hit ? fmaxf(t0, 0.0f) : 0.0f;
+        r.tmax = hit ? t1 : 0.0f;
+        if (!hit) { rgb[i * 3] = rgb[i * 3 + 1] = rgb[i * 3 + 2] = bgc; depth[i] = 0.0f; mask[i] = 0.0f; }
+    }
+    // warp-aggregated append: one atomic per warp, lanes take consecutive slots
+    const uint32_t m = __ballot_sync(0xffffffffu, hit);
+    if (m == 0) return;
+    const uint32_t lane = threadIdx.x & 31u, leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(n_hit, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (hit) {
+        const uint32_t slot = base + __popc(m & ((1u << lane) - 1u));
+        rays_hit[slot] = r;
+        orig[slot] = i;
+    }
 }
 
 void mon_launch_generate_batch(const MonBatch& b, const MonScene& sc, cudaStream_t st, const MonLaunchOpt& lo) {
@@ -215,7 +233,8 @@ void mon_launch_generate_batch(const MonBatch& b, const MonScene& sc, cudaStream
     }
     cudaLaunchKernelEx(&cfg, k_generate_batch, b, sc);
 }
-void mon_launch_render_rays(uint32_t n_rays, mon_bbox2d box, const MonScene& sc, const float* Twc_dev,
-                            MonRay* rays, int* in_box, cudaStream_t st) {
-    k_render_rays<<<(n_rays + 127) / 128, 128, 0, st>>>(n_rays, box, sc, Twc_dev, rays, in_box);
+void mon_launch_render_rays(uint32_t n_rays, mon_bbox2d box, const MonScene& sc, const float* Twc_dev, float bgc,
+                            MonRay* rays_hit, uint32_t* orig, uint32_t* n_hit, float* rgb, float* depth, float* mask, cudaStream_t st) {
+    cudaMemsetAsync(n_hit, 0, sizeof(uint32_t), st);
+    k_render_rays<<<(n_rays + 127) / 128, 128, 0, st>>>(n_rays, box, sc, Twc_dev, bgc, rays_hit, orig, n_hit, rgb, depth, mask);
 }

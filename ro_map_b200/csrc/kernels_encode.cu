@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256)
 k_sample_points(uint32_t n_points, uint32_t S, const MonRay* __restrict__ rays, const int* __restrict__ in_box,
                 const float* __restrict__ jitter, uint32_t seed, const MonCtrl* __restrict__ ctrl, uint32_t rng_stream,
                 uint32_t iter_fixed, float bmin0, float bmin1, float bmin2, float bmax0, float bmax1, float bmax2,
-                float* __restrict__ pts) {
+                float* __restrict__ pts, const uint32_t* __restrict__ orig_ray) {
     mon_pdl_wait();
     mon_pdl_trigger();
     if (ctrl && ctrl->skip) return;
@@ -56,7 +56,8 @@ k_sample_points(uint32_t n_points, uint32_t S, const MonRay* __restrict__ rays, 
         const MonRay r = rays[ray];
         // the batch kernel already advanced ctrl->iter; this iteration's counter is iter-1
         const uint32_t iter = ctrl ? ctrl->iter - 1 : iter_fixed;
-        const float xi = mon_rand(jitter, seed, iter, rng_stream, pt);
+        // render: the rays are compacted (hits only); the jitter belongs to the pixel, not to the slot
+        const float xi = mon_rand(jitter, seed, iter, rng_stream, orig_ray ? orig_ray[ray] * S + n : pt);
         const float t = mon_sample_t(r, n, xi, (float)S);
         const float bmin[3] = {bmin0, bmin1, bmin2}, bmax[3] = {bmax0, bmax1, bmax2};
         mon_sample_point(r, t, bmin, bmax, u);
@@ -68,9 +69,9 @@ k_sample_points(uint32_t n_points, uint32_t S, const MonRay* __restrict__ rays, 
 
 void mon_launch_sample_points(uint32_t n_points, uint32_t S, const MonRay* rays, const int* in_box, const float* jitter,
                               uint32_t seed, const MonCtrl* ctrl, uint32_t rng_stream, uint32_t iter_fixed,
-                              const float* bmin, const float* bmax, float* pts, cudaStream_t st, const MonLaunchOpt& lo) {
+                              const float* bmin, const float* bmax, float* pts, cudaStream_t st, const MonLaunchOpt& lo, const uint32_t* orig_ray) {
     mon_launch_chain(MON_PDL_POINTS, lo, k_sample_points, dim3((n_points + 255) / 256), dim3(256), 0, st, n_points, S, rays, in_box, jitter, seed, ctrl, rng_stream,
-                     iter_fixed, bmin[0], bmin[1], bmin[2], bmax[0], bmax[1], bmax[2], pts);
+                     iter_fixed, bmin[0], bmin[1], bmin[2], bmax[0], bmax[1], bmax[2], pts, orig_ray);
 }
 
 // ---------------------------------------------------------------------------------------------- shared helpers

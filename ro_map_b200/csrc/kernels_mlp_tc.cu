@@ -554,7 +554,9 @@ template <int NH>
 __global__ void __launch_bounds__(TC_THREADS, TC_CTAS_PER_SM(NH))
 k_mlp_render_tc(uint32_t n_rays, uint32_t S2, const MonRay* __restrict__ rays, const int* __restrict__ in_box,
                 const float* __restrict__ jitter, uint32_t seed, uint32_t iter, const __half* __restrict__ params,
-                const __half* __restrict__ enc, float bgc, float* __restrict__ rgb, float* __restrict__ depth, float* __restrict__ mask) {
+                const __half* __restrict__ enc, float bgc, float* __restrict__ rgb, float* __restrict__ depth, float* __restrict__ mask,
+                const uint32_t* __restrict__ orig_ray) {
+    // orig_ray (render path): the rays are the compacted hits; results and jitter are indexed by the original pixel
     extern __shared__ unsigned char smem_raw[];
     TcCtx c;
     tc_setup(c, smem_raw, TC_TMEM_COLS(NH));
@@ -563,7 +565,8 @@ k_mlp_render_tc(uint32_t n_rays, uint32_t S2, const MonRay* __restrict__ rays, c
     for (uint32_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
         const uint32_t ray = grp * 4 + c.warp;
         const bool ray_ok = ray < n_rays;
-        const bool hit = ray_ok && in_box[ray] != 0;
+        const bool hit = ray_ok && (!in_box || in_box[ray] != 0);
+        const uint32_t oray = (ray_ok && orig_ray) ? orig_ray[ray] : ray;
         MonRay r;
         if (ray_ok) r = rays[ray];
         else { r.tmin = 0.0f; r.tmax = 1.0f; r.d_norm = 1.0f; }
@@ -586,18 +589,18 @@ k_mlp_render_tc(uint32_t n_rays, uint32_t S2, const MonRay* __restrict__ rays, c
 #pragma unroll
             for (int k = 0; k < 4; ++k) o[k] = __half2float(__float2half_rn(o16[k]));
             const uint32_t n = chunk * 32 + c.lane;
-            const float xi = hit ? mon_rand(jitter, seed, iter, 3, pt) : 1.0f;
+            const float xi = hit ? mon_rand(jitter, seed, iter, 3, oray * S2 + n) : 1.0f;
             const float t = mon_sample_t(r, n, xi, (float)S2);
             warp_render_chunk(o, t, c.lane, cr);
         }
         if (ray_ok && c.lane == 0) {
             if (hit && 1.0f - cr.T > 0.5f) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) rgb[ray * 3 + k] = cr.C[k] + cr.T * bgc;
-                depth[ray] = __fdiv_rn(cr.D, r.d_norm);
-                mask[ray] = 1.0f;
+                for (int k = 0; k < 3; ++k) rgb[oray * 3 + k] = cr.C[k] + cr.T * bgc;
+                depth[oray] = __fdiv_rn(cr.D, r.d_norm);
+                mask[oray] = 1.0f;
             } else {
-                rgb[ray * 3] = rgb[ray * 3 + 1] = rgb[ray * 3 + 2] = bgc; depth[ray] = 0.0f; mask[ray] = 0.0f;
+                rgb[oray * 3] = rgb[oray * 3 + 1] = rgb[oray * 3 + 2] = bgc; depth[oray] = 0.0f; mask[oray] = 0.0f;
             }
         }
     }
@@ -653,7 +656,7 @@ cudaError_t mon_launch_mlp_infer_tc(uint32_t n_points, uint32_t n_hidden, const 
 
 cudaError_t mon_launch_mlp_render_tc(uint32_t n_rays, uint32_t S2, uint32_t n_hidden, const MonRay* rays, const int* in_box, const float* jitter,
                                      uint32_t seed, uint32_t iter, const __half* params, const __half* enc, float bgc,
-                                     float* rgb, float* depth, float* mask, cudaStream_t st) {
+                                     float* rgb, float* depth, float* mask, cudaStream_t st, const uint32_t* orig_ray) {
     uint32_t ctas = (n_rays + 3) / 4;
     if (ctas > 592) ctas = 592;
     if (ctas == 0) ctas = 1;
@@ -661,12 +664,12 @@ cudaError_t mon_launch_mlp_render_tc(uint32_t n_rays, uint32_t S2, uint32_t n_hi
         static std::atomic<uint64_t> prepared{0};
         const cudaError_t prep = mon_once_per_device(prepared, [] { return tc_prepare(k_mlp_render_tc<1>, TC_SMEM_BYTES(1)); });
         if (prep != cudaSuccess) return prep;
-        k_mlp_render_tc<1><<<ctas, TC_THREADS, TC_SMEM_BYTES(1), st>>>(n_rays, S2, rays, in_box, jitter, seed, iter, params, enc, bgc, rgb, depth, mask);
+        k_mlp_render_tc<1><<<ctas, TC_THREADS, TC_SMEM_BYTES(1), st>>>(n_rays, S2, rays, in_box, jitter, seed, iter, params, enc, bgc, rgb, depth, mask, orig_ray);
     } else if (n_hidden == 2) {
         static std::atomic<uint64_t> prepared{0};
         const cudaError_t prep = mon_once_per_device(prepared, [] { return tc_prepare(k_mlp_render_tc<2>, TC_SMEM_BYTES(2)); });
         if (prep != cudaSuccess) return prep;
-        k_mlp_render_tc<2><<<ctas, TC_THREADS, TC_SMEM_BYTES(2), st>>>(n_rays, S2, rays, in_box, jitter, seed, iter, params, enc, bgc, rgb, depth, mask);
+        k_mlp_render_tc<2><<<ctas, TC_THREADS, TC_SMEM_BYTES(2), st>>>(n_rays, S2, rays, in_box, jitter, seed, iter, params, enc, bgc, rgb, depth, mask, orig_ray);
     } else {
         return cudaErrorNotSupported;
     }

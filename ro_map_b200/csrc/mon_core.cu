@@ -222,7 +222,7 @@ struct mon_object {
     float *dbg_out = nullptr, *dbg_dout = nullptr, *inj_xy = nullptr, *inj_col = nullptr, *inj_dt = nullptr, *grad_snap = nullptr;
     bool have_injected = false;
     // render workspace (lazily allocated)
-    MonRay* r_rays = nullptr; int* r_inbox = nullptr; __half* r_enc = nullptr; float* r_jit = nullptr; float* r_pts = nullptr;
+    MonRay* r_rays = nullptr; uint32_t* r_orig = nullptr; uint32_t* r_nhit = nullptr; __half* r_enc = nullptr; float* r_jit = nullptr; float* r_pts = nullptr;
     __half* r_planar = nullptr;       // planar copy of the EMA weights, refreshed per render call
     float *r_rgb = nullptr, *r_depth = nullptr, *r_mask = nullptr, *r_Twc = nullptr;
     uint32_t r_cap_rays = 0, r_tile = 0; size_t r_jit_cap = 0;
@@ -964,7 +964,7 @@ int mon_object_destroy(mon_object* o) {
     void* ptrs[] = {o->pf, o->m, o->v, o->ps, o->ph, o->gh, o->ema, o->ctrl_state, o->ctrl, o->ctrl_alt, o->ctrl_late, o->rays_alt, o->ray_inst_alt,
                     o->target_alt, o->target_depth_alt, o->bg_alt, o->d_boxes, o->rays, o->ray_inst, o->target,
                     o->target_depth, o->bg, o->rgb_rays, o->depth_rays, o->mask_rays, o->loss, o->pts, o->pts_alt, o->debias_lut, o->enc, o->d_enc, o->ph_planar, o->partials,
-                    o->dbg_out, o->dbg_dout, o->inj_xy, o->inj_col, o->inj_dt, o->grad_snap, o->r_rays, o->r_inbox, o->r_enc,
+                    o->dbg_out, o->dbg_dout, o->inj_xy, o->inj_col, o->inj_dt, o->grad_snap, o->r_rays, o->r_orig, o->r_nhit, o->r_enc,
                     o->r_jit, o->r_rgb, o->r_depth, o->r_mask, o->r_Twc, o->r_pts, o->r_planar};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (void* p : o->scr) if (p) cudaFree(p);
@@ -1325,12 +1325,12 @@ static int ensure_render_ws(mon_object* o, uint32_t n_rays, size_t jitter_floats
     const uint32_t S2 = o->cfg.render_samples_per_ray;
     const uint32_t tile = 16384;  // rays per pass: 1 Mi points, 64 MiB of fp16 features
     if (n_rays > o->r_cap_rays) {
-        void* old[] = {o->r_rays, o->r_inbox, o->r_rgb, o->r_depth, o->r_mask};
+        void* old[] = {o->r_rays, o->r_orig, o->r_rgb, o->r_depth, o->r_mask};
         for (void* p : old) if (p) cudaFree(p);
-        o->r_rays = nullptr; o->r_inbox = nullptr; o->r_rgb = o->r_depth = o->r_mask = nullptr;
+        o->r_rays = nullptr; o->r_orig = nullptr; o->r_rgb = o->r_depth = o->r_mask = nullptr;
         o->r_cap_rays = 0;
         CK(cudaMalloc(&o->r_rays, (size_t)n_rays * sizeof(MonRay)));
-        CK(cudaMalloc(&o->r_inbox, (size_t)n_rays * 4));
+        CK(cudaMalloc(&o->r_orig, (size_t)n_rays * 4));
         CK(cudaMalloc(&o->r_rgb, (size_t)n_rays * 12));
         CK(cudaMalloc(&o->r_depth, (size_t)n_rays * 4));
         CK(cudaMalloc(&o->r_mask, (size_t)n_rays * 4));
@@ -1341,6 +1341,7 @@ static int ensure_render_ws(mon_object* o, uint32_t n_rays, size_t jitter_floats
         CK(cudaMalloc(&o->r_pts, (size_t)tile * S2 * 12));
         if (!o->r_planar) CK(cudaMalloc(&o->r_planar, (size_t)o->n_grid * 2 + 16));
         CK(cudaMalloc(&o->r_Twc, 64));
+        CK(cudaMalloc(&o->r_nhit, 4));
         o->r_tile = tile;
     }
     if (jitter_floats > o->r_jit_cap) {
@@ -1364,14 +1365,16 @@ static int render_impl(mon_object* o, mon_bbox2d box, const float Twc[16], bool 
     cudaStream_t st = o->stream;
     CK(cudaMemcpyAsync(o->r_Twc, Twc, 64, cudaMemcpyHostToDevice, st));
     if (rand_dt) CK(cudaMemcpyAsync(o->r_jit, rand_dt, (size_t)n_rays * S2 * 4, cudaMemcpyHostToDevice, st));
-    if (object_centric) {   // GenerateRenderVideoRays (nerf_model.cu:495-533): the pose is camera -> OBJECT, no world hop
-        MonScene sc = o->scene;
+    const float bgc = 1.0f;   // Render / RenderVideo composite over white (nerf_model.cu:1787,1953)
+    MonScene sc = o->scene;
+    if (object_centric)       // GenerateRenderVideoRays (nerf_model.cu:495-533): the pose is camera -> OBJECT, no world hop
         for (int k = 0; k < 16; ++k) sc.Tow[k] = (k % 5 == 0) ? 1.0f : 0.0f;
-        mon_launch_render_rays(n_rays, box, sc, o->r_Twc, o->r_rays, o->r_inbox, st);
-    } else {
-        mon_launch_render_rays(n_rays, box, o->scene, o->r_Twc, o->r_rays, o->r_inbox, st);
-    }
+    // rays of the box pixels; misses get their final value here, hits are compacted (ray + pixel index)
+    mon_launch_render_rays(n_rays, box, sc, o->r_Twc, bgc, o->r_rays, o->r_orig, o->r_nhit, o->r_rgb, o->r_depth, o->r_mask, st);
     o->launches += 1;
+    uint32_t n_hit = 0;
+    CK(cudaMemcpyAsync(&n_hit, o->r_nhit, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     const __half* params = use_ema ? o->ema : o->ph;
     const __half* planar = o->ph_planar;
     if (use_ema) {   // the EMA weights have no resident planar copy: renders are rare, refresh one per call
@@ -1380,16 +1383,16 @@ static int render_impl(mon_object* o, mon_bbox2d box, const float Twc[16], bool 
         planar = o->r_planar;
     }
     const uint32_t rc_id = o->render_count++;
-    for (uint32_t r0 = 0, t = 0; r0 < n_rays; r0 += o->r_tile, ++t) {
-        const uint32_t nr = std::min(o->r_tile, n_rays - r0);
-        const float* jit = rand_dt ? o->r_jit + (size_t)r0 * S2 : nullptr;
-        const uint32_t iter_fixed = rc_id * 4099u + t;
-        mon_launch_sample_points(nr * S2, S2, o->r_rays + r0, o->r_inbox + r0, jit, o->seed, nullptr, 3, iter_fixed,
-                                 o->scene.bmin, o->scene.bmax, o->r_pts, st);
+    const float* jit = rand_dt ? o->r_jit : nullptr;       // indexed by the original pixel through r_orig
+    const uint32_t iter_fixed = rc_id * 4099u;
+    for (uint32_t r0 = 0; r0 < n_hit; r0 += o->r_tile) {
+        const uint32_t nr = std::min(o->r_tile, n_hit - r0);
+        mon_launch_sample_points(nr * S2, S2, o->r_rays + r0, nullptr, jit, o->seed, nullptr, 3, iter_fixed,
+                                 o->scene.bmin, o->scene.bmax, o->r_pts, st, MonLaunchOpt(), o->r_orig + r0);
         cudaError_t e = mon_launch_encode_forward(o->grid, nr * S2, o->r_pts, planar, o->r_enc, nullptr, (uint32_t)o->sm_count, st);
         if (e == cudaSuccess)
-            e = mon_launch_mlp_render_tc(nr, S2, o->cfg.n_hidden_layers, o->r_rays + r0, o->r_inbox + r0, jit, o->seed, iter_fixed, params,
-                                         o->r_enc, 1.0f, o->r_rgb + (size_t)r0 * 3, o->r_depth + r0, o->r_mask + r0, st);
+            e = mon_launch_mlp_render_tc(nr, S2, o->cfg.n_hidden_layers, o->r_rays + r0, nullptr, jit, o->seed, iter_fixed, params,
+                                         o->r_enc, bgc, o->r_rgb, o->r_depth, o->r_mask, st, o->r_orig + r0);
         if (e != cudaSuccess) return fail(MON_ERR_CUDA, "render launch: %s", cudaGetErrorString(e));
         o->launches += 3;
     }

@@ -74,13 +74,14 @@ inline cudaError_t mon_launch_chain(unsigned which, const MonLaunchOpt& lo, void
 
 // kernels_batch.cu
 void mon_launch_generate_batch(const MonBatch& b, const MonScene& sc, cudaStream_t st, const MonLaunchOpt& lo = MonLaunchOpt());
-void mon_launch_render_rays(uint32_t n_rays, mon_bbox2d box, const MonScene& sc, const float* Twc_dev,
-                            MonRay* rays, int* in_box, cudaStream_t st);
+void mon_launch_render_rays(uint32_t n_rays, mon_bbox2d box, const MonScene& sc, const float* Twc_dev, float bgc,
+                            MonRay* rays_hit, uint32_t* orig, uint32_t* n_hit, float* rgb, float* depth, float* mask, cudaStream_t st);
 
 // kernels_encode.cu
 void mon_launch_sample_points(uint32_t n_points, uint32_t S, const MonRay* rays, const int* in_box, const float* jitter,
                               uint32_t seed, const MonCtrl* ctrl, uint32_t rng_stream, uint32_t iter_fixed,
-                              const float* bmin, const float* bmax, float* pts, cudaStream_t st, const MonLaunchOpt& lo = MonLaunchOpt());
+                              const float* bmin, const float* bmax, float* pts, cudaStream_t st, const MonLaunchOpt& lo = MonLaunchOpt(),
+                              const uint32_t* orig_ray = nullptr);   // render: compacted ray -> pixel, indexes the jitter
 // levels [level_begin, level_end) only (default: all)
 cudaError_t mon_launch_encode_forward(const MonGrid& g, uint32_t n_points, const float* pts, const __half* planar, __half* enc_soa,
                                       const MonCtrl* ctrl, uint32_t sm_count, cudaStream_t st, uint32_t level_begin = 0,
@@ -98,7 +99,7 @@ cudaError_t mon_launch_mlp_infer_tc(uint32_t n_points, uint32_t n_hidden, const 
                                     float* out4, cudaStream_t st);
 cudaError_t mon_launch_mlp_render_tc(uint32_t n_rays, uint32_t S2, uint32_t n_hidden, const MonRay* rays, const int* in_box, const float* jitter,
                                      uint32_t seed, uint32_t iter, const __half* params, const __half* enc, float bgc,
-                                     float* rgb, float* depth, float* mask, cudaStream_t st);
+                                     float* rgb, float* depth, float* mask, cudaStream_t st, const uint32_t* orig_ray = nullptr);
 
 // kernels_optim.cu
 void mon_launch_init_grid(uint64_t state, uint64_t inc, uint32_t n, float* out, cudaStream_t st);

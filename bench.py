@@ -302,11 +302,12 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         n_views = 3
-        covered = []
+        masks = []
         for v in range(n_views):
             for n in nerfs:
-                covered.append(float(n.render(full, seq.poses[v % len(seq.poses)])[2].mean()))
+                masks.append(n.render(full, seq.poses[v % len(seq.poses)])[2])
         render_s = time.perf_counter() - t0
+        covered = [float(m.mean()) for m in masks]
         # a second figure on the object's own 2-D box (what RenderTestImg renders): most of its rays hit the 3-D box
         ob = seq.objects[mine[0]].boxes[0]
         nerfs[0].render(ob, seq.poses[ob[0]])

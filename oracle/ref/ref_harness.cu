@@ -9,11 +9,14 @@
 //     exactly the objects NeRF_Model::ResetNetwork builds (MON/Core/src/nerf_model.cu:1286-1342) and the
 //     calls Step_No_Compacted / Train_Step make (:1552-1607, :1630-1648).
 //   * RO-MAP's own glue kernels (GenerateRays, fill_rollover_rays, GenerateInputPoints, VolumeRender,
-//     VolumeRenderGradient_No_Compacted, SumLoss; nerf_model.cu:280-294,369-446,536-566,735-954,1231-1253)
-//     cannot be compiled here — every Core translation unit includes Eigen, OpenCV 3 and GLEW, none of which
-//     is installed — so they are RESTATED below in the reference's launch shape (one thread per ray,
-//     128-thread blocks, float pixels, AoS points, cuRAND XORWOW host API, the three stream syncs).
-//     They are the small, scalar part of an iteration; timing results label this arm accordingly.
+//     VolumeRenderGradient_No_Compacted, SumLoss, GenerateRenderRays, GenerateRenderInputPoints,
+//     VolumeRender_Render; nerf_model.cu:280-294,369-493,536-626,735-954,1134-1253): with -DROMAP_GENUINE (what
+//     oracle/ref/Makefile builds) this file #includes the reference's nerf_model.cu FROM WHERE IT LIES, unmodified,
+//     and launches those very kernels.  Every Core translation unit includes Eigen, OpenCV 3 and GLEW, none of which
+//     is installed here, so oracle/ref/shim/ provides stand-ins for exactly the types and calls that file names
+//     (fixed-size vectors, a 4x4 matrix, cv::Mat as a buffer, GL handle types); the arithmetic of the fixed-size
+//     expressions is written the way Eigen evaluates them (see shim/Eigen/Core).
+//     Without the flag the kernels RESTATED below in the reference's launch shape are used (kept for comparison).
 #include <tiny-cuda-nn/common_device.h>
 #include <tiny-cuda-nn/encodings/grid.h>
 #include <tiny-cuda-nn/loss.h>
@@ -21,6 +24,11 @@
 #include <tiny-cuda-nn/network_with_input_encoding.h>
 #include <tiny-cuda-nn/optimizer.h>
 #include <tiny-cuda-nn/trainer.h>
+
+#ifdef ROMAP_GENUINE
+// the reference's own translation unit, in place (its NeRF_Model host methods compile too but are never called here)
+#include ROMAP_NERF_MODEL_CU
+#endif
 
 #include <curand.h>
 
@@ -91,6 +99,22 @@ __device__ bool h_slab(const float* lo, const float* hi, const float* o, const f
 }
 
 struct Scene { float Tow[16], lo[3], hi[3]; };
+
+#ifdef ROMAP_GENUINE
+static_assert(sizeof(nerf::Ray) == sizeof(RRay) && sizeof(nerf::FrameIdAndBbox) == sizeof(RBox) && sizeof(nerf::MetaData) == sizeof(RMeta) &&
+              sizeof(Eigen::Matrix4f) == 64, "harness buffers must have the reference's POD layouts");
+nerf::BoundingBox genuine_box(const Ref* r) {
+    nerf::BoundingBox b;
+    b.min = Eigen::Vector3f(r->bmin[0], r->bmin[1], r->bmin[2]);
+    b.max = Eigen::Vector3f(r->bmax[0], r->bmax[1], r->bmax[2]);
+    return b;
+}
+Eigen::Matrix4f genuine_Tow(const Ref* r) {
+    Eigen::Matrix4f T;
+    for (int i = 0; i < 16; ++i) T.data()[i] = r->Tow[i];
+    return T;
+}
+#endif
 
 __global__ void g_rays(uint32_t R, uint32_t n_boxes, Scene sc, uint32_t* counter, const RBox* boxes, const RMeta* meta,
                        const float* sxy, const float* rcol, RRay* rays, uint8_t* rinst, float* tgt, float* tgtd,
@@ -437,24 +461,48 @@ int ref_train(void* h, uint32_t iters, const float* inj_xy, const float* inj_col
                 curandGenerateUniform(r->gen, r->rcol.data(), R * 3);
             }
             CUDA_CHECK_THROW(cudaMemsetAsync(r->counter.data(), 0, 4, st));
+#ifdef ROMAP_GENUINE
+            linear_kernel(nerf::GenerateRays, 0, st, R, (size_t)r->n_boxes, genuine_box(r), r->counter.data(), reinterpret_cast<nerf::FrameIdAndBbox*>(r->boxes.data()),
+                          genuine_Tow(r), reinterpret_cast<nerf::MetaData*>(r->meta.data()), r->sxy.data(), r->rcol.data(),
+                          reinterpret_cast<nerf::Ray*>(r->rays.data()), r->rinst.data(), r->target.data(), r->target_depth.data(), r->K.data(), r->H, r->W,
+                          r->instance_id, r->use_depth != 0);
+            CUDA_CHECK_THROW(cudaStreamSynchronize(st));
+            linear_kernel(nerf::fill_rollover_rays, 0, st, R, r->counter.data(), reinterpret_cast<nerf::Ray*>(r->rays.data()), r->rinst.data(), r->target.data(), r->target_depth.data());
+#else
             linear_kernel(g_rays, 0, st, R, r->n_boxes, sc, r->counter.data(), r->boxes.data(), r->meta.data(), r->sxy.data(), r->rcol.data(),
                           r->rays.data(), r->rinst.data(), r->target.data(), r->target_depth.data(), r->K.data(), r->H, r->W,
                           r->instance_id, r->use_depth != 0);
             CUDA_CHECK_THROW(cudaStreamSynchronize(st));
             g_rollover<<<n_blocks_linear(R), n_threads_linear, 0, st>>>(R, r->counter.data(), r->rays.data(), r->rinst.data(), r->target.data(), r->target_depth.data());
+#endif
             if (inj_dt) CUDA_CHECK_THROW(cudaMemcpyAsync(r->rdt.data(), inj_dt, (size_t)N * 4, cudaMemcpyHostToDevice, st));
             else curandGenerateUniform(r->gen, r->rdt.data(), N);
             CUDA_CHECK_THROW(cudaStreamSynchronize(st));
+#ifdef ROMAP_GENUINE
+            linear_kernel(nerf::GenerateInputPoints, 0, st, R, S, genuine_box(r), reinterpret_cast<nerf::Ray*>(r->rays.data()), r->points.data(), r->dist.data(), r->rdt.data());
+#else
             linear_kernel(g_points, 0, st, R, S, sc, r->rays.data(), r->points.data(), r->dist.data(), r->rdt.data());
+#endif
             // Step_No_Compacted (:1552-1607)
             {
                 auto ctx = r->network->forward(st, pts, &out, false, false);
+#ifdef ROMAP_GENUINE
+                linear_kernel(nerf::VolumeRender, 0, st, R, S, ow, genuine_box(r), nerf::ENerfActivation::Logistic, nerf::ENerfActivation::Exponential,
+                              r->out.data(), r->points.data(), r->dist.data(), reinterpret_cast<nerf::Ray*>(r->rays.data()), r->rcol.data(), r->counter.data(),
+                              r->rgb_rays.data(), r->depth_rays.data(), r->mask_rays.data());
+                CUDA_CHECK_THROW(cudaMemsetAsync(r->dout.data(), 0, (size_t)N * ow * sizeof(precision_t), st));
+                linear_kernel(nerf::VolumeRenderGradient_No_Compacted, 0, st, R, S, ow, genuine_box(r), nerf::ENerfActivation::Logistic, nerf::ENerfActivation::Exponential,
+                              128.0f, r->out.data(), r->points.data(), r->dist.data(), reinterpret_cast<nerf::Ray*>(r->rays.data()), r->rinst.data(), r->target.data(),
+                              r->target_depth.data(), r->rgb_rays.data(), r->depth_rays.data(), r->mask_rays.data(), r->dout.data(), r->lossbuf.data());
+                nerf::SumLoss<<<16, 256, 0, st>>>(R, r->lossbuf.data(), r->losssum.data());
+#else
                 linear_kernel(g_render, 0, st, R, S, ow, r->out.data(), r->dist.data(), r->rcol.data(), r->counter.data(),
                               r->rgb_rays.data(), r->depth_rays.data(), r->mask_rays.data());
                 CUDA_CHECK_THROW(cudaMemsetAsync(r->dout.data(), 0, (size_t)N * ow * sizeof(precision_t), st));
                 linear_kernel(g_grad, 0, st, R, S, ow, 128.0f, r->out.data(), r->dist.data(), r->rinst.data(), r->target.data(), r->target_depth.data(),
                               r->rgb_rays.data(), r->depth_rays.data(), r->mask_rays.data(), r->dout.data(), r->lossbuf.data());
                 g_sumloss<<<16, 256, 0, st>>>(R, r->lossbuf.data(), r->losssum.data());
+#endif
                 r->network->backward(st, *ctx, pts, out, dout, nullptr, false, EGradientMode::Overwrite);
             }
             r->trainer->optimizer_step(st, 128.0f);
@@ -501,4 +549,72 @@ int ref_last(void* h, int which, float* out) {
     })
 }
 
+// 1: the RO-MAP kernels in this library are the reference's own (nerf_model.cu compiled in place), 0: the restatement
+int ref_is_genuine(void) {
+#ifdef ROMAP_GENUINE
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+#ifdef ROMAP_GENUINE
+// NeRF_Model::Render's device work (nerf_model.cu:1702-1830) with the reference's own kernels and tiny-cuda-nn's inference
+// on the EMA weights: box = {FrameId, x, y, h, w}; rand_dt: h*w*64 floats in (0,1] (injected instead of cuRAND);
+// outputs rgb[h*w*3], depth[h*w], mask[h*w], plus the rays (9 floats each) and the in-box flags for stage-level checks.
+int ref_render(void* h, const void* box_v, const float* Twc16, const float* rand_dt, float* rgb, float* depth, float* mask, float* rays_out, int* inbox_out) {
+    Ref* r = static_cast<Ref*>(h);
+    GUARD(r, {
+        const nerf::FrameIdAndBbox box = *static_cast<const nerf::FrameIdAndBbox*>(box_v);
+        const uint32_t S2 = 64, n_rays = box.h * box.w;
+        const uint32_t per = 128 / S2, n128 = (n_rays + per - 1) / per * per, batch = n128 * S2;   // RenderRaysPerBatch128 (:1747-1749)
+        cudaStream_t st = r->stream;
+        GPUMemory<nerf::Ray> rays(n_rays);
+        GPUMemory<int> inbox(n_rays);
+        GPUMemory<float> pts((size_t)3 * batch), dist((size_t)S2 * n_rays), out4((size_t)4 * batch), d_rgb(3 * n_rays), d_depth(n_rays), d_mask(n_rays), rdt((size_t)S2 * n_rays);
+        pts.memset(0); out4.memset(0);
+        rdt.copy_from_host(rand_dt, (size_t)S2 * n_rays);
+        Eigen::Matrix4f Twc;
+        for (int i = 0; i < 16; ++i) Twc.data()[i] = Twc16[i];
+        linear_kernel(nerf::GenerateRenderRays, 0, st, n_rays, box, genuine_box(r), Twc, genuine_Tow(r), rays.data(), inbox.data(), r->K.data());
+        linear_kernel(nerf::GenerateRenderInputPoints, 0, st, n_rays, S2, genuine_box(r), rays.data(), inbox.data(), pts.data(), dist.data(), rdt.data());
+        GPUMatrixDynamic<float> in(pts.data(), 3, batch, CM), o4(out4.data(), 4, batch, CM);
+        r->network->inference(st, in, o4);
+        linear_kernel(nerf::VolumeRender_Render, 0, st, n_rays, S2, 4u, genuine_box(r), nerf::ENerfActivation::Logistic, nerf::ENerfActivation::Exponential, 1.0f,
+                      out4.data(), pts.data(), dist.data(), rays.data(), inbox.data(), d_rgb.data(), d_depth.data(), d_mask.data());
+        CUDA_CHECK_THROW(cudaStreamSynchronize(st));
+        d_rgb.copy_to_host(rgb, 3 * n_rays); d_depth.copy_to_host(depth, n_rays); d_mask.copy_to_host(mask, n_rays);
+        if (rays_out) CUDA_CHECK_THROW(cudaMemcpy(rays_out, rays.data(), (size_t)n_rays * 36, cudaMemcpyDeviceToHost));
+        if (inbox_out) inbox.copy_to_host(inbox_out, n_rays);
+    })
+}
+
+#endif
+
 }  // extern "C"
+
+#ifdef ROMAP_GENUINE
+// ---- link-time stand-ins: nerf_model.cu's host methods (never called by this harness) name the marching-cubes unit
+// (marching_cubes.h:49-64) and four OpenGL buffer calls; the library has to resolve them to load. They abort if reached.
+namespace {
+[[noreturn]] void ref_unreachable(const char* what) {
+    fprintf(stderr, "oracle/ref harness: %s is a link-time stand-in and must never run\n", what);
+    abort();
+}
+}  // namespace
+namespace nerf {
+Eigen::Vector3i GetMarchingCubesRes(uint32_t, const BoundingBox&) { ref_unreachable("GetMarchingCubesRes"); }
+void MarchingCubes(const BoundingBox, const Eigen::Vector3i, const float, const tcnn::GPUMemory<float>&, tcnn::GPUMemory<Eigen::Vector3f>&,
+                   tcnn::GPUMemory<uint32_t>&, cudaStream_t) { ref_unreachable("MarchingCubes"); }
+void compute_mesh_1ring(const tcnn::GPUMemory<Eigen::Vector3f>&, const tcnn::GPUMemory<uint32_t>&, tcnn::GPUMemory<Eigen::Vector4f>&,
+                        tcnn::GPUMemory<Eigen::Vector3f>&, cudaStream_t) { ref_unreachable("compute_mesh_1ring"); }
+void save_mesh(tcnn::GPUMemory<Eigen::Vector3f>&, tcnn::GPUMemory<Eigen::Vector3f>&, tcnn::GPUMemory<Eigen::Vector3f>&, tcnn::GPUMemory<uint32_t>&,
+               const char*, bool, float, Eigen::Vector3f) { ref_unreachable("save_mesh"); }
+}  // namespace nerf
+extern "C" {
+void glGenBuffers(GLsizei, GLuint*) { ref_unreachable("glGenBuffers"); }
+void glBindBuffer(GLenum, GLuint) { ref_unreachable("glBindBuffer"); }
+void glBufferData(GLenum, GLsizeiptr, const void*, GLenum) { ref_unreachable("glBufferData"); }
+void glDeleteBuffers(GLsizei, const GLuint*) { ref_unreachable("glDeleteBuffers"); }
+}
+#endif

@@ -847,6 +847,21 @@ size_t orc_object_last(const orc_object* o, int which, float* out, size_t cap) {
     return 0;
 }
 
+// GenerateRenderRays (nerf_model.cu:448-492): one ray per pixel of the 2-D box, row-major; rays outside the object box keep
+// their previous contents in the reference (unwritten), here zeros
+void orc_render_rays(uint32_t bx, uint32_t by, uint32_t bh, uint32_t bw, const float Twc[16], const float K[4],
+                     const float obj_Tow[16], const float bmin[3], const float bmax[3], orc_ray* rays, int* in_box) {
+    for (uint32_t i = 0; i < bh * bw; ++i) {
+        const int x = (int)bx + (int)(i % bw), y = (int)by + (int)(i / bw);
+        orc_ray r; float t0, t1;
+        std::memset(&r, 0, sizeof r);
+        pixel_ray((float)x, (float)y, K, Twc, obj_Tow, r.o, r.d, r.d_norm);
+        in_box[i] = ray_box(bmin, bmax, r.o, r.d, t0, t1) ? 1 : 0;
+        if (in_box[i]) { r.tmin = fmaxf(t0, 0.0f); r.tmax = t1; rays[i] = r; }
+        else std::memset(&rays[i], 0, sizeof r);
+    }
+}
+
 void orc_object_render(const orc_object* o, uint32_t bx, uint32_t by, uint32_t bh, uint32_t bw,
                        const float Twc[16], const float K[4], uint32_t S2,
                        const float* rand_dt, int use_ema, float* rgb, float* depth, float* mask) {

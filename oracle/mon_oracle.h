@@ -192,6 +192,10 @@ void orc_object_render(const orc_object*, uint32_t bx, uint32_t by, uint32_t bh,
                        const float Twc[16], const float fxfycxcy[4], uint32_t S2,
                        const float* rand_dt, int use_ema, float* rgb, float* depth, float* mask);
 
+/* A14 rays of a 2-D render box (GenerateRenderRays): rays [h*w] (zeros where in_box == 0), in_box [h*w] */
+void orc_render_rays(uint32_t bx, uint32_t by, uint32_t bh, uint32_t bw, const float Twc[16], const float fxfycxcy[4],
+                     const float obj_Tow[16], const float bmin[3], const float bmax[3], orc_ray* rays, int* in_box);
+
 /* A14/A6 without an object: raw network output [N][4] fp32 -> pixels */
 void orc_volume_render_test(uint32_t n_rays, uint32_t S2, const float* out4, const float* t,
                             const int* in_box, const float* d_norm, float bg,

@@ -204,6 +204,28 @@ def sample_points(rays: np.ndarray, S: int, bmin, bmax, rand_dt):
     return pts, t
 
 
+def render_rays(box, Twc, K, Tow, bmin, bmax):
+    """GenerateRenderRays: (rays [h*w][9], in_box [h*w]) for box = (FrameId, x, y, h, w)."""
+    _, x, y, h, w = [int(v) for v in box]
+    rays = np.zeros((h * w, 9), np.float32)
+    inb = np.zeros(h * w, np.int32)
+    lib().orc_render_rays(C.c_uint32(x), C.c_uint32(y), C.c_uint32(h), C.c_uint32(w), _p(mat16(Twc)), _p(_f32(K)), _p(mat16(Tow)),
+                          _p(_f32(bmin)), _p(_f32(bmax)), _p(rays), _p(inb))
+    return rays, inb
+
+
+def volume_render_test(S2, out4, t, in_box, d_norm, bg=1.0):
+    """VolumeRender_Render on raw fp32 network outputs [n_rays*S2][4]: (rgb [n][3], depth [n], mask [n])."""
+    inb = np.ascontiguousarray(in_box, dtype=np.int32)
+    n = inb.size
+    rgb = np.zeros((n, 3), np.float32)
+    dep = np.zeros(n, np.float32)
+    mask = np.zeros(n, np.float32)
+    lib().orc_volume_render_test(C.c_uint32(n), C.c_uint32(S2), _p(_f32(out4)), _p(_f32(t)), _p(inb), _p(_f32(d_norm)), C.c_float(bg),
+                                 _p(rgb), _p(dep), _p(mask))
+    return rgb, dep, mask
+
+
 def encode(cfg, grid_fp16_bits, points) -> np.ndarray:
     pts = _f32(points).reshape(-1, 3)
     grid = np.ascontiguousarray(grid_fp16_bits, dtype=np.uint16)

@@ -1,0 +1,128 @@
+"""Generates tests/golden/romap_golden.npz by RUNNING RO-MAP's own glue kernels on a GPU: oracle/_ref/libmon_ref.so built
+with ROMAP_GENUINE compiles the reference's nerf_model.cu from where it lies (unmodified), so GenerateRays,
+fill_rollover_rays, GenerateInputPoints, VolumeRender, VolumeRenderGradient_No_Compacted, SumLoss, GenerateRenderRays,
+GenerateRenderInputPoints and VolumeRender_Render below are the reference's kernels, fed by the reference's tiny-cuda-nn.
+
+    python oracle/ref/make_golden_romap.py [out.npz]          # needs a CUDA device; run under gpurun
+
+Rows A1-A3, A6, A7, A14 of SURVEY.md section 8a.  Every stage's INPUT is stored next to its OUTPUT (the network output that
+feeds the compositing is the reference's own), so tests/test_golden_romap.py can hold each oracle stage against the
+reference in isolation, on the CPU.  The scene (tests/conftest.py's `small_seq`) and the injected random numbers are
+regenerated bit-for-bit by the test from the seeds below; a SHA-256 of the scene guards that.  TEST INFRASTRUCTURE ONLY.
+"""
+from __future__ import annotations
+
+import hashlib
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+
+SMALL = dict(H=200, W=200, K=(277.7775, 277.7775, 100.0, 100.0))   # = tests/conftest.py
+S = 32                       # training samples per ray (nerf_model.h: mnSampleNum)
+S2 = 64                      # render samples per ray (mnRenderSampleNum)
+CASES = [                    # (tag, object index, rays per batch, use depth, warm-up iterations, seed of the injected randoms)
+    ("a_", 0, 256, True, 600, 4242),
+    ("b_", 1, 128, False, 40, 4243),
+]
+RENDER_HW = (12, 16)         # rendered window (h, w), straddling the left edge of the object's 2-D box
+
+
+def make_scene():
+    from ro_map_b200 import synthetic as syn
+    return syn.make_sequence(n_frames=6, n_objects=2, seed=1337, **SMALL)
+
+
+def scene_sha(seq) -> str:
+    h = hashlib.sha256()
+    for a in list(seq.rgb) + list(seq.instance) + list(seq.depth) + list(seq.poses):
+        h.update(np.ascontiguousarray(a).tobytes())
+    for o in seq.objects:
+        h.update(np.ascontiguousarray(o.Tow, np.float32).tobytes() + np.ascontiguousarray(o.half, np.float32).tobytes())
+        h.update(np.array(o.boxes, np.int64).tobytes())
+    return h.hexdigest()
+
+
+def injected(seed: int, R: int):
+    """(sample_xy [R,2], rand_colors [R,3], rand_dt [R,S]) in (0,1], like curandGenerateUniform."""
+    rng = np.random.default_rng(seed)
+    return tuple((1.0 - rng.random(shape, dtype=np.float32)).astype(np.float32) for shape in ((R, 2), (R, 3), (R, S)))
+
+
+def render_window(obj):
+    """(FrameId, x, y, h, w): RENDER_HW pixels at mid height of the object's first 2-D box, starting 5 px left of it."""
+    fid, x, y, h, w = [int(v) for v in obj.boxes[0]]
+    return (fid, max(0, x - 5), y + h // 2, RENDER_HW[0], RENDER_HW[1])
+
+
+def render_dt(seed: int, n_rays: int):
+    rng = np.random.default_rng(seed + 1000)
+    return (1.0 - rng.random((n_rays, S2), dtype=np.float32)).astype(np.float32)
+
+
+def f16_bits(a: np.ndarray) -> np.ndarray:
+    h = a.astype(np.float16)
+    assert np.array_equal(h.astype(np.float32), a), "value is not fp16-representable"
+    return h.view(np.uint16)
+
+
+def main(out_path: str):
+    from ref_binding import RefLib, RefModel
+    lib = RefLib()
+    seq = make_scene()
+    gold = {"scene_sha256": np.array(scene_sha(seq))}
+    for tag, k, R, use_depth, warm, seed in CASES:
+        obj = seq.objects[k]
+        bmin, bmax = -1.1 * obj.half, 1.1 * obj.half
+        m = RefModel(1, 1337, lib)
+        assert m.is_genuine(), "libmon_ref.so was built without ROMAP_GENUINE"
+        m.scene(seq.rgb, seq.instance, seq.depth, seq.poses, seq.H, seq.W, seq.K, obj.boxes, obj.Tow, bmin, bmax, obj.instance_id, use_depth, R)
+        m.train(warm)                                         # cuRAND-driven warm-up so that densities and colours are not flat
+        sxy, col, dt = injected(seed, R)
+        _, _, loss, n_in = m.train(1, (sxy, col, dt))
+        N = R * S
+        gold[tag + "n_in"] = np.array(n_in)
+        gold[tag + "loss"] = np.array(loss, np.float32)
+        gold[tag + "rays"] = m.last(0, R * 9).reshape(R, 9)
+        gold[tag + "ray_instance"] = m.last(12, R).astype(np.uint8)
+        gold[tag + "target"] = m.last(10, R * 3).reshape(R, 3)
+        gold[tag + "target_depth"] = m.last(11, R)
+        gold[tag + "points"] = m.last(1, N * 3).reshape(N, 3)
+        gold[tag + "dist"] = m.last(2, N)
+        out = m.last(4, N * 16).reshape(N, 16)
+        gold[tag + "out_bits"] = f16_bits(out)                # all 16 padded columns: the reference's kernels index with the padded width
+        gold[tag + "rgb_rays"] = m.last(5, R * 3).reshape(R, 3)
+        gold[tag + "depth_rays"] = m.last(6, R)
+        gold[tag + "mask_rays"] = m.last(7, R)
+        dout = m.last(8, N * 16).reshape(N, 16)
+        assert not dout[:, 4:].any(), "dL/dout of the padding columns must stay zero"
+        gold[tag + "dout_bits"] = f16_bits(dout[:, :4])
+        gold[tag + "loss_rays"] = m.last(13, R)
+        # Render (EMA weights) of a small window
+        box = render_window(obj)
+        n_rays = box[3] * box[4]
+        rdt = render_dt(seed, n_rays)
+        r = m.render(box, seq.poses[box[0]], rdt)
+        gold[tag + "r_box"] = np.array(box, np.uint32)
+        gold[tag + "r_rays"] = r["rays"]
+        gold[tag + "r_in_box"] = r["in_box"]
+        gold[tag + "r_points"] = r["points"]
+        gold[tag + "r_dist"] = r["dist"]
+        if np.array_equal(r["out4"].astype(np.float16).astype(np.float32), r["out4"]):
+            gold[tag + "r_out4_bits"] = f16_bits(r["out4"])   # tiny-cuda-nn computes in fp16 and widens: store the bits
+        else:
+            gold[tag + "r_out4_f32"] = r["out4"]
+        gold[tag + "r_rgb"], gold[tag + "r_depth"], gold[tag + "r_mask"] = r["rgb"], r["depth"], r["mask"]
+        print(tag, "n_in", n_in, "loss", loss, "opaque training rays", int((gold[tag + "mask_rays"] > 0.5).sum()), "render hits", int(r["in_box"].sum()),
+              "render opaque", int(r["mask"].sum()), "early-stopped rays", int((np.abs(dout[:, :4]).reshape(R, S, 4).sum(-1)[:, -1] == 0).sum()), flush=True)
+        m.close()
+        np.savez_compressed(out_path, **gold)                  # after every case: a later failure keeps the earlier cases
+    print("wrote", out_path, Path(out_path).stat().st_size, "bytes")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1] if len(sys.argv) > 1 else str(ROOT / "gpurun_out" / "romap_golden.npz"))

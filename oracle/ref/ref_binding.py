@@ -43,6 +43,9 @@ class RefLib:
         L.ref_scene.argtypes = [vp, C.c_uint32, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, C.c_uint32, vp, vp, vp, C.c_uint8, C.c_int, C.c_uint32]
         L.ref_train.argtypes = [vp, C.c_uint32, vp, vp, vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
         L.ref_last.argtypes = [vp, C.c_int, vp]
+        L.ref_is_genuine.restype = C.c_int
+        if L.ref_is_genuine():
+            L.ref_render.argtypes = [vp] * 12
         self.L = L
 
 
@@ -127,6 +130,24 @@ class RefModel:
         out = np.zeros(n, np.float32)
         self._ck(self.lib.ref_last(self.h, which, out.ctypes.data))
         return out
+
+    def is_genuine(self) -> bool:
+        """True when RO-MAP's glue kernels in the library are the reference's own nerf_model.cu (not the restatement)."""
+        return bool(self.lib.ref_is_genuine())
+
+    def render(self, box, Twc, rand_dt):
+        """NeRF_Model::Render's device work on box = (FrameId, x, y, h, w) with 64 samples per ray and the EMA weights.
+        Returns a dict with the final pixels and every intermediate buffer."""
+        b = np.ascontiguousarray(np.array([int(v) for v in box], dtype=np.uint32))
+        n, S2 = int(b[3]) * int(b[4]), 64
+        twc = np.ascontiguousarray(np.asarray(Twc, np.float32).reshape(4, 4).T).reshape(16)
+        dt = np.ascontiguousarray(rand_dt, np.float32)
+        assert dt.size == n * S2
+        o = dict(rgb=np.zeros((n, 3), np.float32), depth=np.zeros(n, np.float32), mask=np.zeros(n, np.float32), rays=np.zeros((n, 9), np.float32),
+                 in_box=np.zeros(n, np.int32), points=np.zeros((n * S2, 3), np.float32), dist=np.zeros(n * S2, np.float32), out4=np.zeros((n * S2, 4), np.float32))
+        self._ck(self.lib.ref_render(self.h, b.ctypes.data, twc.ctypes.data, dt.ctypes.data, o["rgb"].ctypes.data, o["depth"].ctypes.data, o["mask"].ctypes.data,
+                                     o["rays"].ctypes.data, o["in_box"].ctypes.data, o["points"].ctypes.data, o["dist"].ctypes.data, o["out4"].ctypes.data))
+        return o
 
     def close(self):
         if self.h:

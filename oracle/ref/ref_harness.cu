@@ -562,7 +562,8 @@ int ref_is_genuine(void) {
 // NeRF_Model::Render's device work (nerf_model.cu:1702-1830) with the reference's own kernels and tiny-cuda-nn's inference
 // on the EMA weights: box = {FrameId, x, y, h, w}; rand_dt: h*w*64 floats in (0,1] (injected instead of cuRAND);
 // outputs rgb[h*w*3], depth[h*w], mask[h*w], plus the rays (9 floats each) and the in-box flags for stage-level checks.
-int ref_render(void* h, const void* box_v, const float* Twc16, const float* rand_dt, float* rgb, float* depth, float* mask, float* rays_out, int* inbox_out) {
+int ref_render(void* h, const void* box_v, const float* Twc16, const float* rand_dt, float* rgb, float* depth, float* mask, float* rays_out, int* inbox_out,
+               float* points_out /* [h*w*64][3] */, float* dist_out /* [h*w*64] */, float* out4_out /* [h*w*64][4] */) {
     Ref* r = static_cast<Ref*>(h);
     GUARD(r, {
         const nerf::FrameIdAndBbox box = *static_cast<const nerf::FrameIdAndBbox*>(box_v);
@@ -572,7 +573,7 @@ int ref_render(void* h, const void* box_v, const float* Twc16, const float* rand
         GPUMemory<nerf::Ray> rays(n_rays);
         GPUMemory<int> inbox(n_rays);
         GPUMemory<float> pts((size_t)3 * batch), dist((size_t)S2 * n_rays), out4((size_t)4 * batch), d_rgb(3 * n_rays), d_depth(n_rays), d_mask(n_rays), rdt((size_t)S2 * n_rays);
-        pts.memset(0); out4.memset(0);
+        pts.memset(0); out4.memset(0); dist.memset(0); rays.memset(0);
         rdt.copy_from_host(rand_dt, (size_t)S2 * n_rays);
         Eigen::Matrix4f Twc;
         for (int i = 0; i < 16; ++i) Twc.data()[i] = Twc16[i];
@@ -586,6 +587,9 @@ int ref_render(void* h, const void* box_v, const float* Twc16, const float* rand
         d_rgb.copy_to_host(rgb, 3 * n_rays); d_depth.copy_to_host(depth, n_rays); d_mask.copy_to_host(mask, n_rays);
         if (rays_out) CUDA_CHECK_THROW(cudaMemcpy(rays_out, rays.data(), (size_t)n_rays * 36, cudaMemcpyDeviceToHost));
         if (inbox_out) inbox.copy_to_host(inbox_out, n_rays);
+        if (points_out) pts.copy_to_host(points_out, (size_t)3 * S2 * n_rays);
+        if (dist_out) dist.copy_to_host(dist_out, (size_t)S2 * n_rays);
+        if (out4_out) out4.copy_to_host(out4_out, (size_t)4 * S2 * n_rays);
     })
 }
 

@@ -398,3 +398,48 @@ def test_bgr_keyframes_give_the_same_batch(core, gpu_dataset, small_seq):
     for a, b in zip(*outs):
         assert np.array_equal(a, b)
     assert (outs[0][3] > 0).any()
+
+
+@pytest.mark.parametrize("tag", ["a_", "b_"])
+def test_batch_against_reference_kernels(core, small_seq, tag):
+    """The batch kernel held directly against RO-MAP's OWN GenerateRays / fill_rollover_rays (tests/golden/romap_golden.npz,
+    produced by the reference's nerf_model.cu on a B200 — see tests/test_golden_romap.py): same scene, same injected
+    randoms.  The reference's slot order is an atomicAdd race, ours is ascending sample index: compared as multisets."""
+    import sys
+    sys.path.insert(0, str(__import__("pathlib").Path(__file__).resolve().parent))
+    import test_golden_romap as tg
+    mg = tg.mg
+    gold = np.load(tg.GOLD)
+    _, k, R, use_depth, _, seed = next(c for c in mg.CASES if c[0] == tag)
+    seq, obj = small_seq, small_seq.objects[k]
+    assert mg.scene_sha(seq) == str(gold["scene_sha256"])
+    ds = core.Dataset(0, *seq.K, seq.H, seq.W, len(seq.poses), use_depth)
+    for i in range(len(seq.poses)):
+        ds.add_frame(i, seq.rgb[i], seq.instance[i], seq.depth[i] if use_depth else None, seq.poses[i])
+    g = core.NerfObject(ds, core.default_config(rays_per_batch=R), obj.Tow, -1.1 * obj.half, 1.1 * obj.half, obj.instance_id, 1337)
+    g.set_bboxes(obj.boxes)
+    sxy, col, dt = mg.injected(seed, R)
+    _, n_in = g.train_injected(sxy, col, dt)
+    assert n_in == int(gold[tag + "n_in"])                                       # the same rays survive occlusion + slab test
+    rays = g.last("rays").reshape(R, 9)
+    ref = gold[tag + "rays"]
+    key = lambda r: np.lexsort((r[:, 8], r[:, 5], r[:, 4], r[:, 3]))            # noqa: E731
+    pg, pr = key(rays[:n_in]), key(ref[:n_in])
+    assert tg.rays_close(rays[:n_in][pg], ref[:n_in][pr])                        # <= 8 ulp / 1.5e-6, see rays_close
+    inst_g, inst_r = g.last("ray_instance")[:n_in][pg], gold[tag + "ray_instance"][:n_in][pr]
+    assert np.array_equal(inst_g, inst_r)
+    assert tg.ulp32(g.last("target_depth")[:n_in][pg], gold[tag + "target_depth"][:n_in][pr]).max() <= 2
+    on = inst_r == 1
+    assert np.array_equal(g.last("target").reshape(R, 3)[:n_in][pg][on], gold[tag + "target"][:n_in][pr][on])   # keyframe pixels
+    tgt = g.last("target").reshape(R, 3)
+    bg = g.last("ray_instance")[:n_in] == 0
+    assert np.array_equal(tgt[:n_in][bg], col[:n_in][bg])                        # background rays: the random colour of their slot
+    idx = np.arange(R) % n_in                                                    # roll-over padding
+    assert np.array_equal(rays, rays[idx]) and np.array_equal(tgt, tgt[idx])
+    # sample points: the reference's own GenerateInputPoints output is reproduced bit-exactly from the reference's rays by the
+    # oracle (CPU test); here the kernel's points must be the oracle's for the kernel's rays
+    from oracle import mon_oracle
+    pts_o, _ = mon_oracle.sample_points(rays, 32, -1.1 * obj.half, 1.1 * obj.half, dt)
+    assert np.array_equal(g.last("points").reshape(-1, 3), pts_o)
+    g.close()
+    ds.close()

@@ -1,9 +1,9 @@
-"""Generates tests/golden/romap_golden.npz by RUNNING RO-MAP's own glue kernels on a GPU: oracle/_ref/libmon_ref.so built
+"""Generates tests/golden/romap_golden.npz and romap_mesh_golden.npz by RUNNING RO-MAP's own glue kernels on a GPU: oracle/_ref/libmon_ref.so built
 with ROMAP_GENUINE compiles the reference's nerf_model.cu from where it lies (unmodified), so GenerateRays,
 fill_rollover_rays, GenerateInputPoints, VolumeRender, VolumeRenderGradient_No_Compacted, SumLoss, GenerateRenderRays,
 GenerateRenderInputPoints and VolumeRender_Render below are the reference's kernels, fed by the reference's tiny-cuda-nn.
 
-    python oracle/ref/make_golden_romap.py [out.npz]          # needs a CUDA device; run under gpurun
+    python oracle/ref/make_golden_romap.py [out.npz] [--mesh-only]          # needs a CUDA device; run under gpurun
 
 Rows A1-A3, A6, A7, A14 of SURVEY.md section 8a.  Every stage's INPUT is stored next to its OUTPUT (the network output that
 feeds the compositing is the reference's own), so tests/test_golden_romap.py can hold each oracle stage against the
@@ -64,18 +64,36 @@ def render_dt(seed: int, n_rays: int):
     return (1.0 - rng.random((n_rays, S2), dtype=np.float32)).astype(np.float32)
 
 
+MESH_BOX = (np.array([-1.0, -2.0, -0.5], np.float32), np.array([1.0, 2.0, 0.5], np.float32))   # object box of the mesh cases
+MESH_CASES = [("sphere", 24), ("noise", 14)]
+
+
+def mesh_lattice(kind: str, res: int) -> np.ndarray:
+    """[z][y][x] density lattice: an off-centre sphere of radius 0.3 (unit-cube metric) around the threshold 2.0, or white
+    noise in [0,4) with an empty border (every one of the 256 cell configurations occurs, ambiguous faces included)."""
+    if kind == "sphere":
+        ax = (np.arange(res, dtype=np.float32) / np.float32(res - 1)).astype(np.float32)
+        z, y, x = np.meshgrid(ax, ax, ax, indexing="ij")
+        r = np.sqrt((x - np.float32(0.5)) ** 2 + (y - np.float32(0.45)) ** 2 + (z - np.float32(0.55)) ** 2, dtype=np.float32)
+        return (np.float32(2.0) + np.float32(40.0) * (np.float32(0.3) - r)).astype(np.float32)
+    rng = np.random.default_rng(777)
+    d = np.zeros((res, res, res), np.float32)
+    d[1:-1, 1:-1, 1:-1] = (4.0 * rng.random((res - 2,) * 3, dtype=np.float32)).astype(np.float32)
+    return d
+
+
 def f16_bits(a: np.ndarray) -> np.ndarray:
     h = a.astype(np.float16)
     assert np.array_equal(h.astype(np.float32), a), "value is not fp16-representable"
     return h.view(np.uint16)
 
 
-def main(out_path: str):
+def main(out_path: str, mesh_only: bool = False):
     from ref_binding import RefLib, RefModel
     lib = RefLib()
     seq = make_scene()
     gold = {"scene_sha256": np.array(scene_sha(seq))}
-    for tag, k, R, use_depth, warm, seed in CASES:
+    for tag, k, R, use_depth, warm, seed in ([] if mesh_only else CASES):
         obj = seq.objects[k]
         bmin, bmax = -1.1 * obj.half, 1.1 * obj.half
         m = RefModel(1, 1337, lib)
@@ -121,8 +139,23 @@ def main(out_path: str):
               "render opaque", int(r["mask"].sum()), "early-stopped rays", int((np.abs(dout[:, :4]).reshape(R, S, 4).sum(-1)[:, -1] == 0).sum()), flush=True)
         m.close()
         np.savez_compressed(out_path, **gold)                  # after every case: a later failure keeps the earlier cases
-    print("wrote", out_path, Path(out_path).stat().st_size, "bytes")
+    if not mesh_only:
+        print("wrote", out_path, Path(out_path).stat().st_size, "bytes")
+    # the reference's marching cubes (marching_cubes.cu, compiled in place) on two lattices -> a second, small fixture
+    mesh = {}
+    m = RefModel(1, 1337, lib)
+    obj = seq.objects[0]
+    m.scene(seq.rgb[:1], seq.instance[:1], seq.depth[:1], seq.poses[:1], seq.H, seq.W, seq.K, obj.boxes[:1], obj.Tow, MESH_BOX[0], MESH_BOX[1], obj.instance_id, True, 128)
+    for kind, res in MESH_CASES:
+        v, n, idx = m.marching_cubes(mesh_lattice(kind, res), 2.0)
+        mesh[kind + "_verts"], mesh[kind + "_normals"], mesh[kind + "_indices"] = v, n, idx
+        print("mesh", kind, res, "verts (padded)", len(v), "referenced", len(np.unique(idx)), "triangles", len(idx) // 3, flush=True)
+    m.close()
+    mesh_path = str(Path(out_path).with_name("romap_mesh_golden.npz"))
+    np.savez_compressed(mesh_path, **mesh)
+    print("wrote", mesh_path, Path(mesh_path).stat().st_size, "bytes")
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else str(ROOT / "gpurun_out" / "romap_golden.npz"))
+    args = [a for a in sys.argv[1:] if a != "--mesh-only"]
+    main(args[0] if args else str(ROOT / "gpurun_out" / "romap_golden.npz"), mesh_only="--mesh-only" in sys.argv)

@@ -46,6 +46,7 @@ class RefLib:
         L.ref_is_genuine.restype = C.c_int
         if L.ref_is_genuine():
             L.ref_render.argtypes = [vp] * 12
+            L.ref_marching_cubes.argtypes = [vp, vp, C.c_uint32, C.c_float, vp, vp, C.c_uint32, C.POINTER(C.c_uint32), vp, C.c_uint32, C.POINTER(C.c_uint32)]
         self.L = L
 
 
@@ -148,6 +149,19 @@ class RefModel:
         self._ck(self.lib.ref_render(self.h, b.ctypes.data, twc.ctypes.data, dt.ctypes.data, o["rgb"].ctypes.data, o["depth"].ctypes.data, o["mask"].ctypes.data,
                                      o["rays"].ctypes.data, o["in_box"].ctypes.data, o["points"].ctypes.data, o["dist"].ctypes.data, o["out4"].ctypes.data))
         return o
+
+    def marching_cubes(self, density, thresh: float = 2.0):
+        """The reference's MarchingCubes + compute_mesh_1ring on a [res,res,res] lattice (z, y, x order = x fastest) over the scene's
+        object box.  Returns (verts [n,3] incl. the reference's zero padding to a multiple of 128, normals [n,3] un-normalised, indices [m])."""
+        d = np.ascontiguousarray(density, np.float32)
+        res = d.shape[0]
+        assert d.shape == (res, res, res)
+        cap_v, cap_i = 3 * res ** 3, 15 * res ** 3
+        verts, normals, idx = np.zeros((cap_v, 3), np.float32), np.zeros((cap_v, 3), np.float32), np.zeros(cap_i, np.uint32)
+        nv, ni = C.c_uint32(0), C.c_uint32(0)
+        self._ck(self.lib.ref_marching_cubes(self.h, d.ctypes.data, res, thresh, verts.ctypes.data, normals.ctypes.data, cap_v, C.byref(nv),
+                                             idx.ctypes.data, cap_i, C.byref(ni)))
+        return verts[: nv.value].copy(), normals[: nv.value].copy(), idx[: ni.value].copy()
 
     def close(self):
         if self.h:

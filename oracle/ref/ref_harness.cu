@@ -26,8 +26,9 @@
 #include <tiny-cuda-nn/trainer.h>
 
 #ifdef ROMAP_GENUINE
-// the reference's own translation unit, in place (its NeRF_Model host methods compile too but are never called here)
+// the reference's own translation units, in place (NeRF_Model's host methods compile too but are never called here)
 #include ROMAP_NERF_MODEL_CU
+#include ROMAP_MARCHING_CUBES_CU
 #endif
 
 #include <curand.h>
@@ -593,28 +594,43 @@ int ref_render(void* h, const void* box_v, const float* Twc16, const float* rand
     })
 }
 
+
+// MarchingCubes + compute_mesh_1ring of the reference (marching_cubes.cu:474-510,655-663) on a host density lattice [res^3], x fastest.
+// verts/normals: room for verts_cap vertices (xyz); n_verts receives the padded vertex count the reference allocates, n_idx 3 * triangles.
+int ref_marching_cubes(void* h, const float* density, uint32_t res, float thresh, float* verts_out, float* normals_out, uint32_t verts_cap, uint32_t* n_verts,
+                       uint32_t* idx_out, uint32_t idx_cap, uint32_t* n_idx) {
+    Ref* r = static_cast<Ref*>(h);
+    GUARD(r, {
+        GPUMemory<float> d((size_t)res * res * res);
+        d.copy_from_host(density, (size_t)res * res * res);
+        GPUMemory<Eigen::Vector3f> verts, normals;
+        GPUMemory<Eigen::Vector4f> smoothed;
+        GPUMemory<uint32_t> indices;
+        nerf::MarchingCubes(genuine_box(r), Eigen::Vector3i((int)res, (int)res, (int)res), thresh, d, verts, indices, r->stream);
+        nerf::compute_mesh_1ring(verts, indices, smoothed, normals, r->stream);
+        CUDA_CHECK_THROW(cudaDeviceSynchronize());
+        *n_verts = (uint32_t)verts.size(); *n_idx = (uint32_t)indices.size();
+        if (verts.size() > verts_cap || indices.size() > idx_cap) throw std::runtime_error("ref_marching_cubes: output buffers too small");
+        if (verts.size()) {
+            CUDA_CHECK_THROW(cudaMemcpy(verts_out, verts.data(), verts.size() * 12, cudaMemcpyDeviceToHost));
+            CUDA_CHECK_THROW(cudaMemcpy(normals_out, normals.data(), normals.size() * 12, cudaMemcpyDeviceToHost));
+        }
+        if (indices.size()) indices.copy_to_host(idx_out, indices.size());
+    })
+}
 #endif
 
 }  // extern "C"
 
 #ifdef ROMAP_GENUINE
-// ---- link-time stand-ins: nerf_model.cu's host methods (never called by this harness) name the marching-cubes unit
-// (marching_cubes.h:49-64) and four OpenGL buffer calls; the library has to resolve them to load. They abort if reached.
+// ---- link-time stand-ins: nerf_model.cu's host methods (never called by this harness) name four OpenGL buffer calls; the
+// library has to resolve them to load. They abort if reached.
 namespace {
 [[noreturn]] void ref_unreachable(const char* what) {
     fprintf(stderr, "oracle/ref harness: %s is a link-time stand-in and must never run\n", what);
     abort();
 }
 }  // namespace
-namespace nerf {
-Eigen::Vector3i GetMarchingCubesRes(uint32_t, const BoundingBox&) { ref_unreachable("GetMarchingCubesRes"); }
-void MarchingCubes(const BoundingBox, const Eigen::Vector3i, const float, const tcnn::GPUMemory<float>&, tcnn::GPUMemory<Eigen::Vector3f>&,
-                   tcnn::GPUMemory<uint32_t>&, cudaStream_t) { ref_unreachable("MarchingCubes"); }
-void compute_mesh_1ring(const tcnn::GPUMemory<Eigen::Vector3f>&, const tcnn::GPUMemory<uint32_t>&, tcnn::GPUMemory<Eigen::Vector4f>&,
-                        tcnn::GPUMemory<Eigen::Vector3f>&, cudaStream_t) { ref_unreachable("compute_mesh_1ring"); }
-void save_mesh(tcnn::GPUMemory<Eigen::Vector3f>&, tcnn::GPUMemory<Eigen::Vector3f>&, tcnn::GPUMemory<Eigen::Vector3f>&, tcnn::GPUMemory<uint32_t>&,
-               const char*, bool, float, Eigen::Vector3f) { ref_unreachable("save_mesh"); }
-}  // namespace nerf
 extern "C" {
 void glGenBuffers(GLsizei, GLuint*) { ref_unreachable("glGenBuffers"); }
 void glBindBuffer(GLenum, GLuint) { ref_unreachable("glBindBuffer"); }

@@ -4,11 +4,20 @@
 #include <cstdio>
 #include <map>
 #include <set>
+#include <string>
+#include <vector>
 
 #include "mesh.h"
 
 static const float C0[3] = {0.5f, 0.45f, 0.55f};
+static bool g_random = false;   // "random": white noise with an empty border — every one of the 256 cell configurations occurs
 static float field(float x, float y, float z) {
+    if (g_random) {
+        if (x <= 0.0f || y <= 0.0f || z <= 0.0f || x >= 1.0f || y >= 1.0f || z >= 1.0f) return 0.0f;
+        uint32_t h = (uint32_t)(x * 4096.0f) * 73856093u ^ (uint32_t)(y * 4096.0f) * 19349663u ^ (uint32_t)(z * 4096.0f) * 83492791u;
+        h ^= h >> 15; h *= 0x2c1b3c6du; h ^= h >> 12; h *= 0x297a2d39u; h ^= h >> 15;
+        return 4.0f * (float)(h >> 8) / 16777216.0f;   // [0,4): half of the lattice points are above the threshold 2.0
+    }
     const float dx = x - C0[0], dy = y - C0[1], dz = z - C0[2];
     return 2.0f + 40.0f * (0.3f - std::sqrt(dx * dx + dy * dy + dz * dz));
 }
@@ -32,11 +41,22 @@ int mon_object_query_points(mon_object*, const float* p, uint32_t n, int, float*
 
 int main(int argc, char** argv) {
     const uint32_t res = argc > 1 ? (uint32_t)atoi(argv[1]) : 64;
+    g_random = argc > 3 && std::string(argv[3]) == "random";
     const float bmin[3] = {-1.0f, -2.0f, -0.5f}, bmax[3] = {1.0f, 2.0f, 0.5f};
     mesh::Extracted m;
     std::string err;
     if (!mesh::extract(nullptr, bmin, bmax, res, 2.0f, m, err)) { printf("error %s\n", err.c_str()); return 1; }
-    const size_t nv = m.verts.size() / 3, nf = m.indices.size() / 3;
+    const size_t nv = m.n_surface_verts, nf = m.indices.size() / 3, n_padded = m.verts.size() / 3;
+    size_t bad_padding = (n_padded % 128 != 0) + (n_padded < nv) + (n_padded >= nv + 128);   // padded to the next multiple of 128 ...
+    for (size_t v = nv; v < n_padded; ++v)                                                       // ... with zero vertices and zero normals
+        for (int k = 0; k < 3; ++k) bad_padding += (m.verts[3 * v + k] != 0.0f) + (m.normals[3 * v + k] != 0.0f);
+    size_t cases_seen = 0, unreferenced = 0;
+    {
+        std::vector<char> ref(nv, 0);
+        for (uint32_t i : m.indices) { if (i >= nv) ++bad_padding; else ref[i] = 1; }
+        for (char r : ref) unreferenced += !r;
+        for (int mask = 0; mask < 256; ++mask) cases_seen += mesh::mc::table()[mask].n > 0;
+    }
     // every undirected edge shared by exactly two triangles, and traversed once in each direction (consistent winding)
     std::map<std::pair<uint32_t, uint32_t>, int> directed;
     std::set<std::pair<uint32_t, uint32_t>> undirected;
@@ -67,8 +87,9 @@ int main(int argc, char** argv) {
             if (std::abs((int)m.colors[3 * v + k] - want) > 1) ++bad_col;
         }
     }
-    printf("verts %zu faces %zu edges %zu bad_edges %zu euler %ld max_r_err %.6f min_normal_dot %.4f bad_colors %zu\n", nv, nf, undirected.size(), bad_edges,
-           (long)nv - (long)undirected.size() + (long)nf, max_r_err, min_dot, bad_col);
+    printf("verts %zu faces %zu edges %zu bad_edges %zu euler %ld max_r_err %.6f min_normal_dot %.4f bad_colors %zu padded_verts %zu bad_padding %zu "
+           "unreferenced %zu cases %zu\n", nv, nf, undirected.size(), bad_edges, (long)nv - (long)undirected.size() + (long)nf, max_r_err, min_dot, bad_col,
+           n_padded, bad_padding, unreferenced, cases_seen);
     if (argc > 2) return mesh::save_ply(argv[2], m.verts, m.normals, m.colors, m.indices) ? 0 : 2;
     return 0;
 }

@@ -169,3 +169,69 @@ def test_render_rays_points_and_pixels(oracle, scene, case):
     assert np.allclose(rgb, g["r_rgb"], rtol=0, atol=2e-6)
     assert np.allclose(dep, g["r_depth"], rtol=2e-6, atol=2e-6)
     assert (g["r_rgb"][~hit] == 1.0).all() and not g["r_depth"][~hit].any()       # misses: white, depth 0
+
+
+# ---- mesh: ro_map_b200/host/mesh.h against the reference's own MarchingCubes + compute_mesh_1ring ----------------------------
+MESH_GOLD = ROOT / "tests" / "golden" / "romap_mesh_golden.npz"
+
+
+def _our_marching_cubes(tmp_path, kind, res):
+    import subprocess
+    exe = tmp_path / "mesh_golden"
+    if not exe.exists():
+        subprocess.run(["g++", "-O2", "-std=c++17", f"-I{ROOT / 'ro_map_b200' / 'host'}", f"-I{ROOT / 'include'}",
+                        str(ROOT / "tests" / "host" / "mesh_golden.cpp"), "-o", str(exe)], check=True)
+    lat = tmp_path / f"{kind}.f32"
+    mg.mesh_lattice(kind, res).tofile(lat)
+    lo, hi = mg.MESH_BOX
+    out = subprocess.run([str(exe), str(lat), str(res), "2.0", *[repr(float(v)) for v in lo], *[repr(float(v)) for v in hi], str(tmp_path / kind)],
+                         capture_output=True, text=True, check=True).stdout.split()
+    n_surface = int(out[0])
+    verts = np.fromfile(str(tmp_path / kind) + ".verts", np.float32).reshape(-1, 3)
+    normals = np.fromfile(str(tmp_path / kind) + ".normals", np.float32).reshape(-1, 3)
+    idx = np.fromfile(str(tmp_path / kind) + ".indices", np.uint32)
+    return n_surface, verts, normals, idx
+
+
+def _canonical_triangles(verts, idx):
+    """triangles as rows of 9 coordinates, vertex order rotated so that the smallest vertex comes first (winding kept)"""
+    t = verts[idx.reshape(-1, 3)]                                              # [m, 3, 3]
+    order = np.lexsort((t[:, :, 2], t[:, :, 1], t[:, :, 0]), axis=1)[:, 0]     # index of the smallest vertex of each triangle
+    rolled = np.stack([np.roll(t[i], -order[i], axis=0) for i in range(len(t))]) if len(t) else t
+    return rolled.reshape(-1, 9)
+
+
+@pytest.mark.parametrize("kind,res", mg.MESH_CASES)
+def test_marching_cubes_against_reference(tmp_path, kind, res):
+    """(f)1: vertices, triangles and 1-ring normals of the host mesh extraction vs the reference's marching_cubes.cu run on a
+    B200 (vertex order there is an atomicAdd race: compared as sets).  The triangle lists per cell configuration are derived,
+    not copied (mesh.h); the reference's published table resolves a face whose corners alternate differently for a
+    configuration and its complement (the known source of cracks), ours by one rule.  Measured: bit-identical vertex sets and
+    equal triangle counts on both lattices; about half of the triangles identical, the others differ by the diagonal chosen
+    inside a polygon."""
+    gold = np.load(MESH_GOLD)
+    rv, rn, ri = gold[kind + "_verts"], gold[kind + "_normals"], gold[kind + "_indices"]
+    n_surface, v, n, idx = _our_marching_cubes(tmp_path, kind, res)
+    assert len(v) == len(rv) and len(v) % 128 == 0                             # the reference pads the vertex count to a multiple of 128 ...
+    used = np.unique(ri)
+    assert len(used) == n_surface and not rv[np.setdiff1d(np.arange(len(rv)), used)].any()   # ... with zero vertices
+    assert not v[n_surface:].any() and np.array_equal(np.unique(idx), np.arange(n_surface))
+    key = lambda a: np.lexsort((a[:, 2], a[:, 1], a[:, 0]))                    # noqa: E731
+    a, b = v[:n_surface], rv[used]
+    a, b = a[key(a)], b[key(b)]
+    assert np.array_equal(a, b)                                                # (x + (thresh-f0)/(f1-f0)) * scale + min: bit-identical vertex set
+    ta, tb = _canonical_triangles(v, idx), _canonical_triangles(rv, ri)
+    assert len(ta) == len(tb)                                                  # same number of triangles, also on the noise lattice
+    sa = {tuple(r) for r in ta}
+    sb = {tuple(r) for r in tb}
+    common = len(sa & sb) / max(len(sb), 1)
+    assert common > 0.45, common                # identical incl. winding; the rest differ by the diagonal chosen inside a polygon (measured 0.51 / 0.54)
+    # the differing triangles cover the same polygons: both meshes use every surface vertex and are closed (checked in test_host_facade)
+    # normals (1-ring, area weighted): same direction per vertex up to the diagonal choice
+    rn_u = rn[used] / np.maximum(np.linalg.norm(rn[used], axis=1, keepdims=True), 1e-30)
+    na, nb = n[:n_surface][key(v[:n_surface])], rn_u[key(rv[used])]
+    dots = np.sum(na * nb, axis=1)
+    if kind == "sphere":
+        assert (dots > 0.95).all() and np.median(dots) > 0.999, dots.min()
+    else:
+        assert np.median(dots) > 0.9 and (dots > 0).mean() > 0.97, (np.median(dots), (dots > 0).mean())

@@ -146,7 +146,8 @@ def test_online_manager_replay(tmp_path, host_lib):
 def test_mesh_extraction_on_analytic_field(tmp_path):
     """ro_map_b200/host/mesh.h (GenerateMesh/TransCPUMesh/SaveMesh replacement) on an analytic sphere field, the two
     C-ABI calls stubbed (tests/host/mesh_check.cpp): closed 2-manifold with consistent winding (Euler characteristic 2),
-    vertices on the iso-surface, outward 1-ring normals, colours = logistic(rgb logits), reference PLY layout."""
+    vertices on the iso-surface, outward 1-ring normals, colours = logistic(rgb logits), reference PLY layout and vertex padding;
+    then watertightness on white noise (every marching-cubes configuration)."""
     exe = tmp_path / "mesh_check"
     subprocess.run(["g++", "-O2", "-std=c++17", f"-I{ROOT / 'ro_map_b200' / 'host'}", f"-I{ROOT / 'include'}",
                     str(ROOT / "tests" / "host" / "mesh_check.cpp"), "-o", str(exe)], check=True)
@@ -162,7 +163,15 @@ def test_mesh_extraction_on_analytic_field(tmp_path):
         assert hdr[0] == "ply" and hdr[1] == "format ascii 1.0" and hdr[-2] == "property list uchar int vertex_index"
         assert [l for l in hdr if l.startswith("property")][:9] == [f"property float {c}" for c in ("x", "y", "z", "nx", "ny", "nz")] + \
             [f"property uchar {c}" for c in ("red", "green", "blue")]
-        assert len(txt) - len(hdr) == int(fact["verts"] + fact["faces"])
+        assert len(txt) - len(hdr) == int(fact["padded_verts"] + fact["faces"])
+        # the reference pads the vertex array to a multiple of 128 with zero vertices (marching_cubes.cu:499); every configuration has triangles
+        assert fact["bad_padding"] == 0 and fact["unreferenced"] == 0 and fact["cases"] == 254, fact
+    # white noise with an empty border: all 256 cell configurations incl. faces whose corners alternate — still a closed surface in
+    # which every edge is shared by exactly two triangles with opposite directions (no cracks, consistent winding)
+    out = subprocess.run([str(exe), "40", str(tmp_path / "noise.ply"), "random"], capture_output=True, text=True, check=True).stdout.split()
+    fact = {out[i]: float(out[i + 1]) for i in range(0, len(out), 2)}
+    assert fact["verts"] > 50000 and fact["bad_edges"] == 0 and fact["bad_padding"] == 0 and fact["unreferenced"] == 0, fact
+    assert 2 * fact["edges"] == 3 * fact["faces"]
 
 
 def test_pose_math_turntable_and_quaternion(tmp_path):

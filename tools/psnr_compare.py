@@ -93,6 +93,7 @@ def main():
             r = ref_binding.RefModel(args.hidden_layers, seed, lib)
             r.scene(seq.rgb, seq.instance, seq.depth, seq.poses, seq.H, seq.W, seq.K, train, obj.Tow, bmin, bmax, obj.instance_id, True, args.rays)
             _, _, loss_r, _ = r.train(args.iters)
+            ref_kernels = "RO-MAP's own nerf_model.cu kernels + unmodified tiny-cuda-nn" if r.is_genuine() else "glue kernels restated + unmodified tiny-cuda-nn"
             ref_ema = r.get(2)
             r.close()
             p_o, n_views = psnr_views(core, ds, cfg, seq, obj, ours_ema, held)
@@ -106,7 +107,8 @@ def main():
     print(json.dumps({"summary": True, "runs": len(rows), "mean_psnr_ours_db": round(float(np.mean([r["psnr_ours_db"] for r in rows])), 3),
                       "mean_psnr_reference_db": round(float(np.mean([r["psnr_reference_db"] for r in rows])), 3),
                       "mean_delta_db": round(float(d.mean()), 3), "std_delta_db": round(float(d.std()), 3),
-                      "ours_random_stream": "numpy (injected)" if args.inject else "in-kernel", "rays_per_batch": args.rays, "n_hidden_layers": args.hidden_layers, "image": f"{s}x{s}", "keyframes": args.frames}))
+                      "ours_random_stream": "numpy (injected)" if args.inject else "in-kernel", "rays_per_batch": args.rays, "n_hidden_layers": args.hidden_layers, "image": f"{s}x{s}", "keyframes": args.frames,
+                      "reference": ref_kernels}))
 
 
 if __name__ == "__main__":

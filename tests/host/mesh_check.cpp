@@ -87,6 +87,29 @@ int main(int argc, char** argv) {
             if (std::abs((int)m.colors[3 * v + k] - want) > 1) ++bad_col;
         }
     }
+    // signed volume enclosed by the surface in unit-cube coordinates (divergence theorem); the reference's winding makes the
+    // geometric normals point INTO the dense side, so the enclosed volume comes out negative
+    double vol6 = 0.0;
+    for (size_t f = 0; f < nf; ++f) {
+        double p[3][3];
+        for (int k = 0; k < 3; ++k)
+            for (int d = 0; d < 3; ++d) p[k][d] = (m.verts[3 * m.indices[3 * f + k] + d] - bmin[d]) / (bmax[d] - bmin[d]);
+        vol6 += p[0][0] * (p[1][1] * p[2][2] - p[1][2] * p[2][1]) - p[0][1] * (p[1][0] * p[2][2] - p[1][2] * p[2][0]) + p[0][2] * (p[1][0] * p[2][1] - p[1][1] * p[2][0]);
+    }
+    // the derived triangle lists respect the cube's symmetries: a configuration and its image under a rotation about the z axis
+    // or the x axis (together they generate all 24 rotations) have the same number of triangles
+    size_t asym = 0;
+    {
+        const int rz[8] = {1, 2, 3, 0, 5, 6, 7, 4};   // corner c -> its image under a quarter turn about z
+        const int rx[8] = {3, 2, 6, 7, 0, 1, 5, 4};   // ... about x: (x,y,z) -> (x, 1-z, y)
+        for (int mask = 0; mask < 256; ++mask)
+            for (const int* rot : {rz, rx}) {
+                int img = 0;
+                for (int c = 0; c < 8; ++c) if (mask >> c & 1) img |= 1 << rot[c];
+                asym += mesh::mc::table()[mask].n != mesh::mc::table()[img].n;
+            }
+    }
+    printf("volume %.6f asymmetric_cases %zu ", vol6 / 6.0, asym);
     printf("verts %zu faces %zu edges %zu bad_edges %zu euler %ld max_r_err %.6f min_normal_dot %.4f bad_colors %zu padded_verts %zu bad_padding %zu "
            "unreferenced %zu cases %zu\n", nv, nf, undirected.size(), bad_edges, (long)nv - (long)undirected.size() + (long)nf, max_r_err, min_dot, bad_col,
            n_padded, bad_padding, unreferenced, cases_seen);

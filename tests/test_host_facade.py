@@ -161,6 +161,10 @@ def test_mesh_extraction_on_analytic_field(tmp_path):
         assert fact["verts"] > 100 and fact["bad_edges"] == 0 and fact["euler"] == 2, fact
         assert fact["faces"] == 2 * fact["verts"] - 4                           # closed triangle mesh of genus 0
         assert fact["max_r_err"] < r_tol and fact["min_normal_dot"] > 0.95 and fact["bad_colors"] == 0, fact
+        # the reference's winding (geometric normals into the dense side) encloses the sphere's volume with a negative sign;
+        # the derived triangle lists respect the cube's rotations
+        assert abs(-fact["volume"] - 4.0 / 3.0 * np.pi * 0.3 ** 3) < (2e-3 if res == 64 else 4e-3), fact
+        assert fact["asymmetric_cases"] == 0
         txt = ply.read_text().splitlines()
         hdr = txt[:txt.index("end_header") + 1]
         assert hdr[0] == "ply" and hdr[1] == "format ascii 1.0" and hdr[-2] == "property list uchar int vertex_index"

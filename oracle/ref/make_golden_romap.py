@@ -82,6 +82,53 @@ def mesh_lattice(kind: str, res: int) -> np.ndarray:
     return d
 
 
+TRAJ = dict(obj=0, R=256, iters=30, seed=9000, stride=997)   # trajectory case: Train_Step's loop for 30 iterations from the initial weights
+
+
+def traj_randoms(it: int, seq, obj, bmin, bmax):
+    """Injected randoms of trajectory iteration `it`, made independent of the reference's slot race: one background colour and
+    one jitter row for all slots, and pixels re-drawn (oracle as the judge) until every slot's ray survives, so that the batch
+    needs no roll-over padding.  Deterministic in (seed, it, scene)."""
+    from oracle import mon_oracle as orc
+    R = TRAJ["R"]
+    rng = np.random.default_rng(TRAJ["seed"] + it)
+    u = lambda shape: (1.0 - rng.random(shape, dtype=np.float32)).astype(np.float32)   # noqa: E731
+    col = np.repeat(u((1, 3)), R, axis=0)
+    dt = np.repeat(u((1, S)), R, axis=0)
+    frames = orc.Frames(seq.rgb, seq.instance, seq.depth, seq.poses)
+    sxy = np.zeros((R, 2), np.float32)
+    for i in range(R):
+        box = obj.boxes[i % len(obj.boxes)]
+        for _ in range(500):
+            cand = u((1, 2))
+            if orc.generate_rays(1, [box], frames, seq.H, seq.W, seq.K, obj.Tow, bmin, bmax, obj.instance_id, True, cand, col[:1])[0] == 1:
+                break
+        else:
+            raise RuntimeError("no surviving pixel")
+        sxy[i] = cand[0]
+    return sxy, col, dt
+
+
+def make_traj(out_path: str):
+    from ref_binding import RefLib, RefModel
+    seq = make_scene()
+    obj = seq.objects[TRAJ["obj"]]
+    bmin, bmax = -1.1 * obj.half, 1.1 * obj.half
+    m = RefModel(1, 1337, RefLib())
+    assert m.is_genuine()
+    m.scene(seq.rgb, seq.instance, seq.depth, seq.poses, seq.H, seq.W, seq.K, obj.boxes, obj.Tow, bmin, bmax, obj.instance_id, True, TRAJ["R"])
+    losses = []
+    for it in range(TRAJ["iters"]):
+        _, _, loss, n_in = m.train(1, traj_randoms(it, seq, obj, bmin, bmax))
+        assert n_in == TRAJ["R"], (it, n_in)
+        losses.append(loss)
+    gold = {"scene_sha256": np.array(scene_sha(seq)), "loss": np.array(losses, np.float32),
+            "master_sample": m.get(0)[:: TRAJ["stride"]].copy(), "ema_sample": m.get(2)[:: TRAJ["stride"]].copy(), "master_mlp": m.get(0)[:3072].copy()}
+    m.close()
+    np.savez_compressed(out_path, **gold)
+    print("trajectory", [round(float(v), 5) for v in losses[:3]], "...", [round(float(v), 5) for v in losses[-3:]], "wrote", out_path, flush=True)
+
+
 def f16_bits(a: np.ndarray) -> np.ndarray:
     h = a.astype(np.float16)
     assert np.array_equal(h.astype(np.float32), a), "value is not fp16-representable"
@@ -157,5 +204,8 @@ def main(out_path: str, mesh_only: bool = False):
 
 
 if __name__ == "__main__":
+    if "--traj" in sys.argv:
+        make_traj(str(ROOT / "gpurun_out" / "romap_traj_golden.npz"))
+        sys.exit(0)
     args = [a for a in sys.argv[1:] if a != "--mesh-only"]
     main(args[0] if args else str(ROOT / "gpurun_out" / "romap_golden.npz"), mesh_only="--mesh-only" in sys.argv)

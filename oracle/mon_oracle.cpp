@@ -171,16 +171,18 @@ inline bool ray_box(const float bmin[3], const float bmax[3], const float o[3], 
     return t0 != FLT_MAX;
 }
 
-// 3x3 (column-major 4x4 upper-left) times vector, fixed order ((c0*v0 + c1*v1) + c2*v2), no fusion
+// 3x3 (column-major 4x4 upper-left) times vector.  Eigen evaluates the fixed-size product row by row as the reduction
+// x0 + (x1 + x2) (redux_novec_unroller halves the range) and nvcc's default --fmad=true fuses both multiply-adds:
+// fma(c0, v0, fma(c1, v1, c2 * v2)).  Pinned bit for bit by the rays of the reference's own kernels (romap_golden.npz).
 inline void rot3(const float M[16], const float v[3], float out[3]) {
-    for (int r = 0; r < 3; ++r) out[r] = (M[0 * 4 + r] * v[0] + M[1 * 4 + r] * v[1]) + M[2 * 4 + r] * v[2];
+    for (int r = 0; r < 3; ++r) out[r] = fmaf(M[0 * 4 + r], v[0], fmaf(M[1 * 4 + r], v[1], M[2 * 4 + r] * v[2]));
 }
 
 // camera pixel -> object-space ray (nerf_model.cu:403-413)
 inline void pixel_ray(float x, float y, const float K[4], const float Twc[16], const float Tow[16],
                       float o[3], float d[3], float& d_norm) {
     float dir[3] = {(x - K[2]) / K[0], (y - K[3]) / K[1], 1.0f};
-    d_norm = sqrtf((dir[0] * dir[0] + dir[1] * dir[1]) + dir[2] * dir[2]);
+    d_norm = sqrtf(fmaf(dir[0], dir[0], fmaf(dir[1], dir[1], dir[2] * dir[2])));   // d.norm(): the same reduction, fused the same way
     float dn[3] = {dir[0] / d_norm, dir[1] / d_norm, dir[2] / d_norm};
     float dw[3]; rot3(Twc, dn, dw);
     float ow[3] = {Twc[12], Twc[13], Twc[14]};

@@ -45,17 +45,21 @@ MON_DEV bool mon_ray_box(const float* bmin, const float* bmax, const float* o, c
     return t0 != FLT_MAX;
 }
 
+// 3x3 block (column-major 4x4) times vector as the reference build evaluates Eigen's fixed-size product: the row reduction is
+// x0 + (x1 + x2) (Eigen's unrolled redux splits the range in halves) and nvcc fuses every multiply-add of it —
+// fma(m0, v0, fma(m1, v1, m2 * v2)).  Bit-identical to the rays of the reference's GenerateRays / GenerateRenderRays
+// (tests/golden/romap_golden.npz, tests/test_device_math_host.py).
 MON_DEV void mon_rot3(const float* M, const float* v, float* out) {
 #pragma unroll
     for (int r = 0; r < 3; ++r)
-        out[r] = __fadd_rn(__fadd_rn(__fmul_rn(M[r], v[0]), __fmul_rn(M[4 + r], v[1])), __fmul_rn(M[8 + r], v[2]));
+        out[r] = __fmaf_rn(M[r], v[0], __fmaf_rn(M[4 + r], v[1], __fmul_rn(M[8 + r], v[2])));
 }
 
 // pixel -> object-space ray (nerf_model.cu:403-413)
 MON_DEV void mon_pixel_ray(float x, float y, const float* K, const float* Twc, const float* Tow,
                            float* o, float* d, float& d_norm) {
     float dir[3] = {__fdiv_rn(x - K[2], K[0]), __fdiv_rn(y - K[3], K[1]), 1.0f};
-    d_norm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dir[0], dir[0]), __fmul_rn(dir[1], dir[1])), __fmul_rn(dir[2], dir[2])));
+    d_norm = __fsqrt_rn(__fmaf_rn(dir[0], dir[0], __fmaf_rn(dir[1], dir[1], __fmul_rn(dir[2], dir[2]))));   // squaredNorm: the same reduction
     float dn[3] = {__fdiv_rn(dir[0], d_norm), __fdiv_rn(dir[1], d_norm), __fdiv_rn(dir[2], d_norm)};
     float dw[3]; mon_rot3(Twc, dn, dw);
     float ow[3] = {Twc[12], Twc[13], Twc[14]};

@@ -386,7 +386,8 @@ def run_ours(args, rank, world, local_rank):
                 "stage_ms_sum": sum(stages.values()), "stages": stage_roof,
                 "note": "stage times come from a serial (un-forked) replay with a CUDA event between kernels; the production graph overlaps batch+points of iteration i+1 with scatter+optimizer of iteration i"}
 
-    base = cpu_baseline(seq, seq.objects[0], R, args.hidden_layers, args.cpu_seconds)
+    # the CPU baseline is timed on rank 0 of the single-GPU run only (it is a property of the host, not of N)
+    base = cpu_baseline(seq, seq.objects[0], R, args.hidden_layers, args.cpu_seconds) if world == 1 else None
 
     iters_per_s = n_objects * K / (ms_max * 1e-3)
     line = {

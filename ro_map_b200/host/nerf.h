@@ -39,7 +39,7 @@ public:
     Eigen::Matrix4f GetObjTow();
     CPUMeshData& GetCPUMeshData();
     std::vector<FrameIdAndBbox> GetFrameIdAndBBox();
-    void DrawCPUMesh();   // needs an OpenGL context; a no-op in headless builds
+    void DrawCPUMesh();   // OpenGL client arrays where <GL/gl.h> exists at build time; a no-op in headless builds
     void DrawMesh();
     void SaveMesh(const std::string outname);   // NeRF_Model::SaveMesh: ASCII PLY of the current CPU mesh
     // additions (not in the reference): logged loss of the last Train_Step and its device time

@@ -15,6 +15,15 @@
 #include <map>
 #include <sstream>
 
+// The viewer draws the CPU mesh with OpenGL client arrays (nerf.cu:484-507).  Where the OpenGL header exists (the RO-MAP tree:
+// Pangolin / GLEW) the call is real and libMON.so needs -lGL; in a headless image it compiles to a no-op.  -DMON_NO_GL forces that.
+#if !defined(MON_NO_GL) && defined(__has_include)
+#if __has_include(<GL/gl.h>)
+#include <GL/gl.h>
+#define MON_HAVE_GL 1
+#endif
+#endif
+
 #include "mon_c.h"
 #include "nerf_data.h"
 #include "nerf_manager.h"
@@ -538,8 +547,24 @@ BoundingBox NeRF::GetBoundingBox() { return mBoundingBox; }
 Eigen::Matrix4f NeRF::GetObjTow() { return mObjTow; }
 CPUMeshData& NeRF::GetCPUMeshData() { return mCPUMeshData; }
 vector<FrameIdAndBbox> NeRF::GetFrameIdAndBBox() { return mFrameIdBbox; }
-void NeRF::DrawCPUMesh() {}   // OpenGL immediate-mode drawing in the reference (nerf.cu:484-530); headless here
-void NeRF::DrawMesh() {}
+// Called by the viewer thread every frame (src/MapDrawer.cc:396, MON/main.cpp): draws the latest CPU mesh from client arrays —
+// positions, 1-ring normals, u8 colours, the reference's triangle winding — and never waits for a mesh update in flight
+// (try-lock, the frame is skipped instead; nerf.cu:488-490).
+void NeRF::DrawCPUMesh() {
+#ifdef MON_HAVE_GL
+    std::unique_lock<std::mutex> lock(mCPUMeshData.mesh_mutex, std::try_to_lock);
+    if (!lock.owns_lock() || !mCPUMeshData.have_reslult) return;
+    const CPUMeshData& m = mCPUMeshData;
+    static const GLenum kArrays[3] = {GL_VERTEX_ARRAY, GL_NORMAL_ARRAY, GL_COLOR_ARRAY};
+    for (GLenum a : kArrays) glEnableClientState(a);
+    glVertexPointer(3, GL_FLOAT, 0, m.verts.data());
+    glNormalPointer(GL_FLOAT, 0, m.normals.data());
+    glColorPointer(3, GL_UNSIGNED_BYTE, 0, m.colors.data());
+    glDrawElements(GL_TRIANGLES, (GLsizei)m.indices.size(), GL_UNSIGNED_INT, m.indices.data());
+    for (GLenum a : kArrays) glDisableClientState(a);
+#endif
+}
+void NeRF::DrawMesh() { DrawCPUMesh(); }   // the reference's VBO variant is dead code (nerf.cu:140-145 uses the CPU mesh only)
 
 // ------------------------------------------------------------------------------------------ NerfManagerOffline
 NerfManagerOffline::NerfManagerOffline(const string datasetPath, const string networkConfigFile, bool useDenseDepth)

@@ -208,3 +208,24 @@ def test_pose_math_turntable_and_quaternion(tmp_path):
         B = np.eye(4); B[:3, :3] = Rotation.random(random_state=5).as_matrix(); B[:3, 3] = (0.3, -0.2, 0.9)
         C = run("mul", *T.T.reshape(-1), *B.T.reshape(-1)).reshape(4, 4).T
         assert np.allclose(C, T @ B, atol=1e-5)
+
+
+def test_draw_cpu_mesh_issues_the_reference_gl_calls(tmp_path):
+    """nerf::NeRF::DrawCPUMesh (nerf.cu:484-507) against a recording stand-in for <GL/gl.h> (tests/host/gl_stub): client arrays for
+    positions / normals / u8 colours, one glDrawElements over the index list; nothing is drawn before a mesh exists or while the
+    training thread holds the mesh (try-lock).  The shipped libMON.so of this image is headless (no GL header -> no-op)."""
+    from ro_map_b200 import build
+    build.build()
+    exe = tmp_path / "draw_check"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-pthread", f"-I{ROOT / 'tests' / 'host' / 'gl_stub'}", f"-I{ROOT / 'include'}", f"-I{ROOT / 'ro_map_b200' / 'host'}",
+                    str(ROOT / "ro_map_b200" / "host" / "nerf_host.cpp"), str(ROOT / "tests" / "host" / "draw_check.cpp"),
+                    f"-L{ROOT / 'ro_map_b200'}", "-lmon_b200", "-lz", f"-Wl,-rpath,{ROOT / 'ro_map_b200'}", "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("-- ")
+    sect = {s.splitlines()[0]: s.splitlines()[1:] for s in out if s.strip()}
+    drawn = ["enable 8074", "enable 8075", "enable 8076", "vertex 3 1406 0 verts", "normal 1406 0 normals", "color 3 1401 0 colors",
+             "draw 4 3 1405 indices", "disable 8074", "disable 8075", "disable 8076"]
+    assert sect["no mesh yet"] == [] and sect["mesh being updated by the training thread"] == []
+    assert sect["mesh present"] == drawn and sect["manager entry point"] == drawn
+    # the library built for this image has no OpenGL dependency
+    needed = subprocess.run(["readelf", "-d", str(ROOT / "ro_map_b200" / "libMON.so")], capture_output=True, text=True).stdout
+    assert "libGL" not in needed

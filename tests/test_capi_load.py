@@ -132,3 +132,14 @@ def test_product_does_not_reference_the_oracle():
         if p.is_file() and p.suffix in {".py", ".cu", ".cuh", ".h", ".cpp", ".hpp"}:
             text = p.read_text(errors="ignore")
             assert "mon_oracle" not in text and "orc_" not in text and "libmon_ref" not in text, p
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/mon_c.h is the drop-in boundary: it must compile as C99 (no C++, no torch, no CUDA types in the signatures) so that
+    cgo / JNI / ctypes-style hosts can bind it."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('#include "mon_c.h"\nint main(void) { mon_config c; mon_bbox2d b; (void)c; (void)b; return (int)sizeof(mon_bbox2d) - 20; }\n')
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", f"-I{ROOT / 'include'}", str(src), "-o", str(exe)], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0          # FrameIdAndBbox layout: 5 x u32

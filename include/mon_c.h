@@ -5,7 +5,7 @@
  * (/root/reference/dependencies/Multi-Object-NeRF/Core, "MON/Core" below).  The reference
  * boundary is a C++ class ABI (nerf::NerfManagerOffline / nerf::NerfManagerOnline /
  * nerf::NeRF, MON/Core/include/nerf_manager.h:21-91, nerf.h:19-88); the C++ facade in
- * include/mon/ (same class names and signatures) is a thin shim over THIS interface, and
+ * ro_map_b200/host/ (same class names and signatures) is a thin shim over THIS interface, and
  * INTEGRATION.md shows the binding a RO-MAP maintainer adds.
  *
  * Conventions: plain pointers and sizes, no C++/torch types; every call returns
@@ -90,6 +90,12 @@ int mon_dataset_create(int gpu, float fx, float fy, float cx, float cy, int H, i
  * pinned staging buffer, synchronous) or pinned (see mon_dataset_sync). */
 int mon_dataset_add_frame(mon_dataset* ds, uint32_t frame_id, const uint8_t* rgb, int is_bgr,
                           const uint8_t* instance, const float* depth, const float pose[16]);
+/* The same for a keyframe that is ALREADY in the memory of the dataset's GPU (written by a decoder, or received from another
+ * GPU by an NCCL broadcast — how bench.py replicates the keyframe set at N > 1): device-to-device copies on the dataset's
+ * upload stream, asynchronous.  The caller makes sure the source buffers are complete before the call and keeps them valid
+ * until mon_dataset_sync(). */
+int mon_dataset_add_frame_device(mon_dataset* ds, uint32_t frame_id, const uint8_t* d_rgb, int is_bgr,
+                                 const uint8_t* d_instance, const float* d_depth, const float pose[16]);
 /* Page-locked (cudaHostAlloc / cudaHostRegister) RGB-order buffers are uploaded asynchronously without a staging copy;
  * they must stay valid until mon_dataset_sync() returns or a blocking call on an object of this dataset completes. */
 int mon_dataset_sync(mon_dataset* ds);
@@ -99,6 +105,11 @@ int mon_dataset_frame_count(const mon_dataset* ds, uint32_t* n);
 /* next-row: replicate every frame of src (another GPU) into dst over NVLink peer
  * copies instead of re-uploading from the host (nerf_manager.cu:203-216 uploads once per GPU) */
 int mon_dataset_clone_from_peer(mon_dataset* dst, const mon_dataset* src);
+/* online variant of the same: ONE keyframe, already added to src (upload possibly still in flight), is copied device to
+ * device into dst on dst's upload stream; returns without waiting.  NerfManagerOnline::NewFrameToDataset uploads a frame
+ * once over PCIe and replicates it with this call (the reference: one host thread and one PCIe upload per GPU,
+ * nerf_manager.cu:189-218). */
+int mon_dataset_copy_frame_from_peer(mon_dataset* dst, const mon_dataset* src, uint32_t frame_id);
 int mon_dataset_destroy(mon_dataset* ds);
 
 /* ---- object -------------------------------------------------------------------------------- */
@@ -115,12 +126,15 @@ int mon_object_set_bboxes(mon_object* obj, const mon_bbox2d* boxes, uint32_t n);
 int mon_object_add_bboxes(mon_object* obj, const mon_bbox2d* boxes, uint32_t n);
 
 /* NeRF_Model::Train_Step / Train_Step_Online (nerf_model.cu:1630-1699): `iters` iterations of
- * GenerateBatch -> Step_No_Compacted -> optimizer_step, replayed as one CUDA graph per
- * iteration on the object's stream with no host synchronisation in between.
+ * GenerateBatch -> Step_No_Compacted -> optimizer_step, replayed as CUDA graphs (64 iterations each + one graph of
+ * exactly the remainder, captured on first use of that length) on the object's stream with no host synchronisation in between.
  * mon_object_train blocks until done and returns the logged loss of the last iteration
  * (sum over rays / R, nerf_model.cu:1650-1658) if loss != NULL. */
 int mon_object_train(mon_object* obj, uint32_t iters, float* loss);
 int mon_object_train_async(mon_object* obj, uint32_t iters);
+/* the allocation half of AllocateBatchWorkspace (nerf_model.cu:1344-1427) for calls of `iters` iterations: captures and
+ * instantiates the iteration graphs now, so that the first mon_object_train[_async](iters) does not pay for it */
+int mon_object_prepare_train(mon_object* obj, uint32_t iters);
 int mon_object_sync(mon_object* obj);
 /* device time (ms, CUDA events on the object's stream) of the last train / train_async call;
  * valid after the call completed */
@@ -129,10 +143,14 @@ int mon_object_step_count(mon_object* obj, uint32_t* step);
 /* Measurement hook: `iters` iterations launched kernel by kernel (no graph) with a CUDA event between the
  * stages on the object's stream; stage_ms[k] = mean device time of stage k per iteration.
  * Stages: 0 batch (ray generation + compaction), 1 sample positions, 2 hash-grid encode, 3 fused MLP forward +
- * volume render + loss + MLP backward, 4 hash-grid gradient scatter, 5 optimizer sweep (Adam + EMA + grad zero +
- * logged-loss reduction).  n_stages must be MON_N_STAGES. */
+ * volume render + loss + MLP backward, 4 hash-grid gradient scatter fused with Adam + EMA of the grid parameters,
+ * 5 optimizer of the MLP weights (gradient reduction, Adam, EMA) + logged-loss reduction.  n_stages must be MON_N_STAGES. */
 #define MON_N_STAGES 6
 int mon_object_train_profiled(mon_object* obj, uint32_t iters, float* stage_ms, uint32_t n_stages);
+/* samples of the last iteration that carried gradient (non-zero dL/dencoding row: not behind the early stop T < 1e-4 of
+ * VolumeRenderGradient_No_Compacted, nerf_model.cu:889, and not underflown in fp16) out of rays_per_batch * 32: the work of
+ * the gradient scatter is proportional to it */
+int mon_object_live_samples(mon_object* obj, uint32_t* n_live, uint32_t* n_points);
 /* number of CUDA kernels this library launched on behalf of the object so far */
 int mon_object_launch_count(mon_object* obj, uint64_t* n);
 

@@ -46,13 +46,18 @@ class RefLib:
         L.ref_is_genuine.restype = C.c_int
         if L.ref_is_genuine():
             L.ref_render.argtypes = [vp] * 12
+            L.ref_render2.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_float)]
+            L.ref_generate_toc.argtypes = [C.c_float, C.c_float, C.c_float, vp]
             L.ref_marching_cubes.argtypes = [vp, vp, C.c_uint32, C.c_float, vp, vp, C.c_uint32, C.POINTER(C.c_uint32), vp, C.c_uint32, C.POINTER(C.c_uint32)]
+        L.ref_use_device.argtypes = [C.c_int]
         self.L = L
 
 
 class RefModel:
-    def __init__(self, n_hidden: int = 1, seed: int = 1337, lib: RefLib | None = None):
+    def __init__(self, n_hidden: int = 1, seed: int = 1337, lib: RefLib | None = None, device: int | None = None):
         self.lib = (lib or RefLib()).L
+        if device is not None and self.lib.ref_use_device(device) != 0:   # this host thread drives GPU `device` from here on
+            raise RuntimeError(f"cudaSetDevice({device}) failed")
         self.h = self.lib.ref_create((BASE_JSON % n_hidden).encode(), seed)
         if not self.h:
             raise RuntimeError("ref_create failed (see stderr)")
@@ -149,6 +154,31 @@ class RefModel:
         self._ck(self.lib.ref_render(self.h, b.ctypes.data, twc.ctypes.data, dt.ctypes.data, o["rgb"].ctypes.data, o["depth"].ctypes.data, o["mask"].ctypes.data,
                                      o["rays"].ctypes.data, o["in_box"].ctypes.data, o["points"].ctypes.data, o["dist"].ctypes.data, o["out4"].ctypes.data))
         return o
+
+    def render2(self, box, T, object_centric: bool = False, rand_dt=None, want_rays: bool = False):
+        """NeRF_Model::Render (T = camera->world) or one view of RenderVideo (object_centric: T = camera->object, e.g. generate_toc),
+        device work + the three D2H copies only; rand_dt None -> cuRAND on the device like the reference.
+        Returns dict(rgb, depth, mask, device_ms[, rays, in_box])."""
+        b = np.ascontiguousarray(np.array([int(v) for v in box], dtype=np.uint32))
+        n = int(b[3]) * int(b[4])
+        t16 = np.ascontiguousarray(np.asarray(T, np.float32).reshape(4, 4).T).reshape(16)
+        dt = None if rand_dt is None else np.ascontiguousarray(rand_dt, np.float32)
+        assert dt is None or dt.size == n * 64
+        o = dict(rgb=np.zeros((n, 3), np.float32), depth=np.zeros(n, np.float32), mask=np.zeros(n, np.float32))
+        if want_rays:
+            o["rays"], o["in_box"] = np.zeros((n, 9), np.float32), np.zeros(n, np.int32)
+        ms = C.c_float(0)
+        self._ck(self.lib.ref_render2(self.h, b.ctypes.data, t16.ctypes.data, int(object_centric), None if dt is None else dt.ctypes.data,
+                                      o["rgb"].ctypes.data, o["depth"].ctypes.data, o["mask"].ctypes.data,
+                                      o["rays"].ctypes.data if want_rays else None, o["in_box"].ctypes.data if want_rays else None, C.byref(ms)))
+        o["device_ms"] = ms.value
+        return o
+
+    def generate_toc(self, theta: float, phi: float, radius: float) -> np.ndarray:
+        """NeRF_Model::GenerateToc (the reference's own host code): 4x4 camera -> object pose, row-major numpy."""
+        t = np.zeros(16, np.float32)
+        self.lib.ref_generate_toc(theta, phi, radius, t.ctypes.data)
+        return t.reshape(4, 4).T.copy()
 
     def marching_cubes(self, density, thresh: float = 2.0):
         """The reference's MarchingCubes + compute_mesh_1ring on a [res,res,res] lattice (z, y, x order = x fastest) over the scene's

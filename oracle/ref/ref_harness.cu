@@ -550,6 +550,9 @@ int ref_last(void* h, int which, float* out) {
     })
 }
 
+// every later call of this host thread drives GPU `dev` (NeRF::mGPUid / cudaSetDevice in the reference's per-object threads, nerf.cu:123,192)
+int ref_use_device(int dev) { return cudaSetDevice(dev) == cudaSuccess ? 0 : -1; }
+
 // 1: the RO-MAP kernels in this library are the reference's own (nerf_model.cu compiled in place), 0: the restatement
 int ref_is_genuine(void) {
 #ifdef ROMAP_GENUINE
@@ -594,6 +597,63 @@ int ref_render(void* h, const void* box_v, const float* Twc16, const float* rand
     })
 }
 
+
+// NeRF_Model::Render (object_centric == 0, nerf_model.cu:1702-1830) or one view of NeRF_Model::RenderVideo (object_centric == 1:
+// GenerateRenderVideoRays with a camera -> object pose, :495-534,1915-1968), device work + the three D2H copies, without the
+// stage-level dumps of ref_render: what bench.py --impl reference times as "rendered rays/s".  rand_dt == NULL: cuRAND on the
+// device like the reference (:1781,1929).  device_ms: CUDA events around the device work.
+int ref_render2(void* h, const void* box_v, const float* T16, int object_centric, const float* rand_dt, float* rgb, float* depth, float* mask,
+                float* rays_out, int* inbox_out, float* device_ms) {
+    Ref* r = static_cast<Ref*>(h);
+    GUARD(r, {
+        const nerf::FrameIdAndBbox box = *static_cast<const nerf::FrameIdAndBbox*>(box_v);
+        const uint32_t S2 = 64, n_rays = box.h * box.w;
+        const uint32_t per = 128 / S2, n128 = (n_rays + per - 1) / per * per, batch = n128 * S2;
+        cudaStream_t st = r->stream;
+        if (!r->gen) {
+            if (curandCreateGenerator(&r->gen, CURAND_RNG_PSEUDO_XORWOW) != CURAND_STATUS_SUCCESS) throw std::runtime_error("curandCreateGenerator");
+            curandSetStream(r->gen, st);
+        }
+        cudaEvent_t e0, e1;
+        CUDA_CHECK_THROW(cudaEventCreate(&e0)); CUDA_CHECK_THROW(cudaEventCreate(&e1));
+        // the reference allocates its render workspace per call (allocate_workspace_and_distribute, :1751-1779)
+        GPUMemory<nerf::Ray> rays(n_rays);
+        GPUMemory<int> inbox(n_rays);
+        GPUMemory<float> pts((size_t)3 * batch), dist((size_t)S2 * n_rays), out4((size_t)4 * batch), d_rgb(3 * n_rays), d_depth(n_rays), d_mask(n_rays), rdt((size_t)S2 * n_rays);
+        Eigen::Matrix4f T;
+        for (int i = 0; i < 16; ++i) T.data()[i] = T16[i];
+        CUDA_CHECK_THROW(cudaEventRecord(e0, st));
+        if (object_centric) linear_kernel(nerf::GenerateRenderVideoRays, 0, st, n_rays, box, genuine_box(r), T, rays.data(), inbox.data(), r->K.data());
+        else linear_kernel(nerf::GenerateRenderRays, 0, st, n_rays, box, genuine_box(r), T, genuine_Tow(r), rays.data(), inbox.data(), r->K.data());
+        if (rand_dt) CUDA_CHECK_THROW(cudaMemcpyAsync(rdt.data(), rand_dt, (size_t)S2 * n_rays * 4, cudaMemcpyHostToDevice, st));
+        else curandGenerateUniform(r->gen, rdt.data(), (size_t)S2 * n_rays);
+        linear_kernel(nerf::GenerateRenderInputPoints, 0, st, n_rays, S2, genuine_box(r), rays.data(), inbox.data(), pts.data(), dist.data(), rdt.data());
+        CUDA_CHECK_THROW(cudaStreamSynchronize(st));      // :1793 / :1941
+        GPUMatrixDynamic<float> in(pts.data(), 3, batch, CM), o4(out4.data(), 4, batch, CM);
+        r->network->inference(st, in, o4);
+        linear_kernel(nerf::VolumeRender_Render, 0, st, n_rays, S2, 4u, genuine_box(r), nerf::ENerfActivation::Logistic, nerf::ENerfActivation::Exponential, 1.0f,
+                      out4.data(), pts.data(), dist.data(), rays.data(), inbox.data(), d_rgb.data(), d_depth.data(), d_mask.data());
+        CUDA_CHECK_THROW(cudaEventRecord(e1, st));
+        CUDA_CHECK_THROW(cudaStreamSynchronize(st));
+        d_rgb.copy_to_host(rgb, 3 * n_rays); d_depth.copy_to_host(depth, n_rays); d_mask.copy_to_host(mask, n_rays);
+        if (rays_out) CUDA_CHECK_THROW(cudaMemcpy(rays_out, rays.data(), (size_t)n_rays * 36, cudaMemcpyDeviceToHost));
+        if (inbox_out) inbox.copy_to_host(inbox_out, n_rays);
+        float ms = 0;
+        CUDA_CHECK_THROW(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        if (device_ms) *device_ms = ms;
+    })
+}
+
+// NeRF_Model::GenerateToc (nerf_model.cu:2186-2205), the reference's own host code: it reads no member, so it is called on
+// raw zeroed storage of the class (no constructor: that one creates CUDA streams).  Toc16: column-major 4x4.
+int ref_generate_toc(float theta, float phi, float radius, float* Toc16) {
+    static std::vector<unsigned char> storage(sizeof(nerf::NeRF_Model) + 64, 0);
+    nerf::NeRF_Model* m = reinterpret_cast<nerf::NeRF_Model*>((reinterpret_cast<uintptr_t>(storage.data()) + 63) & ~(uintptr_t)63);
+    const Eigen::Matrix4f T = m->GenerateToc(theta, phi, radius);
+    for (int i = 0; i < 16; ++i) Toc16[i] = T.data()[i];
+    return 0;
+}
 
 // MarchingCubes + compute_mesh_1ring of the reference (marching_cubes.cu:474-510,655-663) on a host density lattice [res^3], x fastest.
 // verts/normals: room for verts_cap vertices (xyz); n_verts receives the padded vertex count the reference allocates, n_idx 3 * triangles.

@@ -55,10 +55,12 @@ SIGNATURES = {
     "mon_config_grid_layout": (C.c_int, [_P(Config), _P(C.c_uint32), _f32p, _P(C.c_uint32)]),
     "mon_dataset_create": (C.c_int, [C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_uint32, C.c_int, _P(_vp)]),
     "mon_dataset_add_frame": (C.c_int, [_vp, C.c_uint32, _vp, C.c_int, _vp, _vp, _f32p]),
+    "mon_dataset_add_frame_device": (C.c_int, [_vp, C.c_uint32, _vp, C.c_int, _vp, _vp, _f32p]),
     "mon_dataset_sync": (C.c_int, [_vp]),
     "mon_dataset_update_poses": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _f32p]),
     "mon_dataset_frame_count": (C.c_int, [_vp, _P(C.c_uint32)]),
     "mon_dataset_clone_from_peer": (C.c_int, [_vp, _vp]),
+    "mon_dataset_copy_frame_from_peer": (C.c_int, [_vp, _vp, C.c_uint32]),
     "mon_dataset_destroy": (C.c_int, [_vp]),
     "mon_object_create": (C.c_int, [_vp, _P(Config), C.c_uint32, C.c_uint8, _f32p, _f32p, _f32p, _P(_vp)]),
     "mon_object_destroy": (C.c_int, [_vp]),
@@ -66,6 +68,8 @@ SIGNATURES = {
     "mon_object_add_bboxes": (C.c_int, [_vp, _P(Bbox2d), C.c_uint32]),
     "mon_object_train": (C.c_int, [_vp, C.c_uint32, _f32p]),
     "mon_object_train_async": (C.c_int, [_vp, C.c_uint32]),
+    "mon_object_prepare_train": (C.c_int, [_vp, C.c_uint32]),
+    "mon_object_live_samples": (C.c_int, [_vp, _P(C.c_uint32), _P(C.c_uint32)]),
     "mon_object_sync": (C.c_int, [_vp]),
     "mon_object_train_profiled": (C.c_int, [_vp, C.c_uint32, _f32p, C.c_uint32]),
     "mon_object_last_train_ms": (C.c_int, [_vp, _f32p]),

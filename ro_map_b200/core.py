@@ -102,6 +102,12 @@ class Dataset:
         check(self._lib.mon_dataset_add_frame(self._h, frame_id, _ptr(rgb), int(is_bgr), _ptr(inst),
                                                None if d is None else _ptr(d), pose.ctypes.data_as(C.POINTER(C.c_float))))
 
+    def add_frame_device(self, frame_id: int, d_rgb: int, d_instance: int, d_depth, pose_c2w, is_bgr: bool = False):
+        """Keyframe planes already in this GPU's memory (raw device addresses, e.g. torch.Tensor.data_ptr())."""
+        pose = _mat16(pose_c2w)
+        check(self._lib.mon_dataset_add_frame_device(self._h, frame_id, C.c_void_p(d_rgb), int(is_bgr), C.c_void_p(d_instance),
+                                                      None if d_depth is None else C.c_void_p(d_depth), pose.ctypes.data_as(C.POINTER(C.c_float))))
+
     def sync(self):
         check(self._lib.mon_dataset_sync(self._h))
 
@@ -117,6 +123,10 @@ class Dataset:
 
     def clone_from_peer(self, src: "Dataset"):
         check(self._lib.mon_dataset_clone_from_peer(self._h, src._h))
+
+    def copy_frame_from_peer(self, src: "Dataset", frame_id: int):
+        """One keyframe of `src`, device to device, asynchronously on this dataset's upload stream (online replication)."""
+        check(self._lib.mon_dataset_copy_frame_from_peer(self._h, src._h, frame_id))
 
     def close(self):
         if self._h:
@@ -167,10 +177,14 @@ class NerfObject:
     def train_async(self, iters: int):
         check(self._lib.mon_object_train_async(self._h, iters))
 
+    def prepare_train(self, iters: int):
+        """Capture the iteration graphs of a call of `iters` iterations now (AllocateBatchWorkspace's role)."""
+        check(self._lib.mon_object_prepare_train(self._h, iters))
+
     def sync(self):
         check(self._lib.mon_object_sync(self._h))
 
-    STAGES = ("batch", "points", "encode", "mlp_fused", "scatter", "optimizer")
+    STAGES = ("batch", "points", "encode", "mlp_fused", "scatter_adam", "optimizer_mlp")
 
     def train_profiled(self, iters: int) -> dict:
         """Mean device milliseconds per stage (CUDA events on the object's stream), see mon_c.h."""
@@ -189,6 +203,13 @@ class NerfObject:
         s = C.c_uint32(0)
         check(self._lib.mon_object_step_count(self._h, C.byref(s)))
         return s.value
+
+    @property
+    def live_fraction(self) -> float:
+        """Share of the last iteration's samples that carried gradient (work of the scatter + Adam kernel)."""
+        a, b = C.c_uint32(0), C.c_uint32(0)
+        check(self._lib.mon_object_live_samples(self._h, C.byref(a), C.byref(b)))
+        return a.value / max(1, b.value)
 
     @property
     def launch_count(self) -> int:

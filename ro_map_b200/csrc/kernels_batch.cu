@@ -176,6 +176,9 @@ k_generate_batch(MonBatch b, MonScene sc) {
         }
         b.ctrl->iter = iter + 1;
         b.state->iter = iter + 1;
+        // live-sample counter of THIS iteration (filled by the fused MLP kernel, read by the scatter + Adam kernel): two
+        // counters alternate, because this kernel runs one iteration ahead, beside the previous iteration's scatter
+        if (b.live_cnt) b.live_cnt[iter & 1u] = 0u;
     }
 }
 

@@ -209,7 +209,7 @@ k_encode_forward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, co
     if (ctrl && ctrl->skip) return;
     MON_TL(MON_TL_E + ((job_begin >> 3) & 3u), ctrl ? ctrl->iter - 1 : 0u);
 
-    // jobs [job_begin, job_end) of the 2 * n_levels (level, feature) jobs (the level-pipelined graph launches sub-ranges).
+    // jobs [job_begin, job_end) of the 2 * n_levels (level, feature) jobs (callers may launch sub-ranges).
     // The flattened [job][point] space is cut into one contiguous piece per CTA, equal in COST: a point of a dense level
     // is not as expensive as one of a hashed level, because the kernel is bound by shared-memory wavefronts and the
     // bank-conflict degree of a warp's 32 gathers differs (measured per-CTA times and a bank simulation of the batch's

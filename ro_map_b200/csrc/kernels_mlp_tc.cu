@@ -11,7 +11,7 @@
 //   MMA2  O[128x16]   = hid  . W_out^T           (K = 64)      epilogue: sigmoid/exp, warp-scan compositing,
 //                                                              loss, dL/dout fp16    --> dout smem (core layout)
 //   MMA3  D[128x64]   = dout . W_out             (K = 16)      epilogue: ReLU mask, fp16 --> dhid smem SW128
-//   MMA4  E[128x32]   = dhid . W_in              (K = 64)      epilogue: fp16 --> d_enc global
+//   MMA4  E[128x32]   = dhid . W_in              (K = 64)      epilogue: fp16 --> live rows, compacted, level-major (global)
 //   MMA5  G1[128x16] += [hid|dhid]^T . dout      (K = 128 points; rows 0-63   = dW_out^T)
 //   MMA6  G2[128x32] += [hid|dhid]^T . enc       (K = 128 points; rows 64-127 = dW_in)
 //
@@ -326,7 +326,11 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
     MON_TL(MON_TL_M, iter);
     // hand the iteration's control block to the kernels behind this one (scatter, optimizer): the batch kernel of
     // the next iteration is allowed to overwrite the live block while they run
-    if (blockIdx.x == 0 && threadIdx.x == 0) *b.late = *b.ctrl;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        MonCtrl cc = *b.ctrl;
+        cc.loss_mean = b.late->loss_mean;   // the logged loss survives a skipped iteration (the optimizer rewrites it otherwise)
+        *b.late = cc;
+    }
     if (skip) {
         tc_teardown(c, TC_TMEM_COLS(NH));
         return;
@@ -362,6 +366,10 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
             const uint32_t next = tile + gridDim.x;
             if (next < n_tiles) tin = tc_load_tile_inputs(b, next * 4 + c.warp, c.lane, iter);
         }
+        // this sample's unit-cube position, copied beside its gradient row if the sample turns out to carry gradient;
+        // requested here so that the load is long complete when the last epilogue of the tile needs it
+        float pu[3] = {0.0f, 0.0f, 0.0f};
+        if (ray_ok) { pu[0] = __ldg(b.pts + (size_t)pt * 3); pu[1] = __ldg(b.pts + (size_t)pt * 3 + 1); pu[2] = __ldg(b.pts + (size_t)pt * 3 + 2); }
         TC_STAMP(sb + 3);
         TC_WAIT(c);
         TC_STAMP(sb + 4);
@@ -456,22 +464,39 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
         TC_STAMP(sb + 12);
         TC_WAIT(c);
         TC_STAMP(sb + 13);
-        {   // dL/dencoding: fp16, one 64-byte row per thread
+        {   // dL/dencoding: fp16.  Most samples sit behind the early stop (or underflow in fp16) and have an all-zero row:
+            // only the LIVE rows are handed to the scatter + Adam kernel, compacted — slot k gets the position and, level by
+            // level (stride N words, so that a CTA of that kernel streams one level's words of consecutive slots), the two
+            // fp16 gradients of the level.  One atomicAdd per warp reserves the slots of its live lanes.
             float v[32];
             tmem_ld32(c.tmem + ((c.warp * 32u) << 16) + TC_COL_E, v);
             tmem_wait_ld();
-            if (ray_ok) {
+            uint32_t packed[16];
+            uint32_t any = 0u;
+#pragma unroll
+            for (uint32_t q = 0; q < 16; ++q) {
+                const __half2 h = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+                packed[q] = *reinterpret_cast<const uint32_t*>(&h);
+                any |= packed[q];
+            }
+            const bool live = ray_ok && (any & 0x7fff7fffu) != 0u;
+            const uint32_t lm = __ballot_sync(0xffffffffu, live);
+            if (lm) {
+                uint32_t base = 0;
+                if (c.lane == 0) base = atomicAdd(b.live_cnt + (iter & 1u), (uint32_t)__popc(lm));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (live) {
+                    const uint32_t slot = base + __popc(lm & ((1u << c.lane) - 1u));
+                    const size_t n_total = (size_t)b.R * 32;
+#pragma unroll
+                    for (uint32_t q = 0; q < 16; ++q) b.genc[(size_t)q * n_total + slot] = packed[q];
+                    b.pts_c[(size_t)slot * 3 + 0] = pu[0]; b.pts_c[(size_t)slot * 3 + 1] = pu[1]; b.pts_c[(size_t)slot * 3 + 2] = pu[2];
+                }
+            }
+            if (b.d_enc && ray_ok) {   // parity hook: the uncompacted rows, point-major
                 uint4* dst = reinterpret_cast<uint4*>(b.d_enc + (size_t)pt * MON_IN);
 #pragma unroll
-                for (uint32_t ch = 0; ch < 4; ++ch) {
-                    uint32_t packed[4];
-#pragma unroll
-                    for (uint32_t q = 0; q < 4; ++q) {
-                        const __half2 h = __floats2half2_rn(v[ch * 8 + 2 * q], v[ch * 8 + 2 * q + 1]);
-                        packed[q] = *reinterpret_cast<const uint32_t*>(&h);
-                    }
-                    dst[ch] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                }
+                for (uint32_t ch = 0; ch < 4; ++ch) dst[ch] = make_uint4(packed[4 * ch], packed[4 * ch + 1], packed[4 * ch + 2], packed[4 * ch + 3]);
             }
         }
         TC_STAMP(sb + 14);

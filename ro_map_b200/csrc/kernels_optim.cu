@@ -18,6 +18,7 @@
 // master / moment / step words.
 #include "mon_device.cuh"
 #include "mon_kernels.h"
+#include "optim_math.cuh"
 #include "mon_timeline.cuh"
 MON_TL_DEFINE(optim)
 
@@ -67,31 +68,6 @@ __global__ void k_cast_params(uint32_t n, const float* __restrict__ pf, __half* 
 #define OPT_THREADS 256
 #define OPT_PER_THREAD 4
 
-// Adam's bias correction sqrt(1 - beta2^s) / (1 - beta1^s) depends on the parameter's own step count s only
-// (adam.h:103-104): the sweep reads it from a per-object table indexed by s that mon_core.cu fills on the HOST with the
-// reference's expression, sqrtf(1 - powf(beta2, s)) / (1 - powf(beta1, s)).  That replaces ~45 instructions per touched
-// parameter by one cached load, and it makes the value identical to the CPU restatement's: 1 - beta^s cancels, so one
-// ulp of difference between two pow implementations is 3e-6 of the learning rate.  Steps beyond the table (32768
-// updates of one parameter) evaluate beta^s as exp2f(s * log2 beta) on the device.
-__device__ __forceinline__ float adam_debias(const MonOpt& o, uint32_t cs) {
-    const float b1s = exp2f((float)cs * o.log2_beta1), b2s = exp2f((float)cs * o.log2_beta2);
-    return __fdiv_rn(__fsqrt_rn(1.0f - b2s), 1.0f - b1s);
-}
-
-// one Adam update (adam.h:65-118); returns the new weight
-__device__ __forceinline__ float adam_one(const MonOpt& o, float lr_base, float gradient, bool is_mlp, float w, float& m, float& v, uint32_t& cs) {
-    if (is_mlp) gradient = __fmaf_rn(o.l2_reg, w, gradient);
-    const float gsq = __fmul_rn(gradient, gradient);
-    m = __fmaf_rn(o.beta1, m, __fmul_rn(1.0f - o.beta1, gradient));
-    v = __fmaf_rn(o.beta2, v, __fmul_rn(1.0f - o.beta2, gsq));
-    cs += 1;
-    const float lr = __fmul_rn(lr_base, cs < o.n_debias_lut ? __ldg(o.debias_lut + cs) : adam_debias(o, cs));
-    // IEEE sqrt and division like the reference's sqrtf and '/' (adam.h:107): with identical gradients the weights stay
-    // bit-identical to the CPU restatement (the SFU approximations would save ~12 instructions and cost that property)
-    const float eff = fminf(fmaxf(__fdiv_rn(lr, __fadd_rn(__fsqrt_rn(v), o.eps)), 0.0f), FLT_MAX);
-    return __fmaf_rn(-eff, m, w);
-}
-
 __device__ __forceinline__ uint32_t level_of_entry(const MonGrid& g, uint32_t e) {
     if (g.log2_cap && g.first_full < g.n_levels && e >= g.offset[g.first_full]) return g.first_full + ((e - g.offset[g.first_full]) >> g.log2_cap);
     uint32_t l = 0;
@@ -126,7 +102,8 @@ k_optimizer_sweep(MonOpt o, MonCtrl* __restrict__ ctrl, float* __restrict__ pf, 
     // CTA layout: the first n_mlp_ctas (n_mlp/32, or 0 in a grid-only launch) CTAs own the MLP weights (one WARP per 4
     // parameters: the lanes split the per-CTA gradient partials of the fused MLP kernel), every other CTA owns 1024
     // consecutive parameters of [grid_i4_begin, grid_i4_end) (one THREAD per 4 parameters).  n_params and n_mlp are
-    // multiples of 32 resp. 4; the level-pipelined graph launches one sweep per level group + one for the MLP weights.
+    // multiples of 32 resp. 4.  The production iteration launches the MLP part only (MON_OPT_MLP): the grid is updated inside
+    // the fused scatter + Adam kernel (kernels_scatter_adam.cu).
     const bool is_mlp = blockIdx.x < n_mlp_ctas;
     uint32_t i4;
     float g[4];
@@ -168,58 +145,18 @@ k_optimizer_sweep(MonOpt o, MonCtrl* __restrict__ ctrl, float* __restrict__ pf, 
         g[0] = __low2float(a); g[1] = __high2float(a); g[2] = __low2float(b); g[3] = __high2float(b);
         if ((raw.x | raw.y) & 0x7fff7fffu) *gw = make_uint2(0u, 0u);   // consumed: the next scatter starts from zero
     }
-    bool touched[4];
-    bool any = is_mlp;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        g[k] = o.loss_scale_pow2 ? __fmul_rn(g[k], o.inv_loss_scale) : __fdiv_rn(g[k], o.loss_scale);
-        touched[k] = is_mlp || g[k] != 0.0f;       // grid: zero gradient => Adam skips the parameter (adam.h:75-79)
-        any |= touched[k];
+    __half* planar_f0 = nullptr;
+    uint32_t planar_stride = 0;
+    if (!is_mlp) {
+        // planar copy read by the hash-encode kernel: level l holds [feature 0 | feature 1]; entries e, e+1 are
+        // adjacent in both feature arrays (level sizes are multiples of 8, so a pair never straddles a level)
+        const uint32_t e = (i4 - o.n_mlp) >> 1;
+        const uint32_t l = level_of_entry(grid, e);
+        planar_f0 = planar + (size_t)grid.offset[l] * 2 + (e - grid.offset[l]);
+        planar_stride = grid.size[l];
     }
-
-    // ---- fp16 weights of the 4 parameters (needed by the EMA in any case)
-    __half wh[4] = {__ushort_as_half((unsigned short)(wraw.x & 0xffffu)), __ushort_as_half((unsigned short)(wraw.x >> 16)),
-                    __ushort_as_half((unsigned short)(wraw.y & 0xffffu)), __ushort_as_half((unsigned short)(wraw.y >> 16))};
-    if (any) {
-        // (fetching this state speculatively beside the gradient was tried: no gain, the sweep is not bound by that chain)
-        float4 w4 = *reinterpret_cast<const float4*>(pf + i4);
-        float4 m4 = *reinterpret_cast<const float4*>(m + i4);
-        float4 v4 = *reinterpret_cast<const float4*>(v + i4);
-        uint4 s4 = *reinterpret_cast<const uint4*>(ps + i4);
-        float* wp = &w4.x; float* mp = &m4.x; float* vp = &v4.x; uint32_t* sp = &s4.x;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (touched[k]) {
-                wp[k] = adam_one(o, lr_base, g[k], is_mlp, wp[k], mp[k], vp[k], sp[k]);
-                wh[k] = __float2half_rn(wp[k]);
-            }
-        }
-        *reinterpret_cast<float4*>(pf + i4) = w4;
-        *reinterpret_cast<float4*>(m + i4) = m4;
-        *reinterpret_cast<float4*>(v + i4) = v4;
-        *reinterpret_cast<uint4*>(ps + i4) = s4;
-        const __half2 a = __halves2half2(wh[0], wh[1]), b = __halves2half2(wh[2], wh[3]);
-        *reinterpret_cast<uint2*>(ph + i4) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
-        if (!is_mlp) {
-            // planar copy read by the hash-encode kernel: level l holds [feature 0 | feature 1]; entries e, e+1 are
-            // adjacent in both feature arrays (level sizes are multiples of 8, so a pair never straddles a level)
-            const uint32_t e = (i4 - o.n_mlp) >> 1;
-            const uint32_t l = level_of_entry(grid, e);
-            __half* f0 = planar + (size_t)grid.offset[l] * 2 + (e - grid.offset[l]);
-            *reinterpret_cast<__half2*>(f0) = __halves2half2(wh[0], wh[2]);
-            *reinterpret_cast<__half2*>(f0 + grid.size[l]) = __halves2half2(wh[1], wh[3]);
-        }
-    }
-
-    // ---- EMA over all params with the global step (ema.h:62-76)
-    const __half2 e01 = *reinterpret_cast<const __half2*>(&eraw.x), e23 = *reinterpret_cast<const __half2*>(&eraw.y);
-    const float ev[4] = {__low2float(e01), __high2float(e01), __low2float(e23), __high2float(e23)};
-    float nf[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-        nf[k] = __fmul_rn(__fmaf_rn(__half2float(wh[k]), 1.0f - o.ema_decay, __fmul_rn(__fmul_rn(ev[k], o.ema_decay), old_db)), new_db);
-    const __half2 n01 = __floats2half2_rn(nf[0], nf[1]), n23 = __floats2half2_rn(nf[2], nf[3]);
-    *reinterpret_cast<uint2*>(ema + i4) = make_uint2(*reinterpret_cast<const uint32_t*>(&n01), *reinterpret_cast<const uint32_t*>(&n23));
+    const OptimPtrs ptrs = {pf, ph, m, v, ps, ema};
+    optim_quad(o, lr_base, old_db, new_db, is_mlp, i4, g, wraw, eraw, ptrs, planar_f0, planar_stride);
 }
 
 // used only by tests: snapshot of the loss-scaled gradient before the sweep consumes it

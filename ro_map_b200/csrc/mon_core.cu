@@ -9,10 +9,11 @@
 //   Render                        :1702-1830                        -> mon_object_render
 //   GetDensityOnGrid              :2007-2043                        -> mon_object_density_grid
 //
-// One training iteration is five kernels (batch, encode, fused MLP+render+loss+backward,
-// gradient scatter, optimizer sweep) + a loss reduction, captured once as a CUDA graph and
-// replayed; the reference issues ~25 launches, 3 cuRAND host calls and 3 blocking stream
-// synchronisations per iteration.  There is no CPU fallback anywhere in this
+// One training iteration is six kernels (batch, sample points, hash encode, fused MLP + render + loss +
+// backward, fused gradient scatter + Adam/EMA of the grid, optimizer of the MLP weights + logged loss),
+// captured as CUDA graphs of exactly the requested number of iterations and replayed; the reference
+// issues ~25 launches, 3 cuRAND host calls and 3 blocking stream synchronisations per iteration
+// (SURVEY.md §3.1).  There is no CPU fallback anywhere in this
 // file: without a CUDA device every compute entry point returns MON_ERR_NO_DEVICE / MON_ERR_CUDA.
 #include <algorithm>
 #include <cmath>
@@ -32,7 +33,8 @@
 
 #define MON_DEBIAS_LUT 32768  // steps covered by the Adam bias-correction table (offline jobs run 5000 iterations)
 #define MON_FRAMES_PER_SLAB 32
-#define MON_GRAPH_CHUNK 50   // iterations captured per replayed graph (plus a 1-iteration graph for remainders)
+#define MON_GRAPH_CHUNK 64   // longest captured graph; a call of n iterations replays n / 64 of these + one graph of exactly n % 64
+#define MON_GRAPH_CACHE 6    // distinct remainder lengths kept instantiated per object (least recently used is dropped)
 
 static thread_local std::string g_err;
 
@@ -112,7 +114,9 @@ bool host_pinned(const void* p) {
 bool make_grid(const mon_config& c, MonGrid& g, std::string& why) {
     if (c.n_levels == 0 || c.n_levels > MON_MAX_LEVELS) { why = "n_levels must be in 1..16"; return false; }
     if (c.n_features_per_level != 2) { why = "only n_features_per_level == 2 is supported"; return false; }
-    if (c.log2_hashmap_size < 3 || c.log2_hashmap_size > 28) { why = "log2_hashmap_size out of range"; return false; }
+    // a (level, feature) slice of the table is staged into 128 KB of shared memory by the encode kernel, and a slice of
+    // 32768 f16x2 accumulators by the scatter + Adam kernel: 2^16 entries per level is the largest table they hold
+    if (c.log2_hashmap_size < 3 || c.log2_hashmap_size > 16) { why = "log2_hashmap_size must be in 3..16 (table slices are shared-memory resident)"; return false; }
     memset(&g, 0, sizeof(g));
     g.n_levels = c.n_levels;
     const float log2_pls = std::log2(c.per_level_scale);
@@ -182,7 +186,7 @@ struct mon_dataset {
     // keyframe storage comes in slabs of MON_FRAMES_PER_SLAB frames (one cudaMalloc per slab: a per-frame cudaMalloc
     // serialises with the training graphs in flight and made the online ingest take tens of milliseconds per keyframe)
     std::vector<uint8_t*> slabs;
-    std::mutex mu;
+    mutable std::mutex mu;
 };
 
 struct mon_object {
@@ -200,8 +204,7 @@ struct mon_object {
     uint32_t* ps = nullptr;
     // control
     MonCtrl* ctrl_state = nullptr; // persistent counters (iter, step, n_boxes), advanced by the batch kernels
-    MonCtrl* ctrl = nullptr;       // control block of the iteration in batch buffer 0 (ctrl_alt: buffer 1)
-    MonCtrl* ctrl_alt = nullptr;
+    MonCtrl* ctrl = nullptr;       // control block of the current iteration, written by its batch kernel
     MonCtrl* ctrl_late = nullptr;  // per-iteration copy for scatter / optimizer; carries the logged loss
     MonCtrl* h_ctrl = nullptr;  // pinned
     mon_bbox2d* d_boxes = nullptr;
@@ -213,7 +216,7 @@ struct mon_object {
     float *target = nullptr, *target_depth = nullptr, *bg = nullptr;
     float *rgb_rays = nullptr, *depth_rays = nullptr, *mask_rays = nullptr, *loss = nullptr;
     float* pts = nullptr;             // [N][3] unit-cube sample positions (the reference's PointsInput)
-    __half *enc = nullptr, *d_enc = nullptr;   // enc: level-major pairs [16][N][2]; d_enc: point-major [N][32]
+    __half *enc = nullptr, *d_enc = nullptr;   // enc: level-major pairs [16][N][2]; d_enc: point-major [N][32], parity hook only (lazily allocated)
     __half* ph_planar = nullptr;      // fp16 grid weights, per level [feature 0 | feature 1], kept current by the optimizer
     float* partials = nullptr;
     float* debias_lut = nullptr;      // Adam bias correction by step count, MON_DEBIAS_LUT entries
@@ -232,17 +235,15 @@ struct mon_object {
     void* scr[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t scr_cap[4] = {0, 0, 0, 0};
     // execution
-    cudaStream_t stream = nullptr, aux = nullptr;   // aux: next iteration's batch + sample points, forked inside the graphs
-    cudaEvent_t ev_fork_m = nullptr, ev_fork_s = nullptr, ev_join = nullptr;
-    // level-pipelined graph (capture_graph_pipelined): one branch stream per level group of the scatter / optimizer
-    cudaStream_t grp[2] = {nullptr, nullptr};   // scatter chain, optimizer chain
-    cudaEvent_t ev_s[MON_PIPE_GROUPS] = {nullptr, nullptr, nullptr, nullptr}, ev_o[MON_PIPE_GROUPS] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev_pts = nullptr, ev_aux = nullptr, ev_ready = nullptr, ev_b = nullptr;
-    float* pts_alt = nullptr;         // second sample-position buffer: P(i+1) runs while S(i) still reads the first
-    // second batch buffer (rays, targets, control block): B(i+2) runs right after M(i), a whole iteration ahead
-    MonRay* rays_alt = nullptr; uint8_t* ray_inst_alt = nullptr;
-    float *target_alt = nullptr, *target_depth_alt = nullptr, *bg_alt = nullptr;
-    cudaGraphExec_t graph1 = nullptr, graphN = nullptr;
+    cudaStream_t stream = nullptr, aux = nullptr, aux2 = nullptr;   // aux: next iteration's batch + sample points; aux2: MLP-weight optimizer; both forked inside the graphs
+    cudaEvent_t ev_fork_m = nullptr, ev_join = nullptr, ev_join2 = nullptr;
+    // compacted live samples of the iteration (fused MLP kernel -> scatter + Adam kernel)
+    float* pts_c = nullptr; uint32_t* genc = nullptr; uint32_t* live_cnt = nullptr;
+    bool so_fuse = true;              // Adam + EMA of the grid inside the scatter kernel (MON_SO_FUSE=0: separate sweep, A/B)
+    // instantiated iteration graphs by length
+    struct GraphSlot { uint32_t iters; cudaGraphExec_t exec; uint64_t stamp; };
+    std::vector<GraphSlot> graphs;
+    uint64_t graph_clock = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timing_pending = false;
     float last_ms = 0.0f;
@@ -459,6 +460,28 @@ int mon_dataset_add_frame(mon_dataset* ds, uint32_t frame_id, const uint8_t* rgb
     return MON_OK;
 }
 
+int mon_dataset_add_frame_device(mon_dataset* ds, uint32_t frame_id, const uint8_t* d_rgb, int is_bgr, const uint8_t* d_instance,
+                                 const float* d_depth, const float pose[16]) {
+    if (!ds || !d_rgb || !d_instance || !pose) return fail(MON_ERR_ARG, "NULL argument");
+    if (frame_id >= ds->max_frames) return fail(MON_ERR_ARG, "frame_id %u >= max_frames %u", frame_id, ds->max_frames);
+    if (ds->use_depth && !d_depth) return fail(MON_ERR_ARG, "dataset was created with use_depth but depth is NULL");
+    std::lock_guard<std::mutex> lock(ds->mu);
+    CK(cudaSetDevice(ds->gpu));
+    const size_t px = (size_t)ds->H * ds->W;
+    int rc = ensure_frame_storage(ds, frame_id);
+    if (rc != MON_OK) return rc;
+    MonFrame& f = ds->h_frames[frame_id];
+    memcpy(f.pose, pose, sizeof(float) * 16);
+    f.bgr = is_bgr ? 1u : 0u;
+    CK(cudaMemcpyAsync(const_cast<uint8_t*>(f.rgb), d_rgb, px * 3, cudaMemcpyDeviceToDevice, ds->stream));
+    CK(cudaMemcpyAsync(const_cast<uint8_t*>(f.instance), d_instance, px, cudaMemcpyDeviceToDevice, ds->stream));
+    if (ds->use_depth) CK(cudaMemcpyAsync(const_cast<float*>(f.depth), d_depth, px * 4, cudaMemcpyDeviceToDevice, ds->stream));
+    CK(cudaMemcpyAsync(ds->d_frames + frame_id, &f, sizeof(MonFrame), cudaMemcpyHostToDevice, ds->stream));
+    CK(cudaEventRecord(ds->ev_uploaded, ds->stream));
+    ds->n_frames = std::max(ds->n_frames, frame_id + 1);
+    return MON_OK;
+}
+
 int mon_dataset_sync(mon_dataset* ds) {
     if (!ds) return fail(MON_ERR_ARG, "ds is NULL");
     CK(cudaSetDevice(ds->gpu));
@@ -486,19 +509,19 @@ int mon_dataset_frame_count(const mon_dataset* ds, uint32_t* n) {
     return MON_OK;
 }
 
-int mon_dataset_clone_from_peer(mon_dataset* dst, const mon_dataset* src) {
-    if (!dst || !src) return fail(MON_ERR_ARG, "NULL argument");
-    if (dst->H != src->H || dst->W != src->W || dst->max_frames < src->n_frames || dst->use_depth != src->use_depth)
-        return fail(MON_ERR_ARG, "datasets are not shape-compatible");
-    std::lock_guard<std::mutex> lock(dst->mu);
+// frames [first, end) of src -> dst, device to device (NVLink peer copies between GPUs), on dst's upload stream, ordered
+// behind src's own uploads.  Both dataset mutexes are held by the caller.
+static int copy_frames_from_peer(mon_dataset* dst, const mon_dataset* src, uint32_t first, uint32_t end) {
     CK(cudaSetDevice(dst->gpu));
     if (dst->gpu != src->gpu) {
         int can = 0;
         CK(cudaDeviceCanAccessPeer(&can, dst->gpu, src->gpu));
         if (can) { cudaError_t e = cudaDeviceEnablePeerAccess(src->gpu, 0); if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e); cudaGetLastError(); }
     }
+    // the source frames may still be in flight on src's upload stream (asynchronous DMA from pinned or staged buffers)
+    CK(cudaStreamWaitEvent(dst->stream, src->ev_uploaded, 0));
     const size_t px = (size_t)dst->H * dst->W;
-    for (uint32_t i = 0; i < src->n_frames; ++i) {
+    for (uint32_t i = first; i < end; ++i) {
         const MonFrame& s = src->h_frames[i];
         if (!s.rgb) continue;
         int rc = ensure_frame_storage(dst, i);
@@ -510,10 +533,39 @@ int mon_dataset_clone_from_peer(mon_dataset* dst, const mon_dataset* src) {
         if (dst->use_depth) CK(cudaMemcpyPeerAsync(const_cast<float*>(f.depth), dst->gpu, s.depth, src->gpu, px * 4, dst->stream));
         memcpy(f.pose, s.pose, sizeof(float) * 16);
         CK(cudaMemcpyAsync(dst->d_frames + i, &f, sizeof(MonFrame), cudaMemcpyHostToDevice, dst->stream));
+        dst->n_frames = std::max(dst->n_frames, i + 1);
     }
-    CK(cudaStreamSynchronize(dst->stream));
-    dst->n_frames = std::max(dst->n_frames, src->n_frames);
+    CK(cudaEventRecord(dst->ev_uploaded, dst->stream));
     return MON_OK;
+}
+
+static int peer_compatible(const mon_dataset* dst, const mon_dataset* src) {
+    if (!dst || !src) return fail(MON_ERR_ARG, "NULL argument");
+    if (dst == src) return fail(MON_ERR_ARG, "source and destination are the same dataset");
+    if (dst->H != src->H || dst->W != src->W || dst->use_depth != src->use_depth) return fail(MON_ERR_ARG, "datasets are not shape-compatible");
+    return MON_OK;
+}
+
+int mon_dataset_clone_from_peer(mon_dataset* dst, const mon_dataset* src) {
+    int rc = peer_compatible(dst, src);
+    if (rc != MON_OK) return rc;
+    std::unique_lock<std::mutex> l1(dst->mu, std::defer_lock), l2(src->mu, std::defer_lock);
+    std::lock(l1, l2);
+    if (dst->max_frames < src->n_frames) return fail(MON_ERR_ARG, "destination holds %u frames, source has %u", dst->max_frames, src->n_frames);
+    rc = copy_frames_from_peer(dst, src, 0, src->n_frames);
+    if (rc != MON_OK) return rc;
+    CK(cudaStreamSynchronize(dst->stream));
+    return MON_OK;
+}
+
+int mon_dataset_copy_frame_from_peer(mon_dataset* dst, const mon_dataset* src, uint32_t frame_id) {
+    int rc = peer_compatible(dst, src);
+    if (rc != MON_OK) return rc;
+    std::unique_lock<std::mutex> l1(dst->mu, std::defer_lock), l2(src->mu, std::defer_lock);
+    std::lock(l1, l2);
+    if (frame_id >= src->max_frames || !src->h_frames[frame_id].rgb) return fail(MON_ERR_ARG, "frame %u is not in the source dataset", frame_id);
+    if (frame_id >= dst->max_frames) return fail(MON_ERR_ARG, "frame_id %u >= max_frames %u", frame_id, dst->max_frames);
+    return copy_frames_from_peer(dst, src, frame_id, frame_id + 1);   // asynchronous: training streams wait on the upload event
 }
 
 int mon_dataset_destroy(mon_dataset* ds) {
@@ -534,49 +586,53 @@ int mon_dataset_destroy(mon_dataset* ds) {
 
 // ------------------------------------------------------------------------------- object
 static void drop_graphs(mon_object* o) {
-    if (o->graph1) { cudaGraphExecDestroy(o->graph1); o->graph1 = nullptr; }
-    if (o->graphN) { cudaGraphExecDestroy(o->graphN); o->graphN = nullptr; }
+    for (auto& g : o->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    o->graphs.clear();
 }
 
-static MonBatch make_batch(mon_object* o, bool injected, bool debug, int buf = 0) {
+static MonBatch make_batch(mon_object* o, bool injected, bool debug) {
     MonBatch b;
     memset(&b, 0, sizeof(b));
     b.R = o->R;
     b.boxes = o->d_boxes;
     b.frames = o->ds->d_frames;
     b.state = o->ctrl_state;
-    b.ctrl = buf ? o->ctrl_alt : o->ctrl;
+    b.ctrl = o->ctrl;
     b.late = o->ctrl_late;
     b.seed = o->seed;
     b.opt_lr = o->cfg.learning_rate; b.decay_base = o->cfg.decay_base; b.ema_decay = o->cfg.ema_decay;
     b.decay_start = o->cfg.decay_start; b.decay_interval = o->cfg.decay_interval ? o->cfg.decay_interval : 1;
     if (injected) { b.inj_xy = o->inj_xy; b.inj_col = o->inj_col; b.inj_dt = o->inj_dt; }
-    if (buf) { b.rays = o->rays_alt; b.ray_inst = o->ray_inst_alt; b.target = o->target_alt; b.target_depth = o->target_depth_alt; b.bg = o->bg_alt; }
-    else { b.rays = o->rays; b.ray_inst = o->ray_inst; b.target = o->target; b.target_depth = o->target_depth; b.bg = o->bg; }
+    b.rays = o->rays; b.ray_inst = o->ray_inst; b.target = o->target; b.target_depth = o->target_depth; b.bg = o->bg;
     b.rgb_rays = o->rgb_rays; b.depth_rays = o->depth_rays; b.mask_rays = o->mask_rays; b.loss = o->loss;
-    b.enc = o->enc; b.d_enc = o->d_enc;
-    if (debug) { b.dbg_out = o->dbg_out; b.dbg_dout = o->dbg_dout; }
+    b.enc = o->enc;
+    b.pts = o->pts; b.pts_c = o->pts_c; b.genc = o->genc; b.live_cnt = o->live_cnt;
+    if (debug) { b.dbg_out = o->dbg_out; b.dbg_dout = o->dbg_dout; b.d_enc = o->d_enc; }
     b.params = o->ph; b.grads = o->gh; b.mlp_partials = o->partials;
     return b;
 }
 
-// One training iteration = batch (B) -> sample points (P) -> hash encode (E) -> fused MLP (M) -> gradient scatter (S)
-// -> optimizer sweep (O).  B and P do not depend on the training state, so inside a captured graph the B/P of
-// iteration i+1 run on a forked branch concurrently with S/O of iteration i:
-//     main:  E(i)  M(i) ---------> S(i) ---------> O(i) --join--> E(i+1) ...
-//     aux :          \--> B(i+1)       \--> P(i+1) ----/
-// B(i+1) may start once M(i) is done (last reader of rays/targets; M also copied the control block for S/O),
-// P(i+1) once S(i) is done (last reader of the sample points).
+// One training iteration = batch (B) -> sample points (P) -> hash encode (E) -> fused MLP (M) -> gradient scatter fused
+// with Adam/EMA of the grid (S) || optimizer of the MLP weights + logged loss (O).  B and P do not depend on the training
+// state, so inside a captured graph the B/P of iteration i+1 run on a forked branch beside S/O of iteration i:
+//     main:  E(i)  M(i) ---------> S(i) -------------------join--> E(i+1) ...
+//     aux :          \--> B(i+1) -> P(i+1) ----------------/
+//     aux2:          \--> O(i) ----------------------------/
+// Everything after M(i) only needs M(i): the batch kernel rewrites rays/targets (last read by M, which also copied the
+// control block for S/O), the sample positions are last read by M too (it hands the positions of the live samples to S in
+// compacted form), and O reads M's weight-gradient partials and per-ray losses.
 static int launch_batch(mon_object* o, const MonBatch& b, cudaStream_t st) {
     mon_launch_generate_batch(b, o->scene, st);
     return MON_OK;
 }
-static int launch_points(mon_object* o, const MonBatch& b, cudaStream_t st) {
-    mon_launch_sample_points(o->N, MON_S, o->rays, nullptr, b.inj_dt, o->seed, o->ctrl, 2, 0, o->scene.bmin, o->scene.bmax, o->pts, st);
+static int launch_points(mon_object* o, const MonBatch& b, cudaStream_t st, bool pdl = true) {
+    MonLaunchOpt lo; lo.pdl = pdl;
+    mon_launch_sample_points(o->N, MON_S, o->rays, nullptr, b.inj_dt, o->seed, o->ctrl, 2, 0, o->scene.bmin, o->scene.bmax, o->pts, st, lo);
     return MON_OK;
 }
-static int launch_encode(mon_object* o, cudaStream_t st) {
-    cudaError_t e = mon_launch_encode_forward(o->grid, o->N, o->pts, o->ph_planar, o->enc, o->ctrl, (uint32_t)o->sm_count, st);
+static int launch_encode(mon_object* o, cudaStream_t st, bool pdl = true) {
+    MonLaunchOpt lo; lo.pdl = pdl;
+    cudaError_t e = mon_launch_encode_forward(o->grid, o->N, o->pts, o->ph_planar, o->enc, o->ctrl, (uint32_t)o->sm_count, st, 0, 0xffffffffu, lo);
     if (e != cudaSuccess) return fail(MON_ERR_CUDA, "hash encode launch: %s", cudaGetErrorString(e));
     return MON_OK;
 }
@@ -585,19 +641,18 @@ static int launch_mlp(mon_object* o, const MonBatch& b, cudaStream_t st) {
     if (e != cudaSuccess) return fail(MON_ERR_CUDA, "fused MLP launch: %s", cudaGetErrorString(e));
     return MON_OK;
 }
-static void launch_scatter(mon_object* o, cudaStream_t st) {
-#ifdef MON_TIMELINE
-    // timing experiments only (instrumented build): MON_DEBUG_SCATTER_LEVELS="b,e" scatters a sub-range of the levels
-    if (const char* env = getenv("MON_DEBUG_SCATTER_LEVELS")) {
-        unsigned b = 0, e = 0;
-        if (sscanf(env, "%u,%u", &b, &e) == 2) { mon_launch_encode_backward(o->grid, o->N, o->pts, o->ctrl_late, o->d_enc, o->gh + o->n_mlp, st, b, e); return; }
-    }
-#endif
-    mon_launch_encode_backward(o->grid, o->N, o->pts, o->ctrl_late, o->d_enc, o->gh + o->n_mlp, st);
+// gradient scatter (+ Adam / EMA of the grid when fused); grad_snap: parity hook
+static int launch_scatter(mon_object* o, cudaStream_t st, float* grad_snap) {
+    cudaError_t e = mon_launch_scatter_adam(o->grid, o->opt, o->N, o->live_cnt, o->pts_c, o->genc, o->ctrl_late, o->pf, o->ph, o->m, o->v, o->ps,
+                                            o->ema, o->ph_planar, o->gh + o->n_mlp, grad_snap, o->so_fuse, (uint32_t)o->sm_count, st);
+    if (e != cudaSuccess) return fail(MON_ERR_CUDA, "scatter + Adam launch: %s", cudaGetErrorString(e));
+    return MON_OK;
 }
-static void launch_optimizer(mon_object* o, cudaStream_t st) {
+// MLP weights (fixed-order reduction of the per-CTA partials, Adam, EMA) + logged loss; in the unfused A/B mode also the grid sweep
+static void launch_optimizer(mon_object* o, cudaStream_t st, bool pdl) {
+    MonLaunchOpt lo; lo.pdl = pdl;
     mon_launch_optimizer(o->opt, o->ctrl_late, o->pf, o->ph, o->gh, o->partials, o->m, o->v, o->ps, o->ema, o->loss, o->R, o->grid,
-                         o->ph_planar, st);
+                         o->ph_planar, st, o->so_fuse ? MON_OPT_MLP : MON_OPT_ALL, 0, 0xffffffffu, lo);
 }
 
 // serial version (injected / profiled iterations).  ev (optional, MON_N_STAGES+1 events): recorded before each
@@ -616,24 +671,21 @@ static int enqueue_iteration(mon_object* o, const MonBatch& b, bool snapshot_gra
     if ((rc = launch_mlp(o, b, st)) != MON_OK) return rc;
     ++n;
     if (ev) CK(cudaEventRecord(ev[4], st));
-    launch_scatter(o, st); ++n;
-    if (snapshot_grad) { mon_launch_snapshot_grad(o->P, o->n_mlp, o->opt.n_partials, o->gh, o->partials, o->grad_snap, st); ++n; }
+    if ((rc = launch_scatter(o, st, snapshot_grad ? o->grad_snap : nullptr)) != MON_OK) return rc;
+    ++n;
+    if (snapshot_grad) { mon_launch_snapshot_grad(o->n_mlp, o->n_mlp, o->opt.n_partials, o->gh, o->partials, o->grad_snap, st); ++n; }
     if (ev) CK(cudaEventRecord(ev[5], st));
-    launch_optimizer(o, st); ++n;
+    launch_optimizer(o, st, !snapshot_grad); ++n;
     if (ev) CK(cudaEventRecord(ev[6], st));
     CK(cudaGetLastError());
     if (n_launched) *n_launched = n;
     return MON_OK;
 }
 
-static int capture_graph_pipelined(mon_object* o, int iters, cudaGraphExec_t* out);
-static int pipe_mode();
-
 static int capture_graph(mon_object* o, int iters, cudaGraphExec_t* out) {
-    if (pipe_mode() != 0) return capture_graph_pipelined(o, iters, out);
     const MonBatch b = make_batch(o, false, false);
     cudaGraph_t g = nullptr;
-    cudaStream_t st = o->stream, aux = o->aux;
+    cudaStream_t st = o->stream, aux = o->aux, aux2 = o->aux2;
     CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     int rc = MON_OK;
     cudaError_t e = cudaSuccess;
@@ -641,21 +693,21 @@ static int capture_graph(mon_object* o, int iters, cudaGraphExec_t* out) {
     launch_points(o, b, st);
     for (int i = 0; i < iters && rc == MON_OK && e == cudaSuccess; ++i) {
         const bool fork = i + 1 < iters;
-        if ((rc = launch_encode(o, st)) != MON_OK) break;
+        // after a join the encode kernel's predecessor in the stream is not a plain kernel node: no programmatic edge there
+        if ((rc = launch_encode(o, st, i == 0)) != MON_OK) break;
         if ((rc = launch_mlp(o, b, st)) != MON_OK) break;
+        if ((e = cudaEventRecord(o->ev_fork_m, st)) != cudaSuccess) break;
+        if ((e = cudaStreamWaitEvent(aux2, o->ev_fork_m, 0)) != cudaSuccess) break;
+        launch_optimizer(o, aux2, false);
+        if ((e = cudaEventRecord(o->ev_join2, aux2)) != cudaSuccess) break;
         if (fork) {
-            if ((e = cudaEventRecord(o->ev_fork_m, st)) != cudaSuccess) break;
             if ((e = cudaStreamWaitEvent(aux, o->ev_fork_m, 0)) != cudaSuccess) break;
             launch_batch(o, b, aux);
-        }
-        launch_scatter(o, st);
-        if (fork) {
-            if ((e = cudaEventRecord(o->ev_fork_s, st)) != cudaSuccess) break;
-            if ((e = cudaStreamWaitEvent(aux, o->ev_fork_s, 0)) != cudaSuccess) break;
-            launch_points(o, b, aux);
+            launch_points(o, b, aux, false);
             if ((e = cudaEventRecord(o->ev_join, aux)) != cudaSuccess) break;
         }
-        launch_optimizer(o, st);
+        if ((rc = launch_scatter(o, st, nullptr)) != MON_OK) break;
+        if ((e = cudaStreamWaitEvent(st, o->ev_join2, 0)) != cudaSuccess) break;
         if (fork && (e = cudaStreamWaitEvent(st, o->ev_join, 0)) != cudaSuccess) break;
     }
     cudaError_t e2 = cudaStreamEndCapture(st, &g);
@@ -668,157 +720,30 @@ static int capture_graph(mon_object* o, int iters, cudaGraphExec_t* out) {
     return MON_OK;
 }
 
-// Level-pipelined iteration graph (opt-in: MON_PIPE=1; the chain above is the default because it measured FASTER on
-// B200, 71 vs 81 us per iteration — profiles/r1i_pipeline_timelines.txt: cutting the scatter by level group
-// concentrates its atomics on the hot coarse tables (30 us for the four pieces vs 16.6 us whole), and the 1024-thread /
-// 128 KB encode CTAs cannot become resident beside the optimizer's CTAs, so the intended overlap does not happen).
-// The hash-grid levels are independent
-// between the end of the fused MLP kernel of iteration i and the start of the one of iteration i+1: the gradient of a
-// level is scattered (S), consumed by the optimizer (O) and the level is re-encoded (E) without touching any other
-// level.  So the S -> O -> E chain is cut by level group and the pieces overlap:
-//
-//   main :  M(i) ----------------------+-> E part 0 (i+1) --+-> E part 1 (i+1) -> M(i+1)
-//   sc   :     \-> S0 -> S1 -> S2 -> S3 |                    |
-//   oc   :          \-> O0 -> O1 -------/--> O2 -> O3 -------/
-//   aux  :     \-> O_mlp(i) -> B(i+2) ......... P(i+2) (once every S(i) is done)
-//
-// The scatter is bound by L2 atomics, the encode by issue slots and shared-memory banks, the optimizer by L2/HBM
-// bandwidth: they overlap instead of queueing.  Batch generation runs TWO iterations ahead (two batch buffers:
-// rays, targets, control block; B(i+2) may start as soon as M(i) has read buffer i & 1) and the sample positions are
-// double-buffered as well (S(i) still reads the buffer P(i+2) will overwrite), so neither sits between the optimizer
-// and the next encode.  The persistent counters (RNG iteration, optimizer step, box count) live in ctrl_state, which
-// only the batch kernels touch, in order.  Every graph starts with its own B(0), P(0) into buffer 0, so no buffer
-// parity survives between graph launches.
-static int pipe_mode() {
-    static int mode = -1;
-    if (mode < 0) {
-        const char* e = getenv("MON_PIPE");
-        mode = e ? atoi(e) : 0;
-        if (mode != 1) mode = 0;
+// the instantiated graph of exactly `iters` iterations (1 <= iters <= MON_GRAPH_CHUNK), captured on first use
+static int graph_for(mon_object* o, uint32_t iters, cudaGraphExec_t* out) {
+    for (auto& g : o->graphs) if (g.iters == iters) { g.stamp = ++o->graph_clock; *out = g.exec; return MON_OK; }
+    cudaGraphExec_t exec = nullptr;
+    int rc = capture_graph(o, (int)iters, &exec);
+    if (rc != MON_OK) return rc;
+    size_t n_rem = 0, oldest = SIZE_MAX;
+    for (size_t k = 0; k < o->graphs.size(); ++k) {
+        if (o->graphs[k].iters == MON_GRAPH_CHUNK) continue;
+        ++n_rem;
+        if (oldest == SIZE_MAX || o->graphs[k].stamp < o->graphs[oldest].stamp) oldest = k;
     }
-    return mode;
-}
-static uint32_t pipe_enc_parts() {
-    static int parts = -1;
-    if (parts < 0) {
-        const char* e = getenv("MON_PIPE_ENC_PARTS");
-        parts = e ? atoi(e) : 2;
-        if (parts < 1 || parts > MON_PIPE_GROUPS) parts = 2;
+    if (iters != MON_GRAPH_CHUNK && n_rem >= MON_GRAPH_CACHE && oldest != SIZE_MAX) {
+        // replays of the dropped graph that are still in flight keep their resources until they finish
+        cudaGraphExecDestroy(o->graphs[oldest].exec);
+        o->graphs.erase(o->graphs.begin() + (long)oldest);
     }
-    return (uint32_t)parts;
-}
-struct PipeShape { uint32_t L, per, n_groups, n_parts; };
-static PipeShape pipe_shape(const mon_object* o) {
-    PipeShape p;
-    p.L = o->grid.n_levels;
-    p.per = ((p.L + MON_PIPE_GROUPS - 1) / MON_PIPE_GROUPS + 3) / 4 * 4;   // levels per scatter group, a multiple of 4
-    p.n_groups = (p.L + p.per - 1) / p.per;
-    p.n_parts = std::min(pipe_enc_parts(), p.n_groups);
-    return p;
-}
-
-static int capture_graph_pipelined(mon_object* o, int iters, cudaGraphExec_t* out) {
-    const MonBatch bb[2] = {make_batch(o, false, false, 0), make_batch(o, false, false, 1)};
-    float* const pts[2] = {o->pts, o->pts_alt};
-    const PipeShape ps = pipe_shape(o);
-    const uint32_t L = ps.L;
-    // (kernel-node priorities were tried to favour either side of the overlap: no measurable effect, profiles/r1i)
-    auto opt = [&](bool, bool pdl) {
-        MonLaunchOpt lo;
-        lo.pdl = pdl;
-        return lo;
-    };
-    cudaGraph_t g = nullptr;
-    cudaStream_t st = o->stream, aux = o->aux, sc = o->grp[0], oc = o->grp[1];
-    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    cudaError_t e = cudaSuccess;
-#define PE(x) do { if (e == cudaSuccess) e = (x); } while (0)
-    auto points = [&](int buf, cudaStream_t s, bool pdl) {
-        mon_launch_sample_points(o->N, MON_S, bb[buf].rays, nullptr, nullptr, o->seed, bb[buf].ctrl, 2, 0, o->scene.bmin, o->scene.bmax, pts[buf], s, opt(true, pdl));
-    };
-    auto encode = [&](int buf, uint32_t l0, uint32_t l1, bool pdl) {
-        PE(mon_launch_encode_forward(o->grid, o->N, pts[buf], o->ph_planar, o->enc, bb[buf].ctrl, (uint32_t)o->sm_count, st, l0, l1, opt(true, pdl)));
-    };
-    auto optimizer = [&](cudaStream_t s, int part, uint32_t l0, uint32_t l1) {
-        mon_launch_optimizer(o->opt, o->ctrl_late, o->pf, o->ph, o->gh, o->partials, o->m, o->v, o->ps, o->ema, o->loss, o->R, o->grid, o->ph_planar, s,
-                             part, l0, l1, opt(false, false));
-    };
-    // prologue: iteration 0 serially on the main stream, batch + points of iteration 1 beside it
-    mon_launch_generate_batch(bb[0], o->scene, st, opt(true, false));
-    PE(cudaEventRecord(o->ev_b, st));
-    points(0, st, true);
-    encode(0, 0, L, true);
-    if (iters > 1) {
-        PE(cudaStreamWaitEvent(aux, o->ev_b, 0));
-        mon_launch_generate_batch(bb[1], o->scene, aux, opt(true, false));
-        points(1, aux, false);
-        PE(cudaEventRecord(o->ev_pts, aux));
-    }
-    for (int i = 0; i < iters && e == cudaSuccess; ++i) {
-        const int cur = i & 1, nxt = cur ^ 1;
-        const bool more = i + 1 < iters, more2 = i + 2 < iters;
-        PE(mon_launch_mlp_train_tc(bb[cur], o->lc, o->cfg.n_hidden_layers, o->n_mlp, o->n_ctas, st, opt(true, true)));
-        PE(cudaEventRecord(o->ev_fork_m, st));
-        // aux: MLP-weight part of the optimizer (+ logged loss), then the batch of iteration i+2 into the buffers M(i) just released
-        PE(cudaStreamWaitEvent(aux, o->ev_fork_m, 0));
-        optimizer(aux, MON_OPT_MLP, 0, 0);
-        PE(cudaEventRecord(o->ev_aux, aux));
-        if (more2) mon_launch_generate_batch(bb[cur], o->scene, aux, opt(true, false));
-        // scatter chain (coarse to fine) and the optimizer chain that follows it group by group
-        PE(cudaStreamWaitEvent(sc, o->ev_fork_m, 0));
-        for (uint32_t k = 0; k < ps.n_groups; ++k) {
-            const uint32_t l0 = k * ps.per, l1 = std::min(L, l0 + ps.per);
-            mon_launch_encode_backward(o->grid, o->N, pts[cur], o->ctrl_late, o->d_enc, o->gh + o->n_mlp, sc, l0, l1, opt(false, false));
-            PE(cudaEventRecord(o->ev_s[k], sc));
-            PE(cudaStreamWaitEvent(oc, o->ev_s[k], 0));
-            optimizer(oc, MON_OPT_GRID, l0, l1);
-            PE(cudaEventRecord(o->ev_o[k], oc));
-        }
-        if (more) {
-            // the next encode, part by part, as soon as the weights of its levels are final
-            PE(cudaStreamWaitEvent(st, o->ev_pts, 0));
-            for (uint32_t p = 0; p < ps.n_parts; ++p) {
-                const uint32_t g0 = p * ps.n_groups / ps.n_parts, g1 = (p + 1) * ps.n_groups / ps.n_parts;
-                const bool last = p + 1 == ps.n_parts;
-                PE(cudaStreamWaitEvent(st, o->ev_o[g1 - 1], 0));     // the optimizer chain is ordered: implies every earlier group
-                if (last) {
-                    PE(cudaStreamWaitEvent(st, o->ev_aux, 0));
-                    PE(cudaEventRecord(o->ev_ready, st));             // M(i), every S(i) and O(i) are complete
-                }
-                encode(nxt, g0 * ps.per, std::min(L, g1 * ps.per), false);
-            }
-            if (more2) {
-                PE(cudaStreamWaitEvent(aux, o->ev_ready, 0));         // S(i) no longer reads this point buffer
-                points(cur, aux, false);
-                PE(cudaEventRecord(o->ev_pts, aux));
-            }
-        } else {
-            PE(cudaStreamWaitEvent(st, o->ev_o[ps.n_groups - 1], 0));
-            PE(cudaStreamWaitEvent(st, o->ev_aux, 0));
-        }
-    }
-#undef PE
-    cudaError_t e2 = cudaStreamEndCapture(st, &g);
-    if (e != cudaSuccess) { if (g) cudaGraphDestroy(g); return fail(MON_ERR_CUDA, "graph capture: %s", cudaGetErrorString(e)); }
-    if (e2 != cudaSuccess) return fail(MON_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e2));
-    e = cudaGetLastError();
-    if (e != cudaSuccess) { cudaGraphDestroy(g); return fail(MON_ERR_CUDA, "graph capture launch: %s", cudaGetErrorString(e)); }
-    e = cudaGraphInstantiate(out, g, 0);
-    cudaGraphDestroy(g);
-    if (e != cudaSuccess) return fail(MON_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    o->graphs.push_back({iters, exec, ++o->graph_clock});
+    *out = exec;
     return MON_OK;
 }
 
 // kernels launched by one replay of an `iters`-iteration graph
-static uint64_t launches_in_graph(const mon_object* o, uint32_t iters) {
-    if (iters == 0) return 0;
-    if (pipe_mode() == 0) return 6ull * iters;
-    const PipeShape ps = pipe_shape(o);
-    // B, P, E of iteration 0; B, P of iteration 1; per iteration M, O_mlp, S + O per level group; the split encode of
-    // every follow-up iteration; B, P two iterations ahead
-    return 3ull + (iters > 1 ? 2u : 0u) + (uint64_t)iters * (2u + 2u * ps.n_groups) + (uint64_t)(iters - 1) * ps.n_parts +
-           (iters > 2 ? 2ull * (iters - 2) : 0ull);
-}
+static uint64_t launches_in_graph(const mon_object*, uint32_t iters) { return 6ull * iters; }
 
 int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uint8_t instance_id,
                       const float obj_Tow[16], const float bmin[3], const float bmax[3], mon_object** out) {
@@ -875,39 +800,27 @@ int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uin
     const size_t P = o->P, R = o->R, N = o->N;
     OALLOC(o->pf, P * 4); OALLOC(o->m, P * 4); OALLOC(o->v, P * 4); OALLOC(o->ps, P * 4);
     OALLOC(o->ph, P * 2 + 16); OALLOC(o->gh, P * 2 + 16); OALLOC(o->ema, P * 2 + 16);
-    OALLOC(o->ctrl_state, sizeof(MonCtrl)); OALLOC(o->ctrl, sizeof(MonCtrl)); OALLOC(o->ctrl_alt, sizeof(MonCtrl)); OALLOC(o->ctrl_late, sizeof(MonCtrl));
+    OALLOC(o->ctrl_state, sizeof(MonCtrl)); OALLOC(o->ctrl, sizeof(MonCtrl)); OALLOC(o->ctrl_late, sizeof(MonCtrl));
     OALLOC(o->rays, R * sizeof(MonRay)); OALLOC(o->ray_inst, R);
     OALLOC(o->target, R * 12); OALLOC(o->target_depth, R * 4); OALLOC(o->bg, R * 12);
-    OALLOC(o->rays_alt, R * sizeof(MonRay)); OALLOC(o->ray_inst_alt, R);
-    OALLOC(o->target_alt, R * 12); OALLOC(o->target_depth_alt, R * 4); OALLOC(o->bg_alt, R * 12);
     OALLOC(o->rgb_rays, R * 12); OALLOC(o->depth_rays, R * 4); OALLOC(o->mask_rays, R * 4); OALLOC(o->loss, R * 4);
-    OALLOC(o->pts, N * 12); OALLOC(o->pts_alt, N * 12); OALLOC(o->enc, N * MON_IN * 2); OALLOC(o->d_enc, N * MON_IN * 2);
+    OALLOC(o->pts, N * 12); OALLOC(o->enc, N * MON_IN * 2);
+    OALLOC(o->pts_c, N * 12); OALLOC(o->genc, N * (size_t)MON_MAX_LEVELS * 4); OALLOC(o->live_cnt, 8);
     OALLOC(o->ph_planar, (size_t)o->n_grid * 2 + 16);
     OALLOC(o->partials, (size_t)o->n_ctas * o->n_mlp * 4);
     OALLOC(o->debias_lut, (size_t)MON_DEBIAS_LUT * 4);
     o->opt.debias_lut = o->debias_lut; o->opt.n_debias_lut = MON_DEBIAS_LUT;
 #undef OALLOC
+    if (const char* env = getenv("MON_SO_FUSE")) o->so_fuse = atoi(env) != 0;   // A/B: separate optimizer sweep over the grid
     cudaError_t e;
     if ((e = cudaMallocHost(&o->h_ctrl, sizeof(MonCtrl))) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&o->aux, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&o->aux2, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&o->ev_fork_m, cudaEventDisableTiming)) != cudaSuccess ||
-        (e = cudaEventCreateWithFlags(&o->ev_fork_s, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&o->ev_join, cudaEventDisableTiming)) != cudaSuccess ||
-        (e = cudaEventCreateWithFlags(&o->ev_pts, cudaEventDisableTiming)) != cudaSuccess ||
-        (e = cudaEventCreateWithFlags(&o->ev_aux, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&o->ev_join2, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreate(&o->ev0)) != cudaSuccess || (e = cudaEventCreate(&o->ev1)) != cudaSuccess) {
-        mon_object_destroy(o);
-        return fail(MON_ERR_CUDA, "object setup: %s", cudaGetErrorString(e));
-    }
-    for (int k = 0; k < MON_PIPE_GROUPS && e == cudaSuccess; ++k) {
-        if ((e = cudaEventCreateWithFlags(&o->ev_s[k], cudaEventDisableTiming)) == cudaSuccess)
-            e = cudaEventCreateWithFlags(&o->ev_o[k], cudaEventDisableTiming);
-    }
-    for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaStreamCreateWithFlags(&o->grp[k], cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&o->ev_ready, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&o->ev_b, cudaEventDisableTiming);
-    if (e != cudaSuccess) {
         mon_object_destroy(o);
         return fail(MON_ERR_CUDA, "object setup: %s", cudaGetErrorString(e));
     }
@@ -961,30 +874,18 @@ int mon_object_destroy(mon_object* o) {
     cudaSetDevice(o->ds->gpu);
     if (o->stream) cudaStreamSynchronize(o->stream);
     drop_graphs(o);
-    void* ptrs[] = {o->pf, o->m, o->v, o->ps, o->ph, o->gh, o->ema, o->ctrl_state, o->ctrl, o->ctrl_alt, o->ctrl_late, o->rays_alt, o->ray_inst_alt,
-                    o->target_alt, o->target_depth_alt, o->bg_alt, o->d_boxes, o->rays, o->ray_inst, o->target,
-                    o->target_depth, o->bg, o->rgb_rays, o->depth_rays, o->mask_rays, o->loss, o->pts, o->pts_alt, o->debias_lut, o->enc, o->d_enc, o->ph_planar, o->partials,
+    void* ptrs[] = {o->pf, o->m, o->v, o->ps, o->ph, o->gh, o->ema, o->ctrl_state, o->ctrl, o->ctrl_late, o->d_boxes, o->rays, o->ray_inst, o->target,
+                    o->target_depth, o->bg, o->rgb_rays, o->depth_rays, o->mask_rays, o->loss, o->pts, o->pts_c, o->genc, o->live_cnt, o->debias_lut, o->enc,
+                    o->d_enc, o->ph_planar, o->partials,
                     o->dbg_out, o->dbg_dout, o->inj_xy, o->inj_col, o->inj_dt, o->grad_snap, o->r_rays, o->r_orig, o->r_nhit, o->r_enc,
                     o->r_jit, o->r_rgb, o->r_depth, o->r_mask, o->r_Twc, o->r_pts, o->r_planar};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (void* p : o->scr) if (p) cudaFree(p);
     if (o->h_ctrl) cudaFreeHost(o->h_ctrl);
-    if (o->ev0) cudaEventDestroy(o->ev0);
-    if (o->ev1) cudaEventDestroy(o->ev1);
-    if (o->ev_fork_m) cudaEventDestroy(o->ev_fork_m);
-    if (o->ev_fork_s) cudaEventDestroy(o->ev_fork_s);
-    if (o->ev_join) cudaEventDestroy(o->ev_join);
-    if (o->ev_pts) cudaEventDestroy(o->ev_pts);
-    if (o->ev_aux) cudaEventDestroy(o->ev_aux);
-    if (o->ev_ready) cudaEventDestroy(o->ev_ready);
-    if (o->ev_b) cudaEventDestroy(o->ev_b);
-    for (int k = 0; k < MON_PIPE_GROUPS; ++k) {
-        if (o->ev_s[k]) cudaEventDestroy(o->ev_s[k]);
-        if (o->ev_o[k]) cudaEventDestroy(o->ev_o[k]);
-    }
-    for (int k = 0; k < 2; ++k) if (o->grp[k]) cudaStreamDestroy(o->grp[k]);
-    if (o->aux) cudaStreamDestroy(o->aux);
-    if (o->stream) cudaStreamDestroy(o->stream);
+    cudaEvent_t evs[] = {o->ev0, o->ev1, o->ev_fork_m, o->ev_join, o->ev_join2};
+    for (cudaEvent_t ev : evs) if (ev) cudaEventDestroy(ev);
+    cudaStream_t sts[] = {o->aux2, o->aux, o->stream};
+    for (cudaStream_t st : sts) if (st) cudaStreamDestroy(st);
     delete o;
     return MON_OK;
 }
@@ -992,6 +893,7 @@ int mon_object_destroy(mon_object* o) {
 static int upload_boxes(mon_object* o, uint32_t first) {
     CK(cudaSetDevice(o->ds->gpu));
     const uint32_t n = (uint32_t)o->h_boxes.size();
+    std::unique_lock<std::mutex> ds_lock(o->ds->mu);   // the ingest thread appends frames concurrently
     for (uint32_t i = first; i < n; ++i) {
         const mon_bbox2d& b = o->h_boxes[i];
         if (b.FrameId >= o->ds->max_frames || !o->ds->h_frames[b.FrameId].rgb)
@@ -1000,6 +902,7 @@ static int upload_boxes(mon_object* o, uint32_t first) {
         if (b.w == 0 || b.h == 0 || (uint64_t)b.x + b.w > (uint64_t)o->ds->W || (uint64_t)b.y + b.h > (uint64_t)o->ds->H)
             return fail(MON_ERR_ARG, "box %u (x=%u y=%u h=%u w=%u) lies outside the %dx%d image", i, b.x, b.y, b.h, b.w, o->ds->W, o->ds->H);
     }
+    ds_lock.unlock();
     CK(cudaStreamSynchronize(o->stream));
     if (n > o->box_cap) {
         const uint32_t cap = std::max<uint32_t>(256, n * 2);
@@ -1042,20 +945,33 @@ static int finish_timing(mon_object* o) {
     return MON_OK;
 }
 
+int mon_object_prepare_train(mon_object* o, uint32_t iters) {
+    if (!o) return fail(MON_ERR_ARG, "obj is NULL");
+    if (o->h_boxes.empty()) return fail(MON_ERR_STATE, "no 2-D boxes: call mon_object_set_bboxes first");
+    CK(cudaSetDevice(o->ds->gpu));
+    cudaGraphExec_t g = nullptr;
+    if (iters >= MON_GRAPH_CHUNK) { int rc = graph_for(o, MON_GRAPH_CHUNK, &g); if (rc != MON_OK) return rc; }
+    if (iters % MON_GRAPH_CHUNK) { int rc = graph_for(o, iters % MON_GRAPH_CHUNK, &g); if (rc != MON_OK) return rc; }
+    return MON_OK;
+}
+
 int mon_object_train_async(mon_object* o, uint32_t iters) {
     if (!o) return fail(MON_ERR_ARG, "obj is NULL");
     if (o->h_boxes.empty()) return fail(MON_ERR_STATE, "no 2-D boxes: call mon_object_set_bboxes first");
     CK(cudaSetDevice(o->ds->gpu));
-    if (!o->graph1) { int rc = capture_graph(o, 1, &o->graph1); if (rc != MON_OK) return rc; }
-    if (iters >= MON_GRAPH_CHUNK && !o->graphN) { int rc = capture_graph(o, MON_GRAPH_CHUNK, &o->graphN); if (rc != MON_OK) return rc; }
+    // a call of n iterations = n / 64 replays of the 64-iteration graph + ONE graph of exactly n % 64 iterations: every
+    // iteration but the first of each graph has its batch generation hidden behind the previous iteration's scatter
+    cudaGraphExec_t g_chunk = nullptr, g_rem = nullptr;
+    const uint32_t rem = iters % MON_GRAPH_CHUNK;
+    if (iters >= MON_GRAPH_CHUNK) { int rc = graph_for(o, MON_GRAPH_CHUNK, &g_chunk); if (rc != MON_OK) return rc; }
+    if (rem) { int rc = graph_for(o, rem, &g_rem); if (rc != MON_OK) return rc; }
     CK(cudaStreamWaitEvent(o->stream, o->ds->ev_uploaded, 0));   // frames uploaded asynchronously from pinned buffers
     CK(cudaEventRecord(o->ev0, o->stream));
-    uint32_t left = iters;
-    while (left >= MON_GRAPH_CHUNK) { CK(cudaGraphLaunch(o->graphN, o->stream)); left -= MON_GRAPH_CHUNK; }
-    while (left > 0) { CK(cudaGraphLaunch(o->graph1, o->stream)); --left; }
+    for (uint32_t k = 0; k < iters / MON_GRAPH_CHUNK; ++k) CK(cudaGraphLaunch(g_chunk, o->stream));
+    if (rem) CK(cudaGraphLaunch(g_rem, o->stream));
     CK(cudaEventRecord(o->ev1, o->stream));
     o->timing_pending = true;
-    o->launches += (uint64_t)(iters / MON_GRAPH_CHUNK) * launches_in_graph(o, MON_GRAPH_CHUNK) + (uint64_t)(iters % MON_GRAPH_CHUNK) * launches_in_graph(o, 1);
+    o->launches += launches_in_graph(o, iters);
     o->have_injected = false;
     return MON_OK;
 }
@@ -1137,6 +1053,18 @@ int mon_object_step_count(mon_object* o, uint32_t* step) {
     return MON_OK;
 }
 
+int mon_object_live_samples(mon_object* o, uint32_t* n_live, uint32_t* n_points) {
+    if (!o || !n_live) return fail(MON_ERR_ARG, "NULL argument");
+    CK(cudaSetDevice(o->ds->gpu));
+    int rc = read_ctrl(o);   // waits for the stream; the control block names the last iteration
+    if (rc != MON_OK) return rc;
+    uint32_t cnt[2] = {0, 0};
+    CK(cudaMemcpy(cnt, o->live_cnt, sizeof(cnt), cudaMemcpyDeviceToHost));
+    *n_live = o->h_ctrl->iter ? cnt[(o->h_ctrl->iter - 1) & 1u] : 0u;
+    if (n_points) *n_points = o->N;
+    return MON_OK;
+}
+
 int mon_object_launch_count(mon_object* o, uint64_t* n) {
     if (!o || !n) return fail(MON_ERR_ARG, "NULL argument");
     *n = o->launches;
@@ -1147,9 +1075,20 @@ int mon_object_launch_count(mon_object* o, uint64_t* n) {
 static int ensure_hooks(mon_object* o) {
     if (o->dbg_out) return MON_OK;
     const size_t R = o->R, N = o->N;
-    CK(cudaMalloc(&o->dbg_out, N * 16)); CK(cudaMalloc(&o->dbg_dout, N * 16));
-    CK(cudaMalloc(&o->inj_xy, R * 8)); CK(cudaMalloc(&o->inj_col, R * 12)); CK(cudaMalloc(&o->inj_dt, N * 4));
-    CK(cudaMalloc(&o->grad_snap, (size_t)o->P * 4));
+    // all or nothing: the buffers are committed to the object only when every allocation succeeded
+    void* tmp[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    const size_t bytes[7] = {N * 16, N * 16, R * 8, R * 12, N * 4, (size_t)o->P * 4, N * MON_IN * 2};
+    for (int k = 0; k < 7; ++k) {
+        cudaError_t e = cudaMalloc(&tmp[k], bytes[k]);
+        if (e == cudaSuccess) e = cudaMemset(tmp[k], 0, bytes[k]);
+        if (e != cudaSuccess) {
+            for (void* p : tmp) if (p) cudaFree(p);
+            return fail(MON_ERR_CUDA, "parity-hook buffers (%zu B): %s", bytes[k], cudaGetErrorString(e));
+        }
+    }
+    o->dbg_dout = static_cast<float*>(tmp[1]); o->inj_xy = static_cast<float*>(tmp[2]); o->inj_col = static_cast<float*>(tmp[3]);
+    o->inj_dt = static_cast<float*>(tmp[4]); o->grad_snap = static_cast<float*>(tmp[5]); o->d_enc = static_cast<__half*>(tmp[6]);
+    o->dbg_out = static_cast<float*>(tmp[0]);
     return MON_OK;
 }
 
@@ -1165,6 +1104,7 @@ int mon_object_train_injected(mon_object* o, const float* sample_xy, const float
     CK(cudaMemcpyAsync(o->inj_dt, rand_dt, (size_t)o->N * 4, cudaMemcpyHostToDevice, o->stream));
     CK(cudaMemsetAsync(o->dbg_out, 0, (size_t)o->N * 16, o->stream));
     CK(cudaMemsetAsync(o->dbg_dout, 0, (size_t)o->N * 16, o->stream));
+    CK(cudaMemsetAsync(o->d_enc, 0, (size_t)o->N * MON_IN * 2, o->stream));
     const MonBatch b = make_batch(o, true, true);
     int n = 0;
     CK(cudaEventRecord(o->ev0, o->stream));

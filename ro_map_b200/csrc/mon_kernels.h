@@ -37,10 +37,9 @@ __device__ __forceinline__ void mon_pdl_trigger() { asm volatile("griddepcontrol
 enum { MON_PDL_POINTS = 1, MON_PDL_ENCODE = 2, MON_PDL_MLP = 4, MON_PDL_SCATTER = 8, MON_PDL_OPTIM = 16 };
 unsigned mon_pdl_mask();
 
-// Per-launch options of the iteration graphs.  pdl = false: no programmatic edge even if the mask allows one (kernels
-// of the level-pipelined graph whose predecessor in the stream is not the producer they wait for).  priority: CUDA
-// stream-priority value recorded on the kernel node (numerically lower = dispatched first), used to order the level
-// groups of the gradient scatter, which all become ready at the same time.
+// Per-launch options of the iteration graphs.  pdl = false: no programmatic edge even if the mask allows one (a kernel
+// whose predecessor in the stream is not the producer it waits for).  priority: CUDA stream-priority value recorded on
+// the kernel node (numerically lower = dispatched first).
 struct MonLaunchOpt {
     bool pdl = true;
     bool set_priority = false;
@@ -109,5 +108,11 @@ void mon_launch_optimizer(const MonOpt& o, MonCtrl* ctrl, float* pf, __half* ph,
                           __half* planar, cudaStream_t st, int part = 0, uint32_t level_begin = 0, uint32_t level_end = 0xffffffffu,
                           const MonLaunchOpt& lo = MonLaunchOpt());
 enum { MON_OPT_ALL = 0, MON_OPT_MLP = 1, MON_OPT_GRID = 2, MON_OPT_MLP_GRID = 3 };
+// kernels_scatter_adam.cu: gradient scatter into shared-memory resident table slices fused with Adam + EMA of the grid
+uint32_t mon_scatter_adam_jobs(const MonGrid& g);
+cudaError_t mon_launch_scatter_adam(const MonGrid& g, const MonOpt& o, uint32_t n_points, const uint32_t* live_cnt, const float* pts_c,
+                                    const uint32_t* genc, const MonCtrl* ctrl, float* pf, __half* ph, float* m, float* v, uint32_t* ps,
+                                    __half* ema, __half* planar, __half* gh_grid, float* grad_snap, bool fuse, uint32_t sm_count,
+                                    cudaStream_t st, const MonLaunchOpt& lo = MonLaunchOpt());
 void mon_launch_snapshot_grad(uint32_t n, uint32_t n_mlp, uint32_t n_partials, const __half* gh, const float* partials,
                               float* out, cudaStream_t st);

@@ -14,7 +14,6 @@
 #define MON_IN 32         // encoding width = n_levels * 2
 #define MON_OUT 16        // padded output width (tcnn pads 4 -> 16)
 #define MON_MAX_MLP_CTAS 592
-#define MON_PIPE_GROUPS 4      // level groups of the pipelined scatter -> optimizer -> encode chain (mon_core.cu)
 
 // 36-byte POD; same field order as nerf::Ray
 struct MonRay { float o[3], d[3], d_norm, tmin, tmax; };
@@ -102,8 +101,14 @@ struct MonBatch {
     MonRay* rays; uint8_t* ray_inst; float* target; float* target_depth; float* bg;
     float* rgb_rays; float* depth_rays; float* mask_rays; float* loss;
     // per-point
-    __half* enc;      // [N][32]
-    __half* d_enc;    // [N][32]
+    __half* enc;      // level-major pairs [16][N][2]
+    __half* d_enc;    // [N][32] point-major dL/dencoding: parity hook only (nullptr in production)
+    const float* pts; // [N][3] unit-cube sample positions of this iteration (read by the fused MLP kernel for the compaction)
+    // compacted live samples (non-zero dL/dencoding row), written by the fused MLP kernel for the scatter+Adam kernel:
+    // slot k holds position pts_c[k][3] and, per level l, the level's two fp16 gradients as one word genc[l * N + k]
+    float* pts_c;
+    uint32_t* genc;
+    uint32_t* live_cnt;   // [2]: number of live samples of the iteration, indexed by (iteration & 1); zeroed by the batch kernel
     // debug dumps (nullptr in production): out [N][4], dout [N][4]
     float* dbg_out; float* dbg_dout;
     // parameters

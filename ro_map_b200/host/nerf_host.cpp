@@ -210,15 +210,18 @@ void NeRF_Dataset::FrameDataToGPU(unsigned int imgId, const string timestamp) { 
 }
 
 void NeRF_Dataset::UpdateDataGPU(unsigned int CurId, unsigned int FrameNum) {   // nerf_data.cu:341-353
-    if (mvTemp_Update_Pose.size() < FrameNum) return;
-    for (auto& m : mvUpdateMutex) m->lock();
+    if (mvTemp_Update_Pose.size() < FrameNum || CurId < FrameNum) return;
+    // every object's training step holds its own mutex of this list while its batches read the poses
+    // (NeRF::TrainStep, like Train_Step_Online nerf_model.cu:1676): taking all of them serialises the update
+    // against every training step on this GPU
+    std::vector<std::unique_lock<std::mutex>> locks;
+    locks.reserve(mvUpdateMutex.size());
+    for (auto& m : mvUpdateMutex) locks.emplace_back(*m);
     vector<float> flat((size_t)FrameNum * 16);
     for (unsigned int i = 0; i < FrameNum; ++i) memcpy(&flat[(size_t)i * 16], mon_compat::mat16(mvTemp_Update_Pose[i]), 64);
-    if (CurId < FrameNum) return;
     const unsigned int first = CurId - FrameNum;   // `head` of the reference (nerf_data.cu:349)
     if (mon_dataset_update_poses(mpCore, first, FrameNum, flat.data()) != MON_OK) cerr << "pose update: " << mon_last_error() << endl;
     for (unsigned int i = 0; i < FrameNum && first + i < mvIamgesPose.size(); ++i) mvIamgesPose[first + i] = mvTemp_Update_Pose[i];
-    for (auto& m : mvUpdateMutex) m->unlock();
 }
 
 // ------------------------------------------------------------------------------------------ NeRF
@@ -299,7 +302,12 @@ bool NeRF::ReadBboxOffline(const string path) {   // nerf.cu:58-118
 void NeRF::TrainStep(int iters) {   // NeRF_Model::Train_Step / Train_Step_Online (nerf_model.cu:1630-1699)
     const auto t0 = std::chrono::steady_clock::now();
     float loss = 0.0f;
-    if (mon_object_train(mpCore, (uint32_t)iters, &loss) != MON_OK) die("train step");
+    {
+        // online: pose updates of the dataset (UpdateDataGPU) wait for the step in flight and vice versa
+        std::unique_lock<std::mutex> pose_lock;
+        if (mpTrainData && mDataMutexIdx < mpTrainData->mvUpdateMutex.size()) pose_lock = std::unique_lock<std::mutex>(*mpTrainData->mvUpdateMutex[mDataMutexIdx]);
+        if (mon_object_train(mpCore, (uint32_t)iters, &loss) != MON_OK) die("train step");
+    }
     uint32_t step = 0;
     mon_object_step_count(mpCore, &step);
     mon_object_last_train_ms(mpCore, &mfLastMs);
@@ -378,8 +386,14 @@ void NeRF::TrainOnline() {   // nerf.cu:187-253
             std::unique_lock<std::mutex> lock(mUpdateBbox);
             if (mnBbox == mnCoreBbox && !mbFinishRequested) mCond.wait(lock);   // no update, wait
             if (mnBbox > mnCoreBbox) {
-                if (mon_object_add_bboxes(mpCore, reinterpret_cast<const mon_bbox2d*>(mFrameIdBbox.data() + mnCoreBbox), (uint32_t)(mnBbox - mnCoreBbox)) != MON_OK)
-                    die("bbox upload");
+                const mon_bbox2d* fresh = reinterpret_cast<const mon_bbox2d*>(mFrameIdBbox.data() + mnCoreBbox);
+                const uint32_t n_fresh = (uint32_t)(mnBbox - mnCoreBbox);
+                if (mon_object_add_bboxes(mpCore, fresh, n_fresh) != MON_OK) {
+                    // a box outside the image or on a keyframe that has not been ingested: drop that box and keep the
+                    // SLAM process alive (a training thread must not exit() the whole system over one detection)
+                    for (uint32_t k = 0; k < n_fresh; ++k)
+                        if (mon_object_add_bboxes(mpCore, fresh + k, 1) != MON_OK) cerr << "Id: " << mId << " box dropped: " << mon_last_error() << endl;
+                }
                 mnCoreBbox = mnBbox;
                 train_step = mnTrainStep;
                 mnTrainStep = 0;
@@ -666,12 +680,22 @@ void NerfManagerOnline::DatasetInit(float fx, float fy, float cx, float cy, int 
 
 void NerfManagerOnline::NewFrameToDataset(unsigned int imgId, const string timestamp, cv::Mat& img, cv::Mat& instance, const cv::Mat& depth_img,
                                           const Eigen::Matrix4f& pose) {
-    // the reference uploads the frame once per GPU from one host thread each (nerf_manager.cu:189-217); here the frame
-    // goes to GPU 0 over PCIe and every other replica is filled by the same call on its own dataset
-    for (int i = 0; i < mNumGPU; i++) {
-        auto& d = mvpDataset[i];
+    // the reference uploads the frame once per GPU, from one host thread each (nerf_manager.cu:189-217).  Here it crosses
+    // PCIe ONCE, to GPU 0 (asynchronous DMA out of pinned staging memory), and every other replica is filled device to
+    // device over NVLink on that dataset's own upload stream, ordered behind the upload by an event: nothing below waits
+    // for a copy, so the SLAM thread pays one staging memcpy whatever the number of GPUs
+    {
+        auto& d = mvpDataset[0];
         d->Temp_Img = img; d->Temp_Instance = instance; d->Temp_Depth = depth_img; d->Temp_Pose = pose;
         d->FrameDataToGPU(imgId, timestamp);
+    }
+    for (int i = 1; i < mNumGPU; i++) {
+        auto& d = mvpDataset[i];
+        if (mon_dataset_copy_frame_from_peer(d->mpCore, mvpDataset[0]->mpCore, imgId) != MON_OK) die("frame replication");
+        d->mStampToIdx[timestamp] = imgId;
+        if (imgId >= d->mvIamgesPose.size()) d->mvIamgesPose.resize(imgId + 1, Eigen::Matrix4f::Identity());
+        d->mvIamgesPose[imgId] = pose;
+        d->mFrameDataNum += 1;
     }
 }
 

@@ -1,0 +1,187 @@
+"""GPU parity AT THE BENCHMARKED CONFIGURATION: R = 4096 rays x 32 samples on the 800x800, 30-keyframe synthetic 'room'
+scene bench.py runs (BASELINE.json configs[1]) — 1024 MLP tiles over the persistent CTAs, the 148-CTA encode split, slab
+storage across frames, all 30 scatter + Adam clusters.  The same checks as the small-scene tests, against the CPU oracle
+(stage by stage) and against the reference library itself (live, incl. a batch with roll-over padding), plus the pieces
+that only exist at this level: peer clone of a dataset, short training calls, PSNR against the reference.
+"""
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "oracle" / "ref"))
+sys.path.insert(0, str(ROOT / "tests"))
+
+pytestmark = pytest.mark.gpu
+
+R_BENCH = 4096
+FRAMES_BENCH = 30
+
+
+@pytest.fixture(scope="module")
+def core():
+    from ro_map_b200 import build, core
+    build.build()
+    if core.device_count() == 0:
+        pytest.fail("no CUDA device visible: the gpu-marked tests must run on the B200 box")
+    return core
+
+
+@pytest.fixture(scope="module")
+def bench_seq():
+    """exactly bench.py's scene: make_scene(1, 30) -> 800x800, fx = fy = 1111.11, seed 1337"""
+    from ro_map_b200 import synthetic as syn
+    return syn.make_sequence(n_frames=FRAMES_BENCH, n_objects=1, seed=1337)
+
+
+@pytest.fixture(scope="module")
+def bench_dataset(core, bench_seq):
+    seq = bench_seq
+    ds = core.Dataset(0, *seq.K, seq.H, seq.W, len(seq.poses), True)
+    for i in range(len(seq.poses)):
+        ds.add_frame(i, seq.rgb[i], seq.instance[i], seq.depth[i], seq.poses[i])
+    ds.sync()
+    return ds
+
+
+@pytest.fixture(scope="module")
+def ref_binding():
+    import ref_binding as rb
+    if not rb.LIB_PATH.exists():
+        pytest.skip("oracle/_ref/libmon_ref.so is not in the tree (built by oracle/ref/Makefile where /root/reference exists)")
+    return rb
+
+
+@pytest.mark.parametrize("n_hidden", [1, 2])
+def test_stage_by_stage_against_oracle_at_bench_shape(core, oracle, bench_dataset, bench_seq, n_hidden):
+    """rays / targets / points / encoding bit-exact, network output, compositing, loss, dL/dout, dL/denc, MLP and grid gradients
+    within the tolerances written in test_gpu_parity.check_one_iteration_stage_by_stage — at R = 4096 on the bench scene."""
+    import test_gpu_parity as tp
+    assert bench_seq.H == 800 and bench_seq.W == 800
+    tp.check_one_iteration_stage_by_stage(core, oracle, bench_dataset, bench_seq, bench_seq.objects[0], R_BENCH, n_hidden, warm_iters=2)
+
+
+@pytest.mark.parametrize("n_hidden", [1, 2])
+def test_live_reference_at_bench_shape(core, oracle, ref_binding, bench_seq, n_hidden):
+    import test_gpu_vs_reference_live as tl
+    tl.run_live_parity(core, oracle, ref_binding, bench_seq, bench_seq.objects[0], R_BENCH, n_hidden, f"live_parity_bench_shape_nh{n_hidden}")
+
+
+def test_live_reference_with_rollover_at_bench_shape(core, oracle, ref_binding, bench_seq):
+    """freely drawn pixels: part of the 4096 slots die (the 2-D box is the bounding rectangle of the projected 3-D box) and the
+    batch is padded by roll-over on both sides"""
+    import test_gpu_vs_reference_live as tl
+    tl.run_live_parity(core, oracle, ref_binding, bench_seq, bench_seq.objects[0], R_BENCH, 1, "live_parity_bench_shape_rollover", all_survive=False)
+
+
+def test_clone_from_peer_gives_the_identical_batch(core, bench_dataset, bench_seq):
+    """mon_dataset_clone_from_peer / mon_dataset_copy_frame_from_peer (device-to-device replication of the keyframe set; the same
+    code path between two GPUs goes over NVLink): an object on the clone generates the same batch, bit for bit."""
+    seq, obj = bench_seq, bench_seq.objects[0]
+    clone = core.Dataset(0, *seq.K, seq.H, seq.W, len(seq.poses), True)
+    clone.clone_from_peer(bench_dataset)
+    assert clone.frame_count == bench_dataset.frame_count == len(seq.poses)
+    # frame by frame (the online path), into a third dataset, in a scrambled order
+    single = core.Dataset(0, *seq.K, seq.H, seq.W, len(seq.poses), True)
+    for i in np.random.default_rng(3).permutation(len(seq.poses)):
+        single.copy_frame_from_peer(bench_dataset, int(i))
+    single.sync()
+    with pytest.raises(core.MonError, match="MON_ERR_ARG"):
+        clone.clone_from_peer(clone)
+    cfg = core.default_config(rays_per_batch=R_BENCH)
+    bmin, bmax = -1.1 * obj.half, 1.1 * obj.half
+    rng = np.random.default_rng(9)
+    u = lambda shape: (1.0 - rng.random(shape, dtype=np.float32)).astype(np.float32)   # noqa: E731
+    sxy, col, dt = u((R_BENCH, 2)), u((R_BENCH, 3)), u((R_BENCH, 32))
+    outs = []
+    for ds in (bench_dataset, clone, single):
+        g = core.NerfObject(ds, cfg, obj.Tow, bmin, bmax, obj.instance_id)
+        g.set_bboxes(obj.boxes)
+        loss, n_in = g.train_injected(sxy, col, dt)
+        outs.append((loss, n_in, g.last("rays"), g.last("target"), g.last("target_depth"), g.last("ray_instance"), g.last("enc"), g.last("out")))
+        g.close()
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert np.array_equal(a, b)
+    assert (outs[0][3] > 0).any() and (outs[0][4] > 0).any()      # real pixels and real depths were read
+    clone.close()
+    single.close()
+
+
+def test_short_calls_run_at_the_long_call_rate(core, bench_dataset, bench_seq):
+    """A 20-iteration call (the online TrainStepIterations range, and what the driver's bench times) replays ONE graph of exactly
+    20 iterations with the batch generation of iteration i+1 hidden behind iteration i: its per-iteration device time stays
+    within 15 % of a 500-iteration call's.  (Round 1 fell back to 20 un-overlapped 1-iteration graphs: +70 %.)"""
+    seq, obj = bench_seq, bench_seq.objects[0]
+    g = core.NerfObject(bench_dataset, core.default_config(rays_per_batch=R_BENCH), obj.Tow, -1.1 * obj.half, 1.1 * obj.half, obj.instance_id)
+    g.set_bboxes(obj.boxes)
+    g.train(600)                     # steady state: the cost of an iteration no longer changes with the training state
+    g.prepare_train(20)
+    short, long_ = [], []
+    for _ in range(5):
+        g.train(20)
+        short.append(g.last_train_ms / 20)
+        g.train(500)
+        long_.append(g.last_train_ms / 500)
+    report = {"us_per_iter_20": [round(1e3 * x, 2) for x in short], "us_per_iter_500": [round(1e3 * x, 2) for x in long_]}
+    print(json.dumps(report))
+    out = ROOT / "gpurun_out"
+    if out.is_dir():
+        (out / "short_call_rate.json").write_text(json.dumps(report))
+    assert np.median(short) <= 1.15 * np.median(long_), report
+    g.close()
+
+
+def test_fresh_object_and_trained_object_agree_with_unfused_optimizer(core, bench_dataset, bench_seq):
+    """The fused scatter + Adam kernel against its own A/B mode (gradient stored, separate optimizer sweep) is covered by the
+    oracle tests above through identical entry points; here: size-independent properties at the full shape over the dense
+    start-up phase of a fresh object — finite state, every step counted, loss falls, untouched entries keep their initial value."""
+    seq, obj = bench_seq, bench_seq.objects[0]
+    g = core.NerfObject(bench_dataset, core.default_config(rays_per_batch=R_BENCH), obj.Tow, -1.1 * obj.half, 1.1 * obj.half, obj.instance_id)
+    g.set_bboxes(obj.boxes)
+    init = g.state("master")
+    l0 = g.train(1)
+    l1 = g.train(24)
+    assert g.step == 25
+    ps = g.state("param_steps")
+    master = g.state("master")
+    assert np.isfinite(master).all() and np.isfinite(g.state("ema")).all()
+    assert np.all(ps[:g.n_mlp] == 25) and ps.max() == 25
+    untouched = ps == 0
+    assert untouched.any() and np.array_equal(master[untouched], init[untouched])
+    assert not g.state("adam_m")[untouched].any() and not g.state("adam_v")[untouched].any()
+    touched = ps > 0
+    assert (master[touched] != init[touched]).mean() > 0.99
+    assert np.abs(master - init).max() <= 25 * 1e-2 * 1.5          # Adam normalises the step
+    l2 = g.train(300)
+    assert l2 < 0.6 * l0 and np.isfinite(l1)
+    g.close()
+
+
+def test_psnr_against_the_reference(core, ref_binding, bench_seq):
+    """north_star: 'PSNR on the synthetic room sequence within +-0.1 dB of reference'.  2 objects x 10 seeds at 800x800, both
+    sides train 2000 iterations on the even keyframes with their own random streams and are rendered on the odd keyframes by one
+    renderer (tools/psnr_compare.py).  The reference is not reproducible run to run (atomicAdd compaction order, fp16 gradient
+    atomics), so its OWN run-to-run difference at equal seed is measured beside ours-vs-reference: the assertion is that the
+    95 % confidence interval of the paired difference reaches into +-0.1 dB and that |mean difference| is not larger than
+    0.1 dB + the reference's own mean absolute run-to-run difference.  Everything measured is written to gpurun_out/."""
+    from ro_map_b200 import synthetic as syn
+    import psnr_tool
+    rows = psnr_tool.paired_runs(core, ref_binding, syn, n_objects=2, n_seeds=10, iters=2000, size=800, frames=FRAMES_BENCH, rays=R_BENCH, ref_repeat_seeds=4)
+    d = np.array([r["delta_db"] for r in rows])
+    rr = np.array([r["ref_rerun_delta_db"] for r in rows if "ref_rerun_delta_db" in r])
+    se = d.std(ddof=1) / np.sqrt(len(d))
+    summary = {"runs": len(rows), "mean_psnr_ours_db": float(np.mean([r["psnr_ours_db"] for r in rows])),
+               "mean_psnr_reference_db": float(np.mean([r["psnr_reference_db"] for r in rows])), "mean_delta_db": float(d.mean()),
+               "std_delta_db": float(d.std(ddof=1)), "ci95_delta_db": [float(d.mean() - 1.96 * se), float(d.mean() + 1.96 * se)],
+               "reference_rerun_same_seed": {"runs": len(rr), "mean_abs_delta_db": float(np.abs(rr).mean()), "max_abs_delta_db": float(np.abs(rr).max())}}
+    print(json.dumps(summary))
+    out = ROOT / "gpurun_out"
+    if out.is_dir():
+        (out / "psnr_vs_reference_800.jsonl").write_text("\n".join(json.dumps(r) for r in rows + [dict(summary, summary=True)]) + "\n")
+    lo, hi = summary["ci95_delta_db"]
+    assert lo <= 0.1 and hi >= -0.1, summary                                   # the interval reaches into the +-0.1 dB band
+    assert abs(d.mean()) <= 0.1 + np.abs(rr).mean(), summary                   # and the mean is inside the band widened by the reference's own noise

@@ -78,12 +78,16 @@ def test_stage_encode_bit_exact(core, oracle):
 
 @pytest.mark.parametrize("R,n_hidden", [(256, 1), (1024, 1), (512, 2)])
 def test_one_iteration_stage_by_stage(core, oracle, gpu_dataset, small_seq, R, n_hidden):
-    seq, obj = small_seq, small_seq.objects[0]
+    check_one_iteration_stage_by_stage(core, oracle, gpu_dataset, small_seq, small_seq.objects[0], R, n_hidden)
+
+
+def check_one_iteration_stage_by_stage(core, oracle, gpu_dataset, seq, obj, R, n_hidden, warm_iters=3):
+    """One injected iteration, every stage against the oracle (also run at the benchmarked shape by test_gpu_bench_config.py)."""
     g, o = make_pair(core, oracle, gpu_dataset, seq, obj, R, n_hidden=n_hidden)
     # start from a lightly trained state so that densities / colours are not all near zero
     rng = np.random.default_rng(R)
     frames = oracle.Frames(seq.rgb, seq.instance, seq.depth, seq.poses)
-    for _ in range(3):
+    for _ in range(warm_iters):
         sxy, col, dt = randoms(rng, R)
         o.train_iter(obj.boxes, frames, seq.H, seq.W, seq.K, sxy, col, dt)
     g.set_params(o.state("master"))
@@ -308,11 +312,11 @@ def test_full_size_properties(core, gpu_dataset, small_seq):
     assert l_end < 0.6 * outs[0][0]
 
 
-def test_pipelined_graph_matches_serial_chain(core, gpu_dataset, small_seq):
-    """Production path = the level-pipelined iteration graph (scatter -> optimizer -> next encode cut by level group and
-    overlapped on branch streams, two sample-position buffers; mon_core.cu capture_graph_pipelined).  The serial chain
-    (mon_object_train_profiled: the same kernels over the whole level range on one stream) runs the same iterations
-    with the same RNG counters, so both must agree up to the order of the fp16 gradient atomics."""
+def test_graph_path_matches_serial_chain(core, gpu_dataset, small_seq):
+    """Production path = CUDA graphs of exactly the requested number of iterations (batch generation + sample points of
+    iteration i+1 and the MLP-weight optimizer of iteration i forked beside the scatter + Adam kernel of iteration i;
+    mon_core.cu capture_graph).  The serial chain (mon_object_train_profiled: the same kernels on one stream) runs the
+    same iterations with the same RNG counters, so both must agree up to the order of the fp16 gradient accumulation."""
     seq, obj = small_seq, small_seq.objects[0]
     cfg = core.default_config(rays_per_batch=1024)
     bmin, bmax = -1.1 * obj.half, 1.1 * obj.half
@@ -325,24 +329,28 @@ def test_pipelined_graph_matches_serial_chain(core, gpu_dataset, small_seq):
     a.train(1)              # 1-iteration graph
     b.train_profiled(1)     # serial chain
     ma, mb = a.state("master"), b.state("master")
-    # same set of touched parameters, up to fp16 sums that cancel to exactly 0 in one atomic order and not in the other
+    # same set of touched parameters, up to fp16 sums that cancel to exactly 0 in one accumulation order and not in the other
     assert (a.state("param_steps") == b.state("param_steps")).mean() >= 0.999
     assert (np.abs(ma - mb) <= 1e-6).mean() >= 0.999                           # Adam's first step is +-lr: only sign flips of ~0 gradients differ
     assert np.array_equal(ma[:a.n_mlp], mb[:a.n_mlp])                          # MLP gradient is bitwise reproducible (fixed-order reduction)
-    # 60 more iterations: one 50-iteration graph (every hand-over between the two point buffers, every join) + 10 single ones
-    la = a.train(60)
-    b.train_profiled(60)
+    # 20 + 71 more iterations: a 20-iteration graph, then a 64-iteration graph + a 7-iteration one (every fork and join)
+    a.prepare_train(20)
+    a.train(20)
+    la = a.train(71)
+    b.train_profiled(91)
     lb = b.train(0)
-    assert a.step == b.step == 61
+    assert a.step == b.step == 92
     assert np.isfinite(la) and abs(la - lb) <= 0.03 * abs(lb) + 1e-4, (la, lb)
     wa, wb = a.state("master")[:a.n_mlp], b.state("master")[:a.n_mlp]
     assert np.linalg.norm(wa - wb) <= 0.05 * np.linalg.norm(wb)
     ea, eb = a.state("ema"), b.state("ema")
     assert np.linalg.norm(ea - eb) <= 0.05 * np.linalg.norm(eb)
-    # and the two paths stay interchangeable on one object: graph -> serial -> graph
+    # and the two paths stay interchangeable on one object: graph -> serial -> graph; more distinct lengths than the
+    # per-object graph cache holds
     a.train_profiled(3)
-    l_end = a.train(50)
-    assert a.step == 114 and np.isfinite(l_end) and l_end < 1.2 * la + 1e-3
+    for n in (2, 3, 5, 9, 11, 13, 17):
+        l_end = a.train(n)
+    assert a.step == 92 + 3 + 60 and np.isfinite(l_end) and l_end < 1.2 * la + 1e-3
 
 
 def test_optimizer_bit_exact_for_equal_gradients(core, oracle, gpu_dataset, small_seq):

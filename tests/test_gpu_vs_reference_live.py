@@ -49,9 +49,16 @@ def _sorted_by_ray(rays):
 
 @pytest.mark.parametrize("n_hidden", [1, 2])
 def test_one_iteration_and_render_against_the_reference(core, oracle, ref_binding, small_seq, n_hidden):
+    run_live_parity(core, oracle, ref_binding, small_seq, small_seq.objects[0], 256, n_hidden, f"live_parity_vs_reference_nh{n_hidden}")
+
+
+def run_live_parity(core, oracle, ref_binding, seq, obj, R, n_hidden, report_name, all_survive=True, warm_iters=300):
+    """One Train_Step iteration + one Render, reference library vs the CUDA path, same inputs (see the module docstring).
+    all_survive=False: pixels are drawn freely, some slots die (corner of the 2-D box outside the 3-D box, occlusion) and the
+    batch is padded by roll-over; WHICH rays are repeated is the reference's atomicAdd race, so per-ray results are compared
+    ray by ray and the batch-level sums (loss, gradients) only loosely."""
     import test_golden_romap as tg
-    seq, obj = small_seq, small_seq.objects[0]
-    R, S, S2 = 256, 32, 64
+    S, S2 = 32, 64
     bmin, bmax = -1.1 * obj.half, 1.1 * obj.half
     ds = core.Dataset(0, *seq.K, seq.H, seq.W, len(seq.poses), True)
     for i in range(len(seq.poses)):
@@ -61,7 +68,7 @@ def test_one_iteration_and_render_against_the_reference(core, oracle, ref_bindin
     r = ref_binding.RefModel(n_hidden, 1337)
     assert r.is_genuine(), "the reference library must contain RO-MAP's own kernels"
     r.scene(seq.rgb, seq.instance, seq.depth, seq.poses, seq.H, seq.W, seq.K, obj.boxes, obj.Tow, bmin, bmax, obj.instance_id, True, R)
-    report = {"n_hidden_layers": n_hidden}
+    report = {"n_hidden_layers": n_hidden, "rays_per_batch": R, "image": [seq.H, seq.W], "keyframes": len(seq.poses), "all_slots_survive": all_survive}
 
     # A12: parameter initialisation — the reference's Trainer(seed 1337) against ours, all 1.9 M values
     assert np.array_equal(r.get(0), g.state("master"))
@@ -70,7 +77,7 @@ def test_one_iteration_and_render_against_the_reference(core, oracle, ref_bindin
     # leaves Adam moments, step counters and the EMA untouched in both implementations)
     g0 = core.NerfObject(ds, g.cfg, obj.Tow, bmin, bmax, obj.instance_id, 1337)
     g0.set_bboxes(obj.boxes)
-    g0.train(300)
+    g0.train(warm_iters)
     master = g0.state("master")
     g0.close()
     g.set_params(master)
@@ -83,26 +90,43 @@ def test_one_iteration_and_render_against_the_reference(core, oracle, ref_bindin
     # every slot must survive (pixel not occluded, ray hits the object box): with n_in < R the batch is padded by repeating slots
     # 0 .. R-n_in-1, and WHICH rays those are is the reference's atomicAdd race — loss and gradients would then differ legitimately
     frames = oracle.Frames(seq.rgb, seq.instance, seq.depth, seq.poses)
-    sxy = np.zeros((R, 2), np.float32)
-    for i in range(R):
-        box = obj.boxes[i % len(obj.boxes)]
+    if all_survive:
+        sxy = np.zeros((R, 2), np.float32)
+        cand = u((R, 2))
+        todo = np.arange(R)
         for _ in range(200):
-            cand = u((1, 2))
-            if oracle.generate_rays(1, [box], frames, seq.H, seq.W, seq.K, obj.Tow, bmin, bmax, obj.instance_id, True, cand, col[:1])[0] == 1:
+            # slot i keeps its candidate if it survives on its own (box i % n_boxes)
+            alive = np.zeros(len(todo), bool)
+            for k, i in enumerate(todo):
+                alive[k] = oracle.generate_rays(1, [obj.boxes[i % len(obj.boxes)]], frames, seq.H, seq.W, seq.K, obj.Tow, bmin, bmax, obj.instance_id, True,
+                                                cand[i:i + 1], col[:1])[0] == 1
+            sxy[todo[alive]] = cand[todo[alive]]
+            todo = todo[~alive]
+            if len(todo) == 0:
                 break
+            cand[todo] = u((len(todo), 2))
         else:
             pytest.fail("no surviving pixel found for a slot")
-        sxy[i] = cand[0]
+    else:
+        sxy = u((R, 2))
     _, _, loss_r, n_in_r = r.train(1, (sxy, col, dt))
     loss_g, n_in_g = g.train_injected(sxy, col, dt)
-    assert n_in_g == n_in_r == R
-    n = R
+    assert n_in_g == n_in_r
+    assert (n_in_g == R) if all_survive else (0 < n_in_g < R)
+    n = n_in_g
 
     rays_g, rays_r = g.last("rays").reshape(R, 9), r.last(0, R * 9).reshape(R, 9)
     pg, pr = _sorted_by_ray(rays_g[:n]), _sorted_by_ray(rays_r[:n])
     assert tg.rays_close(rays_g[:n][pg], rays_r[:n][pr])                               # <= 8 ulp / 1.5e-6 (see test_golden_romap.rays_close)
     assert np.array_equal(g.last("ray_instance")[:n][pg], r.last(12, R)[:n][pr])
     assert np.array_equal(g.last("target").reshape(R, 3)[:n][pg], r.last(10, R * 3).reshape(R, 3)[:n][pr])   # pixels and the (constant) background colour
+
+    if not all_survive:
+        # fill_rollover_rays (nerf_model.cu:280-294): slot i >= n_in repeats slot i % n_in, on both sides
+        for rays in (rays_g, rays_r):
+            assert np.array_equal(rays[n:], rays[np.arange(n, R) % n])
+    # with padded slots the batch-level sums weigh a race-dependent subset of the rays twice on the reference side
+    lim_l2, lim_cos, lim_frac = (0.15, 0.995, 0.97) if all_survive else (0.45, 0.95, 0.90)
 
     # ---- measure everything first (the report is written before any tolerance is applied), then assert ----------------------
     checks = []   # (name, measured, limit, ok)
@@ -127,7 +151,7 @@ def test_one_iteration_and_render_against_the_reference(core, oracle, ref_bindin
     lg, lr = g.last("loss")[:n][pg], r.last(13, R)[:n][pr]
     check("loss_rays_max_abs_diff", np.abs(lg - lr).max(), 0.25)                          # measured 0.073 (the same single ray)
     report["loss"] = [float(loss_g), float(loss_r)]
-    check("loss_rel_diff", abs(loss_g - loss_r) / max(abs(loss_r), 1e-6), 8e-2)          # measured 7e-4 / 2.2e-2;        # SumLoss / R (R % 256 == 0)
+    check("loss_rel_diff", abs(loss_g - loss_r) / max(abs(loss_r), 1e-6), 8e-2 if all_survive else 0.15)          # measured 7e-4 / 2.2e-2;        # SumLoss / R (R % 256 == 0)
     # dL/dout (fp16, loss scale 128)
     do_g = g.last("dout").reshape(R, S, 4)[:n][pg]
     do_r = r.last(8, R * S * 16).reshape(R, S, 16)[:n][pr][:, :, :4]
@@ -140,26 +164,26 @@ def test_one_iteration_and_render_against_the_reference(core, oracle, ref_bindin
     blocks = [("W_in", 0, 64 * 32)] + [(f"W_h{i}", 64 * 32 + i * 4096, 64 * 32 + (i + 1) * 4096) for i in range(n_hidden - 1)] + [("W_out", n_mlp - 16 * 64, n_mlp)]
     for bname, lo, hi in blocks:
         a_, b_ = gg[lo:hi], gr[lo:hi]
-        check(f"grad_{bname}_rel_l2", np.linalg.norm(a_ - b_) / max(np.linalg.norm(b_), 1e-30), 0.15)
-        check(f"grad_{bname}_max_abs_rel_to_scale", np.abs(a_ - b_).max() / max(np.abs(b_).max(), 1e-30), 0.3)
+        check(f"grad_{bname}_rel_l2", np.linalg.norm(a_ - b_) / max(np.linalg.norm(b_), 1e-30), lim_l2)
+        check(f"grad_{bname}_max_abs_rel_to_scale", np.abs(a_ - b_).max() / max(np.abs(b_).max(), 1e-30), 0.3 if all_survive else 0.6)
         cos = float(np.dot(a_, b_) / max(np.linalg.norm(a_) * np.linalg.norm(b_), 1e-30))
-        check(f"grad_{bname}_cosine", cos, 0.995, ok=cos >= 0.995)                         # measured 0.9993 .. 0.99999 (rel. L2 0.4 - 3.8 %)
+        check(f"grad_{bname}_cosine", cos, lim_cos, ok=cos >= lim_cos)                         # measured 0.9993 .. 0.99999 (rel. L2 0.4 - 3.8 %)
     sup = ((gg[n_mlp:] != 0) == (gr[n_mlp:] != 0)).mean()
     check("grad_grid_support_agreement", sup, 0.98, ok=sup >= 0.98)                      # measured 0.9939 / 0.9960 (fp16 underflow of ~0 sums)
     touched = (gr[n_mlp:] != 0) & (gg[n_mlp:] != 0)
-    check("grad_grid_rel_l2", np.linalg.norm((gg[n_mlp:] - gr[n_mlp:])[touched]) / np.linalg.norm(gr[n_mlp:][touched]), 0.15)   # measured 0.031 / 0.044
+    check("grad_grid_rel_l2", np.linalg.norm((gg[n_mlp:] - gr[n_mlp:])[touched]) / np.linalg.norm(gr[n_mlp:][touched]), lim_l2)   # measured 0.031 / 0.044
     gcos = float(np.dot(gg[n_mlp:], gr[n_mlp:]) / (np.linalg.norm(gg[n_mlp:]) * np.linalg.norm(gr[n_mlp:])))
-    check("grad_grid_cosine", gcos, 0.995, ok=gcos >= 0.995)                              # measured 0.9990 / 0.9995
+    check("grad_grid_cosine", gcos, lim_cos, ok=gcos >= lim_cos)                              # measured 0.9990 / 0.9995
 
     # after the optimizer step: fp32 master weights.  The FIRST Adam step moves every touched parameter by lr * sign(gradient) = 1e-2
     # whatever the magnitude, so entries whose ~0 gradient differs in sign (or in being touched at all) end 1e-2 .. 2e-2 apart and
     # everything else agrees to rounding
     dm = np.abs(g.state("master") - r.get(0))
     frac = float((dm <= 1e-5).mean())
-    check("master_fraction_within_1e-5", frac, 0.97, ok=frac >= 0.97)                    # measured 0.9928 / 0.9941
+    check("master_fraction_within_1e-5", frac, lim_frac, ok=frac >= lim_frac)                    # measured 0.9928 / 0.9941
     check("master_max_abs_diff", dm.max(), 2.5e-2)
     frac_mlp = float((dm[:n_mlp] <= 1e-5).mean())
-    check("master_mlp_fraction_within_1e-5", frac_mlp, 0.95, ok=frac_mlp >= 0.95)        # measured 0.9967 / 0.9876
+    check("master_mlp_fraction_within_1e-5", frac_mlp, 0.95 if all_survive else 0.85, ok=frac_mlp >= (0.95 if all_survive else 0.85))        # measured 0.9967 / 0.9876
 
     # Render (EMA weights after that one step) of a window across the object's edge, same injected jitter
     fid, x, y, h, w = [int(v) for v in obj.boxes[0]]
@@ -180,10 +204,35 @@ def test_one_iteration_and_render_against_the_reference(core, oracle, ref_bindin
     check("render_psnr_db", psnr, 40.0, ok=psnr >= 40.0)                                # between the two renders; measured 52.8 / 51.4 dB
     check("render_depth_mean_abs_diff", np.abs(dep_g - rr["depth"])[same].mean(), 5e-3)   # measured 3e-4
 
+    # one view of RenderVideo (nerf_model.cu:1832-1991): the reference's GenerateRenderVideoRays with a turn-table pose from its own
+    # GenerateToc against mon_object_render_object_centric, same EMA weights, same injected jitter; a strip across the image centre
+    # (the turn-table camera looks at the object origin) wide enough to leave the object on both sides
+    radius = float(6.0 * np.max(obj.half))
+    for theta in (6.0, 132.0, 306.0):
+        Toc = r.generate_toc(theta, 30.0, radius)
+        vh, vw = 8, min(seq.W, 4 * (int(2.6 * seq.K[0] * float(np.max(obj.half)) / radius) // 4 + 8))
+        vbox = (0, seq.W // 2 - vw // 2, seq.H // 2 - vh // 2, vh, vw)
+        jit = u((vh * vw, S2))
+        vr = r.render2(vbox, Toc, object_centric=True, rand_dt=jit, want_rays=True)
+        v_rgb, v_dep, v_mask = g.render(vbox, Toc, use_ema=True, rand_dt=jit, object_centric=True)
+        v_rgb, v_dep, v_mask = v_rgb.reshape(-1, 3), v_dep.reshape(-1), v_mask.reshape(-1)
+        vhit = vr["in_box"] == 1
+        tag = f"video_theta{int(theta)}"
+        report[tag + "_rays_hit_miss"] = [int(vhit.sum()), int((~vhit).sum())]
+        check(tag + "_misses_white", 0.0 if bool((v_rgb[~vhit] == 1.0).all() and not v_dep[~vhit].any() and not v_mask[~vhit].any()) else 1.0, 0.0)
+        vsame = v_mask == vr["mask"]
+        check(tag + "_mask_agreement", vsame.mean(), 0.98, ok=vsame.mean() >= 0.98)
+        report[tag + "_opaque_fraction"] = float(vr["mask"].mean())
+        vmse = float(((v_rgb - vr["rgb"])[vsame] ** 2).mean())
+        vpsnr = float(-10 * np.log10(max(vmse, 1e-12)))
+        check(tag + "_psnr_db", vpsnr, 40.0, ok=vpsnr >= 40.0)
+        check(tag + "_depth_mean_abs_diff", np.abs(v_dep - vr["depth"])[vsame].mean(), 5e-3)
+        assert 0 < vhit.sum() < vhit.size, (tag, int(vhit.sum()), vhit.size)
+
     report["failed"] = [c[0] for c in checks if not c[3]]
     out = ROOT / "gpurun_out"
     if out.is_dir():
-        (out / f"live_parity_vs_reference_nh{n_hidden}.json").write_text(json.dumps(report, indent=1))
+        (out / f"{report_name}.json").write_text(json.dumps(report, indent=1))
     print(json.dumps(report))
     g.close()
     r.close()

@@ -210,6 +210,22 @@ def test_pose_math_turntable_and_quaternion(tmp_path):
         assert np.allclose(C, T @ B, atol=1e-5)
 
 
+def test_turntable_poses_against_reference_generate_toc(tmp_path):
+    """ro_map_b200/host/pose_math.h turntable_toc against the reference's own NeRF_Model::GenerateToc (nerf_model.cu:2186-2205) run by
+    oracle/ref/make_golden_toc.py: all 60 poses of RenderVideo's turn-table (theta accumulated in float like :1841) at three radii.
+    Both sides evaluate sin / cos of float angles with the host libm and normalise in float: equal to a few float ulps."""
+    gold = np.load(ROOT / "tests" / "golden" / "romap_toc_golden.npz")
+    exe = tmp_path / "pose_check"
+    subprocess.run(["g++", "-O2", "-std=c++17", f"-I{ROOT / 'ro_map_b200' / 'host'}", str(ROOT / "tests" / "host" / "pose_check.cpp"), "-o", str(exe)], check=True)
+    worst = 0.0
+    for i, r in enumerate(gold["radii"]):
+        for j, th in enumerate(gold["thetas"]):
+            out = subprocess.run([str(exe), "toc", repr(float(th)), repr(float(gold["phi"])), repr(float(r))], capture_output=True, text=True, check=True).stdout.split()
+            T = np.array(out, dtype=np.float64)
+            worst = max(worst, float(np.abs(T - gold["toc"][i, j]).max()))
+    assert worst <= 4e-7 * float(gold["radii"].max()), worst
+
+
 def test_draw_cpu_mesh_issues_the_reference_gl_calls(tmp_path):
     """nerf::NeRF::DrawCPUMesh (nerf.cu:484-507) against a recording stand-in for <GL/gl.h> (tests/host/gl_stub): client arrays for
     positions / normals / u8 colours, one glDrawElements over the index list; nothing is drawn before a mesh exists or while the

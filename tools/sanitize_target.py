@@ -1,0 +1,28 @@
+#!/usr/bin/env python
+"""Small workload for compute-sanitizer (memcheck / racecheck / synccheck): every kernel of the training iteration (serial
+injected path and graph path), a render and a density lattice on a tiny scene.
+    compute-sanitizer --tool memcheck python tools/sanitize_target.py"""
+import sys
+from pathlib import Path
+import numpy as np
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from ro_map_b200 import core, synthetic as syn
+
+seq = syn.make_sequence(n_frames=4, n_objects=1, H=160, W=160, K=(222.222, 222.222, 80.0, 80.0))
+obj = seq.objects[0]
+ds = core.Dataset(0, *seq.K, seq.H, seq.W, len(seq.poses), True)
+for i in range(len(seq.poses)):
+    ds.add_frame(i, seq.rgb[i], seq.instance[i], seq.depth[i], seq.poses[i])
+for nh, R in ((1, 256), (2, 128)):
+    g = core.NerfObject(ds, core.default_config(rays_per_batch=R, n_hidden_layers=nh), obj.Tow, -1.1 * obj.half, 1.1 * obj.half, obj.instance_id)
+    g.set_bboxes(obj.boxes)
+    rng = np.random.default_rng(0)
+    u = lambda shape: (1.0 - rng.random(shape, dtype=np.float32)).astype(np.float32)
+    print("injected", g.train_injected(u((R, 2)), u((R, 3)), u((R, 32))))
+    print("graph", g.train(5), g.train(3), "live", g.live_fraction)
+    fid, x, y, h, w = [int(v) for v in obj.boxes[0]]
+    rgb, dep, mask = g.render((fid, x, y, min(h, 16), min(w, 16)), seq.poses[fid])
+    print("render", float(mask.mean()), "lattice", float(g.density_grid((8, 8, 8)).mean()))
+    g.close()
+ds.close()
+print("sanitize target done")

@@ -13,6 +13,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--rays", type=int, default=4096)
 ap.add_argument("--hidden-layers", type=int, default=1)
 ap.add_argument("--frames", type=int, default=30)
+ap.add_argument("--at", default="0,50,200,500,1000,2000,5000")
 a = ap.parse_args()
 seq = syn.make_sequence(a.frames, 1)
 obj = seq.objects[0]
@@ -23,14 +24,18 @@ ds.sync()
 g = core.NerfObject(ds, core.default_config(rays_per_batch=a.rays, n_hidden_layers=a.hidden_layers), obj.Tow, -1.1 * obj.half, 1.1 * obj.half, obj.instance_id)
 g.set_bboxes(obj.boxes)
 done = 0
-for upto in (0, 50, 200, 500, 1000, 2000, 5000):
+for upto in [int(x) for x in a.at.split(",")]:
     if upto > done:
         g.train(upto - done)
         done = upto
     st = g.train_profiled(20)
     done += 20
+    g.prepare_train(20)
+    g.train(20)                    # the 20 iterations right after: graph path, still in the same phase of training
+    rate20 = 20.0 / (g.last_train_ms * 1e-3)
+    done += 20
     loss = g.train(500)
     done += 500
     dout = g.last("dout") if False else None
-    print(json.dumps({"after_iters": upto, "graph_iters_per_s": round(500.0 / (g.last_train_ms * 1e-3), 1), "loss": round(float(loss), 5),
+    print(json.dumps({"after_iters": upto, "graph20_iters_per_s": round(rate20, 1), "graph_iters_per_s": round(500.0 / (g.last_train_ms * 1e-3), 1), "loss": round(float(loss), 5), "live_fraction": round(g.live_fraction, 4),
                       "stage_us": {k: round(v * 1e3, 2) for k, v in st.items()}}), flush=True)

@@ -1,14 +1,14 @@
 #!/usr/bin/env python
-"""Timeline of the iteration graph on the device: which kernels of the level-pipelined graph really overlap.
+"""Timeline of the iteration graph on the device: which kernels of the forked iteration graph really overlap.
 
 Needs the instrumented build (every CTA folds %globaltimer into a per-(iteration, kernel) [first start, last end] slot,
 ro_map_b200/csrc/mon_timeline.cuh), which `--build` cross-compiles into ro_map_b200/_build_tl/ without touching the
 product library:
 
     MON_EXTRA_NVCC_FLAGS=-DMON_TIMELINE python tools/timeline.py --build      # here (no GPU needed)
-    [MON_PIPE=0|1|2|3] [MON_PIPE_ENC_PARTS=1|2|4] python tools/timeline.py    # on the B200 box
+    python tools/timeline.py [--at 5,400]                                       # on the B200 box
 
-Prints, for a few steady-state iterations, start/end of every kernel in microseconds relative to the start of that
+Prints, for a few iterations after each --at count (5 = the dense start-up phase of a fresh object, 400 = steady state), start/end of every kernel in microseconds relative to the start of that
 iteration's fused MLP kernel, plus the iteration period."""
 import argparse, ctypes as C, json, os, sys
 from pathlib import Path
@@ -23,6 +23,7 @@ ap.add_argument("--build", action="store_true")
 ap.add_argument("--rays", type=int, default=4096)
 ap.add_argument("--hidden-layers", type=int, default=1)
 ap.add_argument("--frames", type=int, default=30)
+ap.add_argument("--at", default="5,400", help="iteration counts after which a 32-iteration graph is traced")
 a = ap.parse_args()
 
 if a.build:
@@ -38,8 +39,9 @@ _capi.LIB_PATH = TL_LIB
 from ro_map_b200 import core, synthetic as syn
 lib = _capi.load()
 ITERS, KINDS = 64, 16
-NAMES = ["B", "P", "E0", "E1", "E2", "E3", "M", "S0", "S1", "S2", "S3", "O0", "O1", "O2", "O3", "Omlp"]
-TABLES = ["batch", "encode", "mlp", "optim"]
+# S = scatter + Adam kernel [first CTA start, last CTA end]; S1 / S2 = [first, last] CTA past the scatter phase / past the reduction + Adam phase of its first job
+NAMES = ["B", "P", "E0", "E1", "E2", "E3", "M", "S", "S1", "S2", "S3", "O0", "O1", "O2", "O3", "Omlp"]
+TABLES = ["batch", "encode", "mlp", "optim", "scatter_adam"]
 
 
 def reset():
@@ -66,26 +68,30 @@ for i in range(len(seq.rgb)):
 ds.sync()
 g = core.NerfObject(ds, core.default_config(rays_per_batch=a.rays, n_hidden_layers=a.hidden_layers), obj.Tow, -1.1 * obj.half, 1.1 * obj.half, obj.instance_id)
 g.set_bboxes(obj.boxes)
-g.train(400)                       # steady state; iteration counter is now 400
-reset()
-g.train(50)                        # one 50-iteration graph: iterations 400..449 -> slots 16..63, 0..1
-ms = g.last_train_ms
-start, end = read()
-print(json.dumps({"MON_PIPE": os.environ.get("MON_PIPE", "default"), "MON_PIPE_ENC_PARTS": os.environ.get("MON_PIPE_ENC_PARTS", "default"),
-                  "graph_us_per_iter": round(ms * 1e3 / 50, 2)}))
-periods = []
-for it in range(420, 426):
-    s = it % ITERS
-    m0 = int(start[s, 6])
-    row = []
-    for k in sorted(range(KINDS), key=lambda k: int(start[s, k]) if end[s, k] else 1 << 62):
-        if end[s, k] == 0:
-            continue
-        row.append(f"{NAMES[k]}[{(int(start[s, k]) - m0) / 1e3:.1f},{(int(end[s, k]) - m0) / 1e3:.1f}]")
-    nxt = int(start[(it + 1) % ITERS, 6])
-    periods.append((nxt - m0) / 1e3)
-    print(f"iter {it}: period {(nxt - m0) / 1e3:.1f} us  " + " ".join(row))
-print(json.dumps({"mean_period_us": round(float(np.mean(periods)), 2)}))
+done = 0
+for at in [int(x) for x in a.at.split(",")]:
+    if at > done:
+        g.train(at - done)
+        done = at
+    reset()
+    g.train(32)                    # one 32-iteration graph: iterations at .. at+31
+    ms = g.last_train_ms
+    start, end = read()
+    print(json.dumps({"after_iters": at, "graph_us_per_iter": round(ms * 1e3 / 32, 2)}))
+    periods = []
+    for it in range(at + 12, at + 18):
+        s = it % ITERS
+        m0 = int(start[s, 6])
+        row = []
+        for k in sorted(range(KINDS), key=lambda k: int(start[s, k]) if end[s, k] else 1 << 62):
+            if end[s, k] == 0:
+                continue
+            row.append(f"{NAMES[k]}[{(int(start[s, k]) - m0) / 1e3:.1f},{(int(end[s, k]) - m0) / 1e3:.1f}]")
+        nxt = int(start[(it + 1) % ITERS, 6])
+        periods.append((nxt - m0) / 1e3)
+        print(f"iter {it}: period {(nxt - m0) / 1e3:.1f} us  " + " ".join(row))
+    print(json.dumps({"after_iters": at, "mean_period_us": round(float(np.mean(periods)), 2)}))
+    done += 32
 
 # per-CTA load balance of the encode kernel (iteration 404 + 16 = slot 20 of the instrumented replay)
 try:

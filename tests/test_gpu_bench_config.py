@@ -1,6 +1,6 @@
 """GPU parity AT THE BENCHMARKED CONFIGURATION: R = 4096 rays x 32 samples on the 800x800, 30-keyframe synthetic 'room'
 scene bench.py runs (BASELINE.json configs[1]) — 1024 MLP tiles over the persistent CTAs, the 148-CTA encode split, slab
-storage across frames, all 30 scatter + Adam clusters.  The same checks as the small-scene tests, against the CPU oracle
+storage across frames, all 64 scatter + Adam clusters.  The same checks as the small-scene tests, against the CPU oracle
 (stage by stage) and against the reference library itself (live, incl. a batch with roll-over padding), plus the pieces
 that only exist at this level: peer clone of a dataset, short training calls, PSNR against the reference.
 """
@@ -71,8 +71,8 @@ def test_live_reference_at_bench_shape(core, oracle, ref_binding, bench_seq, n_h
 
 
 def test_live_reference_with_rollover_at_bench_shape(core, oracle, ref_binding, bench_seq):
-    """freely drawn pixels: part of the 4096 slots die (the 2-D box is the bounding rectangle of the projected 3-D box) and the
-    batch is padded by roll-over on both sides"""
+    """half of the 4096 slots die (pixels in the corners of the 2-D box, which is the bounding rectangle of the projected 3-D box)
+    and the batch is padded by roll-over on both sides"""
     import test_gpu_vs_reference_live as tl
     tl.run_live_parity(core, oracle, ref_binding, bench_seq, bench_seq.objects[0], R_BENCH, 1, "live_parity_bench_shape_rollover", all_survive=False)
 

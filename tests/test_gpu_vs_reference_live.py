@@ -54,9 +54,9 @@ def test_one_iteration_and_render_against_the_reference(core, oracle, ref_bindin
 
 def run_live_parity(core, oracle, ref_binding, seq, obj, R, n_hidden, report_name, all_survive=True, warm_iters=300):
     """One Train_Step iteration + one Render, reference library vs the CUDA path, same inputs (see the module docstring).
-    all_survive=False: pixels are drawn freely, some slots die (corner of the 2-D box outside the 3-D box, occlusion) and the
-    batch is padded by roll-over; WHICH rays are repeated is the reference's atomicAdd race, so per-ray results are compared
-    ray by ray and the batch-level sums (loss, gradients) only loosely."""
+    all_survive=False: every second slot dies (corner of the 2-D box outside the 3-D box) and the batch is padded by roll-over
+    (fill_rollover_rays) on both sides; with n_in = R / 2 every surviving ray is used exactly twice whatever the compaction
+    order, so loss and gradients remain comparable although the reference's slot order is an atomicAdd race."""
     import test_golden_romap as tg
     S, S2 = 32, 64
     bmin, bmax = -1.1 * obj.half, 1.1 * obj.half
@@ -90,29 +90,34 @@ def run_live_parity(core, oracle, ref_binding, seq, obj, R, n_hidden, report_nam
     # every slot must survive (pixel not occluded, ray hits the object box): with n_in < R the batch is padded by repeating slots
     # 0 .. R-n_in-1, and WHICH rays those are is the reference's atomicAdd race — loss and gradients would then differ legitimately
     frames = oracle.Frames(seq.rgb, seq.instance, seq.depth, seq.poses)
-    if all_survive:
-        sxy = np.zeros((R, 2), np.float32)
-        cand = u((R, 2))
-        todo = np.arange(R)
-        for _ in range(200):
-            # slot i keeps its candidate if it survives on its own (box i % n_boxes)
-            alive = np.zeros(len(todo), bool)
-            for k, i in enumerate(todo):
-                alive[k] = oracle.generate_rays(1, [obj.boxes[i % len(obj.boxes)]], frames, seq.H, seq.W, seq.K, obj.Tow, bmin, bmax, obj.instance_id, True,
-                                                cand[i:i + 1], col[:1])[0] == 1
-            sxy[todo[alive]] = cand[todo[alive]]
-            todo = todo[~alive]
-            if len(todo) == 0:
-                break
-            cand[todo] = u((len(todo), 2))
-        else:
-            pytest.fail("no surviving pixel found for a slot")
+    # all_survive: every slot's pixel is re-drawn until its ray survives.  Otherwise: exactly every second slot survives and the
+    # others die, so that n_in = R / 2 and the roll-over padding (slot i >= n_in repeats slot i % n_in) uses every surviving ray
+    # exactly twice WHATEVER the compaction order was: sums over the batch stay independent of the reference's race
+    want = np.ones(R, bool) if all_survive else (np.arange(R) % 2 == 0)
+    sxy = np.zeros((R, 2), np.float32)
+    cand = u((R, 2))
+    todo = np.arange(R)
+    for _ in range(400):
+        alive = np.zeros(len(todo), bool)
+        for k, i in enumerate(todo):
+            alive[k] = oracle.generate_rays(1, [obj.boxes[i % len(obj.boxes)]], frames, seq.H, seq.W, seq.K, obj.Tow, bmin, bmax, obj.instance_id, True,
+                                            cand[i:i + 1], col[:1])[0] == 1
+        ok = alive == want[todo]
+        sxy[todo[ok]] = cand[todo[ok]]
+        todo = todo[~ok]
+        if len(todo) == 0:
+            break
+        cand[todo] = u((len(todo), 2))
+        if not all_survive:
+            # dead slots are rare under uniform sampling (the 2-D box hugs the 3-D box): aim at the corners of the rectangle
+            dead = ~want[todo]
+            cand[todo[dead]] = np.where(u((int(dead.sum()), 2)) < 0.5, 0.002, 0.998).astype(np.float32) * u((int(dead.sum()), 2)) ** 0.05
     else:
-        sxy = u((R, 2))
+        pytest.fail(f"no pixel with the wanted fate found for {len(todo)} slots")
     _, _, loss_r, n_in_r = r.train(1, (sxy, col, dt))
     loss_g, n_in_g = g.train_injected(sxy, col, dt)
     assert n_in_g == n_in_r
-    assert (n_in_g == R) if all_survive else (0 < n_in_g < R)
+    assert n_in_g == (R if all_survive else R // 2)
     n = n_in_g
 
     rays_g, rays_r = g.last("rays").reshape(R, 9), r.last(0, R * 9).reshape(R, 9)
@@ -125,8 +130,7 @@ def run_live_parity(core, oracle, ref_binding, seq, obj, R, n_hidden, report_nam
         # fill_rollover_rays (nerf_model.cu:280-294): slot i >= n_in repeats slot i % n_in, on both sides
         for rays in (rays_g, rays_r):
             assert np.array_equal(rays[n:], rays[np.arange(n, R) % n])
-    # with padded slots the batch-level sums weigh a race-dependent subset of the rays twice on the reference side
-    lim_l2, lim_cos, lim_frac = (0.15, 0.995, 0.97) if all_survive else (0.45, 0.95, 0.90)
+    lim_l2, lim_cos, lim_frac = 0.15, 0.995, 0.97
 
     # ---- measure everything first (the report is written before any tolerance is applied), then assert ----------------------
     checks = []   # (name, measured, limit, ok)
@@ -151,7 +155,7 @@ def run_live_parity(core, oracle, ref_binding, seq, obj, R, n_hidden, report_nam
     lg, lr = g.last("loss")[:n][pg], r.last(13, R)[:n][pr]
     check("loss_rays_max_abs_diff", np.abs(lg - lr).max(), 0.25)                          # measured 0.073 (the same single ray)
     report["loss"] = [float(loss_g), float(loss_r)]
-    check("loss_rel_diff", abs(loss_g - loss_r) / max(abs(loss_r), 1e-6), 8e-2 if all_survive else 0.15)          # measured 7e-4 / 2.2e-2;        # SumLoss / R (R % 256 == 0)
+    check("loss_rel_diff", abs(loss_g - loss_r) / max(abs(loss_r), 1e-6), 8e-2)          # measured 7e-4 / 2.2e-2;        # SumLoss / R (R % 256 == 0)
     # dL/dout (fp16, loss scale 128)
     do_g = g.last("dout").reshape(R, S, 4)[:n][pg]
     do_r = r.last(8, R * S * 16).reshape(R, S, 16)[:n][pr][:, :, :4]
@@ -165,7 +169,7 @@ def run_live_parity(core, oracle, ref_binding, seq, obj, R, n_hidden, report_nam
     for bname, lo, hi in blocks:
         a_, b_ = gg[lo:hi], gr[lo:hi]
         check(f"grad_{bname}_rel_l2", np.linalg.norm(a_ - b_) / max(np.linalg.norm(b_), 1e-30), lim_l2)
-        check(f"grad_{bname}_max_abs_rel_to_scale", np.abs(a_ - b_).max() / max(np.abs(b_).max(), 1e-30), 0.3 if all_survive else 0.6)
+        check(f"grad_{bname}_max_abs_rel_to_scale", np.abs(a_ - b_).max() / max(np.abs(b_).max(), 1e-30), 0.3)
         cos = float(np.dot(a_, b_) / max(np.linalg.norm(a_) * np.linalg.norm(b_), 1e-30))
         check(f"grad_{bname}_cosine", cos, lim_cos, ok=cos >= lim_cos)                         # measured 0.9993 .. 0.99999 (rel. L2 0.4 - 3.8 %)
     sup = ((gg[n_mlp:] != 0) == (gr[n_mlp:] != 0)).mean()
@@ -183,7 +187,7 @@ def run_live_parity(core, oracle, ref_binding, seq, obj, R, n_hidden, report_nam
     check("master_fraction_within_1e-5", frac, lim_frac, ok=frac >= lim_frac)                    # measured 0.9928 / 0.9941
     check("master_max_abs_diff", dm.max(), 2.5e-2)
     frac_mlp = float((dm[:n_mlp] <= 1e-5).mean())
-    check("master_mlp_fraction_within_1e-5", frac_mlp, 0.95 if all_survive else 0.85, ok=frac_mlp >= (0.95 if all_survive else 0.85))        # measured 0.9967 / 0.9876
+    check("master_mlp_fraction_within_1e-5", frac_mlp, 0.95, ok=frac_mlp >= 0.95)        # measured 0.9967 / 0.9876
 
     # Render (EMA weights after that one step) of a window across the object's edge, same injected jitter
     fid, x, y, h, w = [int(v) for v in obj.boxes[0]]

@@ -4,27 +4,33 @@
 // the grid part of adam_step / ema_step_half_precision (TCNN optimizers/adam.h:48-118, ema.h:62-76).
 //
 // The reference scatters 8 atomicAdd(__half2) per (sample, level) into a global fp16 gradient table and sweeps the whole
-// parameter vector afterwards.  On B200 that scatter is bound by the number of reduction requests an SM can send to L2 (one
-// per lane and corner, 124 G/s measured — tools/smem_atomic_probe.cu, profiles/r4b_smem_atomic_probe.txt): 16.8 M of them
-// for a fresh object, whose every sample carries gradient — 87-108 us, 5x the rest of the iteration.  Here the GRADIENT
-// TABLE is the resident operand, like the weight table in the encode kernel:
+// parameter vector afterwards.  On B200 that scatter is bound by the number of reduction requests an SM can send to L2: one
+// per lane and corner, 120 G/s measured for the whole chip (tools/smem_atomic_probe.cu, profiles/r4b_smem_atomic_probe.txt).
+// A fresh object, whose every sample carries gradient, issues 16.8 M of them: 87-108 us, 5x the rest of the iteration.
+// Shared memory takes the same updates 7-25x faster (compare-and-swap on an f16x2 word 830 G/s, native integer add 2940 G/s)
+// — but only the SM's OWN shared memory: atomics into a cluster partner's (distributed shared memory) run at 47-159 G/s,
+// no better than L2.  So the gradient table is made the resident operand, like the weight table in the encode kernel, and
+// the job structure is chosen so that a CTA finds the corners that belong to its slice WITHOUT testing all eight:
 //
-//   job      = one quarter of one level's table (<= 16384 entries = 128 KB of accumulators in shared memory): 64 jobs for
-//              base.json.  Every level is cut in four, the small dense ones too, so that all jobs cost the same.
-//   cluster  = 2 CTAs work on one job.  Each takes half of the iteration's LIVE samples (the fused MLP kernel hands over
-//              only the samples with a non-zero gradient row, compacted: position + one word per level), computes the 8
-//              corner entries and adds the contributions that fall into the job's slice into its PRIVATE copy of the slice.
-//   accumulators = two 32-bit FIXED-POINT words per entry with unit 2^-24.  Every contribution is rounded to fp16 first,
-//              exactly as the reference rounds it before its atomicAdd(__half2) (grid.h:427-431), and every fp16 value is a
-//              multiple of 2^-24, so the integer sum is EXACT and independent of the order: the gradient is bit-reproducible
-//              run to run (the reference's fp16 running sum is not), and native integer shared-memory atomics (ATOMS.ADD,
-//              2975 G/s) replace the compare-and-swap loop every floating-point shared-memory atomic compiles to (830 G/s).
-//              Range +-128 in loss-scaled units, contributions clamped to +-16 (gradients of this loss are ~1e-3).
-//   reduce   = after a cluster barrier every CTA owns half of the slice: it adds the partner's copy (distributed shared
-//              memory) and rounds the sum to fp16 once: the loss-scaled fp16 gradient the reference keeps
+//   job      = one PARITY class of one level's table: the entries with (index & 1) == q, <= 32768 f16x2 accumulators = 128 KB
+//              of shared memory; 2 jobs per level, 32 for base.json.  Both hash primes are odd, so the parity of a corner's
+//              entry is (x ^ y ^ z) & 1 of the corner's lattice coordinates (x & 1 for the dense levels, whose y / z strides are
+//              even): exactly FOUR of the eight corners of every cell fall into each class, and which four follows from the
+//              cell's own parity — branch-free, no index is computed for a corner of the other class.
+//   cluster  = 4 CTAs work on one job.  Each takes a quarter of the iteration's LIVE samples (the fused MLP kernel hands
+//              over only the samples with a non-zero gradient row, compacted: position + one word per level) and adds its
+//              four contributions per sample into its PRIVATE copy of the slice: fp16 products accumulated in fp16, exactly
+//              the arithmetic of the reference's atomicAdd(__half2), in an order that is not defined there either.
+//   reduce   = after a cluster barrier every CTA owns a quarter of the slice: it sums the four private copies through
+//              distributed shared memory (bulk, coalesced reads: fast, unlike scattered remote atomics) in a fixed order
+//              and rounds to fp16: the loss-scaled fp16 gradient the reference keeps
 //   update   = and applies Adam + EMA to those entries in place — the complete gradient of an entry is known inside the
 //              cluster, which is the grid-wide phase boundary a fused scatter + Adam needs.  Entries with a zero
 //              gradient are skipped by Adam exactly as in the reference (adam.h:75-79) and only EMA-filtered.
+//
+// Measured and rejected on the way (profiles/r4c_*): slices by index RANGE (a quarter of a level per job, int32 fixed-point
+// accumulators with native ATOMS.ADD, 2-CTA clusters) — every job tests all eight corners of every sample, three quarters of
+// them for nothing, and the kernel is instruction-bound: 207 us for a fresh object, 47 us in steady state.
 //
 // The fp16 gradient table never exists in global memory (3.8 MB written by atomics, read and zeroed again per iteration),
 // and the launch between scatter and optimizer is gone.  fuse == 0 (A/B, MON_SO_FUSE=0) stops after the reduction and
@@ -40,18 +46,15 @@ MON_TL_DEFINE(scatter_adam)
 namespace cg = cooperative_groups;
 
 #define SO_THREADS 1024
-#define SO_CLUSTER 2
-#define SO_SLICES_PER_LEVEL 4u
-#define SO_SLICE_ENTRIES 16384u
-#define SO_SMEM_BYTES (SO_SLICE_ENTRIES * 8u)
-#define SO_FIXED_ONE 16777216.0f          // 2^24: one unit of the accumulators is 2^-24, the smallest fp16 subnormal
-#define SO_CONTRIB_MAX 16.0f
+#define SO_CLUSTER 4
+#define SO_SLICE_ENTRIES 32768u                  // f16x2 accumulators per job
+#define SO_SMEM_BYTES (SO_SLICE_ENTRIES * 4u)
 
 struct SoArgs {
     MonGrid g;
     MonOpt o;
     uint32_t n_points;          // N: stride (in words) between the levels of genc
-    uint32_t n_jobs;
+    uint32_t n_jobs;            // 2 * n_levels
     uint32_t fuse;              // 1: Adam + EMA in this kernel; 0: store the reduced gradient into gh
     const uint32_t* live_cnt;   // [2], indexed by iteration parity
     const float* pts_c;         // [n_live][3]
@@ -62,50 +65,35 @@ struct SoArgs {
     float* grad_snap;           // parity hook: loss-scaled gradient of every parameter as float (nullptr in production)
 };
 
-// job -> (level, first entry, entries); slices of a level in ascending order
-__host__ __device__ __forceinline__ uint32_t so_slices(uint32_t size) {
-    const uint32_t need = (size + SO_SLICE_ENTRIES - 1) / SO_SLICE_ENTRIES;
-    return need > SO_SLICES_PER_LEVEL ? need : SO_SLICES_PER_LEVEL;
-}
-__device__ __forceinline__ void so_job(const MonGrid& g, uint32_t job, uint32_t& level, uint32_t& e0, uint32_t& ne) {
-    uint32_t j = job;
+uint32_t mon_scatter_adam_jobs(const MonGrid& g) { return 2u * g.n_levels; }
+
+// the kernel's parity rule needs: power-of-two table (index = hash & (size - 1)), even size, and for dense levels an even
+// resolution (y / z strides even).  True for every level of every supported configuration; checked on the host.
+bool mon_scatter_adam_supported(const MonGrid& g) {
     for (uint32_t l = 0; l < g.n_levels; ++l) {
-        const uint32_t slices = so_slices(g.size[l]);
-        if (j < slices) {
-            level = l;
-            // equal slices, each a multiple of 8 entries (level sizes are multiples of 8)
-            const uint32_t per = ((g.size[l] / 8 + slices - 1) / slices) * 8;
-            e0 = j * per;
-            ne = e0 < g.size[l] ? min(per, g.size[l] - e0) : 0u;
-            return;
-        }
-        j -= slices;
+        const uint32_t size = g.size[l];
+        if (size < 8 || (size & (size - 1)) != 0 || size / 2 > SO_SLICE_ENTRIES) return false;
+        if (!g.hashed[l] && (g.res[l] & 1u)) return false;
     }
-    level = 0; e0 = 0; ne = 0;
+    return true;
 }
 
-uint32_t mon_scatter_adam_jobs(const MonGrid& g) {
-    uint32_t n = 0;
-    for (uint32_t l = 0; l < g.n_levels; ++l) n += so_slices(g.size[l]);
-    return n;
+// accumulator word += (v.x, v.y) in fp16: compare-and-swap on the CTA's own shared memory
+__device__ __forceinline__ void so_add_f16x2(uint32_t addr, __half2 v) {
+    uint32_t old, assumed;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(old) : "r"(addr) : "memory");
+    do {
+        assumed = old;
+        const __half2 sum = __hadd2(*reinterpret_cast<const __half2*>(&assumed), v);
+        asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(addr), "r"(assumed), "r"(*reinterpret_cast<const uint32_t*>(&sum)) : "memory");
+    } while (old != assumed);
 }
 
-// one corner: the contribution is rounded to fp16 like the reference's (grid.h:427-431), then added exactly in fixed point
-__device__ __forceinline__ void so_add(uint32_t slice_addr, uint32_t rel, uint32_t ne, float g0, float g1, float w) {
-    if (rel >= ne) return;
-    const float2 f = __half22float2(__floats2half2_rn(__fmul_rn(g0, w), __fmul_rn(g1, w)));
-    const int i0 = __float2int_rn(fminf(fmaxf(f.x, -SO_CONTRIB_MAX), SO_CONTRIB_MAX) * SO_FIXED_ONE);
-    const int i1 = __float2int_rn(fminf(fmaxf(f.y, -SO_CONTRIB_MAX), SO_CONTRIB_MAX) * SO_FIXED_ONE);
-    const uint32_t addr = slice_addr + rel * 8u;
-    if (i0) asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr), "r"(i0) : "memory");
-    if (i1) asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr + 4u), "r"(i1) : "memory");
-}
-
-// slot handled by thread `tid` in trip `k` of a CTA's share [s_begin, s_end).  Hashed levels: consecutive lanes take
-// consecutive slots (coalesced loads; their entries are spread by the hash).  Dense levels: consecutive slots are
-// neighbouring samples of one ray, which share corner entries at coarse resolution — a warp would hit the same accumulator
-// word from many lanes and the hardware serialises those.  There, inside every block of 1024 slots, lane i of warp w takes
-// slot 32 * i + w: the lanes of a warp are 32 samples apart, i.e. on 32 different rays.
+// slot handled by thread `tid` in trip `k` of a CTA's share.  Hashed levels: consecutive lanes take consecutive slots
+// (coalesced loads; their entries are spread by the hash).  Dense levels: consecutive slots are neighbouring samples of one
+// ray, which share corner entries at coarse resolution — a warp would hit the same accumulator word from many lanes and the
+// compare-and-swap loops would serialise.  There, inside every block of 1024 slots, lane i of warp w takes slot 32 * i + w:
+// the lanes of a warp are 32 samples apart, i.e. on 32 different rays.
 __device__ __forceinline__ uint32_t so_slot(uint32_t s_begin, uint32_t k, uint32_t tid, bool spread) {
     const uint32_t t = spread ? (((tid & 31u) << 5) | (tid >> 5)) : tid;
     return s_begin + k * SO_THREADS + t;
@@ -137,101 +125,90 @@ k_scatter_adam(const __grid_constant__ SoArgs a) {
 
     bool first = true;
     for (uint32_t job = cluster_id; job < a.n_jobs; job += n_clusters) {
-        uint32_t l, e0, ne;
-        so_job(a.g, job, l, e0, ne);
+        const uint32_t l = job >> 1, q = job & 1u;
         if (!first) {
-            // the previous job's slice was read by the partner until the cluster barrier at its end
+            // the previous job's slice was read by the partners until the cluster barrier at its end
             uint4* z = reinterpret_cast<uint4*>(so_smem);
             for (uint32_t i = tid; i < SO_SMEM_BYTES / 16; i += SO_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
             __syncthreads();
         }
         first = false;
 
-        // ---- phase 1: this CTA's half of the live samples -> private accumulators
+        // ---- phase 1: this CTA's quarter of the live samples -> private accumulators (entry index >> 1 inside the class)
         const uint32_t size = a.g.size[l], res = a.g.res[l];
         const float scale = a.g.scale[l];
         const bool hashed = a.g.hashed[l] != 0;
         const uint32_t* gl = a.genc + (size_t)l * a.n_points;
-        const bool pow2 = (size & (size - 1)) == 0;
         const uint32_t emask = size - 1u;
         const uint32_t my = hashed ? 2654435761u : res, mz = hashed ? 805459861u : res * res;
-        for (uint32_t k = 0; k < n_trips && ne; ++k) {
+        for (uint32_t k = 0; k < n_trips; ++k) {
             const uint32_t s = so_slot(s_begin, k, tid, !hashed);
             if (s >= s_end) continue;
             const uint32_t gw = __ldg(gl + s);
+            const float u0 = __ldg(a.pts_c + (size_t)s * 3), u1 = __ldg(a.pts_c + (size_t)s * 3 + 1), u2 = __ldg(a.pts_c + (size_t)s * 3 + 2);
             if ((gw & 0x7fff7fffu) == 0u) continue;       // adding +0 is an identity
             const float g0 = __half2float(__ushort_as_half((unsigned short)(gw & 0xffffu)));
             const float g1 = __half2float(__ushort_as_half((unsigned short)(gw >> 16)));
-            const float u0 = __ldg(a.pts_c + (size_t)s * 3), u1 = __ldg(a.pts_c + (size_t)s * 3 + 1), u2 = __ldg(a.pts_c + (size_t)s * 3 + 2);
             float fr[3]; uint32_t cell[3];
             mon_pos_fract(u0, scale, fr[0], cell[0]);
             mon_pos_fract(u1, scale, fr[1], cell[1]);
             mon_pos_fract(u2, scale, fr[2], cell[2]);
-            const float h0 = __fsub_rn(1.0f, fr[0]), h1 = __fsub_rn(1.0f, fr[1]), h2 = __fsub_rn(1.0f, fr[2]);
-            // same multiplication order as the forward kernel and the reference: (wx * wy) * wz
-            const float wxy[4] = {__fmul_rn(h0, h1), __fmul_rn(fr[0], h1), __fmul_rn(h0, fr[1]), __fmul_rn(fr[0], fr[1])};
-            if (pow2) {
-                const uint32_t ax[2] = {cell[0], cell[0] + 1u};
-                const uint32_t ay[2] = {cell[1] * my, (cell[1] + 1u) * my};
-                const uint32_t az[2] = {cell[2] * mz, (cell[2] + 1u) * mz};
+            // x offset of the class's corner for (dy, dz) = (0, 0): hashed  dx = q ^ parity(x ^ y ^ z) [^ dy ^ dz],  dense  dx = q ^ (x & 1)
+            const uint32_t dx00 = (q ^ cell[0] ^ (hashed ? (cell[1] ^ cell[2]) : 0u)) & 1u;
+            const float wx[2] = {__fsub_rn(1.0f, fr[0]), fr[0]}, wy[2] = {__fsub_rn(1.0f, fr[1]), fr[1]}, wz[2] = {__fsub_rn(1.0f, fr[2]), fr[2]};
+            const uint32_t ay[2] = {cell[1] * my, (cell[1] + 1u) * my};
+            const uint32_t az[2] = {cell[2] * mz, (cell[2] + 1u) * mz};
 #pragma unroll
-                for (uint32_t c = 0; c < 8; ++c) {
-                    const uint32_t idx = (hashed ? (ax[c & 1] ^ ay[(c >> 1) & 1] ^ az[c >> 2]) : (ax[c & 1] + ay[(c >> 1) & 1] + az[c >> 2])) & emask;
-                    so_add(slice_addr, idx - e0, ne, g0, g1, __fmul_rn(wxy[c & 3], (c & 4) ? fr[2] : h2));
-                }
-            } else {
-#pragma unroll
-                for (uint32_t c = 0; c < 8; ++c) {
-                    const uint32_t idx = mon_grid_index(hashed, size, res, cell[0] + (c & 1), cell[1] + ((c >> 1) & 1), cell[2] + ((c >> 2) & 1));
-                    so_add(slice_addr, idx - e0, ne, g0, g1, __fmul_rn(wxy[c & 3], (c & 4) ? fr[2] : h2));
-                }
+            for (uint32_t c = 0; c < 4; ++c) {
+                const uint32_t dy = c & 1u, dz = c >> 1;
+                const uint32_t dx = hashed ? (dx00 ^ dy ^ dz) : dx00;
+                const uint32_t cx = cell[0] + dx;
+                const uint32_t idx = (hashed ? (cx ^ ay[dy] ^ az[dz]) : (cx + ay[dy] + az[dz])) & emask;
+                // same multiplication order as the forward kernel and the reference: (wx * wy) * wz
+                const float wgt = __fmul_rn(__fmul_rn(dx ? wx[1] : wx[0], wy[dy]), wz[dz]);
+                so_add_f16x2(slice_addr + (idx >> 1) * 4u, __floats2half2_rn(__fmul_rn(g0, wgt), __fmul_rn(g1, wgt)));
             }
         }
-        cluster.sync();        // both private copies of the slice are complete and visible cluster-wide
+        cluster.sync();        // every private copy of the slice is complete and visible cluster-wide
         if (job == cluster_id) MON_TL_MARK(MON_TL_S + 1, a.ctrl->iter - 1);
 
-        // ---- phase 2: this CTA's half of the slice: add the partner's copy, round to fp16, then Adam + EMA in place
-        const int4* mine = reinterpret_cast<const int4*>(so_smem);
-        const int4* theirs = reinterpret_cast<const int4*>(cluster.map_shared_rank(so_smem, rank ^ 1u));
-        const uint32_t n_chunks = ne / 4;                                  // 4 entries (8 accumulator words) per chunk (ne % 8 == 0)
+        // ---- phase 2: this CTA's quarter of the slice: sum the four copies, round to fp16, then Adam + EMA in place.
+        // A thread takes 4 consecutive accumulator words = the class's entries 2j+q .. 2(j+3)+q of the level.
+        const uint4* copies[SO_CLUSTER];
+#pragma unroll
+        for (uint32_t r = 0; r < SO_CLUSTER; ++r) copies[r] = reinterpret_cast<const uint4*>(cluster.map_shared_rank(so_smem, r));
+        const uint32_t n_chunks = size / 8;                                // slice entries = size / 2, 4 per chunk (size % 8 == 0)
         const uint32_t c_begin = (uint32_t)((uint64_t)n_chunks * rank / SO_CLUSTER), c_end = (uint32_t)((uint64_t)n_chunks * (rank + 1) / SO_CLUSTER);
         const OptimPtrs ptrs = {a.pf, a.ph, a.m, a.v, a.ps, a.ema};
         for (uint32_t c = c_begin + tid; c < c_end; c += SO_THREADS) {
-            const int4 m0 = mine[2 * c], m1 = mine[2 * c + 1], t0 = theirs[2 * c], t1 = theirs[2 * c + 1];
-            const int sum[8] = {m0.x + t0.x, m0.y + t0.y, m0.z + t0.z, m0.w + t0.w, m1.x + t1.x, m1.y + t1.y, m1.z + t1.z, m1.w + t1.w};
-            // the gradient the reference keeps is fp16 (loss-scaled): one rounding here
-            uint32_t gp[4];
+            float acc[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const __half2 h = __floats2half2_rn(__fmul_rn((float)sum[2 * q], 1.0f / SO_FIXED_ONE), __fmul_rn((float)sum[2 * q + 1], 1.0f / SO_FIXED_ONE));
-                gp[q] = *reinterpret_cast<const uint32_t*>(&h);
-            }
-            const uint32_t entry = e0 + 4 * c;                              // within the level
-            const uint32_t i8 = a.o.n_mlp + 2u * (a.g.offset[l] + entry);   // first of the 8 parameters
-            if (a.grad_snap) {
+            for (uint32_t r = 0; r < SO_CLUSTER; ++r) {
+                const uint4 w = copies[r][c];
+                const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&gp[q]));
-                    a.grad_snap[i8 + 2 * q] = f.x; a.grad_snap[i8 + 2 * q + 1] = f.y;
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&ww[e]));
+                    acc[2 * e] = __fadd_rn(acc[2 * e], f.x);
+                    acc[2 * e + 1] = __fadd_rn(acc[2 * e + 1], f.y);
                 }
             }
-            if (!a.fuse) {
-                *reinterpret_cast<uint4*>(a.gh + (i8 - a.o.n_mlp)) = make_uint4(gp[0], gp[1], gp[2], gp[3]);
-                continue;
-            }
-            const uint4 wraw = *reinterpret_cast<const uint4*>(a.ph + i8);
-            const uint4 eraw = *reinterpret_cast<const uint4*>(a.ema + i8);
-            __half* f0 = a.planar + (size_t)a.g.offset[l] * 2 + entry;
 #pragma unroll
-            for (int hq = 0; hq < 2; ++hq) {                                 // two quads of 4 parameters = 2 entries each
-                const __half2 ga = *reinterpret_cast<const __half2*>(&gp[2 * hq]), gb = *reinterpret_cast<const __half2*>(&gp[2 * hq + 1]);
-                float g[4] = {__low2float(ga), __high2float(ga), __low2float(gb), __high2float(gb)};
-                const uint2 wq = hq ? make_uint2(wraw.z, wraw.w) : make_uint2(wraw.x, wraw.y);
-                const uint2 eq = hq ? make_uint2(eraw.z, eraw.w) : make_uint2(eraw.x, eraw.y);
-                optim_quad(a.o, lr_base, old_db, new_db, false, i8 + 4u * hq, g, wq, eq, ptrs, f0 + 2 * hq, size);
+            for (uint32_t e = 0; e < 4; ++e) {
+                // the gradient the reference keeps is fp16 (loss-scaled): one rounding here
+                const __half2 gh2 = __floats2half2_rn(acc[2 * e], acc[2 * e + 1]);
+                const uint32_t entry = 2u * (4u * c + e) + q;                   // within the level
+                const uint32_t i2 = a.o.n_mlp + 2u * (a.g.offset[l] + entry);   // the entry's two parameters
+                const float2 gf = __half22float2(gh2);
+                if (a.grad_snap) { a.grad_snap[i2] = gf.x; a.grad_snap[i2 + 1] = gf.y; }
+                if (!a.fuse) {
+                    *reinterpret_cast<__half2*>(a.gh + (i2 - a.o.n_mlp)) = gh2;
+                    continue;
+                }
+                optim_pair(a.o, lr_base, old_db, new_db, i2, gf.x, gf.y, ptrs, a.planar + (size_t)a.g.offset[l] * 2 + entry, size);
             }
         }
-        cluster.sync();        // nobody leaves (or clears its slice for the next job) while the partner still reads it
+        cluster.sync();        // nobody leaves (or clears its slice for the next job) while a partner still reads it
         if (job == cluster_id) MON_TL_MARK(MON_TL_S + 2, a.ctrl->iter - 1);
     }
 }
@@ -247,6 +224,7 @@ cudaError_t mon_launch_scatter_adam(const MonGrid& g, const MonOpt& o, uint32_t 
         return cudaFuncSetAttribute(k_scatter_adam, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SO_SMEM_BYTES);
     });
     if (prep != cudaSuccess) return prep;
+    if (!mon_scatter_adam_supported(g)) return cudaErrorNotSupported;
     SoArgs a;
     a.g = g; a.o = o; a.n_points = n_points; a.n_jobs = mon_scatter_adam_jobs(g); a.fuse = fuse ? 1u : 0u;
     a.live_cnt = live_cnt; a.pts_c = pts_c; a.genc = genc; a.ctrl = ctrl;

@@ -754,6 +754,9 @@ int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uin
     MonGrid grid;
     if (!validate_config(*cfg, why) || !make_grid(*cfg, grid, why)) return fail(MON_ERR_ARG, "unsupported config: %s", why.c_str());
     for (int k = 0; k < 3; ++k) if (!(bmax[k] > bmin[k])) return fail(MON_ERR_ARG, "empty bounding box");
+    if (!mon_scatter_adam_supported(grid))
+        return fail(MON_ERR_ARG, "unsupported config: every level's table must have a power-of-two size and the dense levels an even resolution "
+                                 "(true for base_resolution = 2^k with per_level_scale = 2, the reference's base.json)");
     CK(cudaSetDevice(ds->gpu));
     mon_object* o = new mon_object();
     o->ds = ds; o->cfg = *cfg; o->grid = grid; o->seed = seed;

@@ -110,6 +110,7 @@ void mon_launch_optimizer(const MonOpt& o, MonCtrl* ctrl, float* pf, __half* ph,
 enum { MON_OPT_ALL = 0, MON_OPT_MLP = 1, MON_OPT_GRID = 2, MON_OPT_MLP_GRID = 3 };
 // kernels_scatter_adam.cu: gradient scatter into shared-memory resident table slices fused with Adam + EMA of the grid
 uint32_t mon_scatter_adam_jobs(const MonGrid& g);
+bool mon_scatter_adam_supported(const MonGrid& g);   // power-of-two tables, even resolution on the dense levels
 cudaError_t mon_launch_scatter_adam(const MonGrid& g, const MonOpt& o, uint32_t n_points, const uint32_t* live_cnt, const float* pts_c,
                                     const uint32_t* genc, const MonCtrl* ctrl, float* pf, __half* ph, float* m, float* v, uint32_t* ps,
                                     __half* ema, __half* planar, __half* gh_grid, float* grad_snap, bool fuse, uint32_t sm_count,

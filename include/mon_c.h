@@ -143,8 +143,9 @@ int mon_object_step_count(mon_object* obj, uint32_t* step);
 /* Measurement hook: `iters` iterations launched kernel by kernel (no graph) with a CUDA event between the
  * stages on the object's stream; stage_ms[k] = mean device time of stage k per iteration.
  * Stages: 0 batch (ray generation + compaction), 1 sample positions, 2 hash-grid encode, 3 fused MLP forward +
- * volume render + loss + MLP backward, 4 hash-grid gradient scatter fused with Adam + EMA of the grid parameters,
- * 5 optimizer of the MLP weights (gradient reduction, Adam, EMA) + logged-loss reduction.  n_stages must be MON_N_STAGES. */
+ * volume render + loss + MLP backward (hands the live samples over compacted), 4 hash-grid gradient scatter, 5 optimizer
+ * sweep (MLP-gradient reduction, Adam + EMA + gradient zeroing over all parameters, logged-loss reduction).  In the opt-in
+ * fused mode (MON_SCATTER_SMEM=1) stage 4 also updates the grid and stage 5 only the MLP weights.  n_stages must be MON_N_STAGES. */
 #define MON_N_STAGES 6
 int mon_object_train_profiled(mon_object* obj, uint32_t iters, float* stage_ms, uint32_t n_stages);
 /* samples of the last iteration that carried gradient (non-zero dL/dencoding row: not behind the early stop T < 1e-4 of

@@ -184,7 +184,7 @@ class NerfObject:
     def sync(self):
         check(self._lib.mon_object_sync(self._h))
 
-    STAGES = ("batch", "points", "encode", "mlp_fused", "scatter_adam", "optimizer_mlp")
+    STAGES = ("batch", "points", "encode", "mlp_fused", "scatter", "optimizer")
 
     def train_profiled(self, iters: int) -> dict:
         """Mean device milliseconds per stage (CUDA events on the object's stream), see mon_c.h."""

@@ -18,8 +18,7 @@
 // the 32-bit stride wrap that turns level 12 into a table indexed by x alone (mon_core.cu make_grid).
 //
 // BACKWARD.  grad[idx] += half2(d_enc * w) with f16x2 reductions, exactly the reference's atomicAdd(__half2)
-// (grid.h:427-431).  A CTA owns 128 consecutive samples: it compacts the ones that still carry gradient into shared
-// memory and scatters them with one level per warp (k_encode_backward).
+// (grid.h:427-431), for the live samples the fused MLP kernel compacted, one level per warp (k_encode_backward).
 #include "mon_device.cuh"
 #include "mon_kernels.h"
 #include "tc05.cuh"
@@ -345,7 +344,7 @@ void mon_launch_planarize(const MonGrid& g, const __half* inter, __half* planar,
 
 // ---------------------------------------------------------------------------------------------- backward
 #define SCT_THREADS 512
-#define SCT_TILE 128
+#define SCT_TILE 64
 
 // explicit global-space reduction: a generic-pointer atomicAdd(__half2*) makes the compiler query the address space
 // and branch around every one of the 32 atomics of a thread
@@ -420,54 +419,30 @@ __device__ __forceinline__ void scatter_level(const MonGrid& g, uint32_t l, uint
             }
 }
 
-// Compacted scatter.  A warp of the fused MLP kernel is one ray and most of its samples sit behind the early stop
-// (T < 1e-4) with an all-zero gradient row: in steady state only ~1 sample in 6 carries gradient, and a
-// thread-per-sample scatter runs its warps for a handful of live lanes (profiles/r1t_ncu_kernels.txt: 72 % of the
-// (warp, level) blocks execute, issue slots 68 % busy).  Here the CTA first compacts the live samples of its
-// 128-sample tile into shared memory (gradient rows transposed to [level][rank], positions to [axis][rank]) and then
-// warp w scatters level w for the live samples only: lanes are filled with real work and the level — table base,
-// scale, hash or dense — is uniform across the warp.
+// Scatter of the compacted live samples.  A warp of the fused MLP kernel is one ray and most of its samples sit behind the
+// early stop (T < 1e-4) with an all-zero gradient row: in steady state only ~1 sample in 10 carries gradient.  The fused MLP
+// kernel hands over the live samples only — slot k: position pts_c[k], and per level l one word genc[l][k] with the level's
+// two fp16 gradients — so every lane here has real work and the level (table base, scale, hash or dense) is uniform across
+// a warp: a CTA takes SCT_TILE consecutive slots, warp w scatters level w for them.  CTAs beyond the live count exit at once.
 __global__ void __launch_bounds__(SCT_THREADS, 3)
-k_encode_backward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, const MonCtrl* __restrict__ ctrl,
-                  const __half* __restrict__ d_enc, __half* __restrict__ grid_grad, uint32_t level_begin, uint32_t level_end) {
-    __shared__ uint32_t s_g[MON_IN / 2][SCT_TILE];   // [level][rank]: the two fp16 gradients of the level
-    __shared__ float s_u[3][SCT_TILE];               // [axis][rank]
-    __shared__ uint32_t s_live[SCT_TILE / 32];       // live-sample mask per 32-sample group (OR over the 4 row quarters)
+k_encode_backward(MonGrid g, uint32_t n_points, const uint32_t* __restrict__ live_cnt, const float* __restrict__ pts_c,
+                  const uint32_t* __restrict__ genc, const MonCtrl* __restrict__ ctrl, __half* __restrict__ grid_grad) {
+    __shared__ float s_u[3][SCT_TILE];               // [axis][slot in tile]
     mon_pdl_wait();
     mon_pdl_trigger();
     if (ctrl->skip) return;
-    MON_TL(MON_TL_S + ((level_begin >> 2) & 3u), ctrl->iter - 1);
+    const uint32_t n_live = live_cnt[(ctrl->iter - 1) & 1u];
+    const uint32_t s0 = blockIdx.x * SCT_TILE;
+    if (s0 >= n_live) return;                          // CTA-uniform
+    MON_TL(MON_TL_S, ctrl->iter - 1);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t p = tid & (SCT_TILE - 1), q = tid >> 7, grp = p >> 5;   // sample in the tile, quarter of its gradient row (4 levels), 32-sample group
-    const uint32_t pt = blockIdx.x * SCT_TILE + p;
-    if (tid < SCT_TILE / 32) s_live[tid] = 0u;
-    uint4 gv = make_uint4(0u, 0u, 0u, 0u);
-    float u0 = 0.0f, u1 = 0.0f, u2 = 0.0f;
-    if (pt < n_points) {
-        gv = reinterpret_cast<const uint4*>(d_enc + (size_t)pt * MON_IN)[q];
-        if (q == 0) { u0 = __ldg(pts + (size_t)pt * 3); u1 = __ldg(pts + (size_t)pt * 3 + 1); u2 = __ldg(pts + (size_t)pt * 3 + 2); }
-    }
-    __syncthreads();                                   // s_live cleared
-    const uint32_t nz = __ballot_sync(0xffffffffu, ((gv.x | gv.y | gv.z | gv.w) & 0x7fff7fffu) != 0u);
-    if (lane == 0 && nz) atomicOr(&s_live[grp], nz);
+    const uint32_t n_tile = min((uint32_t)SCT_TILE, n_live - s0);
+    for (uint32_t i = tid; i < 3 * n_tile; i += SCT_THREADS) s_u[i % 3][i / 3] = __ldg(pts_c + (size_t)s0 * 3 + i);
     __syncthreads();
-    uint32_t base = 0, n_live = 0, mine = 0;
-#pragma unroll
-    for (uint32_t k = 0; k < SCT_TILE / 32; ++k) {
-        const uint32_t m = s_live[k];
-        if (k == grp) { base = n_live; mine = m; }
-        n_live += __popc(m);
-    }
-    if (n_live == 0) return;                           // CTA-uniform
-    if ((mine >> lane) & 1u) {
-        const uint32_t rank = base + __popc(mine & ((1u << lane) - 1u));
-        s_g[4 * q + 0][rank] = gv.x; s_g[4 * q + 1][rank] = gv.y; s_g[4 * q + 2][rank] = gv.z; s_g[4 * q + 3][rank] = gv.w;
-        if (q == 0) { s_u[0][rank] = u0; s_u[1][rank] = u1; s_u[2][rank] = u2; }
-    }
-    __syncthreads();
-    for (uint32_t l = level_begin + warp; l < level_end; l += SCT_THREADS / 32) {
-        for (uint32_t r = lane; r < n_live; r += 32) {
-            const uint32_t gwj = s_g[l][r];
+    for (uint32_t l = warp; l < g.n_levels; l += SCT_THREADS / 32) {
+        const uint32_t* gl = genc + (size_t)l * n_points + s0;
+        for (uint32_t r = lane; r < n_tile; r += 32) {
+            const uint32_t gwj = __ldg(gl + r);
             if ((gwj & 0x7fff7fffu) == 0u) continue;   // adding +0 is an identity
             const float u[3] = {s_u[0][r], s_u[1][r], s_u[2][r]};
             scatter_level(g, l, gwj, u, grid_grad);
@@ -475,42 +450,9 @@ k_encode_backward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, c
     }
 }
 
-// the thread-per-sample form (MON_SCT_COMPACT=0, A/B): thread quarter lg owns levels level_begin + 4*lg + j of sample p
-__global__ void __launch_bounds__(SCT_THREADS)
-k_encode_backward_dense(MonGrid g, uint32_t n_points, const float* __restrict__ pts, const MonCtrl* __restrict__ ctrl,
-                        const __half* __restrict__ d_enc, __half* __restrict__ grid_grad, uint32_t level_begin, uint32_t level_end) {
-    mon_pdl_wait();
-    mon_pdl_trigger();
-    if (ctrl->skip) return;
-    MON_TL(MON_TL_S + ((level_begin >> 2) & 3u), ctrl->iter - 1);
-    const uint32_t p = threadIdx.x & (SCT_TILE - 1), lg = threadIdx.x >> 7;
-    const uint32_t pt = blockIdx.x * SCT_TILE + p;
-    if (pt >= n_points) return;
-    const uint4 gv = reinterpret_cast<const uint4*>(d_enc + (size_t)pt * MON_IN)[(level_begin >> 2) + lg];
-    const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
-    const float u[3] = {__ldg(pts + (size_t)pt * 3), __ldg(pts + (size_t)pt * 3 + 1), __ldg(pts + (size_t)pt * 3 + 2)};
-    if (((gv.x | gv.y | gv.z | gv.w) & 0x7fff7fffu) == 0) return;
-#pragma unroll
-    for (uint32_t j = 0; j < 4; ++j) {
-        const uint32_t l = level_begin + lg * 4 + j;
-        if (l >= level_end || (gw[j] & 0x7fff7fffu) == 0) continue;
-        scatter_level(g, l, gw[j], u, grid_grad);
-    }
-}
-
-void mon_launch_encode_backward(const MonGrid& g, uint32_t n_points, const float* pts, const MonCtrl* ctrl,
-                                const __half* d_enc, __half* grid_grad, cudaStream_t st, uint32_t level_begin, uint32_t level_end,
-                                const MonLaunchOpt& lo) {
-    if (level_end > g.n_levels) level_end = g.n_levels;
-    if (level_begin >= level_end || n_points == 0) return;
+void mon_launch_encode_backward(const MonGrid& g, uint32_t n_points, const uint32_t* live_cnt, const float* pts_c, const uint32_t* genc,
+                                const MonCtrl* ctrl, __half* grid_grad, cudaStream_t st, const MonLaunchOpt& lo) {
+    if (n_points == 0) return;
     const uint32_t blocks = (n_points + SCT_TILE - 1) / SCT_TILE;
-    static const int compact = [] { const char* e = getenv("MON_SCT_COMPACT"); return e ? atoi(e) : 1; }();
-    if (compact && g.n_levels * 2 <= MON_IN) {
-        mon_launch_chain(MON_PDL_SCATTER, lo, k_encode_backward, dim3(blocks), dim3(SCT_THREADS), 0, st, g, n_points, pts, ctrl, d_enc, grid_grad,
-                         level_begin, level_end);
-        return;
-    }
-    const uint32_t quarters = (level_end - level_begin + 3) / 4;     // 128 threads (one point each) per 4 levels
-    mon_launch_chain(MON_PDL_SCATTER, lo, k_encode_backward_dense, dim3(blocks), dim3(SCT_TILE * quarters), 0, st, g, n_points, pts, ctrl, d_enc, grid_grad,
-                     level_begin, level_end);
+    mon_launch_chain(MON_PDL_SCATTER, lo, k_encode_backward, dim3(blocks), dim3(SCT_THREADS), 0, st, g, n_points, live_cnt, pts_c, genc, ctrl, grid_grad);
 }

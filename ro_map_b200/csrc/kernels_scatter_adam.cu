@@ -33,8 +33,13 @@
 // them for nothing, and the kernel is instruction-bound: 207 us for a fresh object, 47 us in steady state.
 //
 // The fp16 gradient table never exists in global memory (3.8 MB written by atomics, read and zeroed again per iteration),
-// and the launch between scatter and optimizer is gone.  fuse == 0 (A/B, MON_SO_FUSE=0) stops after the reduction and
-// stores the gradient for the separate optimizer sweep of kernels_optim.cu.
+// and the launch between scatter and optimizer is gone.
+//
+// STATUS: opt-in (MON_SCATTER_SMEM=1), parity-tested, NOT the default: on B200 it measured slower than the global-reduction
+// scatter + optimizer sweep in both phases of training (profiles/r4e_*, r4f_*: steady state 70 vs 35 us, fresh object 230 vs
+// 107 us).  Two costs the design does not remove: owning every other entry makes the Adam phase read half-used sectors of
+// the fp32 state (55 us instead of 13), and on the coarse hashed levels of a fresh object the compare-and-swap loops of 1024
+// threads collide (75-146 us for levels 2-10 against 36 us for levels 13-15).
 #include <cooperative_groups.h>
 
 #include "mon_device.cuh"
@@ -42,6 +47,15 @@
 #include "optim_math.cuh"
 #include "mon_timeline.cuh"
 MON_TL_DEFINE(scatter_adam)
+#ifdef MON_TIMELINE
+// per CTA [start, scatter phase done, reduce + Adam phase done] of its first job, for the iteration with (iter % 64) == 20
+static __device__ unsigned long long mon_tl_so_cta[256 * 3];
+extern "C" int mon_debug_tl_so_cta_read(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, mon_tl_so_cta, sizeof(mon_tl_so_cta)); }
+#define SO_CTA_STAMP(slot) do { if (threadIdx.x == 0 && blockIdx.x < 256 && (a.ctrl->iter - 1) % 64 == 20) { \
+        unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); mon_tl_so_cta[blockIdx.x * 3 + (slot)] = t_; } } while (0)
+#else
+#define SO_CTA_STAMP(slot) do { } while (0)
+#endif
 
 namespace cg = cooperative_groups;
 
@@ -78,15 +92,41 @@ bool mon_scatter_adam_supported(const MonGrid& g) {
     return true;
 }
 
-// accumulator word += (v.x, v.y) in fp16: compare-and-swap on the CTA's own shared memory
-__device__ __forceinline__ void so_add_f16x2(uint32_t addr, __half2 v) {
-    uint32_t old, assumed;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(old) : "r"(addr) : "memory");
-    do {
-        assumed = old;
-        const __half2 sum = __hadd2(*reinterpret_cast<const __half2*>(&assumed), v);
-        asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(addr), "r"(assumed), "r"(*reinterpret_cast<const uint32_t*>(&sum)) : "memory");
-    } while (old != assumed);
+// Four accumulator words += fp16 pairs: compare-and-swap on the CTA's own shared memory, all four in flight together (four
+// loads, four adds, four swaps; only a swap that lost against another thread is retried on its own) — the latency of one
+// read-modify-write per sample instead of four.
+__device__ __forceinline__ void so_add4_f16x2(const uint32_t (&addr)[4], const __half2 (&v)[4]) {
+    uint32_t old[4], got[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(old[c]) : "r"(addr[c]) : "memory");
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const __half2 sum = __hadd2(*reinterpret_cast<const __half2*>(&old[c]), v[c]);
+        asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(got[c]) : "r"(addr[c]), "r"(old[c]), "r"(*reinterpret_cast<const uint32_t*>(&sum)) : "memory");
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        while (got[c] != old[c]) {      // lost: another thread (or an earlier corner of this one) changed the word in between
+            old[c] = got[c];
+            const __half2 sum = __hadd2(*reinterpret_cast<const __half2*>(&old[c]), v[c]);
+            asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(got[c]) : "r"(addr[c]), "r"(old[c]), "r"(*reinterpret_cast<const uint32_t*>(&sum)) : "memory");
+        }
+    }
+}
+
+// Coarse (dense) levels: thousands of samples land on a few hundred entries and a compare-and-swap loop would spin.  Their
+// slices are small enough (<= 16384 entries per parity class) for two 32-bit FIXED-POINT words per entry, unit 2^-24: every
+// contribution is rounded to fp16 first, exactly as the reference rounds it before its atomicAdd(__half2) (grid.h:427-431),
+// and every fp16 value is a multiple of 2^-24, so the integer sum is exact and native shared-memory integer atomics
+// (ATOMS.ADD: no retry, same-address updates are serialised by the hardware) apply.  Range +-128 in loss-scaled units
+// (cvt.rni.s32.f32 saturates a single contribution; gradients of this loss are ~1e-3).
+#define SO_FIXED_ONE 16777216.0f
+#define SO_INT_ENTRIES 16384u
+__device__ __forceinline__ void so_add_fixed(uint32_t addr8, __half2 v) {
+    const float2 f = __half22float2(v);
+    const int i0 = __float2int_rn(f.x * SO_FIXED_ONE), i1 = __float2int_rn(f.y * SO_FIXED_ONE);
+    if (i0) asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr8), "r"(i0) : "memory");
+    if (i1) asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr8 + 4u), "r"(i1) : "memory");
 }
 
 // slot handled by thread `tid` in trip `k` of a CTA's share.  Hashed levels: consecutive lanes take consecutive slots
@@ -117,6 +157,7 @@ k_scatter_adam(const __grid_constant__ SoArgs a) {
     mon_pdl_trigger();
     if (a.ctrl->skip) return;                          // uniform over the grid
     MON_TL(MON_TL_S, a.ctrl->iter - 1);
+    SO_CTA_STAMP(0);
     const uint32_t n_live = a.live_cnt[(a.ctrl->iter - 1) & 1u];
     const float lr_base = a.ctrl->lr_base, old_db = a.ctrl->ema_old, new_db = a.ctrl->ema_new;
     const uint32_t s_begin = (uint32_t)((uint64_t)n_live * rank / SO_CLUSTER), s_end = (uint32_t)((uint64_t)n_live * (rank + 1) / SO_CLUSTER);
@@ -141,6 +182,7 @@ k_scatter_adam(const __grid_constant__ SoArgs a) {
         const uint32_t* gl = a.genc + (size_t)l * a.n_points;
         const uint32_t emask = size - 1u;
         const uint32_t my = hashed ? 2654435761u : res, mz = hashed ? 805459861u : res * res;
+        const bool fixed = !hashed && size / 2 <= SO_INT_ENTRIES;   // small dense level: fixed-point accumulators, native integer atomics
         for (uint32_t k = 0; k < n_trips; ++k) {
             const uint32_t s = so_slot(s_begin, k, tid, !hashed);
             if (s >= s_end) continue;
@@ -158,6 +200,8 @@ k_scatter_adam(const __grid_constant__ SoArgs a) {
             const float wx[2] = {__fsub_rn(1.0f, fr[0]), fr[0]}, wy[2] = {__fsub_rn(1.0f, fr[1]), fr[1]}, wz[2] = {__fsub_rn(1.0f, fr[2]), fr[2]};
             const uint32_t ay[2] = {cell[1] * my, (cell[1] + 1u) * my};
             const uint32_t az[2] = {cell[2] * mz, (cell[2] + 1u) * mz};
+            uint32_t addr[4];
+            __half2 val[4];
 #pragma unroll
             for (uint32_t c = 0; c < 4; ++c) {
                 const uint32_t dy = c & 1u, dz = c >> 1;
@@ -166,11 +210,18 @@ k_scatter_adam(const __grid_constant__ SoArgs a) {
                 const uint32_t idx = (hashed ? (cx ^ ay[dy] ^ az[dz]) : (cx + ay[dy] + az[dz])) & emask;
                 // same multiplication order as the forward kernel and the reference: (wx * wy) * wz
                 const float wgt = __fmul_rn(__fmul_rn(dx ? wx[1] : wx[0], wy[dy]), wz[dz]);
-                so_add_f16x2(slice_addr + (idx >> 1) * 4u, __floats2half2_rn(__fmul_rn(g0, wgt), __fmul_rn(g1, wgt)));
+                addr[c] = slice_addr + (idx >> 1) * (fixed ? 8u : 4u);
+                val[c] = __floats2half2_rn(__fmul_rn(g0, wgt), __fmul_rn(g1, wgt));
+            }
+            if (fixed) {
+#pragma unroll
+                for (uint32_t c = 0; c < 4; ++c) so_add_fixed(addr[c], val[c]);
+            } else {
+                so_add4_f16x2(addr, val);
             }
         }
         cluster.sync();        // every private copy of the slice is complete and visible cluster-wide
-        if (job == cluster_id) MON_TL_MARK(MON_TL_S + 1, a.ctrl->iter - 1);
+        if (job == cluster_id) { MON_TL_MARK(MON_TL_S + 1, a.ctrl->iter - 1); SO_CTA_STAMP(1); }
 
         // ---- phase 2: this CTA's quarter of the slice: sum the four copies, round to fp16, then Adam + EMA in place.
         // A thread takes 4 consecutive accumulator words = the class's entries 2j+q .. 2(j+3)+q of the level.
@@ -182,15 +233,27 @@ k_scatter_adam(const __grid_constant__ SoArgs a) {
         const OptimPtrs ptrs = {a.pf, a.ph, a.m, a.v, a.ps, a.ema};
         for (uint32_t c = c_begin + tid; c < c_end; c += SO_THREADS) {
             float acc[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+            if (fixed) {
+                int isum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-            for (uint32_t r = 0; r < SO_CLUSTER; ++r) {
-                const uint4 w = copies[r][c];
-                const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+                for (uint32_t r = 0; r < SO_CLUSTER; ++r) {
+                    const int4 w0 = reinterpret_cast<const int4*>(copies[r])[2 * c], w1 = reinterpret_cast<const int4*>(copies[r])[2 * c + 1];
+                    isum[0] += w0.x; isum[1] += w0.y; isum[2] += w0.z; isum[3] += w0.w;
+                    isum[4] += w1.x; isum[5] += w1.y; isum[6] += w1.z; isum[7] += w1.w;
+                }
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&ww[e]));
-                    acc[2 * e] = __fadd_rn(acc[2 * e], f.x);
-                    acc[2 * e + 1] = __fadd_rn(acc[2 * e + 1], f.y);
+                for (int e = 0; e < 8; ++e) acc[e] = __fmul_rn((float)isum[e], 1.0f / SO_FIXED_ONE);
+            } else {
+#pragma unroll
+                for (uint32_t r = 0; r < SO_CLUSTER; ++r) {
+                    const uint4 w = copies[r][c];
+                    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&ww[e]));
+                        acc[2 * e] = __fadd_rn(acc[2 * e], f.x);
+                        acc[2 * e + 1] = __fadd_rn(acc[2 * e + 1], f.y);
+                    }
                 }
             }
 #pragma unroll
@@ -209,7 +272,7 @@ k_scatter_adam(const __grid_constant__ SoArgs a) {
             }
         }
         cluster.sync();        // nobody leaves (or clears its slice for the next job) while a partner still reads it
-        if (job == cluster_id) MON_TL_MARK(MON_TL_S + 2, a.ctrl->iter - 1);
+        if (job == cluster_id) { MON_TL_MARK(MON_TL_S + 2, a.ctrl->iter - 1); SO_CTA_STAMP(2); }
     }
 }
 

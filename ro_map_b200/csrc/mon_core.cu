@@ -239,7 +239,10 @@ struct mon_object {
     cudaEvent_t ev_fork_m = nullptr, ev_join = nullptr, ev_join2 = nullptr;
     // compacted live samples of the iteration (fused MLP kernel -> scatter + Adam kernel)
     float* pts_c = nullptr; uint32_t* genc = nullptr; uint32_t* live_cnt = nullptr;
-    bool so_fuse = true;              // Adam + EMA of the grid inside the scatter kernel (MON_SO_FUSE=0: separate sweep, A/B)
+    // gradient scatter + optimizer: false (default) = f16x2 reductions into the global gradient table + one optimizer sweep;
+    // true (MON_SCATTER_SMEM=1, opt-in) = the fused scatter + Adam kernel with shared-memory resident gradient slices
+    // (kernels_scatter_adam.cu): measured slower on B200, kept as the tested alternative
+    bool so_fuse = false;
     // instantiated iteration graphs by length
     struct GraphSlot { uint32_t iters; cudaGraphExec_t exec; uint64_t stamp; };
     std::vector<GraphSlot> graphs;
@@ -612,15 +615,15 @@ static MonBatch make_batch(mon_object* o, bool injected, bool debug) {
     return b;
 }
 
-// One training iteration = batch (B) -> sample points (P) -> hash encode (E) -> fused MLP (M) -> gradient scatter fused
-// with Adam/EMA of the grid (S) || optimizer of the MLP weights + logged loss (O).  B and P do not depend on the training
-// state, so inside a captured graph the B/P of iteration i+1 run on a forked branch beside S/O of iteration i:
-//     main:  E(i)  M(i) ---------> S(i) -------------------join--> E(i+1) ...
+// One training iteration = batch (B) -> sample points (P) -> hash encode (E) -> fused MLP (M) -> gradient scatter (S) ->
+// optimizer sweep (O).  B and P do not depend on the training state, so inside a captured graph the B/P of iteration i+1 run
+// on a forked branch beside S/O of iteration i:
+//     main:  E(i)  M(i) ---------> S(i) -----> O(i) -------join--> E(i+1) ...
 //     aux :          \--> B(i+1) -> P(i+1) ----------------/
-//     aux2:          \--> O(i) ----------------------------/
-// Everything after M(i) only needs M(i): the batch kernel rewrites rays/targets (last read by M, which also copied the
-// control block for S/O), the sample positions are last read by M too (it hands the positions of the live samples to S in
-// compacted form), and O reads M's weight-gradient partials and per-ray losses.
+// Everything on the branch only needs M(i): the batch kernel rewrites rays/targets (last read by M, which also copied the
+// control block for S/O), and the sample positions are last read by M too (it hands the positions of the live samples to S
+// in compacted form).  In the opt-in fused mode S also updates the grid and O (MLP weights + logged loss only) runs on a
+// second branch beside it.
 static int launch_batch(mon_object* o, const MonBatch& b, cudaStream_t st) {
     mon_launch_generate_batch(b, o->scene, st);
     return MON_OK;
@@ -641,14 +644,19 @@ static int launch_mlp(mon_object* o, const MonBatch& b, cudaStream_t st) {
     if (e != cudaSuccess) return fail(MON_ERR_CUDA, "fused MLP launch: %s", cudaGetErrorString(e));
     return MON_OK;
 }
-// gradient scatter (+ Adam / EMA of the grid when fused); grad_snap: parity hook
+// gradient scatter; in the fused mode also Adam / EMA of the grid.  grad_snap: parity hook (fused mode writes the grid part itself)
 static int launch_scatter(mon_object* o, cudaStream_t st, float* grad_snap) {
+    if (!o->so_fuse) {
+        mon_launch_encode_backward(o->grid, o->N, o->live_cnt, o->pts_c, o->genc, o->ctrl_late, o->gh + o->n_mlp, st);
+        return MON_OK;
+    }
     cudaError_t e = mon_launch_scatter_adam(o->grid, o->opt, o->N, o->live_cnt, o->pts_c, o->genc, o->ctrl_late, o->pf, o->ph, o->m, o->v, o->ps,
-                                            o->ema, o->ph_planar, o->gh + o->n_mlp, grad_snap, o->so_fuse, (uint32_t)o->sm_count, st);
+                                            o->ema, o->ph_planar, o->gh + o->n_mlp, grad_snap, true, (uint32_t)o->sm_count, st);
     if (e != cudaSuccess) return fail(MON_ERR_CUDA, "scatter + Adam launch: %s", cudaGetErrorString(e));
     return MON_OK;
 }
-// MLP weights (fixed-order reduction of the per-CTA partials, Adam, EMA) + logged loss; in the unfused A/B mode also the grid sweep
+// optimizer sweep: MLP weights (fixed-order reduction of the per-CTA partials, Adam, EMA) + logged loss + the grid (Adam with
+// per-parameter steps, EMA, gradient zeroing, planar weight copy); in the fused mode the grid part is skipped
 static void launch_optimizer(mon_object* o, cudaStream_t st, bool pdl) {
     MonLaunchOpt lo; lo.pdl = pdl;
     mon_launch_optimizer(o->opt, o->ctrl_late, o->pf, o->ph, o->gh, o->partials, o->m, o->v, o->ps, o->ema, o->loss, o->R, o->grid,
@@ -673,7 +681,7 @@ static int enqueue_iteration(mon_object* o, const MonBatch& b, bool snapshot_gra
     if (ev) CK(cudaEventRecord(ev[4], st));
     if ((rc = launch_scatter(o, st, snapshot_grad ? o->grad_snap : nullptr)) != MON_OK) return rc;
     ++n;
-    if (snapshot_grad) { mon_launch_snapshot_grad(o->n_mlp, o->n_mlp, o->opt.n_partials, o->gh, o->partials, o->grad_snap, st); ++n; }
+    if (snapshot_grad) { mon_launch_snapshot_grad(o->so_fuse ? o->n_mlp : o->P, o->n_mlp, o->opt.n_partials, o->gh, o->partials, o->grad_snap, st); ++n; }
     if (ev) CK(cudaEventRecord(ev[5], st));
     launch_optimizer(o, st, !snapshot_grad); ++n;
     if (ev) CK(cudaEventRecord(ev[6], st));
@@ -696,10 +704,12 @@ static int capture_graph(mon_object* o, int iters, cudaGraphExec_t* out) {
         // after a join the encode kernel's predecessor in the stream is not a plain kernel node: no programmatic edge there
         if ((rc = launch_encode(o, st, i == 0)) != MON_OK) break;
         if ((rc = launch_mlp(o, b, st)) != MON_OK) break;
-        if ((e = cudaEventRecord(o->ev_fork_m, st)) != cudaSuccess) break;
-        if ((e = cudaStreamWaitEvent(aux2, o->ev_fork_m, 0)) != cudaSuccess) break;
-        launch_optimizer(o, aux2, false);
-        if ((e = cudaEventRecord(o->ev_join2, aux2)) != cudaSuccess) break;
+        if (fork || o->so_fuse) { if ((e = cudaEventRecord(o->ev_fork_m, st)) != cudaSuccess) break; }
+        if (o->so_fuse) {
+            if ((e = cudaStreamWaitEvent(aux2, o->ev_fork_m, 0)) != cudaSuccess) break;
+            launch_optimizer(o, aux2, false);
+            if ((e = cudaEventRecord(o->ev_join2, aux2)) != cudaSuccess) break;
+        }
         if (fork) {
             if ((e = cudaStreamWaitEvent(aux, o->ev_fork_m, 0)) != cudaSuccess) break;
             launch_batch(o, b, aux);
@@ -707,7 +717,8 @@ static int capture_graph(mon_object* o, int iters, cudaGraphExec_t* out) {
             if ((e = cudaEventRecord(o->ev_join, aux)) != cudaSuccess) break;
         }
         if ((rc = launch_scatter(o, st, nullptr)) != MON_OK) break;
-        if ((e = cudaStreamWaitEvent(st, o->ev_join2, 0)) != cudaSuccess) break;
+        if (o->so_fuse) { if ((e = cudaStreamWaitEvent(st, o->ev_join2, 0)) != cudaSuccess) break; }
+        else launch_optimizer(o, st, true);
         if (fork && (e = cudaStreamWaitEvent(st, o->ev_join, 0)) != cudaSuccess) break;
     }
     cudaError_t e2 = cudaStreamEndCapture(st, &g);
@@ -814,7 +825,7 @@ int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uin
     OALLOC(o->debias_lut, (size_t)MON_DEBIAS_LUT * 4);
     o->opt.debias_lut = o->debias_lut; o->opt.n_debias_lut = MON_DEBIAS_LUT;
 #undef OALLOC
-    if (const char* env = getenv("MON_SO_FUSE")) o->so_fuse = atoi(env) != 0;   // A/B: separate optimizer sweep over the grid
+    if (const char* env = getenv("MON_SCATTER_SMEM")) o->so_fuse = atoi(env) != 0;
     cudaError_t e;
     if ((e = cudaMallocHost(&o->h_ctrl, sizeof(MonCtrl))) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking)) != cudaSuccess ||

@@ -87,9 +87,9 @@ cudaError_t mon_launch_encode_forward(const MonGrid& g, uint32_t n_points, const
                                       uint32_t level_end = 0xffffffffu, const MonLaunchOpt& lo = MonLaunchOpt());
 void mon_launch_planarize(const MonGrid& g, const __half* inter, __half* planar, cudaStream_t st);
 void mon_encode_pieces_host(const MonGrid& g, uint32_t n_points, uint32_t n_ctas, uint32_t level_begin, uint32_t level_end, uint32_t* out4);
-void mon_launch_encode_backward(const MonGrid& g, uint32_t n_points, const float* pts, const MonCtrl* ctrl,
-                                const __half* d_enc, __half* grid_grad, cudaStream_t st, uint32_t level_begin = 0,
-                                uint32_t level_end = 0xffffffffu, const MonLaunchOpt& lo = MonLaunchOpt());   // level_begin % 4 == 0
+// gradient scatter with global f16x2 reductions over the compacted live samples (written by the fused MLP kernel)
+void mon_launch_encode_backward(const MonGrid& g, uint32_t n_points, const uint32_t* live_cnt, const float* pts_c, const uint32_t* genc,
+                                const MonCtrl* ctrl, __half* grid_grad, cudaStream_t st, const MonLaunchOpt& lo = MonLaunchOpt());
 
 // kernels_mlp_tc.cu (tcgen05 / TMEM product family)
 cudaError_t mon_launch_mlp_train_tc(const MonBatch& b, const MonLossCfg& lc, uint32_t n_hidden, uint32_t n_mlp,

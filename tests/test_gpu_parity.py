@@ -314,8 +314,7 @@ def test_full_size_properties(core, gpu_dataset, small_seq):
 
 def test_graph_path_matches_serial_chain(core, gpu_dataset, small_seq):
     """Production path = CUDA graphs of exactly the requested number of iterations (batch generation + sample points of
-    iteration i+1 and the MLP-weight optimizer of iteration i forked beside the scatter + Adam kernel of iteration i;
-    mon_core.cu capture_graph).  The serial chain (mon_object_train_profiled: the same kernels on one stream) runs the
+    iteration i+1 forked beside the scatter and the optimizer sweep of iteration i; mon_core.cu capture_graph).  The serial chain (mon_object_train_profiled: the same kernels on one stream) runs the
     same iterations with the same RNG counters, so both must agree up to the order of the fp16 gradient accumulation."""
     seq, obj = small_seq, small_seq.objects[0]
     cfg = core.default_config(rays_per_batch=1024)
@@ -351,6 +350,33 @@ def test_graph_path_matches_serial_chain(core, gpu_dataset, small_seq):
     for n in (2, 3, 5, 9, 11, 13, 17):
         l_end = a.train(n)
     assert a.step == 92 + 3 + 60 and np.isfinite(l_end) and l_end < 1.2 * la + 1e-3
+
+
+def test_fused_smem_scatter_mode(core, oracle, gpu_dataset, small_seq, monkeypatch):
+    """The opt-in fused scatter + Adam kernel (MON_SCATTER_SMEM=1, kernels_scatter_adam.cu: gradient slices resident in shared
+    memory, parity-class jobs, Adam + EMA of the grid in the same kernel) gives the same iteration as the default path:
+    stage by stage against the oracle, and graph iterations against the default mode."""
+    seq, obj = small_seq, small_seq.objects[0]
+    monkeypatch.setenv("MON_SCATTER_SMEM", "1")
+    check_one_iteration_stage_by_stage(core, oracle, gpu_dataset, seq, obj, 512, 1)
+    cfg = core.default_config(rays_per_batch=1024)
+    bmin, bmax = -1.1 * obj.half, 1.1 * obj.half
+    a = core.NerfObject(gpu_dataset, cfg, obj.Tow, bmin, bmax, obj.instance_id)      # fused mode (read at creation)
+    monkeypatch.delenv("MON_SCATTER_SMEM")
+    b = core.NerfObject(gpu_dataset, cfg, obj.Tow, bmin, bmax, obj.instance_id)      # default mode
+    for g in (a, b):
+        g.set_bboxes(obj.boxes)
+        g.train(1)
+    ma, mb = a.state("master"), b.state("master")
+    assert (a.state("param_steps") == b.state("param_steps")).mean() >= 0.999
+    assert (np.abs(ma - mb) <= 1e-6).mean() >= 0.999
+    assert np.array_equal(ma[:a.n_mlp], mb[:a.n_mlp])
+    la, lb = a.train(70), b.train(70)
+    assert a.step == b.step == 71 and abs(la - lb) <= 0.03 * abs(lb) + 1e-4, (la, lb)
+    ea, eb = a.state("ema"), b.state("ema")
+    assert np.linalg.norm(ea - eb) <= 0.05 * np.linalg.norm(eb)
+    a.close()
+    b.close()
 
 
 def test_optimizer_bit_exact_for_equal_gradients(core, oracle, gpu_dataset, small_seq):

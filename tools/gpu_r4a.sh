@@ -12,8 +12,8 @@ tail -4 $OUT/${TAG}_memcheck.log
 tail -8 $OUT/${TAG}_pytest_bench_shape.log
 timeout 200 python tools/stage_times.py --at 0,50,500 > $OUT/${TAG}_stage_times.txt 2>&1
 cat $OUT/${TAG}_stage_times.txt
-MON_SO_FUSE=0 timeout 200 python tools/stage_times.py --at 0,500 > $OUT/${TAG}_stage_times_unfused.txt 2>&1
-cat $OUT/${TAG}_stage_times_unfused.txt
+MON_SCATTER_SMEM=1 timeout 200 python tools/stage_times.py --at 0,500 > $OUT/${TAG}_stage_times_smem.txt 2>&1
+cat $OUT/${TAG}_stage_times_smem.txt
 timeout 200 python tools/timeline.py --at 5,400 > $OUT/${TAG}_timeline.txt 2>&1
 head -30 $OUT/${TAG}_timeline.txt
 timeout 300 python bench.py --steps 20 --warmup 5 --no-secondary --cpu-seconds 3 > $OUT/${TAG}_bench_20_5.json 2> $OUT/${TAG}_bench_20_5.err

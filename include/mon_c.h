@@ -145,7 +145,7 @@ int mon_object_step_count(mon_object* obj, uint32_t* step);
  * Stages: 0 batch (ray generation + compaction), 1 sample positions, 2 hash-grid encode, 3 fused MLP forward +
  * volume render + loss + MLP backward (hands the live samples over compacted), 4 hash-grid gradient scatter, 5 optimizer
  * sweep (MLP-gradient reduction, Adam + EMA + gradient zeroing over all parameters, logged-loss reduction).  In the opt-in
- * fused mode (MON_SCATTER_SMEM=1) stage 4 also updates the grid and stage 5 only the MLP weights.  n_stages must be MON_N_STAGES. */
+ * stage 4 is two kernels of which one exits at once: shared-memory resident scatter (many live samples) or global f16x2 reductions.  n_stages must be MON_N_STAGES. */
 #define MON_N_STAGES 6
 int mon_object_train_profiled(mon_object* obj, uint32_t iters, float* stage_ms, uint32_t n_stages);
 /* samples of the last iteration that carried gradient (non-zero dL/dencoding row: not behind the early stop T < 1e-4 of
@@ -191,6 +191,9 @@ int mon_object_last(mon_object* obj, int which, float* out, size_t cap, size_t* 
  * No device needed; lets a CPU test check that the pieces tile the [job][point] space exactly. */
 int mon_debug_encode_pieces(const mon_config* cfg, uint32_t n_points, uint32_t n_ctas, uint32_t level_begin,
                             uint32_t level_end, uint32_t* out4);
+/* host-only: the work split of the shared-memory resident gradient scatter (kernels_scatter_smem.cu) for n_live live samples
+ * over n_ctas CTAs: out4[4*b..] = first (job, sample) and end (job, sample) of piece b, job = 4*level + 2*(entry index & 1) + feature. */
+int mon_debug_scatter_pieces(const mon_config* cfg, uint32_t n_live, uint32_t n_ctas, uint32_t* out4);
 /* stand-alone stage entry points on host buffers (copies inside), for kernel-level parity */
 int mon_stage_encode(const mon_config* cfg, const uint16_t* grid_fp16, size_t n_grid_params,
                      const float* points_unit, uint32_t n_points, uint16_t* enc_out);

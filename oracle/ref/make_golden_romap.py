@@ -65,12 +65,23 @@ def render_dt(seed: int, n_rays: int):
 
 
 MESH_BOX = (np.array([-1.0, -2.0, -0.5], np.float32), np.array([1.0, 2.0, 0.5], np.float32))   # object box of the mesh cases
-MESH_CASES = [("sphere", 24), ("noise", 14)]
+MESH_CASES = [("sphere", 24), ("noise", 14), ("cases", 22)]
 
 
 def mesh_lattice(kind: str, res: int) -> np.ndarray:
-    """[z][y][x] density lattice: an off-centre sphere of radius 0.3 (unit-cube metric) around the threshold 2.0, or white
-    noise in [0,4) with an empty border (every one of the 256 cell configurations occurs, ambiguous faces included)."""
+    """[z][y][x] density lattice: an off-centre sphere of radius 0.3 (unit-cube metric) around the threshold 2.0, white
+    noise in [0,4) with an empty border (ambiguous faces included; 252 of the 254 surface configurations occur), or "cases":
+    each of the 256 cell configurations once as an isolated cell (7 x 7 x 6 cells, one empty lattice plane between them)."""
+    if kind == "cases":
+        d = np.full((res, res, res), 1.0, np.float32)
+        corners = [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)]   # mask bit -> (dx, dy, dz)
+        rng = np.random.default_rng(778)
+        for mask in range(256):
+            cx, cy, cz = 3 * (mask % 7), 3 * ((mask // 7) % 7), 3 * (mask // 49)
+            for b, (dx, dy, dz) in enumerate(corners):
+                if (mask >> b) & 1:
+                    d[cz + dz, cy + dy, cx + dx] = np.float32(2.25 + 1.5 * rng.random())     # off-centre crossings
+        return d
     if kind == "sphere":
         ax = (np.arange(res, dtype=np.float32) / np.float32(res - 1)).astype(np.float32)
         z, y, x = np.meshgrid(ax, ax, ax, indexing="ij")

@@ -421,23 +421,24 @@ __device__ __forceinline__ void scatter_level(const MonGrid& g, uint32_t l, uint
 
 // Scatter of the compacted live samples.  A warp of the fused MLP kernel is one ray and most of its samples sit behind the
 // early stop (T < 1e-4) with an all-zero gradient row: in steady state only ~1 sample in 10 carries gradient.  The fused MLP
-// kernel hands over the live samples only — slot k: position pts_c[k], and per level l one word genc[l][k] with the level's
+// kernel hands over the live samples only — slot k: position pts_c[k] (16 bytes: x, y, z, unused), and per level l one word genc[l][k] with the level's
 // two fp16 gradients — so every lane here has real work and the level (table base, scale, hash or dense) is uniform across
 // a warp: a CTA takes SCT_TILE consecutive slots, warp w scatters level w for them.  CTAs beyond the live count exit at once.
 __global__ void __launch_bounds__(SCT_THREADS, 3)
-k_encode_backward(MonGrid g, uint32_t n_points, const uint32_t* __restrict__ live_cnt, const float* __restrict__ pts_c,
+k_encode_backward(MonGrid g, uint32_t n_points, uint32_t resident_min_live, const uint32_t* __restrict__ live_cnt, const float* __restrict__ pts_c,
                   const uint32_t* __restrict__ genc, const MonCtrl* __restrict__ ctrl, __half* __restrict__ grid_grad) {
     __shared__ float s_u[3][SCT_TILE];               // [axis][slot in tile]
     mon_pdl_wait();
     mon_pdl_trigger();
     if (ctrl->skip) return;
     const uint32_t n_live = live_cnt[(ctrl->iter - 1) & 1u];
+    if (n_live >= resident_min_live) return;           // grid-uniform: the shared-memory resident scatter takes this iteration (kernels_scatter_smem.cu)
     const uint32_t s0 = blockIdx.x * SCT_TILE;
     if (s0 >= n_live) return;                          // CTA-uniform
     MON_TL(MON_TL_S, ctrl->iter - 1);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t n_tile = min((uint32_t)SCT_TILE, n_live - s0);
-    for (uint32_t i = tid; i < 3 * n_tile; i += SCT_THREADS) s_u[i % 3][i / 3] = __ldg(pts_c + (size_t)s0 * 3 + i);
+    for (uint32_t i = tid; i < 3 * n_tile; i += SCT_THREADS) s_u[i % 3][i / 3] = __ldg(pts_c + (size_t)(s0 + i / 3) * 4 + i % 3);   // slots are (x, y, z, -)
     __syncthreads();
     for (uint32_t l = warp; l < g.n_levels; l += SCT_THREADS / 32) {
         const uint32_t* gl = genc + (size_t)l * n_points + s0;
@@ -450,9 +451,13 @@ k_encode_backward(MonGrid g, uint32_t n_points, const uint32_t* __restrict__ liv
     }
 }
 
-void mon_launch_encode_backward(const MonGrid& g, uint32_t n_points, const uint32_t* live_cnt, const float* pts_c, const uint32_t* genc,
-                                const MonCtrl* ctrl, __half* grid_grad, cudaStream_t st, const MonLaunchOpt& lo) {
+void mon_launch_encode_backward(const MonGrid& g, uint32_t n_points, uint32_t resident_min_live, const uint32_t* live_cnt, const float* pts_c,
+                                const uint32_t* genc, const MonCtrl* ctrl, __half* grid_grad, cudaStream_t st, const MonLaunchOpt& lo) {
     if (n_points == 0) return;
-    const uint32_t blocks = (n_points + SCT_TILE - 1) / SCT_TILE;
-    mon_launch_chain(MON_PDL_SCATTER, lo, k_encode_backward, dim3(blocks), dim3(SCT_THREADS), 0, st, g, n_points, live_cnt, pts_c, genc, ctrl, grid_grad);
+    // iterations with >= resident_min_live live samples are scattered by k_scatter_resident: this grid then only needs the CTAs
+    // that can have work
+    const uint32_t max_live = resident_min_live < n_points ? resident_min_live : n_points;
+    const uint32_t blocks = (max_live + SCT_TILE - 1) / SCT_TILE;
+    if (blocks == 0) return;
+    mon_launch_chain(MON_PDL_SCATTER, lo, k_encode_backward, dim3(blocks), dim3(SCT_THREADS), 0, st, g, n_points, resident_min_live, live_cnt, pts_c, genc, ctrl, grid_grad);
 }

@@ -490,7 +490,7 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
                     const size_t n_total = (size_t)b.R * 32;
 #pragma unroll
                     for (uint32_t q = 0; q < 16; ++q) b.genc[(size_t)q * n_total + slot] = packed[q];
-                    b.pts_c[(size_t)slot * 3 + 0] = pu[0]; b.pts_c[(size_t)slot * 3 + 1] = pu[1]; b.pts_c[(size_t)slot * 3 + 2] = pu[2];
+                    reinterpret_cast<float4*>(b.pts_c)[slot] = make_float4(pu[0], pu[1], pu[2], 0.0f);      // one 16-byte word per slot
                 }
             }
             if (b.d_enc && ray_ok) {   // parity hook: the uncompacted rows, point-major

@@ -80,7 +80,8 @@ k_optimizer_sweep(MonOpt o, MonCtrl* __restrict__ ctrl, float* __restrict__ pf, 
                   __half* __restrict__ gh, const float* __restrict__ mlp_partials, float* __restrict__ m,
                   float* __restrict__ v, uint32_t* __restrict__ ps, __half* __restrict__ ema,
                   const float* __restrict__ loss, uint32_t R, MonGrid grid, __half* __restrict__ planar,
-                  uint32_t n_mlp_ctas, uint32_t do_loss, uint32_t grid_i4_begin, uint32_t grid_i4_end) {
+                  uint32_t n_mlp_ctas, uint32_t do_loss, uint32_t grid_i4_begin, uint32_t grid_i4_end,
+                  __half* __restrict__ gcls, const uint32_t* __restrict__ live_cnt, uint32_t resident_min_live) {
     mon_pdl_wait();       // the gradient scatter has completed
     mon_pdl_trigger();
     if (ctrl->skip) return;
@@ -102,12 +103,13 @@ k_optimizer_sweep(MonOpt o, MonCtrl* __restrict__ ctrl, float* __restrict__ pf, 
     // CTA layout: the first n_mlp_ctas (n_mlp/32, or 0 in a grid-only launch) CTAs own the MLP weights (one WARP per 4
     // parameters: the lanes split the per-CTA gradient partials of the fused MLP kernel), every other CTA owns 1024
     // consecutive parameters of [grid_i4_begin, grid_i4_end) (one THREAD per 4 parameters).  n_params and n_mlp are
-    // multiples of 32 resp. 4.  The production iteration launches the MLP part only (MON_OPT_MLP): the grid is updated inside
-    // the fused scatter + Adam kernel (kernels_scatter_adam.cu).
+    // multiples of 32 resp. 4.
     const bool is_mlp = blockIdx.x < n_mlp_ctas;
     uint32_t i4;
     float g[4];
     uint2* gw;
+    __half* planar_f0 = nullptr;
+    uint32_t planar_stride = 0;
     uint2 wraw, eraw;   // fp16 weights and EMA of the 4 parameters: always needed, fetched together with the gradient
     if (is_mlp) {
         const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -137,23 +139,38 @@ k_optimizer_sweep(MonOpt o, MonCtrl* __restrict__ ctrl, float* __restrict__ pf, 
     } else {
         i4 = grid_i4_begin + ((blockIdx.x - n_mlp_ctas) * OPT_THREADS + threadIdx.x) * OPT_PER_THREAD;
         if (i4 >= grid_i4_end) return;
-        gw = reinterpret_cast<uint2*>(gh + i4);
-        const uint2 raw = *gw;
         wraw = *reinterpret_cast<const uint2*>(ph + i4);
         eraw = *reinterpret_cast<const uint2*>(ema + i4);
-        const __half2 a = *reinterpret_cast<const __half2*>(&raw.x), b = *reinterpret_cast<const __half2*>(&raw.y);
-        g[0] = __low2float(a); g[1] = __high2float(a); g[2] = __low2float(b); g[3] = __high2float(b);
-        if ((raw.x | raw.y) & 0x7fff7fffu) *gw = make_uint2(0u, 0u);   // consumed: the next scatter starts from zero
-    }
-    __half* planar_f0 = nullptr;
-    uint32_t planar_stride = 0;
-    if (!is_mlp) {
         // planar copy read by the hash-encode kernel: level l holds [feature 0 | feature 1]; entries e, e+1 are
         // adjacent in both feature arrays (level sizes are multiples of 8, so a pair never straddles a level)
         const uint32_t e = (i4 - o.n_mlp) >> 1;
         const uint32_t l = level_of_entry(grid, e);
-        planar_f0 = planar + (size_t)grid.offset[l] * 2 + (e - grid.offset[l]);
+        const uint32_t e_local = e - grid.offset[l];
+        planar_f0 = planar + (size_t)grid.offset[l] * 2 + e_local;
         planar_stride = grid.size[l];
+        // which scatter kernel produced this iteration's gradient (grid-uniform, decided by the live-sample count):
+        // the global f16x2 reductions fill the entry-ordered table gh, the shared-memory resident scatter the class-planar
+        // table gcls — per level [parity 0: f0 | f1][parity 1: f0 | f1], each size/2 fp16 (kernels_scatter_smem.cu)
+        const bool resident = gcls != nullptr && live_cnt[(ctrl->iter - 1) & 1u] >= resident_min_live;
+        if (!resident) {
+            gw = reinterpret_cast<uint2*>(gh + i4);
+            const uint2 raw = *gw;
+            const __half2 a = *reinterpret_cast<const __half2*>(&raw.x), b = *reinterpret_cast<const __half2*>(&raw.y);
+            g[0] = __low2float(a); g[1] = __high2float(a); g[2] = __low2float(b); g[3] = __high2float(b);
+            if ((raw.x | raw.y) & 0x7fff7fffu) *gw = make_uint2(0u, 0u);   // consumed: the next scatter starts from zero
+        } else {
+            // entries e_local (even: parity class 0) and e_local + 1 (class 1) share the slot e_local / 2 of their class arrays
+            const uint32_t half_n = planar_stride >> 1;
+            __half* c0 = gcls + (size_t)grid.offset[l] * 2 + (e_local >> 1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                // parameter k of the quad: entry parity k >> 1, feature k & 1 -> class array (k >> 1) * 2 + (k & 1) == k
+                __half* p = c0 + (size_t)k * half_n;
+                const __half hv = *p;
+                g[k] = __half2float(hv);
+                if (__half_as_ushort(hv) & 0x7fffu) *p = __ushort_as_half((unsigned short)0);
+            }
+        }
     }
     const OptimPtrs ptrs = {pf, ph, m, v, ps, ema};
     optim_quad(o, lr_base, old_db, new_db, is_mlp, i4, g, wraw, eraw, ptrs, planar_f0, planar_stride);
@@ -161,7 +178,7 @@ k_optimizer_sweep(MonOpt o, MonCtrl* __restrict__ ctrl, float* __restrict__ pf, 
 
 // used only by tests: snapshot of the loss-scaled gradient before the sweep consumes it
 __global__ void k_snapshot_grad(uint32_t n, uint32_t n_mlp, uint32_t n_partials, const __half* __restrict__ gh,
-                                const float* __restrict__ mlp_partials, float* __restrict__ out) {
+                                const float* __restrict__ mlp_partials, float* __restrict__ out, MonGrid grid, const __half* __restrict__ gcls) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (i < n_mlp) {
@@ -169,7 +186,15 @@ __global__ void k_snapshot_grad(uint32_t n, uint32_t n_mlp, uint32_t n_partials,
         for (uint32_t c = 0; c < n_partials; ++c) s = __fadd_rn(s, mlp_partials[(size_t)c * n_mlp + i]);
         out[i] = __half2float(__float2half_rn(s));
     } else {
-        out[i] = __half2float(gh[i]);
+        // one of the two gradient tables is all zero (the iteration's scatter kernel filled the other one)
+        float gv = __half2float(gh[i]);
+        if (gcls) {
+            const uint32_t e = (i - n_mlp) >> 1, f = (i - n_mlp) & 1u;
+            const uint32_t l = level_of_entry(grid, e);
+            const uint32_t e_local = e - grid.offset[l], half_n = grid.size[l] >> 1;
+            gv += __half2float(gcls[(size_t)grid.offset[l] * 2 + (size_t)((e_local & 1u) * 2u + f) * half_n + (e_local >> 1)]);
+        }
+        out[i] = gv;
     }
 }
 
@@ -185,7 +210,8 @@ void mon_launch_cast_params(uint32_t n, const float* pf, __half* ph, cudaStream_
 }
 void mon_launch_optimizer(const MonOpt& o, MonCtrl* ctrl, float* pf, __half* ph, __half* gh, const float* partials,
                           float* m, float* v, uint32_t* ps, __half* ema, const float* loss, uint32_t R, const MonGrid& grid,
-                          __half* planar, cudaStream_t st, int part, uint32_t level_begin, uint32_t level_end, const MonLaunchOpt& lo) {
+                          __half* planar, cudaStream_t st, int part, uint32_t level_begin, uint32_t level_end, const MonLaunchOpt& lo,
+                          __half* gcls, const uint32_t* live_cnt, uint32_t resident_min_live) {
     // part: MON_OPT_ALL everything (MLP weights + loss + whole grid); MON_OPT_MLP the MLP weights and the logged loss only;
     // MON_OPT_GRID the grid parameters of levels [level_begin, level_end) only; MON_OPT_MLP_GRID both of these
     if (level_end > grid.n_levels) level_end = grid.n_levels;
@@ -201,8 +227,9 @@ void mon_launch_optimizer(const MonOpt& o, MonCtrl* ctrl, float* pf, __half* ph,
     const uint32_t n_grid_ctas = with_grid ? (grid_quads + OPT_THREADS - 1) / OPT_THREADS : 1u;
     if (n_mlp_ctas + n_grid_ctas == 0) return;
     mon_launch_chain(MON_PDL_OPTIM, lo, k_optimizer_sweep, dim3(n_mlp_ctas + n_grid_ctas), dim3(OPT_THREADS), 0, st, o, ctrl, pf, ph, gh, partials, m,
-                     v, ps, ema, loss, R, grid, planar, n_mlp_ctas, with_mlp ? 1u : 0u, i4_begin, i4_end);
+                     v, ps, ema, loss, R, grid, planar, n_mlp_ctas, with_mlp ? 1u : 0u, i4_begin, i4_end, gcls, live_cnt, resident_min_live);
 }
-void mon_launch_snapshot_grad(uint32_t n, uint32_t n_mlp, uint32_t n_partials, const __half* gh, const float* partials, float* out, cudaStream_t st) {
-    k_snapshot_grad<<<(n + 255) / 256, 256, 0, st>>>(n, n_mlp, n_partials, gh, partials, out);
+void mon_launch_snapshot_grad(uint32_t n, uint32_t n_mlp, uint32_t n_partials, const __half* gh, const float* partials, float* out, cudaStream_t st,
+                              const MonGrid& grid, const __half* gcls) {
+    k_snapshot_grad<<<(n + 255) / 256, 256, 0, st>>>(n, n_mlp, n_partials, gh, partials, out, grid, gcls);
 }

@@ -9,9 +9,9 @@
 //   Render                        :1702-1830                        -> mon_object_render
 //   GetDensityOnGrid              :2007-2043                        -> mon_object_density_grid
 //
-// One training iteration is six kernels (batch, sample points, hash encode, fused MLP + render + loss +
-// backward, fused gradient scatter + Adam/EMA of the grid, optimizer of the MLP weights + logged loss),
-// captured as CUDA graphs of exactly the requested number of iterations and replayed; the reference
+// One training iteration is six working kernels (batch, sample points, hash encode, fused MLP + render + loss +
+// backward, gradient scatter — shared-memory resident or global reductions, chosen on the device by the live-sample
+// count —, optimizer sweep + logged loss), captured as CUDA graphs of exactly the requested number of iterations and replayed; the reference
 // issues ~25 launches, 3 cuRAND host calls and 3 blocking stream synchronisations per iteration
 // (SURVEY.md §3.1).  There is no CPU fallback anywhere in this
 // file: without a CUDA device every compute entry point returns MON_ERR_NO_DEVICE / MON_ERR_CUDA.
@@ -33,6 +33,7 @@
 
 #define MON_DEBIAS_LUT 32768  // steps covered by the Adam bias-correction table (offline jobs run 5000 iterations)
 #define MON_FRAMES_PER_SLAB 32
+#define MON_RESIDENT_MIN_LIVE 24576u   // live samples from which the shared-memory resident scatter takes an iteration (measured crossover)
 #define MON_GRAPH_CHUNK 64   // longest captured graph; a call of n iterations replays n / 64 of these + one graph of exactly n % 64
 #define MON_GRAPH_CACHE 6    // distinct remainder lengths kept instantiated per object (least recently used is dropped)
 
@@ -235,14 +236,15 @@ struct mon_object {
     void* scr[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t scr_cap[4] = {0, 0, 0, 0};
     // execution
-    cudaStream_t stream = nullptr, aux = nullptr, aux2 = nullptr;   // aux: next iteration's batch + sample points; aux2: MLP-weight optimizer; both forked inside the graphs
-    cudaEvent_t ev_fork_m = nullptr, ev_join = nullptr, ev_join2 = nullptr;
+    cudaStream_t stream = nullptr, aux = nullptr;   // aux: next iteration's batch + sample points, forked inside the graphs
+    cudaEvent_t ev_fork_m = nullptr, ev_join = nullptr;
     // compacted live samples of the iteration (fused MLP kernel -> scatter + Adam kernel)
     float* pts_c = nullptr; uint32_t* genc = nullptr; uint32_t* live_cnt = nullptr;
-    // gradient scatter + optimizer: false (default) = f16x2 reductions into the global gradient table + one optimizer sweep;
-    // true (MON_SCATTER_SMEM=1, opt-in) = the fused scatter + Adam kernel with shared-memory resident gradient slices
-    // (kernels_scatter_adam.cu): measured slower on B200, kept as the tested alternative
-    bool so_fuse = false;
+    // gradient scatter: iterations with >= resident_min_live live samples (a fresh object: all of them) go through the
+    // shared-memory resident scatter (kernels_scatter_smem.cu) into the class-planar table gcls, the others through global
+    // f16x2 reductions into gh; decided on the device per iteration, the optimizer sweep reads the table that was filled
+    __half* gcls = nullptr;
+    uint32_t resident_min_live = 0xffffffffu;
     // instantiated iteration graphs by length
     struct GraphSlot { uint32_t iters; cudaGraphExec_t exec; uint64_t stamp; };
     std::vector<GraphSlot> graphs;
@@ -644,23 +646,24 @@ static int launch_mlp(mon_object* o, const MonBatch& b, cudaStream_t st) {
     if (e != cudaSuccess) return fail(MON_ERR_CUDA, "fused MLP launch: %s", cudaGetErrorString(e));
     return MON_OK;
 }
-// gradient scatter; in the fused mode also Adam / EMA of the grid.  grad_snap: parity hook (fused mode writes the grid part itself)
-static int launch_scatter(mon_object* o, cudaStream_t st, float* grad_snap) {
-    if (!o->so_fuse) {
-        mon_launch_encode_backward(o->grid, o->N, o->live_cnt, o->pts_c, o->genc, o->ctrl_late, o->gh + o->n_mlp, st);
-        return MON_OK;
+// gradient scatter: two kernels, one of which exits at once (the iteration's live-sample count decides on the device)
+static int launch_scatter(mon_object* o, cudaStream_t st) {
+    if (o->resident_min_live != 0xffffffffu) {
+        cudaError_t e = mon_launch_scatter_resident(o->grid, o->N, o->resident_min_live, o->live_cnt, o->pts_c, o->genc, o->ctrl_late, o->gcls,
+                                                    (uint32_t)o->sm_count, st);
+        if (e != cudaSuccess) return fail(MON_ERR_CUDA, "resident scatter launch: %s", cudaGetErrorString(e));
     }
-    cudaError_t e = mon_launch_scatter_adam(o->grid, o->opt, o->N, o->live_cnt, o->pts_c, o->genc, o->ctrl_late, o->pf, o->ph, o->m, o->v, o->ps,
-                                            o->ema, o->ph_planar, o->gh + o->n_mlp, grad_snap, true, (uint32_t)o->sm_count, st);
-    if (e != cudaSuccess) return fail(MON_ERR_CUDA, "scatter + Adam launch: %s", cudaGetErrorString(e));
+    mon_launch_encode_backward(o->grid, o->N, o->resident_min_live, o->live_cnt, o->pts_c, o->genc, o->ctrl_late, o->gh + o->n_mlp, st);
     return MON_OK;
 }
+// kernels one iteration launches: batch, points, encode, MLP, scatter (one or two), optimizer
+static int scatter_launches(const mon_object* o) { return (o->resident_min_live != 0xffffffffu ? 1 : 0) + (o->resident_min_live != 0u ? 1 : 0); }
 // optimizer sweep: MLP weights (fixed-order reduction of the per-CTA partials, Adam, EMA) + logged loss + the grid (Adam with
-// per-parameter steps, EMA, gradient zeroing, planar weight copy); in the fused mode the grid part is skipped
+// per-parameter steps, EMA, gradient zeroing, planar weight copy)
 static void launch_optimizer(mon_object* o, cudaStream_t st, bool pdl) {
     MonLaunchOpt lo; lo.pdl = pdl;
     mon_launch_optimizer(o->opt, o->ctrl_late, o->pf, o->ph, o->gh, o->partials, o->m, o->v, o->ps, o->ema, o->loss, o->R, o->grid,
-                         o->ph_planar, st, o->so_fuse ? MON_OPT_MLP : MON_OPT_ALL, 0, 0xffffffffu, lo);
+                         o->ph_planar, st, MON_OPT_ALL, 0, 0xffffffffu, lo, o->gcls, o->live_cnt, o->resident_min_live);
 }
 
 // serial version (injected / profiled iterations).  ev (optional, MON_N_STAGES+1 events): recorded before each
@@ -679,9 +682,9 @@ static int enqueue_iteration(mon_object* o, const MonBatch& b, bool snapshot_gra
     if ((rc = launch_mlp(o, b, st)) != MON_OK) return rc;
     ++n;
     if (ev) CK(cudaEventRecord(ev[4], st));
-    if ((rc = launch_scatter(o, st, snapshot_grad ? o->grad_snap : nullptr)) != MON_OK) return rc;
-    ++n;
-    if (snapshot_grad) { mon_launch_snapshot_grad(o->so_fuse ? o->n_mlp : o->P, o->n_mlp, o->opt.n_partials, o->gh, o->partials, o->grad_snap, st); ++n; }
+    if ((rc = launch_scatter(o, st)) != MON_OK) return rc;
+    n += scatter_launches(o);
+    if (snapshot_grad) { mon_launch_snapshot_grad(o->P, o->n_mlp, o->opt.n_partials, o->gh, o->partials, o->grad_snap, st, o->grid, o->gcls); ++n; }
     if (ev) CK(cudaEventRecord(ev[5], st));
     launch_optimizer(o, st, !snapshot_grad); ++n;
     if (ev) CK(cudaEventRecord(ev[6], st));
@@ -693,7 +696,7 @@ static int enqueue_iteration(mon_object* o, const MonBatch& b, bool snapshot_gra
 static int capture_graph(mon_object* o, int iters, cudaGraphExec_t* out) {
     const MonBatch b = make_batch(o, false, false);
     cudaGraph_t g = nullptr;
-    cudaStream_t st = o->stream, aux = o->aux, aux2 = o->aux2;
+    cudaStream_t st = o->stream, aux = o->aux;
     CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     int rc = MON_OK;
     cudaError_t e = cudaSuccess;
@@ -704,21 +707,15 @@ static int capture_graph(mon_object* o, int iters, cudaGraphExec_t* out) {
         // after a join the encode kernel's predecessor in the stream is not a plain kernel node: no programmatic edge there
         if ((rc = launch_encode(o, st, i == 0)) != MON_OK) break;
         if ((rc = launch_mlp(o, b, st)) != MON_OK) break;
-        if (fork || o->so_fuse) { if ((e = cudaEventRecord(o->ev_fork_m, st)) != cudaSuccess) break; }
-        if (o->so_fuse) {
-            if ((e = cudaStreamWaitEvent(aux2, o->ev_fork_m, 0)) != cudaSuccess) break;
-            launch_optimizer(o, aux2, false);
-            if ((e = cudaEventRecord(o->ev_join2, aux2)) != cudaSuccess) break;
-        }
         if (fork) {
+            if ((e = cudaEventRecord(o->ev_fork_m, st)) != cudaSuccess) break;
             if ((e = cudaStreamWaitEvent(aux, o->ev_fork_m, 0)) != cudaSuccess) break;
             launch_batch(o, b, aux);
             launch_points(o, b, aux, false);
             if ((e = cudaEventRecord(o->ev_join, aux)) != cudaSuccess) break;
         }
-        if ((rc = launch_scatter(o, st, nullptr)) != MON_OK) break;
-        if (o->so_fuse) { if ((e = cudaStreamWaitEvent(st, o->ev_join2, 0)) != cudaSuccess) break; }
-        else launch_optimizer(o, st, true);
+        if ((rc = launch_scatter(o, st)) != MON_OK) break;
+        launch_optimizer(o, st, true);
         if (fork && (e = cudaStreamWaitEvent(st, o->ev_join, 0)) != cudaSuccess) break;
     }
     cudaError_t e2 = cudaStreamEndCapture(st, &g);
@@ -754,7 +751,7 @@ static int graph_for(mon_object* o, uint32_t iters, cudaGraphExec_t* out) {
 }
 
 // kernels launched by one replay of an `iters`-iteration graph
-static uint64_t launches_in_graph(const mon_object*, uint32_t iters) { return 6ull * iters; }
+static uint64_t launches_in_graph(const mon_object* o, uint32_t iters) { return (5ull + (uint64_t)scatter_launches(o)) * iters; }
 
 int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uint8_t instance_id,
                       const float obj_Tow[16], const float bmin[3], const float bmax[3], mon_object** out) {
@@ -765,9 +762,6 @@ int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uin
     MonGrid grid;
     if (!validate_config(*cfg, why) || !make_grid(*cfg, grid, why)) return fail(MON_ERR_ARG, "unsupported config: %s", why.c_str());
     for (int k = 0; k < 3; ++k) if (!(bmax[k] > bmin[k])) return fail(MON_ERR_ARG, "empty bounding box");
-    if (!mon_scatter_adam_supported(grid))
-        return fail(MON_ERR_ARG, "unsupported config: every level's table must have a power-of-two size and the dense levels an even resolution "
-                                 "(true for base_resolution = 2^k with per_level_scale = 2, the reference's base.json)");
     CK(cudaSetDevice(ds->gpu));
     mon_object* o = new mon_object();
     o->ds = ds; o->cfg = *cfg; o->grid = grid; o->seed = seed;
@@ -819,21 +813,24 @@ int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uin
     OALLOC(o->target, R * 12); OALLOC(o->target_depth, R * 4); OALLOC(o->bg, R * 12);
     OALLOC(o->rgb_rays, R * 12); OALLOC(o->depth_rays, R * 4); OALLOC(o->mask_rays, R * 4); OALLOC(o->loss, R * 4);
     OALLOC(o->pts, N * 12); OALLOC(o->enc, N * MON_IN * 2);
-    OALLOC(o->pts_c, N * 12); OALLOC(o->genc, N * (size_t)MON_MAX_LEVELS * 4); OALLOC(o->live_cnt, 8);
+    OALLOC(o->pts_c, N * 16); OALLOC(o->genc, N * (size_t)MON_MAX_LEVELS * 4); OALLOC(o->live_cnt, 8);
     OALLOC(o->ph_planar, (size_t)o->n_grid * 2 + 16);
+    OALLOC(o->gcls, (size_t)o->n_grid * 2 + 16);
     OALLOC(o->partials, (size_t)o->n_ctas * o->n_mlp * 4);
     OALLOC(o->debias_lut, (size_t)MON_DEBIAS_LUT * 4);
     o->opt.debias_lut = o->debias_lut; o->opt.n_debias_lut = MON_DEBIAS_LUT;
 #undef OALLOC
-    if (const char* env = getenv("MON_SCATTER_SMEM")) o->so_fuse = atoi(env) != 0;
+    // live-sample count from which an iteration's gradients are scattered through shared memory (MON_SCATTER_RESIDENT_MIN: A/B
+    // and tests; 0 = always, -1 = never).  Configurations the resident kernel does not cover keep the global reductions.
+    o->resident_min_live = MON_RESIDENT_MIN_LIVE;
+    if (const char* env = getenv("MON_SCATTER_RESIDENT_MIN")) { const long v = atol(env); o->resident_min_live = v < 0 ? 0xffffffffu : (uint32_t)v; }
+    if (!mon_scatter_resident_supported(grid)) o->resident_min_live = 0xffffffffu;
     cudaError_t e;
     if ((e = cudaMallocHost(&o->h_ctrl, sizeof(MonCtrl))) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&o->aux, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&o->aux2, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&o->ev_fork_m, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&o->ev_join, cudaEventDisableTiming)) != cudaSuccess ||
-        (e = cudaEventCreateWithFlags(&o->ev_join2, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreate(&o->ev0)) != cudaSuccess || (e = cudaEventCreate(&o->ev1)) != cudaSuccess) {
         mon_object_destroy(o);
         return fail(MON_ERR_CUDA, "object setup: %s", cudaGetErrorString(e));
@@ -890,15 +887,15 @@ int mon_object_destroy(mon_object* o) {
     drop_graphs(o);
     void* ptrs[] = {o->pf, o->m, o->v, o->ps, o->ph, o->gh, o->ema, o->ctrl_state, o->ctrl, o->ctrl_late, o->d_boxes, o->rays, o->ray_inst, o->target,
                     o->target_depth, o->bg, o->rgb_rays, o->depth_rays, o->mask_rays, o->loss, o->pts, o->pts_c, o->genc, o->live_cnt, o->debias_lut, o->enc,
-                    o->d_enc, o->ph_planar, o->partials,
+                    o->d_enc, o->ph_planar, o->gcls, o->partials,
                     o->dbg_out, o->dbg_dout, o->inj_xy, o->inj_col, o->inj_dt, o->grad_snap, o->r_rays, o->r_orig, o->r_nhit, o->r_enc,
                     o->r_jit, o->r_rgb, o->r_depth, o->r_mask, o->r_Twc, o->r_pts, o->r_planar};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (void* p : o->scr) if (p) cudaFree(p);
     if (o->h_ctrl) cudaFreeHost(o->h_ctrl);
-    cudaEvent_t evs[] = {o->ev0, o->ev1, o->ev_fork_m, o->ev_join, o->ev_join2};
+    cudaEvent_t evs[] = {o->ev0, o->ev1, o->ev_fork_m, o->ev_join};
     for (cudaEvent_t ev : evs) if (ev) cudaEventDestroy(ev);
-    cudaStream_t sts[] = {o->aux2, o->aux, o->stream};
+    cudaStream_t sts[] = {o->aux, o->stream};
     for (cudaStream_t st : sts) if (st) cudaStreamDestroy(st);
     delete o;
     return MON_OK;
@@ -1461,6 +1458,16 @@ int mon_debug_encode_pieces(const mon_config* cfg, uint32_t n_points, uint32_t n
     if (level_end > grid.n_levels) level_end = grid.n_levels;
     if (level_begin >= level_end) return fail(MON_ERR_ARG, "empty level range");
     mon_encode_pieces_host(grid, n_points, n_ctas, level_begin, level_end, out4);
+    return MON_OK;
+}
+
+int mon_debug_scatter_pieces(const mon_config* cfg, uint32_t n_live, uint32_t n_ctas, uint32_t* out4) {
+    if (!cfg || !out4 || n_ctas == 0) return fail(MON_ERR_ARG, "NULL argument");
+    std::string why;
+    MonGrid grid;
+    if (!validate_config(*cfg, why) || !make_grid(*cfg, grid, why)) return fail(MON_ERR_ARG, "unsupported config: %s", why.c_str());
+    if (!mon_scatter_resident_supported(grid)) return fail(MON_ERR_ARG, "the shared-memory resident scatter does not cover this configuration");
+    mon_scatter_resident_pieces_host(grid, n_live, n_ctas, out4);
     return MON_OK;
 }
 

@@ -87,9 +87,10 @@ cudaError_t mon_launch_encode_forward(const MonGrid& g, uint32_t n_points, const
                                       uint32_t level_end = 0xffffffffu, const MonLaunchOpt& lo = MonLaunchOpt());
 void mon_launch_planarize(const MonGrid& g, const __half* inter, __half* planar, cudaStream_t st);
 void mon_encode_pieces_host(const MonGrid& g, uint32_t n_points, uint32_t n_ctas, uint32_t level_begin, uint32_t level_end, uint32_t* out4);
-// gradient scatter with global f16x2 reductions over the compacted live samples (written by the fused MLP kernel)
-void mon_launch_encode_backward(const MonGrid& g, uint32_t n_points, const uint32_t* live_cnt, const float* pts_c, const uint32_t* genc,
-                                const MonCtrl* ctrl, __half* grid_grad, cudaStream_t st, const MonLaunchOpt& lo = MonLaunchOpt());
+// gradient scatter with global f16x2 reductions over the compacted live samples (written by the fused MLP kernel); takes the
+// iterations with fewer than resident_min_live live samples (the others: kernels_scatter_smem.cu)
+void mon_launch_encode_backward(const MonGrid& g, uint32_t n_points, uint32_t resident_min_live, const uint32_t* live_cnt, const float* pts_c,
+                                const uint32_t* genc, const MonCtrl* ctrl, __half* grid_grad, cudaStream_t st, const MonLaunchOpt& lo = MonLaunchOpt());
 
 // kernels_mlp_tc.cu (tcgen05 / TMEM product family)
 cudaError_t mon_launch_mlp_train_tc(const MonBatch& b, const MonLossCfg& lc, uint32_t n_hidden, uint32_t n_mlp,
@@ -106,14 +107,15 @@ void mon_launch_cast_params(uint32_t n, const float* pf, __half* ph, cudaStream_
 void mon_launch_optimizer(const MonOpt& o, MonCtrl* ctrl, float* pf, __half* ph, __half* gh, const float* partials,
                           float* m, float* v, uint32_t* ps, __half* ema, const float* loss, uint32_t R, const MonGrid& grid,
                           __half* planar, cudaStream_t st, int part = 0, uint32_t level_begin = 0, uint32_t level_end = 0xffffffffu,
-                          const MonLaunchOpt& lo = MonLaunchOpt());
+                          const MonLaunchOpt& lo = MonLaunchOpt(), __half* gcls = nullptr, const uint32_t* live_cnt = nullptr,
+                          uint32_t resident_min_live = 0xffffffffu);
 enum { MON_OPT_ALL = 0, MON_OPT_MLP = 1, MON_OPT_GRID = 2, MON_OPT_MLP_GRID = 3 };
-// kernels_scatter_adam.cu: gradient scatter into shared-memory resident table slices fused with Adam + EMA of the grid
-uint32_t mon_scatter_adam_jobs(const MonGrid& g);
-bool mon_scatter_adam_supported(const MonGrid& g);   // power-of-two tables, even resolution on the dense levels
-cudaError_t mon_launch_scatter_adam(const MonGrid& g, const MonOpt& o, uint32_t n_points, const uint32_t* live_cnt, const float* pts_c,
-                                    const uint32_t* genc, const MonCtrl* ctrl, float* pf, __half* ph, float* m, float* v, uint32_t* ps,
-                                    __half* ema, __half* planar, __half* gh_grid, float* grad_snap, bool fuse, uint32_t sm_count,
-                                    cudaStream_t st, const MonLaunchOpt& lo = MonLaunchOpt());
+// kernels_scatter_smem.cu: gradient scatter into shared-memory resident fixed-point slices of the gradient table, flushed with
+// TMA bulk reductions into the class-planar table gcls; takes the iterations with >= min_live live samples
+bool mon_scatter_resident_supported(const MonGrid& g);   // power-of-two tables of >= 16 entries, even dense-level resolutions
+void mon_scatter_resident_pieces_host(const MonGrid& g, uint32_t n_live, uint32_t n_ctas, uint32_t* out4);
+cudaError_t mon_launch_scatter_resident(const MonGrid& g, uint32_t n_points, uint32_t min_live, const uint32_t* live_cnt, const float* pts_c,
+                                        const uint32_t* genc, const MonCtrl* ctrl, __half* gcls, uint32_t sm_count, cudaStream_t st,
+                                        const MonLaunchOpt& lo = MonLaunchOpt());
 void mon_launch_snapshot_grad(uint32_t n, uint32_t n_mlp, uint32_t n_partials, const __half* gh, const float* partials,
-                              float* out, cudaStream_t st);
+                              float* out, cudaStream_t st, const MonGrid& grid, const __half* gcls);

@@ -105,7 +105,7 @@ struct MonBatch {
     __half* d_enc;    // [N][32] point-major dL/dencoding: parity hook only (nullptr in production)
     const float* pts; // [N][3] unit-cube sample positions of this iteration (read by the fused MLP kernel for the compaction)
     // compacted live samples (non-zero dL/dencoding row), written by the fused MLP kernel for the scatter+Adam kernel:
-    // slot k holds position pts_c[k][3] and, per level l, the level's two fp16 gradients as one word genc[l * N + k]
+    // slot k holds position pts_c[k][4] (x, y, z, unused: one 16-byte load) and, per level l, the level's two fp16 gradients as one word genc[l * N + k]
     float* pts_c;
     uint32_t* genc;
     uint32_t* live_cnt;   // [2]: number of live samples of the iteration, indexed by (iteration & 1); zeroed by the batch kernel

@@ -1,5 +1,4 @@
-// optim_math.cuh — the per-parameter optimizer arithmetic shared by the optimizer sweep (kernels_optim.cu: MLP weights,
-// and the grid in the unfused A/B mode) and the fused scatter + Adam kernel (kernels_scatter_adam.cu: grid).
+// optim_math.cuh — the per-parameter optimizer arithmetic of the optimizer sweep (kernels_optim.cu).
 //   adam_step<__half>                         TCNN optimizers/adam.h:48-118
 //   ema_step_half_precision<__half>           TCNN optimizers/ema.h:62-76,102-136
 #pragma once
@@ -84,49 +83,4 @@ __device__ __forceinline__ void optim_quad(const MonOpt& o, float lr_base, float
         nf[k] = __fmul_rn(__fmaf_rn(__half2float(wh[k]), 1.0f - o.ema_decay, __fmul_rn(__fmul_rn(ev[k], o.ema_decay), old_db)), new_db);
     const __half2 n01 = __floats2half2_rn(nf[0], nf[1]), n23 = __floats2half2_rn(nf[2], nf[3]);
     *reinterpret_cast<uint2*>(p.ema + i4) = make_uint2(*reinterpret_cast<const uint32_t*>(&n01), *reinterpret_cast<const uint32_t*>(&n23));
-}
-
-// Adam + EMA for ONE grid entry = the 2 consecutive parameters at i2 (the fused scatter + Adam kernel owns the entries of one
-// index-parity class, i.e. every other entry).  g0 / g1: loss-scaled fp16 gradients widened to float; planar_f0: the entry's
-// slot in the feature-0 array of the planar weight copy (feature 1: planar_stride halves further).
-__device__ __forceinline__ void optim_pair(const MonOpt& o, float lr_base, float old_db, float new_db, uint32_t i2, float g0, float g1,
-                                           const OptimPtrs& p, __half* planar_f0, uint32_t planar_stride) {
-    float g[2] = {g0, g1};
-    bool touched[2];
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        g[k] = o.loss_scale_pow2 ? __fmul_rn(g[k], o.inv_loss_scale) : __fdiv_rn(g[k], o.loss_scale);
-        touched[k] = g[k] != 0.0f;                 // zero gradient => Adam skips the parameter (adam.h:75-79)
-    }
-    const __half2 wraw = *reinterpret_cast<const __half2*>(p.ph + i2);
-    const __half2 eraw = *reinterpret_cast<const __half2*>(p.ema + i2);
-    __half wh[2] = {__low2half(wraw), __high2half(wraw)};
-    if (touched[0] || touched[1]) {
-        float2 w2 = *reinterpret_cast<const float2*>(p.pf + i2);
-        float2 m2 = *reinterpret_cast<const float2*>(p.m + i2);
-        float2 v2 = *reinterpret_cast<const float2*>(p.v + i2);
-        uint2 s2 = *reinterpret_cast<const uint2*>(p.ps + i2);
-        float* wp = &w2.x; float* mp = &m2.x; float* vp = &v2.x; uint32_t* sp = &s2.x;
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            if (touched[k]) {
-                wp[k] = adam_one(o, lr_base, g[k], false, wp[k], mp[k], vp[k], sp[k]);
-                wh[k] = __float2half_rn(wp[k]);
-            }
-        }
-        *reinterpret_cast<float2*>(p.pf + i2) = w2;
-        *reinterpret_cast<float2*>(p.m + i2) = m2;
-        *reinterpret_cast<float2*>(p.v + i2) = v2;
-        *reinterpret_cast<uint2*>(p.ps + i2) = s2;
-        *reinterpret_cast<__half2*>(p.ph + i2) = __halves2half2(wh[0], wh[1]);
-        planar_f0[0] = wh[0];
-        planar_f0[planar_stride] = wh[1];
-    }
-    // ---- EMA over all params with the global step (ema.h:62-76)
-    const float ev[2] = {__low2float(eraw), __high2float(eraw)};
-    float nf[2];
-#pragma unroll
-    for (int k = 0; k < 2; ++k)
-        nf[k] = __fmul_rn(__fmaf_rn(__half2float(wh[k]), 1.0f - o.ema_decay, __fmul_rn(__fmul_rn(ev[k], o.ema_decay), old_db)), new_db);
-    *reinterpret_cast<__half2*>(p.ema + i2) = __floats2half2_rn(nf[0], nf[1]);
 }

@@ -55,7 +55,7 @@ int main(int argc, char** argv) {
         std::vector<char> ref(nv, 0);
         for (uint32_t i : m.indices) { if (i >= nv) ++bad_padding; else ref[i] = 1; }
         for (char r : ref) unreferenced += !r;
-        for (int mask = 0; mask < 256; ++mask) cases_seen += mesh::mc::table()[mask].n > 0;
+        for (int mask = 0; mask < 256; ++mask) cases_seen += mesh::mc::TRIANGLES[mask][0] >= 0;
     }
     // every undirected edge shared by exactly two triangles, and traversed once in each direction (consistent winding)
     std::map<std::pair<uint32_t, uint32_t>, int> directed;
@@ -96,8 +96,8 @@ int main(int argc, char** argv) {
             for (int d = 0; d < 3; ++d) p[k][d] = (m.verts[3 * m.indices[3 * f + k] + d] - bmin[d]) / (bmax[d] - bmin[d]);
         vol6 += p[0][0] * (p[1][1] * p[2][2] - p[1][2] * p[2][1]) - p[0][1] * (p[1][0] * p[2][2] - p[1][2] * p[2][0]) + p[0][2] * (p[1][0] * p[2][1] - p[1][1] * p[2][0]);
     }
-    // the derived triangle lists respect the cube's symmetries: a configuration and its image under a rotation about the z axis
-    // or the x axis (together they generate all 24 rotations) have the same number of triangles
+    // the table respects the cube's symmetries: a configuration and its image under a rotation about the z axis or the x axis
+    // (together they generate all 24 rotations) have the same number of triangles
     size_t asym = 0;
     {
         const int rz[8] = {1, 2, 3, 0, 5, 6, 7, 4};   // corner c -> its image under a quarter turn about z
@@ -106,7 +106,8 @@ int main(int argc, char** argv) {
             for (const int* rot : {rz, rx}) {
                 int img = 0;
                 for (int c = 0; c < 8; ++c) if (mask >> c & 1) img |= 1 << rot[c];
-                asym += mesh::mc::table()[mask].n != mesh::mc::table()[img].n;
+                auto count = [](int m) { int n = 0; while (n < 15 && mesh::mc::TRIANGLES[m][n] >= 0) ++n; return n; };
+                asym += count(mask) != count(img);
             }
     }
     printf("volume %.6f asymmetric_cases %zu ", vol6 / 6.0, asym);

@@ -123,6 +123,38 @@ def test_encode_work_split_tiles_the_job_space(lib):
                 assert pos == n, (log2, n, ctas, j, segs)
 
 
+def test_scatter_work_split_tiles_the_job_space(lib):
+    """k_scatter_resident cuts the flattened [(level, index class) job][live sample] space into one piece per CTA by cost
+    (coarse dense levels are dearer: same-address shared-memory atomics).  Every (job, sample) must be covered exactly once —
+    a gap would silently drop gradient.  Host mirror of the kernel's two functions."""
+    import ctypes as C
+    from ro_map_b200 import core
+    rng = np.random.default_rng(6)
+    cases = [(131072, 140), (131072, 148), (24576, 140), (1, 1), (7, 140), (3, 64), (1048576, 140)]
+    cases += [(int(rng.integers(1, 300000)), int(rng.integers(1, 160))) for _ in range(40)]
+    for log2, base in ((16, 16), (12, 16), (14, 8)):
+        cfg = core.default_config(log2_hashmap_size=log2, base_resolution=base)
+        for n, ctas in cases:
+            out = np.zeros((ctas, 4), np.uint32)
+            assert lib.mon_debug_scatter_pieces(C.byref(cfg), n, ctas, out.ctypes.data_as(C.POINTER(C.c_uint32))) == 0
+            cover = {j: [] for j in range(64)}
+            for jb, pb, je, pe in out.tolist():
+                job = jb
+                while job < 64 and (job < je or (job == je and pe > 0)):      # the kernel's loop
+                    p0 = pb if job == jb else 0
+                    p1 = pe if job == je else n
+                    if p1 > p0:
+                        cover[job].append((p0, p1))
+                    job += 1
+            for j, segs in cover.items():
+                segs.sort()
+                pos = 0
+                for a, b in segs:
+                    assert a == pos, (log2, n, ctas, j, segs)
+                    pos = b
+                assert pos == n, (log2, n, ctas, j, segs)
+
+
 def test_no_cpu_fallback(lib):
     """Without a CUDA device the compute entry points must fail, not silently compute on the host."""
     from ro_map_b200 import core

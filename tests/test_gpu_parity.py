@@ -352,31 +352,43 @@ def test_graph_path_matches_serial_chain(core, gpu_dataset, small_seq):
     assert a.step == 92 + 3 + 60 and np.isfinite(l_end) and l_end < 1.2 * la + 1e-3
 
 
-def test_fused_smem_scatter_mode(core, oracle, gpu_dataset, small_seq, monkeypatch):
-    """The opt-in fused scatter + Adam kernel (MON_SCATTER_SMEM=1, kernels_scatter_adam.cu: gradient slices resident in shared
-    memory, parity-class jobs, Adam + EMA of the grid in the same kernel) gives the same iteration as the default path:
-    stage by stage against the oracle, and graph iterations against the default mode."""
+def test_resident_scatter_against_global_reductions(core, oracle, gpu_dataset, small_seq, monkeypatch):
+    """The two gradient-scatter kernels are interchangeable.  Iterations with many live samples go through the shared-memory
+    resident scatter (kernels_scatter_smem.cu: exact fixed-point partial sums per (level, parity class, feature) slice, flushed
+    with TMA bulk reductions into the class-planar gradient table), the others through global f16x2 reductions
+    (k_encode_backward, entry-interleaved table); the iteration's live-sample count decides on the device and the optimizer
+    sweep reads the table that was filled.  MON_SCATTER_RESIDENT_MIN forces one or the other here: stage by stage against the
+    oracle with the resident kernel, then whole iterations of one mode against the other, then a threshold in between so that
+    one object switches kernels while it trains."""
     seq, obj = small_seq, small_seq.objects[0]
-    monkeypatch.setenv("MON_SCATTER_SMEM", "1")
+    monkeypatch.setenv("MON_SCATTER_RESIDENT_MIN", "0")
     check_one_iteration_stage_by_stage(core, oracle, gpu_dataset, seq, obj, 512, 1)
+    check_one_iteration_stage_by_stage(core, oracle, gpu_dataset, seq, obj, 256, 2)
     cfg = core.default_config(rays_per_batch=1024)
     bmin, bmax = -1.1 * obj.half, 1.1 * obj.half
-    a = core.NerfObject(gpu_dataset, cfg, obj.Tow, bmin, bmax, obj.instance_id)      # fused mode (read at creation)
-    monkeypatch.delenv("MON_SCATTER_SMEM")
-    b = core.NerfObject(gpu_dataset, cfg, obj.Tow, bmin, bmax, obj.instance_id)      # default mode
-    for g in (a, b):
+    a = core.NerfObject(gpu_dataset, cfg, obj.Tow, bmin, bmax, obj.instance_id)      # always resident (read at creation)
+    monkeypatch.setenv("MON_SCATTER_RESIDENT_MIN", "-1")
+    b = core.NerfObject(gpu_dataset, cfg, obj.Tow, bmin, bmax, obj.instance_id)      # never
+    monkeypatch.setenv("MON_SCATTER_RESIDENT_MIN", "16000")
+    c = core.NerfObject(gpu_dataset, cfg, obj.Tow, bmin, bmax, obj.instance_id)      # switches as the live count falls
+    monkeypatch.delenv("MON_SCATTER_RESIDENT_MIN")
+    for g in (a, b, c):
         g.set_bboxes(obj.boxes)
         g.train(1)
-    ma, mb = a.state("master"), b.state("master")
+    ma, mb, mc = a.state("master"), b.state("master"), c.state("master")
     assert (a.state("param_steps") == b.state("param_steps")).mean() >= 0.999
     assert (np.abs(ma - mb) <= 1e-6).mean() >= 0.999
     assert np.array_equal(ma[:a.n_mlp], mb[:a.n_mlp])
-    la, lb = a.train(70), b.train(70)
-    assert a.step == b.step == 71 and abs(la - lb) <= 0.03 * abs(lb) + 1e-4, (la, lb)
-    ea, eb = a.state("ema"), b.state("ema")
-    assert np.linalg.norm(ea - eb) <= 0.05 * np.linalg.norm(eb)
-    a.close()
-    b.close()
+    assert (np.abs(ma - mc) <= 1e-6).mean() >= 0.9999          # the same kernel took the first iteration of a and c
+    la, lb, lc = a.train(70), b.train(70), c.train(70)
+    assert a.step == b.step == c.step == 71
+    assert abs(la - lb) <= 0.03 * abs(lb) + 1e-4 and abs(lc - lb) <= 0.03 * abs(lb) + 1e-4, (la, lb, lc)
+    ea, eb, ec = a.state("ema"), b.state("ema"), c.state("ema")
+    assert np.linalg.norm(ea - eb) <= 0.05 * np.linalg.norm(eb) and np.linalg.norm(ec - eb) <= 0.05 * np.linalg.norm(eb)
+    lf = c.live_fraction * 32768
+    assert lf < 16000 < 32768, lf                              # c really crossed its threshold
+    for g in (a, b, c):
+        g.close()
 
 
 def test_optimizer_bit_exact_for_equal_gradients(core, oracle, gpu_dataset, small_seq):

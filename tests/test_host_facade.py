@@ -150,7 +150,8 @@ def test_mesh_extraction_on_analytic_field(tmp_path):
     """ro_map_b200/host/mesh.h (GenerateMesh/TransCPUMesh/SaveMesh replacement) on an analytic sphere field, the two
     C-ABI calls stubbed (tests/host/mesh_check.cpp): closed 2-manifold with consistent winding (Euler characteristic 2),
     vertices on the iso-surface, outward 1-ring normals, colours = logistic(rgb logits), reference PLY layout and vertex padding;
-    then watertightness on white noise (every marching-cubes configuration)."""
+    then white noise (every marching-cubes configuration): consistent winding everywhere; the classic table the reference uses is
+    known to leave cracks on faces whose corners alternate, identically in the reference (golden comparison: test_golden_romap.py)."""
     exe = tmp_path / "mesh_check"
     subprocess.run(["g++", "-O2", "-std=c++17", f"-I{ROOT / 'ro_map_b200' / 'host'}", f"-I{ROOT / 'include'}",
                     str(ROOT / "tests" / "host" / "mesh_check.cpp"), "-o", str(exe)], check=True)
@@ -162,7 +163,7 @@ def test_mesh_extraction_on_analytic_field(tmp_path):
         assert fact["faces"] == 2 * fact["verts"] - 4                           # closed triangle mesh of genus 0
         assert fact["max_r_err"] < r_tol and fact["min_normal_dot"] > 0.95 and fact["bad_colors"] == 0, fact
         # the reference's winding (geometric normals into the dense side) encloses the sphere's volume with a negative sign;
-        # the derived triangle lists respect the cube's rotations
+        # the table respects the cube's rotations
         assert abs(-fact["volume"] - 4.0 / 3.0 * np.pi * 0.3 ** 3) < (2e-3 if res == 64 else 4e-3), fact
         assert fact["asymmetric_cases"] == 0
         txt = ply.read_text().splitlines()
@@ -173,12 +174,13 @@ def test_mesh_extraction_on_analytic_field(tmp_path):
         assert len(txt) - len(hdr) == int(fact["padded_verts"] + fact["faces"])
         # the reference pads the vertex array to a multiple of 128 with zero vertices (marching_cubes.cu:499); every configuration has triangles
         assert fact["bad_padding"] == 0 and fact["unreferenced"] == 0 and fact["cases"] == 254, fact
-    # white noise with an empty border: all 256 cell configurations incl. faces whose corners alternate — still a closed surface in
-    # which every edge is shared by exactly two triangles with opposite directions (no cracks, consistent winding)
+    # white noise with an empty border: all 256 cell configurations incl. faces whose corners alternate.  The published table
+    # resolves such a face differently for a configuration and its complement, so a few percent of the edges are open there
+    # (exactly as in the reference's mesh: the triangle sets are identical, tests/test_golden_romap.py); every vertex is used
     out = subprocess.run([str(exe), "40", str(tmp_path / "noise.ply"), "random"], capture_output=True, text=True, check=True).stdout.split()
     fact = {out[i]: float(out[i + 1]) for i in range(0, len(out), 2)}
-    assert fact["verts"] > 50000 and fact["bad_edges"] == 0 and fact["bad_padding"] == 0 and fact["unreferenced"] == 0, fact
-    assert 2 * fact["edges"] == 3 * fact["faces"]
+    assert fact["verts"] > 50000 and fact["bad_padding"] == 0 and fact["unreferenced"] == 0, fact
+    assert fact["bad_edges"] <= 0.08 * fact["edges"], fact
 
 
 def test_pose_math_turntable_and_quaternion(tmp_path):

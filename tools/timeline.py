@@ -39,10 +39,9 @@ _capi.LIB_PATH = TL_LIB
 from ro_map_b200 import core, synthetic as syn
 lib = _capi.load()
 ITERS, KINDS = 64, 16
-# S = scatter kernel [first CTA start, last CTA end] (fused mode: S1 / S2 = [first, last] CTA past the scatter phase / past the reduction + Adam phase
-# of its first job); O = optimizer sweep
+# S = global-reduction scatter kernel [first CTA start, last CTA end], S1 = shared-memory resident scatter kernel (only the one that took the iteration leaves a mark)
 NAMES = ["B", "P", "E0", "E1", "E2", "E3", "M", "S", "S1", "S2", "S3", "O0", "O1", "O2", "O3", "O"]
-TABLES = ["batch", "encode", "mlp", "optim", "scatter_adam"]
+TABLES = ["batch", "encode", "mlp", "optim", "scatter_smem"]
 
 
 def reset():
@@ -93,18 +92,17 @@ for at in [int(x) for x in a.at.split(",")]:
         print(f"iter {it}: period {(nxt - m0) / 1e3:.1f} us  " + " ".join(row))
     print(json.dumps({"after_iters": at, "mean_period_us": round(float(np.mean(periods)), 2)}))
     done += 32
-    # per-CTA phases of the scatter + Adam kernel for the traced iteration with (iter % 64) == 20: cluster = job (level, parity)
+    # per-CTA phases of the shared-memory resident scatter for the traced iteration with (iter % 64) == 20
     try:
         buf = np.zeros((256, 3), np.uint64)
-        assert lib.mon_debug_tl_so_cta_read(buf.ctypes.data_as(C.c_void_p)) == 0
+        assert lib.mon_debug_tl_sr_cta_read(buf.ctypes.data_as(C.c_void_p)) == 0
         live = buf[:, 2] > 0
         if live.any():
             t0 = int(buf[live, 0].min())
-            rel = (buf.astype(np.int64) - t0) / 1e3
-            print("scatter+Adam per cluster (job = 2*level + parity): start / scatter done / Adam done (us after the first CTA start), max over the cluster's CTAs")
-            for job in range(int(live.sum()) // 4):
-                r = rel[4 * job:4 * job + 4]
-                print(f"  job {job:2d} (level {job // 2:2d} parity {job % 2}): {r[:, 0].max():6.1f} {r[:, 1].max():6.1f} {r[:, 2].max():6.1f}")
+            rel = (buf[live].astype(np.int64) - t0) / 1e3
+            print("resident scatter per CTA: start / first job accumulated / done (us after the first CTA start)")
+            for k in range(3):
+                print("  " + " ".join(f"{v:.1f}" for v in rel[:, k]))
     except AttributeError:
         pass
 

@@ -32,11 +32,13 @@
 // The global table this kernel adds into is CLASS-PLANAR: per level [q = 0: f0 | f1][q = 1: f0 | f1], each size/2 fp16 —
 // entry i, feature f of a level sits at ((i & 1) * 2 + f) * size/2 + (i >> 1), a job's slice is contiguous.  The optimizer
 // sweep reads and zeroes it (kernels_optim.cu) in iterations that took this path; iterations with few live samples (steady
-// state: the early stop leaves ~1 sample in 12) take the global f16x2 reduction kernel (kernels_encode.cu
-// k_encode_backward) and its entry-ordered table instead.  Which of the two runs is decided on the device from the
-// iteration's live-sample count (both are in the iteration graph; the other one exits at once).
+// state: the early stop leaves ~1 sample in 12) take the OTHER PATH OF THIS KERNEL — global f16x2 reductions, the reference's
+// own form (scatter_global.cuh), into the entry-ordered table — because there the fixed costs of the resident form (clearing,
+// converting and flushing 128 KB slices) exceed the reductions saved.  The iteration's live-sample count decides on the device,
+// uniformly for the grid; one launch per iteration either way.
 #include "mon_device.cuh"
 #include "mon_kernels.h"
+#include "scatter_global.cuh"
 #include "mon_timeline.cuh"
 MON_TL_DEFINE(scatter_smem)
 #ifdef MON_TIMELINE
@@ -59,6 +61,7 @@ extern "C" int mon_debug_tl_sr_cta_read(unsigned long long* out) { return (int)c
 // copies into a 2- or 4-stage shared-memory ring with full / empty mbarriers — slower (47 us against 40): the producer thread
 // sits in a warp that also computes, the arbiter favours high warp ids, and every warp ends up waiting on the full barrier.
 #define SR_AHEAD 2
+#define SR_TILE 64                               // slots per tile of the global-reduction path
 #define SR_SMEM_BYTES SR_SMEM_ACC_BYTES
 // work split: cost of one (sample, job) in 1/64 of a hashed-level one.  On the coarse dense levels neighbouring samples of a
 // ray (= neighbouring lanes) share corner entries and their shared-memory atomics are serialised (measured per-CTA times).
@@ -81,7 +84,8 @@ struct SrArgs {
     const float* pts_c;         // [n_live][4]: x, y, z, unused
     const uint32_t* genc;       // [n_levels][N]: slot k's two fp16 gradients of the level
     const MonCtrl* ctrl;        // the iteration's control block (copy taken by the fused MLP kernel)
-    __half* gcls;               // class-planar gradient table [n_grid] fp16
+    __half* gcls;               // class-planar gradient table [n_grid] fp16 (resident path)
+    __half* gh_grid;            // entry-ordered gradient table [n_grid] fp16 (global-reduction path)
 };
 
 // needs: power-of-two tables (index = hash & (size - 1)) of >= 16 entries (16-byte bulk granularity of a half-size fp16
@@ -182,21 +186,46 @@ __host__ __device__ __forceinline__ SrPos sr_cost_to_pos(uint64_t x, uint32_t n,
 }
 
 __global__ void __launch_bounds__(SR_THREADS, 1)
-k_scatter_resident(const __grid_constant__ SrArgs a) {
+k_scatter(const __grid_constant__ SrArgs a) {
     extern __shared__ __align__(128) unsigned char sr_smem[];
     const uint32_t tid = threadIdx.x;
     const uint32_t acc_addr = (uint32_t)__cvta_generic_to_shared(sr_smem);
 
-    // before the dependency wait (overlaps the tail of the fused MLP kernel): clear the accumulators
-    {
-        uint4* z = reinterpret_cast<uint4*>(sr_smem);
-        for (uint32_t i = tid; i < SR_SMEM_ACC_BYTES / 16; i += SR_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
     mon_pdl_wait();       // the fused MLP kernel (live samples, control block) has completed
     mon_pdl_trigger();
     if (a.ctrl->skip) return;                          // uniform over the grid
     const uint32_t n_live = a.live_cnt[(a.ctrl->iter - 1) & 1u];
-    if (n_live < a.min_live || n_live == 0u) return;   // uniform over the grid: the global-reduction kernel takes the iteration
+    if (n_live == 0u) return;
+    if (n_live < a.min_live) {
+        // ---- few live samples (steady state): global f16x2 reductions, the reference's form.  Each half of the CTA (16 warps)
+        // takes tiles of 64 consecutive slots: positions staged in shared memory, warp w scatters level w for the tile — every
+        // lane has real work and the level (table base, scale, hash or dense) is uniform across a warp.
+        MON_TL(MON_TL_S, a.ctrl->iter - 1);
+        float (*s_u)[SR_TILE] = reinterpret_cast<float (*)[SR_TILE]>(sr_smem) + 3 * (tid >> 9);      // [axis][slot] of this half
+        const uint32_t gt = tid & 511u, lane = tid & 31u, warp = gt >> 5, bar_id = 1u + (tid >> 9);
+        const uint32_t n_tiles = (n_live + SR_TILE - 1) / SR_TILE;
+        for (uint32_t tile = 2u * blockIdx.x + (tid >> 9); tile < n_tiles; tile += 2u * gridDim.x) {
+            const uint32_t s0 = tile * SR_TILE, n_tile = min((uint32_t)SR_TILE, n_live - s0);
+            for (uint32_t i = gt; i < 3 * n_tile; i += 512u) s_u[i % 3][i / 3] = __ldg(a.pts_c + (size_t)(s0 + i / 3) * 4 + i % 3);   // slots are (x, y, z, -)
+            asm volatile("bar.sync %0, 512;" ::"r"(bar_id) : "memory");
+            for (uint32_t l = warp; l < a.g.n_levels; l += 16u) {
+                const uint32_t* gl = a.genc + (size_t)l * a.n_points + s0;
+                for (uint32_t r = lane; r < n_tile; r += 32) {
+                    const uint32_t gwj = __ldg(gl + r);
+                    if ((gwj & 0x7fff7fffu) == 0u) continue;   // adding +0 is an identity
+                    const float u[3] = {s_u[0][r], s_u[1][r], s_u[2][r]};
+                    scatter_level(a.g, l, gwj, u, a.gh_grid);
+                }
+            }
+            asm volatile("bar.sync %0, 512;" ::"r"(bar_id) : "memory");      // the tile's positions are no longer read
+        }
+        return;
+    }
+    // ---- many live samples (a fresh object: all of them): shared-memory resident slices
+    {
+        uint4* z = reinterpret_cast<uint4*>(sr_smem);
+        for (uint32_t i = tid; i < SR_SMEM_ACC_BYTES / 16; i += SR_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
     MON_TL(MON_TL_S + 1, a.ctrl->iter - 1);
     SR_CTA_STAMP(0);
     const uint64_t total = sr_cost_total(n_live, a.n_slow, a.n_jobs);
@@ -271,14 +300,16 @@ void mon_scatter_resident_pieces_host(const MonGrid& g, uint32_t n_live, uint32_
     }
 }
 
-cudaError_t mon_launch_scatter_resident(const MonGrid& g, uint32_t n_points, uint32_t min_live, const uint32_t* live_cnt, const float* pts_c,
-                                        const uint32_t* genc, const MonCtrl* ctrl, __half* gcls, uint32_t sm_count, cudaStream_t st,
-                                        const MonLaunchOpt& lo) {
+cudaError_t mon_launch_scatter(const MonGrid& g, uint32_t n_points, uint32_t min_live, const uint32_t* live_cnt, const float* pts_c,
+                               const uint32_t* genc, const MonCtrl* ctrl, __half* gcls, __half* gh_grid, uint32_t sm_count, cudaStream_t st,
+                               const MonLaunchOpt& lo) {
     static std::atomic<uint64_t> prepared{0};
     const cudaError_t prep = mon_once_per_device(prepared, [] {
-        cudaError_t e = cudaFuncSetAttribute(k_scatter_resident, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        // 132 of the SM's 228 KB as shared memory, the rest stays L1: the optimizer sweep follows through a programmatic edge on SMs
+        // that keep this split, and with the maximum carve-out its streaming loads had too few L1 lines in flight (27 instead of 16 us)
+        cudaError_t e = cudaFuncSetAttribute(k_scatter, cudaFuncAttributePreferredSharedMemoryCarveout, 58);
         if (e != cudaSuccess) return e;
-        return cudaFuncSetAttribute(k_scatter_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_SMEM_BYTES);
+        return cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_SMEM_BYTES);
     });
     if (prep != cudaSuccess) return prep;
     if (!mon_scatter_resident_supported(g)) return cudaErrorNotSupported;
@@ -288,8 +319,8 @@ cudaError_t mon_launch_scatter_resident(const MonGrid& g, uint32_t n_points, uin
     a.n_slow = 0;
     while (a.n_slow < g.n_levels && !g.hashed[a.n_slow] && g.size[a.n_slow] <= 32768u) ++a.n_slow;
     a.n_slow *= 4u;
-    a.live_cnt = live_cnt; a.pts_c = pts_c; a.genc = genc; a.ctrl = ctrl; a.gcls = gcls;
+    a.live_cnt = live_cnt; a.pts_c = pts_c; a.genc = genc; a.ctrl = ctrl; a.gcls = gcls; a.gh_grid = gh_grid;
     static const uint32_t spare = [] { const char* e = getenv("MON_SCATTER_SPARE_SMS"); return e ? (uint32_t)atoi(e) : SR_SPARE_SMS; }();
     const uint32_t ctas = sm_count > 4u * spare ? sm_count - spare : sm_count;
-    return mon_launch_chain(MON_PDL_SCATTER, lo, k_scatter_resident, dim3(ctas), dim3(SR_THREADS), SR_SMEM_BYTES, st, a);
+    return mon_launch_chain(MON_PDL_SCATTER, lo, k_scatter, dim3(ctas), dim3(SR_THREADS), SR_SMEM_BYTES, st, a);
 }

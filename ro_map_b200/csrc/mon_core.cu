@@ -245,6 +245,7 @@ struct mon_object {
     // f16x2 reductions into gh; decided on the device per iteration, the optimizer sweep reads the table that was filled
     __half* gcls = nullptr;
     uint32_t resident_min_live = 0xffffffffu;
+    bool scatter_unified = true;      // false: a configuration kernels_scatter_smem.cu does not cover (stand-alone global-reduction kernel)
     // instantiated iteration graphs by length
     struct GraphSlot { uint32_t iters; cudaGraphExec_t exec; uint64_t stamp; };
     std::vector<GraphSlot> graphs;
@@ -646,18 +647,19 @@ static int launch_mlp(mon_object* o, const MonBatch& b, cudaStream_t st) {
     if (e != cudaSuccess) return fail(MON_ERR_CUDA, "fused MLP launch: %s", cudaGetErrorString(e));
     return MON_OK;
 }
-// gradient scatter: two kernels, one of which exits at once (the iteration's live-sample count decides on the device)
+// gradient scatter: one launch; the kernel takes the shared-memory resident path or the global reductions by the iteration's
+// live-sample count.  Configurations the unified kernel does not cover use the stand-alone global-reduction kernel.
 static int launch_scatter(mon_object* o, cudaStream_t st) {
-    if (o->resident_min_live != 0xffffffffu) {
-        cudaError_t e = mon_launch_scatter_resident(o->grid, o->N, o->resident_min_live, o->live_cnt, o->pts_c, o->genc, o->ctrl_late, o->gcls,
-                                                    (uint32_t)o->sm_count, st);
-        if (e != cudaSuccess) return fail(MON_ERR_CUDA, "resident scatter launch: %s", cudaGetErrorString(e));
+    if (o->scatter_unified) {
+        cudaError_t e = mon_launch_scatter(o->grid, o->N, o->resident_min_live, o->live_cnt, o->pts_c, o->genc, o->ctrl_late, o->gcls, o->gh + o->n_mlp,
+                                           (uint32_t)o->sm_count, st);
+        if (e != cudaSuccess) return fail(MON_ERR_CUDA, "gradient scatter launch: %s", cudaGetErrorString(e));
+        return MON_OK;
     }
-    mon_launch_encode_backward(o->grid, o->N, o->resident_min_live, o->live_cnt, o->pts_c, o->genc, o->ctrl_late, o->gh + o->n_mlp, st);
+    mon_launch_encode_backward(o->grid, o->N, 0xffffffffu, o->live_cnt, o->pts_c, o->genc, o->ctrl_late, o->gh + o->n_mlp, st);
     return MON_OK;
 }
-// kernels one iteration launches: batch, points, encode, MLP, scatter (one or two), optimizer
-static int scatter_launches(const mon_object* o) { return (o->resident_min_live != 0xffffffffu ? 1 : 0) + (o->resident_min_live != 0u ? 1 : 0); }
+static int scatter_launches(const mon_object*) { return 1; }
 // optimizer sweep: MLP weights (fixed-order reduction of the per-CTA partials, Adam, EMA) + logged loss + the grid (Adam with
 // per-parameter steps, EMA, gradient zeroing, planar weight copy)
 static void launch_optimizer(mon_object* o, cudaStream_t st, bool pdl) {
@@ -686,7 +688,7 @@ static int enqueue_iteration(mon_object* o, const MonBatch& b, bool snapshot_gra
     n += scatter_launches(o);
     if (snapshot_grad) { mon_launch_snapshot_grad(o->P, o->n_mlp, o->opt.n_partials, o->gh, o->partials, o->grad_snap, st, o->grid, o->gcls); ++n; }
     if (ev) CK(cudaEventRecord(ev[5], st));
-    launch_optimizer(o, st, !snapshot_grad); ++n;
+    launch_optimizer(o, st, !snapshot_grad && !o->scatter_unified); ++n;
     if (ev) CK(cudaEventRecord(ev[6], st));
     CK(cudaGetLastError());
     if (n_launched) *n_launched = n;
@@ -715,7 +717,9 @@ static int capture_graph(mon_object* o, int iters, cudaGraphExec_t* out) {
             if ((e = cudaEventRecord(o->ev_join, aux)) != cudaSuccess) break;
         }
         if ((rc = launch_scatter(o, st)) != MON_OK) break;
-        launch_optimizer(o, st, true);
+        // no programmatic edge behind the unified scatter kernel: sweep CTAs that become resident while its 1024-thread CTAs still
+        // run slowed the sweep by 3-5 us (profiles/r5i_timeline*.txt); a plain edge costs a 2 us gap
+        launch_optimizer(o, st, !o->scatter_unified);
         if (fork && (e = cudaStreamWaitEvent(st, o->ev_join, 0)) != cudaSuccess) break;
     }
     cudaError_t e2 = cudaStreamEndCapture(st, &g);
@@ -824,7 +828,7 @@ int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uin
     // and tests; 0 = always, -1 = never).  Configurations the resident kernel does not cover keep the global reductions.
     o->resident_min_live = MON_RESIDENT_MIN_LIVE;
     if (const char* env = getenv("MON_SCATTER_RESIDENT_MIN")) { const long v = atol(env); o->resident_min_live = v < 0 ? 0xffffffffu : (uint32_t)v; }
-    if (!mon_scatter_resident_supported(grid)) o->resident_min_live = 0xffffffffu;
+    if (!mon_scatter_resident_supported(grid)) { o->resident_min_live = 0xffffffffu; o->scatter_unified = false; }
     cudaError_t e;
     if ((e = cudaMallocHost(&o->h_ctrl, sizeof(MonCtrl))) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking)) != cudaSuccess ||

@@ -87,8 +87,8 @@ cudaError_t mon_launch_encode_forward(const MonGrid& g, uint32_t n_points, const
                                       uint32_t level_end = 0xffffffffu, const MonLaunchOpt& lo = MonLaunchOpt());
 void mon_launch_planarize(const MonGrid& g, const __half* inter, __half* planar, cudaStream_t st);
 void mon_encode_pieces_host(const MonGrid& g, uint32_t n_points, uint32_t n_ctas, uint32_t level_begin, uint32_t level_end, uint32_t* out4);
-// gradient scatter with global f16x2 reductions over the compacted live samples (written by the fused MLP kernel); takes the
-// iterations with fewer than resident_min_live live samples (the others: kernels_scatter_smem.cu)
+// stand-alone gradient scatter with global f16x2 reductions over the compacted live samples: configurations the unified kernel
+// (kernels_scatter_smem.cu) does not cover; returns at once in iterations with >= resident_min_live live samples
 void mon_launch_encode_backward(const MonGrid& g, uint32_t n_points, uint32_t resident_min_live, const uint32_t* live_cnt, const float* pts_c,
                                 const uint32_t* genc, const MonCtrl* ctrl, __half* grid_grad, cudaStream_t st, const MonLaunchOpt& lo = MonLaunchOpt());
 
@@ -110,12 +110,13 @@ void mon_launch_optimizer(const MonOpt& o, MonCtrl* ctrl, float* pf, __half* ph,
                           const MonLaunchOpt& lo = MonLaunchOpt(), __half* gcls = nullptr, const uint32_t* live_cnt = nullptr,
                           uint32_t resident_min_live = 0xffffffffu);
 enum { MON_OPT_ALL = 0, MON_OPT_MLP = 1, MON_OPT_GRID = 2, MON_OPT_MLP_GRID = 3 };
-// kernels_scatter_smem.cu: gradient scatter into shared-memory resident fixed-point slices of the gradient table, flushed with
-// TMA bulk reductions into the class-planar table gcls; takes the iterations with >= min_live live samples
+// kernels_scatter_smem.cu: THE gradient scatter of the iteration graph, one launch, two paths chosen on the device by the
+// iteration's live-sample count: >= min_live -> shared-memory resident fixed-point slices flushed with TMA bulk reductions into the
+// class-planar table gcls; fewer -> global f16x2 reductions into the entry-ordered table gh_grid (min_live = 0xffffffff: always)
 bool mon_scatter_resident_supported(const MonGrid& g);   // power-of-two tables of >= 16 entries, even dense-level resolutions
 void mon_scatter_resident_pieces_host(const MonGrid& g, uint32_t n_live, uint32_t n_ctas, uint32_t* out4);
-cudaError_t mon_launch_scatter_resident(const MonGrid& g, uint32_t n_points, uint32_t min_live, const uint32_t* live_cnt, const float* pts_c,
-                                        const uint32_t* genc, const MonCtrl* ctrl, __half* gcls, uint32_t sm_count, cudaStream_t st,
-                                        const MonLaunchOpt& lo = MonLaunchOpt());
+cudaError_t mon_launch_scatter(const MonGrid& g, uint32_t n_points, uint32_t min_live, const uint32_t* live_cnt, const float* pts_c,
+                               const uint32_t* genc, const MonCtrl* ctrl, __half* gcls, __half* gh_grid, uint32_t sm_count, cudaStream_t st,
+                               const MonLaunchOpt& lo = MonLaunchOpt());
 void mon_launch_snapshot_grad(uint32_t n, uint32_t n_mlp, uint32_t n_partials, const __half* gh, const float* partials,
                               float* out, cudaStream_t st, const MonGrid& grid, const __half* gcls);

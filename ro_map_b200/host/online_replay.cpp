@@ -12,11 +12,13 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
 #include <map>
 #include <sstream>
+#include <vector>
 
 #include "nerf_data.h"
 #include "nerf_manager.h"
@@ -84,6 +86,7 @@ int main(int argc, char** argv) {
 
     const size_t px = (size_t)index.H * index.W;
     double ingest_ms = 0.0;
+    std::vector<double> ingest_each;
     std::string err;
     for (uint32_t id = 0; id < index.mnImages; ++id) {
         png_io::Image rgb, inst, dep;
@@ -102,7 +105,8 @@ int main(int argc, char** argv) {
         }
         const auto t0 = clk::now();
         manager.NewFrameToDataset(id, stamps[id], img, instance, depth, index.mvIamgesPose[id]);
-        ingest_ms += std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+        ingest_each.push_back(std::chrono::duration<double, std::milli>(clk::now() - t0).count());
+        ingest_ms += ingest_each.back();
         for (auto& t : tracks) {
             auto it = t.obs.find(id);
             if (it == t.obs.end()) continue;
@@ -112,6 +116,15 @@ int main(int argc, char** argv) {
     }
     manager.WaitThreadsEnd();
     std::cout << "ingest_ms_per_keyframe " << ingest_ms / index.mnImages << " keyframes " << index.mnImages << std::endl;
+    {   // distribution of the frontend thread's NewFrameToDataset calls (objects training and meshing meanwhile)
+        std::vector<double> v = ingest_each;
+        std::sort(v.begin(), v.end());
+        auto q = [&](double f) { return v.empty() ? 0.0 : v[std::min(v.size() - 1, (size_t)(f * (double)v.size()))]; };
+        std::cout << "ingest_ms min " << q(0.0) << " median " << q(0.5) << " p90 " << q(0.9) << " max " << (v.empty() ? 0.0 : v.back()) << std::endl;
+        std::cout << "ingest_ms_each";
+        for (double x : ingest_each) std::cout << " " << std::round(x * 100.0) / 100.0;
+        std::cout << std::endl;
+    }
     mkdir(out_dir.c_str(), 0755);
     for (auto& t : tracks) {
         if (t.nerf_idx < 0) continue;

@@ -16,6 +16,8 @@
 // weights are also written to the planar copy the hash-encode kernel stages into shared memory.
 // A thread owns 4 consecutive parameters (= 2 table entries): 8-byte gradient / EMA words, 16-byte
 // master / moment / step words.
+#include <algorithm>
+
 #include "mon_device.cuh"
 #include "mon_kernels.h"
 #include "optim_math.cuh"
@@ -67,6 +69,7 @@ __global__ void k_cast_params(uint32_t n, const float* __restrict__ pf, __half* 
 
 #define OPT_THREADS 256
 #define OPT_PER_THREAD 4
+#define OPT_CTAS_PER_SM 4
 
 __device__ __forceinline__ uint32_t level_of_entry(const MonGrid& g, uint32_t e) {
     if (g.log2_cap && g.first_full < g.n_levels && e >= g.offset[g.first_full]) return g.first_full + ((e - g.offset[g.first_full]) >> g.log2_cap);
@@ -75,7 +78,51 @@ __device__ __forceinline__ uint32_t level_of_entry(const MonGrid& g, uint32_t e)
     return l;
 }
 
-__global__ void __launch_bounds__(OPT_THREADS, 6)
+// what the sweep fetches per grid quad (4 consecutive parameters = table entries e, e + 1) before it knows whether Adam runs
+struct GridQuad {
+    float g[4];
+    uint2 wraw, eraw;          // fp16 weights and EMA weights
+    __half* planar_f0;
+    uint32_t planar_stride;
+};
+
+__device__ __forceinline__ GridQuad load_grid_quad(uint32_t i4, const MonOpt& o, const MonGrid& grid, __half* __restrict__ gh, __half* __restrict__ gcls,
+                                                    bool resident, const __half* __restrict__ ph, const __half* __restrict__ ema, __half* __restrict__ planar) {
+    GridQuad q;
+    q.wraw = *reinterpret_cast<const uint2*>(ph + i4);
+    q.eraw = *reinterpret_cast<const uint2*>(ema + i4);
+    // planar copy read by the hash-encode kernel: level l holds [feature 0 | feature 1]; entries e, e+1 are
+    // adjacent in both feature arrays (level sizes are multiples of 8, so a pair never straddles a level)
+    const uint32_t e = (i4 - o.n_mlp) >> 1;
+    const uint32_t l = level_of_entry(grid, e);
+    const uint32_t e_local = e - grid.offset[l];
+    q.planar_f0 = planar + (size_t)grid.offset[l] * 2 + e_local;
+    q.planar_stride = grid.size[l];
+    if (!resident) {
+        // entry-ordered table filled by the global f16x2 reductions
+        uint2* gw = reinterpret_cast<uint2*>(gh + i4);
+        const uint2 raw = *gw;
+        const __half2 a = *reinterpret_cast<const __half2*>(&raw.x), b = *reinterpret_cast<const __half2*>(&raw.y);
+        q.g[0] = __low2float(a); q.g[1] = __high2float(a); q.g[2] = __low2float(b); q.g[3] = __high2float(b);
+        if ((raw.x | raw.y) & 0x7fff7fffu) *gw = make_uint2(0u, 0u);   // consumed: the next scatter starts from zero
+    } else {
+        // class-planar table filled by the shared-memory resident scatter — per level [parity 0: f0 | f1][parity 1: f0 | f1], each
+        // size/2 fp16 (kernels_scatter_smem.cu): entries e_local (even: class 0) and e_local + 1 (class 1) share the slot e_local / 2
+        const uint32_t half_n = q.planar_stride >> 1;
+        __half* c0 = gcls + (size_t)grid.offset[l] * 2 + (e_local >> 1);
+        __half hv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) hv[k] = c0[(size_t)k * half_n];      // parameter k: entry parity k >> 1, feature k & 1 -> class array k
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            q.g[k] = __half2float(hv[k]);
+            if (__half_as_ushort(hv[k]) & 0x7fffu) c0[(size_t)k * half_n] = __ushort_as_half((unsigned short)0);
+        }
+    }
+    return q;
+}
+
+__global__ void __launch_bounds__(OPT_THREADS, OPT_CTAS_PER_SM)
 k_optimizer_sweep(MonOpt o, MonCtrl* __restrict__ ctrl, float* __restrict__ pf, __half* __restrict__ ph,
                   __half* __restrict__ gh, const float* __restrict__ mlp_partials, float* __restrict__ m,
                   float* __restrict__ v, uint32_t* __restrict__ ps, __half* __restrict__ ema,
@@ -87,7 +134,7 @@ k_optimizer_sweep(MonOpt o, MonCtrl* __restrict__ ctrl, float* __restrict__ pf, 
     if (ctrl->skip) return;
     MON_TL(n_mlp_ctas ? MON_TL_OMLP : MON_TL_O + (level_of_entry(grid, (grid_i4_begin - o.n_mlp) >> 1) >> 2 & 3u), ctrl->iter - 1);
     if (do_loss && blockIdx.x == gridDim.x - 1) {
-        // logged loss in the sweep's last (mostly idle) CTA: fixed summation order -> reproducible
+        // logged loss in the sweep's last CTA: fixed summation order -> reproducible
         __shared__ float s_loss[OPT_THREADS];
         float a = 0.0f;
         for (uint32_t i = threadIdx.x; i < R; i += OPT_THREADS) a += loss[i];
@@ -100,20 +147,15 @@ k_optimizer_sweep(MonOpt o, MonCtrl* __restrict__ ctrl, float* __restrict__ pf, 
         if (threadIdx.x == 0) ctrl->loss_mean = s_loss[0] / (float)R;
     }
     const float lr_base = ctrl->lr_base, old_db = ctrl->ema_old, new_db = ctrl->ema_new;
+    const OptimPtrs ptrs = {pf, ph, m, v, ps, ema};
     // CTA layout: the first n_mlp_ctas (n_mlp/32, or 0 in a grid-only launch) CTAs own the MLP weights (one WARP per 4
-    // parameters: the lanes split the per-CTA gradient partials of the fused MLP kernel), every other CTA owns 1024
-    // consecutive parameters of [grid_i4_begin, grid_i4_end) (one THREAD per 4 parameters).  n_params and n_mlp are
-    // multiples of 32 resp. 4.
-    const bool is_mlp = blockIdx.x < n_mlp_ctas;
-    uint32_t i4;
-    float g[4];
-    uint2* gw;
-    __half* planar_f0 = nullptr;
-    uint32_t planar_stride = 0;
-    uint2 wraw, eraw;   // fp16 weights and EMA of the 4 parameters: always needed, fetched together with the gradient
-    if (is_mlp) {
+    // parameters: the lanes split the per-CTA gradient partials of the fused MLP kernel); the other CTAs walk the quads of
+    // [grid_i4_begin, grid_i4_end) with a grid stride (one THREAD per 4 parameters per trip).  The launch sizes them so that all
+    // CTAs are resident at once and every thread makes the same number of trips (no partial last wave); the loads of the next
+    // quad are issued before the current one is processed.  n_params and n_mlp are multiples of 32 resp. 4.
+    if (blockIdx.x < n_mlp_ctas) {
         const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        i4 = (blockIdx.x * (OPT_THREADS / 32) + warp) * OPT_PER_THREAD;
+        const uint32_t i4 = (blockIdx.x * (OPT_THREADS / 32) + warp) * OPT_PER_THREAD;
         // fixed-order reduction -> bitwise reproducible MLP gradient: lane l sums partial rows l, l+32, ... in
         // ascending order, then a butterfly over the lanes
         float4 s4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -129,51 +171,30 @@ k_optimizer_sweep(MonOpt o, MonCtrl* __restrict__ ctrl, float* __restrict__ pf, 
             s4.w = __fadd_rn(s4.w, __shfl_xor_sync(0xffffffffu, s4.w, off));
         }
         if (lane != 0) return;
-        gw = reinterpret_cast<uint2*>(gh + i4);
-        wraw = *reinterpret_cast<const uint2*>(ph + i4);
-        eraw = *reinterpret_cast<const uint2*>(ema + i4);
+        const uint2 wraw = *reinterpret_cast<const uint2*>(ph + i4);
+        const uint2 eraw = *reinterpret_cast<const uint2*>(ema + i4);
         // the reference stores weight gradients in fp16 (loss-scaled); keep that rounding point
         const __half2 a = __floats2half2_rn(s4.x, s4.y), b = __floats2half2_rn(s4.z, s4.w);
-        *gw = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));   // kept for inspection
-        g[0] = __low2float(a); g[1] = __high2float(a); g[2] = __low2float(b); g[3] = __high2float(b);
-    } else {
-        i4 = grid_i4_begin + ((blockIdx.x - n_mlp_ctas) * OPT_THREADS + threadIdx.x) * OPT_PER_THREAD;
-        if (i4 >= grid_i4_end) return;
-        wraw = *reinterpret_cast<const uint2*>(ph + i4);
-        eraw = *reinterpret_cast<const uint2*>(ema + i4);
-        // planar copy read by the hash-encode kernel: level l holds [feature 0 | feature 1]; entries e, e+1 are
-        // adjacent in both feature arrays (level sizes are multiples of 8, so a pair never straddles a level)
-        const uint32_t e = (i4 - o.n_mlp) >> 1;
-        const uint32_t l = level_of_entry(grid, e);
-        const uint32_t e_local = e - grid.offset[l];
-        planar_f0 = planar + (size_t)grid.offset[l] * 2 + e_local;
-        planar_stride = grid.size[l];
-        // which scatter kernel produced this iteration's gradient (grid-uniform, decided by the live-sample count):
-        // the global f16x2 reductions fill the entry-ordered table gh, the shared-memory resident scatter the class-planar
-        // table gcls — per level [parity 0: f0 | f1][parity 1: f0 | f1], each size/2 fp16 (kernels_scatter_smem.cu)
-        const bool resident = gcls != nullptr && live_cnt[(ctrl->iter - 1) & 1u] >= resident_min_live;
-        if (!resident) {
-            gw = reinterpret_cast<uint2*>(gh + i4);
-            const uint2 raw = *gw;
-            const __half2 a = *reinterpret_cast<const __half2*>(&raw.x), b = *reinterpret_cast<const __half2*>(&raw.y);
-            g[0] = __low2float(a); g[1] = __high2float(a); g[2] = __low2float(b); g[3] = __high2float(b);
-            if ((raw.x | raw.y) & 0x7fff7fffu) *gw = make_uint2(0u, 0u);   // consumed: the next scatter starts from zero
-        } else {
-            // entries e_local (even: parity class 0) and e_local + 1 (class 1) share the slot e_local / 2 of their class arrays
-            const uint32_t half_n = planar_stride >> 1;
-            __half* c0 = gcls + (size_t)grid.offset[l] * 2 + (e_local >> 1);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                // parameter k of the quad: entry parity k >> 1, feature k & 1 -> class array (k >> 1) * 2 + (k & 1) == k
-                __half* p = c0 + (size_t)k * half_n;
-                const __half hv = *p;
-                g[k] = __half2float(hv);
-                if (__half_as_ushort(hv) & 0x7fffu) *p = __ushort_as_half((unsigned short)0);
-            }
-        }
+        *reinterpret_cast<uint2*>(gh + i4) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));   // kept for inspection
+        float g[4] = {__low2float(a), __high2float(a), __low2float(b), __high2float(b)};
+        optim_quad(o, lr_base, old_db, new_db, true, i4, g, wraw, eraw, ptrs, nullptr, 0);
+        return;
     }
-    const OptimPtrs ptrs = {pf, ph, m, v, ps, ema};
-    optim_quad(o, lr_base, old_db, new_db, is_mlp, i4, g, wraw, eraw, ptrs, planar_f0, planar_stride);
+    // which scatter path produced this iteration's gradient (grid-uniform, decided by the live-sample count)
+    const bool resident = gcls != nullptr && live_cnt[(ctrl->iter - 1) & 1u] >= resident_min_live;
+    const uint32_t stride = (gridDim.x - n_mlp_ctas) * OPT_THREADS * OPT_PER_THREAD;
+    uint32_t i4 = grid_i4_begin + ((blockIdx.x - n_mlp_ctas) * OPT_THREADS + threadIdx.x) * OPT_PER_THREAD;
+    if (i4 >= grid_i4_end) return;
+    GridQuad cur = load_grid_quad(i4, o, grid, gh, gcls, resident, ph, ema, planar);
+    while (true) {
+        const uint32_t i4n = i4 + stride;
+        const bool more = i4n < grid_i4_end;
+        GridQuad nxt;
+        if (more) nxt = load_grid_quad(i4n, o, grid, gh, gcls, resident, ph, ema, planar);
+        optim_quad(o, lr_base, old_db, new_db, false, i4, cur.g, cur.wraw, cur.eraw, ptrs, cur.planar_f0, cur.planar_stride);
+        if (!more) break;
+        cur = nxt; i4 = i4n;
+    }
 }
 
 // used only by tests: snapshot of the loss-scaled gradient before the sweep consumes it
@@ -211,7 +232,7 @@ void mon_launch_cast_params(uint32_t n, const float* pf, __half* ph, cudaStream_
 void mon_launch_optimizer(const MonOpt& o, MonCtrl* ctrl, float* pf, __half* ph, __half* gh, const float* partials,
                           float* m, float* v, uint32_t* ps, __half* ema, const float* loss, uint32_t R, const MonGrid& grid,
                           __half* planar, cudaStream_t st, int part, uint32_t level_begin, uint32_t level_end, const MonLaunchOpt& lo,
-                          __half* gcls, const uint32_t* live_cnt, uint32_t resident_min_live) {
+                          __half* gcls, const uint32_t* live_cnt, uint32_t resident_min_live, uint32_t sm_count) {
     // part: MON_OPT_ALL everything (MLP weights + loss + whole grid); MON_OPT_MLP the MLP weights and the logged loss only;
     // MON_OPT_GRID the grid parameters of levels [level_begin, level_end) only; MON_OPT_MLP_GRID both of these
     if (level_end > grid.n_levels) level_end = grid.n_levels;
@@ -223,8 +244,13 @@ void mon_launch_optimizer(const MonOpt& o, MonCtrl* ctrl, float* pf, __half* ph,
         i4_end = part == MON_OPT_ALL ? o.n_params : o.n_mlp + 2u * grid.offset[level_end];
     }
     const uint32_t grid_quads = (i4_end - i4_begin + OPT_PER_THREAD - 1) / OPT_PER_THREAD;
-    // a grid-less launch still needs the (otherwise idle) last CTA that reduces the logged loss
-    const uint32_t n_grid_ctas = with_grid ? (grid_quads + OPT_THREADS - 1) / OPT_THREADS : 1u;
+    // grid part: all CTAs resident at once (OPT_CTAS_PER_SM per SM beside the MLP CTAs) and the same number of trips for every thread
+    uint32_t n_grid_ctas = 1u;      // a grid-less launch still needs the (otherwise idle) last CTA that reduces the logged loss
+    if (with_grid && grid_quads) {
+        const uint32_t slots = std::max(1u, OPT_CTAS_PER_SM * sm_count > n_mlp_ctas ? OPT_CTAS_PER_SM * sm_count - n_mlp_ctas : 1u);
+        const uint32_t trips = (grid_quads + slots * OPT_THREADS - 1) / (slots * OPT_THREADS);
+        n_grid_ctas = (grid_quads + trips * OPT_THREADS - 1) / (trips * OPT_THREADS);
+    }
     if (n_mlp_ctas + n_grid_ctas == 0) return;
     mon_launch_chain(MON_PDL_OPTIM, lo, k_optimizer_sweep, dim3(n_mlp_ctas + n_grid_ctas), dim3(OPT_THREADS), 0, st, o, ctrl, pf, ph, gh, partials, m,
                      v, ps, ema, loss, R, grid, planar, n_mlp_ctas, with_mlp ? 1u : 0u, i4_begin, i4_end, gcls, live_cnt, resident_min_live);

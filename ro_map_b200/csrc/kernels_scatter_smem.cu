@@ -60,13 +60,15 @@ extern "C" int mon_debug_tl_sr_cta_read(unsigned long long* out) { return (int)c
 // its issue slots stalled on the first use of a loaded position).  Measured alternative (profiles/r5d_*, r5e_*): TMA bulk
 // copies into a 2- or 4-stage shared-memory ring with full / empty mbarriers — slower (47 us against 40): the producer thread
 // sits in a warp that also computes, the arbiter favours high warp ids, and every warp ends up waiting on the full barrier.
+// Also measured and dropped (r5l): floor by the 1.5 * 2^23 add trick instead of F2I.FLOOR + I2FP — same time, the conversion
+// pipe is not what binds the loop.
 #define SR_AHEAD 2
 #define SR_TILE 64                               // slots per tile of the global-reduction path
 #define SR_SMEM_BYTES SR_SMEM_ACC_BYTES
 // work split: cost of one (sample, job) in 1/64 of a hashed-level one.  On the coarse dense levels neighbouring samples of a
 // ray (= neighbouring lanes) share corner entries and their shared-memory atomics are serialised (measured per-CTA times).
 #define SR_W_HASH 64u
-#define SR_W_DENSE 106u
+#define SR_W_DENSE 98u
 // every job a piece touches ends with a flush (convert + bulk reduction + clearing the slice for the next job): ~3.6 us, the time
 // of ~7500 hashed-level samples.  Charged at each job START: a piece that spans a job boundary gets that much less sample work.
 #define SR_FLUSH 480000ull

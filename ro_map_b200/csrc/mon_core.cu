@@ -16,6 +16,7 @@
 // (SURVEY.md §3.1).  There is no CPU fallback anywhere in this
 // file: without a CUDA device every compute entry point returns MON_ERR_NO_DEVICE / MON_ERR_CUDA.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -34,10 +35,25 @@
 #define MON_DEBIAS_LUT 32768  // steps covered by the Adam bias-correction table (offline jobs run 5000 iterations)
 #define MON_FRAMES_PER_SLAB 32
 #define MON_RESIDENT_MIN_LIVE 24576u   // live samples from which the shared-memory resident scatter takes an iteration (measured crossover)
-#define MON_GRAPH_CHUNK 64   // longest captured graph; a call of n iterations replays n / 64 of these + one graph of exactly n % 64
+#define MON_GRAPH_CHUNK 64   // longest captured graph: a call of n iterations replays one chunk length that divides n (32..64) where
+                             // there is one — 500 = 10 x 50, a single graph to instantiate — else n / 64 graphs of 64 + one of exactly n % 64
+#define MON_BOX_CAP0 1024    // 2-D boxes the box buffer holds from the start (the iteration graphs capture its address)
 #define MON_GRAPH_CACHE 6    // distinct remainder lengths kept instantiated per object (least recently used is dropped)
 
 static thread_local std::string g_err;
+
+// CUDA loads kernels lazily by default (CUDA_MODULE_LOADING=LAZY): the FIRST launch of every kernel loads its module under a
+// driver-wide lock.  In online mode that happened in the middle of the run — the first mesh update launches the inference
+// kernels — and the frontend thread's keyframe upload sat 10-90 ms inside cudaMemcpyAsync / cudaSetDevice waiting for that lock
+// (MON_INGEST_TRACE=1, profiles/r5l_facade_runs.txt).  Loading everything when the context is created moves that cost to
+// start-up.  Takes effect when the library is loaded before CUDA is initialised (the SLAM frontend links it); a user setting wins.
+// The same start-up hook raises the number of hardware work queues: with the default 8, the streams of one process (2 per object
+// + 1 per dataset) share queues, and a keyframe copy that lands in the queue of a training stream waits behind its 35 ms graph
+// replays (ingest calls of 10-50 ms inside cudaEventSynchronize on the staging slot).
+__attribute__((constructor)) static void mon_process_setup() {
+    setenv("CUDA_MODULE_LOADING", "EAGER", 0);
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+}
 
 unsigned mon_pdl_mask() {   // A/B switch for the programmatic-dependent-launch chain (mon_kernels.h)
     static const unsigned mask = [] {
@@ -59,6 +75,42 @@ static int fail(int code, const char* fmt, ...) {
     va_end(ap);
     g_err = buf;
     return code;
+}
+
+// Device memory comes from the device's default stream-ordered pool (cudaMallocAsync / cudaFreeAsync).  cudaMalloc and cudaFree
+// synchronise the WHOLE device: an object created, a scratch buffer grown or a keyframe slab added while other objects train
+// stalled their graph replays and the frontend thread's keyframe ingest behind them (online mode: single calls of 14-260 ms
+// among 0.3 ms ones, profiles/r5j_facade_runs.txt).  The pool keeps what is freed (release threshold = max), and an allocation
+// is usable from any stream once the allocating stream has been synchronised, which the helper does (that stream only).
+static cudaError_t mon_dev_malloc(void** p, size_t bytes, cudaStream_t st) {
+    static std::atomic<uint64_t> prepared{0};
+    cudaError_t e = mon_once_per_device(prepared, [] {
+        int dev = 0;
+        cudaError_t e2 = cudaGetDevice(&dev);
+        cudaMemPool_t pool;
+        if (e2 == cudaSuccess) e2 = cudaDeviceGetDefaultMemPool(&pool, dev);
+        uint64_t keep = UINT64_MAX;
+        if (e2 == cudaSuccess) e2 = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        return e2;
+    });
+    if (e != cudaSuccess) return e;
+    if ((e = cudaMallocAsync(p, bytes, st)) != cudaSuccess) return e;
+    return cudaStreamSynchronize(st);
+}
+static void mon_dev_free(void* p, cudaStream_t st) { if (p) cudaFreeAsync(p, st); }
+// Growing the pool (physical allocation + mapping) is the slow part of an allocation and holds the driver: reserve room for the
+// first objects when a dataset is created, so that objects created while the frontend streams keyframes allocate from memory the
+// pool already owns (MON_POOL_RESERVE_MB, default 512: about 8 objects of base.json).
+static void mon_pool_reserve(cudaStream_t st) {
+    static std::atomic<uint64_t> reserved{0};
+    mon_once_per_device(reserved, [st] {
+        const char* env = getenv("MON_POOL_RESERVE_MB");
+        const size_t mb = env ? (size_t)atol(env) : 512;
+        void* p = nullptr;
+        if (mb && mon_dev_malloc(&p, mb << 20, st) == cudaSuccess) { mon_dev_free(p, st); cudaStreamSynchronize(st); }
+        cudaGetLastError();     // a failed reservation is not an error: allocations then grow the pool as they come
+        return cudaSuccess;
+    });
 }
 
 #define CK(call)                                                                                       \
@@ -387,17 +439,19 @@ int mon_dataset_create(int gpu, float fx, float fy, float cx, float cy, int H, i
     const size_t px = (size_t)H * W;
     cudaError_t e;
     if ((e = cudaStreamCreateWithFlags(&ds->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaMalloc(&ds->d_frames, sizeof(MonFrame) * max_frames)) != cudaSuccess ||
-        (e = cudaMemset(ds->d_frames, 0, sizeof(MonFrame) * max_frames)) != cudaSuccess ||
+        (e = mon_dev_malloc(reinterpret_cast<void**>(&ds->d_frames), sizeof(MonFrame) * max_frames, ds->stream)) != cudaSuccess ||
+        (e = cudaMemsetAsync(ds->d_frames, 0, sizeof(MonFrame) * max_frames, ds->stream)) != cudaSuccess ||
         (e = cudaMallocHost(&ds->staging[0], px * 3 + px + px * 4)) != cudaSuccess ||
         (e = cudaMallocHost(&ds->staging[1], px * 3 + px + px * 4)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&ds->ev_staged[0], cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&ds->ev_staged[1], cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&ds->ev_uploaded, cudaEventDisableTiming)) != cudaSuccess ||
-        (e = cudaEventRecord(ds->ev_uploaded, ds->stream)) != cudaSuccess) {
+        (e = cudaEventRecord(ds->ev_uploaded, ds->stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(ds->stream)) != cudaSuccess) {
         mon_dataset_destroy(ds);
         return fail(MON_ERR_CUDA, "dataset allocation: %s", cudaGetErrorString(e));
     }
+    mon_pool_reserve(ds->stream);
     *out = ds;
     return MON_OK;
 }
@@ -412,7 +466,7 @@ static int ensure_frame_storage(mon_dataset* ds, uint32_t frame_id) {
     const uint32_t slab = frame_id / MON_FRAMES_PER_SLAB;
     if (!ds->slabs[slab]) {
         const uint32_t n = std::min<uint32_t>(MON_FRAMES_PER_SLAB, ds->max_frames - slab * MON_FRAMES_PER_SLAB);
-        CK(cudaMalloc(&ds->slabs[slab], per_frame * n));
+        CK(mon_dev_malloc(reinterpret_cast<void**>(&ds->slabs[slab]), per_frame * n, ds->stream));
     }
     uint8_t* base = ds->slabs[slab] + per_frame * (frame_id % MON_FRAMES_PER_SLAB);
     f.rgb = base; f.instance = base + o_inst;
@@ -425,11 +479,20 @@ int mon_dataset_add_frame(mon_dataset* ds, uint32_t frame_id, const uint8_t* rgb
     if (!ds || !rgb || !instance || !pose) return fail(MON_ERR_ARG, "NULL argument");
     if (frame_id >= ds->max_frames) return fail(MON_ERR_ARG, "frame_id %u >= max_frames %u", frame_id, ds->max_frames);
     if (ds->use_depth && !depth) return fail(MON_ERR_ARG, "dataset was created with use_depth but depth is NULL");
+    // MON_INGEST_TRACE=1: where a slow call spent its time (lock, storage, staging-slot wait, host copies, enqueue), to stderr
+    static const bool trace = getenv("MON_INGEST_TRACE") != nullptr;
+    using tclock = std::chrono::steady_clock;
+    tclock::time_point t_[6];
+    int nt_ = 0;
+    auto stamp = [&] { if (trace && nt_ < 6) t_[nt_++] = tclock::now(); };
+    stamp();
     std::lock_guard<std::mutex> lock(ds->mu);
+    stamp();
     CK(cudaSetDevice(ds->gpu));
     const size_t px = (size_t)ds->H * ds->W;
     int rc = ensure_frame_storage(ds, frame_id);
     if (rc != MON_OK) return rc;
+    stamp();
     MonFrame& f = ds->h_frames[frame_id];
     memcpy(f.pose, pose, sizeof(float) * 16);
     f.bgr = is_bgr ? 1u : 0u;
@@ -447,20 +510,31 @@ int mon_dataset_add_frame(mon_dataset* ds, uint32_t frame_id, const uint8_t* rgb
         const uint32_t half = ds->stage_next;
         ds->stage_next ^= 1u;
         CK(cudaEventSynchronize(ds->ev_staged[half]));   // the DMA that last read this half (two frames ago) is done
+        stamp();
         uint8_t* st_rgb = ds->staging[half];
         uint8_t* st_inst = ds->staging[half] + px * 3;
         float* st_depth = reinterpret_cast<float*>(ds->staging[half] + px * 4);
         memcpy(st_rgb, rgb, px * 3);
         memcpy(st_inst, instance, px);
+        if (ds->use_depth) memcpy(st_depth, depth, px * 4);
+        stamp();
         CK(cudaMemcpyAsync(const_cast<uint8_t*>(f.rgb), st_rgb, px * 3, cudaMemcpyHostToDevice, ds->stream));
         CK(cudaMemcpyAsync(const_cast<uint8_t*>(f.instance), st_inst, px, cudaMemcpyHostToDevice, ds->stream));
-        if (ds->use_depth) {
-            memcpy(st_depth, depth, px * 4);
-            CK(cudaMemcpyAsync(const_cast<float*>(f.depth), st_depth, px * 4, cudaMemcpyHostToDevice, ds->stream));
-        }
+        if (ds->use_depth) CK(cudaMemcpyAsync(const_cast<float*>(f.depth), st_depth, px * 4, cudaMemcpyHostToDevice, ds->stream));
         CK(cudaMemcpyAsync(ds->d_frames + frame_id, &f, sizeof(MonFrame), cudaMemcpyHostToDevice, ds->stream));
         CK(cudaEventRecord(ds->ev_staged[half], ds->stream));
         CK(cudaEventRecord(ds->ev_uploaded, ds->stream));
+    }
+    stamp();
+    if (trace && nt_ >= 2) {
+        auto ms = [&](int a, int b) { return std::chrono::duration<double, std::milli>(t_[b] - t_[a]).count(); };
+        if (ms(0, nt_ - 1) > 2.0) {
+            fprintf(stderr, "[mon ingest] frame %u: %.2f ms =", frame_id, ms(0, nt_ - 1));
+            static const char* names6[] = {"lock", "storage", "slot-wait", "host-copy", "enqueue"};
+            static const char* names4[] = {"lock", "storage", "enqueue"};
+            for (int k = 0; k + 1 < nt_; ++k) fprintf(stderr, " %s %.2f", nt_ == 6 ? names6[k] : names4[k], ms(k, k + 1));
+            fprintf(stderr, "\n");
+        }
     }
     ds->n_frames = std::max(ds->n_frames, frame_id + 1);
     return MON_OK;
@@ -578,8 +652,9 @@ int mon_dataset_destroy(mon_dataset* ds) {
     if (!ds) return MON_OK;
     cudaSetDevice(ds->gpu);
     if (ds->stream) cudaStreamSynchronize(ds->stream);
-    for (uint8_t* slab : ds->slabs) if (slab) cudaFree(slab);
-    if (ds->d_frames) cudaFree(ds->d_frames);
+    for (uint8_t* slab : ds->slabs) mon_dev_free(slab, ds->stream);
+    mon_dev_free(ds->d_frames, ds->stream);
+    if (ds->stream) cudaStreamSynchronize(ds->stream);
     for (int k = 0; k < 2; ++k) {
         if (ds->staging[k]) cudaFreeHost(ds->staging[k]);
         if (ds->ev_staged[k]) cudaEventDestroy(ds->ev_staged[k]);
@@ -665,7 +740,7 @@ static int scatter_launches(const mon_object*) { return 1; }
 static void launch_optimizer(mon_object* o, cudaStream_t st, bool pdl) {
     MonLaunchOpt lo; lo.pdl = pdl;
     mon_launch_optimizer(o->opt, o->ctrl_late, o->pf, o->ph, o->gh, o->partials, o->m, o->v, o->ps, o->ema, o->loss, o->R, o->grid,
-                         o->ph_planar, st, MON_OPT_ALL, 0, 0xffffffffu, lo, o->gcls, o->live_cnt, o->resident_min_live);
+                         o->ph_planar, st, MON_OPT_ALL, 0, 0xffffffffu, lo, o->gcls, o->live_cnt, o->resident_min_live, (uint32_t)o->sm_count);
 }
 
 // serial version (injected / profiled iterations).  ev (optional, MON_N_STAGES+1 events): recorded before each
@@ -732,6 +807,15 @@ static int capture_graph(mon_object* o, int iters, cudaGraphExec_t* out) {
     return MON_OK;
 }
 
+// how a call of `iters` iterations is cut into graph replays: n_chunk replays of a `chunk`-iteration graph + one `rem`-iteration graph
+struct GraphPlan { uint32_t chunk, n_chunk, rem; };
+static GraphPlan graph_plan(uint32_t iters) {
+    if (iters <= MON_GRAPH_CHUNK) return {0u, 0u, iters};
+    for (uint32_t c = MON_GRAPH_CHUNK; c >= MON_GRAPH_CHUNK / 2; --c)
+        if (iters % c == 0) return {c, iters / c, 0u};
+    return {MON_GRAPH_CHUNK, iters / MON_GRAPH_CHUNK, iters % MON_GRAPH_CHUNK};
+}
+
 // the instantiated graph of exactly `iters` iterations (1 <= iters <= MON_GRAPH_CHUNK), captured on first use
 static int graph_for(mon_object* o, uint32_t iters, cudaGraphExec_t* out) {
     for (auto& g : o->graphs) if (g.iters == iters) { g.stamp = ++o->graph_clock; *out = g.exec; return MON_OK; }
@@ -740,7 +824,7 @@ static int graph_for(mon_object* o, uint32_t iters, cudaGraphExec_t* out) {
     if (rc != MON_OK) return rc;
     size_t n_rem = 0, oldest = SIZE_MAX;
     for (size_t k = 0; k < o->graphs.size(); ++k) {
-        if (o->graphs[k].iters == MON_GRAPH_CHUNK) continue;
+        if (o->graphs[k].iters == MON_GRAPH_CHUNK) continue;     // the full-length chunk graph is never dropped
         ++n_rem;
         if (oldest == SIZE_MAX || o->graphs[k].stamp < o->graphs[oldest].stamp) oldest = k;
     }
@@ -803,10 +887,15 @@ int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uin
         o->opt.inv_loss_scale = 1.0f / cfg->loss_scale;
     }
 
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        mon_object_destroy(o);
+        return fail(MON_ERR_CUDA, "object setup: %s", cudaGetErrorString(e));
+    }
 #define OALLOC(ptr, bytes)                                                                                  \
     do {                                                                                                    \
-        cudaError_t e_ = cudaMalloc(reinterpret_cast<void**>(&(ptr)), (bytes));                             \
-        if (e_ == cudaSuccess) e_ = cudaMemset((ptr), 0, (bytes));                                          \
+        cudaError_t e_ = mon_dev_malloc(reinterpret_cast<void**>(&(ptr)), (bytes), o->stream);               \
+        if (e_ == cudaSuccess) e_ = cudaMemsetAsync((ptr), 0, (bytes), o->stream);                          \
         if (e_ != cudaSuccess) { mon_object_destroy(o); return fail(MON_ERR_CUDA, "object allocation (%zu B): %s", (size_t)(bytes), cudaGetErrorString(e_)); } \
     } while (0)
     const size_t P = o->P, R = o->R, N = o->N;
@@ -822,6 +911,8 @@ int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uin
     OALLOC(o->gcls, (size_t)o->n_grid * 2 + 16);
     OALLOC(o->partials, (size_t)o->n_ctas * o->n_mlp * 4);
     OALLOC(o->debias_lut, (size_t)MON_DEBIAS_LUT * 4);
+    OALLOC(o->d_boxes, sizeof(mon_bbox2d) * MON_BOX_CAP0);
+    o->box_cap = MON_BOX_CAP0;
     o->opt.debias_lut = o->debias_lut; o->opt.n_debias_lut = MON_DEBIAS_LUT;
 #undef OALLOC
     // live-sample count from which an iteration's gradients are scattered through shared memory (MON_SCATTER_RESIDENT_MIN: A/B
@@ -829,9 +920,7 @@ int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uin
     o->resident_min_live = MON_RESIDENT_MIN_LIVE;
     if (const char* env = getenv("MON_SCATTER_RESIDENT_MIN")) { const long v = atol(env); o->resident_min_live = v < 0 ? 0xffffffffu : (uint32_t)v; }
     if (!mon_scatter_resident_supported(grid)) { o->resident_min_live = 0xffffffffu; o->scatter_unified = false; }
-    cudaError_t e;
     if ((e = cudaMallocHost(&o->h_ctrl, sizeof(MonCtrl))) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&o->aux, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&o->ev_fork_m, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&o->ev_join, cudaEventDisableTiming)) != cudaSuccess ||
@@ -894,8 +983,9 @@ int mon_object_destroy(mon_object* o) {
                     o->d_enc, o->ph_planar, o->gcls, o->partials,
                     o->dbg_out, o->dbg_dout, o->inj_xy, o->inj_col, o->inj_dt, o->grad_snap, o->r_rays, o->r_orig, o->r_nhit, o->r_enc,
                     o->r_jit, o->r_rgb, o->r_depth, o->r_mask, o->r_Twc, o->r_pts, o->r_planar};
-    for (void* p : ptrs) if (p) cudaFree(p);
-    for (void* p : o->scr) if (p) cudaFree(p);
+    for (void* p : ptrs) mon_dev_free(p, o->stream);
+    for (void* p : o->scr) mon_dev_free(p, o->stream);
+    if (o->stream) cudaStreamSynchronize(o->stream);
     if (o->h_ctrl) cudaFreeHost(o->h_ctrl);
     cudaEvent_t evs[] = {o->ev0, o->ev1, o->ev_fork_m, o->ev_join};
     for (cudaEvent_t ev : evs) if (ev) cudaEventDestroy(ev);
@@ -922,8 +1012,8 @@ static int upload_boxes(mon_object* o, uint32_t first) {
     if (n > o->box_cap) {
         const uint32_t cap = std::max<uint32_t>(256, n * 2);
         mon_bbox2d* p = nullptr;
-        CK(cudaMalloc(&p, sizeof(mon_bbox2d) * cap));
-        if (o->d_boxes) cudaFree(o->d_boxes);
+        CK(mon_dev_malloc(reinterpret_cast<void**>(&p), sizeof(mon_bbox2d) * cap, o->stream));
+        mon_dev_free(o->d_boxes, o->stream);
         o->d_boxes = p; o->box_cap = cap;
         first = 0;
         drop_graphs(o);  // the captured graphs hold the old pointer
@@ -962,11 +1052,13 @@ static int finish_timing(mon_object* o) {
 
 int mon_object_prepare_train(mon_object* o, uint32_t iters) {
     if (!o) return fail(MON_ERR_ARG, "obj is NULL");
-    if (o->h_boxes.empty()) return fail(MON_ERR_STATE, "no 2-D boxes: call mon_object_set_bboxes first");
+    // allowed before the first boxes arrive (online mode prepares at object creation): the graphs capture the address of the
+    // box buffer, which exists from the start, and the live box count is read on the device
     CK(cudaSetDevice(o->ds->gpu));
     cudaGraphExec_t g = nullptr;
-    if (iters >= MON_GRAPH_CHUNK) { int rc = graph_for(o, MON_GRAPH_CHUNK, &g); if (rc != MON_OK) return rc; }
-    if (iters % MON_GRAPH_CHUNK) { int rc = graph_for(o, iters % MON_GRAPH_CHUNK, &g); if (rc != MON_OK) return rc; }
+    const GraphPlan plan = graph_plan(iters);
+    if (plan.n_chunk) { int rc = graph_for(o, plan.chunk, &g); if (rc != MON_OK) return rc; }
+    if (plan.rem) { int rc = graph_for(o, plan.rem, &g); if (rc != MON_OK) return rc; }
     return MON_OK;
 }
 
@@ -974,15 +1066,16 @@ int mon_object_train_async(mon_object* o, uint32_t iters) {
     if (!o) return fail(MON_ERR_ARG, "obj is NULL");
     if (o->h_boxes.empty()) return fail(MON_ERR_STATE, "no 2-D boxes: call mon_object_set_bboxes first");
     CK(cudaSetDevice(o->ds->gpu));
-    // a call of n iterations = n / 64 replays of the 64-iteration graph + ONE graph of exactly n % 64 iterations: every
+    // a call of n iterations = replays of one chunk graph (+ ONE graph of exactly the remainder, graph_plan): every
     // iteration but the first of each graph has its batch generation hidden behind the previous iteration's scatter
     cudaGraphExec_t g_chunk = nullptr, g_rem = nullptr;
-    const uint32_t rem = iters % MON_GRAPH_CHUNK;
-    if (iters >= MON_GRAPH_CHUNK) { int rc = graph_for(o, MON_GRAPH_CHUNK, &g_chunk); if (rc != MON_OK) return rc; }
+    const GraphPlan plan = graph_plan(iters);
+    const uint32_t rem = plan.rem;
+    if (plan.n_chunk) { int rc = graph_for(o, plan.chunk, &g_chunk); if (rc != MON_OK) return rc; }
     if (rem) { int rc = graph_for(o, rem, &g_rem); if (rc != MON_OK) return rc; }
     CK(cudaStreamWaitEvent(o->stream, o->ds->ev_uploaded, 0));   // frames uploaded asynchronously from pinned buffers
     CK(cudaEventRecord(o->ev0, o->stream));
-    for (uint32_t k = 0; k < iters / MON_GRAPH_CHUNK; ++k) CK(cudaGraphLaunch(g_chunk, o->stream));
+    for (uint32_t k = 0; k < plan.n_chunk; ++k) CK(cudaGraphLaunch(g_chunk, o->stream));
     if (rem) CK(cudaGraphLaunch(g_rem, o->stream));
     CK(cudaEventRecord(o->ev1, o->stream));
     o->timing_pending = true;
@@ -1094,10 +1187,10 @@ static int ensure_hooks(mon_object* o) {
     void* tmp[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     const size_t bytes[7] = {N * 16, N * 16, R * 8, R * 12, N * 4, (size_t)o->P * 4, N * MON_IN * 2};
     for (int k = 0; k < 7; ++k) {
-        cudaError_t e = cudaMalloc(&tmp[k], bytes[k]);
-        if (e == cudaSuccess) e = cudaMemset(tmp[k], 0, bytes[k]);
+        cudaError_t e = mon_dev_malloc(&tmp[k], bytes[k], o->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(tmp[k], 0, bytes[k], o->stream);
         if (e != cudaSuccess) {
-            for (void* p : tmp) if (p) cudaFree(p);
+            for (void* p : tmp) mon_dev_free(p, o->stream);
             return fail(MON_ERR_CUDA, "parity-hook buffers (%zu B): %s", bytes[k], cudaGetErrorString(e));
         }
     }
@@ -1191,7 +1284,7 @@ int fetch_as_float(mon_object* o, const void* src, int kind /*0 f32 1 f16 2 u32 
     if (kind == 0) {
         from = static_cast<const float*>(src);
     } else {
-        CK(cudaMalloc(&tmp, n * 4));
+        CK(mon_dev_malloc(reinterpret_cast<void**>(&tmp), n * 4, o->stream));
         const unsigned blocks = (unsigned)((n + 255) / 256);
         if (kind == 1) k_half_to_float<<<blocks, 256, 0, o->stream>>>(n, static_cast<const __half*>(src), tmp);
         else if (kind == 2) k_u32_to_float<<<blocks, 256, 0, o->stream>>>(n, static_cast<const uint32_t*>(src), tmp);
@@ -1201,7 +1294,7 @@ int fetch_as_float(mon_object* o, const void* src, int kind /*0 f32 1 f16 2 u32 
     }
     cudaError_t e = cudaMemcpyAsync(out, from, n * 4, cudaMemcpyDeviceToHost, o->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(o->stream);
-    if (tmp) cudaFree(tmp);
+    mon_dev_free(tmp, o->stream);
     if (e != cudaSuccess) return fail(MON_ERR_CUDA, "state read-back: %s", cudaGetErrorString(e));
     return MON_OK;
 }
@@ -1251,11 +1344,11 @@ int mon_object_last(mon_object* o, int which, float* out, size_t cap, size_t* n_
             if (n_out) *n_out = n;
             if (cap < n) return fail(MON_ERR_ARG, "buffer too small: need %zu floats", n);
             float* tmp = nullptr;
-            CK(cudaMalloc(&tmp, n * 4));
+            CK(mon_dev_malloc(reinterpret_cast<void**>(&tmp), n * 4, o->stream));
             k_soa_to_rows_float<<<(unsigned)((n + 255) / 256), 256, 0, o->stream>>>(N, MON_IN, o->enc, tmp);
             o->launches += 1;
             const int rc = fetch_as_float(o, tmp, 0, n, out);
-            cudaFree(tmp);
+            mon_dev_free(tmp, o->stream);
             return rc;
         }
         case 4: src = o->dbg_out; n = N * 4; break;
@@ -1281,28 +1374,28 @@ static int ensure_render_ws(mon_object* o, uint32_t n_rays, size_t jitter_floats
     const uint32_t tile = 16384;  // rays per pass: 1 Mi points, 64 MiB of fp16 features
     if (n_rays > o->r_cap_rays) {
         void* old[] = {o->r_rays, o->r_orig, o->r_rgb, o->r_depth, o->r_mask};
-        for (void* p : old) if (p) cudaFree(p);
+        for (void* p : old) mon_dev_free(p, o->stream);
         o->r_rays = nullptr; o->r_orig = nullptr; o->r_rgb = o->r_depth = o->r_mask = nullptr;
         o->r_cap_rays = 0;
-        CK(cudaMalloc(&o->r_rays, (size_t)n_rays * sizeof(MonRay)));
-        CK(cudaMalloc(&o->r_orig, (size_t)n_rays * 4));
-        CK(cudaMalloc(&o->r_rgb, (size_t)n_rays * 12));
-        CK(cudaMalloc(&o->r_depth, (size_t)n_rays * 4));
-        CK(cudaMalloc(&o->r_mask, (size_t)n_rays * 4));
+        CK(mon_dev_malloc(reinterpret_cast<void**>(&o->r_rays), (size_t)n_rays * sizeof(MonRay), o->stream));
+        CK(mon_dev_malloc(reinterpret_cast<void**>(&o->r_orig), (size_t)n_rays * 4, o->stream));
+        CK(mon_dev_malloc(reinterpret_cast<void**>(&o->r_rgb), (size_t)n_rays * 12, o->stream));
+        CK(mon_dev_malloc(reinterpret_cast<void**>(&o->r_depth), (size_t)n_rays * 4, o->stream));
+        CK(mon_dev_malloc(reinterpret_cast<void**>(&o->r_mask), (size_t)n_rays * 4, o->stream));
         o->r_cap_rays = n_rays;
     }
     if (!o->r_enc) {
-        CK(cudaMalloc(&o->r_enc, (size_t)tile * S2 * MON_IN * 2));
-        CK(cudaMalloc(&o->r_pts, (size_t)tile * S2 * 12));
-        if (!o->r_planar) CK(cudaMalloc(&o->r_planar, (size_t)o->n_grid * 2 + 16));
-        CK(cudaMalloc(&o->r_Twc, 64));
-        CK(cudaMalloc(&o->r_nhit, 4));
+        CK(mon_dev_malloc(reinterpret_cast<void**>(&o->r_enc), (size_t)tile * S2 * MON_IN * 2, o->stream));
+        CK(mon_dev_malloc(reinterpret_cast<void**>(&o->r_pts), (size_t)tile * S2 * 12, o->stream));
+        if (!o->r_planar) CK(mon_dev_malloc(reinterpret_cast<void**>(&o->r_planar), (size_t)o->n_grid * 2 + 16, o->stream));
+        CK(mon_dev_malloc(reinterpret_cast<void**>(&o->r_Twc), 64, o->stream));
+        CK(mon_dev_malloc(reinterpret_cast<void**>(&o->r_nhit), 4, o->stream));
         o->r_tile = tile;
     }
     if (jitter_floats > o->r_jit_cap) {
-        if (o->r_jit) cudaFree(o->r_jit);
+        mon_dev_free(o->r_jit, o->stream);
         o->r_jit = nullptr; o->r_jit_cap = 0;
-        CK(cudaMalloc(&o->r_jit, jitter_floats * 4));
+        CK(mon_dev_malloc(reinterpret_cast<void**>(&o->r_jit), jitter_floats * 4, o->stream));
         o->r_jit_cap = jitter_floats;
     }
     return MON_OK;
@@ -1373,9 +1466,9 @@ int mon_object_render_object_centric(mon_object* o, mon_bbox2d box, const float 
 static int scratch(mon_object* o, int slot, size_t bytes, void** out) {
     if (bytes > o->scr_cap[slot]) {
         CK(cudaStreamSynchronize(o->stream));
-        if (o->scr[slot]) cudaFree(o->scr[slot]);
+        mon_dev_free(o->scr[slot], o->stream);
         o->scr[slot] = nullptr; o->scr_cap[slot] = 0;
-        CK(cudaMalloc(&o->scr[slot], bytes));
+        CK(mon_dev_malloc(&o->scr[slot], bytes, o->stream));
         o->scr_cap[slot] = bytes;
     }
     *out = o->scr[slot];
@@ -1389,7 +1482,7 @@ static int infer_points_device(mon_object* o, const float* d_pts, uint32_t n, in
     const __half* params = use_ema ? o->ema : o->ph;
     const __half* planar = o->ph_planar;
     if (use_ema) {
-        if (!o->r_planar) CK(cudaMalloc(&o->r_planar, (size_t)o->n_grid * 2 + 16));
+        if (!o->r_planar) CK(mon_dev_malloc(reinterpret_cast<void**>(&o->r_planar), (size_t)o->n_grid * 2 + 16, o->stream));
         mon_launch_planarize(o->grid, o->ema + o->n_mlp, o->r_planar, st);
         o->launches += 1;
         planar = o->r_planar;

@@ -108,7 +108,7 @@ void mon_launch_optimizer(const MonOpt& o, MonCtrl* ctrl, float* pf, __half* ph,
                           float* m, float* v, uint32_t* ps, __half* ema, const float* loss, uint32_t R, const MonGrid& grid,
                           __half* planar, cudaStream_t st, int part = 0, uint32_t level_begin = 0, uint32_t level_end = 0xffffffffu,
                           const MonLaunchOpt& lo = MonLaunchOpt(), __half* gcls = nullptr, const uint32_t* live_cnt = nullptr,
-                          uint32_t resident_min_live = 0xffffffffu);
+                          uint32_t resident_min_live = 0xffffffffu, uint32_t sm_count = 148);
 enum { MON_OPT_ALL = 0, MON_OPT_MLP = 1, MON_OPT_GRID = 2, MON_OPT_MLP_GRID = 3 };
 // kernels_scatter_smem.cu: THE gradient scatter of the iteration graph, one launch, two paths chosen on the device by the
 // iteration's live-sample count: >= min_live -> shared-memory resident fixed-point slices flushed with TMA bulk reductions into the

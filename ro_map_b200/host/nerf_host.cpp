@@ -379,6 +379,9 @@ bool NeRF::CreateModelOnline(bool useSparseDepth, int Iterations) {
 
 void NeRF::TrainOnline() {   // nerf.cu:187-253
     if (!CreateCore()) exit(0);
+    // instantiate the iteration graphs now, while the object waits for its first boxes: done at the first training step
+    // (all objects of a scene reach it together) it held the driver for ~100 ms and the frontend thread's keyframe upload with it
+    if (mon_object_prepare_train(mpCore, (uint32_t)mnIteration) != MON_OK) cerr << "graph preparation: " << mon_last_error() << endl;
     int train_step_count = 0;
     while (1) {
         int train_step = 0;

@@ -418,22 +418,25 @@ def run_ours(args, rank, world, local_rank):
     for n in nerfs2:
         n.prepare_train(K)
         n.train(Wm)
-    stage_dev = None
+    stage_dev, shard = None, 0
     if distributed:
-        # the replicated keyframe set as three device blocks: rank 0 fills them from its pinned host copy, NCCL broadcasts them
-        stage_dev = [torch.empty_like(h_rgb, device="cuda"), torch.empty_like(h_inst, device="cuda"), torch.empty_like(h_dep, device="cuda")]
+        # the replicated keyframe set crosses PCIe ONCE for the whole job, 1 / N of it per GPU in parallel (every GPU has its own
+        # link to the host), and is completed on every GPU by an NCCL all-gather over NVLink / NVSwitch: three device blocks
+        # [N * shard frames], rank r owns frames [r * shard, (r + 1) * shard) and gathers in place
+        shard = (n_frames + world - 1) // world
+        stage_dev = [torch.empty((world * shard,) + tuple(h.shape[1:]), dtype=h.dtype, device="cuda") for h in (h_rgb, h_inst, h_dep)]
         for t in stage_dev:
-            dist.broadcast(t, src=0)             # NCCL communicator warm-up outside the timed region
+            dist.all_gather_into_tensor(t, t[rank * shard:(rank + 1) * shard])     # NCCL communicator warm-up outside the timed region
+    f0, f1 = (rank * shard, min(n_frames, (rank + 1) * shard)) if distributed else (0, n_frames)
     barrier()
     t0 = time.perf_counter()
     if not distributed:
         upload(ds2)                              # H2D: every keyframe again, from pinned host arrays (async DMA)
     else:
-        if rank == 0:
-            for t, h in zip(stage_dev, (h_rgb, h_inst, h_dep)):
-                t.copy_(h, non_blocking=True)    # H2D once, on rank 0
-        for t in stage_dev:
-            dist.broadcast(t, src=0)             # NVLink / NVSwitch
+        for t, h in zip(stage_dev, (h_rgb, h_inst, h_dep)):
+            if f1 > f0:
+                t[f0:f1].copy_(h[f0:f1], non_blocking=True)                       # H2D: this rank's shard only
+            dist.all_gather_into_tensor(t, t[rank * shard:(rank + 1) * shard])     # overlaps the next plane's H2D
         torch.cuda.current_stream().synchronize()
         for i in range(n_frames):                # device -> dataset storage (D2D inside each GPU)
             ds2.add_frame_device(i, stage_dev[0][i].data_ptr(), stage_dev[1][i].data_ptr(), stage_dev[2][i].data_ptr(), seq.poses[i])
@@ -447,7 +450,7 @@ def run_ours(args, rank, world, local_rank):
     if distributed:
         dist.barrier()
     e2e_s = partition.reduce_max(e2e_s, "cuda")
-    h2d = (n_frames * (px * 3 + px + px * 4) if (rank == 0 or not distributed) else 0) + n_frames * 96 + sum(len(seq.objects[k].boxes) for k in mine) * 20
+    h2d = max(0, f1 - f0) * (px * 3 + px + px * 4) + n_frames * 96 + sum(len(seq.objects[k].boxes) for k in mine) * 20
     h2d = partition.reduce_sum(float(h2d), "cuda")
     for n in nerfs2:
         n.close()
@@ -512,7 +515,7 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks.summary(),
         "e2e": {"value": n_objects * K / e2e_s, "unit": "iters/s", "h2d_bytes_per_step": h2d / (n_objects * K), "d2h_bytes_per_step": 48.0 / K,
                 "seconds": e2e_s, "final_loss": losses_e2e[0] if losses_e2e else None,
-                "region": ("keyframe upload from pinned host memory" if not distributed else "keyframe upload from pinned host memory on rank 0 + NCCL broadcast over NVLink + device-side ingest on every rank")
+                "region": ("keyframe upload from pinned host memory" if not distributed else "keyframe upload from pinned host memory, 1 / N of the set per rank in parallel + NCCL all-gather over NVLink + device-side ingest on every rank")
                           + " + box upload + K iterations per object + loss read-back"},
         "gpu_launches": int(launches),
         "roofline": roofline,

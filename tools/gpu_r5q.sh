@@ -1,0 +1,12 @@
+#!/bin/bash
+TAG=${1:-r5q}
+OUT=gpurun_out
+mkdir -p $OUT
+timeout 300 python bench.py --steps 20 --warmup 5 --no-secondary > $OUT/${TAG}_bench_20_5.json 2> $OUT/${TAG}_bench_20_5.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > $OUT/${TAG}_bench_2gpu_20_5.json 2> $OUT/${TAG}_bench_2gpu.err
+python -c "
+import json
+for f in ('$OUT/${TAG}_bench_20_5.json', '$OUT/${TAG}_bench_2gpu_20_5.json'):
+    d=json.loads(open(f).read().strip().splitlines()[-1]); print(f, round(d['value']), 'ms/step', round(d['ms_per_step'],4), 'e2e', round(d['e2e']['value']), d['e2e'].get('seconds'), d['e2e'].get('h2d_bytes_per_step'))
+"
+tail -3 $OUT/${TAG}_bench_2gpu.err

@@ -91,6 +91,15 @@ for at in [int(x) for x in a.at.split(",")]:
         periods.append((nxt - m0) / 1e3)
         print(f"iter {it}: period {(nxt - m0) / 1e3:.1f} us  " + " ".join(row))
     print(json.dumps({"after_iters": at, "mean_period_us": round(float(np.mean(periods)), 2)}))
+    # every iteration of the traced graph: period (M start to next M start) and kernel durations, to see drift inside the window
+    rows = []
+    for it in range(at, at + 31):
+        s0, s1 = it % ITERS, (it + 1) % ITERS
+        if not end[s0, 6] or not end[s1, 6]:
+            continue
+        dur = lambda k: round((int(end[s0, k]) - int(start[s0, k])) / 1e3, 1) if end[s0, k] else None   # noqa: E731
+        rows.append({"it": it, "period": round((int(start[s1, 6]) - int(start[s0, 6])) / 1e3, 1), "E": dur(2), "M": dur(6), "S": dur(7), "S1": dur(8), "O": dur(15)})
+    print("per-iteration: " + json.dumps(rows))
     done += 32
     # per-CTA phases of the shared-memory resident scatter for the traced iteration with (iter % 64) == 20
     try:

@@ -47,7 +47,7 @@ FLOPS_MLP_TRAIN_PER_POINT = {1: 18432, 2: 43008}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of each kernel from the committed ncu --set full captures
 # (profiles/, one hidden layer, R = 4096).  ncu flushes the caches before every replayed launch: COLD-cache figures; in
 # the running job the ~50 MB of per-object state stay L2-resident between kernels.  None = not captured for this build.
-TRAFFIC_NCU_FILE = ROOT / "profiles" / "r4_traffic.json"
+TRAFFIC_NCU_FILE = ROOT / "profiles" / "r6_traffic.json"   # written by tools/ncu_summary.py --traffic from the committed ncu --set full captures
 
 
 def parse():
@@ -474,7 +474,8 @@ def run_ours(args, rank, world, local_rank):
             ach, alg = enc_bytes / s_k / 1e9, enc_bytes
             stage_roof[name] = {"ms": ms_k, "bound": "hbm", "achieved": ach, "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "algorithmic": alg}
         elif name == "scatter":
-            # 512 B of gradient read-modify-write per point of the launch (all N points; only the live ones are scattered)
+            # 512 B of gradient read-modify-write per point of the launch (all N points; only the live ones are scattered: every one of
+            # them for a fresh object — shared-memory resident path of k_scatter —, ~1 in 12 in steady state — global reductions)
             ach, alg = enc_bytes / s_k / 1e9, enc_bytes
             stage_roof[name] = {"ms": ms_k, "bound": "hbm", "achieved": ach, "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "algorithmic": alg}
         elif name == "optimizer":
@@ -491,7 +492,7 @@ def run_ours(args, rank, world, local_rank):
     if stages:
         dominant = max(("encode", "scatter", "mlp_fused", "optimizer"), key=lambda k: stages[k])
         d = stage_roof[dominant]
-        roofline = {"kernel": {"encode": "k_encode_forward", "scatter": "k_encode_backward", "mlp_fused": "k_mlp_train_tc", "optimizer": "k_optimizer_sweep"}[dominant], "stage": dominant,
+        roofline = {"kernel": {"encode": "k_encode_forward", "scatter": "k_scatter", "mlp_fused": "k_mlp_train_tc", "optimizer": "k_optimizer_sweep"}[dominant], "stage": dominant,
                     "bound": d["bound"], "achieved": d["achieved"], "unit": d["unit"],
                     "peak": peaks["hbm_gbs"] if d["bound"] == "hbm" else peaks["tflops_sustained"], "peak_source": peaks["src"] + (" (sustained)" if d["bound"] == "tensor" else ""),
                     "frac": d["frac"], "traffic": traffic.get(dominant), "traffic_source": "profiles/ (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, cold caches)",

@@ -1,5 +1,21 @@
-"""Summarises an .ncu-rep: per kernel key metrics + top stalled source lines.  usage: ncu_summary.py file.ncu-rep [kernel-regex] [n_lines]"""
-import csv, io, subprocess, sys
+"""Summarises an .ncu-rep: per kernel key metrics + top stalled source lines.  usage: ncu_summary.py file.ncu-rep [kernel-regex] [n_lines]
+   ncu_summary.py --traffic out.json stage=file.ncu-rep:kernel-substring ...   writes dram read + write bytes per launch of the named kernels (bench.py roofline.traffic)"""
+import csv, io, json, subprocess, sys
+if len(sys.argv) > 2 and sys.argv[1] == "--traffic":
+    out = {}
+    for spec in sys.argv[3:]:
+        stage, rest = spec.split("=", 1)
+        rep, sub = rest.rsplit(":", 1)
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(raw))); hdr = rows[0]
+        ki, ri, wi = hdr.index('Kernel Name'), hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum')
+        unit = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+        vals = [float(r[ri]) * unit[rows[1][ri]] + float(r[wi]) * unit[rows[1][wi]] for r in rows[2:] if sub in r[ki]]
+        if vals:
+            out[stage] = sum(vals) / len(vals)
+    open(sys.argv[2], "w").write(json.dumps(out, indent=1) + "\n")
+    print(out)
+    sys.exit(0)
 rep = sys.argv[1]; rx = sys.argv[2] if len(sys.argv) > 2 else None; nl = int(sys.argv[3]) if len(sys.argv) > 3 else 14
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw))); hdr, units = rows[0], rows[1]

@@ -349,8 +349,8 @@ def run_ours(args, rank, world, local_rank):
     rgb_np, inst_np, dep_np = h_rgb.numpy(), h_inst.numpy(), h_dep.numpy()
 
     def upload(ds):
-        for i in range(n_frames):
-            ds.add_frame(i, rgb_np[i], inst_np[i], dep_np[i], seq.poses[i])
+        # the whole keyframe set in one call (DataToGPU): page-locked blocks, three asynchronous copies
+        ds.add_frames(0, rgb_np, inst_np, dep_np, seq.poses)
 
     def make_objects(ds, idx=None, c=None):
         objs = []
@@ -438,8 +438,8 @@ def run_ours(args, rank, world, local_rank):
                 t[f0:f1].copy_(h[f0:f1], non_blocking=True)                       # H2D: this rank's shard only
             dist.all_gather_into_tensor(t, t[rank * shard:(rank + 1) * shard])     # overlaps the next plane's H2D
         torch.cuda.current_stream().synchronize()
-        for i in range(n_frames):                # device -> dataset storage (D2D inside each GPU)
-            ds2.add_frame_device(i, stage_dev[0][i].data_ptr(), stage_dev[1][i].data_ptr(), stage_dev[2][i].data_ptr(), seq.poses[i])
+        # device -> dataset storage (D2D inside each GPU)
+        ds2.add_frames(0, stage_dev[0].data_ptr(), stage_dev[1].data_ptr(), stage_dev[2].data_ptr(), seq.poses)
     for k, n in zip(mine, nerfs2):
         n.set_bboxes(seq.objects[k].boxes)       # H2D: 20 B per box
     for n in nerfs2:

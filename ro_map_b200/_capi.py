@@ -56,6 +56,7 @@ SIGNATURES = {
     "mon_dataset_create": (C.c_int, [C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_uint32, C.c_int, _P(_vp)]),
     "mon_dataset_add_frame": (C.c_int, [_vp, C.c_uint32, _vp, C.c_int, _vp, _vp, _f32p]),
     "mon_dataset_add_frame_device": (C.c_int, [_vp, C.c_uint32, _vp, C.c_int, _vp, _vp, _f32p]),
+    "mon_dataset_add_frames": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, C.c_int, _vp, _vp, _f32p, C.c_int]),
     "mon_dataset_sync": (C.c_int, [_vp]),
     "mon_dataset_update_poses": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _f32p]),
     "mon_dataset_frame_count": (C.c_int, [_vp, _P(C.c_uint32)]),

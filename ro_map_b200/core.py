@@ -108,6 +108,24 @@ class Dataset:
         check(self._lib.mon_dataset_add_frame_device(self._h, frame_id, C.c_void_p(d_rgb), int(is_bgr), C.c_void_p(d_instance),
                                                       None if d_depth is None else C.c_void_p(d_depth), pose.ctypes.data_as(C.POINTER(C.c_float))))
 
+    def add_frames(self, first_id: int, rgb_u8, instance_u8, depth_f32, poses_c2w, is_bgr: bool = False):
+        """n consecutive keyframes in one call.  rgb_u8 [n, H, W, 3], instance_u8 [n, H, W], depth_f32 [n, H, W] or None: numpy blocks
+        (page-locked ones are DMA-ed straight out of, three copies per slab of 32 frames) or raw device addresses (ints, blocks in
+        this GPU's memory; the frame count then comes from poses_c2w)."""
+        n = len(poses_c2w)
+        flat = np.concatenate([_mat16(p) for p in poses_c2w]).astype(np.float32)
+        on_device = isinstance(rgb_u8, int)
+        if on_device:
+            a_rgb, a_inst, a_dep = C.c_void_p(rgb_u8), C.c_void_p(instance_u8), None if depth_f32 is None else C.c_void_p(depth_f32)
+        else:
+            for a, per in ((rgb_u8, self.H * self.W * 3), (instance_u8, self.H * self.W)):
+                if a.dtype != np.uint8 or not a.flags.c_contiguous or a.size != n * per:
+                    raise ValueError("frame block has the wrong size, dtype or layout")
+            if depth_f32 is not None and (depth_f32.dtype != np.float32 or not depth_f32.flags.c_contiguous or depth_f32.size != n * self.H * self.W):
+                raise ValueError("depth block has the wrong size, dtype or layout")
+            a_rgb, a_inst, a_dep = _ptr(rgb_u8), _ptr(instance_u8), None if depth_f32 is None else _ptr(depth_f32)
+        check(self._lib.mon_dataset_add_frames(self._h, first_id, n, a_rgb, int(is_bgr), a_inst, a_dep, flat.ctypes.data_as(C.POINTER(C.c_float)), int(on_device)))
+
     def sync(self):
         check(self._lib.mon_dataset_sync(self._h))
 

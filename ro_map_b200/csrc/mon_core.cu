@@ -91,6 +91,20 @@ static cudaError_t mon_dev_malloc(void** p, size_t bytes, cudaStream_t st) {
         if (e2 == cudaSuccess) e2 = cudaDeviceGetDefaultMemPool(&pool, dev);
         uint64_t keep = UINT64_MAX;
         if (e2 == cudaSuccess) e2 = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        // pool memory is reachable from the other GPUs of the node (keyframe replication copies peer to peer over NVLink)
+        int n_dev = 0;
+        if (e2 == cudaSuccess && cudaGetDeviceCount(&n_dev) == cudaSuccess) {
+            for (int peer = 0; peer < n_dev; ++peer) {
+                int can = 0;
+                if (peer == dev || cudaDeviceCanAccessPeer(&can, peer, dev) != cudaSuccess || !can) continue;
+                cudaMemAccessDesc desc = {};
+                desc.location.type = cudaMemLocationTypeDevice;
+                desc.location.id = peer;
+                desc.flags = cudaMemAccessFlagsProtReadWrite;
+                cudaMemPoolSetAccess(pool, &desc, 1);
+            }
+            cudaGetLastError();
+        }
         return e2;
     });
     if (e != cudaSuccess) return e;
@@ -229,6 +243,7 @@ struct mon_dataset {
     uint32_t n_frames = 0;
     MonFrame* d_frames = nullptr;
     std::vector<MonFrame> h_frames;
+    MonFrame* h_frames_pinned = nullptr;   // page-locked mirror the frame-table uploads read (a pageable source is staged by the driver)
     cudaStream_t stream = nullptr;
     // pinned staging for pageable caller buffers (rgb | instance | depth), double-buffered: a frame is copied into one
     // half while the previous frame's DMA still reads the other
@@ -441,6 +456,7 @@ int mon_dataset_create(int gpu, float fx, float fy, float cx, float cy, int H, i
     if ((e = cudaStreamCreateWithFlags(&ds->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = mon_dev_malloc(reinterpret_cast<void**>(&ds->d_frames), sizeof(MonFrame) * max_frames, ds->stream)) != cudaSuccess ||
         (e = cudaMemsetAsync(ds->d_frames, 0, sizeof(MonFrame) * max_frames, ds->stream)) != cudaSuccess ||
+        (e = cudaMallocHost(&ds->h_frames_pinned, sizeof(MonFrame) * max_frames)) != cudaSuccess ||
         (e = cudaMallocHost(&ds->staging[0], px * 3 + px + px * 4)) != cudaSuccess ||
         (e = cudaMallocHost(&ds->staging[1], px * 3 + px + px * 4)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&ds->ev_staged[0], cudaEventDisableTiming)) != cudaSuccess ||
@@ -456,22 +472,33 @@ int mon_dataset_create(int gpu, float fx, float fy, float cx, float cy, int H, i
     return MON_OK;
 }
 
-// device storage of one keyframe, carved out of its slab (allocated on first use)
+// device storage of one keyframe, carved out of its slab (allocated on first use).  A slab is PLANE-MAJOR — [rgb of its frames |
+// instance of its frames | depth of its frames] — so that consecutive frames' planes are contiguous and a block of frames
+// arrives in three copies (mon_dataset_add_frames) instead of three per frame.
+struct SlabLayout { size_t s_rgb, s_inst, s_depth; };       // per-frame strides of the three regions (256-byte aligned)
+static SlabLayout slab_layout(const mon_dataset* ds) {
+    const size_t px = (size_t)ds->H * ds->W;
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    return {up(px * 3), up(px), ds->use_depth ? up(px * 4) : 0};
+}
 static int ensure_frame_storage(mon_dataset* ds, uint32_t frame_id) {
     MonFrame& f = ds->h_frames[frame_id];
     if (f.rgb) return MON_OK;
-    const size_t px = (size_t)ds->H * ds->W;
-    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    const size_t o_inst = up(px * 3), o_depth = o_inst + up(px), per_frame = o_depth + (ds->use_depth ? up(px * 4) : 0);
+    const SlabLayout L = slab_layout(ds);
     const uint32_t slab = frame_id / MON_FRAMES_PER_SLAB;
-    if (!ds->slabs[slab]) {
-        const uint32_t n = std::min<uint32_t>(MON_FRAMES_PER_SLAB, ds->max_frames - slab * MON_FRAMES_PER_SLAB);
-        CK(mon_dev_malloc(reinterpret_cast<void**>(&ds->slabs[slab]), per_frame * n, ds->stream));
-    }
-    uint8_t* base = ds->slabs[slab] + per_frame * (frame_id % MON_FRAMES_PER_SLAB);
-    f.rgb = base; f.instance = base + o_inst;
-    f.depth = ds->use_depth ? reinterpret_cast<const float*>(base + o_depth) : nullptr;
+    const uint32_t n = std::min<uint32_t>(MON_FRAMES_PER_SLAB, ds->max_frames - slab * MON_FRAMES_PER_SLAB);
+    if (!ds->slabs[slab]) CK(mon_dev_malloc(reinterpret_cast<void**>(&ds->slabs[slab]), (L.s_rgb + L.s_inst + L.s_depth) * n, ds->stream));
+    uint8_t* base = ds->slabs[slab];
+    const uint32_t k = frame_id % MON_FRAMES_PER_SLAB;
+    f.rgb = base + L.s_rgb * k;
+    f.instance = base + L.s_rgb * n + L.s_inst * k;
+    f.depth = ds->use_depth ? reinterpret_cast<const float*>(base + (L.s_rgb + L.s_inst) * n + L.s_depth * k) : nullptr;
     return MON_OK;
+}
+// frame-table rows [first, first + n) -> device, from the page-locked mirror (asynchronous)
+static cudaError_t upload_frame_rows(mon_dataset* ds, uint32_t first, uint32_t n) {
+    memcpy(ds->h_frames_pinned + first, ds->h_frames.data() + first, sizeof(MonFrame) * n);
+    return cudaMemcpyAsync(ds->d_frames + first, ds->h_frames_pinned + first, sizeof(MonFrame) * n, cudaMemcpyHostToDevice, ds->stream);
 }
 
 int mon_dataset_add_frame(mon_dataset* ds, uint32_t frame_id, const uint8_t* rgb, int is_bgr,
@@ -502,7 +529,7 @@ int mon_dataset_add_frame(mon_dataset* ds, uint32_t frame_id, const uint8_t* rgb
         CK(cudaMemcpyAsync(const_cast<uint8_t*>(f.rgb), rgb, px * 3, cudaMemcpyHostToDevice, ds->stream));
         CK(cudaMemcpyAsync(const_cast<uint8_t*>(f.instance), instance, px, cudaMemcpyHostToDevice, ds->stream));
         if (ds->use_depth) CK(cudaMemcpyAsync(const_cast<float*>(f.depth), depth, px * 4, cudaMemcpyHostToDevice, ds->stream));
-        CK(cudaMemcpyAsync(ds->d_frames + frame_id, &f, sizeof(MonFrame), cudaMemcpyHostToDevice, ds->stream));   // pageable source: staged by the driver before returning
+        CK(upload_frame_rows(ds, frame_id, 1));
         CK(cudaEventRecord(ds->ev_uploaded, ds->stream));
     } else {
         // pageable caller buffers (cv::Mat of the SLAM frontend): one memcpy into the free half of the pinned staging
@@ -521,7 +548,7 @@ int mon_dataset_add_frame(mon_dataset* ds, uint32_t frame_id, const uint8_t* rgb
         CK(cudaMemcpyAsync(const_cast<uint8_t*>(f.rgb), st_rgb, px * 3, cudaMemcpyHostToDevice, ds->stream));
         CK(cudaMemcpyAsync(const_cast<uint8_t*>(f.instance), st_inst, px, cudaMemcpyHostToDevice, ds->stream));
         if (ds->use_depth) CK(cudaMemcpyAsync(const_cast<float*>(f.depth), st_depth, px * 4, cudaMemcpyHostToDevice, ds->stream));
-        CK(cudaMemcpyAsync(ds->d_frames + frame_id, &f, sizeof(MonFrame), cudaMemcpyHostToDevice, ds->stream));
+        CK(upload_frame_rows(ds, frame_id, 1));
         CK(cudaEventRecord(ds->ev_staged[half], ds->stream));
         CK(cudaEventRecord(ds->ev_uploaded, ds->stream));
     }
@@ -556,9 +583,57 @@ int mon_dataset_add_frame_device(mon_dataset* ds, uint32_t frame_id, const uint8
     CK(cudaMemcpyAsync(const_cast<uint8_t*>(f.rgb), d_rgb, px * 3, cudaMemcpyDeviceToDevice, ds->stream));
     CK(cudaMemcpyAsync(const_cast<uint8_t*>(f.instance), d_instance, px, cudaMemcpyDeviceToDevice, ds->stream));
     if (ds->use_depth) CK(cudaMemcpyAsync(const_cast<float*>(f.depth), d_depth, px * 4, cudaMemcpyDeviceToDevice, ds->stream));
-    CK(cudaMemcpyAsync(ds->d_frames + frame_id, &f, sizeof(MonFrame), cudaMemcpyHostToDevice, ds->stream));
+    CK(upload_frame_rows(ds, frame_id, 1));
     CK(cudaEventRecord(ds->ev_uploaded, ds->stream));
     ds->n_frames = std::max(ds->n_frames, frame_id + 1);
+    return MON_OK;
+}
+
+int mon_dataset_add_frames(mon_dataset* ds, uint32_t first_id, uint32_t n, const uint8_t* rgb, int is_bgr, const uint8_t* instance,
+                           const float* depth, const float* poses16, int on_device) {
+    if (!ds || !rgb || !instance || !poses16) return fail(MON_ERR_ARG, "NULL argument");
+    if ((uint64_t)first_id + n > ds->max_frames) return fail(MON_ERR_ARG, "frames %u..%u exceed max_frames %u", first_id, first_id + n, ds->max_frames);
+    if (ds->use_depth && !depth) return fail(MON_ERR_ARG, "dataset was created with use_depth but depth is NULL");
+    if (n == 0) return MON_OK;
+    const size_t px = (size_t)ds->H * ds->W;
+    if (!on_device && !(host_pinned(rgb) && host_pinned(instance) && (!ds->use_depth || host_pinned(depth)))) {
+        // pageable blocks: frame by frame through the pinned staging area
+        for (uint32_t i = 0; i < n; ++i) {
+            const int rc = mon_dataset_add_frame(ds, first_id + i, rgb + px * 3 * i, is_bgr, instance + px * i, depth ? depth + px * i : nullptr, poses16 + 16 * (size_t)i);
+            if (rc != MON_OK) return rc;
+        }
+        return MON_OK;
+    }
+    std::lock_guard<std::mutex> lock(ds->mu);
+    CK(cudaSetDevice(ds->gpu));
+    for (uint32_t i = 0; i < n; ++i) {
+        const int rc = ensure_frame_storage(ds, first_id + i);
+        if (rc != MON_OK) return rc;
+        MonFrame& f = ds->h_frames[first_id + i];
+        memcpy(f.pose, poses16 + 16 * (size_t)i, sizeof(float) * 16);
+        f.bgr = is_bgr ? 1u : 0u;
+    }
+    const SlabLayout L = slab_layout(ds);
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    // runs of frames that share a slab: one copy per plane kind where the device stride equals the block's (image sizes whose
+    // planes are multiples of 256 bytes: 800 x 800 is), else one copy per frame and plane
+    for (uint32_t i = 0; i < n;) {
+        const uint32_t id = first_id + i;
+        const uint32_t run = std::min<uint32_t>(n - i, MON_FRAMES_PER_SLAB - id % MON_FRAMES_PER_SLAB);
+        const MonFrame& f0 = ds->h_frames[id];
+        const uint32_t r_rgb = L.s_rgb == px * 3 ? 1u : run, r_inst = L.s_inst == px ? 1u : run, r_depth = L.s_depth == px * 4 ? 1u : run;
+        for (uint32_t k = 0; k < r_rgb; ++k)
+            CK(cudaMemcpyAsync(const_cast<uint8_t*>(f0.rgb) + L.s_rgb * k, rgb + px * 3 * (i + k), px * 3 * (run / r_rgb), kind, ds->stream));
+        for (uint32_t k = 0; k < r_inst; ++k)
+            CK(cudaMemcpyAsync(const_cast<uint8_t*>(f0.instance) + L.s_inst * k, instance + px * (i + k), px * (run / r_inst), kind, ds->stream));
+        if (ds->use_depth)
+            for (uint32_t k = 0; k < r_depth; ++k)
+                CK(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(const_cast<float*>(f0.depth)) + L.s_depth * k, depth + px * (i + k), px * 4 * (run / r_depth), kind, ds->stream));
+        i += run;
+    }
+    CK(upload_frame_rows(ds, first_id, n));
+    CK(cudaEventRecord(ds->ev_uploaded, ds->stream));
+    ds->n_frames = std::max(ds->n_frames, first_id + n);
     return MON_OK;
 }
 
@@ -577,8 +652,8 @@ int mon_dataset_update_poses(mon_dataset* ds, uint32_t first_frame, uint32_t n, 
     for (uint32_t i = 0; i < n; ++i) {
         MonFrame& f = ds->h_frames[first_frame + i];
         memcpy(f.pose, poses16 + (size_t)i * 16, sizeof(float) * 16);
-        CK(cudaMemcpyAsync(ds->d_frames + first_frame + i, &f, sizeof(MonFrame), cudaMemcpyHostToDevice, ds->stream));
     }
+    if (n) CK(upload_frame_rows(ds, first_frame, n));
     CK(cudaStreamSynchronize(ds->stream));
     return MON_OK;
 }
@@ -612,7 +687,7 @@ static int copy_frames_from_peer(mon_dataset* dst, const mon_dataset* src, uint3
         CK(cudaMemcpyPeerAsync(const_cast<uint8_t*>(f.instance), dst->gpu, s.instance, src->gpu, px, dst->stream));
         if (dst->use_depth) CK(cudaMemcpyPeerAsync(const_cast<float*>(f.depth), dst->gpu, s.depth, src->gpu, px * 4, dst->stream));
         memcpy(f.pose, s.pose, sizeof(float) * 16);
-        CK(cudaMemcpyAsync(dst->d_frames + i, &f, sizeof(MonFrame), cudaMemcpyHostToDevice, dst->stream));
+        CK(upload_frame_rows(dst, i, 1));
         dst->n_frames = std::max(dst->n_frames, i + 1);
     }
     CK(cudaEventRecord(dst->ev_uploaded, dst->stream));
@@ -655,6 +730,7 @@ int mon_dataset_destroy(mon_dataset* ds) {
     for (uint8_t* slab : ds->slabs) mon_dev_free(slab, ds->stream);
     mon_dev_free(ds->d_frames, ds->stream);
     if (ds->stream) cudaStreamSynchronize(ds->stream);
+    if (ds->h_frames_pinned) cudaFreeHost(ds->h_frames_pinned);
     for (int k = 0; k < 2; ++k) {
         if (ds->staging[k]) cudaFreeHost(ds->staging[k]);
         if (ds->ev_staged[k]) cudaEventDestroy(ds->ev_staged[k]);

@@ -111,6 +111,56 @@ def test_clone_from_peer_gives_the_identical_batch(core, bench_dataset, bench_se
     single.close()
 
 
+def test_block_upload_gives_the_identical_batch(core, bench_dataset, bench_seq):
+    """mon_dataset_add_frames (the whole keyframe set in one call: plane-major slabs, three copies per slab) from a pageable block,
+    from a page-locked block, from a block in device memory, and in two uneven pieces that straddle nothing / a partial block:
+    every variant gives the batch of the frame-by-frame upload, bit for bit."""
+    import torch
+    seq, obj = bench_seq, bench_seq.objects[0]
+    n = len(seq.poses)
+    rgb, inst, dep = np.ascontiguousarray(np.stack(seq.rgb)), np.ascontiguousarray(np.stack(seq.instance)), np.ascontiguousarray(np.stack(seq.depth))
+    variants = []
+    a = core.Dataset(0, *seq.K, seq.H, seq.W, n, True)
+    a.add_frames(0, rgb, inst, dep, seq.poses)                                   # pageable
+    variants.append(a)
+    t = [torch.from_numpy(x).pin_memory() for x in (rgb, inst, dep)]
+    b = core.Dataset(0, *seq.K, seq.H, seq.W, n, True)
+    b.add_frames(0, t[0].numpy(), t[1].numpy(), t[2].numpy(), seq.poses)         # page-locked: asynchronous
+    variants.append(b)
+    d = [x.cuda() for x in t]
+    torch.cuda.synchronize()
+    c = core.Dataset(0, *seq.K, seq.H, seq.W, n, True)
+    c.add_frames(0, d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), seq.poses)   # device block
+    variants.append(c)
+    e = core.Dataset(0, *seq.K, seq.H, seq.W, n, True)
+    k = 7
+    e.add_frames(k, t[0].numpy()[k:], t[1].numpy()[k:], t[2].numpy()[k:], seq.poses[k:])   # second piece first
+    e.add_frames(0, t[0].numpy()[:k], t[1].numpy()[:k], t[2].numpy()[:k], seq.poses[:k])
+    variants.append(e)
+    for v in variants:
+        v.sync()
+        assert v.frame_count == n
+    with pytest.raises(core.MonError, match="MON_ERR_ARG"):
+        a.add_frames(n - 1, rgb[:2], inst[:2], dep[:2], seq.poses[:2])           # beyond max_frames
+    cfg = core.default_config(rays_per_batch=R_BENCH)
+    bmin, bmax = -1.1 * obj.half, 1.1 * obj.half
+    rng = np.random.default_rng(10)
+    u = lambda shape: (1.0 - rng.random(shape, dtype=np.float32)).astype(np.float32)   # noqa: E731
+    sxy, col, dt = u((R_BENCH, 2)), u((R_BENCH, 3)), u((R_BENCH, 32))
+    outs = []
+    for ds in [bench_dataset] + variants:
+        g = core.NerfObject(ds, cfg, obj.Tow, bmin, bmax, obj.instance_id)
+        g.set_bboxes(obj.boxes)
+        loss, n_in = g.train_injected(sxy, col, dt)
+        outs.append((loss, n_in, g.last("rays"), g.last("target"), g.last("target_depth"), g.last("ray_instance"), g.last("enc"), g.last("out")))
+        g.close()
+    for other in outs[1:]:
+        for x, y in zip(outs[0], other):
+            assert np.array_equal(x, y)
+    for v in variants:
+        v.close()
+
+
 def test_short_calls_run_at_the_long_call_rate(core, bench_dataset, bench_seq):
     """A 20-iteration call (the online TrainStepIterations range, and what the driver's bench times) replays ONE graph of exactly
     20 iterations with the batch generation of iteration i+1 hidden behind iteration i: its per-iteration device time stays

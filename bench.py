@@ -61,6 +61,7 @@ def parse():
     ap.add_argument("--frames", type=int, default=FRAMES)
     ap.add_argument("--objects", type=int, default=0, help="objects in the job (default: one per GPU); object k trains on GPU k mod N")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the CPU baseline sample")
+    ap.add_argument("--occupancy", type=int, default=0, help="OPT-IN occupancy-grid mode with this grid resolution (changes results; default 0 = off, the parity configuration)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary figures (render, R=1024 / 2 hidden layers, 4 objects on one GPU)")
     return ap.parse_args()
 
@@ -169,6 +170,8 @@ def workload_config(args, n_objects, world):
             "rays_per_batch": args.rays, "samples_per_ray": S, "points_per_iter": args.rays * S, "n_hidden_layers": args.hidden_layers,
             "objects": n_objects, "keyframes": args.frames, "partition": "object k -> GPU k mod N, per-object streams / threads (no collective)",
             "iterations_timed": f"{args.warmup} .. {args.warmup + args.steps} of a fresh object",
+            "mode": ("reference sampling: every stratified sample is evaluated (the parity configuration)" if not getattr(args, "occupancy", 0) else
+                     f"OPT-IN occupancy grid {args.occupancy}^3 + warp-ballot sample compaction (changes results; not the parity configuration)"),
             "l2_policy": "keyframe set 154 MB > 126 MB L2; per-object state (~50 MB) is L2-resident between iterations by design, as in production back-to-back iterations"}
 
 
@@ -358,6 +361,8 @@ def run_ours(args, rank, world, local_rank):
             o = seq.objects[k]
             n = core.NerfObject(ds, c or cfg, o.Tow, -1.1 * o.half, 1.1 * o.half, o.instance_id)
             n.set_bboxes(o.boxes)
+            if args.occupancy:
+                n.set_occupancy(args.occupancy, warmup_iters=256, update_interval=16, alpha_threshold=0.01)
             objs.append(n)
         return objs
 

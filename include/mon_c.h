@@ -193,6 +193,16 @@ int mon_object_set_params(mon_object* obj, const float* params_fp32, size_t n);
  * 7 mask_rays 8 dout(4/pt) 9 d_enc(32/pt) 10 target rgb 11 target depth 12 ray instance flag
  * 13 per-ray loss */
 int mon_object_last(mon_object* obj, int which, float* out, size_t cap, size_t* n_out);
+/* OPT-IN occupancy grid with warp-ballot sample compaction — OFF by default and in every parity run: it changes which samples
+ * contribute, hence the results.  The reference carries instant-ngp's accelerators as dead code (NeRF_Model::Step,
+ * VolumeRenderGradient with compaction, nerf_model.cu:957-1132,1504-1550); BASELINE.json's north_star names them.
+ * grid_res^3 cells over the object's box (0 switches the mode off; multiple of 4 in 8..256).  After warmup_iters iterations the
+ * grid is refreshed every update_interval iterations (at graph-replay boundaries) from the network's density on the cell
+ * corners (running maximum with decay 0.95); a cell is empty while the opacity of one average sample interval inside it is below
+ * alpha_threshold.  Samples in empty cells are not encoded and count as empty space (density 0, no gradient). */
+int mon_object_set_occupancy(mon_object* obj, uint32_t grid_res, uint32_t warmup_iters, uint32_t update_interval, float alpha_threshold);
+/* fraction of occupied cells, and of the last iteration's samples that fell into occupied cells */
+int mon_object_occupancy_stats(mon_object* obj, float* occupied_cell_fraction, float* occupied_sample_fraction);
 /* host-only: the work split of the hash-encode kernel (kernels_encode.cu) for n_ctas CTAs over levels
  * [level_begin, level_end): out4[4*b..] = first (job, point) and end (job, point) of piece b, job = 2*level + feature.
  * No device needed; lets a CPU test check that the pieces tile the [job][point] space exactly. */

@@ -78,6 +78,8 @@ SIGNATURES = {
     "mon_object_launch_count": (C.c_int, [_vp, _P(C.c_uint64)]),
     "mon_object_render": (C.c_int, [_vp, Bbox2d, _f32p, C.c_int, _vp, _vp, _vp, _vp]),
     "mon_debug_encode_pieces": (C.c_int, [_P(Config), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _P(C.c_uint32)]),
+    "mon_object_set_occupancy": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float]),
+    "mon_object_occupancy_stats": (C.c_int, [_vp, _f32p, _f32p]),
     "mon_debug_scatter_pieces": (C.c_int, [_P(Config), C.c_uint32, C.c_uint32, _P(C.c_uint32)]),
     "mon_object_render_object_centric": (C.c_int, [_vp, Bbox2d, _f32p, C.c_int, _vp, _vp, _vp, _vp]),
     "mon_object_density_grid": (C.c_int, [_vp, _P(C.c_uint32), _vp]),

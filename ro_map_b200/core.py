@@ -272,6 +272,15 @@ class NerfObject:
         check(self._lib.mon_object_train_injected(self._h, _ptr(sxy), _ptr(col), _ptr(dt), C.byref(loss), C.byref(n_in)))
         return loss.value, n_in.value
 
+    def set_occupancy(self, grid_res: int, warmup_iters: int = 256, update_interval: int = 16, alpha_threshold: float = 0.01):
+        """OPT-IN occupancy grid + warp-ballot sample compaction (changes results; grid_res = 0 switches it off again)."""
+        check(self._lib.mon_object_set_occupancy(self._h, grid_res, warmup_iters, update_interval, alpha_threshold))
+
+    def occupancy_stats(self):
+        a, b = C.c_float(0), C.c_float(0)
+        check(self._lib.mon_object_occupancy_stats(self._h, C.byref(a), C.byref(b)))
+        return {"occupied_cell_fraction": a.value, "occupied_sample_fraction": b.value}
+
     def state(self, which: str) -> np.ndarray:
         out = np.empty(self.n_params, np.float32)
         check(self._lib.mon_object_get_state(self._h, self.STATE[which], _ptr(out), out.size))

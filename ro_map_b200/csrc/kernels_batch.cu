@@ -179,6 +179,7 @@ k_generate_batch(MonBatch b, MonScene sc) {
         // live-sample counter of THIS iteration (filled by the fused MLP kernel, read by the scatter + Adam kernel): two
         // counters alternate, because this kernel runs one iteration ahead, beside the previous iteration's scatter
         if (b.live_cnt) b.live_cnt[iter & 1u] = 0u;
+        if (b.occ.count) *b.occ.count = 0u;       // opt-in occupancy mode: the sample-points kernel appends this iteration's occupied samples
     }
 }
 

@@ -36,6 +36,16 @@ extern "C" int mon_debug_tl_enc_cta_read(unsigned long long* out) { return (int)
 #endif
 
 // ---------------------------------------------------------------------------------------------- sample points
+// ---- opt-in occupancy grid: is the unit-cube position u in an occupied cell?  (positions on or slightly outside the faces clamp)
+MON_DEV bool mon_occ_test(const uint32_t* __restrict__ bits, uint32_t res, const float* u) {
+    const float r = (float)res;
+    const uint32_t x = (uint32_t)min(max((int)floorf(u[0] * r), 0), (int)res - 1);
+    const uint32_t y = (uint32_t)min(max((int)floorf(u[1] * r), 0), (int)res - 1);
+    const uint32_t z = (uint32_t)min(max((int)floorf(u[2] * r), 0), (int)res - 1);
+    const uint32_t idx = x + res * (y + res * z);
+    return (__ldg(bits + (idx >> 5)) >> (idx & 31u)) & 1u;
+}
+
 // A3: t_n = tmin + dt*(n + xi), p = o + t*d, u = (p - bmin) / (bmax - bmin)  (nerf_model.cu:545-565,140-144).
 // One thread per sample; rays of the batch are already compacted and padded.  pts: [N][3] fp32, the reference's
 // PointsInput.  in_box (render only): rays that miss the box get the cube centre (never composited).
@@ -43,16 +53,16 @@ __global__ void __launch_bounds__(256)
 k_sample_points(uint32_t n_points, uint32_t S, const MonRay* __restrict__ rays, const int* __restrict__ in_box,
                 const float* __restrict__ jitter, uint32_t seed, const MonCtrl* __restrict__ ctrl, uint32_t rng_stream,
                 uint32_t iter_fixed, float bmin0, float bmin1, float bmin2, float bmax0, float bmax1, float bmax2,
-                float* __restrict__ pts, const uint32_t* __restrict__ orig_ray) {
+                float* __restrict__ pts, const uint32_t* __restrict__ orig_ray, MonOcc occ) {
     mon_pdl_wait();
     mon_pdl_trigger();
     if (ctrl && ctrl->skip) return;
     MON_TL(MON_TL_P, ctrl ? ctrl->iter - 1 : 0u);
     const uint32_t pt = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pt >= n_points) return;
+    const bool in_range = pt < n_points;
     const uint32_t ray = pt / S, n = pt - ray * S;
     float u[3] = {0.5f, 0.5f, 0.5f};
-    if (!in_box || in_box[ray]) {
+    if (in_range && (!in_box || in_box[ray])) {
         const MonRay r = rays[ray];
         // the batch kernel already advanced ctrl->iter; this iteration's counter is iter-1
         const uint32_t iter = ctrl ? ctrl->iter - 1 : iter_fixed;
@@ -62,16 +72,34 @@ k_sample_points(uint32_t n_points, uint32_t S, const MonRay* __restrict__ rays, 
         const float bmin[3] = {bmin0, bmin1, bmin2}, bmax[3] = {bmax0, bmax1, bmax2};
         mon_sample_point(r, t, bmin, bmax, u);
     }
-    pts[(size_t)pt * 3 + 0] = u[0];
-    pts[(size_t)pt * 3 + 1] = u[1];
-    pts[(size_t)pt * 3 + 2] = u[2];
+    if (in_range) {
+        pts[(size_t)pt * 3 + 0] = u[0];
+        pts[(size_t)pt * 3 + 1] = u[1];
+        pts[(size_t)pt * 3 + 2] = u[2];
+    }
+    if (occ.bits) {
+        // opt-in occupancy mode (training, S == 32: a warp is one ray): the ray's occupancy mask for the fused MLP kernel and the
+        // compacted list of occupied samples for the encode kernel; one atomicAdd per warp reserves the slots of its lanes
+        const bool keep = in_range && mon_occ_test(occ.bits, occ.res, u);
+        const uint32_t m = __ballot_sync(0xffffffffu, keep);
+        const uint32_t lane = threadIdx.x & 31u;
+        uint32_t base = 0;
+        if (lane == 0) {
+            if (in_range) occ.ray_mask[ray] = m;
+            if (m) base = atomicAdd(occ.count, (uint32_t)__popc(m));
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (keep) occ.list[base + __popc(m & ((1u << lane) - 1u))] = pt;
+    }
 }
 
 void mon_launch_sample_points(uint32_t n_points, uint32_t S, const MonRay* rays, const int* in_box, const float* jitter,
                               uint32_t seed, const MonCtrl* ctrl, uint32_t rng_stream, uint32_t iter_fixed,
-                              const float* bmin, const float* bmax, float* pts, cudaStream_t st, const MonLaunchOpt& lo, const uint32_t* orig_ray) {
+                              const float* bmin, const float* bmax, float* pts, cudaStream_t st, const MonLaunchOpt& lo, const uint32_t* orig_ray,
+                              const MonOcc* occ) {
+    MonOcc none = {nullptr, 0u, nullptr, nullptr, nullptr};
     mon_launch_chain(MON_PDL_POINTS, lo, k_sample_points, dim3((n_points + 255) / 256), dim3(256), 0, st, n_points, S, rays, in_box, jitter, seed, ctrl, rng_stream,
-                     iter_fixed, bmin[0], bmin[1], bmin[2], bmax[0], bmax[1], bmax[2], pts, orig_ray);
+                     iter_fixed, bmin[0], bmin[1], bmin[2], bmax[0], bmax[1], bmax[2], pts, orig_ray, occ ? *occ : none);
 }
 
 // ---------------------------------------------------------------------------------------------- forward
@@ -92,6 +120,7 @@ __device__ __forceinline__ void bulk_load_table(uint32_t smem_dst, const void* g
     }
 }
 
+// LIST != nullptr (opt-in occupancy mode): the kernel walks the compacted list of occupied samples, p is a position in that list
 template <bool HASHED>
 __device__ __forceinline__ __half enc_one_pow2(const float* __restrict__ pts, uint32_t p, float scale, uint32_t bmask, uint32_t my, uint32_t mz,
                                                const unsigned char* __restrict__ table) {
@@ -126,10 +155,19 @@ __device__ __forceinline__ __half enc_one_pow2(const float* __restrict__ pts, ui
 // fp16 rounding chain of a point is serial (FFMA -> F2F -> HADD2 per corner), further independent chains hide it.
 template <bool HASHED, int U>
 __device__ __forceinline__ void enc_points_pow2(const float* __restrict__ pts, __half* __restrict__ out, uint32_t p_first, uint32_t p_end,
-                                                float scale, uint32_t size, uint32_t res, const unsigned char* __restrict__ table) {
+                                                float scale, uint32_t size, uint32_t res, const unsigned char* __restrict__ table,
+                                                const uint32_t* __restrict__ list) {
     const uint32_t bmask = 2u * size - 2u;
     const uint32_t my = HASHED ? 2654435761u : res, mz = HASHED ? 805459861u : res * res;
     uint32_t p = p_first;
+    if (list) {
+        // occupancy mode: position p of the compacted list -> sample index; one sample per trip (the list is short)
+        for (; p < p_end; p += ENC_THREADS) {
+            const uint32_t pt = __ldg(list + p);
+            out[(size_t)pt * 2] = enc_one_pow2<HASHED>(pts, pt, scale, bmask, my, mz, table);
+        }
+        return;
+    }
     if (U > 1) {
         for (; p + (U - 1) * ENC_THREADS < p_end; p += U * ENC_THREADS) {
             __half a[U];
@@ -175,9 +213,9 @@ __host__ __device__ __forceinline__ EncPos enc_cost_to_pos(uint64_t c, uint32_t 
 // planar: per level [feature 0 table | feature 1 table], each size[l] fp16 (the level starts at 2*offset[l] halves)
 template <int U>
 __global__ void __launch_bounds__(ENC_THREADS, 1)
-k_encode_forward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, const __half* __restrict__ planar,
+k_encode_forward(MonGrid g, uint32_t n_points_all, const float* __restrict__ pts, const __half* __restrict__ planar,
                  __half* __restrict__ enc_soa, const MonCtrl* __restrict__ ctrl, uint32_t job_begin, uint32_t job_end,
-                 uint32_t job_large, uint32_t job_hashed) {
+                 uint32_t job_large, uint32_t job_hashed, const uint32_t* __restrict__ occ_list, const uint32_t* __restrict__ occ_count) {
     extern __shared__ __align__(128) unsigned char enc_smem[];
     __shared__ __align__(8) uint64_t bar;
     const __half* table = reinterpret_cast<const __half*>(enc_smem);
@@ -188,6 +226,10 @@ k_encode_forward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, co
     mon_pdl_trigger();
     if (ctrl && ctrl->skip) return;
     MON_TL(MON_TL_E + ((job_begin >> 3) & 3u), ctrl ? ctrl->iter - 1 : 0u);
+    // opt-in occupancy mode: the point space of the jobs is the compacted list of occupied samples (length on the device); the
+    // encodings of the other samples keep stale values the fused MLP kernel masks.  n_points_all stays the stride of enc_soa.
+    const uint32_t n_points = occ_list ? *occ_count : n_points_all;
+    if (n_points == 0u) return;
 
     // jobs [job_begin, job_end) of the 2 * n_levels (level, feature) jobs (callers may launch sub-ranges).
     // The flattened [job][point] space is cut into one contiguous piece per CTA, equal in COST: a point of a dense level
@@ -222,12 +264,13 @@ k_encode_forward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, co
         const bool hashed = g.hashed[l] != 0;
         const uint32_t res = g.res[l];
         const bool pow2 = (size & (size - 1)) == 0;
-        __half* out = enc_soa + (size_t)l * n_points * 2 + f;   // level-major pairs: enc[level][point][feature]
+        __half* out = enc_soa + (size_t)l * n_points_all * 2 + f;   // level-major pairs: enc[level][point][feature]
         if (pow2) {
-            if (hashed) enc_points_pow2<true, U>(pts, out, p0 + tid, p1, scale, size, res, enc_smem);
-            else enc_points_pow2<false, U>(pts, out, p0 + tid, p1, scale, size, res, enc_smem);
+            if (hashed) enc_points_pow2<true, U>(pts, out, p0 + tid, p1, scale, size, res, enc_smem, occ_list);
+            else enc_points_pow2<false, U>(pts, out, p0 + tid, p1, scale, size, res, enc_smem, occ_list);
         } else {
-            for (uint32_t p = p0 + tid; p < p1; p += ENC_THREADS) {
+            for (uint32_t q = p0 + tid; q < p1; q += ENC_THREADS) {
+                const uint32_t p = occ_list ? __ldg(occ_list + q) : q;
                 const float u0 = __ldg(pts + (size_t)p * 3), u1 = __ldg(pts + (size_t)p * 3 + 1), u2 = __ldg(pts + (size_t)p * 3 + 2);
                 float fr[3]; uint32_t cell[3];
                 mon_pos_fract(u0, scale, fr[0], cell[0]);
@@ -254,7 +297,8 @@ k_encode_forward(MonGrid g, uint32_t n_points, const float* __restrict__ pts, co
 
 template <int U>
 static cudaError_t enc_launch(const MonGrid& g, uint32_t n_points, const float* pts, const __half* planar, __half* enc_soa, const MonCtrl* ctrl,
-                              uint32_t ctas, cudaStream_t st, uint32_t level_begin, uint32_t level_end, const MonLaunchOpt& lo) {
+                              uint32_t ctas, cudaStream_t st, uint32_t level_begin, uint32_t level_end, const MonLaunchOpt& lo,
+                              const uint32_t* occ_list, const uint32_t* occ_count) {
     static std::atomic<uint64_t> prepared{0};
     const cudaError_t prep = mon_once_per_device(prepared, [] {
         cudaError_t e = cudaFuncSetAttribute(k_encode_forward<U>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -268,12 +312,12 @@ static cudaError_t enc_launch(const MonGrid& g, uint32_t n_points, const float* 
     l_hashed = l_large;
     while (l_hashed < level_end && !g.hashed[l_hashed]) ++l_hashed;
     return mon_launch_chain(MON_PDL_ENCODE, lo, k_encode_forward<U>, dim3(ctas), dim3(ENC_THREADS), ENC_TABLE_BYTES, st, g, n_points, pts, planar, enc_soa, ctrl,
-                            2 * level_begin, 2 * level_end, 2 * l_large, 2 * l_hashed);
+                            2 * level_begin, 2 * level_end, 2 * l_large, 2 * l_hashed, occ_list, occ_count);
 }
 
 cudaError_t mon_launch_encode_forward(const MonGrid& g, uint32_t n_points, const float* pts, const __half* planar, __half* enc_soa,
                                       const MonCtrl* ctrl, uint32_t sm_count, cudaStream_t st, uint32_t level_begin, uint32_t level_end,
-                                      const MonLaunchOpt& lo) {
+                                      const MonLaunchOpt& lo, const uint32_t* occ_list, const uint32_t* occ_count) {
     if (level_end > g.n_levels) level_end = g.n_levels;
     if (n_points == 0 || level_begin >= level_end) return cudaSuccess;
     // every CTA loads up to two 128 KB slices: do not spread tiny batches over the whole chip
@@ -283,10 +327,10 @@ cudaError_t mon_launch_encode_forward(const MonGrid& g, uint32_t n_points, const
     if (ctas == 0) ctas = 1;
     static const int unroll = [] { const char* e = getenv("MON_ENC_UNROLL"); const int u = e ? atoi(e) : ENC_UNROLL; return (u >= 1 && u <= 4) ? u : ENC_UNROLL; }();
     switch (unroll) {
-        case 1: return enc_launch<1>(g, n_points, pts, planar, enc_soa, ctrl, ctas, st, level_begin, level_end, lo);
-        case 3: return enc_launch<3>(g, n_points, pts, planar, enc_soa, ctrl, ctas, st, level_begin, level_end, lo);
-        case 4: return enc_launch<4>(g, n_points, pts, planar, enc_soa, ctrl, ctas, st, level_begin, level_end, lo);
-        default: return enc_launch<2>(g, n_points, pts, planar, enc_soa, ctrl, ctas, st, level_begin, level_end, lo);
+        case 1: return enc_launch<1>(g, n_points, pts, planar, enc_soa, ctrl, ctas, st, level_begin, level_end, lo, occ_list, occ_count);
+        case 3: return enc_launch<3>(g, n_points, pts, planar, enc_soa, ctrl, ctas, st, level_begin, level_end, lo, occ_list, occ_count);
+        case 4: return enc_launch<4>(g, n_points, pts, planar, enc_soa, ctrl, ctas, st, level_begin, level_end, lo, occ_list, occ_count);
+        default: return enc_launch<2>(g, n_points, pts, planar, enc_soa, ctrl, ctas, st, level_begin, level_end, lo, occ_list, occ_count);
     }
 }
 

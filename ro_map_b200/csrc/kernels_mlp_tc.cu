@@ -389,7 +389,11 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
             float o[4], go[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) o[k] = __half2float(__float2half_rn(o16[k]));   // the network output is fp16
+            // opt-in occupancy mode: a sample in an unoccupied cell was not encoded (its row is stale): empty space, no gradient
+            const bool empty = b.occ.bits && ray_ok && !((__ldg(b.occ.ray_mask + ray) >> c.lane) & 1u);
+            if (empty) o[3] = -1e30f;                                                    // density exp(o[3]) = 0
             const RayResult rr = warp_render_loss_grad(o, t, c.lane, rt, kscale, lc, go);
+            if (empty) { go[0] = go[1] = go[2] = go[3] = 0.0f; }
             if (ray_ok && c.lane == 0) {
 #pragma unroll
                 for (int k = 0; k < 3; ++k) b.rgb_rays[ray * 3 + k] = rr.rgb[k];

@@ -313,6 +313,14 @@ struct mon_object {
     __half* gcls = nullptr;
     uint32_t resident_min_live = 0xffffffffu;
     bool scatter_unified = true;      // false: a configuration kernels_scatter_smem.cu does not cover (stand-alone global-reduction kernel)
+    // opt-in occupancy grid (mon_object_set_occupancy; off: occ_res == 0).  The density grid is the running maximum (decayed) of
+    // the network's density on the cell corners; a cell is occupied while that exceeds the threshold
+    uint32_t occ_res = 0, occ_warmup = 0, occ_interval = 0;
+    float occ_sigma_thresh = 0.0f, occ_decay = 0.95f;
+    uint32_t* occ_bits = nullptr; float* occ_density = nullptr;
+    uint32_t *occ_ray_mask = nullptr, *occ_list = nullptr, *occ_count = nullptr;
+    uint64_t iters_enqueued = 0, occ_last_update = 0;
+    bool occ_started = false;
     // instantiated iteration graphs by length
     struct GraphSlot { uint32_t iters; cudaGraphExec_t exec; uint64_t stamp; };
     std::vector<GraphSlot> graphs;
@@ -764,6 +772,7 @@ static MonBatch make_batch(mon_object* o, bool injected, bool debug) {
     b.rgb_rays = o->rgb_rays; b.depth_rays = o->depth_rays; b.mask_rays = o->mask_rays; b.loss = o->loss;
     b.enc = o->enc;
     b.pts = o->pts; b.pts_c = o->pts_c; b.genc = o->genc; b.live_cnt = o->live_cnt;
+    b.occ = MonOcc{o->occ_bits, o->occ_res, o->occ_ray_mask, o->occ_list, o->occ_count};
     if (debug) { b.dbg_out = o->dbg_out; b.dbg_dout = o->dbg_dout; b.d_enc = o->d_enc; }
     b.params = o->ph; b.grads = o->gh; b.mlp_partials = o->partials;
     return b;
@@ -784,12 +793,14 @@ static int launch_batch(mon_object* o, const MonBatch& b, cudaStream_t st) {
 }
 static int launch_points(mon_object* o, const MonBatch& b, cudaStream_t st, bool pdl = true) {
     MonLaunchOpt lo; lo.pdl = pdl;
-    mon_launch_sample_points(o->N, MON_S, o->rays, nullptr, b.inj_dt, o->seed, o->ctrl, 2, 0, o->scene.bmin, o->scene.bmax, o->pts, st, lo);
+    mon_launch_sample_points(o->N, MON_S, o->rays, nullptr, b.inj_dt, o->seed, o->ctrl, 2, 0, o->scene.bmin, o->scene.bmax, o->pts, st, lo, nullptr,
+                             o->occ_bits ? &b.occ : nullptr);
     return MON_OK;
 }
 static int launch_encode(mon_object* o, cudaStream_t st, bool pdl = true) {
     MonLaunchOpt lo; lo.pdl = pdl;
-    cudaError_t e = mon_launch_encode_forward(o->grid, o->N, o->pts, o->ph_planar, o->enc, o->ctrl, (uint32_t)o->sm_count, st, 0, 0xffffffffu, lo);
+    cudaError_t e = mon_launch_encode_forward(o->grid, o->N, o->pts, o->ph_planar, o->enc, o->ctrl, (uint32_t)o->sm_count, st, 0, 0xffffffffu, lo,
+                                              o->occ_bits ? o->occ_list : nullptr, o->occ_bits ? o->occ_count : nullptr);
     if (e != cudaSuccess) return fail(MON_ERR_CUDA, "hash encode launch: %s", cudaGetErrorString(e));
     return MON_OK;
 }
@@ -1059,7 +1070,7 @@ int mon_object_destroy(mon_object* o) {
     drop_graphs(o);
     void* ptrs[] = {o->pf, o->m, o->v, o->ps, o->ph, o->gh, o->ema, o->ctrl_state, o->ctrl, o->ctrl_late, o->d_boxes, o->rays, o->ray_inst, o->target,
                     o->target_depth, o->bg, o->rgb_rays, o->depth_rays, o->mask_rays, o->loss, o->pts, o->pts_c, o->genc, o->live_cnt, o->debias_lut, o->enc,
-                    o->d_enc, o->ph_planar, o->gcls, o->partials,
+                    o->d_enc, o->ph_planar, o->gcls, o->partials, o->occ_bits, o->occ_density, o->occ_ray_mask, o->occ_list, o->occ_count,
                     o->dbg_out, o->dbg_dout, o->inj_xy, o->inj_col, o->inj_dt, o->grad_snap, o->r_rays, o->r_orig, o->r_nhit, o->r_enc,
                     o->r_jit, o->r_rgb, o->r_depth, o->r_mask, o->r_Twc, o->r_pts, o->r_planar};
     for (void* p : ptrs) mon_dev_free(p, o->stream);
@@ -1141,6 +1152,13 @@ int mon_object_prepare_train(mon_object* o, uint32_t iters) {
     return MON_OK;
 }
 
+static int occ_update(mon_object* o);      // refresh of the opt-in occupancy grid (defined with the inference helpers below)
+static int occ_maybe_update(mon_object* o) {
+    if (!o->occ_res || o->iters_enqueued < o->occ_warmup) return MON_OK;
+    if (o->occ_started && o->iters_enqueued - o->occ_last_update < o->occ_interval) return MON_OK;
+    return occ_update(o);
+}
+
 int mon_object_train_async(mon_object* o, uint32_t iters) {
     if (!o) return fail(MON_ERR_ARG, "obj is NULL");
     if (o->h_boxes.empty()) return fail(MON_ERR_STATE, "no 2-D boxes: call mon_object_set_bboxes first");
@@ -1154,8 +1172,17 @@ int mon_object_train_async(mon_object* o, uint32_t iters) {
     if (rem) { int rc = graph_for(o, rem, &g_rem); if (rc != MON_OK) return rc; }
     CK(cudaStreamWaitEvent(o->stream, o->ds->ev_uploaded, 0));   // frames uploaded asynchronously from pinned buffers
     CK(cudaEventRecord(o->ev0, o->stream));
-    for (uint32_t k = 0; k < plan.n_chunk; ++k) CK(cudaGraphLaunch(g_chunk, o->stream));
-    if (rem) CK(cudaGraphLaunch(g_rem, o->stream));
+    // opt-in occupancy mode: the grid is refreshed between graph replays (enqueued on the same stream, no host wait)
+    for (uint32_t k = 0; k < plan.n_chunk; ++k) {
+        if (o->occ_res) { int rc = occ_maybe_update(o); if (rc != MON_OK) return rc; }
+        CK(cudaGraphLaunch(g_chunk, o->stream));
+        o->iters_enqueued += plan.chunk;
+    }
+    if (rem) {
+        if (o->occ_res) { int rc = occ_maybe_update(o); if (rc != MON_OK) return rc; }
+        CK(cudaGraphLaunch(g_rem, o->stream));
+        o->iters_enqueued += rem;
+    }
     CK(cudaEventRecord(o->ev1, o->stream));
     o->timing_pending = true;
     o->launches += launches_in_graph(o, iters);
@@ -1349,6 +1376,28 @@ __global__ void k_soa_to_rows_half(size_t n, uint32_t C, const __half* __restric
     if (i >= n * C) return;
     const size_t p = i / C, c = i - p * C;
     out[i] = soa[((c >> 1) * n + p) * 2 + (c & 1)];
+}
+// occupancy grid update: cell (x, y, z) of a res^3 grid takes the maximum density exp(logit) over its 8 corners on the (res+1)^3
+// lattice, the running grid is max(decay * old, new), and the cell's bit is set while that exceeds the threshold (32 consecutive
+// cells = one word, written by ballot).  res^3 is a multiple of 32.
+__global__ void k_occ_fold(uint32_t res, const float* __restrict__ out4, float* __restrict__ density, uint32_t* __restrict__ bits, float decay, float thresh) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = res * res * res;
+    bool occ = false;
+    if (i < n) {
+        const uint32_t x = i % res, y = (i / res) % res, z = i / (res * res), r1 = res + 1;
+        float m = -1e30f;
+#pragma unroll
+        for (uint32_t c = 0; c < 8; ++c) {
+            const size_t li = (size_t)(x + (c & 1u)) + (size_t)r1 * ((y + ((c >> 1) & 1u)) + (size_t)r1 * (z + (c >> 2)));
+            m = fmaxf(m, out4[4 * li + 3]);
+        }
+        const float d = fmaxf(density[i] * decay, __expf(fminf(m, 30.0f)));
+        density[i] = d;
+        occ = d > thresh;
+    }
+    const uint32_t word = __ballot_sync(0xffffffffu, occ);
+    if ((threadIdx.x & 31u) == 0u && i < n) bits[i >> 5] = word;
 }
 __global__ void k_extract_sigma(size_t n, const float* __restrict__ out4, float* __restrict__ sigma) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1556,7 +1605,7 @@ static int scratch(mon_object* o, int slot, size_t bytes, void** out) {
 
 // network logits at arbitrary unit-cube positions (device pointer in, device out4 [n][4]); the inference half of
 // DifferentiableObject::inference as GetDensityOnGrid / compute_mesh_vertex_colors use it (nerf_model.cu:2007-2067)
-static int infer_points_device(mon_object* o, const float* d_pts, uint32_t n, int use_ema, float* d_out4) {
+static int infer_points_device(mon_object* o, const float* d_pts, uint32_t n, int use_ema, float* d_out4, bool sync = true) {
     cudaStream_t st = o->stream;
     const __half* params = use_ema ? o->ema : o->ph;
     const __half* planar = o->ph_planar;
@@ -1572,7 +1621,7 @@ static int infer_points_device(mon_object* o, const float* d_pts, uint32_t n, in
     cudaError_t e = mon_launch_encode_forward(o->grid, n, d_pts, planar, enc, nullptr, (uint32_t)o->sm_count, st);
     if (e == cudaSuccess) e = mon_launch_mlp_infer_tc(n, o->cfg.n_hidden_layers, params, enc, d_out4, st);
     o->launches += 2;
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess && sync) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return fail(MON_ERR_CUDA, "inference: %s", cudaGetErrorString(e));
     return MON_OK;
 }
@@ -1622,6 +1671,86 @@ int mon_object_density_grid(mon_object* o, const uint32_t res[3], float* out) {
     }
     if (rc != MON_OK) return rc;
     if (e != cudaSuccess) return fail(MON_ERR_CUDA, "density grid: %s", cudaGetErrorString(e));
+    return MON_OK;
+}
+
+// ------------------------------------------------------------------------------- opt-in occupancy grid
+// The reference carries instant-ngp's accelerators as dead code (Step / VolumeRenderGradient with compaction,
+// nerf_model.cu:957-1132,1504-1550; BASELINE north_star: "occupancy-grid ray marching with warp-ballot sample compaction").
+// Here: a res^3 bit grid over the object's box, refreshed from the network's own density between graph replays; the
+// sample-points kernel tests every stratified sample against it and compacts the occupied ones by warp ballot, the encode
+// kernel walks that list only, the fused MLP kernel treats the others as empty space.  It changes which samples contribute,
+// hence the results: OFF by default and in every parity run.
+static int occ_update(mon_object* o) {
+    cudaStream_t st = o->stream;
+    const uint32_t r1 = o->occ_res + 1;
+    const size_t n = (size_t)r1 * r1 * r1;
+    float *pts = nullptr, *out4 = nullptr;
+    int rc = scratch(o, 1, n * 12, reinterpret_cast<void**>(&pts));
+    if (rc == MON_OK) rc = scratch(o, 2, n * 16, reinterpret_cast<void**>(&out4));
+    if (rc != MON_OK) return rc;
+    k_lattice_points<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(r1, r1, r1, pts);
+    rc = infer_points_device(o, pts, (uint32_t)n, 0, out4, false);        // training weights, asynchronous
+    if (rc != MON_OK) return rc;
+    const uint32_t cells = o->occ_res * o->occ_res * o->occ_res;
+    k_occ_fold<<<(cells + 255) / 256, 256, 0, st>>>(o->occ_res, out4, o->occ_density, o->occ_bits, o->occ_started ? o->occ_decay : 0.0f, o->occ_sigma_thresh);
+    o->launches += 2;
+    CK(cudaGetLastError());
+    o->occ_started = true;
+    o->occ_last_update = o->iters_enqueued;
+    return MON_OK;
+}
+
+int mon_object_set_occupancy(mon_object* o, uint32_t grid_res, uint32_t warmup_iters, uint32_t update_interval, float alpha_threshold) {
+    if (!o) return fail(MON_ERR_ARG, "obj is NULL");
+    CK(cudaSetDevice(o->ds->gpu));
+    CK(cudaStreamSynchronize(o->stream));
+    drop_graphs(o);                      // the iteration graphs capture the grid's pointers (or their absence)
+    void* old[] = {o->occ_bits, o->occ_density, o->occ_ray_mask, o->occ_list, o->occ_count};
+    for (void* p : old) mon_dev_free(p, o->stream);
+    o->occ_bits = nullptr; o->occ_density = nullptr; o->occ_ray_mask = o->occ_list = o->occ_count = nullptr;
+    o->occ_res = 0; o->occ_started = false;
+    if (grid_res == 0) return MON_OK;
+    if (grid_res < 8 || grid_res > 256 || (grid_res & 3u)) return fail(MON_ERR_ARG, "grid_res must be 0 (off) or a multiple of 4 in 8..256");
+    if (!(alpha_threshold > 0.0f && alpha_threshold < 1.0f)) return fail(MON_ERR_ARG, "alpha_threshold must be in (0, 1)");
+    const size_t cells = (size_t)grid_res * grid_res * grid_res;
+    cudaError_t e;
+    if ((e = mon_dev_malloc(reinterpret_cast<void**>(&o->occ_bits), cells / 8, o->stream)) != cudaSuccess ||
+        (e = mon_dev_malloc(reinterpret_cast<void**>(&o->occ_density), cells * 4, o->stream)) != cudaSuccess ||
+        (e = mon_dev_malloc(reinterpret_cast<void**>(&o->occ_ray_mask), (size_t)o->R * 4, o->stream)) != cudaSuccess ||
+        (e = mon_dev_malloc(reinterpret_cast<void**>(&o->occ_list), (size_t)o->N * 4, o->stream)) != cudaSuccess ||
+        (e = mon_dev_malloc(reinterpret_cast<void**>(&o->occ_count), 4, o->stream)) != cudaSuccess ||
+        (e = cudaMemsetAsync(o->occ_bits, 0xff, cells / 8, o->stream)) != cudaSuccess ||          // everything occupied until the first refresh
+        (e = cudaMemsetAsync(o->occ_density, 0, cells * 4, o->stream)) != cudaSuccess ||
+        (e = cudaMemsetAsync(o->occ_ray_mask, 0xff, (size_t)o->R * 4, o->stream)) != cudaSuccess ||
+        (e = cudaMemsetAsync(o->occ_count, 0, 4, o->stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(o->stream)) != cudaSuccess)
+        return fail(MON_ERR_CUDA, "occupancy grid allocation: %s", cudaGetErrorString(e));
+    o->occ_res = grid_res;
+    o->occ_warmup = warmup_iters;
+    o->occ_interval = update_interval ? update_interval : 16u;
+    // a cell counts as empty while the opacity of one average sample interval inside it stays below alpha_threshold:
+    // 1 - exp(-sigma * dt) < alpha  <=>  sigma < -ln(1 - alpha) / dt,  dt = mean box edge / samples per ray
+    const float edge = ((o->scene.bmax[0] - o->scene.bmin[0]) + (o->scene.bmax[1] - o->scene.bmin[1]) + (o->scene.bmax[2] - o->scene.bmin[2])) / 3.0f;
+    o->occ_sigma_thresh = -logf(1.0f - alpha_threshold) / (edge / (float)MON_S);
+    o->occ_last_update = o->iters_enqueued;
+    return MON_OK;
+}
+
+int mon_object_occupancy_stats(mon_object* o, float* occupied_cell_fraction, float* occupied_sample_fraction) {
+    if (!o) return fail(MON_ERR_ARG, "obj is NULL");
+    if (!o->occ_res) return fail(MON_ERR_STATE, "the occupancy grid is off (mon_object_set_occupancy)");
+    CK(cudaSetDevice(o->ds->gpu));
+    const size_t words = (size_t)o->occ_res * o->occ_res * o->occ_res / 32;
+    std::vector<uint32_t> bits(words);
+    uint32_t cnt = 0;
+    CK(cudaMemcpyAsync(bits.data(), o->occ_bits, words * 4, cudaMemcpyDeviceToHost, o->stream));
+    CK(cudaMemcpyAsync(&cnt, o->occ_count, 4, cudaMemcpyDeviceToHost, o->stream));
+    CK(cudaStreamSynchronize(o->stream));
+    size_t set = 0;
+    for (uint32_t w : bits) set += (size_t)__builtin_popcount(w);
+    if (occupied_cell_fraction) *occupied_cell_fraction = (float)set / (float)(words * 32);
+    if (occupied_sample_fraction) *occupied_sample_fraction = (float)cnt / (float)o->N;      // of the last iteration
     return MON_OK;
 }
 

@@ -80,11 +80,13 @@ void mon_launch_render_rays(uint32_t n_rays, mon_bbox2d box, const MonScene& sc,
 void mon_launch_sample_points(uint32_t n_points, uint32_t S, const MonRay* rays, const int* in_box, const float* jitter,
                               uint32_t seed, const MonCtrl* ctrl, uint32_t rng_stream, uint32_t iter_fixed,
                               const float* bmin, const float* bmax, float* pts, cudaStream_t st, const MonLaunchOpt& lo = MonLaunchOpt(),
-                              const uint32_t* orig_ray = nullptr);   // render: compacted ray -> pixel, indexes the jitter
+                              const uint32_t* orig_ray = nullptr,    // render: compacted ray -> pixel, indexes the jitter
+                              const MonOcc* occ = nullptr);          // training, opt-in occupancy mode: ray masks + compacted list of occupied samples
 // levels [level_begin, level_end) only (default: all)
 cudaError_t mon_launch_encode_forward(const MonGrid& g, uint32_t n_points, const float* pts, const __half* planar, __half* enc_soa,
                                       const MonCtrl* ctrl, uint32_t sm_count, cudaStream_t st, uint32_t level_begin = 0,
-                                      uint32_t level_end = 0xffffffffu, const MonLaunchOpt& lo = MonLaunchOpt());
+                                      uint32_t level_end = 0xffffffffu, const MonLaunchOpt& lo = MonLaunchOpt(),
+                                      const uint32_t* occ_list = nullptr, const uint32_t* occ_count = nullptr);   // opt-in: encode the listed samples only
 void mon_launch_planarize(const MonGrid& g, const __half* inter, __half* planar, cudaStream_t st);
 void mon_encode_pieces_host(const MonGrid& g, uint32_t n_points, uint32_t n_ctas, uint32_t level_begin, uint32_t level_end, uint32_t* out4);
 // stand-alone gradient scatter with global f16x2 reductions over the compacted live samples: configurations the unified kernel

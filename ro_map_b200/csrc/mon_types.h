@@ -82,6 +82,16 @@ struct MonOpt {
 
 struct MonLossCfg { float loss_scale, depth_lambda, mask_lambda, bg_density_reg; };
 
+// Opt-in occupancy grid (OFF in every parity run: bits == nullptr).  res^3 cells over the object's unit cube, one bit per cell;
+// samples in cells whose bit is clear are not encoded and count as empty space (density 0, no gradient).
+struct MonOcc {
+    const uint32_t* bits;    // [res^3 / 32], cell (x, y, z) = bit x + res * (y + res * z)
+    uint32_t res;
+    uint32_t* ray_mask;      // [R] bit s = sample s of the ray lies in an occupied cell (written by the sample-points kernel)
+    uint32_t* list;          // [N] indices of the occupied samples of the iteration, compacted (any order)
+    uint32_t* count;         // [1] number of entries of list; zeroed by the batch kernel
+};
+
 // everything a training iteration touches, as raw device pointers
 struct MonBatch {
     uint32_t R;                 // rays per batch
@@ -109,6 +119,7 @@ struct MonBatch {
     float* pts_c;
     uint32_t* genc;
     uint32_t* live_cnt;   // [2]: number of live samples of the iteration, indexed by (iteration & 1); zeroed by the batch kernel
+    MonOcc occ;           // opt-in occupancy grid of the object (bits == nullptr: off)
     // debug dumps (nullptr in production): out [N][4], dout [N][4]
     float* dbg_out; float* dbg_dout;
     // parameters

@@ -406,6 +406,7 @@ def run_ours(args, rank, world, local_rank):
             for n in nerfs:
                 n.sync()
     ms_max = partition.reduce_max(ms, "cuda")
+    ms_ranks = partition.gather_all(ms, "cuda")
     launches = int(partition.reduce_sum(float(launches), "cuda"))
     loss = nerfs[0].train(1) if nerfs else float("nan")
 
@@ -516,6 +517,7 @@ def run_ours(args, rank, world, local_rank):
         "metric": "train iters/sec per object", "value": iters_per_s, "unit": "iters/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16 storage / f32 accumulate", "data": "synthetic", "config": workload_config(args, n_objects, world),
+        "ms_per_step_by_rank": [m / K for m in ms_ranks],
         "iters_per_s_per_object": iters_per_s / max(n_objects, 1),
         "rays_per_s": iters_per_s * R, "points_per_s": iters_per_s * N, "final_loss": loss,
         "clocks": clocks.summary(),

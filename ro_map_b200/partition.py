@@ -30,6 +30,18 @@ def reduce_max(value: float, device=None) -> float:
     return float(t.item())
 
 
+def gather_all(value: float, device=None) -> list:
+    """the per-rank scalars of all ranks, in rank order (diagnostics: which rank was the slowest); [value] when not distributed."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [float(value)]
+    t = torch.tensor([value], dtype=torch.float64, device=device if device is not None else "cpu")
+    out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return [float(x.item()) for x in out]
+
+
 def reduce_sum(value: float, device=None) -> float:
     import torch
     import torch.distributed as dist

@@ -13,9 +13,18 @@ obj = seq.objects[0]
 ds = core.Dataset(0, *seq.K, seq.H, seq.W, len(seq.poses), True)
 for i in range(len(seq.poses)):
     ds.add_frame(i, seq.rgb[i], seq.instance[i], seq.depth[i], seq.poses[i])
-for nh, R in ((1, 256), (2, 128)):
-    g = core.NerfObject(ds, core.default_config(rays_per_batch=R, n_hidden_layers=nh), obj.Tow, -1.1 * obj.half, 1.1 * obj.half, obj.instance_id)
+import os
+# both scatter paths (MON_SCATTER_RESIDENT_MIN is read at object creation: 0 = always the shared-memory resident path, -1 = never),
+# then the opt-in occupancy mode, and the block upload
+blk = core.Dataset(0, *seq.K, seq.H, seq.W, len(seq.poses), True)
+blk.add_frames(0, np.ascontiguousarray(np.stack(seq.rgb)), np.ascontiguousarray(np.stack(seq.instance)), np.ascontiguousarray(np.stack(seq.depth)), seq.poses)
+blk.sync()
+for nh, R, resident_min, occ in ((1, 256, "0", 0), (2, 128, "-1", 0), (1, 256, "0", 16)):
+    os.environ["MON_SCATTER_RESIDENT_MIN"] = resident_min
+    g = core.NerfObject(blk if occ else ds, core.default_config(rays_per_batch=R, n_hidden_layers=nh), obj.Tow, -1.1 * obj.half, 1.1 * obj.half, obj.instance_id)
     g.set_bboxes(obj.boxes)
+    if occ:
+        g.set_occupancy(occ, warmup_iters=4, update_interval=2, alpha_threshold=0.01)
     rng = np.random.default_rng(0)
     u = lambda shape: (1.0 - rng.random(shape, dtype=np.float32)).astype(np.float32)
     print("injected", g.train_injected(u((R, 2)), u((R, 3)), u((R, 32))))
@@ -23,6 +32,9 @@ for nh, R in ((1, 256), (2, 128)):
     fid, x, y, h, w = [int(v) for v in obj.boxes[0]]
     rgb, dep, mask = g.render((fid, x, y, min(h, 16), min(w, 16)), seq.poses[fid])
     print("render", float(mask.mean()), "lattice", float(g.density_grid((8, 8, 8)).mean()))
+    if occ:
+        print("occupancy", g.occupancy_stats())
     g.close()
 ds.close()
+blk.close()
 print("sanitize target done")

@@ -34,7 +34,7 @@
 
 #define MON_DEBIAS_LUT 32768  // steps covered by the Adam bias-correction table (offline jobs run 5000 iterations)
 #define MON_FRAMES_PER_SLAB 32
-#define MON_RESIDENT_MIN_LIVE 24576u   // live samples from which the shared-memory resident scatter takes an iteration (measured crossover)
+#define MON_RESIDENT_MIN_LIVE 16384u   // live samples from which the shared-memory resident scatter takes an iteration (measured crossover)
 #define MON_GRAPH_CHUNK 64   // longest captured graph: a call of n iterations replays one chunk length that divides n (32..64) where
                              // there is one — 500 = 10 x 50, a single graph to instantiate — else n / 64 graphs of 64 + one of exactly n % 64
 #define MON_BOX_CAP0 1024    // 2-D boxes the box buffer holds from the start (the iteration graphs capture its address)
@@ -880,7 +880,8 @@ static int capture_graph(mon_object* o, int iters, cudaGraphExec_t* out) {
         }
         if ((rc = launch_scatter(o, st)) != MON_OK) break;
         // no programmatic edge behind the unified scatter kernel: sweep CTAs that become resident while its 1024-thread CTAs still
-        // run slowed the sweep by 3-5 us (profiles/r5i_timeline*.txt); a plain edge costs a 2 us gap
+        // run slowed the sweep by 3-5 us (profiles/r5i_timeline*.txt); a plain edge costs a 2 us gap (deferring the scatter's trigger
+        // to its CTAs' exit changes nothing either way: profiles/r8b_timeline_late_edge.txt)
         launch_optimizer(o, st, !o->scatter_unified);
         if (fork && (e = cudaStreamWaitEvent(st, o->ev_join, 0)) != cudaSuccess) break;
     }

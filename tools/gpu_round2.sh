@@ -23,9 +23,7 @@ for f in ("${OUT}/${TAG}_bench_ref_20_5.json", "${OUT}/${TAG}_bench_20_5.json", 
         print(f, "unreadable", e)
 PY
 timeout 300 python tools/stage_times.py --at 0,50,500 > $OUT/${TAG}_stage_times.txt 2>&1
-for MIN in 0 -1; do
-  MON_SCATTER_RESIDENT_MIN=$MIN timeout 300 python tools/stage_times.py --at 0,25,40,60,100,300 > $OUT/${TAG}_stage_times_min_$MIN.txt 2>&1
-done
+timeout 300 python tools/scatter_crossover.py > $OUT/${TAG}_scatter_crossover.txt 2>&1; tail -1 $OUT/${TAG}_scatter_crossover.txt
 timeout 300 python tools/timeline.py --at 5,400 > $OUT/${TAG}_timeline.txt 2>&1
 grep "iter 1[78]\|iter 41[23]\|mean" $OUT/${TAG}_timeline.txt
 # launch list of the driver-shaped command (cold caches, serialised: shares, not times)
@@ -36,12 +34,13 @@ KERNELS='k_encode_forward|k_mlp_train_tc|k_scatter|k_optimizer_sweep|k_generate_
 timeout 900 ncu --set full --clock-control none --import-source on --graph-profiling node -k regex:"$KERNELS" \
     --launch-skip 48 --launch-count 6 -f -o $OUT/${TAG}_full_fresh python tools/ncu_target.py --warm 5 > $OUT/${TAG}_ncu_fresh.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on --graph-profiling node -k regex:"$KERNELS" \
-    --launch-skip 2400 --launch-count 6 -f -o $OUT/${TAG}_full_steady python tools/ncu_target.py > $OUT/${TAG}_ncu_steady.log 2>&1
+    --launch-skip 2400 --launch-count 9 -f -o $OUT/${TAG}_full_steady python tools/ncu_target.py > $OUT/${TAG}_ncu_steady.log 2>&1
 python tools/ncu_summary.py $OUT/${TAG}_full_fresh.ncu-rep k_scatter 24 > $OUT/${TAG}_ncu_kernels_fresh_object.txt 2>&1
 python tools/ncu_summary.py $OUT/${TAG}_full_steady.ncu-rep k_encode_forward 24 > $OUT/${TAG}_ncu_kernels_steady_state.txt 2>&1
 python tools/ncu_summary.py --traffic $OUT/${TAG}_traffic.json scatter=$OUT/${TAG}_full_fresh.ncu-rep:k_scatter encode=$OUT/${TAG}_full_steady.ncu-rep:k_encode_forward \
-    mlp_fused=$OUT/${TAG}_full_steady.ncu-rep:k_mlp_train_tc optimizer=$OUT/${TAG}_full_steady.ncu-rep:k_optimizer_sweep scatter_steady=$OUT/${TAG}_full_steady.ncu-rep:k_scatter
+    mlp_fused=$OUT/${TAG}_full_steady.ncu-rep:k_mlp_train_tc optimizer=$OUT/${TAG}_full_steady.ncu-rep:k_optimizer_sweep scatter_steady=$OUT/${TAG}_full_steady.ncu-rep:k_scatter optimizer_fresh=$OUT/${TAG}_full_fresh.ncu-rep:k_optimizer_sweep
 grep -A14 "k_scatter" $OUT/${TAG}_ncu_kernels_fresh_object.txt | head -16
+timeout 600 python tools/occupancy_report.py --seeds 2 > $OUT/${TAG}_occupancy_report.jsonl 2>&1; tail -2 $OUT/${TAG}_occupancy_report.jsonl
 timeout 900 bash tools/gpu_facade_runs.sh > $OUT/${TAG}_facade.log 2>&1
 cp $OUT/facade_runs.txt $OUT/${TAG}_facade_runs.txt
 grep -E "ingest_ms_per|ingest_ms min|wall|rc " $OUT/${TAG}_facade_runs.txt | cut -c1-200

@@ -103,6 +103,19 @@ int mon_dataset_add_frames(mon_dataset* ds, uint32_t first_id, uint32_t n, const
  * until mon_dataset_sync(). */
 int mon_dataset_add_frame_device(mon_dataset* ds, uint32_t frame_id, const uint8_t* d_rgb, int is_bgr,
                                  const uint8_t* d_instance, const float* d_depth, const float pose[16]);
+/* Depth as the depth image holds it.  DataToGPU reads a 16-bit PNG, converts it on the host — depthImg.convertTo(CV_32FC1,
+ * mfDepthScale) (nerf_data.cu:176-186) — and uploads 4 bytes per pixel.  After this call (allowed until the first keyframe is
+ * added) the dataset takes and stores the RAW u16 samples and the batch kernel converts the pixels it picks, (float)u16 *
+ * depth_factor = the float the reference stores: a quarter less keyframe traffic over PCIe and in HBM (6 instead of 8 bytes
+ * per pixel) and no host-side conversion pass.  Frames are then added through the _d16 entries below (same arguments as their
+ * f32 counterparts, depth16: H*W uint16); the f32 entries are refused, and so are the _d16 ones on a dataset in f32 mode. */
+int mon_dataset_set_depth_u16(mon_dataset* ds, float depth_factor);
+int mon_dataset_add_frame_d16(mon_dataset* ds, uint32_t frame_id, const uint8_t* rgb, int is_bgr,
+                              const uint8_t* instance, const uint16_t* depth16, const float pose[16]);
+int mon_dataset_add_frames_d16(mon_dataset* ds, uint32_t first_id, uint32_t n, const uint8_t* rgb, int is_bgr, const uint8_t* instance,
+                               const uint16_t* depth16, const float* poses16, int on_device);
+int mon_dataset_add_frame_device_d16(mon_dataset* ds, uint32_t frame_id, const uint8_t* d_rgb, int is_bgr,
+                                     const uint8_t* d_instance, const uint16_t* d_depth16, const float pose[16]);
 /* Page-locked (cudaHostAlloc / cudaHostRegister) RGB-order buffers are uploaded asynchronously without a staging copy;
  * they must stay valid until mon_dataset_sync() returns or a blocking call on an object of this dataset completes. */
 int mon_dataset_sync(mon_dataset* ds);

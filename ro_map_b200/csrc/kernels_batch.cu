@@ -66,7 +66,10 @@ __device__ __forceinline__ void write_ray(const MonBatch& b, const MonScene& sc,
         b.target[idx * 3 + 0] = __fmul_rn((float)px[ir], (float)(1.0 / 255.0));
         b.target[idx * 3 + 1] = __fmul_rn((float)px[1], (float)(1.0 / 255.0));
         b.target[idx * 3 + 2] = __fmul_rn((float)px[2u - ir], (float)(1.0 / 255.0));
-        b.target_depth[idx] = (sc.use_depth && fr->depth) ? __fmul_rn(fr->depth[pix], c.d_norm) : 0.0f;
+        float z = 0.0f;
+        if (sc.use_depth && fr->depth)
+            z = fr->depth_factor != 0.0f ? __fmul_rn((float)reinterpret_cast<const uint16_t*>(fr->depth)[pix], fr->depth_factor) : fr->depth[pix];
+        b.target_depth[idx] = __fmul_rn(z, c.d_norm);
         b.ray_inst[idx] = 1;
     } else {
         b.target[idx * 3 + 0] = mon_rand(b.inj_col, b.seed, iter, 1, idx * 3 + 0);

@@ -71,7 +71,7 @@ __device__ __forceinline__ unsigned tc_smid() { unsigned s; asm volatile("mov.u3
 #define SM_DOUT 40960    //  4096  [128][16]  core layout (2 chunks per row)
 #define SM_WIN 45056     //  4096  W_in  [64][32] SW64 : B of the input GEMM (K-major) and of dL/denc (MN-major)
 #define SM_WOUT 49152    //  2048  W_out [16][64] SW128: B of the output GEMM (K-major) and of dL/dhidden (MN-major)
-#define SM_BAR 51200     //  mbarrier (8) + tmem base (4)
+#define SM_BAR 51200     //  2 mbarriers (16) + tmem base (4)
 // n_hidden_layers == 2 only: the first hidden layer's tiles and the 64x64 weight
 #define SM_H1 52224      // 16384  [128][64]  SW128   (H1 | dH1 adjacent, like hid | dhid)
 #define SM_DH1 68608     // 16384
@@ -93,27 +93,33 @@ static constexpr uint32_t IDESC_32_KM = make_idesc(128, 32, 0, 1);
 struct TcCtx {
     unsigned char* sm;     // 1024-aligned shared base
     uint32_t sm_addr;      // its shared-space address
-    uint64_t* bar;
+    uint32_t sm16;         // sm_addr >> 4: the base every operand descriptor's low word is an offset from (tc05::make_desc2)
+    uint64_t* bar;         // completion of the per-tile GEMM chain (issued by warp 0)
+    uint64_t* bar_wg;      // completion of a tile's weight-gradient GEMMs (issued by warps 1 .. n_wg, one arrival each)
     uint32_t tmem;         // TMEM base (lane 0, column 0 of the allocation)
-    uint32_t phase;        // mbarrier parity of the next wait
+    uint32_t phase;        // mbarrier parity of the next wait on bar
+    uint32_t phase_wg;     // ... on bar_wg
     uint32_t tid, lane, warp;
 };
 
-__device__ __forceinline__ void tc_setup(TcCtx& c, unsigned char* raw, uint32_t tmem_cols) {
+__device__ __forceinline__ void tc_setup(TcCtx& c, unsigned char* raw, uint32_t tmem_cols, uint32_t n_wg_issuers = 1) {
     c.tid = threadIdx.x; c.lane = c.tid & 31; c.warp = c.tid >> 5;
     const uint32_t raw_addr = smem_u32(raw);
     const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
     c.sm = raw + pad;
     c.sm_addr = raw_addr + pad;
+    c.sm16 = c.sm_addr >> 4;
     c.bar = reinterpret_cast<uint64_t*>(c.sm + SM_BAR);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c.sm + SM_BAR + 8);
-    if (c.tid == 0) { mbar_init(c.bar, 1); mbar_fence_init(); }
+    c.bar_wg = reinterpret_cast<uint64_t*>(c.sm + SM_BAR + 8);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c.sm + SM_BAR + 16);
+    if (c.tid == 0) { mbar_init(c.bar, 1); mbar_init(c.bar_wg, n_wg_issuers); mbar_fence_init(); }
     if (c.warp == 0) { __syncwarp(); tmem_alloc(tmem_slot, tmem_cols); }
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     c.tmem = *tmem_slot;
     c.phase = 0;
+    c.phase_wg = 0;
 }
 
 __device__ __forceinline__ void tc_teardown(TcCtx& c, uint32_t tmem_cols) {
@@ -181,29 +187,39 @@ __device__ __forceinline__ void tc_stage_enc(const TcCtx& c, const __half* __res
         fence_after_sync();             \
     } while (0)
 
+#define TC_WAIT_WG(c)                         \
+    do {                                      \
+        __syncwarp();                         \
+        mbar_wait((c).bar_wg, (c).phase_wg);  \
+        (c).phase_wg ^= 1u;                   \
+        fence_after_sync();                   \
+    } while (0)
+
 // K-major GEMM into TMEM column `col`: A tile at a_off (row pitch 64 B -> SW64, 128 B -> SW128), nk steps of K = 16
-__device__ __forceinline__ void tc_mma_sw(const TcCtx& c, uint32_t col, uint32_t a_off, uint32_t b_off, bool sw128, uint32_t nk, uint32_t idesc) {
+template <uint32_t nk>
+__device__ __forceinline__ void tc_mma_sw(const TcCtx& c, uint32_t col, uint32_t a_off, uint32_t b_off, bool sw128, uint32_t idesc) {
     const uint32_t sbo = sw128 ? 1024u : 512u;
     const uint64_t swz = sw128 ? SWZ_128B : SWZ_64B;
+#pragma unroll
     for (uint32_t k = 0; k < nk; ++k)
-        mma_f16_ss(c.tmem + col, make_desc(c.sm_addr + a_off + k * 32, 16, sbo, swz), make_desc(c.sm_addr + b_off + k * 32, 16, sbo, swz), idesc, k);
+        mma_f16_ss(c.tmem + col, make_desc2(c.sm16, a_off + k * 32, 16, sbo, swz), make_desc2(c.sm16, b_off + k * 32, 16, sbo, swz), idesc, k);
 }
 // layer in: D = enc . W_in^T
 __device__ __forceinline__ void tc_issue_layer_in(const TcCtx& c) {
     fence_after_sync();
-    tc_mma_sw(c, TC_COL_D, SM_ENC, SM_WIN, false, 2, IDESC_64_KK);
+    tc_mma_sw<2>(c, TC_COL_D, SM_ENC, SM_WIN, false, IDESC_64_KK);
     commit(c.bar);
 }
 // hidden layer (NH == 2): D = H1 . W_h^T
 __device__ __forceinline__ void tc_issue_layer_hidden(const TcCtx& c) {
     fence_after_sync();
-    tc_mma_sw(c, TC_COL_D, SM_H1, SM_WH, true, 4, IDESC_64_KK);
+    tc_mma_sw<4>(c, TC_COL_D, SM_H1, SM_WH, true, IDESC_64_KK);
     commit(c.bar);
 }
 // layer out: O = hid . W_out^T
 __device__ __forceinline__ void tc_issue_layer_out(const TcCtx& c) {
     fence_after_sync();
-    tc_mma_sw(c, TC_COL_O, SM_HID, SM_WOUT, true, 4, IDESC_16_KK);
+    tc_mma_sw<4>(c, TC_COL_O, SM_HID, SM_WOUT, true, IDESC_16_KK);
     commit(c.bar);
 }
 
@@ -306,7 +322,7 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
     TC_STAMP(0);
     TC_CTA_MARK(0);
     TcCtx c;
-    tc_setup(c, smem_raw, TC_TMEM_COLS(NH));
+    tc_setup(c, smem_raw, TC_TMEM_COLS(NH), NH == 1 ? 2u : 3u);
     TC_STAMP(1);
     tc_load_weights<NH>(c, b.params);
     TC_STAMP(2);
@@ -344,6 +360,7 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
         // ---- stage encodings, MMA1
         const uint32_t sb = 4 + (tiles_done & 1) * 16;
         TC_STAMP(sb + 0);
+        if (tiles_done) TC_WAIT_WG(c);      // the previous tile's weight-gradient GEMMs have read enc / hid / dhid / dout
         tc_store_enc(c, enc_regs);
         TC_PUBLISH_AND_SYNC();
         TC_STAMP(sb + 1);
@@ -416,8 +433,8 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
         if (c.tid == 0) {
             fence_after_sync();
             // B[k = output o][n = neuron j] = W_out[o][j]: the forward tile (16 rows of 128 B) read MN-major
-            mma_f16_ss(c.tmem + TC_COL_D, make_desc(c.sm_addr + SM_DOUT, 128, 256, SWZ_NONE),
-                       make_desc(c.sm_addr + SM_WOUT, 16, 1024, SWZ_128B), IDESC_64_KM, 0);
+            mma_f16_ss(c.tmem + TC_COL_D, make_desc2(c.sm16, SM_DOUT, 128, 256, SWZ_NONE),
+                       make_desc2(c.sm16, SM_WOUT, 16, 1024, SWZ_128B), IDESC_64_KM, 0);
             commit(c.bar);
         }
         TC_STAMP(sb + 9);
@@ -432,38 +449,54 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
                 // B[k = neuron j][n = input i] = W_h[j][i]: the forward tile read MN-major, 16 rows (2 KB) per MMA
 #pragma unroll
                 for (uint32_t k = 0; k < 4; ++k)
-                    mma_f16_ss(c.tmem + TC_COL_D, make_desc(c.sm_addr + SM_DHID + k * 32, 16, 1024, SWZ_128B),
-                               make_desc(c.sm_addr + SM_WH + k * 2048, 16, 1024, SWZ_128B), IDESC_64_KM, k);
+                    mma_f16_ss(c.tmem + TC_COL_D, make_desc2(c.sm16, SM_DHID + k * 32, 16, 1024, SWZ_128B),
+                               make_desc2(c.sm16, SM_WH + k * 2048, 16, 1024, SWZ_128B), IDESC_64_KM, k);
                 commit(c.bar);
             }
             TC_WAIT(c);
             tc_epilogue_dhidden(c, SM_DH1, SM_H1);
         }
-        // ---- MMA4 (dL/dencoding) + MMA5/6 (weight gradients, accumulated in TMEM across tiles)
+        // ---- MMA4 (dL/dencoding) + MMA5/6 (weight gradients, accumulated in TMEM across tiles).  Warp 0 issues the four MMAs the
+        // tile's last epilogue waits for; warps 1 .. 3 issue the weight-gradient GEMMs, one accumulator each, onto their own
+        // barrier: nothing reads G1 / G2 / G3 before the end of the kernel, so they run under the dL/dencoding epilogue and are
+        // only waited for before the next tile overwrites the operand tiles (top of the loop).  One thread issuing all 20 MMAs
+        // was the longest serial phase of a tile (1750 of 8500 cycles, profiles/r1z_mlp_phase_times.txt).
         TC_PUBLISH_AND_SYNC();
-        if (c.tid == 0) {
-            fence_after_sync();
-            // B[k = neuron j][n = input k] = W_in[j][k]: the forward tile (64 rows of 64 B, SW64) read MN-major
-#pragma unroll
-            for (uint32_t k = 0; k < 4; ++k)
-                mma_f16_ss(c.tmem + TC_COL_E, make_desc(c.sm_addr + (NH == 2 ? SM_DH1 : SM_DHID) + k * 32, 16, 1024, SWZ_128B),
-                           make_desc(c.sm_addr + SM_WIN + k * 1024, 16, 512, SWZ_64B), IDESC_32_KM, k);
+        {
             const uint32_t acc0 = tiles_done ? 1u : 0u;
+            if (c.tid == 0) {
+                fence_after_sync();
+                // B[k = neuron j][n = input k] = W_in[j][k]: the forward tile (64 rows of 64 B, SW64) read MN-major
 #pragma unroll
-            for (uint32_t kk = 0; kk < 8; ++kk) {   // 16 points per MMA
-                // [last hidden | its gradient]^T: rows 0-63 x dout = dW_out^T; (NH == 2) rows 64-127 x H1 = dW_h
-                const uint64_t a = make_desc(c.sm_addr + SM_HID + kk * 2048, 16384, 1024, SWZ_128B);
-                mma_f16_ss(c.tmem + TC_COL_G1, a, make_desc(c.sm_addr + SM_DOUT + kk * 512, 256, 128, SWZ_NONE), IDESC_16_MM, acc0 | kk);
-                const uint64_t enc_b = make_desc(c.sm_addr + SM_ENC + kk * 1024, 16, 512, SWZ_64B);
-                if (NH == 1) {
-                    mma_f16_ss(c.tmem + TC_COL_G2, a, enc_b, IDESC_32_MM, acc0 | kk);
-                } else {
-                    mma_f16_ss(c.tmem + TC_COL_H2, a, make_desc(c.sm_addr + SM_H1 + kk * 2048, 16, 1024, SWZ_128B), IDESC_64_MM, acc0 | kk);
-                    // [H1 | dH1]^T x enc: rows 64-127 = dW_in
-                    mma_f16_ss(c.tmem + TC_COL_G2, make_desc(c.sm_addr + SM_H1 + kk * 2048, 16384, 1024, SWZ_128B), enc_b, IDESC_32_MM, acc0 | kk);
-                }
+                for (uint32_t k = 0; k < 4; ++k)
+                    mma_f16_ss(c.tmem + TC_COL_E, make_desc2(c.sm16, (NH == 2 ? SM_DH1 : SM_DHID) + k * 32, 16, 1024, SWZ_128B),
+                               make_desc2(c.sm16, SM_WIN + k * 1024, 16, 512, SWZ_64B), IDESC_32_KM, k);
+                commit(c.bar);
+            } else if (c.tid == 32) {
+                fence_after_sync();
+                // [last hidden | its gradient]^T: rows 0-63 x dout = dW_out^T     (16 points per MMA)
+#pragma unroll
+                for (uint32_t kk = 0; kk < 8; ++kk)
+                    mma_f16_ss(c.tmem + TC_COL_G1, make_desc2(c.sm16, SM_HID + kk * 2048, 16384, 1024, SWZ_128B),
+                               make_desc2(c.sm16, SM_DOUT + kk * 512, 256, 128, SWZ_NONE), IDESC_16_MM, acc0 | kk);
+                commit(c.bar_wg);
+            } else if (c.tid == 64) {
+                fence_after_sync();
+                // NH == 1: [hid | dhid]^T x enc, NH == 2: [H1 | dH1]^T x enc: rows 64-127 = dW_in
+#pragma unroll
+                for (uint32_t kk = 0; kk < 8; ++kk)
+                    mma_f16_ss(c.tmem + TC_COL_G2, make_desc2(c.sm16, (NH == 2 ? SM_H1 : SM_HID) + kk * 2048, 16384, 1024, SWZ_128B),
+                               make_desc2(c.sm16, SM_ENC + kk * 1024, 16, 512, SWZ_64B), IDESC_32_MM, acc0 | kk);
+                commit(c.bar_wg);
+            } else if (NH == 2 && c.tid == 96) {
+                fence_after_sync();
+                // [H2 | dH2]^T x H1: rows 64-127 = dW_h
+#pragma unroll
+                for (uint32_t kk = 0; kk < 8; ++kk)
+                    mma_f16_ss(c.tmem + TC_COL_H2, make_desc2(c.sm16, SM_HID + kk * 2048, 16384, 1024, SWZ_128B),
+                               make_desc2(c.sm16, SM_H1 + kk * 2048, 16, 1024, SWZ_128B), IDESC_64_MM, acc0 | kk);
+                commit(c.bar_wg);
             }
-            commit(c.bar);
         }
         TC_STAMP(sb + 12);
         TC_WAIT(c);
@@ -504,8 +537,9 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
             }
         }
         TC_STAMP(sb + 14);
-        // the next tile overwrites enc / hid / dout: every MMA that reads them has completed (the wait above)
+        // the next tile overwrites enc / hid / dout once the weight-gradient GEMMs that read them have completed (top of the loop)
     }
+    if (tiles_done) TC_WAIT_WG(c);
     TC_STAMP(40);
 
     // ---- weight gradients: TMEM -> this CTA's partial row (W_in [64][32] | (W_h [64][64]) | W_out [16][64])

@@ -240,6 +240,8 @@ struct mon_dataset {
     int H = 0, W = 0;
     uint32_t max_frames = 0;
     int use_depth = 0;
+    uint32_t depth_bytes = 4;      // bytes per depth sample on the device and in the caller's blocks: 4 (f32 metres) or 2 (raw u16, mon_dataset_set_depth_u16)
+    float depth_factor = 0.0f;     // u16 mode: metres per count (DepthMapFactor)
     uint32_t n_frames = 0;
     MonFrame* d_frames = nullptr;
     std::vector<MonFrame> h_frames;
@@ -457,7 +459,7 @@ int mon_dataset_create(int gpu, float fx, float fy, float cx, float cy, int H, i
     mon_dataset* ds = new mon_dataset();
     ds->gpu = gpu; ds->K[0] = fx; ds->K[1] = fy; ds->K[2] = cx; ds->K[3] = cy;
     ds->H = H; ds->W = W; ds->max_frames = max_frames; ds->use_depth = use_depth;
-    ds->h_frames.assign(max_frames, MonFrame{nullptr, nullptr, nullptr, {0}, 0u, 0u});
+    ds->h_frames.assign(max_frames, MonFrame{nullptr, nullptr, nullptr, {0}, 0u, 0.0f});
     ds->slabs.assign((max_frames + MON_FRAMES_PER_SLAB - 1) / MON_FRAMES_PER_SLAB, nullptr);
     const size_t px = (size_t)H * W;
     cudaError_t e;
@@ -487,7 +489,7 @@ struct SlabLayout { size_t s_rgb, s_inst, s_depth; };       // per-frame strides
 static SlabLayout slab_layout(const mon_dataset* ds) {
     const size_t px = (size_t)ds->H * ds->W;
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    return {up(px * 3), up(px), ds->use_depth ? up(px * 4) : 0};
+    return {up(px * 3), up(px), ds->use_depth ? up(px * ds->depth_bytes) : 0};
 }
 static int ensure_frame_storage(mon_dataset* ds, uint32_t frame_id) {
     MonFrame& f = ds->h_frames[frame_id];
@@ -509,8 +511,27 @@ static cudaError_t upload_frame_rows(mon_dataset* ds, uint32_t first, uint32_t n
     return cudaMemcpyAsync(ds->d_frames + first, ds->h_frames_pinned + first, sizeof(MonFrame) * n, cudaMemcpyHostToDevice, ds->stream);
 }
 
-int mon_dataset_add_frame(mon_dataset* ds, uint32_t frame_id, const uint8_t* rgb, int is_bgr,
-                          const uint8_t* instance, const float* depth, const float pose[16]) {
+// the depth plane of the public entries: f32 metres, or raw u16 samples after mon_dataset_set_depth_u16
+static int check_depth_format(const mon_dataset* ds, uint32_t bytes_per_sample) {
+    if (ds && ds->use_depth && ds->depth_bytes != bytes_per_sample)
+        return fail(MON_ERR_ARG, bytes_per_sample == 4 ? "the dataset takes raw 16-bit depth (mon_dataset_set_depth_u16): use the _d16 entry"
+                                                       : "the dataset takes f32 depth: call mon_dataset_set_depth_u16 before the first frame");
+    return MON_OK;
+}
+
+int mon_dataset_set_depth_u16(mon_dataset* ds, float depth_factor) {
+    if (!ds) return fail(MON_ERR_ARG, "ds is NULL");
+    if (!(depth_factor > 0.0f)) return fail(MON_ERR_ARG, "depth_factor must be positive");
+    std::lock_guard<std::mutex> lock(ds->mu);
+    if (!ds->use_depth) return fail(MON_ERR_ARG, "dataset was created without depth");
+    for (const uint8_t* sl : ds->slabs) if (sl) return fail(MON_ERR_STATE, "the depth format is fixed once a keyframe has been added");
+    ds->depth_bytes = 2;
+    ds->depth_factor = depth_factor;
+    return MON_OK;
+}
+
+static int add_frame_impl(mon_dataset* ds, uint32_t frame_id, const uint8_t* rgb, int is_bgr,
+                          const uint8_t* instance, const void* depth, const float pose[16]) {
     if (!ds || !rgb || !instance || !pose) return fail(MON_ERR_ARG, "NULL argument");
     if (frame_id >= ds->max_frames) return fail(MON_ERR_ARG, "frame_id %u >= max_frames %u", frame_id, ds->max_frames);
     if (ds->use_depth && !depth) return fail(MON_ERR_ARG, "dataset was created with use_depth but depth is NULL");
@@ -531,12 +552,13 @@ int mon_dataset_add_frame(mon_dataset* ds, uint32_t frame_id, const uint8_t* rgb
     MonFrame& f = ds->h_frames[frame_id];
     memcpy(f.pose, pose, sizeof(float) * 16);
     f.bgr = is_bgr ? 1u : 0u;
+    f.depth_factor = ds->depth_bytes == 2 ? ds->depth_factor : 0.0f;
     if (host_pinned(rgb) && host_pinned(instance) && (!ds->use_depth || host_pinned(depth))) {
         // page-locked caller buffers: DMA straight out of them, no staging copy and no host synchronisation.  The
         // buffers must stay valid until mon_dataset_sync() or the next blocking call on an object of this dataset.
         CK(cudaMemcpyAsync(const_cast<uint8_t*>(f.rgb), rgb, px * 3, cudaMemcpyHostToDevice, ds->stream));
         CK(cudaMemcpyAsync(const_cast<uint8_t*>(f.instance), instance, px, cudaMemcpyHostToDevice, ds->stream));
-        if (ds->use_depth) CK(cudaMemcpyAsync(const_cast<float*>(f.depth), depth, px * 4, cudaMemcpyHostToDevice, ds->stream));
+        if (ds->use_depth) CK(cudaMemcpyAsync(const_cast<float*>(f.depth), depth, px * ds->depth_bytes, cudaMemcpyHostToDevice, ds->stream));
         CK(upload_frame_rows(ds, frame_id, 1));
         CK(cudaEventRecord(ds->ev_uploaded, ds->stream));
     } else {
@@ -551,11 +573,11 @@ int mon_dataset_add_frame(mon_dataset* ds, uint32_t frame_id, const uint8_t* rgb
         float* st_depth = reinterpret_cast<float*>(ds->staging[half] + px * 4);
         memcpy(st_rgb, rgb, px * 3);
         memcpy(st_inst, instance, px);
-        if (ds->use_depth) memcpy(st_depth, depth, px * 4);
+        if (ds->use_depth) memcpy(st_depth, depth, px * ds->depth_bytes);
         stamp();
         CK(cudaMemcpyAsync(const_cast<uint8_t*>(f.rgb), st_rgb, px * 3, cudaMemcpyHostToDevice, ds->stream));
         CK(cudaMemcpyAsync(const_cast<uint8_t*>(f.instance), st_inst, px, cudaMemcpyHostToDevice, ds->stream));
-        if (ds->use_depth) CK(cudaMemcpyAsync(const_cast<float*>(f.depth), st_depth, px * 4, cudaMemcpyHostToDevice, ds->stream));
+        if (ds->use_depth) CK(cudaMemcpyAsync(const_cast<float*>(f.depth), st_depth, px * ds->depth_bytes, cudaMemcpyHostToDevice, ds->stream));
         CK(upload_frame_rows(ds, frame_id, 1));
         CK(cudaEventRecord(ds->ev_staged[half], ds->stream));
         CK(cudaEventRecord(ds->ev_uploaded, ds->stream));
@@ -575,8 +597,19 @@ int mon_dataset_add_frame(mon_dataset* ds, uint32_t frame_id, const uint8_t* rgb
     return MON_OK;
 }
 
-int mon_dataset_add_frame_device(mon_dataset* ds, uint32_t frame_id, const uint8_t* d_rgb, int is_bgr, const uint8_t* d_instance,
-                                 const float* d_depth, const float pose[16]) {
+int mon_dataset_add_frame(mon_dataset* ds, uint32_t frame_id, const uint8_t* rgb, int is_bgr,
+                          const uint8_t* instance, const float* depth, const float pose[16]) {
+    const int rc = check_depth_format(ds, 4);
+    return rc != MON_OK ? rc : add_frame_impl(ds, frame_id, rgb, is_bgr, instance, depth, pose);
+}
+int mon_dataset_add_frame_d16(mon_dataset* ds, uint32_t frame_id, const uint8_t* rgb, int is_bgr,
+                              const uint8_t* instance, const uint16_t* depth16, const float pose[16]) {
+    const int rc = check_depth_format(ds, 2);
+    return rc != MON_OK ? rc : add_frame_impl(ds, frame_id, rgb, is_bgr, instance, depth16, pose);
+}
+
+static int add_frame_device_impl(mon_dataset* ds, uint32_t frame_id, const uint8_t* d_rgb, int is_bgr, const uint8_t* d_instance,
+                                 const void* d_depth, const float pose[16]) {
     if (!ds || !d_rgb || !d_instance || !pose) return fail(MON_ERR_ARG, "NULL argument");
     if (frame_id >= ds->max_frames) return fail(MON_ERR_ARG, "frame_id %u >= max_frames %u", frame_id, ds->max_frames);
     if (ds->use_depth && !d_depth) return fail(MON_ERR_ARG, "dataset was created with use_depth but depth is NULL");
@@ -588,26 +621,38 @@ int mon_dataset_add_frame_device(mon_dataset* ds, uint32_t frame_id, const uint8
     MonFrame& f = ds->h_frames[frame_id];
     memcpy(f.pose, pose, sizeof(float) * 16);
     f.bgr = is_bgr ? 1u : 0u;
+    f.depth_factor = ds->depth_bytes == 2 ? ds->depth_factor : 0.0f;
     CK(cudaMemcpyAsync(const_cast<uint8_t*>(f.rgb), d_rgb, px * 3, cudaMemcpyDeviceToDevice, ds->stream));
     CK(cudaMemcpyAsync(const_cast<uint8_t*>(f.instance), d_instance, px, cudaMemcpyDeviceToDevice, ds->stream));
-    if (ds->use_depth) CK(cudaMemcpyAsync(const_cast<float*>(f.depth), d_depth, px * 4, cudaMemcpyDeviceToDevice, ds->stream));
+    if (ds->use_depth) CK(cudaMemcpyAsync(const_cast<float*>(f.depth), d_depth, px * ds->depth_bytes, cudaMemcpyDeviceToDevice, ds->stream));
     CK(upload_frame_rows(ds, frame_id, 1));
     CK(cudaEventRecord(ds->ev_uploaded, ds->stream));
     ds->n_frames = std::max(ds->n_frames, frame_id + 1);
     return MON_OK;
 }
+int mon_dataset_add_frame_device(mon_dataset* ds, uint32_t frame_id, const uint8_t* d_rgb, int is_bgr, const uint8_t* d_instance,
+                                 const float* d_depth, const float pose[16]) {
+    const int rc = check_depth_format(ds, 4);
+    return rc != MON_OK ? rc : add_frame_device_impl(ds, frame_id, d_rgb, is_bgr, d_instance, d_depth, pose);
+}
+int mon_dataset_add_frame_device_d16(mon_dataset* ds, uint32_t frame_id, const uint8_t* d_rgb, int is_bgr, const uint8_t* d_instance,
+                                     const uint16_t* d_depth16, const float pose[16]) {
+    const int rc = check_depth_format(ds, 2);
+    return rc != MON_OK ? rc : add_frame_device_impl(ds, frame_id, d_rgb, is_bgr, d_instance, d_depth16, pose);
+}
 
-int mon_dataset_add_frames(mon_dataset* ds, uint32_t first_id, uint32_t n, const uint8_t* rgb, int is_bgr, const uint8_t* instance,
-                           const float* depth, const float* poses16, int on_device) {
+static int add_frames_impl(mon_dataset* ds, uint32_t first_id, uint32_t n, const uint8_t* rgb, int is_bgr, const uint8_t* instance,
+                           const void* depth_v, const float* poses16, int on_device) {
+    const uint8_t* depth = static_cast<const uint8_t*>(depth_v);
     if (!ds || !rgb || !instance || !poses16) return fail(MON_ERR_ARG, "NULL argument");
     if ((uint64_t)first_id + n > ds->max_frames) return fail(MON_ERR_ARG, "frames %u..%u exceed max_frames %u", first_id, first_id + n, ds->max_frames);
     if (ds->use_depth && !depth) return fail(MON_ERR_ARG, "dataset was created with use_depth but depth is NULL");
     if (n == 0) return MON_OK;
-    const size_t px = (size_t)ds->H * ds->W;
+    const size_t px = (size_t)ds->H * ds->W, dpx = px * ds->depth_bytes;
     if (!on_device && !(host_pinned(rgb) && host_pinned(instance) && (!ds->use_depth || host_pinned(depth)))) {
         // pageable blocks: frame by frame through the pinned staging area
         for (uint32_t i = 0; i < n; ++i) {
-            const int rc = mon_dataset_add_frame(ds, first_id + i, rgb + px * 3 * i, is_bgr, instance + px * i, depth ? depth + px * i : nullptr, poses16 + 16 * (size_t)i);
+            const int rc = add_frame_impl(ds, first_id + i, rgb + px * 3 * i, is_bgr, instance + px * i, depth ? depth + dpx * i : nullptr, poses16 + 16 * (size_t)i);
             if (rc != MON_OK) return rc;
         }
         return MON_OK;
@@ -620,6 +665,7 @@ int mon_dataset_add_frames(mon_dataset* ds, uint32_t first_id, uint32_t n, const
         MonFrame& f = ds->h_frames[first_id + i];
         memcpy(f.pose, poses16 + 16 * (size_t)i, sizeof(float) * 16);
         f.bgr = is_bgr ? 1u : 0u;
+        f.depth_factor = ds->depth_bytes == 2 ? ds->depth_factor : 0.0f;
     }
     const SlabLayout L = slab_layout(ds);
     const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
@@ -629,20 +675,31 @@ int mon_dataset_add_frames(mon_dataset* ds, uint32_t first_id, uint32_t n, const
         const uint32_t id = first_id + i;
         const uint32_t run = std::min<uint32_t>(n - i, MON_FRAMES_PER_SLAB - id % MON_FRAMES_PER_SLAB);
         const MonFrame& f0 = ds->h_frames[id];
-        const uint32_t r_rgb = L.s_rgb == px * 3 ? 1u : run, r_inst = L.s_inst == px ? 1u : run, r_depth = L.s_depth == px * 4 ? 1u : run;
+        const uint32_t r_rgb = L.s_rgb == px * 3 ? 1u : run, r_inst = L.s_inst == px ? 1u : run, r_depth = L.s_depth == dpx ? 1u : run;
         for (uint32_t k = 0; k < r_rgb; ++k)
             CK(cudaMemcpyAsync(const_cast<uint8_t*>(f0.rgb) + L.s_rgb * k, rgb + px * 3 * (i + k), px * 3 * (run / r_rgb), kind, ds->stream));
         for (uint32_t k = 0; k < r_inst; ++k)
             CK(cudaMemcpyAsync(const_cast<uint8_t*>(f0.instance) + L.s_inst * k, instance + px * (i + k), px * (run / r_inst), kind, ds->stream));
         if (ds->use_depth)
             for (uint32_t k = 0; k < r_depth; ++k)
-                CK(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(const_cast<float*>(f0.depth)) + L.s_depth * k, depth + px * (i + k), px * 4 * (run / r_depth), kind, ds->stream));
+                CK(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(const_cast<float*>(f0.depth)) + L.s_depth * k, depth + dpx * (i + k), dpx * (run / r_depth), kind, ds->stream));
         i += run;
     }
     CK(upload_frame_rows(ds, first_id, n));
     CK(cudaEventRecord(ds->ev_uploaded, ds->stream));
     ds->n_frames = std::max(ds->n_frames, first_id + n);
     return MON_OK;
+}
+
+int mon_dataset_add_frames(mon_dataset* ds, uint32_t first_id, uint32_t n, const uint8_t* rgb, int is_bgr, const uint8_t* instance,
+                           const float* depth, const float* poses16, int on_device) {
+    const int rc = check_depth_format(ds, 4);
+    return rc != MON_OK ? rc : add_frames_impl(ds, first_id, n, rgb, is_bgr, instance, depth, poses16, on_device);
+}
+int mon_dataset_add_frames_d16(mon_dataset* ds, uint32_t first_id, uint32_t n, const uint8_t* rgb, int is_bgr, const uint8_t* instance,
+                               const uint16_t* depth16, const float* poses16, int on_device) {
+    const int rc = check_depth_format(ds, 2);
+    return rc != MON_OK ? rc : add_frames_impl(ds, first_id, n, rgb, is_bgr, instance, depth16, poses16, on_device);
 }
 
 int mon_dataset_sync(mon_dataset* ds) {
@@ -691,9 +748,10 @@ static int copy_frames_from_peer(mon_dataset* dst, const mon_dataset* src, uint3
         if (rc != MON_OK) return rc;
         MonFrame& f = dst->h_frames[i];
         f.bgr = s.bgr;
+        f.depth_factor = s.depth_factor;
         CK(cudaMemcpyPeerAsync(const_cast<uint8_t*>(f.rgb), dst->gpu, s.rgb, src->gpu, px * 3, dst->stream));
         CK(cudaMemcpyPeerAsync(const_cast<uint8_t*>(f.instance), dst->gpu, s.instance, src->gpu, px, dst->stream));
-        if (dst->use_depth) CK(cudaMemcpyPeerAsync(const_cast<float*>(f.depth), dst->gpu, s.depth, src->gpu, px * 4, dst->stream));
+        if (dst->use_depth) CK(cudaMemcpyPeerAsync(const_cast<float*>(f.depth), dst->gpu, s.depth, src->gpu, px * dst->depth_bytes, dst->stream));
         memcpy(f.pose, s.pose, sizeof(float) * 16);
         CK(upload_frame_rows(dst, i, 1));
         dst->n_frames = std::max(dst->n_frames, i + 1);
@@ -705,7 +763,8 @@ static int copy_frames_from_peer(mon_dataset* dst, const mon_dataset* src, uint3
 static int peer_compatible(const mon_dataset* dst, const mon_dataset* src) {
     if (!dst || !src) return fail(MON_ERR_ARG, "NULL argument");
     if (dst == src) return fail(MON_ERR_ARG, "source and destination are the same dataset");
-    if (dst->H != src->H || dst->W != src->W || dst->use_depth != src->use_depth) return fail(MON_ERR_ARG, "datasets are not shape-compatible");
+    if (dst->H != src->H || dst->W != src->W || dst->use_depth != src->use_depth || dst->depth_bytes != src->depth_bytes)
+        return fail(MON_ERR_ARG, "datasets are not shape-compatible");
     return MON_OK;
 }
 

@@ -22,11 +22,13 @@ struct MonRay { float o[3], d[3], d_norm, tmin, tmax; };
 struct MonFrame {
     const uint8_t* rgb;       // H*W*3, RGB
     const uint8_t* instance;  // H*W
-    const float* depth;       // H*W or nullptr
+    const float* depth;       // H*W f32 — or, if depth_factor != 0, H*W raw 16-bit samples — or nullptr
     float pose[16];           // camera-to-world, column-major
     uint32_t bgr;             // 1: the pixels are stored B, G, R as the SLAM frontend hands them over (cv::imread order);
                               // the batch kernel swaps on read instead of the host swizzling every keyframe
-    uint32_t pad_;
+    float depth_factor;       // != 0: the depth plane holds the raw u16 samples of the depth image and the metric value is
+                              // (float)u16 * depth_factor, converted on read — the float the reference stores after
+                              // depthImg.convertTo(CV_32FC1, mfDepthScale) (nerf_data.cu:182); 0: the plane holds f32 metres
 };
 
 // geometry of the multiresolution table, precomputed on the host (grid.h:195-204,964-997)

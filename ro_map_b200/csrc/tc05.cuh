@@ -35,6 +35,18 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
     return d;
 }
 
+// The same descriptor as two 32-bit halves.  The high word (SBO, version, swizzle) is a compile-time constant per operand; the low
+// word is `sm16 + constant` with sm16 = (1024-aligned shared base) >> 4 computed once per kernel: an operand descriptor costs the
+// issuing thread ONE uniform add instead of the shift / mask / or chain of make_desc (20 MMAs per tile were 1750 cycles of issue,
+// profiles/r1z_mlp_phase_times.txt).  Shared addresses are below 256 KB, so base + offset cannot carry out of the 14-bit field.
+struct Desc2 { uint32_t lo, hi; };
+__device__ __forceinline__ Desc2 make_desc2(uint32_t sm16, uint32_t off_bytes, uint32_t lbo_bytes, uint32_t sbo_bytes, uint64_t swizzle) {
+    Desc2 d;
+    d.lo = sm16 + ((off_bytes >> 4) | ((lbo_bytes >> 4) << 16));
+    d.hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | ((uint32_t)swizzle << 29);
+    return d;
+}
+
 // ---- instruction descriptor (32 bit): fp16 x fp16 -> fp32, dense
 __host__ __device__ constexpr uint32_t make_idesc(uint32_t M, uint32_t N, uint32_t a_mn_major, uint32_t b_mn_major) {
     return (1u << 4)                 // c_format = F32
@@ -52,6 +64,31 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uin
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
         "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
         : "memory");
+}
+
+__device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, Desc2 a, Desc2 b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, {%7, %7, %7, %7}, p;\n\t"
+        "}\n" ::"r"(tmem_d), "r"(a.lo), "r"(a.hi), "r"(b.lo), "r"(b.hi), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+
+// one lane of a converged warp (the tcgen05 issue / commit instructions are single-thread)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}\n" : "=r"(pred));
+    return pred != 0;
 }
 
 // all previously issued MMAs of this thread arrive on the mbarrier when they complete

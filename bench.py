@@ -40,7 +40,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 S = 32
-FRAMES = 30        # 30 keyframes x (1.92 MB rgb + 0.64 MB mask + 2.56 MB depth) = 154 MB > 126 MB L2
+FRAMES = 30        # 30 keyframes x (1.92 MB rgb + 0.64 MB mask + 1.28 MB 16-bit depth) = 115 MB; + ~50 MB of per-object state > 126 MB L2
 BYTES_ENC_PER_POINT = 512       # 16 levels x 8 corners x 2 features x 2 B (gather forward, RMW backward)
 BYTES_OPT_FLOOR_PER_PARAM = 10  # untouched parameter (gradient read + zero, EMA read/read/write)
 FLOPS_MLP_TRAIN_PER_POINT = {1: 18432, 2: 43008}
@@ -132,9 +132,20 @@ def load_traffic():
         return {}
 
 
+DEPTH_FACTOR = 1.0 / 5000.0     # DepthMapFactor of the on-disk schema (synthetic.write_sequence; TUM-style 16-bit depth PNGs)
+
+
 def make_scene(n_objects: int, n_frames: int):
+    """The synthetic sequence as the reference's DataToGPU meets it (nerf_data.cu:171-186): depth is a 16-bit image (`depth16`, what
+    cv::imread(IMREAD_UNCHANGED) returns) and the float plane both arms train on is its convertTo(CV_32FC1, DepthMapFactor):
+    (float)u16 * factor.  The reference arm and the CPU port get that float plane; our arm uploads the 16-bit samples and converts
+    the pixels it picks in-kernel (mon_dataset_set_depth_u16) — the same floats, bit for bit."""
     from ro_map_b200 import synthetic as syn
-    return syn.make_sequence(n_frames=n_frames, n_objects=n_objects, seed=1337)
+    seq = syn.make_sequence(n_frames=n_frames, n_objects=n_objects, seed=1337)
+    f = np.float32(DEPTH_FACTOR)
+    seq.depth16 = [np.clip(np.rint(d / DEPTH_FACTOR), 0, 65535).astype(np.uint16) for d in seq.depth]
+    seq.depth = [d16.astype(np.float32) * f for d16 in seq.depth16]
+    return seq
 
 
 def render_box_400(seq, obj):
@@ -172,7 +183,7 @@ def workload_config(args, n_objects, world):
             "iterations_timed": f"{args.warmup} .. {args.warmup + args.steps} of a fresh object",
             "mode": ("reference sampling: every stratified sample is evaluated (the parity configuration)" if not getattr(args, "occupancy", 0) else
                      f"OPT-IN occupancy grid {args.occupancy}^3 + warp-ballot sample compaction (changes results; not the parity configuration)"),
-            "l2_policy": "keyframe set 154 MB > 126 MB L2; per-object state (~50 MB) is L2-resident between iterations by design, as in production back-to-back iterations"}
+            "l2_policy": "inputs larger than L2: keyframe set 115 MB (u8 RGB + u8 instance + u16 depth; 4096 random pixels of it are read per iteration) + ~50 MB of per-object state > 126 MB L2; the per-object state is L2-resident between iterations by design, as in production back-to-back iterations"}
 
 
 # ----------------------------------------------------------------------------- reference arm
@@ -348,8 +359,14 @@ def run_ours(args, rank, world, local_rank):
     # keyframes in PINNED host memory (the C ABI then DMAs straight out of them, asynchronously): one block per plane kind
     h_rgb = torch.from_numpy(np.ascontiguousarray(np.stack(seq.rgb))).pin_memory()
     h_inst = torch.from_numpy(np.ascontiguousarray(np.stack(seq.instance))).pin_memory()
-    h_dep = torch.from_numpy(np.ascontiguousarray(np.stack(seq.depth))).pin_memory()
-    rgb_np, inst_np, dep_np = h_rgb.numpy(), h_inst.numpy(), h_dep.numpy()
+    # depth: the 16-bit samples of the depth image (int16 view of the same bits: torch / NCCL have no uint16 collectives)
+    h_dep = torch.from_numpy(np.ascontiguousarray(np.stack(seq.depth16)).view(np.int16)).pin_memory()
+    rgb_np, inst_np, dep_np = h_rgb.numpy(), h_inst.numpy(), h_dep.numpy().view(np.uint16)
+
+    def new_dataset():
+        d = core.Dataset(gpu, *seq.K, seq.H, seq.W, n_frames, True)
+        d.set_depth_u16(DEPTH_FACTOR)            # u8 RGB + u8 instance + u16 depth = 6 B / pixel (the reference uploads 17: f32 RGB, u8, f32)
+        return d
 
     def upload(ds):
         # the whole keyframe set in one call (DataToGPU): page-locked blocks, three asynchronous copies
@@ -373,7 +390,7 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     # ---------------- device-timed: inputs resident.  Objects of one rank train concurrently on per-object streams.
-    ds = core.Dataset(gpu, *seq.K, seq.H, seq.W, n_frames, True)
+    ds = new_dataset()
     upload(ds)
     nerfs = make_objects(ds)
     for n in nerfs:
@@ -418,7 +435,7 @@ def run_ours(args, rank, world, local_rank):
         n.close()
 
     # ---------------- end to end from host buffers through the C ABI
-    ds2 = core.Dataset(gpu, *seq.K, seq.H, seq.W, n_frames, True)
+    ds2 = new_dataset()
     upload(ds2)                                  # a throw-away frame set: storage allocation is not billed to the timed region
     nerfs2 = make_objects(ds2)
     for n in nerfs2:
@@ -456,7 +473,7 @@ def run_ours(args, rank, world, local_rank):
     if distributed:
         dist.barrier()
     e2e_s = partition.reduce_max(e2e_s, "cuda")
-    h2d = max(0, f1 - f0) * (px * 3 + px + px * 4) + n_frames * 96 + sum(len(seq.objects[k].boxes) for k in mine) * 20
+    h2d = max(0, f1 - f0) * (px * 3 + px + px * 2) + n_frames * 96 + sum(len(seq.objects[k].boxes) for k in mine) * 20
     h2d = partition.reduce_sum(float(h2d), "cuda")
     for n in nerfs2:
         n.close()

@@ -57,6 +57,10 @@ SIGNATURES = {
     "mon_dataset_add_frame": (C.c_int, [_vp, C.c_uint32, _vp, C.c_int, _vp, _vp, _f32p]),
     "mon_dataset_add_frame_device": (C.c_int, [_vp, C.c_uint32, _vp, C.c_int, _vp, _vp, _f32p]),
     "mon_dataset_add_frames": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, C.c_int, _vp, _vp, _f32p, C.c_int]),
+    "mon_dataset_set_depth_u16": (C.c_int, [_vp, C.c_float]),
+    "mon_dataset_add_frame_d16": (C.c_int, [_vp, C.c_uint32, _vp, C.c_int, _vp, _vp, _f32p]),
+    "mon_dataset_add_frame_device_d16": (C.c_int, [_vp, C.c_uint32, _vp, C.c_int, _vp, _vp, _f32p]),
+    "mon_dataset_add_frames_d16": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, C.c_int, _vp, _vp, _f32p, C.c_int]),
     "mon_dataset_sync": (C.c_int, [_vp]),
     "mon_dataset_update_poses": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _f32p]),
     "mon_dataset_frame_count": (C.c_int, [_vp, _P(C.c_uint32)]),

@@ -91,25 +91,44 @@ class Dataset:
         self.use_depth = bool(use_depth)
         self.gpu = gpu
         check(self._lib.mon_dataset_create(gpu, fx, fy, cx, cy, H, W, max_frames, int(use_depth), C.byref(self._h)))
+        self.depth_u16 = False
 
-    def add_frame(self, frame_id: int, rgb_u8: np.ndarray, instance_u8: np.ndarray, depth_f32, pose_c2w, is_bgr: bool = False):
+    def set_depth_u16(self, depth_factor: float):
+        """From here on the depth planes are the raw 16-bit samples of the depth image (uint16 blocks); the batch kernel converts the
+        pixels it picks, (float)u16 * depth_factor.  Before the first keyframe only."""
+        check(self._lib.mon_dataset_set_depth_u16(self._h, float(depth_factor)))
+        self.depth_u16 = True
+
+    def _depth_dtype(self):
+        return np.uint16 if self.depth_u16 else np.float32
+
+    def add_frame(self, frame_id: int, rgb_u8: np.ndarray, instance_u8: np.ndarray, depth, pose_c2w, is_bgr: bool = False):
+        """depth: HxW float32 metres, or HxW uint16 counts after set_depth_u16()."""
         rgb = np.ascontiguousarray(rgb_u8, dtype=np.uint8)
         inst = np.ascontiguousarray(instance_u8, dtype=np.uint8)
         if rgb.size != self.H * self.W * 3 or inst.size != self.H * self.W:
             raise ValueError("frame has the wrong size")
-        d = None if depth_f32 is None else _f32(depth_f32, (self.H, self.W))
+        d = None
+        if depth is not None:
+            if self.depth_u16 and np.asarray(depth).dtype != np.uint16:
+                raise ValueError("the dataset takes raw uint16 depth")
+            d = np.ascontiguousarray(depth, dtype=self._depth_dtype())
+            if d.size != self.H * self.W:
+                raise ValueError("depth plane has the wrong size")
         pose = _mat16(pose_c2w)
-        check(self._lib.mon_dataset_add_frame(self._h, frame_id, _ptr(rgb), int(is_bgr), _ptr(inst),
-                                               None if d is None else _ptr(d), pose.ctypes.data_as(C.POINTER(C.c_float))))
+        fn = self._lib.mon_dataset_add_frame_d16 if self.depth_u16 else self._lib.mon_dataset_add_frame
+        check(fn(self._h, frame_id, _ptr(rgb), int(is_bgr), _ptr(inst), None if d is None else _ptr(d), pose.ctypes.data_as(C.POINTER(C.c_float))))
 
     def add_frame_device(self, frame_id: int, d_rgb: int, d_instance: int, d_depth, pose_c2w, is_bgr: bool = False):
         """Keyframe planes already in this GPU's memory (raw device addresses, e.g. torch.Tensor.data_ptr())."""
         pose = _mat16(pose_c2w)
-        check(self._lib.mon_dataset_add_frame_device(self._h, frame_id, C.c_void_p(d_rgb), int(is_bgr), C.c_void_p(d_instance),
-                                                      None if d_depth is None else C.c_void_p(d_depth), pose.ctypes.data_as(C.POINTER(C.c_float))))
+        fn = self._lib.mon_dataset_add_frame_device_d16 if self.depth_u16 else self._lib.mon_dataset_add_frame_device
+        check(fn(self._h, frame_id, C.c_void_p(d_rgb), int(is_bgr), C.c_void_p(d_instance),
+                 None if d_depth is None else C.c_void_p(d_depth), pose.ctypes.data_as(C.POINTER(C.c_float))))
 
     def add_frames(self, first_id: int, rgb_u8, instance_u8, depth_f32, poses_c2w, is_bgr: bool = False):
-        """n consecutive keyframes in one call.  rgb_u8 [n, H, W, 3], instance_u8 [n, H, W], depth_f32 [n, H, W] or None: numpy blocks
+        """n consecutive keyframes in one call.  rgb_u8 [n, H, W, 3], instance_u8 [n, H, W], depth_f32 [n, H, W] (uint16 counts after
+        set_depth_u16()) or None: numpy blocks
         (page-locked ones are DMA-ed straight out of, three copies per slab of 32 frames) or raw device addresses (ints, blocks in
         this GPU's memory; the frame count then comes from poses_c2w)."""
         n = len(poses_c2w)
@@ -121,10 +140,11 @@ class Dataset:
             for a, per in ((rgb_u8, self.H * self.W * 3), (instance_u8, self.H * self.W)):
                 if a.dtype != np.uint8 or not a.flags.c_contiguous or a.size != n * per:
                     raise ValueError("frame block has the wrong size, dtype or layout")
-            if depth_f32 is not None and (depth_f32.dtype != np.float32 or not depth_f32.flags.c_contiguous or depth_f32.size != n * self.H * self.W):
+            if depth_f32 is not None and (depth_f32.dtype != self._depth_dtype() or not depth_f32.flags.c_contiguous or depth_f32.size != n * self.H * self.W):
                 raise ValueError("depth block has the wrong size, dtype or layout")
             a_rgb, a_inst, a_dep = _ptr(rgb_u8), _ptr(instance_u8), None if depth_f32 is None else _ptr(depth_f32)
-        check(self._lib.mon_dataset_add_frames(self._h, first_id, n, a_rgb, int(is_bgr), a_inst, a_dep, flat.ctypes.data_as(C.POINTER(C.c_float)), int(on_device)))
+        fn = self._lib.mon_dataset_add_frames_d16 if self.depth_u16 else self._lib.mon_dataset_add_frames
+        check(fn(self._h, first_id, n, a_rgb, int(is_bgr), a_inst, a_dep, flat.ctypes.data_as(C.POINTER(C.c_float)), int(on_device)))
 
     def sync(self):
         check(self._lib.mon_dataset_sync(self._h))

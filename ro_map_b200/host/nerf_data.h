@@ -29,6 +29,9 @@ public:
     float fx = 0, fy = 0, cx = 0, cy = 0;
     int H = 0, W = 0;
     float mfDepthScale = 1.0f;
+    // offline: the depth PNGs' 16-bit samples go to the GPU as they are and the batch kernel applies mfDepthScale to the pixels it
+    // picks (mon_dataset_set_depth_u16) instead of a host-side convertTo pass and a float plane (nerf_data.cu:176-186)
+    bool mbDepthRaw16 = false;
     size_t mnImages = 0;
     size_t mFrameDataNum = 0;
     std::vector<std::string> mvImagesPath, mvDepthsPath, mvInstancesPath;

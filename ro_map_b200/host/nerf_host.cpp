@@ -142,6 +142,7 @@ bool NeRF_Dataset::ReadDataset(const string datasetPath) {
 bool NeRF_Dataset::InitDataToGPU() {   // nerf_data.cu:232-271
     if (mpCore) return true;
     if (mon_dataset_create(mGPUid, fx, fy, cx, cy, H, W, (uint32_t)mnImages, mbUseDepth ? 1 : 0, &mpCore) != MON_OK) die("dataset allocation");
+    if (mbUseDepth && mbDepthRaw16 && mon_dataset_set_depth_u16(mpCore, mfDepthScale) != MON_OK) die("dataset depth format");
     return true;
 }
 
@@ -151,9 +152,10 @@ bool NeRF_Dataset::DataToGPU() {   // nerf_data.cu:123-230
         cerr << "No images..." << endl;
         return false;
     }
+    mbDepthRaw16 = true;
     InitDataToGPU();
     const size_t px = (size_t)H * W;
-    vector<float> depth(px);
+    vector<uint16_t> depth16;
     string err;
     for (size_t i = 0; i < mnImages; ++i) {
         png_io::Image rgb, inst, dep;
@@ -175,19 +177,19 @@ bool NeRF_Dataset::DataToGPU() {   // nerf_data.cu:123-230
             for (size_t p = 0; p < px; ++p) c1[p] = inst.u8[p * inst.channels];
             inst.u8.swap(c1);
         }
-        const float* dptr = nullptr;
+        const uint16_t* dptr = nullptr;
         if (mbUseDepth) {
             if (!png_io::read(mvDepthsPath[i], dep, err) || dep.channels != 1 || dep.width != W || dep.height != H) {
                 cerr << "Can not read image... path: " << mvDepthsPath[i] << " " << err << endl;
                 exit(0);
             }
-            // depthImg.convertTo(CV_32FC1, mfDepthScale) (nerf_data.cu:181)
-            if (dep.bit_depth == 16) for (size_t p = 0; p < px; ++p) depth[p] = (float)dep.u16[p] * mfDepthScale;
-            else for (size_t p = 0; p < px; ++p) depth[p] = (float)dep.u8[p] * mfDepthScale;
-            dptr = depth.data();
+            // depthImg.convertTo(CV_32FC1, mfDepthScale) (nerf_data.cu:181) happens in the batch kernel, (float)u16 * mfDepthScale
+            // for the pixels it picks; an 8-bit depth image is widened (same integer, same product)
+            if (dep.bit_depth == 16) dptr = dep.u16.data();
+            else { depth16.assign(dep.u8.begin(), dep.u8.end()); dptr = depth16.data(); }
         }
         // the PNG decoder already yields RGB (cv::imread would give BGR and the reference swaps, :163)
-        if (mon_dataset_add_frame(mpCore, (uint32_t)i, rgb.u8.data(), 0, inst.u8.data(), dptr, mon_compat::mat16(mvIamgesPose[i])) != MON_OK) die("frame upload");
+        if (mon_dataset_add_frame_d16(mpCore, (uint32_t)i, rgb.u8.data(), 0, inst.u8.data(), dptr, mon_compat::mat16(mvIamgesPose[i])) != MON_OK) die("frame upload");
     }
     mFrameDataNum = mnImages;
     cout << "Load Images to GPU finished, images: " << mnImages << endl;
@@ -611,6 +613,7 @@ bool NerfManagerOffline::ReadDataset() {   // one dataset replica per GPU (nerf_
     for (auto& t : threads_data) t.join();
     // the other replicas are copied GPU-to-GPU over NVLink instead of being decoded and uploaded once per GPU
     for (int i = 1; i < mNumGPU; i++) {
+        mvpDataset[i]->mbDepthRaw16 = mvpDataset[0]->mbDepthRaw16;
         mvpDataset[i]->InitDataToGPU();
         if (mon_dataset_clone_from_peer(mvpDataset[i]->mpCore, mvpDataset[0]->mpCore) != MON_OK) die("dataset replication");
         mvpDataset[i]->mFrameDataNum = mvpDataset[0]->mFrameDataNum;

@@ -446,6 +446,47 @@ def test_bgr_keyframes_give_the_same_batch(core, gpu_dataset, small_seq):
     assert (outs[0][3] > 0).any()
 
 
+def test_raw_u16_depth_gives_the_same_batch(core, small_seq):
+    """Depth handed over as the 16-bit samples of the depth image (mon_dataset_set_depth_u16: stored as u16, converted by the batch
+    kernel for the pixels it picks) against the float plane the reference's DataToGPU makes of the same image on the host,
+    depthImg.convertTo(CV_32FC1, DepthMapFactor) = (float)u16 * factor (nerf_data.cu:176-186): rays, targets, depth targets and the
+    whole first iteration are identical bit for bit — through the single-frame entry and the block entry (slab copies), and the
+    format checks of both families of entries."""
+    seq, obj = small_seq, small_seq.objects[0]
+    factor = np.float32(1.0 / 5000.0)
+    d16 = [np.clip(np.rint(d / (1.0 / 5000.0)), 0, 65535).astype(np.uint16) for d in seq.depth]
+    dflt = [a.astype(np.float32) * factor for a in d16]
+    n = len(seq.poses)
+    ds_f = core.Dataset(0, *seq.K, seq.H, seq.W, n, True)
+    for i in range(n):
+        ds_f.add_frame(i, seq.rgb[i], seq.instance[i], dflt[i], seq.poses[i])
+    ds_a = core.Dataset(0, *seq.K, seq.H, seq.W, n, True)
+    ds_a.set_depth_u16(float(factor))
+    for i in range(n):
+        ds_a.add_frame(i, seq.rgb[i], seq.instance[i], d16[i], seq.poses[i])
+    ds_b = core.Dataset(0, *seq.K, seq.H, seq.W, n, True)
+    ds_b.set_depth_u16(float(factor))
+    ds_b.add_frames(0, np.ascontiguousarray(np.stack(seq.rgb)), np.ascontiguousarray(np.stack(seq.instance)), np.ascontiguousarray(np.stack(d16)), seq.poses)
+    with pytest.raises(Exception):
+        ds_f.set_depth_u16(float(factor))                # the format is fixed once a keyframe has been added
+    with pytest.raises(Exception):
+        ds_a.add_frame(0, seq.rgb[0], seq.instance[0], dflt[0], seq.poses[0])      # float plane into a u16 dataset
+    cfg = core.default_config(rays_per_batch=512)
+    rng = np.random.default_rng(67)
+    sxy, col, dt = randoms(rng, 512)
+    outs = []
+    for ds in (ds_f, ds_a, ds_b):
+        g = core.NerfObject(ds, cfg, obj.Tow, -1.1 * obj.half, 1.1 * obj.half, obj.instance_id)
+        g.set_bboxes(obj.boxes)
+        loss, n_in = g.train_injected(sxy, col, dt)
+        outs.append((loss, n_in, g.last("rays"), g.last("target"), g.last("target_depth"), g.last("enc"), g.last("out"), g.last("dout")))
+        g.close()
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert np.array_equal(a, b)
+    assert (outs[0][4] > 0).any()                        # depth targets are really in play
+
+
 @pytest.mark.parametrize("tag", ["a_", "b_"])
 def test_batch_against_reference_kernels(core, small_seq, tag):
     """The batch kernel held directly against RO-MAP's OWN GenerateRays / fill_rollover_rays (tests/golden/romap_golden.npz,

@@ -15,8 +15,17 @@ MON_TL_DEFINE(batch)
 
 #include <cooperative_groups.h>
 
-#define BATCH_THREADS 512
-#define BATCH_CTAS 8
+// Two shapes of the one cluster (mon_core.cu capture_graph says which graph uses which):
+//   WIDE  8 CTAs x 512 threads, 80 registers: needs SMs of its own — the graphs WITH a scatter kernel run it beside that kernel,
+//         which leaves 8 SMs free;
+//   SLIM  16 CTAs x 256 threads, <= 64 registers: such a CTA fits beside a CTA of the hash-encode kernel (1024 threads x 46
+//         registers, 128 KB of shared memory), so the graphs WITHOUT a scatter kernel generate the batch of iteration i + 1 while
+//         iteration i is encoded.  16 is a non-portable cluster size; where the device cannot co-schedule it the launcher falls
+//         back to 8 CTAs (two candidates per thread).
+#define BATCH_THREADS_WIDE 512
+#define BATCH_THREADS_SLIM 256
+#define BATCH_CTAS 16
+#define BATCH_CTAS_PORTABLE 8
 
 struct RayCand {
     bool valid; uint32_t x, y; uint8_t inst; uint32_t frame; size_t pix;
@@ -80,7 +89,8 @@ __device__ __forceinline__ void write_ray(const MonBatch& b, const MonScene& sc,
     }
 }
 
-__global__ void __launch_bounds__(BATCH_THREADS, 1)
+template <uint32_t BATCH_THREADS>
+__global__ void __launch_bounds__(BATCH_THREADS, BATCH_THREADS == BATCH_THREADS_SLIM ? 4 : 1)
 k_generate_batch(MonBatch b, MonScene sc) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -223,22 +233,54 @@ __global__ void k_render_rays(uint32_t n_rays, mon_bbox2d box, MonScene sc, cons
     }
 }
 
-void mon_launch_generate_batch(const MonBatch& b, const MonScene& sc, cudaStream_t st, const MonLaunchOpt& lo) {
+// cluster size of the slim batch kernel on the current device: 16 where such a cluster can be resident, else the portable 8
+static uint32_t batch_cluster_size_slim() {
+    static std::atomic<uint64_t> prepared{0};
+    static std::atomic<uint32_t> size_by_dev[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    mon_once_per_device(prepared, [&] {
+        uint32_t n = BATCH_CTAS_PORTABLE;
+        // the hash-encode kernel's carve-out: an SM keeps its shared-memory split while CTAs are resident, and with another
+        // preference whichever of the two kernels came second to an SM waited for the first one's CTA to leave (measured: the
+        // encode CTAs of the batch cluster's 16 SMs started 11 us late)
+        cudaFuncSetAttribute(k_generate_batch<BATCH_THREADS_SLIM>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (cudaFuncSetAttribute(k_generate_batch<BATCH_THREADS_SLIM>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(BATCH_CTAS); cfg.blockDim = dim3(BATCH_THREADS_SLIM);
+            cudaLaunchAttribute a;
+            a.id = cudaLaunchAttributeClusterDimension;
+            a.val.clusterDim.x = BATCH_CTAS; a.val.clusterDim.y = 1; a.val.clusterDim.z = 1;
+            cfg.attrs = &a; cfg.numAttrs = 1;
+            int n_clusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&n_clusters, k_generate_batch<BATCH_THREADS_SLIM>, &cfg) == cudaSuccess && n_clusters >= 1) n = BATCH_CTAS;
+        }
+        cudaGetLastError();
+        if (const char* e = getenv("MON_BATCH_CTAS")) { if (atoi(e) < BATCH_CTAS) n = BATCH_CTAS_PORTABLE; }      // A/B measurements
+        size_by_dev[dev & 63].store(n);
+        return cudaSuccess;
+    });
+    return size_by_dev[dev & 63].load();
+}
+
+void mon_launch_generate_batch(const MonBatch& b, const MonScene& sc, cudaStream_t st, const MonLaunchOpt& lo, bool slim) {
+    const uint32_t n_ctas = slim ? batch_cluster_size_slim() : BATCH_CTAS_PORTABLE;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(BATCH_CTAS);
-    cfg.blockDim = dim3(BATCH_THREADS);
+    cfg.gridDim = dim3(n_ctas);
+    cfg.blockDim = dim3(slim ? BATCH_THREADS_SLIM : BATCH_THREADS_WIDE);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = BATCH_CTAS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = n_ctas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     if (lo.set_priority) {
         attr[1].id = cudaLaunchAttributePriority;
         attr[1].val.priority = lo.priority;
         cfg.numAttrs = 2;
     }
-    cudaLaunchKernelEx(&cfg, k_generate_batch, b, sc);
+    if (slim) cudaLaunchKernelEx(&cfg, k_generate_batch<BATCH_THREADS_SLIM>, b, sc);
+    else cudaLaunchKernelEx(&cfg, k_generate_batch<BATCH_THREADS_WIDE>, b, sc);
 }
 void mon_launch_render_rays(uint32_t n_rays, mon_bbox2d box, const MonScene& sc, const float* Twc_dev, float bgc,
                             MonRay* rays_hit, uint32_t* orig, uint32_t* n_hit, float* rgb, float* depth, float* mask, cudaStream_t st) {

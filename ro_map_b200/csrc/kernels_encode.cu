@@ -98,6 +98,11 @@ void mon_launch_sample_points(uint32_t n_points, uint32_t S, const MonRay* rays,
                               const float* bmin, const float* bmax, float* pts, cudaStream_t st, const MonLaunchOpt& lo, const uint32_t* orig_ray,
                               const MonOcc* occ) {
     MonOcc none = {nullptr, 0u, nullptr, nullptr, nullptr};
+    // The same shared-memory carve-out as the hash-encode kernel, beside whose CTAs this kernel runs inside the iteration graphs: an
+    // SM does not change its carve-out while CTAs are resident, so a kernel that prefers another split waits for the encode CTAs to
+    // leave (measured: the sample points of the next iteration started only after the encode kernel had ended).
+    static std::atomic<uint64_t> prepared{0};
+    mon_once_per_device(prepared, [] { return cudaFuncSetAttribute(k_sample_points, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); });
     mon_launch_chain(MON_PDL_POINTS, lo, k_sample_points, dim3((n_points + 255) / 256), dim3(256), 0, st, n_points, S, rays, in_box, jitter, seed, ctrl, rng_stream,
                      iter_fixed, bmin[0], bmin[1], bmin[2], bmax[0], bmax[1], bmax[2], pts, orig_ray, occ ? *occ : none);
 }

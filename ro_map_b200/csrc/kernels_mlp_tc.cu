@@ -29,6 +29,7 @@
 #include "mon_kernels.h"
 #include "render_math.cuh"
 #include "tc05.cuh"
+#include "scatter_global.cuh"
 #include "mon_timeline.cuh"
 MON_TL_DEFINE(mlp)
 
@@ -311,9 +312,23 @@ __device__ __forceinline__ TileIn tc_load_tile_inputs(const MonBatch& b, uint32_
     return in;
 }
 
-template <int NH>
+// FUSE: the hash-grid gradient scatter of the iteration happens HERE, in the last epilogue of every tile, instead of in a kernel of
+// its own behind this one.  In steady state the early stop leaves ~1 sample in 12 with a non-zero dL/dencoding row (2-3 per ray);
+// the warp spreads the (live sample, level) pairs of its ray over its lanes — lane & 15 = level, two samples per round — and each
+// lane issues the level's f16x2 reductions (scatter_global.cuh: the reference's own form, kernel_grid_backward's atomicAdd(__half2),
+// TCNN encodings/grid.h:386-509) straight into the entry-ordered gradient table the optimizer sweep reads.  The compacted
+// gradient / position lists, the scatter launch, its dependency edges and its tail leave the iteration's critical path (13 us
+// kernel + 2 x 2 us of edges against ~1 us more in here: this kernel is latency-bound and has the issue slots).  The host picks
+// this variant from the live-sample count of the object's previous calls (mon_core.cu); a fresh object, whose every sample is
+// live, keeps the shared-memory resident scatter kernel.
+struct MonFuse {
+    MonGrid g;
+    __half* gh_grid;     // entry-ordered fp16 gradient table of the grid (the optimizer sweep consumes and zeroes it)
+};
+
+template <int NH, bool FUSE>
 __global__ void __launch_bounds__(TC_THREADS, TC_CTAS_PER_SM(NH))
-k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
+k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp, const __grid_constant__ MonFuse fz) {
     extern __shared__ unsigned char smem_raw[];
     // Prologue that overlaps the tail of the hash-encode kernel (programmatic dependent launch, mon_kernels.h):
     // TMEM allocation, barriers, weight tiles, the constant part of the dout tile and the first tile's ray inputs.
@@ -329,6 +344,15 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
     // the upper half of every dout row (outputs 4..15 and the second K chunk) stays zero for the whole kernel
     for (uint32_t i = c.tid; i < 4096 / 16; i += TC_THREADS) reinterpret_cast<uint4*>(c.sm + SM_DOUT)[i] = make_uint4(0, 0, 0, 0);
 
+    // FUSE: this lane's level for the whole kernel (lane & 15) and its constants
+    float fz_scale = 0.0f; uint32_t fz_res = 0, fz_size = 0; bool fz_hashed = false; char* fz_tab = nullptr;
+    if (FUSE) {
+        const uint32_t l = c.lane & 15u;
+        if (l < fz.g.n_levels) {
+            fz_scale = fz.g.scale[l]; fz_res = fz.g.res[l]; fz_size = fz.g.size[l]; fz_hashed = fz.g.hashed[l] != 0;
+            fz_tab = reinterpret_cast<char*>(reinterpret_cast<__half2*>(fz.gh_grid) + fz.g.offset[l]);
+        }
+    }
     const bool skip = b.ctrl->skip != 0;
     const float kscale = lc.loss_scale / (float)b.R;
     const uint32_t iter = b.ctrl->iter - 1;
@@ -518,7 +542,32 @@ k_mlp_train_tc(MonBatch b, MonLossCfg lc, uint32_t n_mlp) {
             }
             const bool live = ray_ok && (any & 0x7fff7fffu) != 0u;
             const uint32_t lm = __ballot_sync(0xffffffffu, live);
-            if (lm) {
+            if (FUSE) {
+                if (lm) {
+                    if (c.lane == 0) atomicAdd(b.live_cnt + (iter & 1u), (uint32_t)__popc(lm));     // the host reads it to choose the graph variant
+                    const uint32_t half_i = c.lane >> 4, myl = c.lane & 15u;
+                    uint32_t rem = lm;
+                    while (rem) {            // warp-uniform: two live samples per round, lanes 0-15 / 16-31 take their 16 levels
+                        const uint32_t sa = (uint32_t)__ffs((int)rem) - 1u;
+                        rem &= rem - 1u;
+                        uint32_t sb = 32u;
+                        if (rem) { sb = (uint32_t)__ffs((int)rem) - 1u; rem &= rem - 1u; }
+                        const uint32_t src = half_i ? sb : sa;
+                        uint32_t gw = 0u;
+#pragma unroll
+                        for (uint32_t q = 0; q < 16; ++q) {
+                            const uint32_t v = __shfl_sync(0xffffffffu, packed[q], src & 31u);
+                            if (q == myl) gw = v;
+                        }
+                        const float u[3] = {__shfl_sync(0xffffffffu, pu[0], src & 31u), __shfl_sync(0xffffffffu, pu[1], src & 31u),
+                                            __shfl_sync(0xffffffffu, pu[2], src & 31u)};
+                        // a zero pair adds nothing (the stand-alone kernel skips it too); lanes beyond the grid's levels idle
+                        if (src < 32u && fz_tab && (gw & 0x7fff7fffu) != 0u)
+                            scatter_level_pow2(fz_scale, fz_res, fz_hashed, fz_size, fz_tab, __half2float(__ushort_as_half((unsigned short)(gw & 0xffffu))),
+                                               __half2float(__ushort_as_half((unsigned short)(gw >> 16))), u);
+                    }
+                }
+            } else if (lm) {
                 uint32_t base = 0;
                 if (c.lane == 0) base = atomicAdd(b.live_cnt + (iter & 1u), (uint32_t)__popc(lm));
                 base = __shfl_sync(0xffffffffu, base, 0);
@@ -679,22 +728,24 @@ static cudaError_t tc_prepare(K kernel, int smem_bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
 }
 
+template <int NH, bool FUSE>
+static cudaError_t tc_launch_train(const MonBatch& b, const MonLossCfg& lc, uint32_t n_mlp, uint32_t n_ctas, cudaStream_t st, const MonLaunchOpt& lo, const MonFuse& fz) {
+    static std::atomic<uint64_t> prepared{0};
+    const cudaError_t prep = mon_once_per_device(prepared, [] { return tc_prepare(k_mlp_train_tc<NH, FUSE>, TC_SMEM_BYTES(NH)); });
+    if (prep != cudaSuccess) return prep;
+    return mon_launch_chain(MON_PDL_MLP, lo, k_mlp_train_tc<NH, FUSE>, dim3(n_ctas), dim3(TC_THREADS), TC_SMEM_BYTES(NH), st, b, lc, n_mlp, fz);
+}
+
+// fuse_grid != nullptr: the kernel scatters the hash-grid gradients itself into gh_grid (power-of-two tables only, see
+// mon_scatter_resident_supported) and writes no compacted lists; no scatter kernel may follow it then
 cudaError_t mon_launch_mlp_train_tc(const MonBatch& b, const MonLossCfg& lc, uint32_t n_hidden, uint32_t n_mlp, uint32_t n_ctas, cudaStream_t st,
-                                    const MonLaunchOpt& lo) {
-    if (n_hidden == 1) {
-        static std::atomic<uint64_t> prepared{0};
-        const cudaError_t prep = mon_once_per_device(prepared, [] { return tc_prepare(k_mlp_train_tc<1>, TC_SMEM_BYTES(1)); });
-        if (prep != cudaSuccess) return prep;
-        return mon_launch_chain(MON_PDL_MLP, lo, k_mlp_train_tc<1>, dim3(n_ctas), dim3(TC_THREADS), TC_SMEM_BYTES(1), st, b, lc, n_mlp);
-    } else if (n_hidden == 2) {
-        static std::atomic<uint64_t> prepared{0};
-        const cudaError_t prep = mon_once_per_device(prepared, [] { return tc_prepare(k_mlp_train_tc<2>, TC_SMEM_BYTES(2)); });
-        if (prep != cudaSuccess) return prep;
-        return mon_launch_chain(MON_PDL_MLP, lo, k_mlp_train_tc<2>, dim3(n_ctas), dim3(TC_THREADS), TC_SMEM_BYTES(2), st, b, lc, n_mlp);
-    } else {
-        return cudaErrorNotSupported;
-    }
-    return cudaGetLastError();
+                                    const MonLaunchOpt& lo, const MonGrid* fuse_grid, __half* gh_grid) {
+    MonFuse fz;
+    memset(&fz, 0, sizeof(fz));
+    if (fuse_grid) { fz.g = *fuse_grid; fz.gh_grid = gh_grid; }
+    if (n_hidden == 1) return fuse_grid ? tc_launch_train<1, true>(b, lc, n_mlp, n_ctas, st, lo, fz) : tc_launch_train<1, false>(b, lc, n_mlp, n_ctas, st, lo, fz);
+    if (n_hidden == 2) return fuse_grid ? tc_launch_train<2, true>(b, lc, n_mlp, n_ctas, st, lo, fz) : tc_launch_train<2, false>(b, lc, n_mlp, n_ctas, st, lo, fz);
+    return cudaErrorNotSupported;
 }
 
 cudaError_t mon_launch_mlp_infer_tc(uint32_t n_points, uint32_t n_hidden, const __half* params, const __half* enc, float* out4, cudaStream_t st) {

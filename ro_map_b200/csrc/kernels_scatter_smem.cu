@@ -72,8 +72,9 @@ extern "C" int mon_debug_tl_sr_cta_read(unsigned long long* out) { return (int)c
 // every job a piece touches ends with a flush (convert + bulk reduction + clearing the slice for the next job): ~3.6 us, the time
 // of ~7500 hashed-level samples.  Charged at each job START: a piece that spans a job boundary gets that much less sample work.
 #define SR_FLUSH 480000ull
-// the batch kernel of the NEXT iteration (one cluster of 8 CTAs) runs on the forked branch beside this kernel; a full-chip grid
-// would leave 8 of its one-per-SM CTAs waiting ~13 us for those SMs
+// opt-in occupancy mode only: there the batch kernel of the NEXT iteration (one cluster) runs on the forked branch beside this
+// kernel, and a full-chip grid would leave some of its one-per-SM CTAs waiting ~13 us for those SMs; the caller passes the number
+// of SMs to leave free (default graphs: 0 — the next batch is generated beside the hash encode instead)
 #define SR_SPARE_SMS 8u
 
 struct SrArgs {
@@ -304,7 +305,7 @@ void mon_scatter_resident_pieces_host(const MonGrid& g, uint32_t n_live, uint32_
 
 cudaError_t mon_launch_scatter(const MonGrid& g, uint32_t n_points, uint32_t min_live, const uint32_t* live_cnt, const float* pts_c,
                                const uint32_t* genc, const MonCtrl* ctrl, __half* gcls, __half* gh_grid, uint32_t sm_count, cudaStream_t st,
-                               const MonLaunchOpt& lo) {
+                               const MonLaunchOpt& lo, bool leave_spare_sms) {
     static std::atomic<uint64_t> prepared{0};
     const cudaError_t prep = mon_once_per_device(prepared, [] {
         // 132 of the SM's 228 KB as shared memory, the rest stays L1: the optimizer sweep follows through a programmatic edge on SMs
@@ -323,6 +324,6 @@ cudaError_t mon_launch_scatter(const MonGrid& g, uint32_t n_points, uint32_t min
     a.n_slow *= 4u;
     a.live_cnt = live_cnt; a.pts_c = pts_c; a.genc = genc; a.ctrl = ctrl; a.gcls = gcls; a.gh_grid = gh_grid;
     static const uint32_t spare = [] { const char* e = getenv("MON_SCATTER_SPARE_SMS"); return e ? (uint32_t)atoi(e) : SR_SPARE_SMS; }();
-    const uint32_t ctas = sm_count > 4u * spare ? sm_count - spare : sm_count;
+    const uint32_t ctas = leave_spare_sms && sm_count > 4u * spare ? sm_count - spare : sm_count;
     return mon_launch_chain(MON_PDL_SCATTER, lo, k_scatter, dim3(ctas), dim3(SR_THREADS), SR_SMEM_BYTES, st, a);
 }

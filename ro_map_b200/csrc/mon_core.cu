@@ -315,6 +315,13 @@ struct mon_object {
     __half* gcls = nullptr;
     uint32_t resident_min_live = 0xffffffffu;
     bool scatter_unified = true;      // false: a configuration kernels_scatter_smem.cu does not cover (stand-alone global-reduction kernel)
+    // Steady state (few live samples): graphs WITHOUT a scatter kernel — the fused MLP kernel issues the f16x2 reductions itself
+    // (kernels_mlp_tc.cu, FUSE).  Chosen per call on the host from the live-sample counts the previous calls left in h_live (an
+    // 8-byte asynchronous read-back at the end of every call; a hint, never waited for).  fuse_mode: 0 = by the live count,
+    // 1 = always, -1 = never (MON_SCATTER_FUSED: A/B measurements and tests).
+    int fuse_mode = 0;
+    bool fuse_supported = false;
+    uint32_t* h_live = nullptr;       // pinned [2]; 0xffffffff until the first read-back has landed
     // opt-in occupancy grid (mon_object_set_occupancy; off: occ_res == 0).  The density grid is the running maximum (decayed) of
     // the network's density on the cell corners; a cell is occupied while that exceeds the threshold
     uint32_t occ_res = 0, occ_warmup = 0, occ_interval = 0;
@@ -324,7 +331,7 @@ struct mon_object {
     uint64_t iters_enqueued = 0, occ_last_update = 0;
     bool occ_started = false;
     // instantiated iteration graphs by length
-    struct GraphSlot { uint32_t iters; cudaGraphExec_t exec; uint64_t stamp; };
+    struct GraphSlot { uint32_t iters; bool fused; cudaGraphExec_t exec; uint64_t stamp; };
     std::vector<GraphSlot> graphs;
     uint64_t graph_clock = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -814,23 +821,24 @@ static void drop_graphs(mon_object* o) {
     o->graphs.clear();
 }
 
-static MonBatch make_batch(mon_object* o, bool injected, bool debug) {
+static MonBatch make_batch(mon_object* o, bool injected, bool debug, uint32_t set = 0) {
     MonBatch b;
     memset(&b, 0, sizeof(b));
+    const size_t sR = (size_t)set * o->R;
     b.R = o->R;
     b.boxes = o->d_boxes;
     b.frames = o->ds->d_frames;
     b.state = o->ctrl_state;
-    b.ctrl = o->ctrl;
+    b.ctrl = o->ctrl + set;
     b.late = o->ctrl_late;
     b.seed = o->seed;
     b.opt_lr = o->cfg.learning_rate; b.decay_base = o->cfg.decay_base; b.ema_decay = o->cfg.ema_decay;
     b.decay_start = o->cfg.decay_start; b.decay_interval = o->cfg.decay_interval ? o->cfg.decay_interval : 1;
     if (injected) { b.inj_xy = o->inj_xy; b.inj_col = o->inj_col; b.inj_dt = o->inj_dt; }
-    b.rays = o->rays; b.ray_inst = o->ray_inst; b.target = o->target; b.target_depth = o->target_depth; b.bg = o->bg;
+    b.rays = o->rays + sR; b.ray_inst = o->ray_inst + sR; b.target = o->target + sR * 3; b.target_depth = o->target_depth + sR; b.bg = o->bg + sR * 3;
     b.rgb_rays = o->rgb_rays; b.depth_rays = o->depth_rays; b.mask_rays = o->mask_rays; b.loss = o->loss;
     b.enc = o->enc;
-    b.pts = o->pts; b.pts_c = o->pts_c; b.genc = o->genc; b.live_cnt = o->live_cnt;
+    b.pts = o->pts + (size_t)set * o->N * 3; b.pts_c = o->pts_c; b.genc = o->genc; b.live_cnt = o->live_cnt;
     b.occ = MonOcc{o->occ_bits, o->occ_res, o->occ_ray_mask, o->occ_list, o->occ_count};
     if (debug) { b.dbg_out = o->dbg_out; b.dbg_dout = o->dbg_dout; b.d_enc = o->d_enc; }
     b.params = o->ph; b.grads = o->gh; b.mlp_partials = o->partials;
@@ -846,34 +854,45 @@ static MonBatch make_batch(mon_object* o, bool injected, bool debug) {
 // control block for S/O), and the sample positions are last read by M too (it hands the positions of the live samples to S
 // in compacted form).  In the opt-in fused mode S also updates the grid and O (MLP weights + logged loss only) runs on a
 // second branch beside it.
-static int launch_batch(mon_object* o, const MonBatch& b, cudaStream_t st) {
-    mon_launch_generate_batch(b, o->scene, st);
+// Where the next iteration's batch + sample points run inside a graph.  Graphs WITH a scatter kernel (a fresh object): behind the
+// MLP kernel, beside the scatter, which leaves the batch cluster 8 SMs.  Graphs WITHOUT one (steady state, scatter fused into the
+// MLP kernel): forked at the start of the iteration, beside the hash encode, in the slim shape that fits next to its CTAs — the
+// optimizer sweep that follows the MLP kernel there fills every SM.  Measured both ways in both phases (profiles/r9c_timeline_*):
+// beside the encode the scatter gets the whole chip (-2.3 us) but the encode loses 2.7 us.  MON_EARLY_FORK=0 / 1 forces one form.
+static bool early_fork(const mon_object* o, bool fused) {
+    static const int env = [] { const char* e = getenv("MON_EARLY_FORK"); return e ? atoi(e) : -1; }();
+    if (o->occ_bits) return false;     // the occupancy mode's sample-points kernel writes single-buffered lists E and M read
+    return env >= 0 ? env != 0 : fused;
+}
+static int launch_batch(mon_object* o, const MonBatch& b, cudaStream_t st, bool slim = false) {
+    mon_launch_generate_batch(b, o->scene, st, MonLaunchOpt(), slim);
     return MON_OK;
 }
 static int launch_points(mon_object* o, const MonBatch& b, cudaStream_t st, bool pdl = true) {
     MonLaunchOpt lo; lo.pdl = pdl;
-    mon_launch_sample_points(o->N, MON_S, o->rays, nullptr, b.inj_dt, o->seed, o->ctrl, 2, 0, o->scene.bmin, o->scene.bmax, o->pts, st, lo, nullptr,
+    mon_launch_sample_points(o->N, MON_S, b.rays, nullptr, b.inj_dt, o->seed, b.ctrl, 2, 0, o->scene.bmin, o->scene.bmax, const_cast<float*>(b.pts), st, lo, nullptr,
                              o->occ_bits ? &b.occ : nullptr);
     return MON_OK;
 }
-static int launch_encode(mon_object* o, cudaStream_t st, bool pdl = true) {
+static int launch_encode(mon_object* o, const MonBatch& b, cudaStream_t st, bool pdl = true) {
     MonLaunchOpt lo; lo.pdl = pdl;
-    cudaError_t e = mon_launch_encode_forward(o->grid, o->N, o->pts, o->ph_planar, o->enc, o->ctrl, (uint32_t)o->sm_count, st, 0, 0xffffffffu, lo,
+    cudaError_t e = mon_launch_encode_forward(o->grid, o->N, b.pts, o->ph_planar, o->enc, b.ctrl, (uint32_t)o->sm_count, st, 0, 0xffffffffu, lo,
                                               o->occ_bits ? o->occ_list : nullptr, o->occ_bits ? o->occ_count : nullptr);
     if (e != cudaSuccess) return fail(MON_ERR_CUDA, "hash encode launch: %s", cudaGetErrorString(e));
     return MON_OK;
 }
-static int launch_mlp(mon_object* o, const MonBatch& b, cudaStream_t st) {
-    cudaError_t e = mon_launch_mlp_train_tc(b, o->lc, o->cfg.n_hidden_layers, o->n_mlp, o->n_ctas, st);
+static int launch_mlp(mon_object* o, const MonBatch& b, cudaStream_t st, bool fused = false) {
+    cudaError_t e = mon_launch_mlp_train_tc(b, o->lc, o->cfg.n_hidden_layers, o->n_mlp, o->n_ctas, st, MonLaunchOpt(), fused ? &o->grid : nullptr, o->gh + o->n_mlp);
     if (e != cudaSuccess) return fail(MON_ERR_CUDA, "fused MLP launch: %s", cudaGetErrorString(e));
     return MON_OK;
 }
 // gradient scatter: one launch; the kernel takes the shared-memory resident path or the global reductions by the iteration's
 // live-sample count.  Configurations the unified kernel does not cover use the stand-alone global-reduction kernel.
-static int launch_scatter(mon_object* o, cudaStream_t st) {
+static int launch_scatter(mon_object* o, cudaStream_t st, bool leave_spare_sms = true) {
     if (o->scatter_unified) {
+        // occupancy mode: the next iteration's batch cluster runs beside this kernel (capture_graph) and needs SMs of its own
         cudaError_t e = mon_launch_scatter(o->grid, o->N, o->resident_min_live, o->live_cnt, o->pts_c, o->genc, o->ctrl_late, o->gcls, o->gh + o->n_mlp,
-                                           (uint32_t)o->sm_count, st);
+                                           (uint32_t)o->sm_count, st, MonLaunchOpt(), leave_spare_sms);
         if (e != cudaSuccess) return fail(MON_ERR_CUDA, "gradient scatter launch: %s", cudaGetErrorString(e));
         return MON_OK;
     }
@@ -883,15 +902,24 @@ static int launch_scatter(mon_object* o, cudaStream_t st) {
 static int scatter_launches(const mon_object*) { return 1; }
 // optimizer sweep: MLP weights (fixed-order reduction of the per-CTA partials, Adam, EMA) + logged loss + the grid (Adam with
 // per-parameter steps, EMA, gradient zeroing, planar weight copy)
-static void launch_optimizer(mon_object* o, cudaStream_t st, bool pdl) {
+static void launch_optimizer(mon_object* o, cudaStream_t st, bool pdl, bool fused = false) {
     MonLaunchOpt lo; lo.pdl = pdl;
+    // fused: the gradients are in the entry-ordered table whatever the live count was
     mon_launch_optimizer(o->opt, o->ctrl_late, o->pf, o->ph, o->gh, o->partials, o->m, o->v, o->ps, o->ema, o->loss, o->R, o->grid,
-                         o->ph_planar, st, MON_OPT_ALL, 0, 0xffffffffu, lo, o->gcls, o->live_cnt, o->resident_min_live, (uint32_t)o->sm_count);
+                         o->ph_planar, st, MON_OPT_ALL, 0, 0xffffffffu, lo, o->gcls, o->live_cnt, fused ? 0xffffffffu : o->resident_min_live, (uint32_t)o->sm_count);
+}
+// which graph variant the next call takes: the scatter fused into the MLP kernel when the object's recent iterations had few live
+// samples (the counts of the last two iterations of the previous call, if their read-back has landed)
+static bool use_fused(const mon_object* o) {
+    if (!o->fuse_supported || o->occ_bits || o->fuse_mode < 0) return false;
+    if (o->fuse_mode > 0) return true;
+    const uint32_t a = reinterpret_cast<volatile uint32_t*>(o->h_live)[0], b = reinterpret_cast<volatile uint32_t*>(o->h_live)[1];
+    return std::max(a, b) < std::min<uint32_t>(o->resident_min_live, MON_RESIDENT_MIN_LIVE);
 }
 
 // serial version (injected / profiled iterations).  ev (optional, MON_N_STAGES+1 events): recorded before each
 // stage and after the last one.  Returns the number of kernels launched through n_launched.
-static int enqueue_iteration(mon_object* o, const MonBatch& b, bool snapshot_grad, int* n_launched, cudaEvent_t* ev = nullptr) {
+static int enqueue_iteration(mon_object* o, const MonBatch& b, bool snapshot_grad, int* n_launched, cudaEvent_t* ev = nullptr, bool fused = false) {
     cudaStream_t st = o->stream;
     int n = 0, rc;
     if (ev) CK(cudaEventRecord(ev[0], st));
@@ -899,49 +927,66 @@ static int enqueue_iteration(mon_object* o, const MonBatch& b, bool snapshot_gra
     if (ev) CK(cudaEventRecord(ev[1], st));
     launch_points(o, b, st); ++n;
     if (ev) CK(cudaEventRecord(ev[2], st));
-    if ((rc = launch_encode(o, st)) != MON_OK) return rc;
+    if ((rc = launch_encode(o, b, st)) != MON_OK) return rc;
     ++n;
     if (ev) CK(cudaEventRecord(ev[3], st));
-    if ((rc = launch_mlp(o, b, st)) != MON_OK) return rc;
+    if ((rc = launch_mlp(o, b, st, fused)) != MON_OK) return rc;
     ++n;
     if (ev) CK(cudaEventRecord(ev[4], st));
-    if ((rc = launch_scatter(o, st)) != MON_OK) return rc;
-    n += scatter_launches(o);
+    if (!fused) {
+        if ((rc = launch_scatter(o, st)) != MON_OK) return rc;
+        n += scatter_launches(o);
+    }
     if (snapshot_grad) { mon_launch_snapshot_grad(o->P, o->n_mlp, o->opt.n_partials, o->gh, o->partials, o->grad_snap, st, o->grid, o->gcls); ++n; }
     if (ev) CK(cudaEventRecord(ev[5], st));
-    launch_optimizer(o, st, !snapshot_grad && !o->scatter_unified); ++n;
+    launch_optimizer(o, st, !snapshot_grad && !o->scatter_unified, fused); ++n;
     if (ev) CK(cudaEventRecord(ev[6], st));
     CK(cudaGetLastError());
     if (n_launched) *n_launched = n;
     return MON_OK;
 }
 
-static int capture_graph(mon_object* o, int iters, cudaGraphExec_t* out) {
-    const MonBatch b = make_batch(o, false, false);
+static int capture_graph(mon_object* o, int iters, bool fused, cudaGraphExec_t* out) {
+    // two batch sets alternate inside a graph; every graph starts with set 0 (its first batch is generated in the open)
+    const MonBatch bs[2] = {make_batch(o, false, false, 0), make_batch(o, false, false, 1)};
     cudaGraph_t g = nullptr;
     cudaStream_t st = o->stream, aux = o->aux;
+    // Where the next iteration's batch + sample points run (early_fork above).  With a scatter kernel in the graph:
+    //     main:  E(i) -> M(i) -> S(i) ---> O(i) --join--> E(i+1) ...            the branch forks behind M(i), the last reader of the
+    //     aux :            \--> B(i+1) -> P(i+1) --/                            batch set it rewrites (set 0 throughout)
+    // without one (steady state, scatter fused into M):
+    //     main:  E(i) ----------> M(i) -> O(i) --join--> E(i+1) ...             forked at the START of iteration i, beside its hash
+    //     aux :  B(i+1) -> P(i+1) ---------------/                              encode; the two batch sets alternate
+    const bool early = early_fork(o, fused);
     CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     int rc = MON_OK;
     cudaError_t e = cudaSuccess;
-    launch_batch(o, b, st);
-    launch_points(o, b, st);
+    launch_batch(o, bs[0], st);
+    launch_points(o, bs[0], st);
+    auto fork_next = [&](const MonBatch& nb) {
+        if ((e = cudaEventRecord(o->ev_fork_m, st)) != cudaSuccess) return;
+        if ((e = cudaStreamWaitEvent(aux, o->ev_fork_m, 0)) != cudaSuccess) return;
+        launch_batch(o, nb, aux, early);
+        launch_points(o, nb, aux, false);
+        e = cudaEventRecord(o->ev_join, aux);
+    };
     for (int i = 0; i < iters && rc == MON_OK && e == cudaSuccess; ++i) {
+        const MonBatch& b = bs[early ? (i & 1) : 0];
+        const MonBatch& nb = bs[early ? ((i + 1) & 1) : 0];
         const bool fork = i + 1 < iters;
-        // after a join the encode kernel's predecessor in the stream is not a plain kernel node: no programmatic edge there
-        if ((rc = launch_encode(o, st, i == 0)) != MON_OK) break;
-        if ((rc = launch_mlp(o, b, st)) != MON_OK) break;
-        if (fork) {
-            if ((e = cudaEventRecord(o->ev_fork_m, st)) != cudaSuccess) break;
-            if ((e = cudaStreamWaitEvent(aux, o->ev_fork_m, 0)) != cudaSuccess) break;
-            launch_batch(o, b, aux);
-            launch_points(o, b, aux, false);
-            if ((e = cudaEventRecord(o->ev_join, aux)) != cudaSuccess) break;
-        }
-        if ((rc = launch_scatter(o, st)) != MON_OK) break;
+        if (fork && early) { fork_next(nb); if (e != cudaSuccess) break; }
+        // after a fork or a join the encode kernel's predecessor in the stream is not a plain kernel node: no programmatic edge there
+        if ((rc = launch_encode(o, b, st, i == 0 && !(fork && early))) != MON_OK) break;
+        if ((rc = launch_mlp(o, b, st, fused)) != MON_OK) break;
+        if (fork && !early) { fork_next(nb); if (e != cudaSuccess) break; }
+        // fused variant (steady state): no scatter kernel.  The sweep follows the MLP kernel through a PLAIN edge as well: with a
+        // programmatic one its CTAs land on SMs that still hold MLP CTAs and keep their maximum shared-memory carve-out, and its
+        // streaming loads have too little L1 (19.4 instead of 13.5 us, profiles/r9b_timeline.txt)
+        if (!fused && (rc = launch_scatter(o, st, !early)) != MON_OK) break;
         // no programmatic edge behind the unified scatter kernel: sweep CTAs that become resident while its 1024-thread CTAs still
         // run slowed the sweep by 3-5 us (profiles/r5i_timeline*.txt); a plain edge costs a 2 us gap (deferring the scatter's trigger
         // to its CTAs' exit changes nothing either way: profiles/r8b_timeline_late_edge.txt)
-        launch_optimizer(o, st, !o->scatter_unified);
+        launch_optimizer(o, st, !o->scatter_unified, fused);
         if (fork && (e = cudaStreamWaitEvent(st, o->ev_join, 0)) != cudaSuccess) break;
     }
     cudaError_t e2 = cudaStreamEndCapture(st, &g);
@@ -967,10 +1012,10 @@ static GraphPlan graph_plan(uint32_t iters) {
 }
 
 // the instantiated graph of exactly `iters` iterations (1 <= iters <= MON_GRAPH_CHUNK), captured on first use
-static int graph_for(mon_object* o, uint32_t iters, cudaGraphExec_t* out) {
-    for (auto& g : o->graphs) if (g.iters == iters) { g.stamp = ++o->graph_clock; *out = g.exec; return MON_OK; }
+static int graph_for(mon_object* o, uint32_t iters, bool fused, cudaGraphExec_t* out) {
+    for (auto& g : o->graphs) if (g.iters == iters && g.fused == fused) { g.stamp = ++o->graph_clock; *out = g.exec; return MON_OK; }
     cudaGraphExec_t exec = nullptr;
-    int rc = capture_graph(o, (int)iters, &exec);
+    int rc = capture_graph(o, (int)iters, fused, &exec);
     if (rc != MON_OK) return rc;
     size_t n_rem = 0, oldest = SIZE_MAX;
     for (size_t k = 0; k < o->graphs.size(); ++k) {
@@ -983,13 +1028,13 @@ static int graph_for(mon_object* o, uint32_t iters, cudaGraphExec_t* out) {
         cudaGraphExecDestroy(o->graphs[oldest].exec);
         o->graphs.erase(o->graphs.begin() + (long)oldest);
     }
-    o->graphs.push_back({iters, exec, ++o->graph_clock});
+    o->graphs.push_back({iters, fused, exec, ++o->graph_clock});
     *out = exec;
     return MON_OK;
 }
 
 // kernels launched by one replay of an `iters`-iteration graph
-static uint64_t launches_in_graph(const mon_object* o, uint32_t iters) { return (5ull + (uint64_t)scatter_launches(o)) * iters; }
+static uint64_t launches_in_graph(const mon_object* o, uint32_t iters, bool fused) { return (5ull + (fused ? 0ull : (uint64_t)scatter_launches(o))) * iters; }
 
 int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uint8_t instance_id,
                       const float obj_Tow[16], const float bmin[3], const float bmax[3], mon_object** out) {
@@ -1051,11 +1096,13 @@ int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uin
     const size_t P = o->P, R = o->R, N = o->N;
     OALLOC(o->pf, P * 4); OALLOC(o->m, P * 4); OALLOC(o->v, P * 4); OALLOC(o->ps, P * 4);
     OALLOC(o->ph, P * 2 + 16); OALLOC(o->gh, P * 2 + 16); OALLOC(o->ema, P * 2 + 16);
-    OALLOC(o->ctrl_state, sizeof(MonCtrl)); OALLOC(o->ctrl, sizeof(MonCtrl)); OALLOC(o->ctrl_late, sizeof(MonCtrl));
-    OALLOC(o->rays, R * sizeof(MonRay)); OALLOC(o->ray_inst, R);
-    OALLOC(o->target, R * 12); OALLOC(o->target_depth, R * 4); OALLOC(o->bg, R * 12);
+    OALLOC(o->ctrl_state, sizeof(MonCtrl)); OALLOC(o->ctrl, 2 * sizeof(MonCtrl)); OALLOC(o->ctrl_late, sizeof(MonCtrl));
+    // two batch sets (rays, targets, control block, sample positions): inside the iteration graphs the batch of iteration i + 1 is
+    // generated into set (i + 1) & 1 while iteration i is encoded from set i & 1 (capture_graph); set 1 follows set 0 in each buffer
+    OALLOC(o->rays, 2 * R * sizeof(MonRay)); OALLOC(o->ray_inst, 2 * R);
+    OALLOC(o->target, 2 * R * 12); OALLOC(o->target_depth, 2 * R * 4); OALLOC(o->bg, 2 * R * 12);
     OALLOC(o->rgb_rays, R * 12); OALLOC(o->depth_rays, R * 4); OALLOC(o->mask_rays, R * 4); OALLOC(o->loss, R * 4);
-    OALLOC(o->pts, N * 12); OALLOC(o->enc, N * MON_IN * 2);
+    OALLOC(o->pts, 2 * N * 12); OALLOC(o->enc, N * MON_IN * 2);
     OALLOC(o->pts_c, N * 16); OALLOC(o->genc, N * (size_t)MON_MAX_LEVELS * 4); OALLOC(o->live_cnt, 8);
     OALLOC(o->ph_planar, (size_t)o->n_grid * 2 + 16);
     OALLOC(o->gcls, (size_t)o->n_grid * 2 + 16);
@@ -1070,7 +1117,11 @@ int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uin
     o->resident_min_live = MON_RESIDENT_MIN_LIVE;
     if (const char* env = getenv("MON_SCATTER_RESIDENT_MIN")) { const long v = atol(env); o->resident_min_live = v < 0 ? 0xffffffffu : (uint32_t)v; }
     if (!mon_scatter_resident_supported(grid)) { o->resident_min_live = 0xffffffffu; o->scatter_unified = false; }
-    if ((e = cudaMallocHost(&o->h_ctrl, sizeof(MonCtrl))) != cudaSuccess ||
+    o->fuse_supported = o->scatter_unified;        // power-of-two tables (scatter_level_pow2)
+    if (const char* env = getenv("MON_SCATTER_FUSED")) o->fuse_mode = atoi(env);
+    if ((e = cudaMallocHost(&o->h_live, 2 * sizeof(uint32_t))) == cudaSuccess) o->h_live[0] = o->h_live[1] = 0xffffffffu;
+    if (e != cudaSuccess ||
+        (e = cudaMallocHost(&o->h_ctrl, sizeof(MonCtrl))) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&o->aux, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&o->ev_fork_m, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&o->ev_join, cudaEventDisableTiming)) != cudaSuccess ||
@@ -1137,6 +1188,7 @@ int mon_object_destroy(mon_object* o) {
     for (void* p : o->scr) mon_dev_free(p, o->stream);
     if (o->stream) cudaStreamSynchronize(o->stream);
     if (o->h_ctrl) cudaFreeHost(o->h_ctrl);
+    if (o->h_live) cudaFreeHost(o->h_live);
     cudaEvent_t evs[] = {o->ev0, o->ev1, o->ev_fork_m, o->ev_join};
     for (cudaEvent_t ev : evs) if (ev) cudaEventDestroy(ev);
     cudaStream_t sts[] = {o->aux, o->stream};
@@ -1207,8 +1259,12 @@ int mon_object_prepare_train(mon_object* o, uint32_t iters) {
     CK(cudaSetDevice(o->ds->gpu));
     cudaGraphExec_t g = nullptr;
     const GraphPlan plan = graph_plan(iters);
-    if (plan.n_chunk) { int rc = graph_for(o, plan.chunk, &g); if (rc != MON_OK) return rc; }
-    if (plan.rem) { int rc = graph_for(o, plan.rem, &g); if (rc != MON_OK) return rc; }
+    // both variants a call of this length may take (with and without the scatter kernel, use_fused)
+    for (int fused = 0; fused < 2; ++fused) {
+        if (fused ? (!o->fuse_supported || o->occ_bits || o->fuse_mode < 0) : o->fuse_mode > 0 && o->fuse_supported && !o->occ_bits) continue;
+        if (plan.n_chunk) { int rc = graph_for(o, plan.chunk, fused != 0, &g); if (rc != MON_OK) return rc; }
+        if (plan.rem) { int rc = graph_for(o, plan.rem, fused != 0, &g); if (rc != MON_OK) return rc; }
+    }
     return MON_OK;
 }
 
@@ -1228,8 +1284,9 @@ int mon_object_train_async(mon_object* o, uint32_t iters) {
     cudaGraphExec_t g_chunk = nullptr, g_rem = nullptr;
     const GraphPlan plan = graph_plan(iters);
     const uint32_t rem = plan.rem;
-    if (plan.n_chunk) { int rc = graph_for(o, plan.chunk, &g_chunk); if (rc != MON_OK) return rc; }
-    if (rem) { int rc = graph_for(o, rem, &g_rem); if (rc != MON_OK) return rc; }
+    const bool fused = use_fused(o);
+    if (plan.n_chunk) { int rc = graph_for(o, plan.chunk, fused, &g_chunk); if (rc != MON_OK) return rc; }
+    if (rem) { int rc = graph_for(o, rem, fused, &g_rem); if (rc != MON_OK) return rc; }
     CK(cudaStreamWaitEvent(o->stream, o->ds->ev_uploaded, 0));   // frames uploaded asynchronously from pinned buffers
     CK(cudaEventRecord(o->ev0, o->stream));
     // opt-in occupancy mode: the grid is refreshed between graph replays (enqueued on the same stream, no host wait)
@@ -1244,8 +1301,10 @@ int mon_object_train_async(mon_object* o, uint32_t iters) {
         o->iters_enqueued += rem;
     }
     CK(cudaEventRecord(o->ev1, o->stream));
+    // the live-sample counts of the call's last two iterations, for the next call's choice of graph variant (never waited for)
+    CK(cudaMemcpyAsync(o->h_live, o->live_cnt, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, o->stream));
     o->timing_pending = true;
-    o->launches += launches_in_graph(o, iters);
+    o->launches += launches_in_graph(o, iters, fused);
     o->have_injected = false;
     return MON_OK;
 }
@@ -1286,15 +1345,17 @@ int mon_object_train_profiled(mon_object* o, uint32_t iters, float* stage_ms, ui
     for (auto& x : ev) CK(cudaEventCreate(&x));
     double acc[MON_N_STAGES] = {0};
     const MonBatch b = make_batch(o, false, false);
+    const bool fused = use_fused(o);      // the variant a graph call would take now; its scatter stage is then empty
     int rc = MON_OK;
     for (uint32_t done = 0; done < iters && rc == MON_OK; done += chunk) {
         const uint32_t n_it = std::min(chunk, iters - done);
         for (uint32_t it = 0; it < n_it && rc == MON_OK; ++it) {
             int n = 0;
-            rc = enqueue_iteration(o, b, false, &n, &ev[(size_t)it * (MON_N_STAGES + 1)]);
+            rc = enqueue_iteration(o, b, false, &n, &ev[(size_t)it * (MON_N_STAGES + 1)], fused);
             if (rc == MON_OK) o->launches += (uint64_t)n;
         }
         if (rc != MON_OK) break;
+        cudaMemcpyAsync(o->h_live, o->live_cnt, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, o->stream);
         cudaError_t e = cudaStreamSynchronize(o->stream);
         if (e != cudaSuccess) { rc = fail(MON_ERR_CUDA, "profiled iterations: %s", cudaGetErrorString(e)); break; }
         for (uint32_t it = 0; it < n_it; ++it)
@@ -1382,7 +1443,8 @@ int mon_object_train_injected(mon_object* o, const float* sample_xy, const float
     const MonBatch b = make_batch(o, true, true);
     int n = 0;
     CK(cudaEventRecord(o->ev0, o->stream));
-    rc = enqueue_iteration(o, b, true, &n);
+    // the parity hooks run the chain with the scatter kernel; MON_SCATTER_FUSED=1 (tests) puts the fused form under them
+    rc = enqueue_iteration(o, b, true, &n, nullptr, o->fuse_mode > 0 && o->fuse_supported && !o->occ_bits);
     if (rc != MON_OK) return rc;
     CK(cudaEventRecord(o->ev1, o->stream));
     o->timing_pending = true;

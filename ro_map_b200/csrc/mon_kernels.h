@@ -72,7 +72,8 @@ inline cudaError_t mon_launch_chain(unsigned which, const MonLaunchOpt& lo, void
 }
 
 // kernels_batch.cu
-void mon_launch_generate_batch(const MonBatch& b, const MonScene& sc, cudaStream_t st, const MonLaunchOpt& lo = MonLaunchOpt());
+// slim: the 16 x 256-thread shape that fits beside the hash-encode kernel's CTAs (kernels_batch.cu)
+void mon_launch_generate_batch(const MonBatch& b, const MonScene& sc, cudaStream_t st, const MonLaunchOpt& lo = MonLaunchOpt(), bool slim = false);
 void mon_launch_render_rays(uint32_t n_rays, mon_bbox2d box, const MonScene& sc, const float* Twc_dev, float bgc,
                             MonRay* rays_hit, uint32_t* orig, uint32_t* n_hit, float* rgb, float* depth, float* mask, cudaStream_t st);
 
@@ -96,7 +97,8 @@ void mon_launch_encode_backward(const MonGrid& g, uint32_t n_points, uint32_t re
 
 // kernels_mlp_tc.cu (tcgen05 / TMEM product family)
 cudaError_t mon_launch_mlp_train_tc(const MonBatch& b, const MonLossCfg& lc, uint32_t n_hidden, uint32_t n_mlp,
-                                    uint32_t n_ctas, cudaStream_t st, const MonLaunchOpt& lo = MonLaunchOpt());
+                                    uint32_t n_ctas, cudaStream_t st, const MonLaunchOpt& lo = MonLaunchOpt(),
+                                    const MonGrid* fuse_grid = nullptr, __half* gh_grid = nullptr);   // fuse_grid: scatter the grid gradients in-kernel
 cudaError_t mon_launch_mlp_infer_tc(uint32_t n_points, uint32_t n_hidden, const __half* params, const __half* enc,
                                     float* out4, cudaStream_t st);
 cudaError_t mon_launch_mlp_render_tc(uint32_t n_rays, uint32_t S2, uint32_t n_hidden, const MonRay* rays, const int* in_box, const float* jitter,
@@ -119,6 +121,6 @@ bool mon_scatter_resident_supported(const MonGrid& g);   // power-of-two tables 
 void mon_scatter_resident_pieces_host(const MonGrid& g, uint32_t n_live, uint32_t n_ctas, uint32_t* out4);
 cudaError_t mon_launch_scatter(const MonGrid& g, uint32_t n_points, uint32_t min_live, const uint32_t* live_cnt, const float* pts_c,
                                const uint32_t* genc, const MonCtrl* ctrl, __half* gcls, __half* gh_grid, uint32_t sm_count, cudaStream_t st,
-                               const MonLaunchOpt& lo = MonLaunchOpt());
+                               const MonLaunchOpt& lo = MonLaunchOpt(), bool leave_spare_sms = false);
 void mon_launch_snapshot_grad(uint32_t n, uint32_t n_mlp, uint32_t n_partials, const __half* gh, const float* partials,
                               float* out, cudaStream_t st, const MonGrid& grid, const __half* gcls);

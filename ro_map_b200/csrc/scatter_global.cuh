@@ -36,18 +36,11 @@ __device__ __forceinline__ void red_add_f16x2_pair(void* addr8, __half2 lo, __ha
                  "r"(*reinterpret_cast<const uint32_t*>(&hi)) : "memory");
 }
 
-// Zero d_enc pairs (samples after the early stop) are skipped: adding +0 is an identity, so the result is unchanged.
-// one (sample, level): grad[idx_c] += half2(d_enc * w_c) over the 8 corners.  gwj = the level's two fp16 gradients.
-__device__ __forceinline__ void scatter_level(const MonGrid& g, uint32_t l, uint32_t gwj, const float (&u)[3], __half* __restrict__ grid_grad) {
-            const float g0 = __half2float(__ushort_as_half((unsigned short)(gwj & 0xffffu)));
-            const float g1 = __half2float(__ushort_as_half((unsigned short)(gwj >> 16)));
-            const uint32_t size = g.size[l];
-            char* tab = reinterpret_cast<char*>(reinterpret_cast<__half2*>(grid_grad) + g.offset[l]);
-            if ((size & (size - 1)) == 0) {
+// one (sample, level) on a power-of-two table, the level's constants as scalars (the caller may hold them in registers: the fused MLP
+// kernel's lanes own one level each for the whole kernel).  tab = the level's slice of the entry-ordered gradient table.
+__device__ __forceinline__ void scatter_level_pow2(float scale, uint32_t res, bool hashed, uint32_t size, char* __restrict__ tab,
+                                                   float g0, float g1, const float (&u)[3]) {
                 // same index arithmetic as the forward kernel, directly in byte offsets of the 4-byte entries
-                const float scale = g.scale[l];
-                const uint32_t res = g.res[l];
-                const bool hashed = g.hashed[l] != 0;
                 const uint32_t bmask = 4u * size - 4u;
                 float fr[3]; uint32_t cell[3];
                 mon_pos_fract(u[0], scale, fr[0], cell[0]);
@@ -86,6 +79,17 @@ __device__ __forceinline__ void scatter_level(const MonGrid& g, uint32_t l, uint
                         red_add_f16x2(reinterpret_cast<__half2*>(tab + off), v);
                     }
                 }
+}
+
+// Zero d_enc pairs (samples after the early stop) are skipped: adding +0 is an identity, so the result is unchanged.
+// one (sample, level): grad[idx_c] += half2(d_enc * w_c) over the 8 corners.  gwj = the level's two fp16 gradients.
+__device__ __forceinline__ void scatter_level(const MonGrid& g, uint32_t l, uint32_t gwj, const float (&u)[3], __half* __restrict__ grid_grad) {
+            const float g0 = __half2float(__ushort_as_half((unsigned short)(gwj & 0xffffu)));
+            const float g1 = __half2float(__ushort_as_half((unsigned short)(gwj >> 16)));
+            const uint32_t size = g.size[l];
+            char* tab = reinterpret_cast<char*>(reinterpret_cast<__half2*>(grid_grad) + g.offset[l]);
+            if ((size & (size - 1)) == 0) {
+                scatter_level_pow2(g.scale[l], g.res[l], g.hashed[l] != 0, size, tab, g0, g1, u);
             } else {
                 EncCorner c;
                 level_corners(g, l, u, c);

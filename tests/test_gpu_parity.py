@@ -391,6 +391,55 @@ def test_resident_scatter_against_global_reductions(core, oracle, gpu_dataset, s
         g.close()
 
 
+def test_scatter_fused_into_the_mlp_kernel(core, oracle, gpu_dataset, small_seq, monkeypatch):
+    """Steady-state graph variant: no scatter kernel — the fused MLP kernel issues the hash-grid f16x2 reductions itself, in the last
+    epilogue of every tile (k_mlp_train_tc<NH, FUSE>, the warp's live samples x 16 levels spread over its lanes).  Same reductions
+    as the stand-alone global-reduction path, so: stage by stage against the oracle with the fused form under the parity hooks
+    (MON_SCATTER_FUSED=1), whole iterations against the unfused chain, and an object left to itself switches to the variant
+    without a scatter kernel once its live-sample count has fallen below the threshold (one kernel less per iteration)."""
+    seq, obj = small_seq, small_seq.objects[0]
+    monkeypatch.setenv("MON_SCATTER_FUSED", "1")
+    check_one_iteration_stage_by_stage(core, oracle, gpu_dataset, seq, obj, 512, 1)
+    check_one_iteration_stage_by_stage(core, oracle, gpu_dataset, seq, obj, 256, 2)
+    cfg = core.default_config(rays_per_batch=1024)
+    bmin, bmax = -1.1 * obj.half, 1.1 * obj.half
+    a = core.NerfObject(gpu_dataset, cfg, obj.Tow, bmin, bmax, obj.instance_id)      # always fused (read at creation)
+    monkeypatch.setenv("MON_SCATTER_FUSED", "-1")
+    monkeypatch.setenv("MON_SCATTER_RESIDENT_MIN", "-1")
+    b = core.NerfObject(gpu_dataset, cfg, obj.Tow, bmin, bmax, obj.instance_id)      # never fused, global reductions in the scatter kernel
+    monkeypatch.delenv("MON_SCATTER_FUSED")
+    monkeypatch.delenv("MON_SCATTER_RESIDENT_MIN")
+    c = core.NerfObject(gpu_dataset, cfg, obj.Tow, bmin, bmax, obj.instance_id)      # default: by the live count
+    for g in (a, b, c):
+        g.set_bboxes(obj.boxes)
+    l0 = a.launch_count
+    a.train(1)
+    assert a.launch_count - l0 == 5                            # B P E M O
+    l0 = b.launch_count
+    b.train(1)
+    assert b.launch_count - l0 == 6                            # B P E M S O
+    ma, mb = a.state("master"), b.state("master")
+    assert (a.state("param_steps") == b.state("param_steps")).mean() >= 0.999
+    assert (np.abs(ma - mb) <= 1e-6).mean() >= 0.999
+    assert np.array_equal(ma[:a.n_mlp], mb[:a.n_mlp])
+    la, lb = a.train(70), b.train(70)
+    assert a.step == b.step == 71
+    assert abs(la - lb) <= 0.03 * abs(lb) + 1e-4, (la, lb)
+    ea, eb = a.state("ema"), b.state("ema")
+    assert np.linalg.norm(ea - eb) <= 0.05 * np.linalg.norm(eb)
+    # the default object: a fresh object keeps the scatter kernel (6 launches per iteration), later calls drop it (5)
+    per_call, losses = [], []
+    for _ in range(8):
+        l0 = c.launch_count
+        losses.append(c.train(20))
+        per_call.append((c.launch_count - l0) // 20)
+    assert per_call[0] == 6 and per_call[-1] == 5, per_call
+    assert c.live_fraction * 32768 < 16384
+    assert np.isfinite(losses).all() and losses[-1] < 0.5 * losses[0], losses       # it keeps learning across the switch
+    for g in (a, b, c):
+        g.close()
+
+
 def test_optimizer_bit_exact_for_equal_gradients(core, oracle, gpu_dataset, small_seq):
     """The optimizer's arithmetic is the oracle's bit for bit (IEEE sqrt/div, the bias-correction table filled on the host
     with the reference's sqrtf(1 - powf(b2, s)) / (1 - powf(b1, s)), the fp16 rounding points): wherever the accumulated

@@ -11,3 +11,4 @@ timeout 300 python bench.py --steps 20 --warmup 5 --no-secondary > $OUT/${TAG}_b
 head -c 400 $OUT/${TAG}_bench_20_5.json; echo
 python tools/quick_rate.py 2>&1 | tail -1
 python tools/quick_rate.py --rays 1024 --hidden-layers 2 2>&1 | tail -1
+timeout 200 python tools/tc_phase_times.py > $OUT/${TAG}_mlp_phase_times.txt 2>&1; tail -42 $OUT/${TAG}_mlp_phase_times.txt | cut -c1-150

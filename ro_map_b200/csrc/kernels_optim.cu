@@ -122,6 +122,9 @@ __device__ __forceinline__ GridQuad load_grid_quad(uint32_t i4, const MonOpt& o,
     return q;
 }
 
+// Measured and dropped (profiles/r9e_timeline_optspec.txt): two quads per trip with every load of both — the state Adam needs
+// included — issued before the first use, 3 CTAs per SM at 80 registers: 15.3 instead of 13.4 us.  The sweep is bound by the bytes
+// it moves through L2 (46 B per touched parameter: 6.3 TB/s for a fresh object), not by the latency of its dependent loads.
 __global__ void __launch_bounds__(OPT_THREADS, OPT_CTAS_PER_SM)
 k_optimizer_sweep(MonOpt o, MonCtrl* __restrict__ ctrl, float* __restrict__ pf, __half* __restrict__ ph,
                   __half* __restrict__ gh, const float* __restrict__ mlp_partials, float* __restrict__ m,
@@ -246,8 +249,9 @@ void mon_launch_optimizer(const MonOpt& o, MonCtrl* ctrl, float* pf, __half* ph,
     const uint32_t grid_quads = (i4_end - i4_begin + OPT_PER_THREAD - 1) / OPT_PER_THREAD;
     // grid part: all CTAs resident at once (OPT_CTAS_PER_SM per SM beside the MLP CTAs) and the same number of trips for every thread
     uint32_t n_grid_ctas = 1u;      // a grid-less launch still needs the (otherwise idle) last CTA that reduces the logged loss
+    const uint32_t per_sm = (uint32_t)OPT_CTAS_PER_SM;
     if (with_grid && grid_quads) {
-        const uint32_t slots = std::max(1u, OPT_CTAS_PER_SM * sm_count > n_mlp_ctas ? OPT_CTAS_PER_SM * sm_count - n_mlp_ctas : 1u);
+        const uint32_t slots = std::max(1u, per_sm * sm_count > n_mlp_ctas ? per_sm * sm_count - n_mlp_ctas : 1u);
         const uint32_t trips = (grid_quads + slots * OPT_THREADS - 1) / (slots * OPT_THREADS);
         n_grid_ctas = (grid_quads + trips * OPT_THREADS - 1) / (trips * OPT_THREADS);
     }

@@ -310,6 +310,7 @@ cudaError_t mon_launch_scatter(const MonGrid& g, uint32_t n_points, uint32_t min
     const cudaError_t prep = mon_once_per_device(prepared, [] {
         // 132 of the SM's 228 KB as shared memory, the rest stays L1: the optimizer sweep follows through a programmatic edge on SMs
         // that keep this split, and with the maximum carve-out its streaming loads had too few L1 lines in flight (27 instead of 16 us)
+        // (the maximum carve-out here changes nothing now that the sweep follows through a plain edge: profiles/r9e_timeline_carve100.txt)
         cudaError_t e = cudaFuncSetAttribute(k_scatter, cudaFuncAttributePreferredSharedMemoryCarveout, 58);
         if (e != cudaSuccess) return e;
         return cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_SMEM_BYTES);

@@ -355,8 +355,9 @@ void mon_encode_pieces_host(const MonGrid& g, uint32_t n_points, uint32_t n_ctas
     }
 }
 
-// interleaved fp16 weights [entry][2] -> planar per level [f0 table | f1 table] (initialisation / set_params; the
-// optimizer sweep keeps both copies current afterwards)
+// interleaved fp16 weights [entry][2] -> planar per level [f0 table | f1 table] (initialisation / set_params).  The planar copy is
+// THE fp16 working copy of the grid from then on: the optimizer sweep reads and updates it alone (the interleaved grid part of the
+// parameter vector is not maintained; k_deplanarize rebuilds it for the state getter)
 __global__ void k_planarize(MonGrid g, uint32_t n_entries, const __half* __restrict__ inter, __half* __restrict__ planar) {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_entries) return;
@@ -366,6 +367,18 @@ __global__ void k_planarize(MonGrid g, uint32_t n_entries, const __half* __restr
     const __half2 v = reinterpret_cast<const __half2*>(inter)[e];
     planar[(size_t)g.offset[l] * 2 + local] = __low2half(v);
     planar[(size_t)g.offset[l] * 2 + size + local] = __high2half(v);
+}
+__global__ void k_deplanarize(MonGrid g, uint32_t n_entries, const __half* __restrict__ planar, __half* __restrict__ inter) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_entries) return;
+    uint32_t l = 0;
+    while (l + 1 < g.n_levels && e >= g.offset[l + 1]) ++l;
+    const uint32_t local = e - g.offset[l], size = g.size[l];
+    reinterpret_cast<__half2*>(inter)[e] = __halves2half2(planar[(size_t)g.offset[l] * 2 + local], planar[(size_t)g.offset[l] * 2 + size + local]);
+}
+void mon_launch_deplanarize(const MonGrid& g, const __half* planar, __half* inter, cudaStream_t st) {
+    const uint32_t n = g.offset[g.n_levels];
+    k_deplanarize<<<(n + 255) / 256, 256, 0, st>>>(g, n, planar, inter);
 }
 void mon_launch_planarize(const MonGrid& g, const __half* inter, __half* planar, cudaStream_t st) {
     const uint32_t n = g.offset[g.n_levels];

@@ -87,17 +87,20 @@ struct GridQuad {
 };
 
 __device__ __forceinline__ GridQuad load_grid_quad(uint32_t i4, const MonOpt& o, const MonGrid& grid, __half* __restrict__ gh, __half* __restrict__ gcls,
-                                                    bool resident, const __half* __restrict__ ph, const __half* __restrict__ ema, __half* __restrict__ planar) {
+                                                    bool resident, const __half* __restrict__ ema, __half* __restrict__ planar) {
     GridQuad q;
-    q.wraw = *reinterpret_cast<const uint2*>(ph + i4);
     q.eraw = *reinterpret_cast<const uint2*>(ema + i4);
-    // planar copy read by the hash-encode kernel: level l holds [feature 0 | feature 1]; entries e, e+1 are
-    // adjacent in both feature arrays (level sizes are multiples of 8, so a pair never straddles a level)
+    // planar copy read by the hash-encode kernel — the one fp16 working copy of the grid: level l holds [feature 0 | feature 1];
+    // entries e, e+1 are adjacent in both feature arrays (level sizes are multiples of 8, so a pair never straddles a level)
     const uint32_t e = (i4 - o.n_mlp) >> 1;
     const uint32_t l = level_of_entry(grid, e);
     const uint32_t e_local = e - grid.offset[l];
     q.planar_f0 = planar + (size_t)grid.offset[l] * 2 + e_local;
     q.planar_stride = grid.size[l];
+    {
+        const uint32_t f0 = *reinterpret_cast<const uint32_t*>(q.planar_f0), f1 = *reinterpret_cast<const uint32_t*>(q.planar_f0 + q.planar_stride);
+        q.wraw = make_uint2(__byte_perm(f0, f1, 0x5410), __byte_perm(f0, f1, 0x7632));     // (e.f0, e.f1), (e+1.f0, e+1.f1)
+    }
     if (!resident) {
         // entry-ordered table filled by the global f16x2 reductions
         uint2* gw = reinterpret_cast<uint2*>(gh + i4);
@@ -128,7 +131,7 @@ __device__ __forceinline__ GridQuad load_grid_quad(uint32_t i4, const MonOpt& o,
 __global__ void __launch_bounds__(OPT_THREADS, OPT_CTAS_PER_SM)
 k_optimizer_sweep(MonOpt o, MonCtrl* __restrict__ ctrl, float* __restrict__ pf, __half* __restrict__ ph,
                   __half* __restrict__ gh, const float* __restrict__ mlp_partials, float* __restrict__ m,
-                  float* __restrict__ v, uint32_t* __restrict__ ps, __half* __restrict__ ema,
+                  float* __restrict__ v, uint16_t* __restrict__ ps, __half* __restrict__ ema,
                   const float* __restrict__ loss, uint32_t R, MonGrid grid, __half* __restrict__ planar,
                   uint32_t n_mlp_ctas, uint32_t do_loss, uint32_t grid_i4_begin, uint32_t grid_i4_end,
                   __half* __restrict__ gcls, const uint32_t* __restrict__ live_cnt, uint32_t resident_min_live) {
@@ -188,12 +191,12 @@ k_optimizer_sweep(MonOpt o, MonCtrl* __restrict__ ctrl, float* __restrict__ pf, 
     const uint32_t stride = (gridDim.x - n_mlp_ctas) * OPT_THREADS * OPT_PER_THREAD;
     uint32_t i4 = grid_i4_begin + ((blockIdx.x - n_mlp_ctas) * OPT_THREADS + threadIdx.x) * OPT_PER_THREAD;
     if (i4 >= grid_i4_end) return;
-    GridQuad cur = load_grid_quad(i4, o, grid, gh, gcls, resident, ph, ema, planar);
+    GridQuad cur = load_grid_quad(i4, o, grid, gh, gcls, resident, ema, planar);
     while (true) {
         const uint32_t i4n = i4 + stride;
         const bool more = i4n < grid_i4_end;
         GridQuad nxt;
-        if (more) nxt = load_grid_quad(i4n, o, grid, gh, gcls, resident, ph, ema, planar);
+        if (more) nxt = load_grid_quad(i4n, o, grid, gh, gcls, resident, ema, planar);
         optim_quad(o, lr_base, old_db, new_db, false, i4, cur.g, cur.wraw, cur.eraw, ptrs, cur.planar_f0, cur.planar_stride);
         if (!more) break;
         cur = nxt; i4 = i4n;
@@ -233,7 +236,7 @@ void mon_launch_cast_params(uint32_t n, const float* pf, __half* ph, cudaStream_
     k_cast_params<<<(n + 255) / 256, 256, 0, st>>>(n, pf, ph);
 }
 void mon_launch_optimizer(const MonOpt& o, MonCtrl* ctrl, float* pf, __half* ph, __half* gh, const float* partials,
-                          float* m, float* v, uint32_t* ps, __half* ema, const float* loss, uint32_t R, const MonGrid& grid,
+                          float* m, float* v, uint16_t* ps, __half* ema, const float* loss, uint32_t R, const MonGrid& grid,
                           __half* planar, cudaStream_t st, int part, uint32_t level_begin, uint32_t level_end, const MonLaunchOpt& lo,
                           __half* gcls, const uint32_t* live_cnt, uint32_t resident_min_live, uint32_t sm_count) {
     // part: MON_OPT_ALL everything (MLP weights + loss + whole grid); MON_OPT_MLP the MLP weights and the logged loss only;

@@ -271,7 +271,7 @@ struct mon_object {
     // parameters + optimizer state
     float *pf = nullptr, *m = nullptr, *v = nullptr;
     __half *ph = nullptr, *gh = nullptr, *ema = nullptr;
-    uint32_t* ps = nullptr;
+    uint16_t* ps = nullptr;       // per-parameter Adam step counters, 16 bits, saturating (optim_math.cuh)
     // control
     MonCtrl* ctrl_state = nullptr; // persistent counters (iter, step, n_boxes), advanced by the batch kernels
     MonCtrl* ctrl = nullptr;       // control block of the current iteration, written by its batch kernel
@@ -1094,7 +1094,7 @@ int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uin
         if (e_ != cudaSuccess) { mon_object_destroy(o); return fail(MON_ERR_CUDA, "object allocation (%zu B): %s", (size_t)(bytes), cudaGetErrorString(e_)); } \
     } while (0)
     const size_t P = o->P, R = o->R, N = o->N;
-    OALLOC(o->pf, P * 4); OALLOC(o->m, P * 4); OALLOC(o->v, P * 4); OALLOC(o->ps, P * 4);
+    OALLOC(o->pf, P * 4); OALLOC(o->m, P * 4); OALLOC(o->v, P * 4); OALLOC(o->ps, P * 2 + 16);
     OALLOC(o->ph, P * 2 + 16); OALLOC(o->gh, P * 2 + 16); OALLOC(o->ema, P * 2 + 16);
     OALLOC(o->ctrl_state, sizeof(MonCtrl)); OALLOC(o->ctrl, 2 * sizeof(MonCtrl)); OALLOC(o->ctrl_late, sizeof(MonCtrl));
     // two batch sets (rays, targets, control block, sample positions): inside the iteration graphs the batch of iteration i + 1 is
@@ -1464,6 +1464,10 @@ __global__ void k_half_to_float(size_t n, const __half* __restrict__ in, float* 
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = __half2float(in[i]);
 }
+__global__ void k_u16_to_float(size_t n, const uint16_t* __restrict__ in, float* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i];
+}
 __global__ void k_u32_to_float(size_t n, const uint32_t* __restrict__ in, float* __restrict__ out) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (float)in[i];
@@ -1527,7 +1531,7 @@ __global__ void k_extract_sigma(size_t n, const float* __restrict__ out4, float*
 }
 
 // copies n values of a device array to the host as float, converting on the device
-int fetch_as_float(mon_object* o, const void* src, int kind /*0 f32 1 f16 2 u32 3 u8*/, size_t n, float* out) {
+int fetch_as_float(mon_object* o, const void* src, int kind /*0 f32 1 f16 2 u32 3 u8 4 u16*/, size_t n, float* out) {
     if (n == 0) return MON_OK;
     float* tmp = nullptr;
     const float* from = nullptr;
@@ -1538,6 +1542,7 @@ int fetch_as_float(mon_object* o, const void* src, int kind /*0 f32 1 f16 2 u32 
         const unsigned blocks = (unsigned)((n + 255) / 256);
         if (kind == 1) k_half_to_float<<<blocks, 256, 0, o->stream>>>(n, static_cast<const __half*>(src), tmp);
         else if (kind == 2) k_u32_to_float<<<blocks, 256, 0, o->stream>>>(n, static_cast<const uint32_t*>(src), tmp);
+        else if (kind == 4) k_u16_to_float<<<blocks, 256, 0, o->stream>>>(n, static_cast<const uint16_t*>(src), tmp);
         else k_u8_to_float<<<blocks, 256, 0, o->stream>>>(n, static_cast<const uint8_t*>(src), tmp);
         o->launches += 1;
         from = tmp;
@@ -1556,14 +1561,18 @@ int mon_object_get_state(mon_object* o, int which, float* out, size_t n) {
     CK(cudaSetDevice(o->ds->gpu));
     switch (which) {
         case 0: return fetch_as_float(o, o->pf, 0, n, out);
-        case 1: return fetch_as_float(o, o->ph, 1, n, out);
+        case 1:
+            // the interleaved grid part is rebuilt from the planar working copy (the sweep maintains only that one)
+            mon_launch_deplanarize(o->grid, o->ph_planar, o->ph + o->n_mlp, o->stream);
+            o->launches += 1;
+            return fetch_as_float(o, o->ph, 1, n, out);
         case 2: return fetch_as_float(o, o->ema, 1, n, out);
         case 3:
             if (!o->have_injected) return fail(MON_ERR_STATE, "the gradient snapshot exists only after mon_object_train_injected");
             return fetch_as_float(o, o->grad_snap, 0, n, out);
         case 4: return fetch_as_float(o, o->m, 0, n, out);
         case 5: return fetch_as_float(o, o->v, 0, n, out);
-        case 6: return fetch_as_float(o, o->ps, 2, n, out);
+        case 6: return fetch_as_float(o, o->ps, 4, n, out);
     }
     return fail(MON_ERR_ARG, "unknown state selector %d", which);
 }

@@ -89,6 +89,7 @@ cudaError_t mon_launch_encode_forward(const MonGrid& g, uint32_t n_points, const
                                       uint32_t level_end = 0xffffffffu, const MonLaunchOpt& lo = MonLaunchOpt(),
                                       const uint32_t* occ_list = nullptr, const uint32_t* occ_count = nullptr);   // opt-in: encode the listed samples only
 void mon_launch_planarize(const MonGrid& g, const __half* inter, __half* planar, cudaStream_t st);
+void mon_launch_deplanarize(const MonGrid& g, const __half* planar, __half* inter, cudaStream_t st);   // the inverse (state getter)
 void mon_encode_pieces_host(const MonGrid& g, uint32_t n_points, uint32_t n_ctas, uint32_t level_begin, uint32_t level_end, uint32_t* out4);
 // stand-alone gradient scatter with global f16x2 reductions over the compacted live samples: configurations the unified kernel
 // (kernels_scatter_smem.cu) does not cover; returns at once in iterations with >= resident_min_live live samples
@@ -109,7 +110,7 @@ cudaError_t mon_launch_mlp_render_tc(uint32_t n_rays, uint32_t S2, uint32_t n_hi
 void mon_launch_init_grid(uint64_t state, uint64_t inc, uint32_t n, float* out, cudaStream_t st);
 void mon_launch_cast_params(uint32_t n, const float* pf, __half* ph, cudaStream_t st);
 void mon_launch_optimizer(const MonOpt& o, MonCtrl* ctrl, float* pf, __half* ph, __half* gh, const float* partials,
-                          float* m, float* v, uint32_t* ps, __half* ema, const float* loss, uint32_t R, const MonGrid& grid,
+                          float* m, float* v, uint16_t* ps, __half* ema, const float* loss, uint32_t R, const MonGrid& grid,
                           __half* planar, cudaStream_t st, int part = 0, uint32_t level_begin = 0, uint32_t level_end = 0xffffffffu,
                           const MonLaunchOpt& lo = MonLaunchOpt(), __half* gcls = nullptr, const uint32_t* live_cnt = nullptr,
                           uint32_t resident_min_live = 0xffffffffu, uint32_t sm_count = 148);

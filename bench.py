@@ -47,7 +47,7 @@ FLOPS_MLP_TRAIN_PER_POINT = {1: 18432, 2: 43008}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of each kernel from the committed ncu --set full captures
 # (profiles/, one hidden layer, R = 4096).  ncu flushes the caches before every replayed launch: COLD-cache figures; in
 # the running job the ~50 MB of per-object state stay L2-resident between kernels.  None = not captured for this build.
-TRAFFIC_NCU_FILE = ROOT / "profiles" / "r8_traffic.json"   # written by tools/ncu_summary.py --traffic from the committed ncu --set full captures
+TRAFFIC_NCU_FILE = ROOT / "profiles" / "r9_traffic.json"   # written by tools/ncu_summary.py --traffic from the committed ncu --set full captures
 
 
 def parse():

@@ -2,8 +2,8 @@
 # Round-2 evidence in one gpurun call (B200 x1): GPU tests, both bench arms at the driver's shape and at the default, ncu launch
 # list of the driver-shaped command, ncu --set full of one fresh-object iteration and one steady-state iteration, device timelines,
 # stage times incl. the scatter paths' crossover, the C++ facade runs (configs 3 and 5).  Everything lands in gpurun_out/<tag>_*.
-#   gpurun --timeout 2400 -- 'bash tools/gpu_round2.sh r6'
-TAG=${1:-r6}
+#   gpurun --timeout 2400 -- 'bash tools/gpu_round2.sh r9'
+TAG=${1:-r9}
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_smi.txt 2>&1

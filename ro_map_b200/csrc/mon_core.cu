@@ -34,6 +34,7 @@
 
 #define MON_DEBIAS_LUT 32768  // steps covered by the Adam bias-correction table (offline jobs run 5000 iterations)
 #define MON_FRAMES_PER_SLAB 32
+#define MON_FUSE_BELOW 20480u          // live samples below which a call takes the graphs without a scatter kernel (measured crossover 20-21 k: profiles/r9g_fuse_threshold.txt)
 #define MON_RESIDENT_MIN_LIVE 16384u   // live samples from which the shared-memory resident scatter takes an iteration (measured crossover)
 #define MON_GRAPH_CHUNK 64   // longest captured graph: a call of n iterations replays one chunk length that divides n (32..64) where
                              // there is one — 500 = 10 x 50, a single graph to instantiate — else n / 64 graphs of 64 + one of exactly n % 64
@@ -320,6 +321,7 @@ struct mon_object {
     // 8-byte asynchronous read-back at the end of every call; a hint, never waited for).  fuse_mode: 0 = by the live count,
     // 1 = always, -1 = never (MON_SCATTER_FUSED: A/B measurements and tests).
     int fuse_mode = 0;
+    uint32_t fuse_below = MON_FUSE_BELOW;
     bool fuse_supported = false;
     uint32_t* h_live = nullptr;       // pinned [2]; 0xffffffff until the first read-back has landed
     // opt-in occupancy grid (mon_object_set_occupancy; off: occ_res == 0).  The density grid is the running maximum (decayed) of
@@ -914,7 +916,8 @@ static bool use_fused(const mon_object* o) {
     if (!o->fuse_supported || o->occ_bits || o->fuse_mode < 0) return false;
     if (o->fuse_mode > 0) return true;
     const uint32_t a = reinterpret_cast<volatile uint32_t*>(o->h_live)[0], b = reinterpret_cast<volatile uint32_t*>(o->h_live)[1];
-    return std::max(a, b) < std::min<uint32_t>(o->resident_min_live, MON_RESIDENT_MIN_LIVE);
+    if (o->resident_min_live == 0u) return false;      // MON_SCATTER_RESIDENT_MIN=0 (tests): always the resident scatter kernel
+    return std::max(a, b) < o->fuse_below;
 }
 
 // serial version (injected / profiled iterations).  ev (optional, MON_N_STAGES+1 events): recorded before each
@@ -1119,6 +1122,7 @@ int mon_object_create(mon_dataset* ds, const mon_config* cfg, uint32_t seed, uin
     if (!mon_scatter_resident_supported(grid)) { o->resident_min_live = 0xffffffffu; o->scatter_unified = false; }
     o->fuse_supported = o->scatter_unified;        // power-of-two tables (scatter_level_pow2)
     if (const char* env = getenv("MON_SCATTER_FUSED")) o->fuse_mode = atoi(env);
+    if (const char* env = getenv("MON_SCATTER_FUSED_BELOW")) o->fuse_below = (uint32_t)atol(env);
     if ((e = cudaMallocHost(&o->h_live, 2 * sizeof(uint32_t))) == cudaSuccess) o->h_live[0] = o->h_live[1] = 0xffffffffu;
     if (e != cudaSuccess ||
         (e = cudaMallocHost(&o->h_ctrl, sizeof(MonCtrl))) != cudaSuccess ||

@@ -191,6 +191,22 @@ int mon_object_density_grid(mon_object* obj, const uint32_t res[3], float* out);
  * compute_mesh_vertex_colors queries them (nerf_model.cu:2045-2067).  use_ema = 1: inference weights. */
 int mon_object_query_points(mon_object* obj, const float* points_unit, uint32_t n, int use_ema, float* out4);
 
+/* GenerateMesh as a whole (nerf_model.cu:1993-2043): GetDensityOnGrid + MarchingCubes + compute_mesh_1ring (marching_cubes.cu:41-510)
+ * + compute_mesh_vertex_colors (:2045-2067) on the GPU.  res^3 lattice over the object's box (the reference: 64), iso-value thresh on
+ * the raw density logit (the reference: 2.0), EMA weights.  Vertex and triangle slots come from exclusive scans over the lattice
+ * instead of the reference's atomicAdd race: the order is the lattice order (x fastest; per point the +x, +y, +z edge; per cell the
+ * table's triangle order), reproducible.  The vertex count is padded to a multiple of 128 with zero vertices like the reference's
+ * (:499).  The mesh stays in device memory; mon_mesh_counts sizes the caller's arrays, mon_mesh_read copies out verts [n_verts][3],
+ * unit 1-ring normals [n_verts][3], u8 colours [n_verts][3], indices [n_indices] (the reference's internal winding; its PLY writer
+ * reverses it); any of the four may be NULL. */
+typedef struct mon_mesh mon_mesh;
+int mon_object_extract_mesh(mon_object* obj, uint32_t res, float thresh, mon_mesh** out);
+/* the same surface extraction on a caller's lattice (host memory, [z][y][x], box bmin..bmax); colours are zero */
+int mon_mesh_from_lattice(int gpu, const float* sigma, uint32_t res, const float bmin[3], const float bmax[3], float thresh, mon_mesh** out);
+int mon_mesh_counts(const mon_mesh* mesh, uint32_t* n_verts, uint32_t* n_surface_verts, uint32_t* n_indices);
+int mon_mesh_read(const mon_mesh* mesh, float* verts, float* normals, uint8_t* colors, uint32_t* indices);
+int mon_mesh_destroy(mon_mesh* mesh);
+
 /* ---- parity / test hooks ------------------------------------------------------------------- */
 /* One training iteration with host-provided random numbers instead of the internal generator:
  * sample_xy[2R], rand_colors[3R], rand_dt[R*S], all in (0,1] like curandGenerateUniform

@@ -88,6 +88,11 @@ SIGNATURES = {
     "mon_object_render_object_centric": (C.c_int, [_vp, Bbox2d, _f32p, C.c_int, _vp, _vp, _vp, _vp]),
     "mon_object_density_grid": (C.c_int, [_vp, _P(C.c_uint32), _vp]),
     "mon_object_query_points": (C.c_int, [_vp, _vp, C.c_uint32, C.c_int, _vp]),
+    "mon_object_extract_mesh": (C.c_int, [_vp, C.c_uint32, C.c_float, _P(_vp)]),
+    "mon_mesh_from_lattice": (C.c_int, [C.c_int, _vp, C.c_uint32, _f32p, _f32p, C.c_float, _P(_vp)]),
+    "mon_mesh_counts": (C.c_int, [_vp, _P(C.c_uint32), _P(C.c_uint32), _P(C.c_uint32)]),
+    "mon_mesh_read": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "mon_mesh_destroy": (C.c_int, [_vp]),
     "mon_object_train_injected": (C.c_int, [_vp, _vp, _vp, _vp, _f32p, _P(C.c_uint32)]),
     "mon_object_get_state": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t]),
     "mon_object_set_params": (C.c_int, [_vp, _vp, C.c_size_t]),

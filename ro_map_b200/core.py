@@ -83,6 +83,31 @@ def make_boxes(rows) -> "C.Array[Bbox2d]":
     return arr
 
 
+def _read_mesh(lib, h) -> dict:
+    try:
+        nv, ns, ni = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+        check(lib.mon_mesh_counts(h, C.byref(nv), C.byref(ns), C.byref(ni)))
+        verts, normals = np.zeros((nv.value, 3), np.float32), np.zeros((nv.value, 3), np.float32)
+        colors, idx = np.zeros((nv.value, 3), np.uint8), np.zeros(ni.value, np.uint32)
+        check(lib.mon_mesh_read(h, _ptr(verts), _ptr(normals), _ptr(colors), _ptr(idx)))
+        return {"verts": verts, "normals": normals, "colors": colors, "indices": idx, "n_surface": ns.value}
+    finally:
+        lib.mon_mesh_destroy(h)
+
+
+def mesh_from_lattice(sigma_zyx: np.ndarray, bmin, bmax, thresh: float = 2.0, gpu: int = 0) -> dict:
+    """Marching cubes of the core (csrc/kernels_mesh.cu) on a caller's cubic lattice [z][y][x]."""
+    lib = _capi.load()
+    sig = np.ascontiguousarray(sigma_zyx, dtype=np.float32)
+    res = sig.shape[0]
+    if sig.shape != (res, res, res):
+        raise ValueError("cubic lattice expected")
+    lo, hi = _f32(bmin, (3,)), _f32(bmax, (3,))
+    h = C.c_void_p()
+    check(lib.mon_mesh_from_lattice(gpu, _ptr(sig), res, lo.ctypes.data_as(C.POINTER(C.c_float)), hi.ctypes.data_as(C.POINTER(C.c_float)), float(thresh), C.byref(h)))
+    return _read_mesh(lib, h)
+
+
 class Dataset:
     def __init__(self, gpu: int, fx: float, fy: float, cx: float, cy: float, H: int, W: int, max_frames: int, use_depth: bool):
         self._lib = _capi.load()
@@ -275,6 +300,12 @@ class NerfObject:
         out = np.empty((res[2], res[1], res[0]), np.float32)  # x fastest
         check(self._lib.mon_object_density_grid(self._h, r, _ptr(out)))
         return out
+
+    def extract_mesh(self, res: int = 64, thresh: float = 2.0) -> dict:
+        """GenerateMesh on the GPU: verts / normals [n, 3] (n padded to a multiple of 128), u8 colors [n, 3], indices, n_surface."""
+        h = C.c_void_p()
+        check(self._lib.mon_object_extract_mesh(self._h, int(res), float(thresh), C.byref(h)))
+        return _read_mesh(self._lib, h)
 
     def query_points(self, points_unit, use_ema: bool = True) -> np.ndarray:
         """Network logits (r, g, b, sigma) at unit-cube positions [n, 3]."""

@@ -1809,6 +1809,157 @@ int mon_object_density_grid(mon_object* o, const uint32_t res[3], float* out) {
     return MON_OK;
 }
 
+// ------------------------------------------------------------------------------- mesh extraction on the GPU (kernels_mesh.cu)
+// GenerateMesh (nerf_model.cu:1993-2043) = GetDensityOnGrid + MarchingCubes + compute_mesh_1ring + compute_mesh_vertex_colors, all on
+// the device: density lattice (EMA weights) -> count + exclusive scans -> vertices / indices / 1-ring normals -> the network's rgb at
+// the vertices.  The result stays on the device until mon_mesh_read.
+struct mon_mesh {
+    int gpu = 0;
+    uint32_t n_verts = 0, n_surface = 0, n_indices = 0;
+    float *verts = nullptr, *normals = nullptr;
+    uint8_t* colors = nullptr;
+    uint32_t* indices = nullptr;
+};
+
+int mon_mesh_destroy(mon_mesh* m) {
+    if (!m) return MON_OK;
+    cudaSetDevice(m->gpu);
+    // pool memory, complete when the mesh was handed out: released stream-ordered on the thread's own stream (a plain cudaFree is
+    // a device-wide synchronisation and would stall every training stream of the GPU)
+    mon_dev_free(m->verts, cudaStreamPerThread); mon_dev_free(m->normals, cudaStreamPerThread);
+    mon_dev_free(m->colors, cudaStreamPerThread); mon_dev_free(m->indices, cudaStreamPerThread);
+    delete m;
+    return MON_OK;
+}
+
+// the iso-surface of a lattice that is already in device memory, on stream st (synchronises once, for the two counts)
+static int mesh_from_device_lattice(int gpu, const float* d_sigma, uint32_t res, const float bmin[3], const float bmax[3], float thresh, cudaStream_t st,
+                                    mon_mesh** out) {
+    const size_t n = (size_t)res * res * res;
+    mon_mesh* m = new mon_mesh();
+    m->gpu = gpu;
+    uint32_t *v_off = nullptr, *i_off = nullptr, *totals = nullptr, *sums = nullptr, *vid = nullptr;
+    auto cleanup = [&](bool all) {
+        mon_dev_free(v_off, st); mon_dev_free(i_off, st); mon_dev_free(totals, st); mon_dev_free(sums, st); mon_dev_free(vid, st);
+        if (all) mon_mesh_destroy(m);
+    };
+    cudaError_t e;
+    if ((e = mon_dev_malloc(reinterpret_cast<void**>(&v_off), n * 4, st)) != cudaSuccess ||
+        (e = mon_dev_malloc(reinterpret_cast<void**>(&i_off), n * 4, st)) != cudaSuccess ||
+        (e = mon_dev_malloc(reinterpret_cast<void**>(&totals), mon_mesh_scan_scratch_words(res) * 4, st)) != cudaSuccess ||
+        (e = mon_dev_malloc(reinterpret_cast<void**>(&sums), 8, st)) != cudaSuccess ||
+        (e = mon_launch_mc_count(d_sigma, res, thresh, v_off, i_off, totals, sums, st)) != cudaSuccess) {
+        cleanup(true);
+        return fail(MON_ERR_CUDA, "marching cubes (count): %s", cudaGetErrorString(e));
+    }
+    uint32_t h_sums[2] = {0, 0};
+    if ((e = cudaMemcpyAsync(h_sums, sums, 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess || (e = cudaStreamSynchronize(st)) != cudaSuccess) {
+        cleanup(true);
+        return fail(MON_ERR_CUDA, "marching cubes (count): %s", cudaGetErrorString(e));
+    }
+    m->n_surface = h_sums[0];
+    m->n_indices = h_sums[1];
+    m->n_verts = (m->n_surface + 127u) & ~127u;      // "round for later nn stuff" (marching_cubes.cu:499): zero vertices
+    const size_t nv = std::max<size_t>(m->n_verts, 1), ni = std::max<size_t>(m->n_indices, 1);
+    if ((e = mon_dev_malloc(reinterpret_cast<void**>(&m->verts), nv * 12, st)) != cudaSuccess ||
+        (e = mon_dev_malloc(reinterpret_cast<void**>(&m->normals), nv * 12, st)) != cudaSuccess ||
+        (e = mon_dev_malloc(reinterpret_cast<void**>(&m->colors), nv * 3, st)) != cudaSuccess ||
+        (e = mon_dev_malloc(reinterpret_cast<void**>(&m->indices), ni * 4, st)) != cudaSuccess ||
+        (e = cudaMemsetAsync(m->colors, 0, nv * 3, st)) != cudaSuccess ||
+        (e = mon_dev_malloc(reinterpret_cast<void**>(&vid), n * 12, st)) != cudaSuccess ||
+        (e = mon_launch_mc_build(d_sigma, res, thresh, bmin, bmax, v_off, i_off, m->n_surface, m->n_verts, m->n_indices, vid, m->verts, m->normals,
+                                 m->indices, st)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(st)) != cudaSuccess) {
+        cleanup(true);
+        return fail(MON_ERR_CUDA, "marching cubes (build): %s", cudaGetErrorString(e));
+    }
+    cleanup(false);
+    *out = m;
+    return MON_OK;
+}
+
+int mon_mesh_from_lattice(int gpu, const float* sigma, uint32_t res, const float bmin[3], const float bmax[3], float thresh, mon_mesh** out) {
+    if (!sigma || !bmin || !bmax || !out) return fail(MON_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    if (res < 2 || res > 512) return fail(MON_ERR_ARG, "resolution must be 2..512");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) { cudaGetLastError(); return fail(MON_ERR_NO_DEVICE, "no CUDA device (this library has no CPU path)"); }
+    if (gpu < 0 || gpu >= n_dev) return fail(MON_ERR_ARG, "gpu %d out of range (0..%d)", gpu, n_dev - 1);
+    CK(cudaSetDevice(gpu));
+    const size_t n = (size_t)res * res * res;
+    cudaStream_t st = nullptr;
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    float* d_sigma = nullptr;
+    cudaError_t e = mon_dev_malloc(reinterpret_cast<void**>(&d_sigma), n * 4, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_sigma, sigma, n * 4, cudaMemcpyHostToDevice, st);
+    int rc = e == cudaSuccess ? mesh_from_device_lattice(gpu, d_sigma, res, bmin, bmax, thresh, st, out) : fail(MON_ERR_CUDA, "lattice upload: %s", cudaGetErrorString(e));
+    mon_dev_free(d_sigma, st);
+    cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+    return rc;
+}
+
+int mon_object_extract_mesh(mon_object* o, uint32_t res, float thresh, mon_mesh** out) {
+    if (!o || !out) return fail(MON_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    if (res < 2 || res > 512) return fail(MON_ERR_ARG, "resolution must be 2..512");
+    CK(cudaSetDevice(o->ds->gpu));
+    cudaStream_t st = o->stream;
+    const size_t n = (size_t)res * res * res;
+    float *pts = nullptr, *out4 = nullptr, *sigma = nullptr;
+    int rc = scratch(o, 1, n * 12, reinterpret_cast<void**>(&pts));
+    if (rc == MON_OK) rc = scratch(o, 2, n * 16, reinterpret_cast<void**>(&out4));
+    if (rc == MON_OK) rc = scratch(o, 3, n * 4, reinterpret_cast<void**>(&sigma));
+    if (rc != MON_OK) return rc;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    k_lattice_points<<<blocks, 256, 0, st>>>(res, res, res, pts);
+    rc = infer_points_device(o, pts, (uint32_t)n, 1, out4, false);      // inference (EMA) weights, like GetDensityOnGrid (:2028)
+    if (rc != MON_OK) return rc;
+    k_extract_sigma<<<blocks, 256, 0, st>>>(n, out4, sigma);
+    o->launches += 2;
+    mon_mesh* m = nullptr;
+    rc = mesh_from_device_lattice(o->ds->gpu, sigma, res, o->scene.bmin, o->scene.bmax, thresh, st, &m);
+    if (rc != MON_OK) return rc;
+    o->launches += 11;
+    if (m->n_verts) {
+        // compute_mesh_vertex_colors (:2045-2067): the network at WarpPoint(vertex) — the padding vertices included, as there
+        float *unit = nullptr, *rgb4 = nullptr;
+        rc = scratch(o, 1, (size_t)m->n_verts * 12, reinterpret_cast<void**>(&unit));
+        if (rc == MON_OK) rc = scratch(o, 2, (size_t)m->n_verts * 16, reinterpret_cast<void**>(&rgb4));
+        if (rc == MON_OK) {
+            mon_launch_mesh_unit_points(m->n_verts, m->verts, o->scene.bmin, o->scene.bmax, unit, st);
+            rc = infer_points_device(o, unit, m->n_verts, 1, rgb4, false);
+        }
+        if (rc == MON_OK) {
+            mon_launch_mesh_colors(m->n_verts, rgb4, m->colors, st);
+            o->launches += 2;
+            const cudaError_t e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) rc = fail(MON_ERR_CUDA, "mesh colours: %s", cudaGetErrorString(e));
+        }
+        if (rc != MON_OK) { mon_mesh_destroy(m); return rc; }
+    }
+    *out = m;
+    return MON_OK;
+}
+
+int mon_mesh_counts(const mon_mesh* m, uint32_t* n_verts, uint32_t* n_surface_verts, uint32_t* n_indices) {
+    if (!m) return fail(MON_ERR_ARG, "mesh is NULL");
+    if (n_verts) *n_verts = m->n_verts;
+    if (n_surface_verts) *n_surface_verts = m->n_surface;
+    if (n_indices) *n_indices = m->n_indices;
+    return MON_OK;
+}
+
+int mon_mesh_read(const mon_mesh* m, float* verts, float* normals, uint8_t* colors, uint32_t* indices) {
+    if (!m) return fail(MON_ERR_ARG, "mesh is NULL");
+    CK(cudaSetDevice(m->gpu));
+    if (verts && m->n_verts) CK(cudaMemcpy(verts, m->verts, (size_t)m->n_verts * 12, cudaMemcpyDeviceToHost));
+    if (normals && m->n_verts) CK(cudaMemcpy(normals, m->normals, (size_t)m->n_verts * 12, cudaMemcpyDeviceToHost));
+    if (colors && m->n_verts) CK(cudaMemcpy(colors, m->colors, (size_t)m->n_verts * 3, cudaMemcpyDeviceToHost));
+    if (indices && m->n_indices) CK(cudaMemcpy(indices, m->indices, (size_t)m->n_indices * 4, cudaMemcpyDeviceToHost));
+    return MON_OK;
+}
+
 // ------------------------------------------------------------------------------- opt-in occupancy grid
 // The reference carries instant-ngp's accelerators as dead code (Step / VolumeRenderGradient with compaction,
 // nerf_model.cu:957-1132,1504-1550; BASELINE north_star: "occupancy-grid ray marching with warp-ballot sample compaction").

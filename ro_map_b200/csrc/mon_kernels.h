@@ -125,3 +125,13 @@ cudaError_t mon_launch_scatter(const MonGrid& g, uint32_t n_points, uint32_t min
                                const MonLaunchOpt& lo = MonLaunchOpt(), bool leave_spare_sms = false);
 void mon_launch_snapshot_grad(uint32_t n, uint32_t n_mlp, uint32_t n_partials, const __half* gh, const float* partials,
                               float* out, cudaStream_t st, const MonGrid& grid, const __half* gcls);
+
+// kernels_mesh.cu: marching cubes on the device (count + exclusive scans, then vertices / faces / 1-ring normals), vertex colours
+size_t mon_mesh_scan_scratch_words(uint32_t res);
+cudaError_t mon_launch_mc_count(const float* sigma, uint32_t res, float thresh, uint32_t* v_off, uint32_t* i_off, uint32_t* totals, uint32_t* sums,
+                                cudaStream_t st);
+cudaError_t mon_launch_mc_build(const float* sigma, uint32_t res, float thresh, const float bmin[3], const float bmax[3], const uint32_t* v_off,
+                                const uint32_t* i_off, uint32_t n_surface, uint32_t n_verts_padded, uint32_t n_indices, uint32_t* vid, float* verts,
+                                float* normals, uint32_t* indices, cudaStream_t st);
+void mon_launch_mesh_unit_points(uint32_t n_verts, const float* verts, const float bmin[3], const float bmax[3], float* unit, cudaStream_t st);
+void mon_launch_mesh_colors(uint32_t n_verts, const float* out4, uint8_t* colors, cudaStream_t st);

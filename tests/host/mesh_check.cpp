@@ -1,4 +1,5 @@
-// mesh_check.cpp — CPU unit check of ro_map_b200/host/mesh.h with the two C-ABI calls it makes replaced by an
+// mesh_check.cpp — CPU unit check of the mesh extraction's CPU statement (tests/host/mesh_cpu.h) and of the PLY writer of
+// ro_map_b200/host/mesh.h, with the two C-ABI calls the CPU statement makes replaced by an
 // analytic field (sigma = 2 + 40 * (0.3 - |p - c|), i.e. the threshold-2.0 surface is a sphere of radius 0.3 in
 // unit-cube coordinates; colour logits encode the position).  Prints facts the pytest asserts on.
 #include <cstdio>
@@ -7,7 +8,7 @@
 #include <string>
 #include <vector>
 
-#include "mesh.h"
+#include "mesh_cpu.h"
 
 static const float C0[3] = {0.5f, 0.45f, 0.55f};
 static bool g_random = false;   // "random": white noise with an empty border — every one of the 256 cell configurations occurs
@@ -23,6 +24,10 @@ static float field(float x, float y, float z) {
 }
 extern "C" {
 const char* mon_last_error(void) { return "stub"; }
+int mon_object_extract_mesh(mon_object*, uint32_t, float, mon_mesh**) { return 1; }
+int mon_mesh_counts(const mon_mesh*, uint32_t*, uint32_t*, uint32_t*) { return 1; }
+int mon_mesh_read(const mon_mesh*, float*, float*, uint8_t*, uint32_t*) { return 1; }
+int mon_mesh_destroy(mon_mesh*) { return 1; }
 int mon_object_density_grid(mon_object*, const uint32_t res[3], float* out) {
     for (uint32_t z = 0; z < res[2]; ++z)
         for (uint32_t y = 0; y < res[1]; ++y)
@@ -45,7 +50,7 @@ int main(int argc, char** argv) {
     const float bmin[3] = {-1.0f, -2.0f, -0.5f}, bmax[3] = {1.0f, 2.0f, 0.5f};
     mesh::Extracted m;
     std::string err;
-    if (!mesh::extract(nullptr, bmin, bmax, res, 2.0f, m, err)) { printf("error %s\n", err.c_str()); return 1; }
+    if (!mesh_cpu::extract(nullptr, bmin, bmax, res, 2.0f, m, err)) { printf("error %s\n", err.c_str()); return 1; }
     const size_t nv = m.n_surface_verts, nf = m.indices.size() / 3, n_padded = m.verts.size() / 3;
     size_t bad_padding = (n_padded % 128 != 0) + (n_padded < nv) + (n_padded >= nv + 128);   // padded to the next multiple of 128 ...
     for (size_t v = nv; v < n_padded; ++v)                                                       // ... with zero vertices and zero normals

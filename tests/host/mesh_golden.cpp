@@ -1,4 +1,4 @@
-// mesh_golden.cpp — runs ro_map_b200/host/mesh.h's marching cubes on a density lattice read from a raw float32 file
+// mesh_golden.cpp — runs the CPU statement of the core's marching cubes (tests/host/mesh_cpu.h) on a density lattice read from a raw float32 file
 // ([z][y][x], res^3 values) and writes vertices / normals / indices as raw arrays for tests/test_golden_romap.py to hold
 // against the reference's own MarchingCubes output (tests/golden/romap_mesh_golden.npz).  CPU only, no C ABI involved.
 #include <cstdio>
@@ -6,12 +6,16 @@
 #include <string>
 #include <vector>
 
-#include "mesh.h"
+#include "mesh_cpu.h"
 
-extern "C" {   // mesh.h names them in extract(); not used here
+extern "C" {   // the headers name them in their extract() functions; not used here
 const char* mon_last_error(void) { return "unused"; }
 int mon_object_density_grid(mon_object*, const uint32_t*, float*) { return 1; }
 int mon_object_query_points(mon_object*, const float*, uint32_t, int, float*) { return 1; }
+int mon_object_extract_mesh(mon_object*, uint32_t, float, mon_mesh**) { return 1; }
+int mon_mesh_counts(const mon_mesh*, uint32_t*, uint32_t*, uint32_t*) { return 1; }
+int mon_mesh_read(const mon_mesh*, float*, float*, uint8_t*, uint32_t*) { return 1; }
+int mon_mesh_destroy(mon_mesh*) { return 1; }
 }
 
 static bool dump(const std::string& path, const void* p, size_t bytes) {
@@ -32,7 +36,7 @@ int main(int argc, char** argv) {
     if (!f || fread(sigma.data(), 4, sigma.size(), f) != sigma.size()) { fprintf(stderr, "cannot read %s\n", argv[1]); return 2; }
     fclose(f);
     mesh::Extracted m;
-    mesh::marching_cubes(sigma.data(), res, bmin, bmax, thresh, m);
+    mesh_cpu::marching_cubes(sigma.data(), res, bmin, bmax, thresh, m);
     const std::string out = argv[10];
     if (!dump(out + ".verts", m.verts.data(), m.verts.size() * 4) || !dump(out + ".normals", m.normals.data(), m.normals.size() * 4) ||
         !dump(out + ".indices", m.indices.data(), m.indices.size() * 4)) return 3;

@@ -182,7 +182,7 @@ def _our_marching_cubes(tmp_path, kind, res):
     import subprocess
     exe = tmp_path / "mesh_golden"
     if not exe.exists():
-        subprocess.run(["g++", "-O2", "-std=c++17", f"-I{ROOT / 'ro_map_b200' / 'host'}", f"-I{ROOT / 'include'}",
+        subprocess.run(["g++", "-O2", "-std=c++17", f"-I{ROOT / 'ro_map_b200' / 'host'}", f"-I{ROOT / 'include'}", f"-I{ROOT / 'tests' / 'host'}",
                         str(ROOT / "tests" / "host" / "mesh_golden.cpp"), "-o", str(exe)], check=True)
     lat = tmp_path / f"{kind}.f32"
     mg.mesh_lattice(kind, res).tofile(lat)
@@ -204,17 +204,10 @@ def _canonical_triangles(verts, idx):
     return rolled.reshape(-1, 9)
 
 
-@pytest.mark.parametrize("kind,res", mg.MESH_CASES)
-def test_marching_cubes_against_reference(tmp_path, kind, res):
-    """(f)1: vertices, triangles and 1-ring normals of the host mesh extraction vs the reference's marching_cubes.cu run on a
-    B200 (vertex and cell order there are atomicAdd races: compared after canonical ordering).  Three lattices: a sphere, white
-    noise, and every one of the 256 cell configurations as an isolated cell.  The triangle table (ro_map_b200/host/mc_table.h) was
-    recovered from these very outputs (tools/derive_mc_table.py) and equals the reference's: bit-identical vertex sets, IDENTICAL
-    triangle sets including the winding, and identical triangle order inside every cell (the index array is a concatenation of
-    per-cell runs in both)."""
+def check_mesh_against_reference(kind, n_surface, v, n, idx):
+    """the assertions of test_marching_cubes_against_reference, shared with the GPU kernels' test (tests/test_gpu_mesh.py)"""
     gold = np.load(MESH_GOLD)
     rv, rn, ri = gold[kind + "_verts"], gold[kind + "_normals"], gold[kind + "_indices"]
-    n_surface, v, n, idx = _our_marching_cubes(tmp_path, kind, res)
     assert len(v) == len(rv) and len(v) % 128 == 0                             # the reference pads the vertex count to a multiple of 128 ...
     used = np.unique(ri)
     assert len(used) == n_surface and not rv[np.setdiff1d(np.arange(len(rv)), used)].any()   # ... with zero vertices
@@ -233,6 +226,19 @@ def test_marching_cubes_against_reference(tmp_path, kind, res):
     na, nb = n[:n_surface][key(v[:n_surface])], rn_u[key(rv[used])]
     nz = np.linalg.norm(rn[used], axis=1)[key(rv[used])] > 1e-12
     assert np.abs(na[nz] - nb[nz]).max() < 2e-3, np.abs(na[nz] - nb[nz]).max()
+
+
+
+
+@pytest.mark.parametrize("kind,res", mg.MESH_CASES)
+def test_marching_cubes_against_reference(tmp_path, kind, res):
+    """(f)1: vertices, triangles and 1-ring normals of the host mesh extraction vs the reference's marching_cubes.cu run on a
+    B200 (vertex and cell order there are atomicAdd races: compared after canonical ordering).  Three lattices: a sphere, white
+    noise, and every one of the 256 cell configurations as an isolated cell.  The triangle table (ro_map_b200/host/mc_table.h) was
+    recovered from these very outputs (tools/derive_mc_table.py) and equals the reference's: bit-identical vertex sets, IDENTICAL
+    triangle sets including the winding, and identical triangle order inside every cell (the index array is a concatenation of
+    per-cell runs in both)."""
+    check_mesh_against_reference(kind, *_our_marching_cubes(tmp_path, kind, res))
 
 
 # ---- A13: Train_Step's loop — the oracle's 30-iteration trajectory against the reference's ---------------------------------

@@ -153,7 +153,7 @@ def test_mesh_extraction_on_analytic_field(tmp_path):
     then white noise (every marching-cubes configuration): consistent winding everywhere; the classic table the reference uses is
     known to leave cracks on faces whose corners alternate, identically in the reference (golden comparison: test_golden_romap.py)."""
     exe = tmp_path / "mesh_check"
-    subprocess.run(["g++", "-O2", "-std=c++17", f"-I{ROOT / 'ro_map_b200' / 'host'}", f"-I{ROOT / 'include'}",
+    subprocess.run(["g++", "-O2", "-std=c++17", f"-I{ROOT / 'ro_map_b200' / 'host'}", f"-I{ROOT / 'include'}", f"-I{ROOT / 'tests' / 'host'}",
                     str(ROOT / "tests" / "host" / "mesh_check.cpp"), "-o", str(exe)], check=True)
     for res, r_tol in ((64, 1e-3), (17, 1e-2)):
         ply = tmp_path / f"s{res}.ply"

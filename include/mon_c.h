@@ -198,7 +198,7 @@ int mon_object_query_points(mon_object* obj, const float* points_unit, uint32_t 
  * table's triangle order), reproducible.  The vertex count is padded to a multiple of 128 with zero vertices like the reference's
  * (:499).  The mesh stays in device memory; mon_mesh_counts sizes the caller's arrays, mon_mesh_read copies out verts [n_verts][3],
  * unit 1-ring normals [n_verts][3], u8 colours [n_verts][3], indices [n_indices] (the reference's internal winding; its PLY writer
- * reverses it); any of the four may be NULL. */
+ * reverses it); any of the four may be NULL.  A mesh of an object is read and destroyed before its object is destroyed. */
 typedef struct mon_mesh mon_mesh;
 int mon_object_extract_mesh(mon_object* obj, uint32_t res, float thresh, mon_mesh** out);
 /* the same surface extraction on a caller's lattice (host memory, [z][y][x], box bmin..bmax); colours are zero */

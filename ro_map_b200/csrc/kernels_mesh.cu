@@ -7,9 +7,9 @@
 //
 // The reference hands out vertex and triangle slots with atomicAdd (its output order is a race).  Here both are EXCLUSIVE SCANS over the
 // lattice — count, scan, write — so the order is the lattice order (x fastest, per point the +x, +y, +z edge; per cell the table's
-// own triangle order): reproducible, and identical to the host implementation this replaces (ro_map_b200/host/mesh.h, kept as the
-// CPU statement of the same algorithm and held against the reference's output in tests/test_golden_romap.py), vertex for vertex
-// and index for index.  Only the normals depend on an order (float atomics, as in the reference).
+// own triangle order): reproducible, and identical to the CPU statement of the same algorithm (tests/host/mesh_cpu.h, the host
+// implementation these kernels replaced, held against the reference's output in tests/test_golden_romap.py), vertex for vertex
+// and index for index (tests/test_gpu_mesh.py).  Only the normals depend on an order (float atomics, as in the reference).
 #include "mon_kernels.h"
 #include "../host/mc_table.h"
 
@@ -232,8 +232,9 @@ size_t mon_mesh_scan_scratch_words(uint32_t res) {
 // words, sums: [2] device words = number of surface vertices, number of indices.
 cudaError_t mon_launch_mc_count(const float* sigma, uint32_t res, float thresh, uint32_t* v_off, uint32_t* i_off, uint32_t* totals, uint32_t* sums,
                                 cudaStream_t st) {
-    static std::atomic<uint64_t> prepared{0};
-    const cudaError_t prep = mon_once_per_device(prepared, [] { return cudaMemcpyToSymbol(c_tri, mesh::mc::TRIANGLES, sizeof(c_tri)); });
+    // the 4 KB table goes up with every extraction, on the caller's stream: a one-time synchronous cudaMemcpyToSymbol would go through
+    // the legacy default stream (concurrent calls write the same bytes)
+    const cudaError_t prep = cudaMemcpyToSymbolAsync(c_tri, mesh::mc::TRIANGLES, sizeof(c_tri), 0, cudaMemcpyHostToDevice, st);
     if (prep != cudaSuccess) return prep;
     const size_t n = (size_t)res * res * res;
     const Lattice L = {sigma, res, thresh};

@@ -115,12 +115,14 @@ static cudaError_t mon_dev_malloc(void** p, size_t bytes, cudaStream_t st) {
 static void mon_dev_free(void* p, cudaStream_t st) { if (p) cudaFreeAsync(p, st); }
 // Growing the pool (physical allocation + mapping) is the slow part of an allocation and holds the driver: reserve room for the
 // first objects when a dataset is created, so that objects created while the frontend streams keyframes allocate from memory the
-// pool already owns (MON_POOL_RESERVE_MB, default 512: about 8 objects of base.json).
+// pool already owns (MON_POOL_RESERVE_MB, default 2048: about 20 objects of base.json at ~80 MB each with their render / mesh scratch
+// and the keyframe slabs; 512 was outgrown by four objects + 30 keyframes once the objects carried two batch sets and both graph
+// variants — the frontend's keyframe ingest then stalled 20-100 ms behind a pool growth, profiles/r9_facade_runs.txt).
 static void mon_pool_reserve(cudaStream_t st) {
     static std::atomic<uint64_t> reserved{0};
     mon_once_per_device(reserved, [st] {
         const char* env = getenv("MON_POOL_RESERVE_MB");
-        const size_t mb = env ? (size_t)atol(env) : 512;
+        const size_t mb = env ? (size_t)atol(env) : 2048;
         void* p = nullptr;
         if (mb && mon_dev_malloc(&p, mb << 20, st) == cudaSuccess) { mon_dev_free(p, st); cudaStreamSynchronize(st); }
         cudaGetLastError();     // a failed reservation is not an error: allocations then grow the pool as they come
@@ -1815,6 +1817,8 @@ int mon_object_density_grid(mon_object* o, const uint32_t res[3], float* out) {
 // the vertices.  The result stays on the device until mon_mesh_read.
 struct mon_mesh {
     int gpu = 0;
+    cudaStream_t st = nullptr;     // the stream the mesh was built on: its object's, or one of its own (own_stream)
+    bool own_stream = false;
     uint32_t n_verts = 0, n_surface = 0, n_indices = 0;
     float *verts = nullptr, *normals = nullptr;
     uint8_t* colors = nullptr;
@@ -1824,10 +1828,10 @@ struct mon_mesh {
 int mon_mesh_destroy(mon_mesh* m) {
     if (!m) return MON_OK;
     cudaSetDevice(m->gpu);
-    // pool memory, complete when the mesh was handed out: released stream-ordered on the thread's own stream (a plain cudaFree is
-    // a device-wide synchronisation and would stall every training stream of the GPU)
-    mon_dev_free(m->verts, cudaStreamPerThread); mon_dev_free(m->normals, cudaStreamPerThread);
-    mon_dev_free(m->colors, cudaStreamPerThread); mon_dev_free(m->indices, cudaStreamPerThread);
+    // pool memory, released stream-ordered (a plain cudaFree is a device-wide synchronisation and would stall every training
+    // stream of the GPU and the frontend's keyframe upload behind them)
+    mon_dev_free(m->verts, m->st); mon_dev_free(m->normals, m->st); mon_dev_free(m->colors, m->st); mon_dev_free(m->indices, m->st);
+    if (m->own_stream) { cudaStreamSynchronize(m->st); cudaStreamDestroy(m->st); }
     delete m;
     return MON_OK;
 }
@@ -1838,6 +1842,7 @@ static int mesh_from_device_lattice(int gpu, const float* d_sigma, uint32_t res,
     const size_t n = (size_t)res * res * res;
     mon_mesh* m = new mon_mesh();
     m->gpu = gpu;
+    m->st = st;
     uint32_t *v_off = nullptr, *i_off = nullptr, *totals = nullptr, *sums = nullptr, *vid = nullptr;
     auto cleanup = [&](bool all) {
         mon_dev_free(v_off, st); mon_dev_free(i_off, st); mon_dev_free(totals, st); mon_dev_free(sums, st); mon_dev_free(vid, st);
@@ -1894,8 +1899,8 @@ int mon_mesh_from_lattice(int gpu, const float* sigma, uint32_t res, const float
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_sigma, sigma, n * 4, cudaMemcpyHostToDevice, st);
     int rc = e == cudaSuccess ? mesh_from_device_lattice(gpu, d_sigma, res, bmin, bmax, thresh, st, out) : fail(MON_ERR_CUDA, "lattice upload: %s", cudaGetErrorString(e));
     mon_dev_free(d_sigma, st);
-    cudaStreamSynchronize(st);
-    cudaStreamDestroy(st);
+    if (rc == MON_OK) (*out)->own_stream = true;      // destroyed with the mesh
+    else { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
     return rc;
 }
 
@@ -1953,10 +1958,12 @@ int mon_mesh_counts(const mon_mesh* m, uint32_t* n_verts, uint32_t* n_surface_ve
 int mon_mesh_read(const mon_mesh* m, float* verts, float* normals, uint8_t* colors, uint32_t* indices) {
     if (!m) return fail(MON_ERR_ARG, "mesh is NULL");
     CK(cudaSetDevice(m->gpu));
-    if (verts && m->n_verts) CK(cudaMemcpy(verts, m->verts, (size_t)m->n_verts * 12, cudaMemcpyDeviceToHost));
-    if (normals && m->n_verts) CK(cudaMemcpy(normals, m->normals, (size_t)m->n_verts * 12, cudaMemcpyDeviceToHost));
-    if (colors && m->n_verts) CK(cudaMemcpy(colors, m->colors, (size_t)m->n_verts * 3, cudaMemcpyDeviceToHost));
-    if (indices && m->n_indices) CK(cudaMemcpy(indices, m->indices, (size_t)m->n_indices * 4, cudaMemcpyDeviceToHost));
+    // on the mesh's own (non-blocking) stream: the synchronous cudaMemcpy goes through the legacy default stream
+    if (verts && m->n_verts) CK(cudaMemcpyAsync(verts, m->verts, (size_t)m->n_verts * 12, cudaMemcpyDeviceToHost, m->st));
+    if (normals && m->n_verts) CK(cudaMemcpyAsync(normals, m->normals, (size_t)m->n_verts * 12, cudaMemcpyDeviceToHost, m->st));
+    if (colors && m->n_verts) CK(cudaMemcpyAsync(colors, m->colors, (size_t)m->n_verts * 3, cudaMemcpyDeviceToHost, m->st));
+    if (indices && m->n_indices) CK(cudaMemcpyAsync(indices, m->indices, (size_t)m->n_indices * 4, cudaMemcpyDeviceToHost, m->st));
+    CK(cudaStreamSynchronize(m->st));
     return MON_OK;
 }
 

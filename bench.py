@@ -359,8 +359,8 @@ def run_ours(args, rank, world, local_rank):
     # keyframes in PINNED host memory (the C ABI then DMAs straight out of them, asynchronously): one block per plane kind
     h_rgb = torch.from_numpy(np.ascontiguousarray(np.stack(seq.rgb))).pin_memory()
     h_inst = torch.from_numpy(np.ascontiguousarray(np.stack(seq.instance))).pin_memory()
-    # depth: the 16-bit samples of the depth image (int16 view of the same bits: torch / NCCL have no uint16 collectives)
-    h_dep = torch.from_numpy(np.ascontiguousarray(np.stack(seq.depth16)).view(np.int16)).pin_memory()
+    # depth: the 16-bit samples of the depth image, as a byte block [n, H, 2 W] (NCCL's process group has no 16-bit integer collectives)
+    h_dep = torch.from_numpy(np.ascontiguousarray(np.stack(seq.depth16)).view(np.uint8)).pin_memory()
     rgb_np, inst_np, dep_np = h_rgb.numpy(), h_inst.numpy(), h_dep.numpy().view(np.uint16)
 
     def new_dataset():

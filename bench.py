@@ -491,14 +491,17 @@ def run_ours(args, rank, world, local_rank):
     n_mlp = 3072 if args.hidden_layers == 1 else 3072 + 4096
     P_grid = 1908736
     stage_roof = {}
+    # 5 kernels per iteration = the timed calls took the steady-state graphs (no scatter kernel; what the profiled twin's events
+    # bracket there is an empty stage, a few microseconds of event overhead)
+    fused_window = launches / max(1, K * n_objects) < 5.5
     for name, ms_k in stages.items():
         s_k = max(ms_k, 1e-9) * 1e-3
         if name == "encode":
             ach, alg = enc_bytes / s_k / 1e9, enc_bytes
             stage_roof[name] = {"ms": ms_k, "bound": "hbm", "achieved": ach, "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "algorithmic": alg}
-        elif name == "scatter" and ms_k < 1e-6:
+        elif name == "scatter" and fused_window:
             # steady-state graph variant: no scatter kernel, the fused MLP kernel issues the reductions (its time is in mlp_fused)
-            stage_roof[name] = {"ms": 0.0, "note": "no scatter kernel in this window: the hash-grid reductions are issued by the fused MLP kernel (steady-state graph variant)"}
+            stage_roof[name] = {"ms": ms_k, "note": "no scatter kernel in this window: the hash-grid reductions are issued by the fused MLP kernel (steady-state graph variant); the time is the event pair's own"}
         elif name == "scatter":
             # 512 B of gradient read-modify-write per point of the launch (all N points; only the live ones are scattered: every one of
             # them for a fresh object — shared-memory resident path of k_scatter —, ~1 in 12 in steady state — global reductions)
@@ -516,7 +519,7 @@ def run_ours(args, rank, world, local_rank):
             stage_roof[name] = {"ms": ms_k}
     roofline = None
     if stages:
-        dominant = max(("encode", "scatter", "mlp_fused", "optimizer"), key=lambda k: stages[k])
+        dominant = max(("encode", "mlp_fused", "optimizer") + (() if fused_window else ("scatter",)), key=lambda k: stages[k])
         d = stage_roof[dominant]
         roofline = {"kernel": {"encode": "k_encode_forward", "scatter": "k_scatter", "mlp_fused": "k_mlp_train_tc", "optimizer": "k_optimizer_sweep"}[dominant], "stage": dominant,
                     "bound": d["bound"], "achieved": d["achieved"], "unit": d["unit"],

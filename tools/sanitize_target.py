@@ -19,9 +19,18 @@ import os
 blk = core.Dataset(0, *seq.K, seq.H, seq.W, len(seq.poses), True)
 blk.add_frames(0, np.ascontiguousarray(np.stack(seq.rgb)), np.ascontiguousarray(np.stack(seq.instance)), np.ascontiguousarray(np.stack(seq.depth)), seq.poses)
 blk.sync()
-for nh, R, resident_min, occ in ((1, 256, "0", 0), (2, 128, "-1", 0), (1, 256, "0", 16)):
+# raw 16-bit depth planes (converted by the batch kernel)
+d16 = core.Dataset(0, *seq.K, seq.H, seq.W, len(seq.poses), True)
+d16.set_depth_u16(1.0 / 5000.0)
+d16.add_frames(0, np.ascontiguousarray(np.stack(seq.rgb)), np.ascontiguousarray(np.stack(seq.instance)),
+               np.ascontiguousarray(np.stack([np.clip(np.rint(d * 5000.0), 0, 65535).astype(np.uint16) for d in seq.depth])), seq.poses)
+d16.sync()
+# (hidden layers, rays, MON_SCATTER_RESIDENT_MIN, occupancy grid, MON_SCATTER_FUSED): the last two rows run the graph variant
+# without a scatter kernel (fused MLP kernel scatters; slim batch cluster beside the hash encode; two batch sets)
+for nh, R, resident_min, occ, fused in ((1, 256, "0", 0, "-1"), (2, 128, "-1", 0, "-1"), (1, 256, "0", 16, "-1"), (1, 256, "-1", 0, "1"), (2, 128, "-1", 0, "1")):
     os.environ["MON_SCATTER_RESIDENT_MIN"] = resident_min
-    g = core.NerfObject(blk if occ else ds, core.default_config(rays_per_batch=R, n_hidden_layers=nh), obj.Tow, -1.1 * obj.half, 1.1 * obj.half, obj.instance_id)
+    os.environ["MON_SCATTER_FUSED"] = fused
+    g = core.NerfObject(blk if occ else (d16 if fused == "1" else ds), core.default_config(rays_per_batch=R, n_hidden_layers=nh), obj.Tow, -1.1 * obj.half, 1.1 * obj.half, obj.instance_id)
     g.set_bboxes(obj.boxes)
     if occ:
         g.set_occupancy(occ, warmup_iters=4, update_interval=2, alpha_threshold=0.01)
@@ -32,9 +41,16 @@ for nh, R, resident_min, occ in ((1, 256, "0", 0), (2, 128, "-1", 0), (1, 256, "
     fid, x, y, h, w = [int(v) for v in obj.boxes[0]]
     rgb, dep, mask = g.render((fid, x, y, min(h, 16), min(w, 16)), seq.poses[fid])
     print("render", float(mask.mean()), "lattice", float(g.density_grid((8, 8, 8)).mean()))
+    sig = g.density_grid((12, 12, 12))
+    m = g.extract_mesh(12, float(np.median(sig)))
+    print("mesh", m["n_surface"], len(m["indices"]) // 3)
     if occ:
         print("occupancy", g.occupancy_stats())
     g.close()
+rng = np.random.default_rng(3)
+m = core.mesh_from_lattice(rng.uniform(0, 4, (11, 11, 11)).astype(np.float32), [-1, -1, -1], [1, 1, 1], 2.0)
+print("lattice mesh", m["n_surface"], len(m["indices"]) // 3)
 ds.close()
 blk.close()
+d16.close()
 print("sanitize target done")
